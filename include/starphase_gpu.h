@@ -1,0 +1,164 @@
+/*
+ * starphase_gpu.h -- C ABI of libstarphase_gpu.so (B200 / sm_100a scoring path).
+ *
+ * This is the drop-in boundary for pb-StarPhase's data-parallel hot path.  The
+ * reference (Rust, single process, no FFI of its own) reaches all of its
+ * alignment arithmetic through `minimap2::Aligner::map` (call sites listed
+ * below); a thin `extern "C"` crate (rust/starphase-gpu-sys)
+ * binds exactly the entry points declared here.  Plain pointers and sizes only;
+ * every buffer is caller-owned and borrowed for the duration of one call;
+ * calls are blocking and not re-entrant per context (the reference host is
+ * single-threaded, src/cli/diplotype.rs:185-191).
+ *
+ * Distance definition:
+ *     D(P, T) = min over placements of pattern P inside text T of
+ *               (edits + unaligned P bases)            [unit costs]
+ * = the reference's `nm + unmapped` for a unit-cost-optimal minimap2 mapping:
+ *   - HLA allele vs consensus/read, query side penalised
+ *       src/hla/caller.rs:1433-1462, src/util/mapping.rs:22-57   (P = allele)
+ *   - HLA read vs allele index, allele side penalised
+ *       src/hla/realigner.rs:116-146                             (P = allele)
+ *   - CYP2D6 read segment vs consensus, segment fully explained
+ *       src/cyp2d6/chaining.rs:48-94                             (P = segment)
+ *   - CYP2D6 read vs 39 D6/D7/hybrid templates
+ *       src/cyp2d6/haplotyper.rs:193-249                         (P = template)
+ * Non-ACGT bytes (N, *) match nothing.  Empty pattern => 0; empty text => |P|.
+ *
+ * There is NO CPU fallback: every entry point fails with SP_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef STARPHASE_GPU_H
+#define STARPHASE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sp_status {
+    SP_OK = 0,
+    SP_ERR_INVALID = 1,     /* bad argument (null pointer, bad offsets, k out of range ...)          */
+    SP_ERR_CUDA = 2,        /* CUDA runtime failure or no usable device; see sp_last_error            */
+    SP_ERR_TOO_LONG = 3,    /* a pattern exceeds SP_MAX_PATTERN_LEN or a text exceeds the tile budget  */
+    SP_ERR_NOMEM = 4,       /* host or device allocation failed                                       */
+    SP_ERR_RANGE = 5        /* value does not fit the device format (e.g. > 65535 alleles for top-k)  */
+} sp_status;
+
+/* Longest pattern one warp can hold: 32 lanes x 16 words x 32 rows. */
+#define SP_MAX_PATTERN_LEN 16384
+
+/* Concatenated ASCII sequences: sequence i = bases[offsets[i] .. offsets[i+1]).
+ * Mirrors how the reference hands `&[u8]` sequences to Aligner::with_seq / map. */
+typedef struct sp_seqset {
+    const uint8_t *bases;
+    const int64_t *offsets; /* n + 1 entries, offsets[0] may be > 0, non-decreasing */
+    int64_t n;
+} sp_seqset;
+
+/* Text boundary mode.  SP_INFIX: both text ends free (every reference call site).
+ * SP_PREFIX: the placement must start at text position 0 (used on reversed
+ * sequences to recover the start of the aligned span). */
+typedef enum sp_mode { SP_INFIX = 0, SP_PREFIX = 1 } sp_mode;
+
+typedef struct sp_ctx sp_ctx;           /* one per process per GPU; owns stream, events, scratch */
+typedef struct sp_patterns sp_patterns; /* device-resident packed pattern set (alleles / segments) */
+typedef struct sp_targets sp_targets;   /* device-resident packed text set (reads / consensuses)   */
+typedef struct sp_dmatrix sp_dmatrix;   /* device-resident distance matrix, u16 or i32             */
+
+/* One ranked pair: allele-pair for HLA (north_star K2), chain-pair for CYP2D6
+ * (src/cyp2d6/chaining.rs:409-534).  Ordering key is (score, i, j) ascending,
+ * i <= j -- the reference's ChainScore::compare_tuple (chaining.rs:188-197).
+ * c1 = #{reads r : D[r,i] <= D[r,j]} so the host can apply is_passing_dual
+ * (src/hla/caller.rs:1225-1247) unchanged. */
+typedef struct sp_pair_rec {
+    uint64_t score;
+    uint32_t i, j;
+    uint32_t c1;
+    uint32_t _pad;
+} sp_pair_rec;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to launch on (e.g. the host framework's
+ * current stream), or NULL to create a private non-blocking stream. */
+sp_status sp_ctx_create(int device, void *stream, sp_ctx **out);
+void sp_ctx_destroy(sp_ctx *ctx);
+/* Message for the last failing call on this context ("" if none).  Maps to the
+ * reference's Box<dyn Error> strings.  ctx may be NULL for creation failures. */
+const char *sp_last_error(const sp_ctx *ctx);
+/* Device time in ms of the most recent launch of kernel `which`
+ * (0 = K1 scoring, 1 = K2 pair scoring, 2 = pattern pack, 3 = text pack), measured
+ * with CUDA events on the context stream; < 0 if it has not run.  Synchronises. */
+float sp_last_kernel_ms(sp_ctx *ctx, int which);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t sp_launch_count(const sp_ctx *ctx);
+/* Block until all work queued on the context stream has finished. */
+sp_status sp_ctx_synchronize(sp_ctx *ctx);
+
+/* ---- K1: batched infix edit distance ---------------------------------------------------- */
+/* Upload + 2-bit/Peq-pack a pattern set (the allele database of one gene, or the read
+ * segments of one CYP2D6 sample).  Done once per database, like HlaRealigner::new builds the
+ * allele index once (src/hla/realigner.rs:42-91).  mode selects the pad-row encoding. */
+sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, sp_mode mode, sp_patterns **out);
+void sp_patterns_destroy(sp_patterns *p);
+int64_t sp_patterns_count(const sp_patterns *p);
+/* sum of |P| over the set (for GCUPS accounting) */
+int64_t sp_patterns_total_len(const sp_patterns *p);
+/* rows the packed layout really computes per text column (>= total_len; padding included) */
+int64_t sp_patterns_padded_rows(const sp_patterns *p);
+
+/* Upload + pack a text set (reads / consensus sequences) into tile streams. */
+sp_status sp_targets_create(sp_ctx *ctx, const sp_seqset *targets, sp_targets **out);
+void sp_targets_destroy(sp_targets *t);
+int64_t sp_targets_count(const sp_targets *t);
+int64_t sp_targets_total_len(const sp_targets *t);
+
+/* Score every (target, pattern) pair on the device; result stays in HBM.
+ * elem_bits: 16 (uint16, for K2) or 32 (int32).  Layout: D[p * ld + t] ("allele-major",
+ * reads contiguous) with ld = targets rounded up to a multiple of 64.
+ * want_end_col != 0 also records the smallest end column of a best placement. */
+sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t, const sp_patterns *p,
+                          int elem_bits, int want_end_col, sp_dmatrix **out);
+void sp_dmatrix_destroy(sp_dmatrix *d);
+/* Copy to host as int32 D[t * n_patterns + p] (row = target), optionally end columns. */
+sp_status sp_dmatrix_to_host(sp_ctx *ctx, const sp_dmatrix *d, int32_t *D, int32_t *end_col);
+/* Raw device pointer / geometry for zero-copy consumers (torch, NCCL all-gather). */
+void *sp_dmatrix_device_ptr(const sp_dmatrix *d);
+int64_t sp_dmatrix_ld(const sp_dmatrix *d);
+int sp_dmatrix_elem_bits(const sp_dmatrix *d);
+/* Wrap caller-owned device memory (e.g. an all-gathered matrix) as a dmatrix view. */
+sp_status sp_dmatrix_wrap(sp_ctx *ctx, void *dev_ptr, int64_t n_targets, int64_t n_patterns,
+                          int64_t ld, int elem_bits, sp_dmatrix **out);
+
+/* One-call form with host buffers on both sides (seams S1/S2/S3 of SURVEY.md §8b):
+ * D[t * n_patterns + p], caller-allocated; end_col optional (NULL to skip). */
+sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns,
+                         sp_mode mode, int32_t *D, int32_t *end_col);
+
+/* ---- K2: pair scoring -------------------------------------------------------------------- */
+/* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
+ * writes the k smallest by (S, i, j) into out (k <= 64), returns the count in *n_out.
+ * Restricting i to a row range is how allele-pair blocks are sharded across GPUs; merging the
+ * per-shard lists by the same key reproduces the single-GPU answer exactly. */
+sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64_t i_begin, int64_t i_end,
+                              int k, sp_pair_rec *out, int *n_out);
+/* Full upper-triangular matrix S[i * n + j] (j >= i; other entries 0) to host memory.  Used by the
+ * CYP2D6 chain-pair path where float penalties are added on the host (chaining.rs:459-497). */
+sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint64_t *S);
+/* Host-buffer convenience: D is [R][A] row-major int32 (R reads, A alleles / chains). */
+sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, int k,
+                                   sp_pair_rec *out, int *n_out);
+sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+/* Integer-ALU microbenchmark used for the roofline denominator: runs a
+ * dependent-free LOP3/IADD3 (kind 0), IMAD (kind 1) or mixed (kind 2) loop on every SM and
+ * returns achieved 32-bit lane-ops per second. */
+sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s);
+const char *sp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARPHASE_GPU_H */

@@ -1,0 +1,292 @@
+"""ctypes mirror of include/starphase_gpu.h.
+
+This is the binding a Python host would use; the Rust host of the reference binds the same
+symbols through rust/starphase-gpu-sys.  Nothing here computes on the
+CPU: a missing library or a missing GPU raises SpError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+SP_INFIX, SP_PREFIX = 0, 1
+_STATUS = {0: "SP_OK", 1: "SP_ERR_INVALID", 2: "SP_ERR_CUDA", 3: "SP_ERR_TOO_LONG", 4: "SP_ERR_NOMEM", 5: "SP_ERR_RANGE"}
+
+
+class SpError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{_STATUS.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+
+
+class SeqSet(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("offsets", C.c_void_p), ("n", C.c_int64)]
+
+
+class PairRec(C.Structure):
+    _fields_ = [("score", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / "libstarphase_gpu.so"
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/starphase_gpu.h declares
+_P = C.c_void_p
+SIGNATURES = {
+    "sp_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "sp_ctx_destroy": (None, [_P]),
+    "sp_last_error": (C.c_char_p, [_P]),
+    "sp_last_kernel_ms": (C.c_float, [_P, C.c_int]),
+    "sp_launch_count": (C.c_uint64, [_P]),
+    "sp_ctx_synchronize": (C.c_int, [_P]),
+    "sp_patterns_create": (C.c_int, [_P, C.POINTER(SeqSet), C.c_int, C.POINTER(_P)]),
+    "sp_patterns_destroy": (None, [_P]),
+    "sp_patterns_count": (C.c_int64, [_P]),
+    "sp_patterns_total_len": (C.c_int64, [_P]),
+    "sp_patterns_padded_rows": (C.c_int64, [_P]),
+    "sp_targets_create": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(_P)]),
+    "sp_targets_destroy": (None, [_P]),
+    "sp_targets_count": (C.c_int64, [_P]),
+    "sp_targets_total_len": (C.c_int64, [_P]),
+    "sp_score_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "sp_dmatrix_destroy": (None, [_P]),
+    "sp_dmatrix_to_host": (C.c_int, [_P, _P, _P, _P]),
+    "sp_dmatrix_device_ptr": (_P, [_P]),
+    "sp_dmatrix_ld": (C.c_int64, [_P]),
+    "sp_dmatrix_elem_bits": (C.c_int, [_P]),
+    "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
+    "sp_pair_minsum_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
+    "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
+    "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
+    "sp_pair_minsum_full_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    "sp_int_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "sp_version": (C.c_char_p, []),
+}
+
+
+def load_library():
+    """Loads libstarphase_gpu.so (built in-tree by pb_starphase_b200.build).  Fails loudly if it
+    is missing: there is no eager / CPU path to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        raise SpError(2, f"{path} is missing -- run `python -m pb_starphase_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def pack_sequences(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """list of bytes -> (uint8 bases, int64 offsets[n+1]) in the sp_seqset layout."""
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+    joined = b"".join(bytes(s) for s in seqs)
+    bases = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, dtype=np.uint8)
+    return bases, offs
+
+
+def _seqset(bases: np.ndarray, offs: np.ndarray) -> SeqSet:
+    assert bases.dtype == np.uint8 and offs.dtype == np.int64 and bases.flags.c_contiguous and offs.flags.c_contiguous
+    return SeqSet(bases.ctypes.data, offs.ctypes.data, len(offs) - 1)
+
+
+class Context:
+    """sp_ctx: one per process per GPU."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = load_library()
+        h = _P()
+        st = self._lib.sp_ctx_create(device, _P(stream) if stream else None, C.byref(h))
+        if st != 0:
+            raise SpError(st, self._lib.sp_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def _check(self, st: int):
+        if st != 0:
+            raise SpError(st, self._lib.sp_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- K1 ---------------------------------------------------------------------------------
+    def patterns(self, seqs, mode: int = SP_INFIX) -> "PatternSet":
+        return PatternSet(self, seqs, mode)
+
+    def targets(self, seqs) -> "TargetSet":
+        return TargetSet(self, seqs)
+
+    def score_device(self, targets: "TargetSet", patterns: "PatternSet", elem_bits: int = 16,
+                     want_end_col: bool = False) -> "DMatrix":
+        h = _P()
+        self._check(self._lib.sp_score_device(self._h, targets._h, patterns._h, elem_bits, int(want_end_col), C.byref(h)))
+        return DMatrix(self, h, targets.n, patterns.n, want_end_col)
+
+    def score_batch(self, targets, patterns, mode: int = SP_INFIX, want_end_col: bool = False):
+        """Host buffers in, host int32 matrix out: D[t, p] (and end columns).  One C-ABI call."""
+        tb, to = targets if isinstance(targets, tuple) else pack_sequences(targets)
+        pb, po = patterns if isinstance(patterns, tuple) else pack_sequences(patterns)
+        nt, np_ = len(to) - 1, len(po) - 1
+        D = np.empty((nt, np_), dtype=np.int32)
+        E = np.empty((nt, np_), dtype=np.int32) if want_end_col else None
+        ts, ps = _seqset(tb, to), _seqset(pb, po)
+        self._check(self._lib.sp_score_batch(self._h, C.byref(ts), C.byref(ps), mode, D.ctypes.data,
+                                             E.ctypes.data if E is not None else None))
+        return (D, E) if want_end_col else D
+
+    # -- K2 ---------------------------------------------------------------------------------
+    def pair_minsum_topk(self, d, k: int = 10, i_begin: int = 0, i_end: Optional[int] = None):
+        """d: DMatrix (device) or host int32 array [R, A].  Returns list of (score, i, j, c1)."""
+        recs = (PairRec * k)()
+        n = C.c_int(0)
+        if isinstance(d, DMatrix):
+            self._check(self._lib.sp_pair_minsum_topk(self._h, d._h, i_begin, d.n_patterns if i_end is None else i_end, k, recs, C.byref(n)))
+        else:
+            a = np.ascontiguousarray(d, dtype=np.int32)
+            self._check(self._lib.sp_pair_minsum_topk_host(self._h, a.ctypes.data, a.shape[0], a.shape[1], k, recs, C.byref(n)))
+        return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
+
+    def pair_minsum_full(self, d) -> np.ndarray:
+        if isinstance(d, DMatrix):
+            A = d.n_patterns
+            S = np.zeros((A, A), dtype=np.uint64)
+            self._check(self._lib.sp_pair_minsum_full(self._h, d._h, S.ctypes.data))
+        else:
+            a = np.ascontiguousarray(d, dtype=np.int32)
+            S = np.zeros((a.shape[1], a.shape[1]), dtype=np.uint64)
+            self._check(self._lib.sp_pair_minsum_full_host(self._h, a.ctypes.data, a.shape[0], a.shape[1], S.ctypes.data))
+        return S
+
+    # -- misc -------------------------------------------------------------------------------
+    def last_kernel_ms(self, which: int) -> float:
+        return float(self._lib.sp_last_kernel_ms(self._h, which))
+
+    def launch_count(self) -> int:
+        return int(self._lib.sp_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.sp_ctx_synchronize(self._h))
+
+    def int_peak(self, kind: int = 0) -> float:
+        v = C.c_double(0)
+        self._check(self._lib.sp_int_peak(self._h, kind, C.byref(v)))
+        return v.value
+
+    def wrap_dmatrix(self, dev_ptr: int, n_targets: int, n_patterns: int, ld: int, elem_bits: int) -> "DMatrix":
+        h = _P()
+        self._check(self._lib.sp_dmatrix_wrap(self._h, _P(dev_ptr), n_targets, n_patterns, ld, elem_bits, C.byref(h)))
+        return DMatrix(self, h, n_targets, n_patterns, False)
+
+
+class PatternSet:
+    def __init__(self, ctx: Context, seqs, mode: int = SP_INFIX):
+        self.ctx = ctx
+        bases, offs = seqs if isinstance(seqs, tuple) else pack_sequences(seqs)
+        ss = _seqset(bases, offs)
+        h = _P()
+        ctx._check(ctx._lib.sp_patterns_create(ctx._h, C.byref(ss), mode, C.byref(h)))
+        self._h = h
+        self.n = len(offs) - 1
+        self.total_len = int(ctx._lib.sp_patterns_total_len(h))
+        self.padded_rows = int(ctx._lib.sp_patterns_padded_rows(h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sp_patterns_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TargetSet:
+    def __init__(self, ctx: Context, seqs):
+        self.ctx = ctx
+        bases, offs = seqs if isinstance(seqs, tuple) else pack_sequences(seqs)
+        ss = _seqset(bases, offs)
+        h = _P()
+        ctx._check(ctx._lib.sp_targets_create(ctx._h, C.byref(ss), C.byref(h)))
+        self._h = h
+        self.n = len(offs) - 1
+        self.total_len = int(ctx._lib.sp_targets_total_len(h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sp_targets_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DMatrix:
+    """Device-resident distance matrix, allele-major: D[p * ld + t]."""
+
+    def __init__(self, ctx: Context, h, n_targets: int, n_patterns: int, has_end: bool):
+        self.ctx, self._h = ctx, h
+        self.n_targets, self.n_patterns, self.has_end = n_targets, n_patterns, has_end
+
+    @property
+    def device_ptr(self) -> int:
+        return int(self.ctx._lib.sp_dmatrix_device_ptr(self._h) or 0)
+
+    @property
+    def ld(self) -> int:
+        return int(self.ctx._lib.sp_dmatrix_ld(self._h))
+
+    @property
+    def elem_bits(self) -> int:
+        return int(self.ctx._lib.sp_dmatrix_elem_bits(self._h))
+
+    def to_host(self, want_end_col: bool = False):
+        D = np.zeros((self.n_targets, self.n_patterns), dtype=np.int32)
+        E = np.zeros((self.n_targets, self.n_patterns), dtype=np.int32) if want_end_col else None
+        self.ctx._check(self.ctx._lib.sp_dmatrix_to_host(self.ctx._h, self._h, D.ctypes.data,
+                                                         E.ctypes.data if E is not None else None))
+        return (D, E) if want_end_col else D
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sp_dmatrix_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

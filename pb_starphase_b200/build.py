@@ -1,0 +1,50 @@
+"""Builds libstarphase_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libstarphase_gpu.so"
+SOURCES = ["starphase_gpu.cu", "sp_kernels.cuh", "sp_addchain.inc", "../../include/starphase_gpu.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+    "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libstarphase_gpu.so")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any((CSRC / s).resolve().stat().st_mtime > t for s in SOURCES)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    subprocess.check_call([sys.executable, str(CSRC / "gen_addchain.py")], cwd=CSRC)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "starphase_gpu.cu")]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

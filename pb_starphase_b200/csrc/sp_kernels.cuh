@@ -1,0 +1,542 @@
+// sp_kernels.cuh -- device code of libstarphase_gpu.so (sm_100a only).
+//
+// K1  k1_infix      batched infix edit distance, pattern-stationary systolic warps
+//                   (replaces the per-allele minimap2 calls of src/hla/caller.rs:1413-1500,
+//                    src/hla/realigner.rs:116-146, src/cyp2d6/chaining.rs:48-94,
+//                    src/cyp2d6/haplotyper.rs:193-249 of the reference)
+// K2  k2_pair_minsum  S[i,j] = sum_r min(D[r,i], D[r,j]) + per-CTA top-k by (S,i,j)
+//                   (north_star pair scoring; CYP2D6 form of src/cyp2d6/chaining.rs:409-534)
+// plus the pack kernels that turn ASCII sequences into the device formats.
+//
+// See DESIGN.md §4 for the layouts and the op-count model.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sp {
+
+// ------------------------------------------------------------------------------------------
+// Geometry shared by host and device
+// ------------------------------------------------------------------------------------------
+constexpr int K1_WARPS = 8;                 // warps (= pattern bins) per CTA
+constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int K1_CHUNK = 8;                 // text columns per chunk (one uint2 of byte codes)
+constexpr int PEQ_ROWS = 6;                 // A,C,G,T, N(other), pv-init
+__host__ __device__ constexpr int blob_words(int U) { return PEQ_ROWS * 32 * U + 64; }
+__host__ __device__ constexpr int vec_width(int U) { return (U % 4 == 0) ? 4 : 2; }
+// info1 bit layout
+constexpr uint32_t INFO_FIRST = 1u << 30;
+constexpr uint32_t INFO_LAST = 1u << 31;
+constexpr uint32_t INFO_LEN_MASK = (1u << 30) - 1;
+constexpr uint32_t NO_PATTERN = 0xFFFFFFFFu;
+
+struct K1Params {
+    const uint32_t *blobs;          // [n_groups][K1_WARPS][blob_words(U)]
+    const uint2 *text;              // chunk stream of all tiles
+    const int32_t *tile_chunk_off;  // [n_tiles + 1], even
+    const int32_t *tile_text0;      // [n_tiles] first text index of the tile
+    void *out;                      // D[p * ld + t], u16 or i32
+    int32_t *out_end;               // end columns (same layout, i32) or nullptr
+    long long ld;
+    int n_groups, n_tiles;
+    int out16;
+    int prefix_mode;                // SP_PREFIX: top row delta +1
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#include "sp_addchain.inc"
+
+// ------------------------------------------------------------------------------------------
+// K1: one text column for one lane (32*U pattern rows as a U-word big integer).
+// Myers 1999 with Hyyro's hin/hout at lane boundaries only; inside the lane the U words are
+// linked by the adder carry (IADD3.X) and funnel shifts (SHF.L.W), 10 ALU ops per word.
+// ------------------------------------------------------------------------------------------
+template <int U>
+__device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)[U]) {
+    constexpr int V = vec_width(U);
+#pragma unroll
+    for (int q = 0; q < U / V; ++q) {
+        if (V == 4) {
+            uint4 x = *reinterpret_cast<const uint4 *>(row_lane + q * 128);
+            v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        } else {
+            uint2 x = *reinterpret_cast<const uint2 *>(row_lane + q * 64);
+            v[2 * q + 0] = x.x; v[2 * q + 1] = x.y;
+        }
+    }
+}
+
+template <int U, bool TRACK_END>
+__device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t code, uint32_t (&pv)[U],
+                                            uint32_t (&mv)[U], uint32_t &X, uint32_t &Y, uint32_t &cph,
+                                            uint32_t &cmh, int &score, int &best, int &col, int &best_col) {
+    uint32_t eq[U], xv[U], t[U], sum[U];
+    load_row<U>(peq_lane + code * (32 * U), eq);
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = eq[u] | mv[u];
+    eq[0] |= (Y >> 31);  // hin < 0
+#pragma unroll
+    for (int u = 0; u < U; ++u) t[u] = eq[u] & pv[u];
+    AddChain<U>::run(sum, t, pv);
+    uint32_t ph[U], mh[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t xh = (sum[u] ^ pv[u]) | eq[u];
+        ph[u] = mv[u] | ~(xh | pv[u]);
+        mh[u] = pv[u] & xh;
+    }
+    // horizontal delta of the lane's last row: carry for the next lane, score for a last lane
+    cph = __funnelshift_l(ph[U - 1], cph, 1);
+    cmh = __funnelshift_l(mh[U - 1], cmh, 1);
+    score += static_cast<int>(ph[U - 1] >> 31) - static_cast<int>(mh[U - 1] >> 31);
+    if (TRACK_END) {
+        ++col;
+        if (score < best) { best = score; best_col = col; }
+    } else {
+        best = min(best, score);
+    }
+#pragma unroll
+    for (int u = U - 1; u >= 1; --u) {
+        uint32_t phs = __funnelshift_l(ph[u - 1], ph[u], 1);
+        uint32_t mhs = __funnelshift_l(mh[u - 1], mh[u], 1);
+        pv[u] = mhs | ~(xv[u] | phs);
+        mv[u] = phs & xv[u];
+    }
+    {
+        uint32_t phs = __funnelshift_l(X, ph[0], 1);
+        uint32_t mhs = __funnelshift_l(Y, mh[0], 1);
+        pv[0] = mhs | ~(xv[0] | phs);
+        mv[0] = phs & xv[0];
+    }
+    X <<= 1;
+    Y <<= 1;
+}
+
+template <int U, bool TRACK_END>
+__device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s_text, int nch, int text0,
+                                            const K1Params &p) {
+    constexpr int V = vec_width(U);
+    const int lane = threadIdx.x & 31;
+    const uint32_t pat = blob[PEQ_ROWS * 32 * U + lane];
+    const uint32_t info1 = blob[PEQ_ROWS * 32 * U + 32 + lane];
+    const bool first = (info1 & INFO_FIRST) != 0;
+    const bool last = (info1 & INFO_LAST) != 0;
+    const int m = static_cast<int>(info1 & INFO_LEN_MASK);
+    const uint32_t *peq_lane = blob + lane * V;
+    const uint32_t cin_first = p.prefix_mode ? 0x00FFu : 0u;
+
+    uint32_t pv[U], mv[U];
+    load_row<U>(peq_lane + 5 * (32 * U), pv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) mv[u] = 0;
+    int score = m, best = m, col = 0, best_col = 0;
+    uint32_t carry_out = 0;
+    int tcount = 0;
+
+    const int nsteps = nch + 31;
+    for (int s = 0; s < nsteps; ++s) {
+        uint32_t cin = __shfl_up_sync(0xffffffffu, carry_out, 1);
+        if (first) cin = cin_first;
+        const int idx = s - lane;
+        if (static_cast<unsigned>(idx) < static_cast<unsigned>(nch)) {
+            const uint2 w = s_text[idx];
+            uint32_t X = cin << 24, Y = cin << 16;
+            uint32_t cph = 0, cmh = 0;
+#pragma unroll
+            for (int c = 0; c < K1_CHUNK; ++c) {
+                const uint32_t word = (c < 4) ? w.x : w.y;
+                const uint32_t code = (word >> (8 * (c & 3))) & (c == 7 ? 0x7Fu : 0xFFu);
+                column_step<U, TRACK_END>(peq_lane, code, pv, mv, X, Y, cph, cmh, score, best, col, best_col);
+            }
+            carry_out = cph | (cmh << 8);
+            if (static_cast<int>(w.y) < 0) {  // last chunk of a text: emit + reset
+                if (last) {
+                    const long long o = static_cast<long long>(pat) * p.ld + (text0 + tcount);
+                    if (p.out16) reinterpret_cast<uint16_t *>(p.out)[o] = static_cast<uint16_t>(best);
+                    else reinterpret_cast<int32_t *>(p.out)[o] = best;
+                    if (TRACK_END) p.out_end[o] = best_col;
+                }
+                ++tcount;
+                load_row<U>(peq_lane + 5 * (32 * U), pv);
+#pragma unroll
+                for (int u = 0; u < U; ++u) mv[u] = 0;
+                score = m; best = m; col = 0; best_col = 0;
+            }
+        }
+    }
+}
+
+#ifndef SP_K1_MIN_BLOCKS
+#define SP_K1_MIN_BLOCKS 2
+#endif
+
+template <int U, bool TRACK_END>
+__global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K1Params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    constexpr int BW = blob_words(U);
+    uint32_t *s_blob = reinterpret_cast<uint32_t *>(smem_raw);
+    uint2 *s_text = reinterpret_cast<uint2 *>(smem_raw + K1_WARPS * BW * 4);
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+
+    uint32_t parity = 0;
+    const int n_items = p.n_groups * p.n_tiles;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int g = item / p.n_tiles;
+        const int tile = item - g * p.n_tiles;
+        const int c0 = p.tile_chunk_off[tile];
+        const int nch = p.tile_chunk_off[tile + 1] - c0;
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            const uint32_t bytes_blob = K1_WARPS * BW * 4;
+            const uint32_t bytes_text = static_cast<uint32_t>(nch) * 8u;
+            mbar_expect_tx(&mbar, bytes_blob + bytes_text);
+            tma_bulk_g2s(s_blob, p.blobs + static_cast<size_t>(g) * K1_WARPS * BW, bytes_blob, &mbar);
+            tma_bulk_g2s(s_text, p.text + c0, bytes_text, &mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        k1_warp_run<U, TRACK_END>(s_blob + warp * BW, s_text, nch, p.tile_text0[tile], p);
+        __syncthreads();  // everyone is done with this item's shared memory
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pack kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t base_code(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+// one thread per (bin, lane, word): builds the six 32-row masks of that word
+__global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long *__restrict__ offs,
+                              const int32_t *__restrict__ lane_pat, const int32_t *__restrict__ lane_row0,
+                              const uint32_t *__restrict__ lane_info1, uint32_t *__restrict__ blobs, int n_bins,
+                              int U, int prefix_mode) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(n_bins) * 32 * U;
+    if (idx >= total) return;
+    const int bin = static_cast<int>(idx / (32 * U));
+    const int rem = static_cast<int>(idx - static_cast<long long>(bin) * 32 * U);
+    const int lane = rem / U, u = rem % U;
+    const int V = vec_width(U);
+    const int BW = blob_words(U);
+    const int pat = lane_pat[bin * 32 + lane];
+    uint32_t mask[PEQ_ROWS] = {0, 0, 0, 0, 0, 0};
+    if (pat >= 0) {
+        const uint8_t *P = bases + offs[pat];
+        const int row0 = lane_row0[bin * 32 + lane] + 32 * u;
+        for (int b = 0; b < 32; ++b) {
+            const int r = row0 + b;
+            const uint32_t bit = 1u << b;
+            if (r < 0) {  // pad row above the pattern: wildcard (infix) / pass-through (prefix)
+                if (!prefix_mode) { mask[0] |= bit; mask[1] |= bit; mask[2] |= bit; mask[3] |= bit; mask[4] |= bit; }
+            } else {
+                const uint32_t c = base_code(P[r]);
+                if (c < 4) mask[c] |= bit;
+                mask[5] |= bit;
+            }
+        }
+    }
+    uint32_t *blob = blobs + static_cast<size_t>(bin) * BW;
+#pragma unroll
+    for (int k = 0; k < PEQ_ROWS; ++k) blob[(k * (U / V) + u / V) * 32 * V + lane * V + (u % V)] = mask[k];
+    if (u == 0) {
+        blob[PEQ_ROWS * 32 * U + lane] = pat >= 0 ? static_cast<uint32_t>(pat) : NO_PATTERN;
+        blob[PEQ_ROWS * 32 * U + 32 + lane] = pat >= 0 ? lane_info1[bin * 32 + lane] : INFO_FIRST;
+    }
+}
+
+// one CTA per text; 8 byte-codes per chunk; bit 7 of the last byte of the last chunk ends the text
+__global__ void pack_texts(const uint8_t *__restrict__ bases, const long long *__restrict__ offs,
+                           const int32_t *__restrict__ text_chunk0, const int32_t *__restrict__ text_nch,
+                           uint2 *__restrict__ out, int n_texts) {
+    for (int t = blockIdx.x; t < n_texts; t += gridDim.x) {
+        const uint8_t *T = bases + offs[t];
+        const long long n = offs[t + 1] - offs[t];
+        const int nc = text_nch[t];
+        uint2 *dst = out + text_chunk0[t];
+        for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+            uint32_t w[2] = {0, 0};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const long long colx = static_cast<long long>(k) * 8 + c;
+                uint32_t code = colx < n ? base_code(T[colx]) : 4u;
+                w[c >> 2] |= code << (8 * (c & 3));
+            }
+            if (k == nc - 1) w[1] |= 0x80000000u;
+            dst[k] = make_uint2(w[0], w[1]);
+        }
+    }
+}
+
+// D[p*ld + t] (u16 / i32) -> host-order int32 rows[t * np + p]
+template <typename T>
+__global__ void dmatrix_to_rows(const T *__restrict__ D, long long ld, int nt, int np, int32_t *__restrict__ rows) {
+    __shared__ int32_t tile[32][33];
+    const int t0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < np && t < nt) ? static_cast<int32_t>(D[static_cast<long long>(p) * ld + t]) : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, p = p0 + threadIdx.x;
+        if (t < nt && p < np) rows[static_cast<long long>(t) * np + p] = tile[threadIdx.x][i];
+    }
+}
+
+// host-order int32 rows[r * A + a] -> D[a*ld + r] int32 (for the *_host K2 entry points)
+__global__ void rows_to_dmatrix(const int32_t *__restrict__ rows, int R, int A, long long ld, int32_t *__restrict__ D) {
+    __shared__ int32_t tile[32][33];
+    const int a0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, a = a0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && a < A) ? rows[static_cast<long long>(r) * A + a] : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int a = a0 + i, r = r0 + threadIdx.x;
+        if (a < A && r < R) D[static_cast<long long>(a) * ld + r] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: pair min-sum.  CTA = 64 x 64 pair tile (i-tile I, j-tile J >= I), 256 threads x (4 x 4).
+// ------------------------------------------------------------------------------------------
+constexpr int K2_TILE = 64;
+constexpr int K2_RC = 64;        // reads per shared-memory stage
+constexpr int K2_THREADS = 256;
+constexpr int K2_MAXK = 64;
+
+struct PairKey {
+    unsigned long long score;
+    unsigned long long ij;  // i << 32 | j
+};
+__device__ __forceinline__ bool key_less(const PairKey &a, const PairKey &b) {
+    return a.score < b.score || (a.score == b.score && a.ij < b.ij);
+}
+
+struct K2Params {
+    const void *D;        // [A][ld], u16 or i32
+    long long ld;
+    int R, A;
+    int i_begin, i_end;   // row range owned by this call
+    int tile_i0;          // first i-tile index (i_begin / 64)
+    int n_tiles_j;        // ceil(A / 64)
+    int k;                // top-k per CTA (0 in full mode)
+    PairKey *cand;        // [n_ctas][k]   (top-k mode)
+    unsigned long long *S; // [A][A]       (full mode)
+};
+
+// linear CTA index -> (I, J) with J >= I over rows I in [tile_i0, tile_i1)
+__device__ __forceinline__ void k2_decode_tile(int bid, int tile_i0, int n_tiles_j, int &I, int &J) {
+    int I_ = tile_i0;
+    int rem = bid;
+    while (rem >= n_tiles_j - I_) { rem -= n_tiles_j - I_; ++I_; }
+    I = I_;
+    J = I_ + rem;
+}
+
+template <typename T, bool FULL>
+__global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
+    __shared__ __align__(16) int32_t sA[K2_RC][K2_TILE + 4];
+    __shared__ __align__(16) int32_t sB[K2_RC][K2_TILE + 4];
+    __shared__ PairKey s_red[K2_THREADS / 32];
+    __shared__ PairKey s_last;
+
+    int I, J;
+    k2_decode_tile(blockIdx.x, p.tile_i0, p.n_tiles_j, I, J);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const T *D = reinterpret_cast<const T *>(p.D);
+
+    unsigned long long acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+
+    for (int r0 = 0; r0 < p.R; r0 += K2_RC) {
+        // stage: D[(I*64 + a) * ld + r0 + r] -> sA[r][a]   (reads contiguous in global memory)
+        for (int e = threadIdx.x; e < K2_TILE * K2_RC; e += K2_THREADS) {
+            const int a = e / K2_RC, r = e % K2_RC;
+            const int ga = I * K2_TILE + a, gb = J * K2_TILE + a, gr = r0 + r;
+            int32_t va = 0, vb = 0;
+            if (gr < p.R) {
+                if (ga < p.A) va = static_cast<int32_t>(D[static_cast<long long>(ga) * p.ld + gr]);
+                if (gb < p.A) vb = static_cast<int32_t>(D[static_cast<long long>(gb) * p.ld + gr]);
+            }
+            sA[r][a] = va;
+            sB[r][a] = vb;
+        }
+        __syncthreads();
+        uint32_t part[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) part[a][b] = 0;
+#pragma unroll 8
+        for (int r = 0; r < K2_RC; ++r) {
+            const int4 va = *reinterpret_cast<const int4 *>(&sA[r][ty * 4]);
+            const int4 vb = *reinterpret_cast<const int4 *>(&sB[r][tx * 4]);
+            const int xa[4] = {va.x, va.y, va.z, va.w};
+            const int xb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) part[a][b] += static_cast<uint32_t>(min(xa[a], xb[b]));
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += part[a][b];
+        __syncthreads();
+    }
+
+    // validity: i <= j, inside the matrix, i inside the owned row range
+    PairKey keys[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int gi = I * K2_TILE + ty * 4 + a, gj = J * K2_TILE + tx * 4 + b;
+            const bool ok = gi < p.A && gj < p.A && gi <= gj && gi >= p.i_begin && gi < p.i_end;
+            if (FULL) {
+                if (ok) p.S[static_cast<long long>(gi) * p.A + gj] = acc[a][b];
+            } else {
+                keys[a * 4 + b].score = ok ? acc[a][b] : ~0ull;
+                keys[a * 4 + b].ij = ok ? ((static_cast<unsigned long long>(gi) << 32) | static_cast<unsigned>(gj)) : ~0ull;
+            }
+        }
+    if (FULL) return;
+
+    // k rounds of block-wide lexicographic argmin over keys strictly greater than the last one taken
+    PairKey lastk;
+    lastk.score = 0; lastk.ij = 0;
+    bool have_last = false;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int round = 0; round < p.k; ++round) {
+        PairKey best;
+        best.score = ~0ull; best.ij = ~0ull;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const bool gt = !have_last || key_less(lastk, keys[q]);
+            if (gt && key_less(keys[q], best)) best = keys[q];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            PairKey o;
+            o.score = __shfl_xor_sync(0xffffffffu, best.score, off);
+            o.ij = __shfl_xor_sync(0xffffffffu, best.ij, off);
+            if (key_less(o, best)) best = o;
+        }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            PairKey b = s_red[0];
+            for (int w = 1; w < K2_THREADS / 32; ++w)
+                if (key_less(s_red[w], b)) b = s_red[w];
+            s_last = b;
+            p.cand[static_cast<long long>(blockIdx.x) * p.k + round] = b;
+        }
+        __syncthreads();
+        lastk = s_last;
+        have_last = true;
+    }
+}
+
+// c1[q] = #{r : D[i_q][r] <= D[j_q][r]} for the final records; one CTA per record
+template <typename T>
+__global__ void k2_count_c1(const T *__restrict__ D, long long ld, int R, const uint32_t *__restrict__ ij,
+                            uint32_t *__restrict__ c1) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t i = ij[2 * blockIdx.x], j = ij[2 * blockIdx.x + 1];
+    uint32_t cnt = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x)
+        cnt += D[static_cast<long long>(i) * ld + r] <= D[static_cast<long long>(j) * ld + r];
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) c1[blockIdx.x] = s_cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// Integer pipe microbenchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters) {
+    uint32_t a[8], b = threadIdx.x * 2654435761u + 1u, c = blockIdx.x + 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x + i * 7919u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (KIND == 0) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if (KIND == 1) {
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if (KIND == 2) {
+                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else {
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                }
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+}  // namespace sp

@@ -1,0 +1,813 @@
+// starphase_gpu.cu -- host side of libstarphase_gpu.so: the C ABI of include/starphase_gpu.h.
+// No torch types, no CPU fallback: every entry point needs a usable sm_100 device.
+#include "../../include/starphase_gpu.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sp_kernels.cuh"
+
+using namespace sp;
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct sp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    int smem_optin = 0;
+    std::string err;
+    cudaEvent_t ev[4][2] = {};
+    bool ev_valid[4] = {false, false, false, false};
+    uint64_t launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+struct sp_patterns {
+    sp_ctx *ctx = nullptr;
+    int64_t n = 0, total_len = 0, padded_rows = 0;
+    sp_mode mode = SP_INFIX;
+    int U = 0;
+    int n_bins = 0, n_groups = 0;
+    uint32_t *d_blobs = nullptr;
+};
+
+struct TextPack {
+    int tc = 0;  // tile capacity in chunks
+    int n_tiles = 0;
+    int64_t total_chunks = 0;
+    uint2 *d_text = nullptr;
+    int32_t *d_tile_off = nullptr;
+    int32_t *d_tile_text0 = nullptr;
+};
+
+struct sp_targets {
+    sp_ctx *ctx = nullptr;
+    int64_t n = 0, total_len = 0;
+    uint8_t *d_bases = nullptr;
+    long long *d_offs = nullptr;
+    std::vector<int32_t> nch;  // chunks per text
+    int32_t max_nch = 0;
+    int64_t sum_nch = 0;
+    std::map<int, TextPack> packs;
+};
+
+struct sp_dmatrix {
+    sp_ctx *ctx = nullptr;
+    void *d = nullptr;
+    int32_t *d_end = nullptr;
+    int64_t nt = 0, np = 0, ld = 0;
+    int elem_bits = 32;
+    bool owned = true;
+};
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static sp_status fail(sp_ctx *ctx, sp_status st, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_err = msg;
+    return st;
+}
+#define SP_CUDA(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, SP_ERR_CUDA,                                                          \
+                        std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" +   \
+                            std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+static void ev_begin(sp_ctx *ctx, int which) { cudaEventRecord(ctx->ev[which][0], ctx->stream); }
+static void ev_end(sp_ctx *ctx, int which) {
+    cudaEventRecord(ctx->ev[which][1], ctx->stream);
+    ctx->ev_valid[which] = true;
+}
+
+extern "C" const char *sp_version(void) { return "starphase_gpu 0.1.0 (sm_100a)"; }
+
+extern "C" const char *sp_last_error(const sp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
+    if (!out) return fail(nullptr, SP_ERR_INVALID, "sp_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SP_ERR_CUDA,
+                    std::string("no CUDA device available (this library has no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SP_ERR_INVALID, "sp_ctx_create: bad device ordinal");
+    SP_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SP_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SP_ERR_CUDA,
+                    "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; libstarphase_gpu is built for sm_100a only");
+    sp_ctx *ctx = new (std::nothrow) sp_ctx();
+    if (!ctx) return fail(nullptr, SP_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return fail(nullptr, SP_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        ctx->own_stream = true;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
+    *out = ctx;
+    return SP_OK;
+}
+
+extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" sp_status sp_ctx_synchronize(sp_ctx *ctx) {
+    if (!ctx) return SP_ERR_INVALID;
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SP_OK;
+}
+
+extern "C" float sp_last_kernel_ms(sp_ctx *ctx, int which) {
+    if (!ctx || which < 0 || which > 3 || !ctx->ev_valid[which]) return -1.0f;
+    if (cudaEventSynchronize(ctx->ev[which][1]) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[which][0], ctx->ev[which][1]) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+extern "C" uint64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// sequence-set validation / upload
+// ------------------------------------------------------------------------------------------
+static sp_status check_seqset(sp_ctx *ctx, const sp_seqset *s, const char *what) {
+    if (!s) return fail(ctx, SP_ERR_INVALID, std::string(what) + ": seqset is NULL");
+    if (s->n < 0) return fail(ctx, SP_ERR_INVALID, std::string(what) + ": negative count");
+    if (s->n > 0 && !s->offsets) return fail(ctx, SP_ERR_INVALID, std::string(what) + ": offsets is NULL");
+    for (int64_t i = 0; i < s->n; ++i)
+        if (s->offsets[i + 1] < s->offsets[i])
+            return fail(ctx, SP_ERR_INVALID, std::string(what) + ": offsets must be non-decreasing");
+    if (s->n > 0 && s->offsets[s->n] > s->offsets[0] && !s->bases)
+        return fail(ctx, SP_ERR_INVALID, std::string(what) + ": bases is NULL");
+    if (s->n > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, std::string(what) + ": too many sequences");
+    return SP_OK;
+}
+
+// copies bases[offsets[0]..offsets[n]) to the device and rebased offsets (offs[0] = 0)
+static sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_bases, long long **d_offs) {
+    const int64_t base0 = s->n ? s->offsets[0] : 0;
+    const int64_t nbytes = s->n ? s->offsets[s->n] - base0 : 0;
+    std::vector<long long> offs(static_cast<size_t>(s->n) + 1);
+    for (int64_t i = 0; i <= s->n; ++i) offs[static_cast<size_t>(i)] = s->n ? s->offsets[i] - base0 : 0;
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(d_bases), static_cast<size_t>(std::max<int64_t>(nbytes, 16))));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(d_offs), offs.size() * sizeof(long long)));
+    if (nbytes)
+        SP_CUDA(ctx, cudaMemcpyAsync(*d_bases, s->bases + base0, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(*d_offs, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a stack-owned vector
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// patterns: choose lane width U, bin-pack patterns into 32-lane warps, build Peq blobs on device
+// ------------------------------------------------------------------------------------------
+static const int kUs[] = {4, 6, 8, 10, 12, 16};
+
+struct BinPlan {
+    int U = 0;
+    int n_bins = 0;
+    std::vector<int32_t> lane_pat, lane_row0;
+    std::vector<uint32_t> lane_info1;
+};
+
+// best-fit decreasing over lane counts; returns false if some pattern needs more than 32 lanes
+static bool plan_bins(const std::vector<int64_t> &lens, int U, BinPlan &plan, bool fill) {
+    const int64_t rows = 32ll * U;
+    const size_t n = lens.size();
+    std::vector<std::pair<int, int32_t>> items;  // (lanes, pattern)
+    items.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (lens[i] == 0) continue;
+        const int64_t nl = (lens[i] + rows - 1) / rows;
+        if (nl > 32) return false;
+        items.emplace_back(static_cast<int>(nl), static_cast<int32_t>(i));
+    }
+    std::stable_sort(items.begin(), items.end(),
+                     [](const std::pair<int, int32_t> &a, const std::pair<int, int32_t> &b) { return a.first > b.first; });
+    std::vector<std::vector<int>> by_rem(33);
+    std::vector<int> bin_used;  // lanes used per bin
+    plan.U = U;
+    if (fill) { plan.lane_pat.clear(); plan.lane_row0.clear(); plan.lane_info1.clear(); }
+    for (const auto &it : items) {
+        const int s = it.first;
+        int bin = -1;
+        for (int rem = s; rem <= 32; ++rem)
+            if (!by_rem[rem].empty()) { bin = by_rem[rem].back(); by_rem[rem].pop_back(); break; }
+        if (bin < 0) {
+            bin = static_cast<int>(bin_used.size());
+            bin_used.push_back(0);
+            if (fill) {
+                plan.lane_pat.resize(plan.lane_pat.size() + 32, -1);
+                plan.lane_row0.resize(plan.lane_row0.size() + 32, 0);
+                plan.lane_info1.resize(plan.lane_info1.size() + 32, INFO_FIRST);
+            }
+        }
+        const int start = bin_used[bin];
+        if (fill) {
+            const int64_t m = lens[static_cast<size_t>(it.second)];
+            const int64_t pad = static_cast<int64_t>(s) * rows - m;
+            for (int li = 0; li < s; ++li) {
+                const size_t o = static_cast<size_t>(bin) * 32 + start + li;
+                plan.lane_pat[o] = it.second;
+                plan.lane_row0[o] = static_cast<int32_t>(li * rows - pad);
+                plan.lane_info1[o] =
+                    static_cast<uint32_t>(m) | (li == 0 ? INFO_FIRST : 0u) | (li == s - 1 ? INFO_LAST : 0u);
+            }
+        }
+        bin_used[bin] += s;
+        by_rem[32 - bin_used[bin]].push_back(bin);
+    }
+    plan.n_bins = static_cast<int>(bin_used.size());
+    return true;
+}
+
+extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, sp_mode mode, sp_patterns **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out) return fail(ctx, SP_ERR_INVALID, "sp_patterns_create: out is NULL");
+    *out = nullptr;
+    sp_status st = check_seqset(ctx, patterns, "patterns");
+    if (st != SP_OK) return st;
+    if (mode != SP_INFIX && mode != SP_PREFIX) return fail(ctx, SP_ERR_INVALID, "bad mode");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    std::vector<int64_t> lens(static_cast<size_t>(patterns->n));
+    int64_t total = 0, maxlen = 0;
+    for (int64_t i = 0; i < patterns->n; ++i) {
+        lens[static_cast<size_t>(i)] = patterns->offsets[i + 1] - patterns->offsets[i];
+        total += lens[static_cast<size_t>(i)];
+        maxlen = std::max(maxlen, lens[static_cast<size_t>(i)]);
+    }
+    if (maxlen > SP_MAX_PATTERN_LEN)
+        return fail(ctx, SP_ERR_TOO_LONG,
+                    "pattern of " + std::to_string(maxlen) + " bases exceeds SP_MAX_PATTERN_LEN (" +
+                        std::to_string(SP_MAX_PATTERN_LEN) + ")");
+
+    // pick the lane width with the lowest modelled cost: bins x (10 ALU ops per word + per-column overhead)
+    int bestU = 0;
+    double best_cost = 0;
+    const char *forceU = getenv("SP_FORCE_U");
+    for (int U : kUs) {
+        if (forceU && atoi(forceU) != U) continue;
+        BinPlan probe;
+        if (!plan_bins(lens, U, probe, false)) continue;
+        const double cost = static_cast<double>(std::max(probe.n_bins, 1)) * (10.0 * U + 12.0);
+        if (!bestU || cost < best_cost) { bestU = U; best_cost = cost; }
+    }
+    if (!bestU) return fail(ctx, SP_ERR_TOO_LONG, "no lane width fits the longest pattern");
+    BinPlan plan;
+    plan_bins(lens, bestU, plan, true);
+    const int U = bestU;
+    const int n_groups = std::max(1, (plan.n_bins + K1_WARPS - 1) / K1_WARPS);
+    const int n_bins_pad = n_groups * K1_WARPS;
+    plan.lane_pat.resize(static_cast<size_t>(n_bins_pad) * 32, -1);
+    plan.lane_row0.resize(static_cast<size_t>(n_bins_pad) * 32, 0);
+    plan.lane_info1.resize(static_cast<size_t>(n_bins_pad) * 32, INFO_FIRST);
+
+    sp_patterns *p = new (std::nothrow) sp_patterns();
+    if (!p) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    p->ctx = ctx; p->n = patterns->n; p->total_len = total; p->mode = mode; p->U = U;
+    p->n_bins = n_bins_pad; p->n_groups = n_groups;
+    p->padded_rows = static_cast<int64_t>(plan.n_bins) * 32 * 32 * U;
+
+    uint8_t *d_bases = nullptr; long long *d_offs = nullptr;
+    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr; uint32_t *d_lane_info1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_bases); cudaFree(d_offs); cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
+    };
+#define SP_TRY(x)                                   \
+    do {                                            \
+        sp_status s__ = (x);                        \
+        if (s__ != SP_OK) { cleanup(); sp_patterns_destroy(p); return s__; } \
+    } while (0)
+    SP_TRY(upload_seqset(ctx, patterns, &d_bases, &d_offs));
+    const size_t tab = static_cast<size_t>(n_bins_pad) * 32;
+    auto cu = [&](cudaError_t e, const char *what) -> sp_status {
+        if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return SP_OK;
+    };
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc lane_pat"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc lane_row0"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc lane_info1"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&p->d_blobs), static_cast<size_t>(n_bins_pad) * blob_words(U) * 4),
+              "cudaMalloc blobs"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, plan.lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, plan.lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, plan.lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    {
+        const long long total_threads = static_cast<long long>(n_bins_pad) * 32 * U;
+        const int blocks = static_cast<int>((total_threads + 255) / 256);
+        ev_begin(ctx, 2);
+        pack_patterns<<<blocks, 256, 0, ctx->stream>>>(d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1,
+                                                       p->d_blobs, n_bins_pad, U, mode == SP_PREFIX ? 1 : 0);
+        ev_end(ctx, 2);
+        ++ctx->launches;
+        SP_TRY(cu(cudaGetLastError(), "pack_patterns launch"));
+    }
+    SP_TRY(cu(cudaStreamSynchronize(ctx->stream), "pack_patterns"));
+#undef SP_TRY
+    cleanup();
+    *out = p;
+    return SP_OK;
+}
+
+extern "C" void sp_patterns_destroy(sp_patterns *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_blobs);
+    delete p;
+}
+extern "C" int64_t sp_patterns_count(const sp_patterns *p) { return p ? p->n : 0; }
+extern "C" int64_t sp_patterns_total_len(const sp_patterns *p) { return p ? p->total_len : 0; }
+extern "C" int64_t sp_patterns_padded_rows(const sp_patterns *p) { return p ? p->padded_rows : 0; }
+
+// ------------------------------------------------------------------------------------------
+// targets
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_targets_create(sp_ctx *ctx, const sp_seqset *targets, sp_targets **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out) return fail(ctx, SP_ERR_INVALID, "sp_targets_create: out is NULL");
+    *out = nullptr;
+    sp_status st = check_seqset(ctx, targets, "targets");
+    if (st != SP_OK) return st;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    sp_targets *t = new (std::nothrow) sp_targets();
+    if (!t) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    t->ctx = ctx; t->n = targets->n;
+    t->nch.resize(static_cast<size_t>(targets->n));
+    for (int64_t i = 0; i < targets->n; ++i) {
+        const int64_t len = targets->offsets[i + 1] - targets->offsets[i];
+        t->total_len += len;
+        const int64_t nc = std::max<int64_t>(1, (len + K1_CHUNK - 1) / K1_CHUNK);
+        if (nc > 0x3FFFFFFF) { delete t; return fail(ctx, SP_ERR_TOO_LONG, "text too long"); }
+        t->nch[static_cast<size_t>(i)] = static_cast<int32_t>(nc);
+        t->max_nch = std::max(t->max_nch, static_cast<int32_t>(nc));
+        t->sum_nch += nc;
+    }
+    st = upload_seqset(ctx, targets, &t->d_bases, &t->d_offs);
+    if (st != SP_OK) { sp_targets_destroy(t); return st; }
+    *out = t;
+    return SP_OK;
+}
+
+extern "C" void sp_targets_destroy(sp_targets *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    for (auto &kv : t->packs) {
+        cudaFree(kv.second.d_text); cudaFree(kv.second.d_tile_off); cudaFree(kv.second.d_tile_text0);
+    }
+    cudaFree(t->d_bases); cudaFree(t->d_offs);
+    delete t;
+}
+extern "C" int64_t sp_targets_count(const sp_targets *t) { return t ? t->n : 0; }
+extern "C" int64_t sp_targets_total_len(const sp_targets *t) { return t ? t->total_len : 0; }
+
+// builds (or returns the cached) tile stream for tile capacity tc
+static sp_status get_text_pack(sp_ctx *ctx, sp_targets *t, int tc, const TextPack **out) {
+    auto it = t->packs.find(tc);
+    if (it != t->packs.end()) { *out = &it->second; return SP_OK; }
+    std::vector<int32_t> tile_off(1, 0), tile_text0, text_chunk0(static_cast<size_t>(t->n));
+    int64_t cur = 0, tile_start = 0;
+    bool open = false;
+    for (int64_t i = 0; i < t->n; ++i) {
+        const int32_t nc = t->nch[static_cast<size_t>(i)];
+        if (open && cur - tile_start + nc > tc) {  // close the tile, pad to an even chunk count (16-byte TMA granule)
+            cur += (cur - tile_start) & 1;
+            tile_off.push_back(static_cast<int32_t>(cur));
+            open = false;
+        }
+        if (!open) { tile_start = cur; tile_text0.push_back(static_cast<int32_t>(i)); open = true; }
+        text_chunk0[static_cast<size_t>(i)] = static_cast<int32_t>(cur);
+        cur += nc;
+        if (cur > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "text set too large for one call");
+    }
+    if (open) { cur += (cur - tile_start) & 1; tile_off.push_back(static_cast<int32_t>(cur)); }
+    TextPack pk;
+    pk.tc = tc; pk.n_tiles = static_cast<int>(tile_text0.size()); pk.total_chunks = cur;
+    int32_t *d_chunk0 = nullptr, *d_nch = nullptr;
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_text), static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_tile_off), tile_off.size() * 4));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_tile_text0), std::max<size_t>(tile_text0.size(), 1) * 4));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_chunk0), std::max<size_t>(text_chunk0.size(), 1) * 4));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_nch), std::max<size_t>(t->nch.size(), 1) * 4));
+    SP_CUDA(ctx, cudaMemsetAsync(pk.d_text, 0x04, static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8, ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(pk.d_tile_off, tile_off.data(), tile_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!tile_text0.empty())
+        SP_CUDA(ctx, cudaMemcpyAsync(pk.d_tile_text0, tile_text0.data(), tile_text0.size() * 4, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    if (t->n) {
+        SP_CUDA(ctx, cudaMemcpyAsync(d_chunk0, text_chunk0.data(), text_chunk0.size() * 4, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        SP_CUDA(ctx, cudaMemcpyAsync(d_nch, t->nch.data(), t->nch.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const int blocks = static_cast<int>(std::min<int64_t>(t->n, 65535));
+        ev_begin(ctx, 3);
+        pack_texts<<<blocks, 128, 0, ctx->stream>>>(t->d_bases, t->d_offs, d_chunk0, d_nch, pk.d_text,
+                                                    static_cast<int>(t->n));
+        ev_end(ctx, 3);
+        ++ctx->launches;
+        SP_CUDA(ctx, cudaGetLastError());
+    }
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    cudaFree(d_chunk0); cudaFree(d_nch);
+    auto ins = t->packs.emplace(tc, pk);
+    *out = &ins.first->second;
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 launch
+// ------------------------------------------------------------------------------------------
+template <int U, bool TE>
+static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_items) {
+    SP_CUDA(ctx, cudaFuncSetAttribute(k1_infix<U, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int occ = 0;
+    SP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_infix<U, TE>, K1_THREADS, smem));
+    if (occ < 1) return fail(ctx, SP_ERR_CUDA, "K1 does not fit on an SM with the requested shared memory");
+    // persistent CTAs: a multiple of the SM count, each looping over (pattern-group, text-tile) items
+    const int grid = std::min(n_items, ctx->num_sms * occ);
+    ev_begin(ctx, 0);
+    k1_infix<U, TE><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+    ev_end(ctx, 0);
+    ++ctx->launches;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+template <bool TE>
+static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t smem, int n_items) {
+    switch (U) {
+        case 4: return launch_k1<4, TE>(ctx, prm, smem, n_items);
+        case 6: return launch_k1<6, TE>(ctx, prm, smem, n_items);
+        case 8: return launch_k1<8, TE>(ctx, prm, smem, n_items);
+        case 10: return launch_k1<10, TE>(ctx, prm, smem, n_items);
+        case 12: return launch_k1<12, TE>(ctx, prm, smem, n_items);
+        case 16: return launch_k1<16, TE>(ctx, prm, smem, n_items);
+        default: return fail(ctx, SP_ERR_INVALID, "unsupported lane width");
+    }
+}
+
+extern "C" sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t_in, const sp_patterns *p, int elem_bits,
+                                     int want_end_col, sp_dmatrix **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!t_in || !p || !out) return fail(ctx, SP_ERR_INVALID, "sp_score_device: NULL argument");
+    if (elem_bits != 16 && elem_bits != 32) return fail(ctx, SP_ERR_INVALID, "elem_bits must be 16 or 32");
+    *out = nullptr;
+    sp_targets *t = const_cast<sp_targets *>(t_in);  // the tile-stream cache is an implementation detail
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    sp_dmatrix *d = new (std::nothrow) sp_dmatrix();
+    if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    d->ctx = ctx; d->nt = t->n; d->np = p->n; d->elem_bits = elem_bits;
+    d->ld = (t->n + 63) / 64 * 64;
+    const size_t elems = static_cast<size_t>(std::max<int64_t>(d->np * d->ld, 1));
+    cudaError_t e = cudaMalloc(&d->d, elems * (elem_bits / 8));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, elems * (elem_bits / 8), ctx->stream);
+    if (e == cudaSuccess && want_end_col) {
+        e = cudaMalloc(reinterpret_cast<void **>(&d->d_end), elems * 4);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d->d_end, 0, elems * 4, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        sp_dmatrix_destroy(d);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA,
+                    std::string("distance matrix allocation: ") + cudaGetErrorString(e));
+    }
+    if (t->n == 0 || p->n == 0 || p->total_len == 0) { *out = d; return SP_OK; }
+
+    // tile capacity: 32 KB of text by default, grown for long texts, shrunk when the work list would be too short
+    const int U = p->U;
+    const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
+    const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
+    int64_t tc = 4096;
+    const int64_t want_items = 4ll * ctx->num_sms;
+    if (static_cast<int64_t>(p->n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
+        const int64_t want_tiles = (want_items + p->n_groups - 1) / p->n_groups;
+        tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
+    }
+    tc = std::max<int64_t>(tc, t->max_nch);
+    tc = (tc + 1) / 2 * 2;
+    if (tc > max_tc) {
+        sp_dmatrix_destroy(d);
+        return fail(ctx, SP_ERR_TOO_LONG,
+                    "text of " + std::to_string(static_cast<long long>(t->max_nch) * K1_CHUNK) +
+                        " columns exceeds the shared-memory tile budget (" + std::to_string(max_tc * K1_CHUNK) + ")");
+    }
+    const TextPack *pk = nullptr;
+    sp_status st = get_text_pack(ctx, t, static_cast<int>(tc), &pk);
+    if (st != SP_OK) { sp_dmatrix_destroy(d); return st; }
+
+    K1Params prm;
+    prm.blobs = p->d_blobs; prm.text = pk->d_text; prm.tile_chunk_off = pk->d_tile_off; prm.tile_text0 = pk->d_tile_text0;
+    prm.out = d->d; prm.out_end = d->d_end; prm.ld = d->ld;
+    prm.n_groups = p->n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
+    prm.prefix_mode = p->mode == SP_PREFIX;
+    const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
+    if (n_items64 > 0x7FFFFFFFll) { sp_dmatrix_destroy(d); return fail(ctx, SP_ERR_RANGE, "work list too large"); }
+    const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
+    st = want_end_col ? dispatch_k1<true>(ctx, U, prm, smem, static_cast<int>(n_items64))
+                      : dispatch_k1<false>(ctx, U, prm, smem, static_cast<int>(n_items64));
+    if (st != SP_OK) { sp_dmatrix_destroy(d); return st; }
+    *out = d;
+    return SP_OK;
+}
+
+extern "C" void sp_dmatrix_destroy(sp_dmatrix *d) {
+    if (!d) return;
+    if (d->owned) {
+        cudaSetDevice(d->ctx->device);
+        cudaStreamSynchronize(d->ctx->stream);
+        cudaFree(d->d);
+        cudaFree(d->d_end);
+    }
+    delete d;
+}
+extern "C" void *sp_dmatrix_device_ptr(const sp_dmatrix *d) { return d ? d->d : nullptr; }
+extern "C" int64_t sp_dmatrix_ld(const sp_dmatrix *d) { return d ? d->ld : 0; }
+extern "C" int sp_dmatrix_elem_bits(const sp_dmatrix *d) { return d ? d->elem_bits : 0; }
+
+extern "C" sp_status sp_dmatrix_wrap(sp_ctx *ctx, void *dev_ptr, int64_t n_targets, int64_t n_patterns, int64_t ld,
+                                     int elem_bits, sp_dmatrix **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out || (!dev_ptr && n_targets * n_patterns > 0) || n_targets < 0 || n_patterns < 0 || ld < n_targets ||
+        (elem_bits != 16 && elem_bits != 32))
+        return fail(ctx, SP_ERR_INVALID, "sp_dmatrix_wrap: bad argument");
+    sp_dmatrix *d = new (std::nothrow) sp_dmatrix();
+    if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    d->ctx = ctx; d->d = dev_ptr; d->nt = n_targets; d->np = n_patterns; d->ld = ld; d->elem_bits = elem_bits;
+    d->owned = false;
+    *out = d;
+    return SP_OK;
+}
+
+extern "C" sp_status sp_dmatrix_to_host(sp_ctx *ctx, const sp_dmatrix *d, int32_t *D, int32_t *end_col) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!d || (!D && !end_col)) return fail(ctx, SP_ERR_INVALID, "sp_dmatrix_to_host: NULL argument");
+    if (end_col && !d->d_end) return fail(ctx, SP_ERR_INVALID, "matrix was scored without end columns");
+    if (d->nt == 0 || d->np == 0) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = static_cast<size_t>(d->nt * d->np);
+    int32_t *rows = nullptr;
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&rows), n * 4));
+    const dim3 grid(static_cast<unsigned>((d->nt + 31) / 32), static_cast<unsigned>((d->np + 31) / 32)), blk(32, 8);
+    cudaError_t e = cudaSuccess;
+    if (D) {
+        if (d->elem_bits == 16)
+            dmatrix_to_rows<uint16_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld,
+                                                                     static_cast<int>(d->nt), static_cast<int>(d->np), rows);
+        else
+            dmatrix_to_rows<int32_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld,
+                                                                    static_cast<int>(d->nt), static_cast<int>(d->np), rows);
+        ++ctx->launches;
+        e = cudaMemcpyAsync(D, rows, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e == cudaSuccess && end_col) {
+        dmatrix_to_rows<int32_t><<<grid, blk, 0, ctx->stream>>>(d->d_end, d->ld, static_cast<int>(d->nt),
+                                                                static_cast<int>(d->np), rows);
+        ++ctx->launches;
+        e = cudaMemcpyAsync(end_col, rows, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(rows);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("sp_dmatrix_to_host: ") + cudaGetErrorString(e));
+    return SP_OK;
+}
+
+extern "C" sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, sp_mode mode,
+                                    int32_t *D, int32_t *end_col) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!D) return fail(ctx, SP_ERR_INVALID, "sp_score_batch: D is NULL");
+    sp_patterns *p = nullptr; sp_targets *t = nullptr; sp_dmatrix *d = nullptr;
+    sp_status st = sp_patterns_create(ctx, patterns, mode, &p);
+    if (st == SP_OK) st = sp_targets_create(ctx, targets, &t);
+    if (st == SP_OK) st = sp_score_device(ctx, t, p, 32, end_col != nullptr, &d);
+    if (st == SP_OK) st = sp_dmatrix_to_host(ctx, d, D, end_col);
+    sp_dmatrix_destroy(d); sp_targets_destroy(t); sp_patterns_destroy(p);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------
+static sp_status k2_check(sp_ctx *ctx, const sp_dmatrix *d) {
+    if (!d) return fail(ctx, SP_ERR_INVALID, "K2: matrix is NULL");
+    if (d->np > 0x7FFFFFFFll || d->nt > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "K2: matrix too large");
+    return SP_OK;
+}
+
+extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64_t i_begin, int64_t i_end, int k,
+                                         sp_pair_rec *out, int *n_out) {
+    if (!ctx) return SP_ERR_INVALID;
+    sp_status st = k2_check(ctx, d);
+    if (st != SP_OK) return st;
+    if (!out || !n_out || k < 1 || k > K2_MAXK) return fail(ctx, SP_ERR_INVALID, "K2: bad k / NULL output");
+    *n_out = 0;
+    const int A = static_cast<int>(d->np);
+    i_begin = std::max<int64_t>(i_begin, 0);
+    i_end = std::min<int64_t>(i_end, A);
+    if (i_begin >= i_end) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    K2Params prm;
+    prm.D = d->d; prm.ld = d->ld; prm.R = static_cast<int>(d->nt); prm.A = A;
+    prm.i_begin = static_cast<int>(i_begin); prm.i_end = static_cast<int>(i_end);
+    prm.tile_i0 = prm.i_begin / K2_TILE;
+    prm.n_tiles_j = (A + K2_TILE - 1) / K2_TILE;
+    prm.k = k; prm.S = nullptr;
+    const int tile_i1 = (prm.i_end + K2_TILE - 1) / K2_TILE;
+    long long n_ctas = 0;
+    for (int I = prm.tile_i0; I < tile_i1; ++I) n_ctas += prm.n_tiles_j - I;
+    if (n_ctas > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "K2: too many tiles");
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&prm.cand), static_cast<size_t>(n_ctas) * k * sizeof(PairKey)));
+    ev_begin(ctx, 1);
+    if (d->elem_bits == 16) k2_pair_minsum<uint16_t, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+    else k2_pair_minsum<int32_t, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+    ev_end(ctx, 1);
+    ++ctx->launches;
+    std::vector<PairKey> cand(static_cast<size_t>(n_ctas) * k);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cand.data(), prm.cand, cand.size() * sizeof(PairKey), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(prm.cand);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2: ") + cudaGetErrorString(e));
+    // merge of the per-tile lists: same (score, i, j) order, so any sharding gives the same answer
+    cand.erase(std::remove_if(cand.begin(), cand.end(), [](const PairKey &c) { return c.ij == ~0ull; }), cand.end());
+    const size_t kk = std::min<size_t>(static_cast<size_t>(k), cand.size());
+    std::partial_sort(cand.begin(), cand.begin() + static_cast<std::ptrdiff_t>(kk), cand.end(),
+                      [](const PairKey &a, const PairKey &b) { return a.score < b.score || (a.score == b.score && a.ij < b.ij); });
+    if (kk == 0) return SP_OK;
+    std::vector<uint32_t> ij(2 * kk), c1(kk);
+    for (size_t q = 0; q < kk; ++q) {
+        ij[2 * q] = static_cast<uint32_t>(cand[q].ij >> 32);
+        ij[2 * q + 1] = static_cast<uint32_t>(cand[q].ij & 0xFFFFFFFFu);
+    }
+    uint32_t *d_ij = nullptr, *d_c1 = nullptr;
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_ij), ij.size() * 4));
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_c1), c1.size() * 4));
+    e = cudaMemcpyAsync(d_ij, ij.data(), ij.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        if (d->elem_bits == 16)
+            k2_count_c1<uint16_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, prm.R, d_ij, d_c1);
+        else
+            k2_count_c1<int32_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, prm.R, d_ij, d_c1);
+        ++ctx->launches;
+        e = cudaMemcpyAsync(c1.data(), d_c1, c1.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ij); cudaFree(d_c1);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2 c1: ") + cudaGetErrorString(e));
+    for (size_t q = 0; q < kk; ++q) {
+        out[q].score = cand[q].score; out[q].i = ij[2 * q]; out[q].j = ij[2 * q + 1]; out[q].c1 = c1[q]; out[q]._pad = 0;
+    }
+    *n_out = static_cast<int>(kk);
+    return SP_OK;
+}
+
+extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint64_t *S) {
+    if (!ctx) return SP_ERR_INVALID;
+    sp_status st = k2_check(ctx, d);
+    if (st != SP_OK) return st;
+    if (!S) return fail(ctx, SP_ERR_INVALID, "K2: S is NULL");
+    const int A = static_cast<int>(d->np);
+    if (A == 0) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    K2Params prm;
+    prm.D = d->d; prm.ld = d->ld; prm.R = static_cast<int>(d->nt); prm.A = A;
+    prm.i_begin = 0; prm.i_end = A; prm.tile_i0 = 0; prm.n_tiles_j = (A + K2_TILE - 1) / K2_TILE;
+    prm.k = 0; prm.cand = nullptr;
+    const long long n_ctas = static_cast<long long>(prm.n_tiles_j) * (prm.n_tiles_j + 1) / 2;
+    const size_t bytes = static_cast<size_t>(A) * A * sizeof(unsigned long long);
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&prm.S), bytes));
+    cudaError_t e = cudaMemsetAsync(prm.S, 0, bytes, ctx->stream);
+    if (e == cudaSuccess) {
+        ev_begin(ctx, 1);
+        if (d->elem_bits == 16) k2_pair_minsum<uint16_t, true><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+        else k2_pair_minsum<int32_t, true><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+        ev_end(ctx, 1);
+        ++ctx->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(S, prm.S, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(prm.S);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2 full: ") + cudaGetErrorString(e));
+    return SP_OK;
+}
+
+// host rows [R][A] int32 -> temporary device matrix
+static sp_status upload_rows(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, sp_dmatrix **out) {
+    if (!D || R < 0 || A < 0) return fail(ctx, SP_ERR_INVALID, "K2 host: bad argument");
+    if (R > 0x7FFFFFF0ll || A > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "K2 host: matrix too large");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    sp_dmatrix *d = new (std::nothrow) sp_dmatrix();
+    if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    d->ctx = ctx; d->nt = R; d->np = A; d->ld = (R + 63) / 64 * 64; d->elem_bits = 32;
+    int32_t *rows = nullptr;
+    const size_t n = static_cast<size_t>(std::max<int64_t>(R * A, 1));
+    cudaError_t e = cudaMalloc(&d->d, static_cast<size_t>(std::max<int64_t>(A * d->ld, 1)) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&rows), n * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, static_cast<size_t>(std::max<int64_t>(A * d->ld, 1)) * 4, ctx->stream);
+    if (e == cudaSuccess && R * A > 0) {
+        e = cudaMemcpyAsync(rows, D, static_cast<size_t>(R * A) * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            const dim3 grid(static_cast<unsigned>((A + 31) / 32), static_cast<unsigned>((R + 31) / 32)), blk(32, 8);
+            rows_to_dmatrix<<<grid, blk, 0, ctx->stream>>>(rows, static_cast<int>(R), static_cast<int>(A), d->ld,
+                                                           static_cast<int32_t *>(d->d));
+            ++ctx->launches;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(rows);
+    if (e != cudaSuccess) { sp_dmatrix_destroy(d); return fail(ctx, SP_ERR_CUDA, std::string("K2 host upload: ") + cudaGetErrorString(e)); }
+    *out = d;
+    return SP_OK;
+}
+
+extern "C" sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, int k,
+                                              sp_pair_rec *out, int *n_out) {
+    if (!ctx) return SP_ERR_INVALID;
+    sp_dmatrix *d = nullptr;
+    sp_status st = upload_rows(ctx, D, R, A, &d);
+    if (st == SP_OK) st = sp_pair_minsum_topk(ctx, d, 0, A, k, out, n_out);
+    sp_dmatrix_destroy(d);
+    return st;
+}
+
+extern "C" sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S) {
+    if (!ctx) return SP_ERR_INVALID;
+    sp_dmatrix *d = nullptr;
+    sp_status st = upload_rows(ctx, D, R, A, &d);
+    if (st == SP_OK) st = sp_pair_minsum_full(ctx, d, S);
+    sp_dmatrix_destroy(d);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// integer pipe peak
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!ops_per_s || kind < 0 || kind > 3) return fail(ctx, SP_ERR_INVALID, "sp_int_peak: bad argument");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = ctx->num_sms * 8, iters = 8192;
+    uint32_t *d_out = nullptr;
+    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_out), static_cast<size_t>(grid) * 256 * 4));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        switch (kind) {
+            case 0: int_peak_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            case 1: int_peak_kernel<1><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            case 2: int_peak_kernel<2><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            default: int_peak_kernel<3><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+        }
+        cudaEventRecord(b, ctx->stream);
+        ++ctx->launches;
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("sp_int_peak: ") + cudaGetErrorString(e));
+    const double ops = static_cast<double>(grid) * 256.0 * iters * 64.0;
+    *ops_per_s = ops / (best_ms * 1e-3);
+    return SP_OK;
+}

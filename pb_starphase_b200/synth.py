@@ -1,0 +1,101 @@
+"""Seeded synthetic inputs of the shapes SURVEY.md §8(d) names (there is no network / no BAM
+fixture, so every bench and most tests run on these).  Pure numpy; deterministic per seed."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+DEFAULT_SEED = 20251106
+
+# (n_dna_alleles, root_len, min_len, max_len, n_cdna_alleles, cdna_len) -- v2.0.0 DB statistics,
+# /root/reference/data/v2.0.0/pbstarphase_20251106.db_stat.txt:44-47 and SURVEY.md §6
+GENE_SHAPES = {
+    "HLA-A": dict(n_dna=5695, root=3100, lo=1301, hi=3537, n_cdna=8949, cdna=1098),
+    "HLA-B": dict(n_dna=6756, root=2990, lo=2657, hi=4103, n_cdna=10680, cdna=1089),
+}
+
+
+def random_seq(rng: np.random.Generator, n: int) -> np.ndarray:
+    return ACGT[rng.integers(0, 4, size=n)]
+
+
+def mutate(rng: np.random.Generator, seq: np.ndarray, n_snp: int, n_indel: int) -> np.ndarray:
+    s = seq.copy()
+    if len(s) == 0:
+        return s
+    for pos in rng.integers(0, len(s), size=n_snp):
+        s[pos] = ACGT[(np.searchsorted(ACGT, s[pos]) + rng.integers(1, 4)) % 4]
+    for _ in range(n_indel):
+        pos = int(rng.integers(0, len(s)))
+        ln = int(rng.integers(1, 4))
+        if rng.random() < 0.5:
+            s = np.concatenate([s[:pos], random_seq(rng, ln), s[pos:]])
+        else:
+            s = np.concatenate([s[:pos], s[pos + ln:]])
+    return s
+
+
+def allele_tree(rng: np.random.Generator, n: int, root_len: int, lo: int, hi: int, partial_frac: float = 0.12) -> List[bytes]:
+    """Mutation tree from one random root: each child copies a random earlier allele and gets
+    Poisson(6) SNPs and (10 %) a 1-3 bp indel, so neighbours differ by a few edits like IMGT/HLA.
+    A fraction is truncated (partial entries) or extended so lengths span [lo, hi]."""
+    seqs = [random_seq(rng, root_len)]
+    for _ in range(1, n):
+        parent = seqs[int(rng.integers(0, len(seqs)))]
+        child = mutate(rng, parent, int(rng.poisson(6)), 1 if rng.random() < 0.10 else 0)
+        seqs.append(child)
+    out = []
+    for s in seqs:
+        r = rng.random()
+        if r < partial_frac and len(s) > lo:
+            new_len = int(rng.integers(lo, len(s)))
+            start = int(rng.integers(0, len(s) - new_len + 1))
+            s = s[start:start + new_len]
+        elif r > 1.0 - partial_frac / 2 and len(s) < hi:
+            ext = int(rng.integers(1, hi - len(s) + 1))
+            s = np.concatenate([random_seq(rng, ext // 2), s, random_seq(rng, ext - ext // 2)])
+        s = s[:hi]
+        out.append(s.tobytes())
+    return out
+
+
+def hifi_reads(rng: np.random.Generator, alleles: List[bytes], n: int, err: float = 0.002, flank: int = 250,
+               lo: int = 2800, hi: int = 4400) -> Tuple[List[bytes], np.ndarray]:
+    """Reads = random allele + `err` errors (70 % homopolymer +-1, rest substitutions) + random flanks."""
+    reads, src = [], np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        a = int(rng.integers(0, len(alleles)))
+        src[i] = a
+        s = np.frombuffer(alleles[a], dtype=np.uint8)
+        n_err = int(rng.poisson(err * len(s)))
+        s = s.copy()
+        for _ in range(n_err):
+            pos = int(rng.integers(0, len(s)))
+            if rng.random() < 0.7:  # homopolymer length error
+                if rng.random() < 0.5:
+                    s = np.concatenate([s[:pos], s[pos:pos + 1], s[pos:]])
+                else:
+                    s = np.concatenate([s[:pos], s[pos + 1:]])
+            else:
+                s[pos] = ACGT[(np.searchsorted(ACGT, s[pos]) + rng.integers(1, 4)) % 4]
+        s = np.concatenate([random_seq(rng, flank), s, random_seq(rng, flank)])
+        if len(s) > hi:
+            s = s[:hi]
+        reads.append(s.tobytes())
+    return reads, src
+
+
+def hla_gene(seed: int, gene: str, n_alleles: int | None = None, n_reads: int = 64, with_cdna: bool = False):
+    """One gene's synthetic workload: (dna_alleles, reads, source_allele_index[, cdna_alleles])."""
+    shape = GENE_SHAPES[gene]
+    rng = np.random.default_rng([seed, sum(gene.encode())])
+    n = n_alleles if n_alleles is not None else shape["n_dna"]
+    alleles = allele_tree(rng, n, shape["root"], shape["lo"], shape["hi"])
+    reads, src = hifi_reads(rng, alleles, n_reads)
+    if not with_cdna:
+        return alleles, reads, src
+    nc = shape["n_cdna"] if n_alleles is None else n_alleles
+    cdna = allele_tree(rng, nc, shape["cdna"], 534, 1208, partial_frac=0.05)
+    return alleles, reads, src, cdna

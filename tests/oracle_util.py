@@ -1,0 +1,86 @@
+"""Test-side loader of the CPU oracle (oracle/sp_oracle.c).  Only tests, smoke() and bench.py's
+cpu_baseline / --impl reference legs import this; the product never does."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+LIB = ORACLE_DIR / "libsp_oracle.so"
+
+
+class PairRec(C.Structure):
+    _fields_ = [("score", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32)]
+
+
+def build_oracle(force: bool = False) -> Path:
+    src = ORACLE_DIR / "sp_oracle.c"
+    if force or not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(ORACLE_DIR), "-B" if force else "-s"])
+    return LIB
+
+
+def _pack(seqs: Sequence[bytes]):
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+    joined = b"".join(bytes(s) for s in seqs)
+    bases = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, dtype=np.uint8)
+    return bases, offs
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(str(build_oracle()))
+        L = self.lib
+        L.sp_oracle_infix_dp.restype = C.c_int64
+        L.sp_oracle_infix_dp.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+        L.sp_oracle_infix_myers.restype = C.c_int64
+        L.sp_oracle_infix_myers.argtypes = L.sp_oracle_infix_dp.argtypes
+        L.sp_oracle_score_batch.restype = C.c_int64
+        L.sp_oracle_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sp_oracle_pair_minsum_topk.restype = C.c_int
+        L.sp_oracle_pair_minsum_topk.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(PairRec)]
+        L.sp_oracle_pair_minsum_full.restype = None
+        L.sp_oracle_pair_minsum_full.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.sp_oracle_num_threads.restype = C.c_int
+
+    def num_threads(self) -> int:
+        return int(self.lib.sp_oracle_num_threads())
+
+    def infix(self, pattern: bytes, text: bytes, prefix: bool = False, impl: str = "dp"):
+        e = C.c_int64(0)
+        fn = self.lib.sp_oracle_infix_dp if impl == "dp" else self.lib.sp_oracle_infix_myers
+        d = fn(bytes(pattern), len(pattern), bytes(text), len(text), int(prefix), C.byref(e))
+        return int(d), int(e.value)
+
+    def score_batch(self, targets, patterns, prefix: bool = False, impl: str = "myers", nthreads: int = 0,
+                    want_end_col: bool = False):
+        """Returns D[t, p] int32 (and end columns) plus the cell count via .last_cells."""
+        tb, to = targets if isinstance(targets, tuple) else _pack(targets)
+        pb, po = patterns if isinstance(patterns, tuple) else _pack(patterns)
+        nt, npat = len(to) - 1, len(po) - 1
+        D = np.zeros((nt, npat), dtype=np.int32)
+        E = np.zeros((nt, npat), dtype=np.int32) if want_end_col else None
+        self.last_cells = int(self.lib.sp_oracle_score_batch(
+            tb.ctypes.data, to.ctypes.data, nt, pb.ctypes.data, po.ctypes.data, npat, int(prefix),
+            0 if impl == "dp" else 1, nthreads, D.ctypes.data, E.ctypes.data if E is not None else None))
+        return (D, E) if want_end_col else D
+
+    def pair_minsum_topk(self, D: np.ndarray, k: int, nthreads: int = 0):
+        D = np.ascontiguousarray(D, dtype=np.int32)
+        recs = (PairRec * k)()
+        n = self.lib.sp_oracle_pair_minsum_topk(D.ctypes.data, D.shape[0], D.shape[1], k, nthreads, recs)
+        return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[:n]]
+
+    def pair_minsum_full(self, D: np.ndarray, nthreads: int = 0) -> np.ndarray:
+        D = np.ascontiguousarray(D, dtype=np.int32)
+        S = np.zeros((D.shape[1], D.shape[1]), dtype=np.uint64)
+        self.lib.sp_oracle_pair_minsum_full(D.ctypes.data, D.shape[0], D.shape[1], nthreads, S.ctypes.data)
+        return S

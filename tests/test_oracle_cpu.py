@@ -1,0 +1,112 @@
+"""CPU suite: pins the oracle (oracle/sp_oracle.c) against itself (DP vs Myers) and against the
+golden vectors re-expressed from the reference's own tests (tests/golden)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+COMP = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+
+def revcomp(s: bytes) -> bytes:
+    return s.translate(COMP)[::-1]
+
+
+def rnd(rng, n):
+    return bytes(rng.choice(list(b"ACGT"), n).tolist())
+
+
+def test_dp_equals_myers_random(oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(250):
+        m, n = int(rng.integers(0, 260)), int(rng.integers(0, 330))
+        P = bytearray(rnd(rng, m))
+        T = bytearray(rnd(rng, n // 2)) + P + bytearray(rnd(rng, n // 2))
+        for _ in range(int(rng.integers(0, 12))):
+            if T:
+                T[int(rng.integers(0, len(T)))] = int(rng.choice(list(b"ACGTN")))
+        for prefix in (False, True):
+            assert oracle.infix(bytes(P), bytes(T), prefix, "dp") == oracle.infix(bytes(P), bytes(T), prefix, "myers")
+
+
+def test_known_small_cases(oracle):
+    # exact substring, one substitution, one deletion from the pattern, N never matches
+    assert oracle.infix(b"ACGT", b"TTACGTTT") == (0, 6)
+    assert oracle.infix(b"ACGT", b"TTAGGTTT")[0] == 1
+    assert oracle.infix(b"ACGT", b"TTAGTTT")[0] == 1
+    assert oracle.infix(b"ACGT", b"TTACNTTT")[0] == 1
+    assert oracle.infix(b"ACNT", b"TTACNTTT")[0] == 1
+    assert oracle.infix(b"", b"ACGT") == (0, 0)
+    assert oracle.infix(b"ACGT", b"") == (4, 0)
+    # prefix mode: placement has to start at text position 0
+    assert oracle.infix(b"ACGT", b"TTACGT", prefix=True)[0] == 2
+    assert oracle.infix(b"ACGT", b"ACGTTT", prefix=True) == (0, 4)
+
+
+def test_block_boundaries(oracle):
+    rng = np.random.default_rng(11)
+    for m in (1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025):
+        P = rnd(rng, m)
+        T = rnd(rng, 50) + P + rnd(rng, 50)
+        for impl in ("myers", "dp"):
+            d, e = oracle.infix(P, T, impl=impl)
+            assert d == 0 and e <= 50 + m
+            if m >= 31:  # a chance earlier occurrence is impossible in practice
+                assert e == 50 + m
+
+
+def test_golden_hla_faux_reference_alleles(oracle):
+    """src/hla/caller.rs:1709-1773: an exact-copy read scores (len, 0, 0) against its own allele,
+    for HLA-A (forward) and HLA-B (read given as the reverse complement, gene on the reverse strand)."""
+    g = json.loads((GOLDEN / "hla_faux.json").read_text())
+    for case in g["expected"]["test_reference_alleles"]:
+        a = g["hla_sequences"][case["hla_id"]]
+        dna, cdna = a["dna_sequence"].encode(), a["cdna_sequence"].encode()
+        read = revcomp(dna) if case["read_is_revcomp"] else dna
+        target = revcomp(read) if case["read_is_revcomp"] else read  # score_read puts the read on the gene strand
+        assert oracle.infix(dna, target, impl="myers")[0] == 0
+        assert oracle.infix(dna, target, impl="dp")[0] == 0
+        # the other gene's allele must not be a perfect hit
+        for other_id, other in g["hla_sequences"].items():
+            if other_id != case["hla_id"]:
+                assert oracle.infix(other["dna_sequence"].encode(), target, impl="myers")[0] > 0
+        assert len(cdna) in (1098, 1089)
+
+
+def test_golden_bad_read(oracle):
+    """src/hla/caller.rs:1783-1809: a 4-bp read matches nothing; the distance is ~|allele| so the
+    score (nm+unmapped)/len is at the worst value (>= 0.99, reported as 1.0 when minimap2 maps nothing)."""
+    g = json.loads((GOLDEN / "hla_faux.json").read_text())
+    for a in g["hla_sequences"].values():
+        dna = a["dna_sequence"].encode()
+        d, _ = oracle.infix(dna, b"ACGT", impl="myers")
+        assert len(dna) - 4 <= d <= len(dna)
+
+
+def test_golden_weight_sequence(oracle):
+    """src/cyp2d6/chaining.rs:1050-1080: P = read segment (fully explained), T = consensus."""
+    g = json.loads((GOLDEN / "weight_sequence.json").read_text())
+    cons = [c.encode() for c in g["consensuses"]]
+    q0, q1 = (q.encode() for q in g["queries"])
+    s0 = [oracle.infix(q0, c)[0] for c in cons]
+    assert s0[0] == 0 and s0[1] == 1 and s0[2] == 1
+    s1 = [oracle.infix(q1, c)[0] for c in cons]
+    assert s1[0] == s1[1] == s1[2] == 1
+
+
+def test_pair_minsum_against_numpy(oracle):
+    rng = np.random.default_rng(3)
+    D = rng.integers(0, 50, size=(37, 23)).astype(np.int32)
+    S = oracle.pair_minsum_full(D)
+    ref = np.zeros_like(S)
+    for i in range(23):
+        for j in range(i, 23):
+            ref[i, j] = np.minimum(D[:, i], D[:, j]).sum()
+    assert (S == ref).all()
+    top = oracle.pair_minsum_topk(D, 10)
+    flat = sorted((int(ref[i, j]), i, j) for i in range(23) for j in range(i, 23))[:10]
+    assert [(s, i, j) for s, i, j, _ in top] == flat
+    for s, i, j, c1 in top:
+        assert c1 == int((D[:, i] <= D[:, j]).sum())
