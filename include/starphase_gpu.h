@@ -68,12 +68,15 @@ typedef struct sp_targets sp_targets;   /* device-resident packed text set (read
 typedef struct sp_dmatrix sp_dmatrix;   /* device-resident distance matrix, u16 or i32             */
 
 /* One ranked pair: allele-pair for HLA (north_star K2), chain-pair for CYP2D6
- * (src/cyp2d6/chaining.rs:409-534).  Ordering key is (score, i, j) ascending,
- * i <= j -- the reference's ChainScore::compare_tuple (chaining.rs:188-197).
- * c1 = #{reads r : D[r,i] <= D[r,j]} so the host can apply is_passing_dual
- * (src/hla/caller.rs:1225-1247) unchanged. */
+ * (src/cyp2d6/chaining.rs:409-534).  Ordering key is (score, score2, i, j) ascending,
+ * i <= j -- the reference's ChainScore::compare_tuple (chaining.rs:188-197), with the
+ * optional secondary sum playing the role of the DNA score behind the cDNA score in
+ * HlaMappingScore's lexicographic order (src/hla/mapping.rs:111-117).
+ * c1 = #{reads r : (D[r,i], D2[r,i]) <= (D[r,j], D2[r,j])} so the host can apply
+ * is_passing_dual (src/hla/caller.rs:1225-1247) unchanged. */
 typedef struct sp_pair_rec {
-    uint64_t score;
+    uint64_t score;  /* sum over reads of min(D[r,i], D[r,j]) on the primary matrix            */
+    uint64_t score2; /* same on the secondary matrix (0 when none was given)                   */
     uint32_t i, j;
     uint32_t c1;
     uint32_t _pad;
@@ -138,16 +141,17 @@ sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
 
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
- * writes the k smallest by (S, i, j) into out (k <= 64), returns the count in *n_out.
+ * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;
+ * writes the k smallest by (S, S2, i, j) into out (k <= 64), returns the count in *n_out.
  * Restricting i to a row range is how allele-pair blocks are sharded across GPUs; merging the
  * per-shard lists by the same key reproduces the single-GPU answer exactly. */
-sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64_t i_begin, int64_t i_end,
-                              int k, sp_pair_rec *out, int *n_out);
+sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const sp_dmatrix *d2, int64_t i_begin,
+                              int64_t i_end, int k, sp_pair_rec *out, int *n_out);
 /* Full upper-triangular matrix S[i * n + j] (j >= i; other entries 0) to host memory.  Used by the
  * CYP2D6 chain-pair path where float penalties are added on the host (chaining.rs:459-497). */
 sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint64_t *S);
-/* Host-buffer convenience: D is [R][A] row-major int32 (R reads, A alleles / chains). */
-sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, int k,
+/* Host-buffer convenience: D (and D2, may be NULL) are [R][A] row-major int32 (R reads, A alleles / chains). */
+sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, const int32_t *D2, int64_t R, int64_t A, int k,
                                    sp_pair_rec *out, int *n_out);
 sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S);
 

@@ -165,17 +165,18 @@ int64_t sp_oracle_score_batch(const uint8_t *tbases, const int64_t *toffs, int64
 /*
  * Diplotype pair scoring in the north_star ("pre-v0.13") form: for every
  * unordered allele pair i <= j, S[i,j] = sum_r min(D[r,i], D[r,j]); keep the k
- * smallest by the lexicographic key (S, i, j) -- the same (score, index1,
+ * smallest by the lexicographic key (S, [S2,] i, j) -- the same (score, index1,
  * index2) order the reference uses for chain pairs (src/cyp2d6/chaining.rs:188-197)
  * with allele index = BTreeMap order of hla_id (src/hla/caller.rs:1413).
  * c1 = #{r : D[r,i] <= D[r,j]} feeds the unchanged het/hom test
  * (src/hla/caller.rs:1225-1247).  D is [R][A] row-major int32.
  * Returns the number of records written (min(k, A(A+1)/2)).
  */
-typedef struct { uint64_t score; uint32_t i, j, c1; } sp_oracle_pair_rec;
+typedef struct { uint64_t score, score2; uint32_t i, j, c1, pad; } sp_oracle_pair_rec;
 
 static int rec_less(const sp_oracle_pair_rec *a, const sp_oracle_pair_rec *b) {
     if (a->score != b->score) return a->score < b->score;
+    if (a->score2 != b->score2) return a->score2 < b->score2;
     if (a->i != b->i) return a->i < b->i;
     return a->j < b->j;
 }
@@ -188,7 +189,10 @@ static void topk_push(sp_oracle_pair_rec *heap, int *n, int k, const sp_oracle_p
     heap[pos] = *r;
 }
 
-int sp_oracle_pair_minsum_topk(const int32_t *D, int64_t R, int64_t A, int k, int nthreads,
+/* D2 may be NULL.  With D2 the key is (S1, S2, i, j): the (cDNA, DNA) lexicographic order of
+ * HlaMappingScore (src/hla/mapping.rs:111-117) carried over to pair sums, and a read counts for
+ * the first allele when (D[r,i], D2[r,i]) <= (D[r,j], D2[r,j]). */
+int sp_oracle_pair_minsum_topk(const int32_t *D, const int32_t *D2, int64_t R, int64_t A, int k, int nthreads,
                                sp_oracle_pair_rec *out) {
     if (k <= 0 || A <= 0) return 0;
 #ifdef _OPENMP
@@ -198,10 +202,14 @@ int sp_oracle_pair_minsum_topk(const int32_t *D, int64_t R, int64_t A, int k, in
     (void)nthreads;
     int maxt = 1;
 #endif
-    /* column-major copy so the inner loop over reads is contiguous */
-    int32_t *Dt = (int32_t *)malloc((size_t)(R * A) * sizeof(int32_t));
+    /* column-major copies so the inner loop over reads is contiguous */
+    int32_t *Dt = (int32_t *)malloc((size_t)(R * A + 1) * sizeof(int32_t));
+    int32_t *Dt2 = D2 ? (int32_t *)malloc((size_t)(R * A + 1) * sizeof(int32_t)) : NULL;
     for (int64_t r = 0; r < R; ++r)
-        for (int64_t a = 0; a < A; ++a) Dt[a * R + r] = D[r * A + a];
+        for (int64_t a = 0; a < A; ++a) {
+            Dt[a * R + r] = D[r * A + a];
+            if (D2) Dt2[a * R + r] = D2[r * A + a];
+        }
     sp_oracle_pair_rec *heaps = (sp_oracle_pair_rec *)malloc((size_t)maxt * k * sizeof(*heaps));
     int *counts = (int *)calloc((size_t)maxt, sizeof(int));
 #pragma omp parallel
@@ -215,16 +223,20 @@ int sp_oracle_pair_minsum_topk(const int32_t *D, int64_t R, int64_t A, int k, in
         int *cnt = &counts[tid];
 #pragma omp for schedule(dynamic, 1)
         for (int64_t i = 0; i < A; ++i) {
-            const int32_t *ci = Dt + i * R;
             for (int64_t j = i; j < A; ++j) {
-                const int32_t *cj = Dt + j * R;
-                uint64_t s = 0; uint32_t c1 = 0;
+                uint64_t s = 0, s2 = 0; uint32_t c1 = 0;
                 for (int64_t r = 0; r < R; ++r) {
-                    int32_t x = ci[r], y = cj[r];
+                    int32_t x = Dt[i * R + r], y = Dt[j * R + r];
                     s += (uint64_t)(x < y ? x : y);
-                    c1 += (x <= y);
+                    int le = x <= y;
+                    if (D2) {
+                        int32_t x2 = Dt2[i * R + r], y2 = Dt2[j * R + r];
+                        s2 += (uint64_t)(x2 < y2 ? x2 : y2);
+                        if (x == y) le = x2 <= y2;
+                    }
+                    c1 += (uint32_t)le;
                 }
-                sp_oracle_pair_rec rec = { s, (uint32_t)i, (uint32_t)j, c1 };
+                sp_oracle_pair_rec rec = { s, s2, (uint32_t)i, (uint32_t)j, c1, 0 };
                 topk_push(heap, cnt, k, &rec);
             }
         }
@@ -232,7 +244,7 @@ int sp_oracle_pair_minsum_topk(const int32_t *D, int64_t R, int64_t A, int k, in
     int n = 0;
     for (int t = 0; t < maxt; ++t)
         for (int q = 0; q < counts[t]; ++q) topk_push(out, &n, k, &heaps[(size_t)t * k + q]);
-    free(heaps); free(counts); free(Dt);
+    free(heaps); free(counts); free(Dt); free(Dt2);
     return n;
 }
 

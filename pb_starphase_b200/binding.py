@@ -28,7 +28,7 @@ class SeqSet(C.Structure):
 
 
 class PairRec(C.Structure):
-    _fields_ = [("score", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32), ("_pad", C.c_uint32)]
+    _fields_ = [("score", C.c_uint64), ("score2", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 def lib_path() -> Path:
@@ -63,9 +63,9 @@ SIGNATURES = {
     "sp_dmatrix_elem_bits": (C.c_int, [_P]),
     "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
-    "sp_pair_minsum_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
+    "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
-    "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
+    "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     "sp_int_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "sp_version": (C.c_char_p, []),
@@ -164,16 +164,22 @@ class Context:
         return (D, E) if want_end_col else D
 
     # -- K2 ---------------------------------------------------------------------------------
-    def pair_minsum_topk(self, d, k: int = 10, i_begin: int = 0, i_end: Optional[int] = None):
-        """d: DMatrix (device) or host int32 array [R, A].  Returns list of (score, i, j, c1)."""
+    def pair_minsum_topk(self, d, k: int = 10, i_begin: int = 0, i_end: Optional[int] = None, d2=None):
+        """d (and optional secondary d2): DMatrix (device) or host int32 array [R, A].
+        Returns a list of (score, i, j, c1) -- or (score, score2, i, j, c1) when d2 is given."""
         recs = (PairRec * k)()
         n = C.c_int(0)
         if isinstance(d, DMatrix):
-            self._check(self._lib.sp_pair_minsum_topk(self._h, d._h, i_begin, d.n_patterns if i_end is None else i_end, k, recs, C.byref(n)))
+            self._check(self._lib.sp_pair_minsum_topk(self._h, d._h, d2._h if d2 is not None else None, i_begin,
+                                                      d.n_patterns if i_end is None else i_end, k, recs, C.byref(n)))
         else:
             a = np.ascontiguousarray(d, dtype=np.int32)
-            self._check(self._lib.sp_pair_minsum_topk_host(self._h, a.ctypes.data, a.shape[0], a.shape[1], k, recs, C.byref(n)))
-        return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
+            a2 = np.ascontiguousarray(d2, dtype=np.int32) if d2 is not None else None
+            self._check(self._lib.sp_pair_minsum_topk_host(self._h, a.ctypes.data, a2.ctypes.data if a2 is not None else None,
+                                                           a.shape[0], a.shape[1], k, recs, C.byref(n)))
+        if d2 is None:
+            return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
+        return [(int(r.score), int(r.score2), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
 
     def pair_minsum_full(self, d) -> np.ndarray:
         if isinstance(d, DMatrix):

@@ -348,23 +348,29 @@ __global__ void rows_to_dmatrix(const int32_t *__restrict__ rows, int R, int A, 
 
 // ------------------------------------------------------------------------------------------
 // K2: pair min-sum.  CTA = 64 x 64 pair tile (i-tile I, j-tile J >= I), 256 threads x (4 x 4).
+// Optional second matrix: key = (S1, S2, i, j), the (cDNA, DNA) lexicographic order of
+// HlaMappingScore (src/hla/mapping.rs:111-117) carried over to pair sums.
 // ------------------------------------------------------------------------------------------
 constexpr int K2_TILE = 64;
-constexpr int K2_RC = 64;        // reads per shared-memory stage
+constexpr int K2_RC = 32;        // reads per shared-memory stage
 constexpr int K2_THREADS = 256;
 constexpr int K2_MAXK = 64;
 
 struct PairKey {
     unsigned long long score;
+    unsigned long long score2;
     unsigned long long ij;  // i << 32 | j
 };
 __device__ __forceinline__ bool key_less(const PairKey &a, const PairKey &b) {
-    return a.score < b.score || (a.score == b.score && a.ij < b.ij);
+    if (a.score != b.score) return a.score < b.score;
+    if (a.score2 != b.score2) return a.score2 < b.score2;
+    return a.ij < b.ij;
 }
 
 struct K2Params {
-    const void *D;        // [A][ld], u16 or i32
-    long long ld;
+    const void *D;        // [A][ld], u16 or i32 (primary)
+    const void *D2;       // secondary matrix, same geometry, or nullptr
+    long long ld, ld2;
     int R, A;
     int i_begin, i_end;   // row range owned by this call
     int tile_i0;          // first i-tile index (i_begin / 64)
@@ -383,43 +389,70 @@ __device__ __forceinline__ void k2_decode_tile(int bid, int tile_i0, int n_tiles
     J = I_ + rem;
 }
 
-template <typename T, bool FULL>
+template <typename T> struct K2Acc { using type = unsigned long long; };
+template <> struct K2Acc<uint16_t> { using type = uint32_t; };  // host checks R * 65535 < 2^32
+
+template <typename T, bool DUAL>
+__device__ __forceinline__ void k2_stage(const K2Params &p, int I, int J, int r0, int32_t (*sA)[K2_TILE + 4],
+                                         int32_t (*sB)[K2_TILE + 4], int32_t (*sA2)[K2_TILE + 4],
+                                         int32_t (*sB2)[K2_TILE + 4]) {
+    const T *D = reinterpret_cast<const T *>(p.D);
+    const T *D2 = reinterpret_cast<const T *>(p.D2);
+    for (int e = threadIdx.x; e < K2_TILE * K2_RC; e += K2_THREADS) {
+        const int a = e / K2_RC, r = e % K2_RC;
+        const int ga = I * K2_TILE + a, gb = J * K2_TILE + a, gr = r0 + r;
+        int32_t va = 0, vb = 0, va2 = 0, vb2 = 0;
+        if (gr < p.R) {
+            if (ga < p.A) {
+                va = static_cast<int32_t>(D[static_cast<long long>(ga) * p.ld + gr]);
+                if (DUAL) va2 = static_cast<int32_t>(D2[static_cast<long long>(ga) * p.ld2 + gr]);
+            }
+            if (gb < p.A) {
+                vb = static_cast<int32_t>(D[static_cast<long long>(gb) * p.ld + gr]);
+                if (DUAL) vb2 = static_cast<int32_t>(D2[static_cast<long long>(gb) * p.ld2 + gr]);
+            }
+        }
+        sA[r][a] = va;
+        sB[r][a] = vb;
+        if (DUAL) { sA2[r][a] = va2; sB2[r][a] = vb2; }
+    }
+}
+
+template <typename T, bool FULL, bool DUAL>
 __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
+    using Acc = typename K2Acc<T>::type;
     __shared__ __align__(16) int32_t sA[K2_RC][K2_TILE + 4];
     __shared__ __align__(16) int32_t sB[K2_RC][K2_TILE + 4];
+    __shared__ __align__(16) int32_t sA2[DUAL ? K2_RC : 1][K2_TILE + 4];
+    __shared__ __align__(16) int32_t sB2[DUAL ? K2_RC : 1][K2_TILE + 4];
     __shared__ PairKey s_red[K2_THREADS / 32];
     __shared__ PairKey s_last;
 
     int I, J;
     k2_decode_tile(blockIdx.x, p.tile_i0, p.n_tiles_j, I, J);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const T *D = reinterpret_cast<const T *>(p.D);
 
-    unsigned long long acc[4][4];
+    Acc acc[4][4], acc2[DUAL ? 4 : 1][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+        for (int b = 0; b < 4; ++b) {
+            acc[a][b] = 0;
+            if (DUAL) acc2[a][b] = 0;
+        }
 
     for (int r0 = 0; r0 < p.R; r0 += K2_RC) {
         // stage: D[(I*64 + a) * ld + r0 + r] -> sA[r][a]   (reads contiguous in global memory)
-        for (int e = threadIdx.x; e < K2_TILE * K2_RC; e += K2_THREADS) {
-            const int a = e / K2_RC, r = e % K2_RC;
-            const int ga = I * K2_TILE + a, gb = J * K2_TILE + a, gr = r0 + r;
-            int32_t va = 0, vb = 0;
-            if (gr < p.R) {
-                if (ga < p.A) va = static_cast<int32_t>(D[static_cast<long long>(ga) * p.ld + gr]);
-                if (gb < p.A) vb = static_cast<int32_t>(D[static_cast<long long>(gb) * p.ld + gr]);
-            }
-            sA[r][a] = va;
-            sB[r][a] = vb;
-        }
+        k2_stage<T, DUAL>(p, I, J, r0, sA, sB, sA2, sB2);
         __syncthreads();
-        uint32_t part[4][4];
+        uint32_t part[4][4], part2[DUAL ? 4 : 1][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) part[a][b] = 0;
+            for (int b = 0; b < 4; ++b) {
+                part[a][b] = 0;
+                if (DUAL) part2[a][b] = 0;
+            }
 #pragma unroll 8
         for (int r = 0; r < K2_RC; ++r) {
             const int4 va = *reinterpret_cast<const int4 *>(&sA[r][ty * 4]);
@@ -430,11 +463,24 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) part[a][b] += static_cast<uint32_t>(min(xa[a], xb[b]));
+            if (DUAL) {
+                const int4 wa = *reinterpret_cast<const int4 *>(&sA2[r][ty * 4]);
+                const int4 wb = *reinterpret_cast<const int4 *>(&sB2[r][tx * 4]);
+                const int ya[4] = {wa.x, wa.y, wa.z, wa.w};
+                const int yb[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) part2[a][b] += static_cast<uint32_t>(min(ya[a], yb[b]));
+            }
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] += part[a][b];
+            for (int b = 0; b < 4; ++b) {
+                acc[a][b] += part[a][b];
+                if (DUAL) acc2[a][b] += part2[a][b];
+            }
         __syncthreads();
     }
 
@@ -449,7 +495,8 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
             if (FULL) {
                 if (ok) p.S[static_cast<long long>(gi) * p.A + gj] = acc[a][b];
             } else {
-                keys[a * 4 + b].score = ok ? acc[a][b] : ~0ull;
+                keys[a * 4 + b].score = ok ? static_cast<unsigned long long>(acc[a][b]) : ~0ull;
+                keys[a * 4 + b].score2 = ok ? (DUAL ? static_cast<unsigned long long>(acc2[DUAL ? a : 0][b]) : 0ull) : ~0ull;
                 keys[a * 4 + b].ij = ok ? ((static_cast<unsigned long long>(gi) << 32) | static_cast<unsigned>(gj)) : ~0ull;
             }
         }
@@ -457,12 +504,12 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
 
     // k rounds of block-wide lexicographic argmin over keys strictly greater than the last one taken
     PairKey lastk;
-    lastk.score = 0; lastk.ij = 0;
+    lastk.score = 0; lastk.score2 = 0; lastk.ij = 0;
     bool have_last = false;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int round = 0; round < p.k; ++round) {
         PairKey best;
-        best.score = ~0ull; best.ij = ~0ull;
+        best.score = ~0ull; best.score2 = ~0ull; best.ij = ~0ull;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const bool gt = !have_last || key_less(lastk, keys[q]);
@@ -472,6 +519,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
         for (int off = 16; off > 0; off >>= 1) {
             PairKey o;
             o.score = __shfl_xor_sync(0xffffffffu, best.score, off);
+            o.score2 = __shfl_xor_sync(0xffffffffu, best.score2, off);
             o.ij = __shfl_xor_sync(0xffffffffu, best.ij, off);
             if (key_less(o, best)) best = o;
         }
@@ -490,17 +538,21 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pair_minsum(const K2Params p) {
     }
 }
 
-// c1[q] = #{r : D[i_q][r] <= D[j_q][r]} for the final records; one CTA per record
+// c1[q] = #{r : (D[i_q][r], D2[i_q][r]) <= (D[j_q][r], D2[j_q][r])} for the final records; one CTA per record
 template <typename T>
-__global__ void k2_count_c1(const T *__restrict__ D, long long ld, int R, const uint32_t *__restrict__ ij,
-                            uint32_t *__restrict__ c1) {
+__global__ void k2_count_c1(const T *__restrict__ D, long long ld, const T *__restrict__ D2, long long ld2, int R,
+                            const uint32_t *__restrict__ ij, uint32_t *__restrict__ c1) {
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const uint32_t i = ij[2 * blockIdx.x], j = ij[2 * blockIdx.x + 1];
     uint32_t cnt = 0;
-    for (int r = threadIdx.x; r < R; r += blockDim.x)
-        cnt += D[static_cast<long long>(i) * ld + r] <= D[static_cast<long long>(j) * ld + r];
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const T x = D[static_cast<long long>(i) * ld + r], y = D[static_cast<long long>(j) * ld + r];
+        bool le = x <= y;
+        if (D2 != nullptr && x == y) le = D2[static_cast<long long>(i) * ld2 + r] <= D2[static_cast<long long>(j) * ld2 + r];
+        cnt += le;
+    }
     for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
     if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, cnt);
     __syncthreads();

@@ -627,12 +627,21 @@ static sp_status k2_check(sp_ctx *ctx, const sp_dmatrix *d) {
     return SP_OK;
 }
 
-extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64_t i_begin, int64_t i_end, int k,
-                                         sp_pair_rec *out, int *n_out) {
+template <typename T>
+static void launch_k2_topk(const K2Params &prm, unsigned n_ctas, bool dual, cudaStream_t st) {
+    if (dual) k2_pair_minsum<T, false, true><<<n_ctas, K2_THREADS, 0, st>>>(prm);
+    else k2_pair_minsum<T, false, false><<<n_ctas, K2_THREADS, 0, st>>>(prm);
+}
+
+extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const sp_dmatrix *d2, int64_t i_begin,
+                                         int64_t i_end, int k, sp_pair_rec *out, int *n_out) {
     if (!ctx) return SP_ERR_INVALID;
     sp_status st = k2_check(ctx, d);
     if (st != SP_OK) return st;
+    if (d2 && (d2->nt != d->nt || d2->np != d->np || d2->elem_bits != d->elem_bits))
+        return fail(ctx, SP_ERR_INVALID, "K2: secondary matrix must have the geometry and element type of the primary");
     if (!out || !n_out || k < 1 || k > K2_MAXK) return fail(ctx, SP_ERR_INVALID, "K2: bad k / NULL output");
+    if (d->elem_bits == 16 && d->nt > 65536) return fail(ctx, SP_ERR_RANGE, "K2: more than 65536 reads need a 32-bit matrix");
     *n_out = 0;
     const int A = static_cast<int>(d->np);
     i_begin = std::max<int64_t>(i_begin, 0);
@@ -640,7 +649,8 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64
     if (i_begin >= i_end) return SP_OK;
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     K2Params prm;
-    prm.D = d->d; prm.ld = d->ld; prm.R = static_cast<int>(d->nt); prm.A = A;
+    prm.D = d->d; prm.ld = d->ld; prm.D2 = d2 ? d2->d : nullptr; prm.ld2 = d2 ? d2->ld : 0;
+    prm.R = static_cast<int>(d->nt); prm.A = A;
     prm.i_begin = static_cast<int>(i_begin); prm.i_end = static_cast<int>(i_end);
     prm.tile_i0 = prm.i_begin / K2_TILE;
     prm.n_tiles_j = (A + K2_TILE - 1) / K2_TILE;
@@ -651,8 +661,8 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64
     if (n_ctas > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "K2: too many tiles");
     SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&prm.cand), static_cast<size_t>(n_ctas) * k * sizeof(PairKey)));
     ev_begin(ctx, 1);
-    if (d->elem_bits == 16) k2_pair_minsum<uint16_t, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
-    else k2_pair_minsum<int32_t, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+    if (d->elem_bits == 16) launch_k2_topk<uint16_t>(prm, static_cast<unsigned>(n_ctas), d2 != nullptr, ctx->stream);
+    else launch_k2_topk<int32_t>(prm, static_cast<unsigned>(n_ctas), d2 != nullptr, ctx->stream);
     ev_end(ctx, 1);
     ++ctx->launches;
     std::vector<PairKey> cand(static_cast<size_t>(n_ctas) * k);
@@ -662,11 +672,15 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(prm.cand);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2: ") + cudaGetErrorString(e));
-    // merge of the per-tile lists: same (score, i, j) order, so any sharding gives the same answer
+    // merge of the per-tile lists: same (score, score2, i, j) order, so any sharding gives the same answer
+    auto less = [](const PairKey &a, const PairKey &b) {
+        if (a.score != b.score) return a.score < b.score;
+        if (a.score2 != b.score2) return a.score2 < b.score2;
+        return a.ij < b.ij;
+    };
     cand.erase(std::remove_if(cand.begin(), cand.end(), [](const PairKey &c) { return c.ij == ~0ull; }), cand.end());
     const size_t kk = std::min<size_t>(static_cast<size_t>(k), cand.size());
-    std::partial_sort(cand.begin(), cand.begin() + static_cast<std::ptrdiff_t>(kk), cand.end(),
-                      [](const PairKey &a, const PairKey &b) { return a.score < b.score || (a.score == b.score && a.ij < b.ij); });
+    std::partial_sort(cand.begin(), cand.begin() + static_cast<std::ptrdiff_t>(kk), cand.end(), less);
     if (kk == 0) return SP_OK;
     std::vector<uint32_t> ij(2 * kk), c1(kk);
     for (size_t q = 0; q < kk; ++q) {
@@ -679,9 +693,11 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64
     e = cudaMemcpyAsync(d_ij, ij.data(), ij.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         if (d->elem_bits == 16)
-            k2_count_c1<uint16_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, prm.R, d_ij, d_c1);
+            k2_count_c1<uint16_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(
+                static_cast<const uint16_t *>(d->d), d->ld, d2 ? static_cast<const uint16_t *>(d2->d) : nullptr, prm.ld2, prm.R, d_ij, d_c1);
         else
-            k2_count_c1<int32_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, prm.R, d_ij, d_c1);
+            k2_count_c1<int32_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(
+                static_cast<const int32_t *>(d->d), d->ld, d2 ? static_cast<const int32_t *>(d2->d) : nullptr, prm.ld2, prm.R, d_ij, d_c1);
         ++ctx->launches;
         e = cudaMemcpyAsync(c1.data(), d_c1, c1.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
     }
@@ -689,7 +705,8 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, int64
     cudaFree(d_ij); cudaFree(d_c1);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2 c1: ") + cudaGetErrorString(e));
     for (size_t q = 0; q < kk; ++q) {
-        out[q].score = cand[q].score; out[q].i = ij[2 * q]; out[q].j = ij[2 * q + 1]; out[q].c1 = c1[q]; out[q]._pad = 0;
+        out[q].score = cand[q].score; out[q].score2 = cand[q].score2;
+        out[q].i = ij[2 * q]; out[q].j = ij[2 * q + 1]; out[q].c1 = c1[q]; out[q]._pad = 0;
     }
     *n_out = static_cast<int>(kk);
     return SP_OK;
@@ -704,7 +721,8 @@ extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint6
     if (A == 0) return SP_OK;
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     K2Params prm;
-    prm.D = d->d; prm.ld = d->ld; prm.R = static_cast<int>(d->nt); prm.A = A;
+    prm.D = d->d; prm.ld = d->ld; prm.D2 = nullptr; prm.ld2 = 0; prm.R = static_cast<int>(d->nt); prm.A = A;
+    if (d->elem_bits == 16 && d->nt > 65536) return fail(ctx, SP_ERR_RANGE, "K2: more than 65536 reads need a 32-bit matrix");
     prm.i_begin = 0; prm.i_end = A; prm.tile_i0 = 0; prm.n_tiles_j = (A + K2_TILE - 1) / K2_TILE;
     prm.k = 0; prm.cand = nullptr;
     const long long n_ctas = static_cast<long long>(prm.n_tiles_j) * (prm.n_tiles_j + 1) / 2;
@@ -713,8 +731,8 @@ extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint6
     cudaError_t e = cudaMemsetAsync(prm.S, 0, bytes, ctx->stream);
     if (e == cudaSuccess) {
         ev_begin(ctx, 1);
-        if (d->elem_bits == 16) k2_pair_minsum<uint16_t, true><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
-        else k2_pair_minsum<int32_t, true><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+        if (d->elem_bits == 16) k2_pair_minsum<uint16_t, true, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
+        else k2_pair_minsum<int32_t, true, false><<<static_cast<unsigned>(n_ctas), K2_THREADS, 0, ctx->stream>>>(prm);
         ev_end(ctx, 1);
         ++ctx->launches;
         e = cudaGetLastError();
@@ -756,13 +774,14 @@ static sp_status upload_rows(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A
     return SP_OK;
 }
 
-extern "C" sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, int k,
-                                              sp_pair_rec *out, int *n_out) {
+extern "C" sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, const int32_t *D2, int64_t R, int64_t A,
+                                              int k, sp_pair_rec *out, int *n_out) {
     if (!ctx) return SP_ERR_INVALID;
-    sp_dmatrix *d = nullptr;
+    sp_dmatrix *d = nullptr, *d2 = nullptr;
     sp_status st = upload_rows(ctx, D, R, A, &d);
-    if (st == SP_OK) st = sp_pair_minsum_topk(ctx, d, 0, A, k, out, n_out);
-    sp_dmatrix_destroy(d);
+    if (st == SP_OK && D2) st = upload_rows(ctx, D2, R, A, &d2);
+    if (st == SP_OK) st = sp_pair_minsum_topk(ctx, d, d2, 0, A, k, out, n_out);
+    sp_dmatrix_destroy(d); sp_dmatrix_destroy(d2);
     return st;
 }
 

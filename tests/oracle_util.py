@@ -15,7 +15,7 @@ LIB = ORACLE_DIR / "libsp_oracle.so"
 
 
 class PairRec(C.Structure):
-    _fields_ = [("score", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32)]
+    _fields_ = [("score", C.c_uint64), ("score2", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32), ("pad", C.c_uint32)]
 
 
 def build_oracle(force: bool = False) -> Path:
@@ -46,7 +46,7 @@ class Oracle:
         L.sp_oracle_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.sp_oracle_pair_minsum_topk.restype = C.c_int
-        L.sp_oracle_pair_minsum_topk.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(PairRec)]
+        L.sp_oracle_pair_minsum_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(PairRec)]
         L.sp_oracle_pair_minsum_full.restype = None
         L.sp_oracle_pair_minsum_full.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.sp_oracle_num_threads.restype = C.c_int
@@ -73,11 +73,15 @@ class Oracle:
             0 if impl == "dp" else 1, nthreads, D.ctypes.data, E.ctypes.data if E is not None else None))
         return (D, E) if want_end_col else D
 
-    def pair_minsum_topk(self, D: np.ndarray, k: int, nthreads: int = 0):
+    def pair_minsum_topk(self, D: np.ndarray, k: int, nthreads: int = 0, D2=None):
         D = np.ascontiguousarray(D, dtype=np.int32)
+        D2 = np.ascontiguousarray(D2, dtype=np.int32) if D2 is not None else None
         recs = (PairRec * k)()
-        n = self.lib.sp_oracle_pair_minsum_topk(D.ctypes.data, D.shape[0], D.shape[1], k, nthreads, recs)
-        return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[:n]]
+        n = self.lib.sp_oracle_pair_minsum_topk(D.ctypes.data, D2.ctypes.data if D2 is not None else None,
+                                                D.shape[0], D.shape[1], k, nthreads, recs)
+        if D2 is None:
+            return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[:n]]
+        return [(int(r.score), int(r.score2), int(r.i), int(r.j), int(r.c1)) for r in recs[:n]]
 
     def pair_minsum_full(self, D: np.ndarray, nthreads: int = 0) -> np.ndarray:
         D = np.ascontiguousarray(D, dtype=np.int32)

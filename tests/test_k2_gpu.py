@@ -37,3 +37,25 @@ def test_device_pipeline_and_row_sharding(ctx, oracle):
         merged += ctx.pair_minsum_topk(dm, 16, lo, hi)
     merged.sort(key=lambda r: (r[0], r[1], r[2]))
     assert merged[:16] == want
+
+
+@pytest.mark.parametrize("R,A", [(5, 7), (70, 130), (33, 65)])
+def test_topk_dual_matrix(ctx, oracle, R, A):
+    """(primary, secondary) lexicographic key = (cDNA, DNA) order of HlaMappingScore
+    (src/hla/mapping.rs:111-117) carried to pair sums; many primary ties force the secondary."""
+    rng = np.random.default_rng(R * 31 + A)
+    D1 = rng.integers(0, 4, size=(R, A)).astype(np.int32)
+    D2 = rng.integers(0, 60, size=(R, A)).astype(np.int32)
+    for k in (1, 16, 64):
+        assert ctx.pair_minsum_topk(D1, k, d2=D2) == oracle.pair_minsum_topk(D1, k, D2=D2)
+
+
+def test_dual_device_matrices(ctx, oracle):
+    alleles, reads, _, cdna = synth.hla_gene(11, "HLA-A", n_alleles=130, n_reads=30, with_cdna=True)
+    rng = np.random.default_rng(4)
+    ctargets = [cdna[int(rng.integers(0, len(cdna)))] for _ in reads]
+    T, Tc = ctx.targets(reads), ctx.targets(ctargets)
+    P, Pc = ctx.patterns(alleles), ctx.patterns(cdna)
+    dd, dc = ctx.score_device(T, P, elem_bits=16), ctx.score_device(Tc, Pc, elem_bits=16)
+    got = ctx.pair_minsum_topk(dc, 12, d2=dd)
+    assert got == oracle.pair_minsum_topk(dc.to_host(), 12, D2=dd.to_host())
