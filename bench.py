@@ -1,0 +1,365 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 scoring path (contract: see the task statement / DESIGN.md §6).
+
+Metric (BASELINE.json): HLA read-allele GCUPS.  Workload: BASELINE.json configs[1], "HLA-A/HLA-B WGS 30x:
+~2k synthetic HiFi reads x full IMGT/HLA allele set" (SURVEY.md §8(d).2): 2,048 reads per GPU against
+12,451 DNA + 19,629 cDNA alleles.  One step = K1(DNA) + K1(cDNA) + K2 (cDNA,DNA)-lexicographic pair
+scoring per gene + top-k merge.  N > 1: reads = 2,048 x N (broadcast), alleles sharded N ways (weak
+scaling), D shards all-gathered over NCCL for K2, per-shard top-k merged.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "hla_read_allele_gcups"
+UNIT = "GCUPS"
+READS_PER_GPU = 2048
+INT_OPS_PER_CELL = 23.0 / 64.0  # Hyyro block step = 23 INT32-pipe ops per 64 cells
+TOPK = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("SP_BENCH_SCALE", "1.0")),
+                    help="debug only: shrink the allele set (a scaled run is NOT a valid bench number)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_workload(n_gpus: int, scale: float):
+    from pb_starphase_b200 import synth
+
+    genes = synth.hla_wgs_workload(synth.DEFAULT_SEED, READS_PER_GPU * n_gpus, scale)
+    A, B = genes["HLA-A"], genes["HLA-B"]
+    w = dict(
+        dna=A["dna"] + B["dna"], cdna=A["cdna"] + B["cdna"],
+        reads=A["reads"] + B["reads"], ctargets=A["ctargets"] + B["ctargets"],
+        # per gene: (dna row0, cdna row0, n alleles with DNA, read col0, n reads)
+        gene_views={
+            "HLA-A": (0, 0, len(A["dna"]), 0, len(A["reads"])),
+            "HLA-B": (len(A["dna"]), len(A["cdna"]), len(B["dna"]), len(A["reads"]), len(B["reads"])),
+        },
+    )
+    w["cells_dna"] = sum(map(len, w["dna"])) * sum(map(len, w["reads"]))
+    w["cells_cdna"] = sum(map(len, w["cdna"])) * sum(map(len, w["ctargets"]))
+    return w
+
+
+def shard_range(n: int, rank: int, world: int):
+    s = (n + world - 1) // world
+    return min(rank * s, n), min((rank + 1) * s, n), s
+
+
+def triangle_rows(n: int, rank: int, world: int):
+    """Row range [lo, hi) of an upper-triangular pair space with ~equal area per rank."""
+    def edge(b):
+        return int(round(n * (1.0 - (1.0 - b / world) ** 0.5)))
+    return edge(rank), (n if rank == world - 1 else edge(rank + 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (oracle port; the reference binary cannot be built here -- DESIGN.md §3)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(w, budget_s: float, steps: int = 1):
+    """Times the oracle's 64-bit Myers on all host threads on a bounded sample of the same workload."""
+    import oracle_util
+
+    orc = oracle_util.Oracle()
+    threads = orc.num_threads()
+    rng = np.random.default_rng(1)
+    reads, ctargets = w["reads"], w["ctargets"]
+    ridx = rng.choice(len(reads), size=min(8, len(reads)), replace=False)
+    # calibrate on a tiny slice, then size the sample for ~budget_s of wall time per step
+    aidx = rng.choice(len(w["dna"]), size=min(32, len(w["dna"])), replace=False)
+    t0 = time.perf_counter()
+    orc.score_batch([reads[i] for i in ridx], [w["dna"][i] for i in aidx])
+    rate = orc.last_cells / max(time.perf_counter() - t0, 1e-6)
+    want_cells = rate * budget_s
+    per_allele = float(np.mean([len(reads[i]) for i in ridx])) * len(ridx) * float(np.mean([len(a) for a in w["dna"]]))
+    n_alleles = int(max(32, min(len(w["dna"]), want_cells * 0.85 / per_allele)))
+    aidx = rng.choice(len(w["dna"]), size=n_alleles, replace=False)
+    cidx = rng.choice(len(w["cdna"]), size=min(len(w["cdna"]), max(32, int(n_alleles * 1.5))), replace=False)
+    times, cells = [], 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.score_batch([reads[i] for i in ridx], [w["dna"][i] for i in aidx])
+        c = orc.last_cells
+        orc.score_batch([ctargets[i] for i in ridx], [w["cdna"][i] for i in cidx])
+        c += orc.last_cells
+        times.append(time.perf_counter() - t0)
+        cells = c
+    sample = f"{len(ridx)} reads x {n_alleles} DNA + {len(cidx)} cDNA alleles of the same workload ({cells / 1e9:.1f} Gcells/step)"
+    return dict(gcups=cells / float(np.mean(times)) / 1e9, cores=threads, sample=sample, ms_per_step=float(np.mean(times)) * 1e3)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = build_workload(args.gpus, args.scale)
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(w, 1.0)
+    res = cpu_sample(w, max(3.0, args.cpu_seconds / max(args.steps, 1)), steps=args.steps)
+    line = dict(metric=METRIC, value=res["gcups"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload_name(args.gpus), note="oracle port of the reference's CPU path (64-bit Myers, "
+                            "OpenMP); the Rust reference + minimap2 cannot be built here"),
+                cpu_baseline=dict(value=res["gcups"], unit=UNIT, cores=res["cores"], kind="port", sample=res["sample"]),
+                e2e=dict(value=res["gcups"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(n):
+    return f"hla_wgs30x: {READS_PER_GPU * n} reads x 12,451 DNA + 19,629 cDNA alleles (BASELINE configs[1]" + (")" if n == 1 else f", reads x{n}, alleles sharded {n} ways)")
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pb_starphase_b200 as sp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the scoring path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = max(args.gpus, world)
+    w = build_workload(n, args.scale)
+
+    stream = torch.cuda.current_stream()
+    ctx = sp.Context(local_rank, stream=stream.cuda_stream)
+    int_peak = ctx.int_peak(0)
+
+    # ---- resident database: this rank's allele shards (prepared once, like HlaRealigner::new) ----
+    d_lo, d_hi, d_S = shard_range(len(w["dna"]), rank, world)
+    c_lo, c_hi, c_S = shard_range(len(w["cdna"]), rank, world)
+    P_dna = ctx.patterns(w["dna"][d_lo:d_hi])
+    P_cdna = ctx.patterns(w["cdna"][c_lo:c_hi])
+    R = len(w["reads"])
+    ld = (R + 63) // 64 * 64
+    cells_local = (sum(map(len, w["dna"][d_lo:d_hi])) * sum(map(len, w["reads"]))
+                   + sum(map(len, w["cdna"][c_lo:c_hi])) * sum(map(len, w["ctargets"])))
+    cells_dna_local = sum(map(len, w["dna"][d_lo:d_hi])) * sum(map(len, w["reads"]))
+    cells_total = w["cells_dna"] + w["cells_cdna"]
+
+    # the read set is generated on rank 0 and broadcast (it is identical by construction; this is the real exchange)
+    reads_pack = sp.binding.pack_sequences(w["reads"])
+    ct_pack = sp.binding.pack_sequences(w["ctargets"])
+    if world > 1:
+        for arr in (reads_pack[0], ct_pack[0]):
+            t = torch.from_numpy(arr).to(dev)
+            dist.broadcast(t, 0)
+            arr[:] = t.cpu().numpy()
+
+    # gather buffers: [world * S][ld] u16, this rank scores straight into its slot
+    full_dna = torch.zeros((world * d_S, ld), dtype=torch.int16, device=dev)
+    full_cdna = torch.zeros((world * c_S, ld), dtype=torch.int16, device=dev)
+    M_dna = ctx.wrap_dmatrix(full_dna.data_ptr(), R, world * d_S, ld, 16)
+    M_cdna = ctx.wrap_dmatrix(full_cdna.data_ptr(), R, world * c_S, ld, 16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    views = {}
+    for gene, (drow, crow, na, col0, nr) in w["gene_views"].items():
+        vd = ctx.wrap_dmatrix(full_dna.data_ptr() + 2 * (drow * ld + col0), nr, na, ld, 16)
+        vc = ctx.wrap_dmatrix(full_cdna.data_ptr() + 2 * (crow * ld + col0), nr, na, ld, 16)
+        views[gene] = (vc, vd, triangle_rows(na, rank, world))
+
+    k1_ms = []
+
+    def device_step(T_dna, T_cdna):
+        ctx.score_into(T_dna, P_dna, M_dna, rank * d_S)
+        k1_ms.append(ctx.last_kernel_ms(0))
+        ctx.score_into(T_cdna, P_cdna, M_cdna, rank * c_S)
+        if world > 1:
+            dist.all_gather_into_tensor(full_dna, full_dna[rank * d_S:(rank + 1) * d_S])
+            dist.all_gather_into_tensor(full_cdna, full_cdna[rank * c_S:(rank + 1) * c_S])
+        out = {}
+        for gene, (vc, vd, (lo, hi)) in views.items():
+            recs = ctx.pair_minsum_topk(vc, TOPK, lo, hi, d2=vd)
+            if world > 1:
+                buf = torch.full((TOPK, 5), -1, dtype=torch.int64, device=dev)
+                if recs:
+                    buf[:len(recs)] = torch.tensor(recs, dtype=torch.int64, device=dev)
+                allb = torch.empty((world * TOPK, 5), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allb, buf)
+                rows = [tuple(int(x) for x in r) for r in allb.cpu().tolist() if r[2] >= 0]
+                rows.sort(key=lambda r: (r[0], r[1], r[2], r[3]))
+                recs = rows[:TOPK]
+            out[gene] = recs
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- `value`: inputs resident in HBM ----
+    T_dna, T_cdna = ctx.targets(reads_pack), ctx.targets(ct_pack)
+    result = None
+    for _ in range(args.warmup):
+        result = device_step(T_dna, T_cdna)
+    k1_ms.clear()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations (256 MB > 126 MB L2)
+        result = device_step(T_dna, T_cdna)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    k1_avg_ms = float(np.mean(k1_ms))
+
+    # ---- `e2e`: host buffers in, host results out, through the C-ABI calls a host program makes ----
+    def e2e_step():
+        Td, Tc = ctx.targets(reads_pack), ctx.targets(ct_pack)  # H2D + pack
+        res = device_step(Td, Tc)
+        own_d = ctx.wrap_dmatrix(full_dna.data_ptr() + 2 * rank * d_S * ld, R, d_hi - d_lo, ld, 16)
+        own_c = ctx.wrap_dmatrix(full_cdna.data_ptr() + 2 * rank * c_S * ld, R, c_hi - c_lo, ld, 16)
+        Dd, Dc = own_d.to_host(), own_c.to_host()  # D2H of this rank's int32 distance matrices
+        own_d.close(); own_c.close(); Td.close(); Tc.close()
+        return res, Dd.nbytes + Dc.nbytes
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        res_e2e, d2h = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert res_e2e == result, "e2e and device-resident runs disagree"
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s, k1_avg_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, k1_avg_ms = (float(x) for x in t.cpu())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        value = cells_total * args.steps / (ms_total * 1e-3) / 1e9
+        e2e_val = cells_total * args.steps / e2e_s / 1e9
+        achieved = INT_OPS_PER_CELL * cells_dna_local / (k1_avg_ms * 1e-3)
+        hbm_bytes = (sum(map(len, w["reads"])) + P_dna.padded_rows * 0.75 + 2.0 * (d_hi - d_lo) * R)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        cpu = cpu_sample(w, args.cpu_seconds) if world == 1 or True else None
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="u32", data="synthetic",
+            config=dict(workload=workload_name(world), seed=20251106, l2="flushed between timed steps (256 MB write)",
+                        step="K1 DNA + K1 cDNA + K2 (cDNA,DNA) pair top-%d per gene" % TOPK,
+                        scale=args.scale, best_pairs={g: (r[0][:4] if r else None) for g, r in result.items()}),
+            clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"]),
+            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(reads_pack[0].nbytes + ct_pack[0].nbytes),
+                     d2h_bytes_per_step=int(d2h)),
+            gpu_launches=int(launches),
+            roofline=dict(bound="int_alu", kernel="k1_infix (DNA launch)", achieved=achieved / 1e12, peak=int_peak / 1e12,
+                          unit="Tops/s (INT32 ALU-pipe lane-ops; 23/64 per cell)", frac=achieved / int_peak,
+                          peak_source="measured live: dependent-free LOP3 loop (sp_int_peak kind 0)",
+                          k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12, traffic=None,
+                          hbm=dict(achieved=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                                   frac=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9 / hbm_peak,
+                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback")),
+            cpu_baseline=dict(value=cpu["gcups"], unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"]),
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -123,6 +123,11 @@ int64_t sp_targets_total_len(const sp_targets *t);
  * want_end_col != 0 also records the smallest end column of a best placement. */
 sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t, const sp_patterns *p,
                           int elem_bits, int want_end_col, sp_dmatrix **out);
+/* Same, but writes rows [pattern_row0, pattern_row0 + n_patterns) of a caller-provided matrix
+ * (e.g. the slot of this rank's allele shard inside an NCCL all-gather buffer wrapped with
+ * sp_dmatrix_wrap).  The destination needs n_targets <= its ld / n_targets. */
+sp_status sp_score_into(sp_ctx *ctx, const sp_targets *t, const sp_patterns *p, sp_dmatrix *dst,
+                        int64_t pattern_row0);
 void sp_dmatrix_destroy(sp_dmatrix *d);
 /* Copy to host as int32 D[t * n_patterns + p] (row = target), optionally end columns. */
 sp_status sp_dmatrix_to_host(sp_ctx *ctx, const sp_dmatrix *d, int32_t *D, int32_t *end_col);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sp_targets_count": (C.c_int64, [_P]),
     "sp_targets_total_len": (C.c_int64, [_P]),
     "sp_score_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "sp_score_into": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "sp_dmatrix_destroy": (None, [_P]),
     "sp_dmatrix_to_host": (C.c_int, [_P, _P, _P, _P]),
     "sp_dmatrix_device_ptr": (_P, [_P]),
@@ -150,6 +151,9 @@ class Context:
         h = _P()
         self._check(self._lib.sp_score_device(self._h, targets._h, patterns._h, elem_bits, int(want_end_col), C.byref(h)))
         return DMatrix(self, h, targets.n, patterns.n, want_end_col)
+
+    def score_into(self, targets: "TargetSet", patterns: "PatternSet", dst: "DMatrix", pattern_row0: int = 0):
+        self._check(self._lib.sp_score_into(self._h, targets._h, patterns._h, dst._h, pattern_row0))
 
     def score_batch(self, targets, patterns, mode: int = SP_INFIX, want_end_col: bool = False):
         """Host buffers in, host int32 matrix out: D[t, p] (and end columns).  One C-ABI call."""

@@ -479,6 +479,44 @@ static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t sme
     }
 }
 
+// runs K1 for (t, p) writing D[(row0 + pattern) * ld + text] into caller-provided device memory
+static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *out, int32_t *out_end, int64_t ld,
+                        int elem_bits, int64_t row0) {
+    if (t->n == 0 || p->n == 0 || p->total_len == 0) return SP_OK;
+    // tile capacity: 32 KB of text by default, grown for long texts, shrunk when the work list would be too short
+    const int U = p->U;
+    const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
+    const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
+    int64_t tc = 4096;
+    const int64_t want_items = 4ll * ctx->num_sms;
+    if (static_cast<int64_t>(p->n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
+        const int64_t want_tiles = (want_items + p->n_groups - 1) / p->n_groups;
+        tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
+    }
+    tc = std::max<int64_t>(tc, t->max_nch);
+    tc = (tc + 1) / 2 * 2;
+    if (tc > max_tc)
+        return fail(ctx, SP_ERR_TOO_LONG,
+                    "text of " + std::to_string(static_cast<long long>(t->max_nch) * K1_CHUNK) +
+                        " columns exceeds the shared-memory tile budget (" + std::to_string(max_tc * K1_CHUNK) + ")");
+    const TextPack *pk = nullptr;
+    sp_status st = get_text_pack(ctx, t, static_cast<int>(tc), &pk);
+    if (st != SP_OK) return st;
+
+    K1Params prm;
+    prm.blobs = p->d_blobs; prm.text = pk->d_text; prm.tile_chunk_off = pk->d_tile_off; prm.tile_text0 = pk->d_tile_text0;
+    prm.out = static_cast<char *>(out) + static_cast<size_t>(row0 * ld) * (elem_bits / 8);
+    prm.out_end = out_end ? out_end + row0 * ld : nullptr;
+    prm.ld = ld;
+    prm.n_groups = p->n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
+    prm.prefix_mode = p->mode == SP_PREFIX;
+    const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
+    if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
+    const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
+    return out_end ? dispatch_k1<true>(ctx, U, prm, smem, static_cast<int>(n_items64))
+                   : dispatch_k1<false>(ctx, U, prm, smem, static_cast<int>(n_items64));
+}
+
 extern "C" sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t_in, const sp_patterns *p, int elem_bits,
                                      int want_end_col, sp_dmatrix **out) {
     if (!ctx) return SP_ERR_INVALID;
@@ -504,43 +542,23 @@ extern "C" sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t_in, const 
         return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA,
                     std::string("distance matrix allocation: ") + cudaGetErrorString(e));
     }
-    if (t->n == 0 || p->n == 0 || p->total_len == 0) { *out = d; return SP_OK; }
-
-    // tile capacity: 32 KB of text by default, grown for long texts, shrunk when the work list would be too short
-    const int U = p->U;
-    const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
-    const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
-    int64_t tc = 4096;
-    const int64_t want_items = 4ll * ctx->num_sms;
-    if (static_cast<int64_t>(p->n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
-        const int64_t want_tiles = (want_items + p->n_groups - 1) / p->n_groups;
-        tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
-    }
-    tc = std::max<int64_t>(tc, t->max_nch);
-    tc = (tc + 1) / 2 * 2;
-    if (tc > max_tc) {
-        sp_dmatrix_destroy(d);
-        return fail(ctx, SP_ERR_TOO_LONG,
-                    "text of " + std::to_string(static_cast<long long>(t->max_nch) * K1_CHUNK) +
-                        " columns exceeds the shared-memory tile budget (" + std::to_string(max_tc * K1_CHUNK) + ")");
-    }
-    const TextPack *pk = nullptr;
-    sp_status st = get_text_pack(ctx, t, static_cast<int>(tc), &pk);
-    if (st != SP_OK) { sp_dmatrix_destroy(d); return st; }
-
-    K1Params prm;
-    prm.blobs = p->d_blobs; prm.text = pk->d_text; prm.tile_chunk_off = pk->d_tile_off; prm.tile_text0 = pk->d_tile_text0;
-    prm.out = d->d; prm.out_end = d->d_end; prm.ld = d->ld;
-    prm.n_groups = p->n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
-    prm.prefix_mode = p->mode == SP_PREFIX;
-    const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
-    if (n_items64 > 0x7FFFFFFFll) { sp_dmatrix_destroy(d); return fail(ctx, SP_ERR_RANGE, "work list too large"); }
-    const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
-    st = want_end_col ? dispatch_k1<true>(ctx, U, prm, smem, static_cast<int>(n_items64))
-                      : dispatch_k1<false>(ctx, U, prm, smem, static_cast<int>(n_items64));
+    sp_status st = run_k1(ctx, t, p, d->d, d->d_end, d->ld, elem_bits, 0);
     if (st != SP_OK) { sp_dmatrix_destroy(d); return st; }
     *out = d;
     return SP_OK;
+}
+
+extern "C" sp_status sp_score_into(sp_ctx *ctx, const sp_targets *t_in, const sp_patterns *p, sp_dmatrix *dst,
+                                   int64_t pattern_row0) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!t_in || !p || !dst) return fail(ctx, SP_ERR_INVALID, "sp_score_into: NULL argument");
+    if (pattern_row0 < 0 || pattern_row0 + p->n > dst->np || t_in->n > dst->nt || t_in->n > dst->ld)
+        return fail(ctx, SP_ERR_INVALID, "sp_score_into: destination matrix is too small");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    // rows of empty patterns are defined as distance 0
+    SP_CUDA(ctx, cudaMemsetAsync(static_cast<char *>(dst->d) + static_cast<size_t>(pattern_row0 * dst->ld) * (dst->elem_bits / 8),
+                                 0, static_cast<size_t>(p->n * dst->ld) * (dst->elem_bits / 8), ctx->stream));
+    return run_k1(ctx, const_cast<sp_targets *>(t_in), p, dst->d, nullptr, dst->ld, dst->elem_bits, pattern_row0);
 }
 
 extern "C" void sp_dmatrix_destroy(sp_dmatrix *d) {

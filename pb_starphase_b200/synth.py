@@ -99,3 +99,27 @@ def hla_gene(seed: int, gene: str, n_alleles: int | None = None, n_reads: int = 
     nc = shape["n_cdna"] if n_alleles is None else n_alleles
     cdna = allele_tree(rng, nc, shape["cdna"], 534, 1208, partial_frac=0.05)
     return alleles, reads, src, cdna
+
+
+def hla_wgs_workload(seed: int = DEFAULT_SEED, n_reads: int = 2048, scale: float = 1.0):
+    """BASELINE.json configs[1] ("HLA-A/HLA-B WGS 30x: ~2k synthetic HiFi reads x full IMGT/HLA allele set"),
+    SURVEY.md §8(d).2.  Per gene: DNA alleles, cDNA alleles (the first n_dna of them belong to the DNA
+    alleles in order, the rest are cDNA-only entries), reads drawn from that gene's DNA alleles and a
+    cDNA target per read (its source allele's cDNA + errors + 50 bp flanks, the stand-in for splice_read,
+    src/hla/caller.rs:1518-1576).  `scale` shrinks the allele counts for tests / CPU samples."""
+    genes = {}
+    per_gene_reads = n_reads // 2
+    for gi, gene in enumerate(("HLA-A", "HLA-B")):
+        shape = GENE_SHAPES[gene]
+        rng = np.random.default_rng([seed, gi, 17])
+        n_dna = max(2, int(round(shape["n_dna"] * scale)))
+        n_cdna = max(n_dna, int(round(shape["n_cdna"] * scale)))
+        dna = allele_tree(rng, n_dna, shape["root"], shape["lo"], shape["hi"])
+        cdna = allele_tree(rng, n_cdna, shape["cdna"], 534, 1208, partial_frac=0.05)
+        reads, src = hifi_reads(rng, dna, per_gene_reads if gi == 0 else n_reads - per_gene_reads)
+        ctargets = []  # cDNA target k belongs to read k
+        for s in src:
+            one, _ = hifi_reads(rng, [cdna[int(s)]], 1, flank=50, lo=0, hi=1400)
+            ctargets.append(one[0])
+        genes[gene] = dict(dna=dna, cdna=cdna, reads=reads, ctargets=ctargets, src=src)
+    return genes
