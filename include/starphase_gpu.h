@@ -162,8 +162,9 @@ sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int
 
 /* ---- misc -------------------------------------------------------------------------------- */
 /* Integer-ALU microbenchmark used for the roofline denominator: runs a
- * dependent-free LOP3/IADD3 (kind 0), IMAD (kind 1) or mixed (kind 2) loop on every SM and
- * returns achieved 32-bit lane-ops per second. */
+ * dependent-free loop on every SM and returns achieved 32-bit lane-ops per second.
+ * kind: 0 = LOP3 (ALU pipe), 1 = IMAD (FMA pipe), 2 = LOP3 + IMAD alternating, 3 = IADD,
+ *       4 = IMAD.HI (FMA pipe), 5 = LOP3 + IMAD.HI alternating. */
 sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s);
 const char *sp_version(void);
 

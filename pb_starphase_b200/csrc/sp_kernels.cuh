@@ -41,6 +41,7 @@ struct K1Params {
     int n_groups, n_tiles;
     int out16;
     int prefix_mode;                // SP_PREFIX: top row delta +1
+    uint32_t one, m1;               // +1 and -1 (0xFFFFFFFF), passed at run time so `x * one + y` stays an IMAD (FMA pipe)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -102,24 +103,41 @@ __device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)
     }
 }
 
+// K1 inner step, "arithmetic form".
+// The ALU pipe (LOP3 / IADD3 / SHF: 64 lanes/clk/SM) bounds this kernel while the FMA pipe idles
+// (profiles/r01_k1_ncu_full.txt: alu 98 %, fma 2 %), and a full-rate IMAD issues for free beside a
+// saturated ALU pipe (profiles/r01_pipe_bench.txt: 8 LOP3 = 16.1 cycles, 8 LOP3 + 8 IMAD = 16.3).
+// Four of Myers' boolean operations are therefore computed as integer add/sub on the FMA pipe, using
+// disjointness / subset facts of the delta vectors (Hyyro's D0 form; npv = ~Pv is the stored state):
+//     nG  = ~(D0 | Pv)            LOP3        G' = D0 | Phs                 LOP3
+//     Ph  = Mv | nG   = Mv + nG   (Mv is a subset of D0)
+//     Mh  = Pv & D0   = D0 + Pv - (D0 | Pv) = D0 - npv + nG
+//     Mv' = Phs & D0  = D0 + Phs - G'
+//     ~Pv' = ~(Mhs | ~G') = G' - Mhs          (Mhs is a subset of D0: a -1 step to the left forces a zero diagonal)
+// leaving per 32-row word 5 LOP3 + 1 IADD3.X + 2 SHF on the ALU pipe (was 7 + 1 + 2) and 6 IMAD on the
+// FMA pipe.  The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
+// The Myers add (Eq & Pv) + Pv becomes t - npv - 1 (borrow chain seeded with 1, SubChain1).
 template <int U, bool TRACK_END>
-__device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t code, uint32_t (&pv)[U],
-                                            uint32_t (&mv)[U], uint32_t &X, uint32_t &Y, uint32_t &cph,
-                                            uint32_t &cmh, int &score, int &best, int &col, int &best_col) {
+__device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t code, uint32_t one, uint32_t m1,
+                                            uint32_t (&npv)[U], uint32_t (&mv)[U], uint32_t &X, uint32_t &Y,
+                                            uint32_t &cph, uint32_t &cmh, int &score, int &best, int &col,
+                                            int &best_col) {
     uint32_t eq[U], xv[U], t[U], sum[U];
     load_row<U>(peq_lane + code * (32 * U), eq);
+    eq[0] |= (Y >> 31);  // hin < 0 (Hyyro): the row above already paid for this column
 #pragma unroll
     for (int u = 0; u < U; ++u) xv[u] = eq[u] | mv[u];
-    eq[0] |= (Y >> 31);  // hin < 0
 #pragma unroll
-    for (int u = 0; u < U; ++u) t[u] = eq[u] & pv[u];
-    AddChain<U>::run(sum, t, pv);
-    uint32_t ph[U], mh[U];
+    for (int u = 0; u < U; ++u) t[u] = eq[u] & ~npv[u];
+    SubChain1<U>::run(sum, t, npv);
+    uint32_t ph[U], mh[U], d0[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        uint32_t xh = (sum[u] ^ pv[u]) | eq[u];
-        ph[u] = mv[u] | ~(xh | pv[u]);
-        mh[u] = pv[u] & xh;
+        d0[u] = ~(sum[u] ^ npv[u]) | xv[u];
+        const uint32_t a1 = npv[u] * m1 + d0[u];   // D0 - npv          (IMAD)
+        const uint32_t ng = ~d0[u] & npv[u];       // ~(D0 | Pv)        (LOP3)
+        mh[u] = ng * one + a1;                     //                   (IMAD)
+        ph[u] = ng * one + mv[u];                  //                   (IMAD)
     }
     // horizontal delta of the lane's last row: carry for the next lane, score for a last lane
     cph = __funnelshift_l(ph[U - 1], cph, 1);
@@ -132,17 +150,13 @@ __device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t c
         best = min(best, score);
     }
 #pragma unroll
-    for (int u = U - 1; u >= 1; --u) {
-        uint32_t phs = __funnelshift_l(ph[u - 1], ph[u], 1);
-        uint32_t mhs = __funnelshift_l(mh[u - 1], mh[u], 1);
-        pv[u] = mhs | ~(xv[u] | phs);
-        mv[u] = phs & xv[u];
-    }
-    {
-        uint32_t phs = __funnelshift_l(X, ph[0], 1);
-        uint32_t mhs = __funnelshift_l(Y, mh[0], 1);
-        pv[0] = mhs | ~(xv[0] | phs);
-        mv[0] = phs & xv[0];
+    for (int u = U - 1; u >= 0; --u) {
+        const uint32_t phs = __funnelshift_l(u ? ph[u - 1] : X, ph[u], 1);
+        const uint32_t mhs = __funnelshift_l(u ? mh[u - 1] : Y, mh[u], 1);
+        const uint32_t b1 = phs * one + d0[u];     // D0 + Phs          (IMAD)
+        const uint32_t g = d0[u] | phs;            //                   (LOP3)
+        mv[u] = g * m1 + b1;                       // Phs & D0          (IMAD)
+        npv[u] = mhs * m1 + g;                     // ~Pv'              (IMAD)
     }
     X <<= 1;
     Y <<= 1;
@@ -161,10 +175,10 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
     const uint32_t *peq_lane = blob + lane * V;
     const uint32_t cin_first = p.prefix_mode ? 0x00FFu : 0u;
 
-    uint32_t pv[U], mv[U];
-    load_row<U>(peq_lane + 5 * (32 * U), pv);
+    uint32_t npv[U], mv[U];  // ~Pv, Mv
+    load_row<U>(peq_lane + 5 * (32 * U), npv);
 #pragma unroll
-    for (int u = 0; u < U; ++u) mv[u] = 0;
+    for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
     int score = m, best = m, col = 0, best_col = 0;
     uint32_t carry_out = 0;
     int tcount = 0;
@@ -182,7 +196,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
             for (int c = 0; c < K1_CHUNK; ++c) {
                 const uint32_t word = (c < 4) ? w.x : w.y;
                 const uint32_t code = (word >> (8 * (c & 3))) & (c == 7 ? 0x7Fu : 0xFFu);
-                column_step<U, TRACK_END>(peq_lane, code, pv, mv, X, Y, cph, cmh, score, best, col, best_col);
+                column_step<U, TRACK_END>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
             }
             carry_out = cph | (cmh << 8);
             if (static_cast<int>(w.y) < 0) {  // last chunk of a text: emit + reset
@@ -193,9 +207,9 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
                     if (TRACK_END) p.out_end[o] = best_col;
                 }
                 ++tcount;
-                load_row<U>(peq_lane + 5 * (32 * U), pv);
+                load_row<U>(peq_lane + 5 * (32 * U), npv);
 #pragma unroll
-                for (int u = 0; u < U; ++u) mv[u] = 0;
+                for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
                 score = m; best = m; col = 0; best_col = 0;
             }
         }
@@ -579,8 +593,13 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters)
                 } else if (KIND == 2) {
                     if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
                     else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
-                } else {
+                } else if (KIND == 3) {
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                } else if (KIND == 4) {
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else {
+                    if (i & 1) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
                 }
             }
         }

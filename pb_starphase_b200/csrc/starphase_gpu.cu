@@ -510,6 +510,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
     prm.ld = ld;
     prm.n_groups = p->n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
     prm.prefix_mode = p->mode == SP_PREFIX;
+    prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
     const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
     if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
     const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
@@ -817,7 +818,7 @@ extern "C" sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int
 // ------------------------------------------------------------------------------------------
 extern "C" sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s) {
     if (!ctx) return SP_ERR_INVALID;
-    if (!ops_per_s || kind < 0 || kind > 3) return fail(ctx, SP_ERR_INVALID, "sp_int_peak: bad argument");
+    if (!ops_per_s || kind < 0 || kind > 5) return fail(ctx, SP_ERR_INVALID, "sp_int_peak: bad argument");
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     const int grid = ctx->num_sms * 8, iters = 8192;
     uint32_t *d_out = nullptr;
@@ -831,7 +832,9 @@ extern "C" sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s) {
             case 0: int_peak_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
             case 1: int_peak_kernel<1><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
             case 2: int_peak_kernel<2><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
-            default: int_peak_kernel<3><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            case 3: int_peak_kernel<3><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            case 4: int_peak_kernel<4><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
+            default: int_peak_kernel<5><<<grid, 256, 0, ctx->stream>>>(d_out, iters); break;
         }
         cudaEventRecord(b, ctx->stream);
         ++ctx->launches;

@@ -14,7 +14,7 @@ from pb_starphase_b200 import synth
 
 out = {}
 ctx = sp.Context(0)
-for kind, name in enumerate(["lop3", "imad", "lop3+imad", "iadd"]):
+for kind, name in enumerate(["lop3", "imad", "lop3+imad", "iadd", "imadhi", "lop3+imadhi"]):
     out[f"int_peak_{name}_Tops"] = ctx.int_peak(kind) / 1e12
 print(json.dumps(out), flush=True)
 
