@@ -111,6 +111,12 @@ int64_t sp_patterns_total_len(const sp_patterns *p);
 /* rows the packed layout really computes per text column (>= total_len; padding included) */
 int64_t sp_patterns_padded_rows(const sp_patterns *p);
 
+/* Host-only (no device touched): how sp_patterns_create would split patterns of the given lengths into
+ * lane-width classes (each class = one K1 launch; a warp of width U holds 32 lanes x U words x 32 rows).
+ * Outputs are arrays of max_classes entries; padded_rows = rows the layout computes per text column. */
+sp_status sp_plan_lane_classes(const int64_t *lens, int64_t n, int max_classes, int *n_classes, int *widths,
+                               int64_t *n_patterns, int64_t *n_warps, int64_t *padded_rows);
+
 /* Upload + pack a text set (reads / consensus sequences) into tile streams. */
 sp_status sp_targets_create(sp_ctx *ctx, const sp_seqset *targets, sp_targets **out);
 void sp_targets_destroy(sp_targets *t);

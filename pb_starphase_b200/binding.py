@@ -51,6 +51,7 @@ SIGNATURES = {
     "sp_patterns_count": (C.c_int64, [_P]),
     "sp_patterns_total_len": (C.c_int64, [_P]),
     "sp_patterns_padded_rows": (C.c_int64, [_P]),
+    "sp_plan_lane_classes": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(C.c_int), _P, _P, _P, C.POINTER(C.c_int64)]),
     "sp_targets_create": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(_P)]),
     "sp_targets_destroy": (None, [_P]),
     "sp_targets_count": (C.c_int64, [_P]),
@@ -99,6 +100,23 @@ def pack_sequences(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
     joined = b"".join(bytes(s) for s in seqs)
     bases = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, dtype=np.uint8)
     return bases, offs
+
+
+def plan_lane_classes(lens, max_classes: int = 4):
+    """Host-only: the lane-width classes sp_patterns_create would use for patterns of these lengths.
+    Returns ([(width, n_patterns, n_warps), ...], padded_rows)."""
+    lib = load_library()
+    a = np.ascontiguousarray(lens, dtype=np.int64)
+    nc = C.c_int(0)
+    w = np.zeros(max_classes, dtype=np.int32)
+    npat = np.zeros(max_classes, dtype=np.int64)
+    nw = np.zeros(max_classes, dtype=np.int64)
+    padded = C.c_int64(0)
+    st = lib.sp_plan_lane_classes(a.ctypes.data, len(a), max_classes, C.byref(nc), w.ctypes.data, npat.ctypes.data,
+                                  nw.ctypes.data, C.byref(padded))
+    if st != 0:
+        raise SpError(st, "sp_plan_lane_classes failed")
+    return [(int(w[k]), int(npat[k]), int(nw[k])) for k in range(nc.value)], int(padded.value)
 
 
 def _seqset(bases: np.ndarray, offs: np.ndarray) -> SeqSet:

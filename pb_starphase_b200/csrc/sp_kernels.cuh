@@ -23,7 +23,7 @@ constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int K1_CHUNK = 8;                 // text columns per chunk (one uint2 of byte codes)
 constexpr int PEQ_ROWS = 6;                 // A,C,G,T, N(other), pv-init
 __host__ __device__ constexpr int blob_words(int U) { return PEQ_ROWS * 32 * U + 64; }
-__host__ __device__ constexpr int vec_width(int U) { return (U % 4 == 0) ? 4 : 2; }
+__host__ __device__ constexpr int vec_width(int U) { return (U % 4 == 0) ? 4 : (U % 2 == 0) ? 2 : 1; }
 // info1 bit layout
 constexpr uint32_t INFO_FIRST = 1u << 30;
 constexpr uint32_t INFO_LAST = 1u << 31;
@@ -96,9 +96,11 @@ __device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)
         if (V == 4) {
             uint4 x = *reinterpret_cast<const uint4 *>(row_lane + q * 128);
             v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        } else {
+        } else if (V == 2) {
             uint2 x = *reinterpret_cast<const uint2 *>(row_lane + q * 64);
             v[2 * q + 0] = x.x; v[2 * q + 1] = x.y;
+        } else {
+            v[q] = row_lane[q * 32];
         }
     }
 }
@@ -168,6 +170,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
     constexpr int V = vec_width(U);
     const int lane = threadIdx.x & 31;
     const uint32_t pat = blob[PEQ_ROWS * 32 * U + lane];
+    if (__all_sync(0xffffffffu, pat == NO_PATTERN)) return;  // filler warp of a partly used group
     const uint32_t info1 = blob[PEQ_ROWS * 32 * U + 32 + lane];
     const bool first = (info1 & INFO_FIRST) != 0;
     const bool last = (info1 & INFO_LAST) != 0;

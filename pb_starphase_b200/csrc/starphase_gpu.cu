@@ -31,13 +31,19 @@ struct sp_ctx {
 
 static thread_local std::string g_create_err;
 
+// One lane-width class of a pattern set: every warp of the class holds 32 lanes x U words x 32 rows.
+struct PatClass {
+    int U = 0;
+    int n_bins = 0;    // warps incl. the fillers that pad the last group
+    int n_groups = 0;  // CTAs' worth of warps (K1_WARPS each)
+    uint32_t *d_blobs = nullptr;
+};
+
 struct sp_patterns {
     sp_ctx *ctx = nullptr;
     int64_t n = 0, total_len = 0, padded_rows = 0;
     sp_mode mode = SP_INFIX;
-    int U = 0;
-    int n_bins = 0, n_groups = 0;
-    uint32_t *d_blobs = nullptr;
+    std::vector<PatClass> classes;
 };
 
 struct TextPack {
@@ -195,7 +201,10 @@ static sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_base
 // ------------------------------------------------------------------------------------------
 // patterns: choose lane width U, bin-pack patterns into 32-lane warps, build Peq blobs on device
 // ------------------------------------------------------------------------------------------
-static const int kUs[] = {4, 6, 8, 10, 12, 16};
+// lane widths compiled into the library
+static const int kUmin = 4, kUmax = 16;
+// modelled ALU-pipe instructions per text column of one warp (8 per word + per-column bookkeeping)
+static double warp_cost(int U) { return 8.0 * U + 17.0; }
 
 struct BinPlan {
     int U = 0;
@@ -204,17 +213,17 @@ struct BinPlan {
     std::vector<uint32_t> lane_info1;
 };
 
-// best-fit decreasing over lane counts; returns false if some pattern needs more than 32 lanes
-static bool plan_bins(const std::vector<int64_t> &lens, int U, BinPlan &plan, bool fill) {
+// best-fit decreasing over lane counts for the patterns listed in `which`; false if one needs more than 32 lanes
+static bool plan_bins(const std::vector<int64_t> &lens, const std::vector<int32_t> &which, int U, BinPlan &plan, bool fill) {
     const int64_t rows = 32ll * U;
-    const size_t n = lens.size();
     std::vector<std::pair<int, int32_t>> items;  // (lanes, pattern)
-    items.reserve(n);
-    for (size_t i = 0; i < n; ++i) {
-        if (lens[i] == 0) continue;
-        const int64_t nl = (lens[i] + rows - 1) / rows;
+    items.reserve(which.size());
+    for (int32_t i : which) {
+        const int64_t len = lens[static_cast<size_t>(i)];
+        if (len == 0) continue;
+        const int64_t nl = (len + rows - 1) / rows;
         if (nl > 32) return false;
-        items.emplace_back(static_cast<int>(nl), static_cast<int32_t>(i));
+        items.emplace_back(static_cast<int>(nl), i);
     }
     std::stable_sort(items.begin(), items.end(),
                      [](const std::pair<int, int32_t> &a, const std::pair<int, int32_t> &b) { return a.first > b.first; });
@@ -255,6 +264,99 @@ static bool plan_bins(const std::vector<int64_t> &lens, int U, BinPlan &plan, bo
     return true;
 }
 
+// Splits the patterns over up to `max_classes` lane widths.  Every pattern goes to the width in the current set that
+// is cheapest for it (cost of a warp of that width / patterns of its lane count a warp holds); widths are added
+// greedily while the packed total (warps x modelled cost per column) drops by more than 1 %.
+static bool choose_classes(const std::vector<int64_t> &lens, int max_classes, std::vector<int> &Us,
+                           std::vector<std::vector<int32_t>> &members) {
+    const size_t n = lens.size();
+    auto assign = [&](const std::vector<int> &set, std::vector<std::vector<int32_t>> &mem) -> bool {
+        mem.assign(set.size(), {});
+        for (size_t i = 0; i < n; ++i) {
+            if (lens[i] == 0) continue;
+            int best = -1;
+            double bc = 0;
+            for (size_t c = 0; c < set.size(); ++c) {
+                const int64_t nl = (lens[i] + 32ll * set[c] - 1) / (32ll * set[c]);
+                if (nl > 32) continue;
+                const double cost = warp_cost(set[c]) / static_cast<double>(32 / nl);
+                if (best < 0 || cost < bc) { best = static_cast<int>(c); bc = cost; }
+            }
+            if (best < 0) return false;
+            mem[static_cast<size_t>(best)].push_back(static_cast<int32_t>(i));
+        }
+        return true;
+    };
+    auto total_cost = [&](const std::vector<int> &set, const std::vector<std::vector<int32_t>> &mem) -> double {
+        double c = 0;
+        for (size_t k = 0; k < set.size(); ++k) {
+            BinPlan probe;
+            plan_bins(lens, mem[k], set[k], probe, false);
+            const int groups = (probe.n_bins + K1_WARPS - 1) / K1_WARPS;
+            c += (probe.n_bins + 0.25 * (groups * K1_WARPS - probe.n_bins)) * warp_cost(set[k]);
+        }
+        return c;
+    };
+    std::vector<int> cand;
+    const char *forceU = getenv("SP_FORCE_U");  // test hook: one fixed lane width
+    for (int U = kUmin; U <= kUmax; ++U)
+        if (!forceU || atoi(forceU) == U) cand.push_back(U);
+    if (forceU) max_classes = 1;
+    std::vector<int> set;
+    std::vector<std::vector<int32_t>> mem;
+    double cur = 0;
+    while (static_cast<int>(set.size()) < max_classes) {
+        int bestU = 0;
+        double bestc = 0;
+        for (int U : cand) {
+            if (std::find(set.begin(), set.end(), U) != set.end()) continue;
+            std::vector<int> trial = set;
+            trial.push_back(U);
+            std::vector<std::vector<int32_t>> tm;
+            if (!assign(trial, tm)) continue;
+            const double c = total_cost(trial, tm);
+            if (!bestU || c < bestc) { bestU = U; bestc = c; }
+        }
+        if (!bestU) break;
+        if (!set.empty() && bestc > 0.99 * cur) break;
+        set.push_back(bestU);
+        cur = bestc;
+    }
+    if (set.empty()) return false;
+    assign(set, mem);
+    Us.clear(); members.clear();
+    for (size_t k = 0; k < set.size(); ++k)
+        if (!mem[k].empty()) { Us.push_back(set[k]); members.push_back(mem[k]); }
+    if (Us.empty()) { Us.push_back(set[0]); members.emplace_back(); }  // only empty patterns
+    return true;
+}
+
+// Host-only view of the planner (no device needed): which lane widths a pattern set would be split into.
+extern "C" sp_status sp_plan_lane_classes(const int64_t *lens, int64_t n, int max_classes, int *n_classes, int *widths,
+                                          int64_t *n_patterns, int64_t *n_warps, int64_t *padded_rows) {
+    if (!lens || n < 0 || !n_classes || !widths || !n_patterns || !n_warps || !padded_rows || max_classes < 1 ||
+        max_classes > 8)
+        return SP_ERR_INVALID;
+    std::vector<int64_t> v(lens, lens + n);
+    for (int64_t x : v)
+        if (x < 0) return SP_ERR_INVALID;
+        else if (x > SP_MAX_PATTERN_LEN) return SP_ERR_TOO_LONG;
+    std::vector<int> Us;
+    std::vector<std::vector<int32_t>> members;
+    if (!choose_classes(v, max_classes, Us, members)) return SP_ERR_TOO_LONG;
+    *n_classes = static_cast<int>(Us.size());
+    *padded_rows = 0;
+    for (size_t k = 0; k < Us.size(); ++k) {
+        BinPlan plan;
+        plan_bins(v, members[k], Us[k], plan, false);
+        widths[k] = Us[k];
+        n_patterns[k] = static_cast<int64_t>(members[k].size());
+        n_warps[k] = plan.n_bins;
+        *padded_rows += static_cast<int64_t>(plan.n_bins) * 32 * 32 * Us[k];
+    }
+    return SP_OK;
+}
+
 extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, sp_mode mode, sp_patterns **out) {
     if (!ctx) return SP_ERR_INVALID;
     if (!out) return fail(ctx, SP_ERR_INVALID, "sp_patterns_create: out is NULL");
@@ -276,68 +378,68 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
                     "pattern of " + std::to_string(maxlen) + " bases exceeds SP_MAX_PATTERN_LEN (" +
                         std::to_string(SP_MAX_PATTERN_LEN) + ")");
 
-    // pick the lane width with the lowest modelled cost: bins x (10 ALU ops per word + per-column overhead)
-    int bestU = 0;
-    double best_cost = 0;
-    const char *forceU = getenv("SP_FORCE_U");
-    for (int U : kUs) {
-        if (forceU && atoi(forceU) != U) continue;
-        BinPlan probe;
-        if (!plan_bins(lens, U, probe, false)) continue;
-        const double cost = static_cast<double>(std::max(probe.n_bins, 1)) * (10.0 * U + 12.0);
-        if (!bestU || cost < best_cost) { bestU = U; best_cost = cost; }
-    }
-    if (!bestU) return fail(ctx, SP_ERR_TOO_LONG, "no lane width fits the longest pattern");
-    BinPlan plan;
-    plan_bins(lens, bestU, plan, true);
-    const int U = bestU;
-    const int n_groups = std::max(1, (plan.n_bins + K1_WARPS - 1) / K1_WARPS);
-    const int n_bins_pad = n_groups * K1_WARPS;
-    plan.lane_pat.resize(static_cast<size_t>(n_bins_pad) * 32, -1);
-    plan.lane_row0.resize(static_cast<size_t>(n_bins_pad) * 32, 0);
-    plan.lane_info1.resize(static_cast<size_t>(n_bins_pad) * 32, INFO_FIRST);
+    std::vector<int> Us;
+    std::vector<std::vector<int32_t>> members;
+    const char *maxc = getenv("SP_MAX_CLASSES");
+    if (!choose_classes(lens, maxc ? std::max(1, atoi(maxc)) : 4, Us, members))
+        return fail(ctx, SP_ERR_TOO_LONG, "no lane width fits the longest pattern");
 
     sp_patterns *p = new (std::nothrow) sp_patterns();
     if (!p) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
-    p->ctx = ctx; p->n = patterns->n; p->total_len = total; p->mode = mode; p->U = U;
-    p->n_bins = n_bins_pad; p->n_groups = n_groups;
-    p->padded_rows = static_cast<int64_t>(plan.n_bins) * 32 * 32 * U;
+    p->ctx = ctx; p->n = patterns->n; p->total_len = total; p->mode = mode;
 
     uint8_t *d_bases = nullptr; long long *d_offs = nullptr;
     int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr; uint32_t *d_lane_info1 = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_bases); cudaFree(d_offs); cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
+    auto free_tabs = [&]() {
+        cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
+        d_lane_pat = d_lane_row0 = nullptr; d_lane_info1 = nullptr;
     };
+    auto cleanup = [&]() { cudaFree(d_bases); cudaFree(d_offs); free_tabs(); };
 #define SP_TRY(x)                                   \
     do {                                            \
         sp_status s__ = (x);                        \
         if (s__ != SP_OK) { cleanup(); sp_patterns_destroy(p); return s__; } \
     } while (0)
-    SP_TRY(upload_seqset(ctx, patterns, &d_bases, &d_offs));
-    const size_t tab = static_cast<size_t>(n_bins_pad) * 32;
     auto cu = [&](cudaError_t e, const char *what) -> sp_status {
         if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
         return SP_OK;
     };
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc lane_pat"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc lane_row0"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc lane_info1"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&p->d_blobs), static_cast<size_t>(n_bins_pad) * blob_words(U) * 4),
-              "cudaMalloc blobs"));
-    SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, plan.lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
-    SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, plan.lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
-    SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, plan.lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
-    {
-        const long long total_threads = static_cast<long long>(n_bins_pad) * 32 * U;
+    SP_TRY(upload_seqset(ctx, patterns, &d_bases, &d_offs));
+    bool first_launch = true;
+    for (size_t k = 0; k < Us.size(); ++k) {
+        const int U = Us[k];
+        BinPlan plan;
+        plan_bins(lens, members[k], U, plan, true);
+        PatClass pc;
+        pc.U = U;
+        pc.n_groups = std::max(1, (plan.n_bins + K1_WARPS - 1) / K1_WARPS);
+        pc.n_bins = pc.n_groups * K1_WARPS;
+        p->padded_rows += static_cast<int64_t>(plan.n_bins) * 32 * 32 * U;
+        const size_t tab = static_cast<size_t>(pc.n_bins) * 32;
+        plan.lane_pat.resize(tab, -1);
+        plan.lane_row0.resize(tab, 0);
+        plan.lane_info1.resize(tab, INFO_FIRST);
+        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc lane_pat"));
+        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc lane_row0"));
+        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc lane_info1"));
+        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&pc.d_blobs), static_cast<size_t>(pc.n_bins) * blob_words(U) * 4),
+                  "cudaMalloc blobs"));
+        p->classes.push_back(pc);  // owned by p from here on
+        SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, plan.lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+        SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, plan.lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+        SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, plan.lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+        const long long total_threads = static_cast<long long>(pc.n_bins) * 32 * U;
         const int blocks = static_cast<int>((total_threads + 255) / 256);
-        ev_begin(ctx, 2);
+        if (first_launch) ev_begin(ctx, 2);
         pack_patterns<<<blocks, 256, 0, ctx->stream>>>(d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1,
-                                                       p->d_blobs, n_bins_pad, U, mode == SP_PREFIX ? 1 : 0);
-        ev_end(ctx, 2);
+                                                       pc.d_blobs, pc.n_bins, U, mode == SP_PREFIX ? 1 : 0);
+        first_launch = false;
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "pack_patterns launch"));
+        SP_TRY(cu(cudaStreamSynchronize(ctx->stream), "pack_patterns"));  // the plan's host vectors die with this iteration
+        free_tabs();
     }
-    SP_TRY(cu(cudaStreamSynchronize(ctx->stream), "pack_patterns"));
+    ev_end(ctx, 2);
 #undef SP_TRY
     cleanup();
     *out = p;
@@ -347,7 +449,7 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
 extern "C" void sp_patterns_destroy(sp_patterns *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    cudaFree(p->d_blobs);
+    for (auto &c : p->classes) cudaFree(c.d_blobs);
     delete p;
 }
 extern "C" int64_t sp_patterns_count(const sp_patterns *p) { return p ? p->n : 0; }
@@ -451,30 +553,28 @@ static sp_status get_text_pack(sp_ctx *ctx, sp_targets *t, int tc, const TextPac
 // K1 launch
 // ------------------------------------------------------------------------------------------
 template <int U, bool TE>
-static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_items) {
+static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_items, bool first, bool last) {
     SP_CUDA(ctx, cudaFuncSetAttribute(k1_infix<U, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     SP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_infix<U, TE>, K1_THREADS, smem));
     if (occ < 1) return fail(ctx, SP_ERR_CUDA, "K1 does not fit on an SM with the requested shared memory");
     // persistent CTAs: a multiple of the SM count, each looping over (pattern-group, text-tile) items
     const int grid = std::min(n_items, ctx->num_sms * occ);
-    ev_begin(ctx, 0);
+    if (first) ev_begin(ctx, 0);  // the K1 timer spans the launches of all lane-width classes of one call
     k1_infix<U, TE><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
-    ev_end(ctx, 0);
+    if (last) ev_end(ctx, 0);
     ++ctx->launches;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;
 }
 
 template <bool TE>
-static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t smem, int n_items) {
+static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t smem, int n_items, bool first, bool last) {
     switch (U) {
-        case 4: return launch_k1<4, TE>(ctx, prm, smem, n_items);
-        case 6: return launch_k1<6, TE>(ctx, prm, smem, n_items);
-        case 8: return launch_k1<8, TE>(ctx, prm, smem, n_items);
-        case 10: return launch_k1<10, TE>(ctx, prm, smem, n_items);
-        case 12: return launch_k1<12, TE>(ctx, prm, smem, n_items);
-        case 16: return launch_k1<16, TE>(ctx, prm, smem, n_items);
+#define SP_CASE(u) case u: return launch_k1<u, TE>(ctx, prm, smem, n_items, first, last)
+        SP_CASE(4); SP_CASE(5); SP_CASE(6); SP_CASE(7); SP_CASE(8); SP_CASE(9); SP_CASE(10); SP_CASE(11);
+        SP_CASE(12); SP_CASE(13); SP_CASE(14); SP_CASE(15); SP_CASE(16);
+#undef SP_CASE
         default: return fail(ctx, SP_ERR_INVALID, "unsupported lane width");
     }
 }
@@ -483,39 +583,45 @@ static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t sme
 static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *out, int32_t *out_end, int64_t ld,
                         int elem_bits, int64_t row0) {
     if (t->n == 0 || p->n == 0 || p->total_len == 0) return SP_OK;
-    // tile capacity: 32 KB of text by default, grown for long texts, shrunk when the work list would be too short
-    const int U = p->U;
-    const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
-    const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
-    int64_t tc = 4096;
-    const int64_t want_items = 4ll * ctx->num_sms;
-    if (static_cast<int64_t>(p->n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
-        const int64_t want_tiles = (want_items + p->n_groups - 1) / p->n_groups;
-        tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
-    }
-    tc = std::max<int64_t>(tc, t->max_nch);
-    tc = (tc + 1) / 2 * 2;
-    if (tc > max_tc)
-        return fail(ctx, SP_ERR_TOO_LONG,
-                    "text of " + std::to_string(static_cast<long long>(t->max_nch) * K1_CHUNK) +
-                        " columns exceeds the shared-memory tile budget (" + std::to_string(max_tc * K1_CHUNK) + ")");
-    const TextPack *pk = nullptr;
-    sp_status st = get_text_pack(ctx, t, static_cast<int>(tc), &pk);
-    if (st != SP_OK) return st;
+    for (size_t k = 0; k < p->classes.size(); ++k) {
+        const PatClass &pc = p->classes[k];
+        // tile capacity: 32 KB of text by default, grown for long texts, shrunk when the work list would be too short
+        const int U = pc.U;
+        const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
+        const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
+        int64_t tc = 4096;
+        const int64_t want_items = 4ll * ctx->num_sms;
+        if (static_cast<int64_t>(pc.n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
+            const int64_t want_tiles = (want_items + pc.n_groups - 1) / pc.n_groups;
+            tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
+        }
+        tc = std::max<int64_t>(tc, t->max_nch);
+        tc = (tc + 1) / 2 * 2;
+        if (tc > max_tc)
+            return fail(ctx, SP_ERR_TOO_LONG,
+                        "text of " + std::to_string(static_cast<long long>(t->max_nch) * K1_CHUNK) +
+                            " columns exceeds the shared-memory tile budget (" + std::to_string(max_tc * K1_CHUNK) + ")");
+        const TextPack *pk = nullptr;
+        sp_status st = get_text_pack(ctx, t, static_cast<int>(tc), &pk);
+        if (st != SP_OK) return st;
 
-    K1Params prm;
-    prm.blobs = p->d_blobs; prm.text = pk->d_text; prm.tile_chunk_off = pk->d_tile_off; prm.tile_text0 = pk->d_tile_text0;
-    prm.out = static_cast<char *>(out) + static_cast<size_t>(row0 * ld) * (elem_bits / 8);
-    prm.out_end = out_end ? out_end + row0 * ld : nullptr;
-    prm.ld = ld;
-    prm.n_groups = p->n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
-    prm.prefix_mode = p->mode == SP_PREFIX;
-    prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
-    const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
-    if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
-    const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
-    return out_end ? dispatch_k1<true>(ctx, U, prm, smem, static_cast<int>(n_items64))
-                   : dispatch_k1<false>(ctx, U, prm, smem, static_cast<int>(n_items64));
+        K1Params prm;
+        prm.blobs = pc.d_blobs; prm.text = pk->d_text; prm.tile_chunk_off = pk->d_tile_off; prm.tile_text0 = pk->d_tile_text0;
+        prm.out = static_cast<char *>(out) + static_cast<size_t>(row0 * ld) * (elem_bits / 8);
+        prm.out_end = out_end ? out_end + row0 * ld : nullptr;
+        prm.ld = ld;
+        prm.n_groups = pc.n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
+        prm.prefix_mode = p->mode == SP_PREFIX;
+        prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
+        const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
+        if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
+        const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
+        const bool first = k == 0, last = k + 1 == p->classes.size();
+        st = out_end ? dispatch_k1<true>(ctx, U, prm, smem, static_cast<int>(n_items64), first, last)
+                     : dispatch_k1<false>(ctx, U, prm, smem, static_cast<int>(n_items64), first, last);
+        if (st != SP_OK) return st;
+    }
+    return SP_OK;
 }
 
 extern "C" sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t_in, const sp_patterns *p, int elem_bits,

@@ -58,7 +58,7 @@ def test_edge_cases_vs_dp(ctx, oracle, prefix):
     assert (E == Eref).all(), np.argwhere(E != Eref)[:10]
 
 
-@pytest.mark.parametrize("force_u", ["4", "6", "8", "10", "12", "16"])
+@pytest.mark.parametrize("force_u", [str(u) for u in range(4, 17)])
 def test_every_lane_width(ctx, oracle, force_u, monkeypatch):
     """Each compiled lane width (U words of 32 rows per lane) must give identical distances."""
     monkeypatch.setenv("SP_FORCE_U", force_u)
