@@ -150,6 +150,15 @@ sp_status sp_dmatrix_wrap(sp_ctx *ctx, void *dev_ptr, int64_t n_targets, int64_t
 sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns,
                          sp_mode mode, int32_t *D, int32_t *end_col);
 
+/* K3 (CYP2D6 seams S3 / a10): distance plus the text span [start_col, end_col) of an optimal placement, for every
+ * (target, pattern): end_col = smallest end of a best placement, start_col = the rightmost start among best
+ * placements ending there (recovered by an anchored pass over the reversed sequences).  Feeds the overlap score of
+ * weight_sequence (src/cyp2d6/chaining.rs:69-81: clipped_start = start_col, clipped_end = |T| - end_col) and the
+ * read span of find_base_type_in_sequence (src/cyp2d6/haplotyper.rs:203-249).  All three outputs are
+ * [n_targets][n_patterns] row-major int32, caller-allocated.  Meant for CYP2D6-sized batches (one warp per pair). */
+sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int32_t *D,
+                         int32_t *start_col, int32_t *end_col);
+
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
  * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;

@@ -163,6 +163,47 @@ int64_t sp_oracle_score_batch(const uint8_t *tbases, const int64_t *toffs, int64
 }
 
 /*
+ * Span of the optimal placement (the fields the reference reads from minimap2::Mapping at
+ * src/cyp2d6/chaining.rs:66-81 and src/cyp2d6/haplotyper.rs:203-249): end = smallest end column of a best
+ * placement; start = the rightmost start among best placements ending there, found by the anchored DP over the
+ * reversed pattern and the reversed text prefix T[0..end).  Returns the distance.
+ */
+int64_t sp_oracle_span(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, int64_t *start, int64_t *end) {
+    int64_t e = 0;
+    int64_t d = sp_oracle_infix_dp(P, m, T, n, 0, &e);
+    uint8_t *rp = (uint8_t *)malloc((size_t)(m + 1));
+    uint8_t *rt = (uint8_t *)malloc((size_t)(e + 1));
+    for (int64_t i = 0; i < m; ++i) rp[i] = P[m - 1 - i];
+    for (int64_t j = 0; j < e; ++j) rt[j] = T[e - 1 - j];
+    int64_t c = 0;
+    int64_t d2 = sp_oracle_infix_dp(rp, m, rt, e, 1, &c);
+    free(rp); free(rt);
+    if (d2 != d) { *start = -1; *end = e; return -1; } /* cannot happen: both are the optimum ending at e */
+    *start = e - c;
+    *end = e;
+    return d;
+}
+
+void sp_oracle_span_batch(const uint8_t *tbases, const int64_t *toffs, int64_t nt,
+                          const uint8_t *pbases, const int64_t *poffs, int64_t np, int nthreads,
+                          int32_t *D, int32_t *S, int32_t *E) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    int64_t total = nt * np;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t k = 0; k < total; ++k) {
+        int64_t t = k / np, p = k % np, s = 0, e = 0;
+        D[k] = (int32_t)sp_oracle_span(pbases + poffs[p], poffs[p + 1] - poffs[p], tbases + toffs[t],
+                                       toffs[t + 1] - toffs[t], &s, &e);
+        S[k] = (int32_t)s;
+        E[k] = (int32_t)e;
+    }
+}
+
+/*
  * Diplotype pair scoring in the north_star ("pre-v0.13") form: for every
  * unordered allele pair i <= j, S[i,j] = sum_r min(D[r,i], D[r,j]); keep the k
  * smallest by the lexicographic key (S, [S2,] i, j) -- the same (score, index1,

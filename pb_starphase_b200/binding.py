@@ -65,6 +65,7 @@ SIGNATURES = {
     "sp_dmatrix_elem_bits": (C.c_int, [_P]),
     "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
+    "sp_score_spans": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), _P, _P, _P]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
     "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
@@ -184,6 +185,17 @@ class Context:
         self._check(self._lib.sp_score_batch(self._h, C.byref(ts), C.byref(ps), mode, D.ctypes.data,
                                              E.ctypes.data if E is not None else None))
         return (D, E) if want_end_col else D
+
+    def score_spans(self, targets, patterns):
+        """K3: (D, start_col, end_col), each [n_targets, n_patterns] int32; the optimal placement of pattern p
+        covers text columns [start, end) of target t."""
+        tb, to = targets if isinstance(targets, tuple) else pack_sequences(targets)
+        pb, po = patterns if isinstance(patterns, tuple) else pack_sequences(patterns)
+        nt, np_ = len(to) - 1, len(po) - 1
+        D, S, E = (np.zeros((nt, np_), dtype=np.int32) for _ in range(3))
+        ts, ps = _seqset(tb, to), _seqset(pb, po)
+        self._check(self._lib.sp_score_spans(self._h, C.byref(ts), C.byref(ps), D.ctypes.data, S.ctypes.data, E.ctypes.data))
+        return D, S, E
 
     # -- K2 ---------------------------------------------------------------------------------
     def pair_minsum_topk(self, d, k: int = 10, i_begin: int = 0, i_end: Optional[int] = None, d2=None):

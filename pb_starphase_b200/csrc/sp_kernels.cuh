@@ -83,6 +83,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 #include "sp_addchain.inc"
 
+// A,C,G,T (either case) -> 0..3; everything else (N, *, ...) -> 4 = matches nothing
+__device__ __forceinline__ uint32_t base_code(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: one text column for one lane (32*U pattern rows as a U-word big integer).
 // Myers 1999 with Hyyro's hin/hout at lane boundaries only; inside the lane the U words are
@@ -258,23 +269,98 @@ __global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K
 }
 
 // ------------------------------------------------------------------------------------------
-// Pack kernels
+// K3 span recovery: start column of the optimal placement that ends at the column K1 reported.
+// For every (text t, pattern p): reversed P against reversed T[0 .. end), anchored at the window start
+// (SP_PREFIX boundary), smallest end column c of a best placement => start = end - c, the rightmost
+// start among optimal placements ending at `end`.  Replaces the m.query_start / m.target_start reads of
+// src/cyp2d6/chaining.rs:69-81 and src/cyp2d6/haplotyper.rs:203-249.  One warp per pair, one pattern
+// per bin (lane width SPAN_U), text bytes read straight from global memory (the pair count is small).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t base_code(uint8_t c) {
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: return 4;
+constexpr int SPAN_U = 16;
+
+struct SpanParams {
+    const uint32_t *blobs;   // [np] bins, reversed rows, prefix pad rows
+    const uint8_t *tbases;   // ASCII texts
+    const long long *toffs;
+    const int32_t *D;        // forward distances  [p * ld + t]
+    const int32_t *E;        // forward end columns [p * ld + t]
+    int32_t *S;              // out: start columns  [p * ld + t]
+    long long ld;
+    int nt, np;
+    uint32_t one, m1;
+};
+
+__global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
+    constexpr int U = SPAN_U;
+    constexpr int V = vec_width(U);
+    constexpr int BW = blob_words(U);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *blob = reinterpret_cast<uint32_t *>(smem_raw) + warp * BW;
+    const long long total = static_cast<long long>(p.nt) * p.np;
+    const long long n_warps = static_cast<long long>(gridDim.x) * K1_WARPS;
+    const long long per = (total + n_warps - 1) / n_warps;
+    const long long q0 = (static_cast<long long>(blockIdx.x) * K1_WARPS + warp) * per;
+    const long long q1 = min(total, q0 + per);
+    int cur_pat = -1;
+    for (long long q = q0; q < q1; ++q) {  // pattern-major so the blob is reloaded rarely
+        const int pat = static_cast<int>(q / p.nt), t = static_cast<int>(q - static_cast<long long>(pat) * p.nt);
+        if (pat != cur_pat) {
+            __syncwarp();
+            const uint32_t *src = p.blobs + static_cast<size_t>(pat) * BW;
+            for (int i = lane; i < BW; i += 32) blob[i] = src[i];
+            __syncwarp();
+            cur_pat = pat;
+        }
+        const uint32_t info1 = blob[PEQ_ROWS * 32 * U + 32 + lane];
+        const bool first = (info1 & INFO_FIRST) != 0, last = (info1 & INFO_LAST) != 0;
+        const int m = static_cast<int>(info1 & INFO_LEN_MASK);
+        const long long o = static_cast<long long>(pat) * p.ld + t;
+        const int e = p.E[o], d = p.D[o];
+        const int m_all = __shfl_sync(0xffffffffu, m, 0);  // lane 0 always belongs to the pattern (or it is empty)
+        const bool empty = blob[PEQ_ROWS * 32 * U] == NO_PATTERN;
+        if (empty) { if (lane == 0) p.S[o] = e; continue; }
+        const int wlen = min(e, m_all + d);
+        const int nch = (wlen + K1_CHUNK - 1) / K1_CHUNK;
+        const uint8_t *T = p.tbases + p.toffs[t];
+        const uint32_t *peq_lane = blob + lane * V;
+        uint32_t npv[U], mv[U];
+        load_row<U>(peq_lane + 5 * (32 * U), npv);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
+        int score = m, best = m, col = 0, best_col = 0;
+        uint32_t carry_out = 0;
+        const int nsteps = nch + 31;
+        for (int s = 0; s < nsteps; ++s) {
+            uint32_t cin = __shfl_up_sync(0xffffffffu, carry_out, 1);
+            if (first) cin = 0x00FFu;  // anchored: the row above the pattern costs one per column
+            const int idx = s - lane;
+            if (static_cast<unsigned>(idx) < static_cast<unsigned>(nch)) {
+                uint32_t X = cin << 24, Y = cin << 16;
+                uint32_t cph = 0, cmh = 0;
+#pragma unroll 1
+                for (int c = 0; c < K1_CHUNK; ++c) {
+                    const int j = idx * K1_CHUNK + c;
+                    const uint32_t code = j < wlen ? base_code(T[e - 1 - j]) : 4u;
+                    column_step<U, true>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
+                }
+                carry_out = cph | (cmh << 8);
+            }
+        }
+        if (last) p.S[o] = e - best_col;
+        if (nch == 0 && lane == 0) p.S[o] = e;  // empty window: the placement is empty, start == end
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Pack kernels
+// ------------------------------------------------------------------------------------------
 
 // one thread per (bin, lane, word): builds the six 32-row masks of that word
 __global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long *__restrict__ offs,
                               const int32_t *__restrict__ lane_pat, const int32_t *__restrict__ lane_row0,
                               const uint32_t *__restrict__ lane_info1, uint32_t *__restrict__ blobs, int n_bins,
-                              int U, int prefix_mode) {
+                              int U, int prefix_mode, int reverse) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(n_bins) * 32 * U;
     if (idx >= total) return;
@@ -287,6 +373,7 @@ __global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long
     uint32_t mask[PEQ_ROWS] = {0, 0, 0, 0, 0, 0};
     if (pat >= 0) {
         const uint8_t *P = bases + offs[pat];
+        const int m = static_cast<int>(offs[pat + 1] - offs[pat]);
         const int row0 = lane_row0[bin * 32 + lane] + 32 * u;
         for (int b = 0; b < 32; ++b) {
             const int r = row0 + b;
@@ -294,7 +381,7 @@ __global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long
             if (r < 0) {  // pad row above the pattern: wildcard (infix) / pass-through (prefix)
                 if (!prefix_mode) { mask[0] |= bit; mask[1] |= bit; mask[2] |= bit; mask[3] |= bit; mask[4] |= bit; }
             } else {
-                const uint32_t c = base_code(P[r]);
+                const uint32_t c = base_code(P[reverse ? m - 1 - r : r]);
                 if (c < 4) mask[c] |= bit;
                 mask[5] |= bit;
             }

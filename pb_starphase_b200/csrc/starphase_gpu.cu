@@ -432,7 +432,7 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
         const int blocks = static_cast<int>((total_threads + 255) / 256);
         if (first_launch) ev_begin(ctx, 2);
         pack_patterns<<<blocks, 256, 0, ctx->stream>>>(d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1,
-                                                       pc.d_blobs, pc.n_bins, U, mode == SP_PREFIX ? 1 : 0);
+                                                       pc.d_blobs, pc.n_bins, U, mode == SP_PREFIX ? 1 : 0, 0);
         first_launch = false;
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "pack_patterns launch"));
@@ -741,6 +741,96 @@ extern "C" sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const
     if (st == SP_OK) st = sp_dmatrix_to_host(ctx, d, D, end_col);
     sp_dmatrix_destroy(d); sp_targets_destroy(t); sp_patterns_destroy(p);
     return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 spans: distance + [start, end) of the optimal placement on the text
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int32_t *D,
+                                    int32_t *start_col, int32_t *end_col) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!D || !start_col || !end_col) return fail(ctx, SP_ERR_INVALID, "sp_score_spans: NULL output");
+    sp_patterns *p = nullptr; sp_targets *t = nullptr; sp_dmatrix *d = nullptr;
+    uint8_t *d_bases = nullptr; long long *d_offs = nullptr;
+    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_S = nullptr;
+    uint32_t *d_lane_info1 = nullptr, *d_blobs = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_bases); cudaFree(d_offs); cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
+        cudaFree(d_blobs); cudaFree(d_S);
+        sp_dmatrix_destroy(d); sp_targets_destroy(t); sp_patterns_destroy(p);
+    };
+    // forward pass: distances and the smallest end column of a best placement
+    sp_status st = sp_patterns_create(ctx, patterns, SP_INFIX, &p);
+    if (st == SP_OK) st = sp_targets_create(ctx, targets, &t);
+    if (st == SP_OK) st = sp_score_device(ctx, t, p, 32, 1, &d);
+    if (st != SP_OK) { cleanup(); return st; }
+    const int64_t np = patterns->n, nt = targets->n;
+    if (np == 0 || nt == 0) { cleanup(); return SP_OK; }
+    auto cu = [&](cudaError_t e, const char *what) -> sp_status {
+        if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return SP_OK;
+    };
+#define SP_TRY(x)                                   \
+    do {                                            \
+        sp_status s__ = (x);                        \
+        if (s__ != SP_OK) { cleanup(); return s__; } \
+    } while (0)
+    // reversed patterns, one per bin, anchored (prefix) pad rows
+    const int64_t rows = 32ll * SPAN_U;
+    const size_t tab = static_cast<size_t>(np) * 32;
+    std::vector<int32_t> lane_pat(tab, -1), lane_row0(tab, 0);
+    std::vector<uint32_t> lane_info1(tab, INFO_FIRST);
+    for (int64_t i = 0; i < np; ++i) {
+        const int64_t m = patterns->offsets[i + 1] - patterns->offsets[i];
+        if (m == 0) continue;
+        const int64_t nl = (m + rows - 1) / rows, pad = nl * rows - m;  // nl <= 32: checked by sp_patterns_create
+        for (int64_t li = 0; li < nl; ++li) {
+            const size_t o = static_cast<size_t>(i) * 32 + static_cast<size_t>(li);
+            lane_pat[o] = static_cast<int32_t>(i);
+            lane_row0[o] = static_cast<int32_t>(li * rows - pad);
+            lane_info1[o] = static_cast<uint32_t>(m) | (li == 0 ? INFO_FIRST : 0u) | (li == nl - 1 ? INFO_LAST : 0u);
+        }
+    }
+    SP_TRY(upload_seqset(ctx, patterns, &d_bases, &d_offs));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(SPAN_U) * 4), "cudaMalloc span blobs"));
+    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_S), static_cast<size_t>(np * d->ld) * 4), "cudaMalloc span starts"));
+    SP_TRY(cu(cudaMemsetAsync(d_S, 0, static_cast<size_t>(np * d->ld) * 4, ctx->stream), "memset"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    {
+        const long long total_threads = static_cast<long long>(np) * 32 * SPAN_U;
+        pack_patterns<<<static_cast<int>((total_threads + 255) / 256), 256, 0, ctx->stream>>>(
+            d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1, d_blobs, static_cast<int>(np), SPAN_U, 1, 1);
+        ++ctx->launches;
+        SP_TRY(cu(cudaGetLastError(), "pack_patterns (reversed)"));
+    }
+    {
+        SpanParams prm;
+        prm.blobs = d_blobs; prm.tbases = t->d_bases; prm.toffs = t->d_offs;
+        prm.D = static_cast<const int32_t *>(d->d); prm.E = d->d_end; prm.S = d_S; prm.ld = d->ld;
+        prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
+        const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(SPAN_U) * 4;
+        SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                  "k3_span_starts smem"));
+        const long long total = nt * np;
+        const int grid = static_cast<int>(std::min<long long>(2ll * ctx->num_sms, (total + K1_WARPS - 1) / K1_WARPS));
+        k3_span_starts<<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        ++ctx->launches;
+        SP_TRY(cu(cudaGetLastError(), "k3_span_starts launch"));
+    }
+    SP_TRY(sp_dmatrix_to_host(ctx, d, D, end_col));
+    {
+        sp_dmatrix view = *d;  // same geometry, start columns as the payload
+        view.d = d_S; view.d_end = nullptr; view.owned = false;
+        SP_TRY(sp_dmatrix_to_host(ctx, &view, start_col, nullptr));
+    }
+#undef SP_TRY
+    cleanup();
+    return SP_OK;
 }
 
 // ------------------------------------------------------------------------------------------

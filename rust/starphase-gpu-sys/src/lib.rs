@@ -1,0 +1,121 @@
+//! `extern "C"` mirror of include/starphase_gpu.h plus the small safe wrapper the pb-StarPhase call sites use.
+//! One `GpuScorer` per process per GPU; calls are blocking, like the `Aligner::map` calls they replace.
+#![allow(non_camel_case_types)]
+use std::ffi::{c_char, c_int, c_void, CStr};
+
+#[repr(C)]
+pub struct sp_seqset {
+    pub bases: *const u8,
+    pub offsets: *const i64,
+    pub n: i64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct sp_pair_rec {
+    pub score: u64,
+    pub score2: u64,
+    pub i: u32,
+    pub j: u32,
+    pub c1: u32,
+    pub _pad: u32,
+}
+
+pub enum sp_ctx {}
+pub enum sp_patterns {}
+pub enum sp_targets {}
+pub enum sp_dmatrix {}
+
+pub const SP_INFIX: c_int = 0;
+pub const SP_PREFIX: c_int = 1;
+
+extern "C" {
+    pub fn sp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut sp_ctx) -> c_int;
+    pub fn sp_ctx_destroy(ctx: *mut sp_ctx);
+    pub fn sp_last_error(ctx: *const sp_ctx) -> *const c_char;
+    pub fn sp_patterns_create(ctx: *mut sp_ctx, p: *const sp_seqset, mode: c_int, out: *mut *mut sp_patterns) -> c_int;
+    pub fn sp_patterns_destroy(p: *mut sp_patterns);
+    pub fn sp_targets_create(ctx: *mut sp_ctx, t: *const sp_seqset, out: *mut *mut sp_targets) -> c_int;
+    pub fn sp_targets_destroy(t: *mut sp_targets);
+    pub fn sp_score_device(ctx: *mut sp_ctx, t: *const sp_targets, p: *const sp_patterns, elem_bits: c_int,
+                           want_end_col: c_int, out: *mut *mut sp_dmatrix) -> c_int;
+    pub fn sp_dmatrix_to_host(ctx: *mut sp_ctx, d: *const sp_dmatrix, dist: *mut i32, end_col: *mut i32) -> c_int;
+    pub fn sp_dmatrix_destroy(d: *mut sp_dmatrix);
+    pub fn sp_score_batch(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, mode: c_int,
+                          dist: *mut i32, end_col: *mut i32) -> c_int;
+    pub fn sp_score_spans(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, dist: *mut i32,
+                          start_col: *mut i32, end_col: *mut i32) -> c_int;
+    pub fn sp_pair_minsum_topk(ctx: *mut sp_ctx, d: *const sp_dmatrix, d2: *const sp_dmatrix, i_begin: i64,
+                               i_end: i64, k: c_int, out: *mut sp_pair_rec, n_out: *mut c_int) -> c_int;
+    pub fn sp_pair_minsum_topk_host(ctx: *mut sp_ctx, d: *const i32, d2: *const i32, r: i64, a: i64, k: c_int,
+                                    out: *mut sp_pair_rec, n_out: *mut c_int) -> c_int;
+    pub fn sp_pair_minsum_full_host(ctx: *mut sp_ctx, d: *const i32, r: i64, a: i64, s: *mut u64) -> c_int;
+}
+
+/// Concatenated sequences in the layout of `sp_seqset`.
+pub struct SeqSet {
+    bases: Vec<u8>,
+    offsets: Vec<i64>,
+}
+
+impl SeqSet {
+    pub fn new<'a>(seqs: impl IntoIterator<Item = &'a [u8]>) -> Self {
+        let mut bases = Vec::new();
+        let mut offsets = vec![0i64];
+        for s in seqs {
+            bases.extend_from_slice(s);
+            offsets.push(bases.len() as i64);
+        }
+        SeqSet { bases, offsets }
+    }
+    pub fn len(&self) -> usize { self.offsets.len() - 1 }
+    pub fn is_empty(&self) -> bool { self.len() == 0 }
+    fn raw(&self) -> sp_seqset {
+        sp_seqset { bases: self.bases.as_ptr(), offsets: self.offsets.as_ptr(), n: self.len() as i64 }
+    }
+}
+
+pub struct GpuScorer { ctx: *mut sp_ctx }
+
+impl GpuScorer {
+    pub fn new(device: i32) -> Result<Self, Box<dyn std::error::Error>> {
+        let mut ctx = std::ptr::null_mut();
+        let st = unsafe { sp_ctx_create(device, std::ptr::null_mut(), &mut ctx) };
+        if st != 0 { return Err(Self::err(std::ptr::null()).into()); }
+        Ok(GpuScorer { ctx })
+    }
+    fn err(ctx: *const sp_ctx) -> String {
+        unsafe { CStr::from_ptr(sp_last_error(ctx)).to_string_lossy().into_owned() }
+    }
+    /// `nm + unmapped` of every pattern against every target: `ret[t * patterns.len() + p]`.
+    pub fn score_batch(&self, targets: &SeqSet, patterns: &SeqSet) -> Result<Vec<i32>, Box<dyn std::error::Error>> {
+        let mut d = vec![0i32; targets.len() * patterns.len()];
+        let st = unsafe { sp_score_batch(self.ctx, &targets.raw(), &patterns.raw(), SP_INFIX, d.as_mut_ptr(), std::ptr::null_mut()) };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        Ok(d)
+    }
+    /// Same plus the text span `[start, end)` of an optimal placement (CYP2D6 overlap scores).
+    pub fn score_spans(&self, targets: &SeqSet, patterns: &SeqSet) -> Result<(Vec<i32>, Vec<i32>, Vec<i32>), Box<dyn std::error::Error>> {
+        let n = targets.len() * patterns.len();
+        let (mut d, mut s, mut e) = (vec![0i32; n], vec![0i32; n], vec![0i32; n]);
+        let st = unsafe { sp_score_spans(self.ctx, &targets.raw(), &patterns.raw(), d.as_mut_ptr(), s.as_mut_ptr(), e.as_mut_ptr()) };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        Ok((d, s, e))
+    }
+    /// k best allele pairs by (sum_r min(D[r,i], D[r,j]), same on D2, i, j); D, D2 are [R][A] row-major.
+    pub fn pair_topk(&self, d: &[i32], d2: Option<&[i32]>, r: usize, a: usize, k: usize) -> Result<Vec<sp_pair_rec>, Box<dyn std::error::Error>> {
+        let mut out = vec![sp_pair_rec::default(); k];
+        let mut n: c_int = 0;
+        let st = unsafe {
+            sp_pair_minsum_topk_host(self.ctx, d.as_ptr(), d2.map_or(std::ptr::null(), |x| x.as_ptr()), r as i64, a as i64,
+                                     k as c_int, out.as_mut_ptr(), &mut n)
+        };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        out.truncate(n as usize);
+        Ok(out)
+    }
+}
+
+impl Drop for GpuScorer {
+    fn drop(&mut self) { unsafe { sp_ctx_destroy(self.ctx) } }
+}

@@ -50,6 +50,9 @@ class Oracle:
         L.sp_oracle_pair_minsum_full.restype = None
         L.sp_oracle_pair_minsum_full.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.sp_oracle_num_threads.restype = C.c_int
+        L.sp_oracle_span_batch.restype = None
+        L.sp_oracle_span_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
 
     def num_threads(self) -> int:
         return int(self.lib.sp_oracle_num_threads())
@@ -72,6 +75,16 @@ class Oracle:
             tb.ctypes.data, to.ctypes.data, nt, pb.ctypes.data, po.ctypes.data, npat, int(prefix),
             0 if impl == "dp" else 1, nthreads, D.ctypes.data, E.ctypes.data if E is not None else None))
         return (D, E) if want_end_col else D
+
+    def score_spans(self, targets, patterns, nthreads: int = 0):
+        """(D, start, end), each [nt, np] int32: see sp_oracle_span."""
+        tb, to = targets if isinstance(targets, tuple) else _pack(targets)
+        pb, po = patterns if isinstance(patterns, tuple) else _pack(patterns)
+        nt, npat = len(to) - 1, len(po) - 1
+        D, S, E = (np.zeros((nt, npat), dtype=np.int32) for _ in range(3))
+        self.lib.sp_oracle_span_batch(tb.ctypes.data, to.ctypes.data, nt, pb.ctypes.data, po.ctypes.data, npat, nthreads,
+                                      D.ctypes.data, S.ctypes.data, E.ctypes.data)
+        return D, S, E
 
     def pair_minsum_topk(self, D: np.ndarray, k: int, nthreads: int = 0, D2=None):
         D = np.ascontiguousarray(D, dtype=np.int32)

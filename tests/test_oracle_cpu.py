@@ -110,3 +110,30 @@ def test_pair_minsum_against_numpy(oracle):
     assert [(s, i, j) for s, i, j, _ in top] == flat
     for s, i, j, c1 in top:
         assert c1 == int((D[:, i] <= D[:, j]).sum())
+
+
+def test_span_convention(oracle):
+    """sp_oracle_span: end = leftmost end of a best placement, start = rightmost start of a best placement
+    ending there; checked against brute force over all substrings on small inputs."""
+    rng = np.random.default_rng(3)
+
+    def lev(a: bytes, b: bytes) -> int:
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[-1] + 1, prev[j - 1] + (0 if ca == cb and ca in b"ACGT" else 1)))
+            prev = cur
+        return prev[-1]
+
+    for _ in range(60):
+        P = rnd(rng, int(rng.integers(1, 9)))
+        T = bytes(rng.choice(list(b"ACGTN"), int(rng.integers(0, 14))).tolist())
+        D, S, E = oracle.score_spans([T], [P])
+        d, s, e = int(D[0, 0]), int(S[0, 0]), int(E[0, 0])
+        best = min(lev(P, T[a:b]) for a in range(len(T) + 1) for b in range(a, len(T) + 1))
+        assert d == best
+        ends = sorted({b for a in range(len(T) + 1) for b in range(a, len(T) + 1) if lev(P, T[a:b]) == best})
+        assert e == ends[0]
+        starts = [a for a in range(e + 1) if lev(P, T[a:e]) == best]
+        assert s == max(starts)
