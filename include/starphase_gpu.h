@@ -137,6 +137,12 @@ sp_status sp_score_into(sp_ctx *ctx, const sp_targets *t, const sp_patterns *p, 
 void sp_dmatrix_destroy(sp_dmatrix *d);
 /* Copy to host as int32 D[t * n_patterns + p] (row = target), optionally end columns. */
 sp_status sp_dmatrix_to_host(sp_ctx *ctx, const sp_dmatrix *d, int32_t *D, int32_t *end_col);
+/* 16-bit read-back of a 16-bit matrix (half the PCIe bytes): D[t * n_patterns + p]. */
+sp_status sp_dmatrix_to_host_u16(sp_ctx *ctx, const sp_dmatrix *d, uint16_t *D);
+/* Pinned (page-locked) host memory: sequence and result buffers allocated here move over PCIe at full speed.
+ * Any host pointer is accepted everywhere; pageable ones are staged by the driver and are several times slower. */
+sp_status sp_host_alloc(sp_ctx *ctx, size_t bytes, void **out);
+void sp_host_free(sp_ctx *ctx, void *ptr);
 /* Raw device pointer / geometry for zero-copy consumers (torch, NCCL all-gather). */
 void *sp_dmatrix_device_ptr(const sp_dmatrix *d);
 int64_t sp_dmatrix_ld(const sp_dmatrix *d);

@@ -60,6 +60,9 @@ SIGNATURES = {
     "sp_score_into": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "sp_dmatrix_destroy": (None, [_P]),
     "sp_dmatrix_to_host": (C.c_int, [_P, _P, _P, _P]),
+    "sp_dmatrix_to_host_u16": (C.c_int, [_P, _P, _P]),
+    "sp_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "sp_host_free": (None, [_P, _P]),
     "sp_dmatrix_device_ptr": (_P, [_P]),
     "sp_dmatrix_ld": (C.c_int64, [_P]),
     "sp_dmatrix_elem_bits": (C.c_int, [_P]),
@@ -136,6 +139,7 @@ class Context:
             raise SpError(st, self._lib.sp_last_error(None).decode())
         self._h = h
         self.device = device
+        self._pinned = []
 
     def _check(self, st: int):
         if st != 0:
@@ -143,6 +147,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr in self._pinned:
+                self._lib.sp_host_free(self._h, ptr)
+            self._pinned = []
             self._lib.sp_ctx_destroy(self._h)
             self._h = None
 
@@ -241,6 +248,16 @@ class Context:
         self._check(self._lib.sp_int_peak(self._h, kind, C.byref(v)))
         return v.value
 
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array backed by page-locked memory from sp_host_alloc (freed with the context)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        ptr = _P()
+        self._check(self._lib.sp_host_alloc(self._h, n, C.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
     def wrap_dmatrix(self, dev_ptr: int, n_targets: int, n_patterns: int, ld: int, elem_bits: int) -> "DMatrix":
         h = _P()
         self._check(self._lib.sp_dmatrix_wrap(self._h, _P(dev_ptr), n_targets, n_patterns, ld, elem_bits, C.byref(h)))
@@ -313,7 +330,18 @@ class DMatrix:
     def elem_bits(self) -> int:
         return int(self.ctx._lib.sp_dmatrix_elem_bits(self._h))
 
-    def to_host(self, want_end_col: bool = False):
+    def to_host_u16(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """16-bit read-back (the matrix must be 16-bit); `out` may be a pinned array from Context.pinned_empty."""
+        D = out if out is not None else np.empty((self.n_targets, self.n_patterns), dtype=np.uint16)
+        assert D.dtype == np.uint16 and D.shape == (self.n_targets, self.n_patterns) and D.flags.c_contiguous
+        self.ctx._check(self.ctx._lib.sp_dmatrix_to_host_u16(self.ctx._h, self._h, D.ctypes.data))
+        return D
+
+    def to_host(self, want_end_col: bool = False, out: Optional[np.ndarray] = None):
+        if out is not None and not want_end_col:
+            assert out.dtype == np.int32 and out.shape == (self.n_targets, self.n_patterns) and out.flags.c_contiguous
+            self.ctx._check(self.ctx._lib.sp_dmatrix_to_host(self.ctx._h, self._h, out.ctypes.data, None))
+            return out
         D = np.zeros((self.n_targets, self.n_patterns), dtype=np.int32)
         E = np.zeros((self.n_targets, self.n_patterns), dtype=np.int32) if want_end_col else None
         self.ctx._check(self.ctx._lib.sp_dmatrix_to_host(self.ctx._h, self._h, D.ctypes.data,

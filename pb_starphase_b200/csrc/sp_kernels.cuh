@@ -419,14 +419,14 @@ __global__ void pack_texts(const uint8_t *__restrict__ bases, const long long *_
     }
 }
 
-// D[p*ld + t] (u16 / i32) -> host-order int32 rows[t * np + p]
-template <typename T>
-__global__ void dmatrix_to_rows(const T *__restrict__ D, long long ld, int nt, int np, int32_t *__restrict__ rows) {
-    __shared__ int32_t tile[32][33];
+// D[p*ld + t] (u16 / i32) -> host-order rows[t * np + p] (int32, or u16 for the 16-bit read-back)
+template <typename T, typename O>
+__global__ void dmatrix_to_rows(const T *__restrict__ D, long long ld, int nt, int np, O *__restrict__ rows) {
+    __shared__ O tile[32][33];
     const int t0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int p = p0 + i, t = t0 + threadIdx.x;
-        tile[i][threadIdx.x] = (p < np && t < nt) ? static_cast<int32_t>(D[static_cast<long long>(p) * ld + t]) : 0;
+        tile[i][threadIdx.x] = (p < np && t < nt) ? static_cast<O>(D[static_cast<long long>(p) * ld + t]) : O(0);
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {

@@ -27,7 +27,23 @@ struct sp_ctx {
     cudaEvent_t ev[4][2] = {};
     bool ev_valid[4] = {false, false, false, false};
     uint64_t launches = 0;
+    void *scratch = nullptr;  // grow-only device staging buffer (transposed result rows), reused across calls
+    size_t scratch_bytes = 0;
 };
+
+// stream-ordered reuse is safe: every user synchronises the context stream before it returns
+static cudaError_t ctx_scratch(sp_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->scratch);
+        ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&ctx->scratch, bytes);
+        if (e != cudaSuccess) return e;
+        ctx->scratch_bytes = bytes;
+    }
+    *out = ctx->scratch;
+    return cudaSuccess;
+}
 
 static thread_local std::string g_create_err;
 
@@ -146,6 +162,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->scratch);
     delete ctx;
 }
 
@@ -704,30 +721,64 @@ extern "C" sp_status sp_dmatrix_to_host(sp_ctx *ctx, const sp_dmatrix *d, int32_
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = static_cast<size_t>(d->nt * d->np);
     int32_t *rows = nullptr;
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&rows), n * 4));
+    SP_CUDA(ctx, ctx_scratch(ctx, n * 4, reinterpret_cast<void **>(&rows)));
     const dim3 grid(static_cast<unsigned>((d->nt + 31) / 32), static_cast<unsigned>((d->np + 31) / 32)), blk(32, 8);
     cudaError_t e = cudaSuccess;
     if (D) {
         if (d->elem_bits == 16)
-            dmatrix_to_rows<uint16_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld,
-                                                                     static_cast<int>(d->nt), static_cast<int>(d->np), rows);
+            dmatrix_to_rows<uint16_t, int32_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld,
+                                                                              static_cast<int>(d->nt), static_cast<int>(d->np), rows);
         else
-            dmatrix_to_rows<int32_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld,
-                                                                    static_cast<int>(d->nt), static_cast<int>(d->np), rows);
+            dmatrix_to_rows<int32_t, int32_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld,
+                                                                             static_cast<int>(d->nt), static_cast<int>(d->np), rows);
         ++ctx->launches;
         e = cudaMemcpyAsync(D, rows, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
     if (e == cudaSuccess && end_col) {
-        dmatrix_to_rows<int32_t><<<grid, blk, 0, ctx->stream>>>(d->d_end, d->ld, static_cast<int>(d->nt),
-                                                                static_cast<int>(d->np), rows);
+        dmatrix_to_rows<int32_t, int32_t><<<grid, blk, 0, ctx->stream>>>(d->d_end, d->ld, static_cast<int>(d->nt),
+                                                                         static_cast<int>(d->np), rows);
         ++ctx->launches;
         e = cudaMemcpyAsync(end_col, rows, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(rows);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("sp_dmatrix_to_host: ") + cudaGetErrorString(e));
     return SP_OK;
+}
+
+extern "C" sp_status sp_dmatrix_to_host_u16(sp_ctx *ctx, const sp_dmatrix *d, uint16_t *D) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!d || !D) return fail(ctx, SP_ERR_INVALID, "sp_dmatrix_to_host_u16: NULL argument");
+    if (d->elem_bits != 16) return fail(ctx, SP_ERR_INVALID, "sp_dmatrix_to_host_u16: matrix is not 16-bit");
+    if (d->nt == 0 || d->np == 0) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = static_cast<size_t>(d->nt * d->np);
+    uint16_t *rows = nullptr;
+    SP_CUDA(ctx, ctx_scratch(ctx, n * 2, reinterpret_cast<void **>(&rows)));
+    const dim3 grid(static_cast<unsigned>((d->nt + 31) / 32), static_cast<unsigned>((d->np + 31) / 32)), blk(32, 8);
+    dmatrix_to_rows<uint16_t, uint16_t><<<grid, blk, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld,
+                                                                       static_cast<int>(d->nt), static_cast<int>(d->np), rows);
+    ++ctx->launches;
+    cudaError_t e = cudaMemcpyAsync(D, rows, n * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("sp_dmatrix_to_host_u16: ") + cudaGetErrorString(e));
+    return SP_OK;
+}
+
+// pinned host memory for callers that want full-speed PCIe copies into / out of the library
+extern "C" sp_status sp_host_alloc(sp_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out) return fail(ctx, SP_ERR_INVALID, "sp_host_alloc: out is NULL");
+    *out = nullptr;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(ctx, SP_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return SP_OK;
+}
+extern "C" void sp_host_free(sp_ctx *ctx, void *ptr) {
+    if (!ctx || !ptr) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(ptr);
 }
 
 extern "C" sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, sp_mode mode,

@@ -127,6 +127,13 @@ def test_device_matrix_u16_and_i32_agree(ctx, oracle):
     assert (a == b).all()
     assert (a == oracle.score_batch(reads, alleles)).all()
     assert d16.ld % 64 == 0 and d16.elem_bits == 16 and d16.device_ptr != 0
+    # 16-bit read-back into pinned memory from sp_host_alloc, and int32 read-back into a caller buffer
+    pin = ctx.pinned_empty(a.shape, np.uint16)
+    assert (d16.to_host_u16(pin) == a).all() and (d16.to_host_u16() == a).all()
+    out = ctx.pinned_empty(a.shape, np.int32)
+    assert (d32.to_host(out=out) == a).all()
+    with pytest.raises(sp.SpError):
+        d32.to_host_u16()
 
 
 def test_sharding_invariance(ctx):
