@@ -190,8 +190,12 @@ def run_ours(args):
     n = max(args.gpus, world)
     w = build_workload(n, args.scale)
 
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the library's kernels, torch's fills/events and the NCCL hand-offs.
+    # (The legacy default stream has handle 0 == NULL, which sp_ctx_create reads as "make a private stream".)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = sp.Context(local_rank, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0
     int_peak = ctx.int_peak(0)       # ALU pipe alone (LOP3)
     int_peak2 = ctx.int_peak(2)      # ALU + FMA pipes (LOP3 + IMAD alternating)
 
@@ -219,6 +223,7 @@ def run_ours(args):
     # gather buffers: [world * S][ld] u16, this rank scores straight into its slot
     full_dna = torch.zeros((world * d_S, ld), dtype=torch.int16, device=dev)
     full_cdna = torch.zeros((world * c_S, ld), dtype=torch.int16, device=dev)
+    gat_dna, gat_cdna = full_dna.view(torch.uint8), full_cdna.view(torch.uint8)
     M_dna = ctx.wrap_dmatrix(full_dna.data_ptr(), R, world * d_S, ld, 16)
     M_cdna = ctx.wrap_dmatrix(full_cdna.data_ptr(), R, world * c_S, ld, 16)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -236,8 +241,9 @@ def run_ours(args):
         k1_ms.append(ctx.last_kernel_ms(0))
         ctx.score_into(T_cdna, P_cdna, M_cdna, rank * c_S)
         if world > 1:
-            dist.all_gather_into_tensor(full_dna, full_dna[rank * d_S:(rank + 1) * d_S])
-            dist.all_gather_into_tensor(full_cdna, full_cdna[rank * c_S:(rank + 1) * c_S])
+            # NCCL has no int16: the shards travel as bytes
+            dist.all_gather_into_tensor(gat_dna, gat_dna[rank * d_S:(rank + 1) * d_S])
+            dist.all_gather_into_tensor(gat_cdna, gat_cdna[rank * c_S:(rank + 1) * c_S])
         out = {}
         for gene, (vc, vd, (lo, hi)) in views.items():
             recs = ctx.pair_minsum_topk(vc, TOPK, lo, hi, d2=vd)

@@ -84,7 +84,8 @@ typedef struct sp_pair_rec {
 
 /* ---- context ------------------------------------------------------------------------- */
 /* device: CUDA ordinal.  stream: a cudaStream_t to launch on (e.g. the host framework's
- * current stream), or NULL to create a private non-blocking stream. */
+ * current stream), or NULL to create a private non-blocking stream.  The legacy default stream (handle 0) cannot
+ * be passed; a host that mixes its own work (e.g. NCCL collectives) with these calls must share an explicit stream. */
 sp_status sp_ctx_create(int device, void *stream, sp_ctx **out);
 void sp_ctx_destroy(sp_ctx *ctx);
 /* Message for the last failing call on this context ("" if none).  Maps to the
