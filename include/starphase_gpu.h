@@ -166,6 +166,16 @@ sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
 sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int32_t *D,
                          int32_t *start_col, int32_t *end_col);
 
+/* K3 (seam S4, src/cyp2d6/chaining.rs:683-731): the window scan of containment_score hoisted out of the pair loop.
+ * Chains are CSR lists of haplotype (consensus) indices; read r owns segments seg_off[r] .. seg_off[r+1]) and
+ * W[segment][hap] is the edit distance of weight_sequence.  Result: device matrix B (int32, chains x reads in the K2
+ * layout) with B[c][r] = best window sum of chain c for read r, or 2 * (sum of per-segment maxima) when the chain is
+ * shorter than the read's segment count.  sp_pair_minsum_full / _topk on B then give, for every chain pair,
+ * sum_r min(B[i][r], B[j][r]) = the reference's summed best_score (its ED is that minus sum_r optimum_r). */
+sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const int32_t *chain_off, const int32_t *chain_items,
+                                 int64_t n_reads, const int32_t *seg_off, const uint32_t *W, int64_t n_haps,
+                                 sp_dmatrix **out);
+
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
  * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;

@@ -309,6 +309,33 @@ void sp_oracle_pair_minsum_full(const int32_t *D, int64_t R, int64_t A, int nthr
         }
 }
 
+/*
+ * Window scan of containment_score (src/cyp2d6/chaining.rs:683-731) for one (read, chain): best window sum, or
+ * 2 * worst_weight when the chain is shorter than the read's segment count.  B is [n_reads][n_chains] row-major.
+ */
+void sp_oracle_chain_windows(int64_t n_chains, const int32_t *chain_off, const int32_t *chain_items, int64_t n_reads,
+                             const int32_t *seg_off, const uint32_t *W, int64_t n_haps, int32_t *B) {
+    for (int64_t r = 0; r < n_reads; ++r) {
+        int64_t s0 = seg_off[r], w = seg_off[r + 1] - s0;
+        uint64_t worst = 0;
+        for (int64_t t = 0; t < w; ++t) {
+            uint32_t mx = 0;
+            for (int64_t k = 0; k < n_haps; ++k) if (W[(s0 + t) * n_haps + k] > mx) mx = W[(s0 + t) * n_haps + k];
+            worst += mx;
+        }
+        for (int64_t c = 0; c < n_chains; ++c) {
+            int64_t c0 = chain_off[c], len = chain_off[c + 1] - c0;
+            uint64_t best = 2 * worst;
+            for (int64_t s = 0; s + w <= len; ++s) {
+                uint64_t tot = 0;
+                for (int64_t t = 0; t < w; ++t) tot += W[(s0 + t) * n_haps + chain_items[c0 + s + t]];
+                if (tot < best) best = tot;
+            }
+            B[r * n_chains + c] = (int32_t)(best > 0x7FFFFFFF ? 0x7FFFFFFF : best);
+        }
+    }
+}
+
 int sp_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
     "sp_score_spans": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), _P, _P, _P]),
+    "sp_chain_window_scores": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(_P)]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
     "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
@@ -203,6 +204,23 @@ class Context:
         ts, ps = _seqset(tb, to), _seqset(pb, po)
         self._check(self._lib.sp_score_spans(self._h, C.byref(ts), C.byref(ps), D.ctypes.data, S.ctypes.data, E.ctypes.data))
         return D, S, E
+
+    def chain_window_scores(self, chains, read_weights, n_haps: int) -> "DMatrix":
+        """K3 chain windows.  chains: list of lists of haplotype indices; read_weights: per read an array
+        [n_segments_of_read, n_haps] of edit distances.  Returns the device matrix B (chains x reads)."""
+        coff = np.zeros(len(chains) + 1, dtype=np.int32)
+        if len(chains):
+            np.cumsum([len(c) for c in chains], out=coff[1:])
+        items = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in chains]) if len(chains) and coff[-1] else np.zeros(1, np.int32), dtype=np.int32)
+        soff = np.zeros(len(read_weights) + 1, dtype=np.int32)
+        if len(read_weights):
+            np.cumsum([len(w) for w in read_weights], out=soff[1:])
+        W = (np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=np.uint32).reshape(-1, n_haps) for w in read_weights]), dtype=np.uint32)
+             if len(read_weights) and soff[-1] else np.zeros((1, max(n_haps, 1)), np.uint32))
+        h = _P()
+        self._check(self._lib.sp_chain_window_scores(self._h, len(chains), coff.ctypes.data, items.ctypes.data, len(read_weights),
+                                                     soff.ctypes.data, W.ctypes.data, n_haps, C.byref(h)))
+        return DMatrix(self, h, len(read_weights), len(chains), False)
 
     # -- K2 ---------------------------------------------------------------------------------
     def pair_minsum_topk(self, d, k: int = 10, i_begin: int = 0, i_end: Optional[int] = None, d2=None):

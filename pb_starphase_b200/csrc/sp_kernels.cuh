@@ -353,6 +353,51 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
 }
 
 // ------------------------------------------------------------------------------------------
+// K3 chain windows: B[c][r] = min over windows s of chain c of sum_t W[r][t][chain_c[s + t]], or 2 * worst_r
+// when the chain is shorter than the read's segment count -- the inner loop of containment_score
+// (src/cyp2d6/chaining.rs:683-731) hoisted out of the chain-pair loop: for a pair (i, j) the reference's
+// best_score is min(B[i][r], B[j][r]), so K2 on B gives the ED term of every pair (chaining.rs:470-485).
+// One thread per (read, chain); reads contiguous in the output (the K2 layout).
+// ------------------------------------------------------------------------------------------
+struct ChainWinParams {
+    const int32_t *chain_off;    // [n_chains + 1]
+    const int32_t *chain_items;  // consensus (haplotype) indices
+    const int32_t *seg_off;      // [n_reads + 1] first segment row of each read in W
+    const uint32_t *W;           // [n_segments][n_haps] edit distances
+    int32_t *B;                  // [n_chains][ld]
+    long long ld;
+    int n_chains, n_reads, n_haps;
+};
+
+__global__ void __launch_bounds__(256) k3_chain_windows(const ChainWinParams p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (r >= p.n_reads) return;
+    const int s0 = p.seg_off[r], w = p.seg_off[r + 1] - s0;
+    const int c0 = p.chain_off[c], len = p.chain_off[c + 1] - c0;
+    uint32_t best;
+    if (len < w) {
+        unsigned long long worst = 0;  // 2 * sum_t max_k W[r][t][k]
+        for (int t = 0; t < w; ++t) {
+            uint32_t mx = 0;
+            for (int k = 0; k < p.n_haps; ++k) mx = max(mx, p.W[static_cast<long long>(s0 + t) * p.n_haps + k]);
+            worst += mx;
+        }
+        best = static_cast<uint32_t>(min(2ull * worst, 0x7FFFFFFFull));
+    } else {
+        best = 0xFFFFFFFFu;
+        for (int s = 0; s + w <= len; ++s) {
+            uint32_t tot = 0;
+            for (int t = 0; t < w; ++t)
+                tot += p.W[static_cast<long long>(s0 + t) * p.n_haps + p.chain_items[c0 + s + t]];
+            best = min(best, tot);
+        }
+        best = min(best, 0x7FFFFFFFu);
+    }
+    p.B[static_cast<long long>(c) * p.ld + r] = static_cast<int32_t>(best);
+}
+
+// ------------------------------------------------------------------------------------------
 // Pack kernels
 // ------------------------------------------------------------------------------------------
 

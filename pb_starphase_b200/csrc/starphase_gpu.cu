@@ -885,6 +885,65 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
 }
 
 // ------------------------------------------------------------------------------------------
+// K3 chain windows
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const int32_t *chain_off,
+                                            const int32_t *chain_items, int64_t n_reads, const int32_t *seg_off,
+                                            const uint32_t *W, int64_t n_haps, sp_dmatrix **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out || n_chains < 0 || n_reads < 0 || n_haps < 0 || (n_chains > 0 && (!chain_off || !chain_items)) ||
+        (n_reads > 0 && (!seg_off || !W)))
+        return fail(ctx, SP_ERR_INVALID, "sp_chain_window_scores: bad argument");
+    *out = nullptr;
+    if (n_chains > 65535 * 32ll || n_reads > 0x7FFFFFF0ll || n_haps > 0x7FFFFFF0ll)
+        return fail(ctx, SP_ERR_RANGE, "sp_chain_window_scores: too many chains / reads");
+    const int64_t n_items = n_chains ? chain_off[n_chains] : 0, n_segs = n_reads ? seg_off[n_reads] : 0;
+    for (int64_t c = 0; c < n_chains; ++c)
+        if (chain_off[c + 1] < chain_off[c]) return fail(ctx, SP_ERR_INVALID, "chain offsets must be non-decreasing");
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (seg_off[r + 1] < seg_off[r]) return fail(ctx, SP_ERR_INVALID, "segment offsets must be non-decreasing");
+    for (int64_t q = 0; q < n_items; ++q)
+        if (chain_items[q] < 0 || chain_items[q] >= n_haps) return fail(ctx, SP_ERR_INVALID, "chain item outside [0, n_haps)");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    sp_dmatrix *d = new (std::nothrow) sp_dmatrix();
+    if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
+    d->ctx = ctx; d->nt = n_reads; d->np = n_chains; d->elem_bits = 32; d->ld = (n_reads + 63) / 64 * 64;
+    int32_t *d_coff = nullptr, *d_items = nullptr, *d_soff = nullptr; uint32_t *d_W = nullptr;
+    auto cleanup = [&]() { cudaFree(d_coff); cudaFree(d_items); cudaFree(d_soff); cudaFree(d_W); };
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        return e;
+    };
+    const size_t elems = static_cast<size_t>(std::max<int64_t>(d->np * d->ld, 1));
+    cudaError_t e = cudaMalloc(&d->d, elems * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, elems * 4, ctx->stream);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_coff), chain_off, static_cast<size_t>(n_chains + 1) * 4 * (n_chains > 0));
+    if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_items), chain_items, static_cast<size_t>(n_items) * 4);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_soff), seg_off, static_cast<size_t>(n_reads + 1) * 4 * (n_reads > 0));
+    if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_W), W, static_cast<size_t>(n_segs * n_haps) * 4);
+    if (e == cudaSuccess && n_chains > 0 && n_reads > 0) {
+        ChainWinParams prm;
+        prm.chain_off = d_coff; prm.chain_items = d_items; prm.seg_off = d_soff; prm.W = d_W;
+        prm.B = static_cast<int32_t *>(d->d); prm.ld = d->ld;
+        prm.n_chains = static_cast<int>(n_chains); prm.n_reads = static_cast<int>(n_reads); prm.n_haps = static_cast<int>(n_haps);
+        const dim3 grid(static_cast<unsigned>((n_reads + 255) / 256), static_cast<unsigned>(n_chains));
+        k3_chain_windows<<<grid, 256, 0, ctx->stream>>>(prm);
+        ++ctx->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the caller's host arrays may go away
+    cleanup();
+    if (e != cudaSuccess) {
+        sp_dmatrix_destroy(d);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA,
+                    std::string("sp_chain_window_scores: ") + cudaGetErrorString(e));
+    }
+    *out = d;
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------
 static sp_status k2_check(sp_ctx *ctx, const sp_dmatrix *d) {

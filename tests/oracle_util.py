@@ -50,6 +50,8 @@ class Oracle:
         L.sp_oracle_pair_minsum_full.restype = None
         L.sp_oracle_pair_minsum_full.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.sp_oracle_num_threads.restype = C.c_int
+        L.sp_oracle_chain_windows.restype = None
+        L.sp_oracle_chain_windows.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.sp_oracle_span_batch.restype = None
         L.sp_oracle_span_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
@@ -85,6 +87,19 @@ class Oracle:
         self.lib.sp_oracle_span_batch(tb.ctypes.data, to.ctypes.data, nt, pb.ctypes.data, po.ctypes.data, npat, nthreads,
                                       D.ctypes.data, S.ctypes.data, E.ctypes.data)
         return D, S, E
+
+    def chain_windows(self, chains, read_weights, n_haps: int) -> np.ndarray:
+        """B[r, c]: see sp_oracle_chain_windows."""
+        coff = np.zeros(len(chains) + 1, dtype=np.int32)
+        np.cumsum([len(c) for c in chains], out=coff[1:])
+        items = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in chains] + [np.zeros(1, np.int32)]), dtype=np.int32)
+        soff = np.zeros(len(read_weights) + 1, dtype=np.int32)
+        np.cumsum([len(w) for w in read_weights], out=soff[1:])
+        W = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=np.uint32).reshape(-1, n_haps) for w in read_weights] + [np.zeros((1, n_haps), np.uint32)]), dtype=np.uint32)
+        B = np.zeros((len(read_weights), len(chains)), dtype=np.int32)
+        self.lib.sp_oracle_chain_windows(len(chains), coff.ctypes.data, items.ctypes.data, len(read_weights), soff.ctypes.data,
+                                         W.ctypes.data, n_haps, B.ctypes.data)
+        return B
 
     def pair_minsum_topk(self, D: np.ndarray, k: int, nthreads: int = 0, D2=None):
         D = np.ascontiguousarray(D, dtype=np.int32)

@@ -104,3 +104,60 @@ def test_template_search_shapes(ctx, oracle):
     # reads 0, 2, 4 carry a noisy D6: its span starts right after the 500-bp flank
     for r in (0, 2, 4):
         assert D[r, 0] <= 10 and abs(int(S[r, 0]) - 500) <= 10
+
+
+def _random_chain_case(rng, n_haps, n_chains, n_reads, max_len=15, max_w=6):
+    chains = [rng.integers(0, n_haps, size=int(rng.integers(1, max_len + 1))).tolist() for _ in range(n_chains)]
+    reads = []
+    for _ in range(n_reads):
+        w = int(rng.integers(1, max_w + 1))
+        truth = rng.integers(0, n_haps, size=w)
+        W = rng.integers(20, 400, size=(w, n_haps)).astype(np.uint32)
+        W[np.arange(w), truth] = rng.integers(0, 6, size=w)  # the true consensus of each segment is close
+        reads.append(W)
+    return chains, reads
+
+
+def test_chain_windows_vs_oracle(ctx, oracle):
+    """containment_score's window scan (src/cyp2d6/chaining.rs:683-731) per (read, chain), incl. chains shorter
+    than the read (2 x worst sentinel), single-segment reads and single-member chains."""
+    rng = np.random.default_rng(41)
+    chains, reads = _random_chain_case(rng, n_haps=7, n_chains=90, n_reads=130)
+    chains += [[0], [6, 6, 6], list(range(7))]
+    B = ctx.chain_window_scores(chains, reads, 7)
+    got = B.to_host()
+    want = oracle.chain_windows(chains, reads, 7)
+    assert got.shape == (len(reads), len(chains)) and (got == want).all()
+    # pair sums on the device matrix == oracle pair sums on the oracle matrix
+    S = ctx.pair_minsum_full(B)
+    assert (S == oracle.pair_minsum_full(want)).all()
+    top = ctx.pair_minsum_topk(B, 10)
+    assert top == oracle.pair_minsum_topk(want, 10)
+
+
+def test_chain_pairs_config4_shape(ctx, oracle):
+    """P = 2,000 chains x R_c = 2,000 reads, w <= 6.  Full B against the oracle; the 2e6 pair
+    sums against numpy on a seeded sample of pairs plus the oracle's top-10."""
+    rng = np.random.default_rng(42)
+    chains, reads = _random_chain_case(rng, n_haps=24, n_chains=2000, n_reads=2000)
+    B = ctx.chain_window_scores(chains, reads, 24)
+    got = B.to_host()
+    want = oracle.chain_windows(chains, reads, 24)
+    assert (got == want).all()
+    S = ctx.pair_minsum_full(B)
+    for _ in range(300):
+        i = int(rng.integers(0, 2000)); j = int(rng.integers(i, 2000))
+        assert int(S[i, j]) == int(np.minimum(want[:, i], want[:, j]).sum())
+    assert (np.tril(S, -1) == 0).all()
+    assert ctx.pair_minsum_topk(B, 10) == oracle.pair_minsum_topk(want, 10)
+
+
+def test_chain_windows_empty_and_errors(ctx):
+    import pb_starphase_b200 as sp
+
+    B = ctx.chain_window_scores([], [np.zeros((2, 3), np.uint32)], 3)
+    assert B.to_host().shape == (1, 0)
+    B = ctx.chain_window_scores([[0, 1]], [], 3)
+    assert B.to_host().shape == (0, 1)
+    with pytest.raises(sp.SpError):
+        ctx.chain_window_scores([[0, 5]], [np.zeros((1, 3), np.uint32)], 3)  # hap index outside [0, n_haps)
