@@ -41,7 +41,7 @@ struct K1Params {
     int n_groups, n_tiles;
     int out16;
     int prefix_mode;                // SP_PREFIX: top row delta +1
-    uint32_t one, m1;               // +1 and -1 (0xFFFFFFFF), passed at run time so `x * one + y` stays an IMAD (FMA pipe)
+    uint32_t one, m1, sixteen;      // +1, -1 (0xFFFFFFFF), 16: passed at run time so `x * one + y` stays an IMAD (FMA pipe)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -155,12 +155,10 @@ __device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t c
     // horizontal delta of the lane's last row: carry for the next lane, score for a last lane
     cph = __funnelshift_l(ph[U - 1], cph, 1);
     cmh = __funnelshift_l(mh[U - 1], cmh, 1);
-    score += static_cast<int>(ph[U - 1] >> 31) - static_cast<int>(mh[U - 1] >> 31);
-    if (TRACK_END) {
+    if (TRACK_END) {  // per-column score and arg-min; without end columns the caller does it per chunk from cph/cmh
+        score += static_cast<int>(ph[U - 1] >> 31) - static_cast<int>(mh[U - 1] >> 31);
         ++col;
         if (score < best) { best = score; best_col = col; }
-    } else {
-        best = min(best, score);
     }
 #pragma unroll
     for (int u = U - 1; u >= 0; --u) {
@@ -175,9 +173,29 @@ __device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t c
     Y <<= 1;
 }
 
+// Score bookkeeping without end columns: the 8 horizontal deltas of a chunk arrive as two 4-column nibble pairs
+// (plus bits, minus bits); a 256-entry table gives each nibble pair's total and its lowest running prefix, so the
+// running score and its minimum advance once per chunk with two table reads (LSU) and a few adds (FMA pipe)
+// instead of three ALU-pipe instructions per column.
+struct ScoreLut {
+    int8_t delta[256];   // index = plus4 | minus4 << 4, bit 3 = first column of the four
+    int8_t minpre[256];  // lowest partial sum after 1..4 columns
+};
+__device__ __forceinline__ void fill_score_lut(ScoreLut *lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        int s = 0, mn = 127;
+        for (int k = 3; k >= 0; --k) {
+            s += ((i >> k) & 1) - ((i >> (4 + k)) & 1);
+            mn = min(mn, s);
+        }
+        lut->delta[i] = static_cast<int8_t>(s);
+        lut->minpre[i] = static_cast<int8_t>(mn);
+    }
+}
+
 template <int U, bool TRACK_END>
 __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s_text, int nch, int text0,
-                                            const K1Params &p) {
+                                            const K1Params &p, const ScoreLut *lut) {
     constexpr int V = vec_width(U);
     const int lane = threadIdx.x & 31;
     const uint32_t pat = blob[PEQ_ROWS * 32 * U + lane];
@@ -203,17 +221,33 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
         if (first) cin = cin_first;
         const int idx = s - lane;
         if (static_cast<unsigned>(idx) < static_cast<unsigned>(nch)) {
-            const uint2 w = s_text[idx];
+            // one byte load per column (LSU pipe) instead of shift+mask on the ALU pipe, which is the bound
+            // (inline PTX so the compiler does not fuse them back into one wide load plus eight extractions)
+            const uint32_t tb = smem_u32(s_text + idx);
+            uint32_t codes[K1_CHUNK];
+            static_assert(K1_CHUNK == 8, "eight explicit byte loads below");
+            asm("ld.shared.u8 %0, [%8];\n\tld.shared.u8 %1, [%8+1];\n\tld.shared.u8 %2, [%8+2];\n\tld.shared.u8 %3, [%8+3];\n\t"
+                "ld.shared.u8 %4, [%8+4];\n\tld.shared.u8 %5, [%8+5];\n\tld.shared.u8 %6, [%8+6];\n\tld.shared.u8 %7, [%8+7];"
+                : "=r"(codes[0]), "=r"(codes[1]), "=r"(codes[2]), "=r"(codes[3]), "=r"(codes[4]), "=r"(codes[5]),
+                  "=r"(codes[6]), "=r"(codes[7])
+                : "r"(tb));
+            const uint32_t end_flag = codes[K1_CHUNK - 1] & 0x80u;
+            codes[K1_CHUNK - 1] &= 0x7Fu;
             uint32_t X = cin << 24, Y = cin << 16;
-            uint32_t cph = 0, cmh = 0;
+            uint32_t cphA = 0, cmhA = 0, cphB = 0, cmhB = 0;  // columns 0-3 and 4-7
 #pragma unroll
-            for (int c = 0; c < K1_CHUNK; ++c) {
-                const uint32_t word = (c < 4) ? w.x : w.y;
-                const uint32_t code = (word >> (8 * (c & 3))) & (c == 7 ? 0x7Fu : 0xFFu);
-                column_step<U, TRACK_END>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
+            for (int c = 0; c < K1_CHUNK; ++c)
+                column_step<U, TRACK_END>(peq_lane, codes[c], p.one, p.m1, npv, mv, X, Y, c < 4 ? cphA : cphB,
+                                          c < 4 ? cmhA : cmhB, score, best, col, best_col);
+            const uint32_t iA = cmhA * p.sixteen + cphA, iB = cmhB * p.sixteen + cphB;  // IMAD: table indices
+            carry_out = (cphA * p.sixteen + cphB) | ((iA & 0xF0u) << 8) | ((iB & 0xF0u) << 4);
+            if (!TRACK_END) {
+                const int dA = lut->delta[iA], mA = lut->minpre[iA], dB = lut->delta[iB], mB = lut->minpre[iB];
+                const int sA = score + dA;
+                best = min(best, min(score + mA, sA + mB));
+                score = sA + dB;
             }
-            carry_out = cph | (cmh << 8);
-            if (static_cast<int>(w.y) < 0) {  // last chunk of a text: emit + reset
+            if (end_flag) {  // last chunk of a text: emit + reset
                 if (last) {
                     const long long o = static_cast<long long>(pat) * p.ld + (text0 + tcount);
                     if (p.out16) reinterpret_cast<uint16_t *>(p.out)[o] = static_cast<uint16_t>(best);
@@ -238,12 +272,14 @@ template <int U, bool TRACK_END>
 __global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ ScoreLut lut;
     constexpr int BW = blob_words(U);
     uint32_t *s_blob = reinterpret_cast<uint32_t *>(smem_raw);
     uint2 *s_text = reinterpret_cast<uint2 *>(smem_raw + K1_WARPS * BW * 4);
     const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    fill_score_lut(&lut);
     __syncthreads();
 
     uint32_t parity = 0;
@@ -263,7 +299,7 @@ __global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K
         }
         mbar_wait(&mbar, parity);
         parity ^= 1u;
-        k1_warp_run<U, TRACK_END>(s_blob + warp * BW, s_text, nch, p.tile_text0[tile], p);
+        k1_warp_run<U, TRACK_END>(s_blob + warp * BW, s_text, nch, p.tile_text0[tile], p, &lut);
         __syncthreads();  // everyone is done with this item's shared memory
     }
 }

@@ -629,7 +629,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         prm.ld = ld;
         prm.n_groups = pc.n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
         prm.prefix_mode = p->mode == SP_PREFIX;
-        prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
+        prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.sixteen = 16u;
         const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
         if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
         const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
