@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SP_BENCH_SCALE", "1.0")),
                     help="debug only: shrink the allele set (a scaled run is NOT a valid bench number)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
+    ap.add_argument("--cohort-samples", type=int, default=6,
+                    help="samples per GPU for the cohort leg (BASELINE configs[4], reported under `cohort`); 0 disables it")
     return ap.parse_args()
 
 
@@ -166,6 +168,94 @@ def run_reference(args):
 
 def workload_name(n):
     return f"hla_wgs30x: {READS_PER_GPU * n} reads x 12,451 DNA + 19,629 cDNA alleles (BASELINE configs[1]" + (")" if n == 1 else f", reads x{n}, alleles sharded {n} ways)")
+
+
+# ---------------------------------------------------------------------------------------------
+# cohort leg (BASELINE configs[4]): independent samples, one at a time per GPU
+# ---------------------------------------------------------------------------------------------
+def run_cohort(ctx, w, n_samples, rank, world):
+    """Each sample = 64 HLA-A + 64 HLA-B reads (DNA + cDNA targets) against the full resident allele sets (K1 x2, K2
+    per gene, per-read best allele read back) + one CYP2D6 case (39-template search over 256 reads, weight_sequence
+    spans for ~650 segments x 24 consensuses, chain windows + pair top-10 over 200 chains).  Samples are independent:
+    ranks work through disjoint samples with no exchange (replicas).  Returns (seconds, samples, cells)."""
+    import pb_starphase_b200 as sp
+    from pb_starphase_b200 import synth
+
+    pack = sp.binding.pack_sequences
+    P_dna, P_cdna = ctx.patterns(w["dna"]), ctx.patterns(w["cdna"])  # the whole database on every rank
+    per_gene = 64
+    genes = list(w["gene_views"].items())
+
+    dbg = os.environ.get("SP_COHORT_DEBUG") == "1"
+    marks = []
+
+    def mark(name):
+        if dbg:
+            ctx.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    def one_sample(sid):
+        cells = 0
+        sel = []
+        marks.clear()
+        mark("start")
+        for _, (_, _, _, col0, nr) in genes:
+            lo = col0 + (sid * per_gene) % max(nr - per_gene, 1)
+            sel += list(range(lo, lo + per_gene))
+        reads = [w["reads"][i] for i in sel]
+        ctg = [w["ctargets"][i] for i in sel]
+        T, Tc = ctx.targets(pack(reads)), ctx.targets(pack(ctg))
+        mark("hla_targets")
+        dd = ctx.score_device(T, P_dna, elem_bits=16)
+        if dbg:
+            marks.append((f"k1dna_kernel={ctx.last_kernel_ms(0):.1f}ms;wall", time.perf_counter()))
+        dc = ctx.score_device(Tc, P_cdna, elem_bits=16)
+        if dbg:
+            marks.append((f"k1cdna_kernel={ctx.last_kernel_ms(0):.1f}ms;wall", time.perf_counter()))
+        cells += sum(map(len, reads)) * P_dna.total_len + sum(map(len, ctg)) * P_cdna.total_len
+        calls = {}
+        for g, (gene, (drow, crow, na, _, _)) in enumerate(genes):
+            vd = ctx.wrap_dmatrix(dd.device_ptr + 2 * (drow * dd.ld + g * per_gene), per_gene, na, dd.ld, 16)
+            vc = ctx.wrap_dmatrix(dc.device_ptr + 2 * (crow * dc.ld + g * per_gene), per_gene, na, dc.ld, 16)
+            calls[gene] = ctx.pair_minsum_topk(vc, 10, d2=vd)
+            vd.close(); vc.close()
+        mark("hla_k1_k2")
+        best_allele = dd.to_host_u16().argmin(axis=1)  # realign_record-style per-read assignment
+        mark("hla_readback")
+        for h in (dd, dc, T, Tc):
+            h.close()
+        c = cyp_inputs[sid]
+        Dt = ctx.score_batch(c["reads"], c["templates"])                      # find_base_type_in_sequence
+        cells += sum(map(len, c["reads"])) * sum(map(len, c["templates"]))
+        mark("cyp_templates")
+        Dw, Sw, Ew = ctx.score_spans(c["consensuses"], c["segments"])          # weight_sequence (+ overlap spans)
+        cells += 2 * sum(map(len, c["consensuses"])) * sum(map(len, c["segments"]))
+        mark("cyp_spans")
+        Wt = np.ascontiguousarray(Dw.T.astype(np.uint32))                       # [segment][consensus]
+        order = np.argsort(c["seg_read"], kind="stable")
+        bounds = np.searchsorted(c["seg_read"][order], np.arange(len(c["reads"]) + 1))
+        Wr = [Wt[order[bounds[r]:bounds[r + 1]]] for r in range(len(c["reads"])) if bounds[r + 1] > bounds[r]]
+        B = ctx.chain_window_scores(c["chains"], Wr, len(c["consensuses"]))
+        calls["CYP2D6"] = ctx.pair_minsum_topk(B, 10)
+        B.close()
+        mark("cyp_chains")
+        if dbg:
+            print("cohort sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+        return cells, (calls, int(best_allele[0]), int(Dt[0, 0]), int(Sw[0, 0]), int(Ew[0, 0]))
+
+    sids = [rank + world * k for k in range(n_samples)]
+    cyp_inputs = {sid: synth.cyp2d6_sample(1000 + sid) for sid in sids}  # host-side inputs exist before the clock starts
+    one_sample(sids[0])  # warm-up (first-use allocations)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    cells = 0
+    for sid in sids:
+        c, _ = one_sample(sid)
+        cells += c
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    P_dna.close(); P_cdna.close()
+    return dt, n_samples, cells
 
 
 # ---------------------------------------------------------------------------------------------
@@ -300,11 +390,20 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     assert res_e2e == result, "e2e and device-resident runs disagree"
 
+    cohort_s, cohort_n, cohort_cells = 0.0, 0, 0
+    if args.cohort_samples > 0:
+        barrier()
+        cohort_s, cohort_n, cohort_cells = run_cohort(ctx, w, args.cohort_samples, rank, world)
+        barrier()
+
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s, k1_avg_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, e2e_s, k1_avg_ms, cohort_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, k1_avg_ms = (float(x) for x in t.cpu())
+        ms_total, e2e_s, k1_avg_ms, cohort_s = (float(x) for x in t.cpu())
+        ct = torch.tensor([cohort_n, cohort_cells], dtype=torch.int64, device=dev)
+        dist.all_reduce(ct)
+        cohort_n, cohort_cells = (int(x) for x in ct.cpu())
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -335,6 +434,12 @@ def run_ours(args):
                      note="per step: sp_targets_create x2 from pinned host sequences, K1 x2, K2 per gene, u16 distance matrices "
                           "[reads x alleles] + top-k records back to pinned host memory"),
             gpu_launches=int(launches),
+            cohort=(dict(samples_per_s=cohort_n / cohort_s, samples=cohort_n, ms_per_sample_per_gpu=cohort_s / (cohort_n / world) * 1e3,
+                         gcups=cohort_cells / cohort_s / 1e9, scaling="replicas: independent samples round-robin over ranks, no exchange",
+                         sample="64 HLA-A + 64 HLA-B reads (DNA + cDNA) x full allele sets (K1, K2 top-10 per gene, per-read best allele) + "
+                                "CYP2D6: 256 reads x 39 templates, ~650 segments x 24 consensuses with spans, 200 chains (chain windows + pair "
+                                "top-10); host buffers in, calls out (BASELINE configs[4], SURVEY 8d.5)")
+                    if cohort_n else None),
             roofline=dict(bound="int_alu", kernel="k1_infix (DNA launches, all lane-width classes)", achieved=achieved / 1e12,
                           peak=int_peak2 / 1e12, unit="Tops/s (algorithmic INT32 lane-ops, 23/64 per cell, SURVEY 8d)",
                           frac=achieved / int_peak2,

@@ -123,3 +123,63 @@ def hla_wgs_workload(seed: int = DEFAULT_SEED, n_reads: int = 2048, scale: float
             ctargets.append(one[0])
         genes[gene] = dict(dna=dna, cdna=cdna, reads=reads, ctargets=ctargets, src=src)
     return genes
+
+
+# ---------------------------------------------------------------------------------------------
+# CYP2D6-shaped sample: region lengths of src/cyp2d6/definitions.rs:13-14, :137-172
+# ---------------------------------------------------------------------------------------------
+CYP_REGION_LENS = dict(d6=6165, d7=5938, star5=3500, rep6=2772, rep7=2772, spacer=1564, link=2919)
+
+
+def cyp2d6_templates(rng: np.random.Generator):
+    """The 39 search templates of generate_cyp_hybrids (src/cyp2d6/definitions.rs:346-464): D6, D7 (97 % identical),
+    *5 signature, 16 + 16 D6/D7 hybrids, REP6, REP7, spacer, link."""
+    d6 = random_seq(rng, CYP_REGION_LENS["d6"])
+    d7 = mutate(rng, d6, int(0.03 * len(d6)), 12)[: CYP_REGION_LENS["d7"]]
+    regions = dict(d6=d6, d7=d7, star5=random_seq(rng, CYP_REGION_LENS["star5"]),
+                   rep6=random_seq(rng, CYP_REGION_LENS["rep6"]), spacer=random_seq(rng, CYP_REGION_LENS["spacer"]),
+                   link=random_seq(rng, CYP_REGION_LENS["link"]))
+    regions["rep7"] = mutate(rng, regions["rep6"], 60, 3)
+    hybrids = []
+    for k in range(16):
+        cut = 350 + 340 * k
+        hybrids.append(np.concatenate([d6[:cut], d7[cut:]]))
+        hybrids.append(np.concatenate([d7[:cut], d6[cut:]]))
+    templates = [d6, d7, regions["star5"]] + hybrids + [regions["rep6"], regions["rep7"], regions["spacer"], regions["link"]]
+    assert len(templates) == 39
+    return regions, [t.tobytes() for t in templates]
+
+
+def cyp2d6_sample(seed: int, n_reads: int = 256, n_consensus: int = 24, n_chains: int = 200):
+    """One sample's CYP2D6 inputs: templates (39), consensuses (K haplotype-region sequences), reads (several regions
+    in a row + flanks), per-read segments (the region slices weight_sequence scores, src/cyp2d6/caller.rs:435-517),
+    and candidate chains over the consensus indices."""
+    rng = np.random.default_rng([seed, 2, 6])
+    regions, templates = cyp2d6_templates(rng)
+    order = ["rep6", "d6", "link", "rep7", "spacer", "d7"]  # the reference haplotype layout
+    cons, cons_kind = [], []
+    for k in range(n_consensus):
+        kind = order[k % len(order)]
+        cons.append(mutate(rng, regions[kind], int(rng.integers(0, 12)), int(rng.integers(0, 2))).tobytes())
+        cons_kind.append(kind)
+    by_kind = {kind: [i for i, kk in enumerate(cons_kind) if kk == kind] for kind in order}
+    reads, segments, seg_read = [], [], []
+    for r in range(n_reads):
+        start = int(rng.integers(0, len(order)))
+        w = int(rng.integers(1, 5))
+        parts = []
+        for t in range(w):
+            kind = order[(start + t) % len(order)]
+            c = cons[int(rng.choice(by_kind[kind]))]
+            seg, _ = hifi_reads(rng, [c], 1, flank=0, lo=0, hi=1 << 30)
+            parts.append(seg[0])
+            segments.append(seg[0])
+            seg_read.append(r)
+        reads.append(random_seq(rng, 300).tobytes() + b"".join(parts) + random_seq(rng, 300).tobytes())
+    chains = []
+    for _ in range(n_chains):
+        start = int(rng.integers(0, len(order)))
+        ln = int(rng.integers(1, 10))
+        chains.append([int(rng.choice(by_kind[order[(start + t) % len(order)]])) for t in range(ln)])
+    return dict(templates=templates, consensuses=cons, reads=reads, segments=segments,
+                seg_read=np.asarray(seg_read, dtype=np.int32), chains=chains)
