@@ -176,6 +176,35 @@ sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const int32_t *c
                                  int64_t n_reads, const int32_t *seg_off, const uint32_t *W, int64_t n_haps,
                                  sp_dmatrix **out);
 
+/* ---- K4: traceback alignment of selected pairs ------------------------------------------ */
+/* What the host reads from a minimap2::Mapping at the HLA call sites (src/hla/processed_match.rs:53-100:
+ * query_start / query_end / target_start / target_end / alignment.nm / alignment.cigar with the EQX flag
+ * of src/hla/caller.rs:1395), for the pattern (minimap2's query: the allele) placed inside the text
+ * (minimap2's target: the consensus / read):
+ *   dist = nm + (|P| - (p_end - p_start)) = D(P, T); nm = edits inside the aligned span;
+ *   [p_start, p_end) aligned part of the pattern (clipped ends are the "unmapped" bases of MappingStats,
+ *   src/data_types/mapping.rs:7-22); [t_start, t_end) aligned part of the text, t_end = the smallest end of
+ *   a best placement (the end column of K1 / K3);
+ *   cigar[cigar_off .. cigar_off + n_cigar) = run-length entries (len << 4) | op, BAM op codes
+ *   1 = I (pattern base without a text base), 2 = D (text base without a pattern base), 7 = '=', 8 = X,
+ *   no clip entries -- exactly what process_mm_cigar (processed_match.rs:210-263) iterates over.
+ * The path is the canonical unit-cost optimum: walking back from (|P|, t_end) the diagonal is taken whenever it
+ * explains the cell, then I, then D (gaps end up left-aligned, as in ksw2). */
+typedef struct sp_align_rec {
+    int32_t dist, nm;
+    int32_t p_start, p_end;
+    int32_t t_start, t_end;
+    int32_t n_cigar, _pad;
+    int64_t cigar_off;
+} sp_align_rec;
+/* Align pair q = (targets[pair_target[q]], patterns[pair_pattern[q]]) for q in [0, n_pairs); recs has n_pairs
+ * entries; cigar has room for cigar_cap entries.  *cigar_used (optional) receives the entries needed; when that
+ * exceeds cigar_cap the call fails with SP_ERR_RANGE and nothing else is written
+ * (sum over pairs of |P| + min(|T|, 2|P|) + 1 always suffices). */
+sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int64_t n_pairs,
+                         const int32_t *pair_target, const int32_t *pair_pattern, sp_align_rec *recs,
+                         uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used);
+
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
  * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;

@@ -204,6 +204,67 @@ void sp_oracle_span_batch(const uint8_t *tbases, const int64_t *toffs, int64_t n
 }
 
 /*
+ * Traceback alignment (checker of the C-ABI's sp_align_pairs): the fields the reference reads from a
+ * minimap2::Mapping in HlaProcessedMatch::add_mapping (src/hla/processed_match.rs:53-100) for pattern P
+ * (minimap2's query, the allele) inside text T (its target, the consensus): aligned spans, nm, and the EQX
+ * CIGAR that process_mm_cigar (processed_match.rs:210-263) walks (1 = I, 2 = D, 7 = '=', 8 = X; clips are the
+ * unaligned pattern ends and are not CIGAR entries).  Full (m+1) x (n+1) int32 matrix, then the canonical walk
+ * back from (m, e), e = smallest end column of a best placement: diagonal if D[i-1][j-1] + cost == D[i][j],
+ * else up if D[i-1][j] + 1 == D[i][j] ('I'), else left ('D'); column 0 only goes up.  Leading / trailing 'I'
+ * runs become p_start / |P| - p_end.  rec = {dist, nm, p_start, p_end, t_start, t_end, n_cigar}; returns the
+ * number of run-length entries written to cigar (forward order), or -1 if cap is too small.
+ */
+int64_t sp_oracle_align(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, int32_t *rec, uint32_t *cigar,
+                        int64_t cap) {
+    const int64_t W = n + 1;
+    int32_t *D = (int32_t *)calloc((size_t)((m + 1) * W), sizeof(int32_t));
+    for (int64_t j = 0; j <= n; ++j) D[j] = 0;
+    for (int64_t i = 1; i <= m; ++i) {
+        int cp = sp_code(P[i - 1]);
+        int32_t *row = D + i * W, *up = row - W;
+        row[0] = (int32_t)i;
+        for (int64_t j = 1; j <= n; ++j) {
+            int ct = sp_code(T[j - 1]);
+            int32_t v = up[j - 1] + ((cp == ct && cp < 4) ? 0 : 1);
+            if (up[j] + 1 < v) v = up[j] + 1;
+            if (row[j - 1] + 1 < v) v = row[j - 1] + 1;
+            row[j] = v;
+        }
+    }
+    int64_t e = 0;
+    for (int64_t j = 1; j <= n; ++j) if (D[m * W + j] < D[m * W + e]) e = j;
+    const int32_t d = D[m * W + e];
+    uint32_t *ops = (uint32_t *)malloc((size_t)(m + n + 2) * sizeof(uint32_t)); /* backward run-length list */
+    int64_t nops = 0, i = m, j = e;
+    uint32_t cur_op = 0, cur_len = 0;
+    while (i > 0) {
+        uint32_t op;
+        if (j == 0) { op = 1; --i; }
+        else {
+            int match = sp_code(P[i - 1]) == sp_code(T[j - 1]) && sp_code(P[i - 1]) < 4;
+            int32_t v = D[i * W + j];
+            if (D[(i - 1) * W + j - 1] + (match ? 0 : 1) == v) { op = match ? 7 : 8; --i; --j; }
+            else if (D[(i - 1) * W + j] + 1 == v) { op = 1; --i; }
+            else { op = 2; --j; }
+        }
+        if (op == cur_op) ++cur_len;
+        else { if (cur_len) ops[nops++] = (cur_len << 4) | cur_op; cur_op = op; cur_len = 1; }
+    }
+    if (cur_len) ops[nops++] = (cur_len << 4) | cur_op;
+    free(D);
+    int64_t lo = 0, hi = nops; /* ops[hi-1] is the first entry in forward order */
+    int32_t clip_s = 0, clip_e = 0;
+    if (hi > lo && (ops[hi - 1] & 15u) == 1) { clip_s = (int32_t)(ops[hi - 1] >> 4); --hi; }
+    if (hi > lo && (ops[lo] & 15u) == 1) { clip_e = (int32_t)(ops[lo] >> 4); ++lo; }
+    rec[0] = d; rec[1] = d - clip_s - clip_e; rec[2] = clip_s; rec[3] = (int32_t)m - clip_e;
+    rec[4] = (int32_t)j; rec[5] = (int32_t)e; rec[6] = (int32_t)(hi - lo);
+    if (hi - lo > cap) { free(ops); return -1; }
+    for (int64_t k = 0; k < hi - lo; ++k) cigar[k] = ops[hi - 1 - k];
+    free(ops);
+    return hi - lo;
+}
+
+/*
  * Diplotype pair scoring in the north_star ("pre-v0.13") form: for every
  * unordered allele pair i <= j, S[i,j] = sum_r min(D[r,i], D[r,j]); keep the k
  * smallest by the lexicographic key (S, [S2,] i, j) -- the same (score, index1,

@@ -31,6 +31,12 @@ class PairRec(C.Structure):
     _fields_ = [("score", C.c_uint64), ("score2", C.c_uint64), ("i", C.c_uint32), ("j", C.c_uint32), ("c1", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class AlignRec(C.Structure):
+    _fields_ = [("dist", C.c_int32), ("nm", C.c_int32), ("p_start", C.c_int32), ("p_end", C.c_int32),
+                ("t_start", C.c_int32), ("t_end", C.c_int32), ("n_cigar", C.c_int32), ("_pad", C.c_int32),
+                ("cigar_off", C.c_int64)]
+
+
 def lib_path() -> Path:
     return Path(__file__).resolve().parent / "libstarphase_gpu.so"
 
@@ -69,6 +75,8 @@ SIGNATURES = {
     "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
     "sp_score_spans": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), _P, _P, _P]),
+    "sp_align_pairs": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
+                                 C.POINTER(C.c_int64)]),
     "sp_chain_window_scores": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(_P)]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
@@ -204,6 +212,32 @@ class Context:
         ts, ps = _seqset(tb, to), _seqset(pb, po)
         self._check(self._lib.sp_score_spans(self._h, C.byref(ts), C.byref(ps), D.ctypes.data, S.ctypes.data, E.ctypes.data))
         return D, S, E
+
+    def align_pairs(self, targets, patterns, pairs):
+        """K4: traceback alignment of the listed (target index, pattern index) pairs.  Returns one dict per pair with
+        the minimap2::Mapping fields the reference reads (src/hla/processed_match.rs:53-100): dist, nm,
+        p_start/p_end (pattern = minimap2's query), t_start/t_end (text = its target) and cigar = [(len, op), ...]
+        with BAM op codes 1 = I, 2 = D, 7 = '=', 8 = X."""
+        tb, to = targets if isinstance(targets, tuple) else pack_sequences(targets)
+        pb, po = patterns if isinstance(patterns, tuple) else pack_sequences(patterns)
+        pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        n = len(pairs)
+        pt, pp = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        tl, pl = np.diff(to), np.diff(po)
+        ok = n and pt.min() >= 0 and pt.max() < len(tl) and pp.min() >= 0 and pp.max() < len(pl)  # else the library rejects it
+        cap = int((pl[pp] + np.minimum(tl[pt], 2 * pl[pp]) + 1).sum()) if ok else 0
+        recs = (AlignRec * max(n, 1))()
+        cig = np.zeros(max(cap, 1), dtype=np.uint32)
+        used = C.c_int64(0)
+        ts, ps = _seqset(tb, to), _seqset(pb, po)
+        self._check(self._lib.sp_align_pairs(self._h, C.byref(ts), C.byref(ps), n, pt.ctypes.data, pp.ctypes.data, recs,
+                                             cig.ctypes.data, cap, C.byref(used)))
+        out = []
+        for r in recs[:n]:
+            c = cig[r.cigar_off:r.cigar_off + r.n_cigar]
+            out.append({"dist": r.dist, "nm": r.nm, "p_start": r.p_start, "p_end": r.p_end, "t_start": r.t_start,
+                        "t_end": r.t_end, "cigar": [(int(x) >> 4, int(x) & 15) for x in c]})
+        return out
 
     def chain_window_scores(self, chains, read_weights, n_haps: int) -> "DMatrix":
         """K3 chain windows.  chains: list of lists of haplotype indices; read_weights: per read an array

@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libstarphase_gpu.so"
-SOURCES = ["starphase_gpu.cu", "sp_kernels.cuh", "sp_addchain.inc", "../../include/starphase_gpu.h"]
+SOURCES = ["starphase_gpu.cu", "sp_kernels.cuh", "sp_align.cuh", "sp_addchain.inc", "../../include/starphase_gpu.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,187 @@
+// sp_align.cuh -- K4: traceback alignment of selected (text, pattern) pairs (sm_100a only).
+//
+// Gives the host everything it reads from a minimap2::Mapping at the HLA call sites
+// (src/hla/processed_match.rs:53-100 of the reference: query_start / query_end / target_start /
+// target_end / nm / EQX cigar), so HlaProcessedMatch::add_mapping, process_mm_cigar (:210-263) and
+// is_better_match (:103-184) run unchanged on GPU output, and MappingStats' (seq_len, nm, unmapped)
+// split (src/data_types/mapping.rs:7-22) is available for the result JSON.  Row N2 of SURVEY.md §8f.
+//
+// One warp per pair, pattern-stationary like K1 (one pattern per bin, lane width ALN_U):
+//   pass 1  infix distance d and the smallest end column e of a best placement (K1 with end columns)
+//   pass 2  the same recurrence over the text window [e - (m + d), e) -- every optimal placement ending at
+//           e lies inside it -- keeping per column the vertical deltas (~Pv, Mv are the state anyway; only
+//           ~Pv is needed) and Hyyro's diagonal-zero vector D0 in HBM scratch
+//   pass 3  lane 0 walks back from (m, e): diagonal when it explains the cell ('=' or 'X'), else up ('I',
+//           a pattern base without a text base), else left ('D').  Taking the diagonal first while walking
+//           backwards left-aligns gaps, the convention of minimap2's ksw2.  Leading / trailing 'I' runs are
+//           the clipped pattern ends (query_start, query_len - query_end).
+// The CIGAR is run-length encoded BAM style, (len << 4) | op with op 1 = I, 2 = D, 7 = '=', 8 = X.
+#pragma once
+#include "sp_kernels.cuh"
+
+namespace sp {
+
+constexpr int ALN_U = 16;
+constexpr uint32_t CIG_I = 1, CIG_D = 2, CIG_EQ = 7, CIG_X = 8;
+
+struct AlignRecDev {  // layout of sp_align_rec (include/starphase_gpu.h)
+    int32_t dist, nm, p_start, p_end, t_start, t_end, n_cigar, pad_;
+    long long cigar_off;
+};
+
+struct AlignParams {
+    const uint32_t *blobs;     // [n distinct patterns] bins: forward rows, infix (wildcard) pad rows
+    const uint8_t *tbases;     // ASCII texts
+    const long long *toffs;
+    const int32_t *pair_t;     // text index of each pair
+    const int32_t *pair_p;     // blob index of each pair
+    const long long *cig_off;  // [n_pairs + 1] region of each pair in `cigar`
+    uint32_t *cigar;
+    uint32_t *scratch;         // [n_slots][slot_words]
+    long long slot_words;
+    AlignRecDev *recs;
+    int n_pairs;
+    uint32_t one, m1;
+};
+
+// the K1 recurrence over `ncols` text columns T[0 .. ncols) for this warp's bin; STORE keeps (D0, ~Pv) per column
+template <bool STORE>
+__device__ __forceinline__ void k4_forward(const uint32_t *peq_lane, const uint8_t *T, int ncols, const AlignParams &p,
+                                           bool first, bool owns, int m, int &best, int &best_col, uint32_t *scr,
+                                           int Wp, int wf4) {
+    constexpr int U = ALN_U;
+    const int lane = threadIdx.x & 31;
+    uint32_t npv[U], mv[U], d0[U];
+    load_row<U>(peq_lane + 5 * (32 * U), npv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; d0[u] = 0; }
+    int score = m, col = 0;
+    best = m; best_col = 0;
+    uint32_t carry_out = 0;
+    const int nch = (ncols + K1_CHUNK - 1) / K1_CHUNK;
+    const int nsteps = nch + 31;
+    for (int s = 0; s < nsteps; ++s) {
+        uint32_t cin = __shfl_up_sync(0xffffffffu, carry_out, 1);
+        if (first) cin = 0u;  // infix: the row above the pattern is free
+        const int idx = s - lane;
+        if (static_cast<unsigned>(idx) < static_cast<unsigned>(nch)) {
+            uint32_t X = cin << 24, Y = cin << 16;
+            uint32_t cph = 0, cmh = 0;
+#pragma unroll 1
+            for (int c = 0; c < K1_CHUNK; ++c) {
+                const int j = idx * K1_CHUNK + c;
+                const uint32_t code = j < ncols ? base_code(T[j]) : 4u;
+                column_step<U, true, STORE>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col,
+                                            best_col, d0);
+                if (STORE && owns && j < ncols) {
+                    uint32_t *dst = scr + static_cast<size_t>(j) * 2 * Wp + (lane * U - wf4);
+#pragma unroll
+                    for (int q = 0; q < U / 4; ++q) {
+                        if (lane * U + 4 * q >= wf4) {
+                            *reinterpret_cast<uint4 *>(dst + 4 * q) = make_uint4(d0[4 * q], d0[4 * q + 1], d0[4 * q + 2], d0[4 * q + 3]);
+                            *reinterpret_cast<uint4 *>(dst + Wp + 4 * q) =
+                                make_uint4(npv[4 * q], npv[4 * q + 1], npv[4 * q + 2], npv[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+            carry_out = cph | (cmh << 8);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
+    constexpr int U = ALN_U;
+    constexpr int V = vec_width(U);
+    constexpr int BW = blob_words(U);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *blob = reinterpret_cast<uint32_t *>(smem_raw) + warp * BW;
+    const int slot = blockIdx.x * K1_WARPS + warp, n_slots = gridDim.x * K1_WARPS;
+    uint32_t *scr = p.scratch + static_cast<size_t>(slot) * p.slot_words;
+    int cur_blob = -1;
+    for (int q = slot; q < p.n_pairs; q += n_slots) {
+        const int pb = p.pair_p[q], t = p.pair_t[q];
+        if (pb != cur_blob) {
+            __syncwarp();
+            const uint32_t *src = p.blobs + static_cast<size_t>(pb) * BW;
+            for (int i = lane; i < BW; i += 32) blob[i] = src[i];
+            __syncwarp();
+            cur_blob = pb;
+        }
+        const uint32_t pat = blob[PEQ_ROWS * 32 * U + lane];
+        const uint32_t info1 = blob[PEQ_ROWS * 32 * U + 32 + lane];
+        const bool owns = pat != NO_PATTERN;
+        const bool first = (info1 & INFO_FIRST) != 0, last = owns && (info1 & INFO_LAST) != 0;
+        const int m = static_cast<int>(info1 & INFO_LEN_MASK);
+        AlignRecDev rec = {0, 0, 0, 0, 0, 0, 0, 0, p.cig_off[q + 1]};
+        if (blob[PEQ_ROWS * 32 * U] == NO_PATTERN) {  // empty pattern: distance 0, empty placement at column 0
+            if (lane == 0) p.recs[q] = rec;
+            continue;
+        }
+        const int m_all = __shfl_sync(0xffffffffu, m, 0);
+        const int nl = (m_all + 32 * U - 1) / (32 * U);
+        const int pad = nl * 32 * U - m_all;
+        const int wf4 = (pad >> 5) & ~3, Wp = nl * U - wf4;
+        const uint8_t *T = p.tbases + p.toffs[t];
+        const int n = static_cast<int>(p.toffs[t + 1] - p.toffs[t]);
+        const uint32_t *peq_lane = blob + lane * V;
+
+        int best, best_col;
+        k4_forward<false>(peq_lane, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
+        const int src_lane = __ffs(__ballot_sync(0xffffffffu, last)) - 1;
+        const int d = __shfl_sync(0xffffffffu, best, src_lane), e = __shfl_sync(0xffffffffu, best_col, src_lane);
+        const int w0 = max(0, e - (m_all + d)), ncols = e - w0;
+        k4_forward<true>(peq_lane, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+            const long long cig_end = p.cig_off[q + 1];
+            long long pos = cig_end;
+            uint32_t cur_op = 0, cur_len = 0;
+            int i = m_all, j = ncols;
+            while (i > 0) {
+                uint32_t op;
+                if (j == 0) {
+                    op = CIG_I; --i;
+                } else {
+                    const int rr = i - 1 + pad, w = rr >> 5, b = rr & 31;
+                    const uint32_t *colp = scr + static_cast<size_t>(j - 1) * 2 * Wp + (w - wf4);
+                    const uint32_t d0w = __ldcg(colp), npvw = __ldcg(colp + Wp);
+                    const uint32_t code = base_code(T[w0 + j - 1]);
+                    const int wl = w / U, wu = w % U;
+                    const bool match = code < 4 && ((blob[(code * (U / V) + wu / V) * 32 * V + wl * V + (wu % V)] >> b) & 1u);
+                    const bool d0b = (d0w >> b) & 1u;
+                    if (match || !d0b) { op = match ? CIG_EQ : CIG_X; --i; --j; }  // the diagonal explains the cell
+                    else if (!((npvw >> b) & 1u)) { op = CIG_I; --i; }             // vertical delta +1
+                    else { op = CIG_D; --j; }
+                }
+                if (op == cur_op) ++cur_len;
+                else {
+                    if (cur_len) p.cigar[--pos] = (cur_len << 4) | cur_op;
+                    cur_op = op; cur_len = 1;
+                }
+            }
+            if (cur_len) p.cigar[--pos] = (cur_len << 4) | cur_op;
+            int ncig = static_cast<int>(cig_end - pos), clip_s = 0, clip_e = 0;
+            if (ncig > 0 && (p.cigar[pos] & 15u) == CIG_I) { clip_s = static_cast<int>(p.cigar[pos] >> 4); ++pos; --ncig; }
+            if (ncig > 0 && (p.cigar[cig_end - 1] & 15u) == CIG_I) { clip_e = static_cast<int>(p.cigar[cig_end - 1] >> 4); --ncig; }
+            rec.dist = d; rec.nm = d - clip_s - clip_e;
+            rec.p_start = clip_s; rec.p_end = m_all - clip_e;
+            rec.t_start = w0 + j; rec.t_end = e;
+            rec.n_cigar = ncig; rec.cigar_off = pos;
+            p.recs[q] = rec;
+        }
+        __syncwarp();
+    }
+}
+
+// dense copy of the kept CIGAR entries: one CTA per pair
+__global__ void k4_compact_cigar(const AlignRecDev *__restrict__ recs, const uint32_t *__restrict__ cigar,
+                                 const long long *__restrict__ out_off, uint32_t *__restrict__ out) {
+    const AlignRecDev r = recs[blockIdx.x];
+    const long long o = out_off[blockIdx.x];
+    for (int i = threadIdx.x; i < r.n_cigar; i += blockDim.x) out[o + i] = cigar[r.cigar_off + i];
+}
+
+}  // namespace sp

@@ -130,11 +130,11 @@ __device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)
 // leaving per 32-row word 5 LOP3 + 1 IADD3.X + 2 SHF on the ALU pipe (was 7 + 1 + 2) and 6 IMAD on the
 // FMA pipe.  The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
 // The Myers add (Eq & Pv) + Pv becomes t - npv - 1 (borrow chain seeded with 1, SubChain1).
-template <int U, bool TRACK_END>
+template <int U, bool TRACK_END, bool KEEP_D0 = false>
 __device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t code, uint32_t one, uint32_t m1,
                                             uint32_t (&npv)[U], uint32_t (&mv)[U], uint32_t &X, uint32_t &Y,
                                             uint32_t &cph, uint32_t &cmh, int &score, int &best, int &col,
-                                            int &best_col) {
+                                            int &best_col, uint32_t *d0_keep = nullptr) {
     uint32_t eq[U], xv[U], t[U], sum[U];
     load_row<U>(peq_lane + code * (32 * U), eq);
     eq[0] |= (Y >> 31);  // hin < 0 (Hyyro): the row above already paid for this column
@@ -151,6 +151,7 @@ __device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t c
         const uint32_t ng = ~d0[u] & npv[u];       // ~(D0 | Pv)        (LOP3)
         mh[u] = ng * one + a1;                     //                   (IMAD)
         ph[u] = ng * one + mv[u];                  //                   (IMAD)
+        if (KEEP_D0) d0_keep[u] = d0[u];           // K4 keeps the diagonal-zero vector for the traceback
     }
     // horizontal delta of the lane's last row: carry for the next lane, score for a last lane
     cph = __funnelshift_l(ph[U - 1], cph, 1);

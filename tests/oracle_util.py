@@ -56,6 +56,19 @@ class Oracle:
         L.sp_oracle_span_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
 
+    def align(self, pattern: bytes, text: bytes) -> dict:
+        """Canonical traceback alignment (sp_oracle_align): the same dict Context.align_pairs returns per pair."""
+        L = self.lib
+        L.sp_oracle_align.restype = C.c_int64
+        L.sp_oracle_align.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+        rec = np.zeros(7, dtype=np.int32)
+        cap = len(pattern) + len(text) + 2
+        cig = np.zeros(cap, dtype=np.uint32)
+        n = L.sp_oracle_align(bytes(pattern), len(pattern), bytes(text), len(text), rec.ctypes.data, cig.ctypes.data, cap)
+        assert n >= 0
+        return {"dist": int(rec[0]), "nm": int(rec[1]), "p_start": int(rec[2]), "p_end": int(rec[3]), "t_start": int(rec[4]),
+                "t_end": int(rec[5]), "cigar": [(int(x) >> 4, int(x) & 15) for x in cig[:n]]}
+
     def num_threads(self) -> int:
         return int(self.lib.sp_oracle_num_threads())
 

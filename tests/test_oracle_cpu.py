@@ -137,3 +137,80 @@ def test_span_convention(oracle):
         assert e == ends[0]
         starts = [a for a in range(e + 1) if lev(P, T[a:e]) == best]
         assert s == max(starts)
+
+
+# ---- sp_oracle_align: the traceback checker of sp_align_pairs (K4) ---------------------------------
+def _replay(pattern: bytes, text: bytes, a: dict):
+    """Walks the CIGAR over the two sequences; returns (pattern bases used, text bases used, edits)."""
+    i, j, edits = a["p_start"], a["t_start"], 0
+    for ln, op in a["cigar"]:
+        for _ in range(ln):
+            if op in (7, 8):
+                same = pattern[i:i + 1].upper() == text[j:j + 1].upper() and pattern[i:i + 1].upper() in (b"A", b"C", b"G", b"T")
+                assert same == (op == 7), (i, j, op)
+                edits += op == 8
+                i += 1; j += 1
+            elif op == 1:
+                i += 1; edits += 1
+            else:
+                assert op == 2
+                j += 1; edits += 1
+    return i, j, edits
+
+
+def test_align_oracle_invariants(oracle):
+    rng = np.random.default_rng(17)
+    for trial in range(60):
+        m, n = int(rng.integers(0, 300)), int(rng.integers(0, 400))
+        p = rnd(rng, m)
+        t = rnd(rng, n)
+        if trial % 3 == 0 and m:  # a noisy copy with flanks, sometimes with N
+            b = bytearray(p)
+            for _ in range(int(rng.integers(0, 8))):
+                b[int(rng.integers(0, len(b)))] = int(rng.choice(list(b"ACGTN")))
+            t = rnd(rng, int(rng.integers(0, 40))) + bytes(b) + rnd(rng, int(rng.integers(0, 40)))
+        a = oracle.align(p, t)
+        d, e = oracle.infix(p, t)
+        assert a["dist"] == d and a["t_end"] == e
+        i, j, edits = _replay(p, t, a)
+        assert (i, j) == (a["p_end"], a["t_end"]) and edits == a["nm"]
+        assert a["nm"] + a["p_start"] + (len(p) - a["p_end"]) == d
+        assert all(op in (1, 2, 7, 8) and ln > 0 for ln, op in a["cigar"])
+        assert all(a["cigar"][k][1] != a["cigar"][k + 1][1] for k in range(len(a["cigar"]) - 1))
+        if a["cigar"]:  # clips were stripped: the aligned part neither starts nor ends with an insertion
+            assert a["cigar"][0][1] != 1 and a["cigar"][-1][1] != 1
+
+
+def test_align_oracle_known(oracle):
+    assert oracle.align(b"ACGT", b"TTACGTTT") == dict(dist=0, nm=0, p_start=0, p_end=4, t_start=2, t_end=6, cigar=[(4, 7)])
+    # one mismatch in the middle
+    assert oracle.align(b"ACGTACGT", b"GGACGAACGTGG")["cigar"] == [(3, 7), (1, 8), (4, 7)]
+    # homopolymer deletion in the pattern is left-aligned: text AAAAA vs pattern AAAA inside unique flanks
+    a = oracle.align(b"CGTAAAATGC", b"CGTAAAAATGC")
+    assert a["dist"] == 1 and a["cigar"] == [(3, 7), (1, 2), (7, 7)]
+    # pattern base missing from the text: insertion, also left-aligned
+    a = oracle.align(b"CGTAAAAATGC", b"CGTAAAATGC")
+    assert a["dist"] == 1 and a["cigar"] == [(3, 7), (1, 1), (7, 7)]
+    # nothing aligns: everything clipped
+    assert oracle.align(b"ACGT", b"") == dict(dist=4, nm=0, p_start=4, p_end=4, t_start=0, t_end=0, cigar=[])
+    assert oracle.align(b"", b"ACGT") == dict(dist=0, nm=0, p_start=0, p_end=0, t_start=0, t_end=0, cigar=[])
+
+
+def test_align_oracle_feeds_process_mm_cigar(oracle):
+    """The CIGAR + clips drive the restated HlaProcessedMatch.add_mapping (src/hla/processed_match.rs:53-100): the
+    last prefix-edit count equals nm + unmapped whenever the clipped allele ends fit inside the consensus."""
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    import starphase_oracle as so
+
+    rng = np.random.default_rng(23)
+    allele = rnd(rng, 400)
+    cons = rnd(rng, 50) + allele[:200] + b"T" + allele[200:390] + rnd(rng, 60)
+    a = oracle.align(allele, cons)
+    m = so.Mapping(a["p_start"], a["p_end"], len(allele), a["t_start"], a["t_end"], len(cons), a["nm"], True, a["cigar"])
+    pm = so.HlaProcessedMatch.worst_match(0)
+    pm.add_mapping(m)
+    pc = pm.processed_cigars[0]
+    assert len(pc) == len(cons) + 1 and pc[0] == 0 and pc[-1] == a["dist"]
+    assert pm.full_mapping_stats[0] == so.MappingStats(len(allele), a["nm"], len(allele) - (a["p_end"] - a["p_start"]))
