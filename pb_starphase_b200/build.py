@@ -46,5 +46,39 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+# ---------------------------------------------------------------------------------------------
+# C++ host above the C ABI (pb_starphase_b200/host): libstarphase_host.so + the pybind11 test module
+# ---------------------------------------------------------------------------------------------
+HOST = HERE / "host"
+HOST_LIB = HERE / "libstarphase_host.so"
+HOST_SOURCES = ["sp_host_core.cpp", "sp_host_gpu.cpp", "sp_host_hla.cpp", "sp_host_cyp2d6.cpp"]
+
+
+def host_module_path() -> Path:
+    import sysconfig
+
+    return HERE / ("_starphase_host" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_host(force: bool = False) -> Path:
+    """g++ build of the C++ host library and its pybind11 module, both in-tree, linked against libstarphase_gpu.so
+    through $ORIGIN so the three files travel together."""
+    import pybind11
+    import sysconfig
+
+    mod = host_module_path()
+    deps = [HOST / s for s in HOST_SOURCES + ["sp_host_py.cpp", "starphase_host.hpp"]] + [HERE.parent / "include" / "starphase_gpu.h"]
+    newest = max(d.stat().st_mtime for d in deps)
+    if not force and HOST_LIB.exists() and mod.exists() and min(HOST_LIB.stat().st_mtime, mod.stat().st_mtime) > newest:
+        return mod
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    common = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-Wl,-rpath,$ORIGIN", "-L", str(HERE)]
+    subprocess.check_call(common + ["-o", str(HOST_LIB)] + [str(HOST / s) for s in HOST_SOURCES] + ["-lstarphase_gpu"])
+    subprocess.check_call(common + ["-fvisibility=hidden", "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+                                    "-o", str(mod), str(HOST / "sp_host_py.cpp"), "-lstarphase_host", "-lstarphase_gpu"])
+    return mod
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,587 @@
+// sp_host_cyp2d6.cpp -- CYP2D6 labels, weights, chains and the chain-pair search above the GPU path.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+
+#include "starphase_host.hpp"
+
+namespace starphase {
+
+using RT = Cyp2d6RegionType;
+
+// ------------------------------------------------------------------------------------------
+// labels -- src/cyp2d6/region_label.rs
+// ------------------------------------------------------------------------------------------
+const char *region_type_name(RT t) {  // Display of Cyp2d6RegionType (strum serialize names)
+    switch (t) {
+        case RT::Unknown: return "UNKNOWN";
+        case RT::Rep6: return "REP6";
+        case RT::Cyp2d6: return "CYP2D6";
+        case RT::LinkRegion: return "link_region";
+        case RT::Rep7: return "REP7";
+        case RT::Spacer: return "spacer";
+        case RT::Cyp2d7: return "CYP2D7";
+        case RT::Cyp2d6Deletion: return "CYP2D6*5";
+        case RT::Hybrid: return "Hybrid";
+        case RT::FalseAllele: return "FalseAllele";
+    }
+    return "UNKNOWN";
+}
+
+RT region_type_from_name(const std::string &s) {
+    for (RT t : {RT::Unknown, RT::Rep6, RT::Cyp2d6, RT::LinkRegion, RT::Rep7, RT::Spacer, RT::Cyp2d7, RT::Cyp2d6Deletion, RT::Hybrid,
+                 RT::FalseAllele})
+        if (s == region_type_name(t)) return t;
+    throw HostError("unknown CYP2D6 region type: " + s);
+}
+
+bool Cyp2d6RegionLabel::is_cyp2d() const {  // :39-55
+    return region_type == RT::Cyp2d6 || region_type == RT::Cyp2d7 || region_type == RT::Cyp2d6Deletion || region_type == RT::Hybrid;
+}
+bool Cyp2d6RegionLabel::is_rep() const { return region_type == RT::Rep6 || region_type == RT::Rep7; }  // :58-60
+bool Cyp2d6RegionLabel::is_reported_allele() const {                                                    // :63-69
+    return region_type == RT::Cyp2d6 || region_type == RT::Cyp2d6Deletion || region_type == RT::Hybrid;
+}
+
+std::string Cyp2d6RegionLabel::full_allele() const {  // :139-168
+    const std::string t = region_type_name(region_type);
+    switch (region_type) {
+        case RT::Cyp2d6: return subtype_label ? t + "*" + *subtype_label : t;
+        case RT::Hybrid: return subtype_label ? *subtype_label : t;
+        case RT::FalseAllele: return subtype_label ? t + "_" + *subtype_label : t;
+        default: return t;
+    }
+}
+
+// Rust: `if let Ok(float_value) = subtype.parse::<f64>() { format!("*{}", float_value.floor() as i64) }`
+static bool parse_rust_f64(const std::string &s, double &out) {
+    if (s.empty()) return false;
+    size_t i = 0;
+    if (s[i] == '+' || s[i] == '-') ++i;
+    std::string rest = s.substr(i);
+    std::string low;
+    for (char c : rest) low.push_back(static_cast<char>(std::tolower(static_cast<unsigned char>(c))));
+    const double sign = s[0] == '-' ? -1.0 : 1.0;
+    if (low == "inf" || low == "infinity") { out = sign * std::numeric_limits<double>::infinity(); return true; }
+    if (low == "nan") { out = std::numeric_limits<double>::quiet_NaN(); return true; }
+    size_t k = 0, digits = 0;
+    while (k < rest.size() && std::isdigit(static_cast<unsigned char>(rest[k]))) { ++k; ++digits; }
+    if (k < rest.size() && rest[k] == '.') {
+        ++k;
+        while (k < rest.size() && std::isdigit(static_cast<unsigned char>(rest[k]))) { ++k; ++digits; }
+    }
+    if (digits == 0) return false;
+    if (k < rest.size() && (rest[k] == 'e' || rest[k] == 'E')) {
+        ++k;
+        if (k < rest.size() && (rest[k] == '+' || rest[k] == '-')) ++k;
+        size_t ed = 0;
+        while (k < rest.size() && std::isdigit(static_cast<unsigned char>(rest[k]))) { ++k; ++ed; }
+        if (ed == 0) return false;
+    }
+    if (k != rest.size()) return false;
+    out = std::strtod(s.c_str(), nullptr);
+    return true;
+}
+
+std::string Cyp2d6RegionLabel::simplify_allele(bool detailed, const std::map<std::string, std::string> &cyp_translate) const {  // :101-136
+    if (region_type == RT::Cyp2d6 || region_type == RT::Hybrid) {
+        if (!subtype_label) return full_allele();
+        const std::string &s = *subtype_label;
+        auto it = cyp_translate.find(s);
+        if (it != cyp_translate.end()) return "*" + it->second;
+        if (detailed) return "*" + s;
+        double v;
+        if (parse_rust_f64(s, v)) {  // `as i64` saturates, NaN -> 0
+            long long iv;
+            if (std::isnan(v)) iv = 0;
+            else if (v >= 9223372036854775807.0) iv = std::numeric_limits<long long>::max();
+            else if (v <= -9223372036854775808.0) iv = std::numeric_limits<long long>::min();
+            else iv = static_cast<long long>(std::floor(v));
+            return "*" + std::to_string(iv);
+        }
+        return "*" + s;
+    }
+    if (region_type == RT::Cyp2d6Deletion) return "*5";
+    return full_allele();
+}
+
+bool Cyp2d6RegionLabel::is_allowed_label() const { return region_type != RT::Unknown && region_type != RT::FalseAllele; }  // :171-173
+
+bool Cyp2d6RegionLabel::is_allowed_label_pair(const Cyp2d6RegionLabel &nxt) const {  // :178-222
+    const RT t1 = region_type, t2 = nxt.region_type;
+    const bool c1 = is_cyp2d(), c2 = nxt.is_cyp2d();
+    const bool double_star5 = t1 == RT::Cyp2d6Deletion && t2 == RT::Cyp2d6Deletion;
+    const bool unexpected = t2 == RT::Rep6 || (c1 && t1 != RT::Cyp2d6Deletion && t2 != RT::LinkRegion) || (t2 == RT::LinkRegion && !c1) ||
+                            (t1 == RT::LinkRegion && !nxt.is_rep()) || (nxt.is_rep() && t1 != RT::LinkRegion) ||
+                            (is_rep() && !(t2 == RT::Spacer || c2)) || (t2 == RT::Spacer && !(is_rep() || t1 == RT::Cyp2d6Deletion)) ||
+                            (t1 == RT::Spacer && !c2) || (t2 == RT::Cyp2d7 && t1 != RT::Spacer) || t1 == RT::Cyp2d7;
+    return !double_star5 && !unexpected;
+}
+
+bool Cyp2d6RegionLabel::is_normalizing_allele(bool normalize_all) const {  // :254-262
+    return normalize_all ? is_cyp2d() : region_type == RT::Cyp2d6;
+}
+
+bool Cyp2d6RegionLabel::is_candidate_chain_head(bool normalize_all) const {  // :227-246
+    if (region_type == RT::Rep6 || region_type == RT::Cyp2d6Deletion) return true;
+    if (region_type == RT::Cyp2d6 || region_type == RT::Hybrid) return is_normalizing_allele(normalize_all);
+    return false;
+}
+
+std::string Cyp2d6Region::index_label() const {
+    return (unique_id ? std::to_string(*unique_id) : std::string("X")) + "_" + label.full_allele();
+}
+
+Cyp2d6Config Cyp2d6Config::default_config() {  // src/cyp2d6/definitions.rs:238-296
+    Cyp2d6Config c;
+    for (const char *part : {"intron1", "exon2", "intron2", "exon3", "intron3", "exon4", "intron4", "exon5", "intron5", "exon6", "intron6",
+                             "exon7", "intron7", "exon8", "intron8", "exon9"})
+        c.cyp_translate[std::string("CYP2D7::CYP2D6::") + part] = "13";
+    c.cyp_translate["CYP2D6::CYP2D7::intron1"] = "68";
+    c.cyp_translate["CYP2D6::CYP2D7::exon2"] = "68";
+    c.cyp_translate["CYP2D6::CYP2D7::exon8"] = "61";
+    c.cyp_translate["CYP2D6::CYP2D7::intron8"] = "63";
+    for (const char *d : {"1", "2", "3", "4", "6", "9", "10", "17", "28", "29", "35", "41", "43", "45", "146"})
+        c.inferred_connections.insert({std::string("*") + d, std::string("*") + d});
+    c.inferred_connections.insert({"*4", "*68"});
+    c.inferred_connections.insert({"*10", "*36"});
+    c.unexpected_singletons = {"*36", "*68"};
+    return c;
+}
+
+std::string convert_chain_to_hap(const std::vector<size_t> &chain, const std::vector<Cyp2d6Region> &hap_regions, Cyp2d6DetailLevel level,
+                                 const std::map<std::string, std::string> &cyp_translate) {
+    size_t num_non_deletion = 0;
+    std::vector<size_t> reportable;
+    for (auto it = chain.rbegin(); it != chain.rend(); ++it) {
+        const Cyp2d6RegionLabel &lab = hap_regions[*it].label;
+        const bool keep = lab.is_cyp2d() && lab.region_type != RT::Cyp2d7;
+        if (keep && lab.region_type != RT::Cyp2d6Deletion) ++num_non_deletion;
+        if (keep) reportable.push_back(*it);
+    }
+    std::vector<std::string> names;
+    for (size_t c : reportable) {
+        const Cyp2d6RegionLabel &lab = hap_regions[c].label;
+        if (lab.region_type == RT::Cyp2d6Deletion && num_non_deletion > 0) continue;
+        switch (level) {
+            case Cyp2d6DetailLevel::CoreAlleles: names.push_back(lab.simplify_allele(false, cyp_translate)); break;
+            case Cyp2d6DetailLevel::SubAlleles: names.push_back(lab.simplify_allele(true, cyp_translate)); break;
+            case Cyp2d6DetailLevel::DeepAlleles: names.push_back("(" + hap_regions[c].index_label() + ")"); break;
+        }
+    }
+    std::string out;
+    for (size_t i = 0; i < names.size();) {
+        size_t j = i;
+        while (j < names.size() && names[j] == names[i]) ++j;
+        if (!out.empty()) out += " + ";
+        out += j - i > 1 ? names[i] + "x" + std::to_string(j - i) : names[i];
+        i = j;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights and chains
+// ------------------------------------------------------------------------------------------
+std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &segments, const SeqList &consensuses,
+                                              const std::vector<Cyp2d6Region> &con_regions) {
+    if (consensuses.size() != con_regions.size()) throw HostError("weight_sequences: consensuses and regions differ in length");
+    std::vector<SequenceWeights> out(segments.size());
+    if (segments.empty()) return out;
+    // pattern = read segment (must be explained completely, chaining.rs:66), text = consensus (free ends, its clips form the overlap)
+    std::vector<int32_t> D, S, E;
+    gpu.score_spans(consensuses, segments, D, S, E);
+    const size_t ns = segments.size(), nc = consensuses.size();
+    for (size_t s = 0; s < ns; ++s) {
+        const size_t seq_len = segments[s].size();
+        SequenceWeights ret(nc, {seq_len, 0.0});  // :41
+        double min_ed_frac = 1.0;
+        for (size_t k = 0; k < nc; ++k) {
+            if (!con_regions[k].label.is_allowed_label()) continue;  // :52-55
+            if (consensuses[k].empty() || seq_len == 0) continue;     // no mapping can exist
+            const size_t o = k * ns + s;                              // [target = consensus][pattern = segment]
+            const size_t match_score = static_cast<size_t>(D[o]);
+            if (match_score >= seq_len) continue;                     // nothing aligned: the aligner reports no hit
+            const size_t con_len = consensuses[k].size();
+            const size_t clipped = static_cast<size_t>(S[o]) + (con_len - static_cast<size_t>(E[o]));
+            const double overlap = 1.0 - static_cast<double>(clipped) / static_cast<double>(con_len);  // :81
+            if (match_score < ret[k].first || (match_score == ret[k].first && overlap > ret[k].second)) {  // :87-92
+                ret[k] = {match_score, overlap};
+                min_ed_frac = std::min(min_ed_frac, std::max(static_cast<double>(match_score), 0.1) / static_cast<double>(seq_len));
+            }
+        }
+        if (min_ed_frac <= 0.05) out[s] = std::move(ret);  // :96-102
+    }
+    return out;
+}
+
+ChainBuild build_chains(const std::map<std::string, std::vector<SequenceWeights>> &read_weights, size_t n_haps) {
+    ChainBuild b;
+    b.best_allele_mapping_counts.assign(n_haps, 0);
+    for (const auto &kv : read_weights) {  // BTreeMap qname order
+        if (kv.second.empty()) continue;
+        std::vector<std::vector<size_t>> putative(1);
+        std::vector<SequenceWeights> weighted;
+        for (const SequenceWeights &ws : kv.second) {
+            if (ws.empty()) continue;
+            size_t min_ed = std::numeric_limits<size_t>::max(), n_min = 0;
+            for (const auto &w : ws) min_ed = std::min(min_ed, w.first);
+            for (const auto &w : ws) n_min += w.first == min_ed;
+            std::vector<std::vector<size_t>> next;
+            for (const auto &pc : putative)
+                for (size_t ci = 0; ci < ws.size(); ++ci)
+                    if (ws[ci].first == min_ed) {
+                        std::vector<size_t> e = pc;
+                        e.push_back(ci);
+                        next.push_back(std::move(e));
+                        if (n_min == 1) ++b.best_allele_mapping_counts[ci];  // inside the per-chain loop, caller.rs:471-483
+                    }
+            putative = std::move(next);
+            weighted.push_back(ws);
+        }
+        if (putative.empty() || (putative.size() == 1 && putative[0].empty())) continue;
+        b.qname_chains[kv.first] = std::move(putative);
+        b.qname_chain_scores[kv.first] = std::move(weighted);
+    }
+    for (auto &kv : b.qname_chains) {  // caller.rs:520-537
+        std::vector<std::vector<size_t>> kept;
+        for (const auto &c : kv.second)
+            if (std::all_of(c.begin(), c.end(), [&](size_t x) { return b.best_allele_mapping_counts[x] > 0; })) kept.push_back(c);
+        if (kept.empty()) throw HostError("chain collapse for read " + kv.first);
+        kv.second = std::move(kept);
+    }
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------
+// chain-pair search
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct ChainCtx {
+    const Cyp2d6Config &cfg;
+    const std::vector<Cyp2d6Region> &regions;
+    std::vector<std::vector<bool>> down, inferred;
+};
+
+double rust_round(double x) {  // f64::round: half away from zero
+    if (std::isnan(x) || std::isinf(x)) return x;
+    return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5);
+}
+
+bool is_sub(const std::vector<size_t> &hay, const std::vector<size_t> &needle) {  // chaining.rs:782-784
+    if (needle.size() > hay.size()) return false;
+    for (size_t s = 0; s + needle.size() <= hay.size(); ++s)
+        if (std::equal(needle.begin(), needle.end(), hay.begin() + static_cast<long>(s))) return true;
+    return false;
+}
+
+size_t unexpected_count(const std::vector<size_t> &chain, const ChainCtx &cx) {  // chaining.rs:739-775
+    std::vector<std::string> reduced;
+    for (size_t c : chain) {
+        const auto &lab = cx.regions[c].label;
+        if (lab.is_cyp2d() && lab.region_type != RT::Cyp2d7) reduced.push_back(lab.simplify_allele(false, cx.cfg.cyp_translate));
+    }
+    size_t errors = 0;
+    if (reduced.empty() || reduced[0].rfind("*", 0) != 0) ++errors;
+    if (reduced.size() == 1 && cx.cfg.unexpected_singletons.count(reduced[0])) ++errors;
+    for (size_t i = 0; i + 1 < reduced.size(); ++i)
+        if (!cx.cfg.inferred_connections.count({reduced[i], reduced[i + 1]})) ++errors;
+    return errors;
+}
+
+size_t count_inferred_edges(const std::vector<size_t> &chain, const ChainCtx &cx) {  // chaining.rs:828-840 (one chain)
+    size_t n = 0;
+    for (size_t i = 0; i + 1 < chain.size(); ++i) n += cx.inferred[chain[i]][chain[i + 1]];
+    return n;
+}
+
+// chaining.rs:603-674: (keep extending?, may be a candidate?)
+std::pair<bool, bool> check_chain_inferrences(const std::vector<size_t> &chain, const ChainCtx &cx) {
+    const size_t last = chain.back();
+    const bool last_is_cyp2d = cx.regions[last].label.is_cyp2d();
+    std::optional<size_t> opt_index;
+    for (size_t ci = chain.size() - 1; ci-- > 0;)
+        if (cx.regions[chain[ci]].label.is_cyp2d()) { opt_index = ci; break; }
+    const size_t start = opt_index.value_or(0);
+    bool detected = false;
+    for (size_t i = start; i + 1 < chain.size(); ++i) detected = detected || cx.inferred[chain[i]][chain[i + 1]];
+    if (!detected) return {true, true};
+    if (!last_is_cyp2d) return {true, false};
+    if (!opt_index) return {true, true};
+    const size_t prev = chain[*opt_index];
+    const auto &h1 = cx.regions[prev].label, &h2 = cx.regions[last].label;
+    const std::string h1m = h1.simplify_allele(false, cx.cfg.cyp_translate), h2m = h2.simplify_allele(false, cx.cfg.cyp_translate);
+    const bool connected = prev != last && cx.cfg.inferred_connections.count({h1m, h2m}) > 0;
+    const bool d7_tail = h2.region_type == RT::Cyp2d7 && h1.region_type != RT::Cyp2d7 && h1.is_cyp2d();
+    const bool allowed = connected || d7_tail;
+    return {allowed, allowed};
+}
+
+}  // namespace
+
+ChainPairResult find_best_chain_pair(GpuAligner &gpu, const Cyp2d6Config &cfg,
+                                     const std::map<std::string, std::vector<std::vector<size_t>>> &obs_chains,
+                                     const std::map<std::string, std::vector<SequenceWeights>> &chain_scores,
+                                     const std::vector<Cyp2d6Region> &hap_regions, bool infer, bool normalize_all, const ChainPenalties &pen,
+                                     bool ignore_limits) {
+    if (pen.lasso_penalty < 0.0) throw HostError("Lasso penalty must be >= 0.0");
+    const size_t n = hap_regions.size();
+    ChainCtx cx{cfg, hap_regions, std::vector<std::vector<bool>>(n, std::vector<bool>(n, false)),
+                std::vector<std::vector<bool>>(n, std::vector<bool>(n, false))};
+    auto lab = [&](size_t i) -> const Cyp2d6RegionLabel & { return hap_regions[i].label; };
+    // (i) observed edges, chaining.rs:243-266
+    for (const auto &kv : obs_chains)
+        for (const auto &chain : kv.second)
+            for (size_t i = 0; i + 1 < chain.size(); ++i) {
+                const size_t a = chain[i], b = chain[i + 1];
+                if (lab(a).is_allowed_label() && lab(b).is_allowed_label() && (ignore_limits || lab(a).is_allowed_label_pair(lab(b))))
+                    cx.down[a][b] = true;
+            }
+    // (ii) inferred edges, :269-305
+    if (infer)
+        for (size_t i = 0; i < n; ++i) {
+            const bool down_no_link = std::none_of(cx.down[i].begin(), cx.down[i].end(), [](bool b) { return b; });
+            for (size_t j = 0; j < n; ++j) {
+                bool up_no_link = true;
+                for (size_t r = 0; r < n; ++r) up_no_link = up_no_link && !cx.down[r][j];
+                if ((down_no_link || up_no_link) && !cx.down[i][j] && lab(i).is_allowed_label() && lab(j).is_allowed_label() &&
+                    lab(i).is_allowed_label_pair(lab(j)))
+                    cx.inferred[i][j] = true;
+            }
+        }
+    // (iii) heads, (iv) enumeration: stack, pop from the back, :308-396
+    std::vector<std::vector<size_t>> remaining, possible;
+    for (size_t i = 0; i < n; ++i)
+        if (ignore_limits || lab(i).is_candidate_chain_head(normalize_all)) remaining.push_back({i});
+    if (remaining.empty()) throw NoChainingHead();
+    while (!remaining.empty()) {
+        std::vector<size_t> cur = std::move(remaining.back());
+        remaining.pop_back();
+        const auto ok = check_chain_inferrences(cur, cx);
+        if (!ok.first) continue;
+        const std::string simplified = convert_chain_to_hap(cur, hap_regions, Cyp2d6DetailLevel::SubAlleles, cfg.cyp_translate);
+        if (ignore_limits || (!simplified.empty() && ok.second)) possible.push_back(cur);
+        const size_t last = cur.back();
+        auto extend = [&](const std::vector<std::vector<bool>> &edges) {
+            for (size_t ext = 0; ext < n; ++ext)
+                if (edges[last][ext] && std::count(cur.begin(), cur.end(), ext) < 3) {
+                    std::vector<size_t> e = cur;
+                    e.push_back(ext);
+                    remaining.push_back(std::move(e));
+                }
+        };
+        extend(cx.down);
+        if (infer) extend(cx.inferred);
+    }
+    if (possible.empty()) throw NoChainsFound();
+    const size_t P = possible.size();
+
+    // integer ED of every pair from the GPU: S[i][j] = sum_r min(B[i][r], B[j][r]); ED = S - sum_r optimum_r (:683-731, :470-485)
+    std::vector<std::vector<int32_t>> chains32(P);
+    for (size_t c = 0; c < P; ++c) chains32[c].assign(possible[c].begin(), possible[c].end());
+    std::vector<std::vector<std::vector<uint32_t>>> W;
+    uint64_t optimum_total = 0;
+    for (const auto &kv : chain_scores) {
+        std::vector<std::vector<uint32_t>> rw;
+        for (const SequenceWeights &seg : kv.second) {
+            if (seg.size() != n) throw HostError("find_best_chain_pair: weight row has the wrong width");
+            std::vector<uint32_t> row(n);
+            uint32_t mn = std::numeric_limits<uint32_t>::max();
+            for (size_t k = 0; k < n; ++k) { row[k] = static_cast<uint32_t>(seg[k].first); mn = std::min(mn, row[k]); }
+            optimum_total += mn;
+            rw.push_back(std::move(row));
+        }
+        W.push_back(std::move(rw));
+    }
+    std::vector<uint64_t> S(P * P, 0);
+    if (!W.empty()) S = gpu.chain_pair_sums(chains32, W, static_cast<int64_t>(n));
+
+    // per-chain integer terms
+    std::vector<std::vector<uint32_t>> counts(P, std::vector<uint32_t>(n, 0));
+    std::vector<size_t> unexp(P, 0), n_inf(P, 0);
+    for (size_t c = 0; c < P; ++c) {
+        for (size_t h : possible[c]) ++counts[c][h];
+        unexp[c] = ignore_limits ? 0 : unexpected_count(possible[c], cx);
+        n_inf[c] = infer ? count_inferred_edges(possible[c], cx) : 0;
+    }
+    std::vector<bool> lasso_hap(n);
+    for (size_t h = 0; h < n; ++h)
+        lasso_hap[h] = lab(h).is_allowed_label() && (ignore_limits || lab(h).is_normalizing_allele(normalize_all) || lab(h).is_reported_allele());
+
+    struct Cand { double lb; uint32_t i, j; uint64_t ed; double lasso, unexpected, inferred; };
+    std::vector<Cand> cands;
+    cands.reserve(P * (P + 1) / 2);
+    for (size_t i = 0; i < P; ++i)
+        for (size_t j = i; j < P; ++j) {
+            size_t extra = 0;  // count_unexpected_alleles, :794-819
+            for (size_t h = 0; h < n; ++h) {
+                const uint32_t hc = counts[i][h] + counts[j][h];
+                if (lasso_hap[h] && hc > 0) extra += hc - 1;
+            }
+            Cand c;
+            c.i = static_cast<uint32_t>(i); c.j = static_cast<uint32_t>(j);
+            c.ed = W.empty() ? 0 : S[i * P + j] - optimum_total;
+            c.lasso = pen.lasso_penalty * static_cast<double>(extra);
+            c.unexpected = static_cast<double>(unexp[i] + unexp[j]) * pen.unexpected_chain_penalty;
+            c.inferred = static_cast<double>(n_inf[i] + n_inf[j]) * pen.inferred_edge_penalty;
+            // primary_score (:172-174) without the multinomial term, which is >= 0
+            c.lb = static_cast<double>(c.ed) * pen.ln_ed_penalty + 0.0 + c.lasso + c.unexpected + c.inferred;
+            cands.push_back(c);
+        }
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+        if (a.lb != b.lb) return a.lb < b.lb;
+        if (a.i != b.i) return a.i < b.i;
+        return a.j < b.j;
+    });
+
+    // exact evaluation in bound order until the bound passes the best score
+    ChainPairResult res;
+    res.n_possible_chains = P;
+    bool have = false;
+    for (const Cand &c : cands) {
+        if (have && c.lb > res.score) break;
+        ++res.n_full_evaluations;
+        const std::vector<size_t> &ci = possible[c.i], &cj = possible[c.j];
+        std::vector<double> hap_weights(n, 0.0);
+        uint64_t ed = 0;
+        for (const auto &kv : chain_scores) {  // containment_score per read, :683-731, BTreeMap order
+            const std::vector<SequenceWeights> &cw = kv.second;
+            const size_t wl = cw.size();
+            uint64_t optimum = 0, worst = 0;
+            for (const auto &seg : cw) {
+                size_t mn = std::numeric_limits<size_t>::max(), mx = 0;
+                for (const auto &w : seg) { mn = std::min(mn, w.first); mx = std::max(mx, w.first); }
+                optimum += mn; worst += mx;
+            }
+            uint64_t best = 2 * worst;
+            std::vector<std::pair<const std::vector<size_t> *, size_t>> best_windows;
+            for (const std::vector<size_t> *other : {&ci, &cj}) {
+                if (other->size() < wl) continue;
+                for (size_t s = 0; s + wl <= other->size(); ++s) {
+                    uint64_t total = 0;
+                    for (size_t t = 0; t < wl; ++t) total += cw[t][(*other)[s + t]].first;
+                    if (total < best) { best = total; best_windows.clear(); }
+                    if (total == best) best_windows.emplace_back(other, s);
+                }
+            }
+            const uint64_t score = best - optimum;
+            ed = ed + score < ed ? std::numeric_limits<uint64_t>::max() : ed + score;  // saturating_add
+            if (!best_windows.empty()) {
+                const double split = 1.0 / static_cast<double>(best_windows.size());
+                for (const auto &bw : best_windows)
+                    for (size_t off = 0; off < wl; ++off) {
+                        const size_t con = (*bw.first)[bw.second + off];
+                        hap_weights[con] += split * cw[off][con].second;
+                    }
+            }
+        }
+        if (ed != c.ed) throw HostError("find_best_chain_pair: GPU edit distance disagrees with the window scan");
+        // multinomial, :854-903
+        std::vector<uint32_t> hc(n);
+        for (size_t h = 0; h < n; ++h) hc[h] = counts[c.i][h] + counts[c.j][h];
+        std::vector<double> cnt;
+        std::vector<uint64_t> coverage;
+        for (size_t h = 0; h < n; ++h)
+            if (hc[h] > 0 && (ignore_limits || lab(h).is_normalizing_allele(normalize_all))) {
+                cnt.push_back(static_cast<double>(hc[h]));
+                const double r = rust_round(hap_weights[h]);
+                coverage.push_back(r <= 0.0 ? 0 : static_cast<uint64_t>(r));
+            }
+        const double total = std::accumulate(cnt.begin(), cnt.end(), 0.0);
+        std::vector<double> probs;
+        for (double x : cnt) probs.push_back(x / total);
+        const uint64_t cov_sum = std::accumulate(coverage.begin(), coverage.end(), uint64_t{0});
+        double mn_pen;
+        if (probs.empty() || cov_sum == 0) {
+            auto has_del = [&](const std::vector<size_t> &ch) {
+                return std::any_of(ch.begin(), ch.end(), [&](size_t h) { return lab(h).region_type == RT::Cyp2d6Deletion; });
+            };
+            if (!normalize_all && has_del(ci) && has_del(cj)) mn_pen = 0.0;
+            else continue;  // invalid pair
+        } else {
+            mn_pen = std::fabs(multinomial_ln_pmf(probs, coverage));
+        }
+        const double ln_ed = static_cast<double>(ed) * pen.ln_ed_penalty;
+        const double score = ln_ed + mn_pen + c.lasso + c.unexpected + c.inferred;  // primary_score, :172-174
+        const bool better = !have || score < res.score || (score == res.score && (c.i < res.index1 || (c.i == res.index1 && c.j < res.index2)));
+        if (better) {
+            have = true;
+            res.score = score; res.index1 = c.i; res.index2 = c.j; res.edit_distance = ed;
+        }
+    }
+    if (!have) throw NoScorePairs();
+    res.best_chains = {possible[res.index1], possible[res.index2]};
+    std::sort(res.best_chains.begin(), res.best_chains.end());  // :568-573
+    std::set<size_t> used;
+    for (const auto &ch : res.best_chains) used.insert(ch.begin(), ch.end());
+    for (size_t i = 0; i < n; ++i)
+        if (!used.count(i)) res.dangling_alleles.push_back(std::to_string(i) + "_" + lab(i).full_allele());  // :576-589
+    (void)is_sub;  // unmet_observations is debug output only (:427-440)
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// the chaining half of diplotype_cyp2d6
+// ------------------------------------------------------------------------------------------
+Json Cyp2d6Call::gene_details() const {
+    Json dips = Json::array(), simple = Json::array(), inexact = Json::array();
+    dips.push(diplotype.to_json());
+    simple.push(simple_diplotype.to_json());
+    Json deep = Json::object();
+    deep.set("basic_diplotype", deep_diplotype.to_json()).set("haplotype_1", Json()).set("haplotype_2", Json());
+    inexact.push(deep);
+    Json j = Json::object();
+    j.set("diplotypes", dips).set("simple_diplotypes", simple).set("inexact_diplotypes", inexact).set("variant_details", Json());
+    j.set("mapping_details", Json()).set("multi_mapping_details", multi_mapping_details);
+    return j;
+}
+
+Cyp2d6Call call_cyp2d6_chains(GpuAligner &gpu, const Cyp2d6Config &cfg, const SeqList &consensuses, std::vector<Cyp2d6Region> hap_regions,
+                              const std::map<std::string, std::vector<Cyp2d6ReadRegion>> &regions_of_interest, bool infer_connections,
+                              bool normalize_all_alleles) {
+    // every read segment against every consensus in one batch (weight_sequence is called once per segment at caller.rs:450)
+    SeqList segments;
+    for (const auto &kv : regions_of_interest)
+        for (const auto &r : kv.second) segments.push_back(r.sequence);
+    const std::vector<SequenceWeights> ws = weight_sequences(gpu, segments, consensuses, hap_regions);
+    std::map<std::string, std::vector<SequenceWeights>> read_weights;
+    size_t s = 0;
+    for (const auto &kv : regions_of_interest) {
+        auto &v = read_weights[kv.first];
+        for (size_t k = 0; k < kv.second.size(); ++k) v.push_back(ws[s++]);
+    }
+    ChainBuild chains = build_chains(read_weights, hap_regions.size());
+
+    Cyp2d6Call call;
+    for (const auto &kv : chains.qname_chains) {  // caller.rs:556-567: zip with ALL regions of the read
+        if (kv.second.size() != 1) continue;
+        const auto &regs = regions_of_interest.at(kv.first);
+        for (size_t k = 0; k < std::min(kv.second[0].size(), regs.size()); ++k) {
+            const size_t con = kv.second[0][k];
+            Json range = Json::object();
+            range.set("start", static_cast<long long>(regs[k].start)).set("end", static_cast<long long>(regs[k].end));
+            Json d = Json::object();
+            d.set("read_qname", kv.first).set("read_position", range).set("consensus_id", static_cast<long long>(con));
+            d.set("consensus_star_allele", hap_regions[con].index_label());
+            call.multi_mapping_details.push(d);
+        }
+    }
+    for (size_t c = 0; c < hap_regions.size(); ++c)  // caller.rs:572-583
+        if (chains.best_allele_mapping_counts[c] == 0 && hap_regions[c].label.region_type != RT::Unknown &&
+            hap_regions[c].label.region_type != RT::FalseAllele)
+            hap_regions[c].label.mark_false_allele();
+
+    call.chain_pair = find_best_chain_pair(gpu, cfg, chains.qname_chains, chains.qname_chain_scores, hap_regions, infer_connections,
+                                           normalize_all_alleles, ChainPenalties(), false);
+    const auto &best = call.chain_pair.best_chains;
+    auto hap = [&](size_t k, Cyp2d6DetailLevel lvl) { return convert_chain_to_hap(best[k], hap_regions, lvl, cfg.cyp_translate); };
+    call.deep_diplotype = {hap(0, Cyp2d6DetailLevel::DeepAlleles), hap(1, Cyp2d6DetailLevel::DeepAlleles)};
+    call.diplotype = {hap(0, Cyp2d6DetailLevel::SubAlleles), hap(1, Cyp2d6DetailLevel::SubAlleles)};
+    call.simple_diplotype = {hap(0, Cyp2d6DetailLevel::CoreAlleles), hap(1, Cyp2d6DetailLevel::CoreAlleles)};
+    call.hap_regions = std::move(hap_regions);
+    return call;
+}
+
+}  // namespace starphase

@@ -1,0 +1,125 @@
+// sp_host_gpu.cpp -- GpuAligner: the only place the host touches libstarphase_gpu.so.
+#include <algorithm>
+
+#include "starphase_host.hpp"
+
+namespace starphase {
+
+namespace {
+struct Packed {
+    std::string bases;
+    std::vector<int64_t> offs;
+    sp_seqset set;
+    explicit Packed(const SeqList &seqs) {
+        offs.assign(1, 0);
+        for (const auto &s : seqs) {
+            bases += s;
+            offs.push_back(static_cast<int64_t>(bases.size()));
+        }
+        if (bases.empty()) bases.push_back('N');  // never read: keeps the pointer non-null
+        set.bases = reinterpret_cast<const uint8_t *>(bases.data());
+        set.offsets = offs.data();
+        set.n = static_cast<int64_t>(seqs.size());
+    }
+};
+}  // namespace
+
+GpuAligner::GpuAligner(int device) {
+    const sp_status st = sp_ctx_create(device, nullptr, &ctx_);
+    if (st != SP_OK) throw HostError(std::string("sp_ctx_create: ") + sp_last_error(nullptr));
+}
+
+GpuAligner::~GpuAligner() { sp_ctx_destroy(ctx_); }
+
+void GpuAligner::check(sp_status st, const char *what) {
+    if (st != SP_OK) throw HostError(std::string(what) + ": " + sp_last_error(ctx_));
+}
+
+uint64_t GpuAligner::launch_count() const { return sp_launch_count(ctx_); }
+
+std::vector<int32_t> GpuAligner::score_batch(const SeqList &targets, const SeqList &patterns) {
+    Packed t(targets), p(patterns);
+    std::vector<int32_t> D(std::max<size_t>(targets.size() * patterns.size(), 1));
+    check(sp_score_batch(ctx_, &t.set, &p.set, SP_INFIX, D.data(), nullptr), "sp_score_batch");
+    D.resize(targets.size() * patterns.size());
+    return D;
+}
+
+void GpuAligner::score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
+                             std::vector<int32_t> &end) {
+    Packed t(targets), p(patterns);
+    const size_t n = std::max<size_t>(targets.size() * patterns.size(), 1);
+    D.assign(n, 0); start.assign(n, 0); end.assign(n, 0);
+    check(sp_score_spans(ctx_, &t.set, &p.set, D.data(), start.data(), end.data()), "sp_score_spans");
+}
+
+std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const SeqList &patterns,
+                                               const std::vector<std::pair<int32_t, int32_t>> &pairs) {
+    Packed t(targets), p(patterns);
+    std::vector<int32_t> pt(pairs.size()), pp(pairs.size());
+    int64_t cap = 0;
+    for (size_t q = 0; q < pairs.size(); ++q) {
+        pt[q] = pairs[q].first; pp[q] = pairs[q].second;
+        if (pt[q] < 0 || pp[q] < 0 || static_cast<size_t>(pt[q]) >= targets.size() || static_cast<size_t>(pp[q]) >= patterns.size())
+            throw HostError("align_pairs: pair index outside the sequence sets");
+        const int64_t m = static_cast<int64_t>(patterns[static_cast<size_t>(pp[q])].size());
+        const int64_t n = static_cast<int64_t>(targets[static_cast<size_t>(pt[q])].size());
+        cap += m + std::min(n, 2 * m) + 1;
+    }
+    std::vector<sp_align_rec> recs(std::max<size_t>(pairs.size(), 1));
+    std::vector<uint32_t> cig(static_cast<size_t>(std::max<int64_t>(cap, 1)));
+    int64_t used = 0;
+    check(sp_align_pairs(ctx_, &t.set, &p.set, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(), recs.data(), cig.data(), cap, &used),
+          "sp_align_pairs");
+    std::vector<Alignment> out(pairs.size());
+    for (size_t q = 0; q < pairs.size(); ++q) {
+        const sp_align_rec &r = recs[q];
+        Alignment &a = out[q];
+        a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
+        a.cigar.reserve(static_cast<size_t>(r.n_cigar));
+        for (int32_t k = 0; k < r.n_cigar; ++k) {
+            const uint32_t e = cig[static_cast<size_t>(r.cigar_off + k)];
+            a.cigar.emplace_back(e >> 4, static_cast<uint8_t>(e & 15u));
+        }
+    }
+    return out;
+}
+
+std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
+                                                      int k) {
+    std::vector<sp_pair_rec> out(static_cast<size_t>(std::max(k, 1)));
+    int n = 0;
+    check(sp_pair_minsum_topk_host(ctx_, D.data(), D2 ? D2->data() : nullptr, R, A, k, out.data(), &n), "sp_pair_minsum_topk_host");
+    out.resize(static_cast<size_t>(n));
+    return out;
+}
+
+std::vector<uint64_t> GpuAligner::chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
+                                                  const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps) {
+    std::vector<int32_t> coff(1, 0), items, soff(1, 0);
+    for (const auto &c : chains) {
+        items.insert(items.end(), c.begin(), c.end());
+        coff.push_back(static_cast<int32_t>(items.size()));
+    }
+    std::vector<uint32_t> W;
+    for (const auto &rw : read_weights) {
+        for (const auto &seg : rw) {
+            if (static_cast<int64_t>(seg.size()) != n_haps) throw HostError("chain_pair_sums: weight row has the wrong width");
+            W.insert(W.end(), seg.begin(), seg.end());
+        }
+        soff.push_back(soff.back() + static_cast<int32_t>(rw.size()));
+    }
+    if (items.empty()) items.push_back(0);
+    if (W.empty()) W.push_back(0);
+    sp_dmatrix *B = nullptr;
+    check(sp_chain_window_scores(ctx_, static_cast<int64_t>(chains.size()), coff.data(), items.data(), static_cast<int64_t>(read_weights.size()),
+                                 soff.data(), W.data(), n_haps, &B),
+          "sp_chain_window_scores");
+    std::vector<uint64_t> S(std::max<size_t>(chains.size() * chains.size(), 1), 0);
+    const sp_status st = sp_pair_minsum_full(ctx_, B, S.data());
+    sp_dmatrix_destroy(B);
+    check(st, "sp_pair_minsum_full");
+    return S;
+}
+
+}  // namespace starphase

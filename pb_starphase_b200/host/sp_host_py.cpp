@@ -1,0 +1,215 @@
+// sp_host_py.cpp -- pybind11 view of the C++ host (module pb_starphase_b200._starphase_host) so that the parity
+// tests can drive the same functions a C++ host would call.  No logic here.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "starphase_host.hpp"
+
+namespace py = pybind11;
+using namespace starphase;
+
+static HlaDatabase make_db(const std::vector<std::tuple<std::string, std::string, std::vector<std::string>, std::optional<std::string>, std::string>> &rows) {
+    HlaDatabase db;
+    for (const auto &r : rows) {
+        HlaAlleleDefinition d;
+        d.hla_id = std::get<0>(r); d.gene_name = std::get<1>(r); d.star_allele = std::get<2>(r);
+        d.dna_sequence = std::get<3>(r); d.cdna_sequence = std::get<4>(r);
+        db.emplace(d.hla_id, std::move(d));
+    }
+    return db;
+}
+
+static std::vector<Cyp2d6Region> make_regions(const std::vector<std::tuple<std::string, std::optional<std::string>, std::optional<size_t>>> &rows) {
+    std::vector<Cyp2d6Region> out;
+    for (const auto &r : rows) {
+        Cyp2d6Region g;
+        g.label.region_type = region_type_from_name(std::get<0>(r));
+        g.label.subtype_label = std::get<1>(r);
+        g.unique_id = std::get<2>(r);
+        out.push_back(std::move(g));
+    }
+    return out;
+}
+
+PYBIND11_MODULE(_starphase_host, m) {
+    m.doc() = "C++ host mirror of pb-StarPhase's hot-path interface above libstarphase_gpu.so";
+    py::register_exception<HostError>(m, "HostError");
+    py::register_exception<NoChainingHead>(m, "NoChainingHead", m.attr("HostError").ptr());
+    py::register_exception<NoChainsFound>(m, "NoChainsFound", m.attr("HostError").ptr());
+    py::register_exception<NoScorePairs>(m, "NoScorePairs", m.attr("HostError").ptr());
+
+    py::class_<Json>(m, "Json").def("pretty", [](const Json &j) { return j.pretty(); });
+
+    py::class_<MappingStats>(m, "MappingStats")
+        .def(py::init<size_t, size_t, size_t>())
+        .def_readwrite("seq_len", &MappingStats::seq_len)
+        .def_readwrite("nm", &MappingStats::nm)
+        .def_readwrite("unmapped", &MappingStats::unmapped)
+        .def("custom_score", &MappingStats::custom_score)
+        .def("mapping_score", &MappingStats::mapping_score)
+        .def("as_tuple", [](const MappingStats &s) { return std::make_tuple(s.seq_len, s.nm, s.unmapped); });
+
+    py::class_<HlaMappingStats>(m, "HlaMappingStats")
+        .def(py::init<>())
+        .def_readwrite("cdna_stats", &HlaMappingStats::cdna_stats)
+        .def_readwrite("dna_stats", &HlaMappingStats::dna_stats)
+        .def("mapping_score", &HlaMappingStats::mapping_score)
+        .def("to_json", &HlaMappingStats::to_json);
+
+    py::class_<Mapping>(m, "Mapping")
+        .def(py::init([](size_t qs, size_t qe, size_t ql, size_t ts, size_t te, size_t tl, size_t nm, bool fwd,
+                         std::vector<std::pair<uint32_t, uint8_t>> cigar) {
+                 Mapping x;
+                 x.query_start = qs; x.query_end = qe; x.query_len = ql; x.target_start = ts; x.target_end = te; x.target_len = tl;
+                 x.nm = nm; x.forward = fwd; x.cigar = std::move(cigar);
+                 return x;
+             }),
+             py::arg("query_start"), py::arg("query_end"), py::arg("query_len"), py::arg("target_start"), py::arg("target_end"),
+             py::arg("target_len"), py::arg("nm"), py::arg("forward") = true, py::arg("cigar") = std::vector<std::pair<uint32_t, uint8_t>>());
+
+    m.def("select_best_mapping", [](const std::vector<Mapping> &ms, bool from_target, bool pen, std::optional<size_t> ov) {
+        auto r = select_best_mapping(ms, from_target, pen, ov);
+        return std::make_pair(r.first, std::make_tuple(r.second.seq_len, r.second.nm, r.second.unmapped));
+    }, py::arg("mappings"), py::arg("unmapped_from_target"), py::arg("penalize_unmapped"), py::arg("base_length_override") = std::nullopt);
+    m.def("process_mm_cigar", &process_mm_cigar);
+    m.def("dp_score", &dp_score);
+
+    py::class_<HlaProcessedMatch>(m, "HlaProcessedMatch")
+        .def(py::init<std::string>())
+        .def_static("worst_match", &HlaProcessedMatch::worst_match)
+        .def("add_mapping", &HlaProcessedMatch::add_mapping)
+        .def("is_better_match", &HlaProcessedMatch::is_better_match)
+        .def("haplotype", &HlaProcessedMatch::haplotype)
+        .def("processed_cigars", &HlaProcessedMatch::processed_cigars)
+        .def("processed_ranges", &HlaProcessedMatch::processed_ranges);
+
+    m.def("ln_gamma", &ln_gamma);
+    m.def("ln_factorial", &ln_factorial);
+    m.def("multinomial_ln_pmf", &multinomial_ln_pmf);
+    m.def("binomial_cdf", &binomial_cdf);
+    m.def("is_passing_dual", &is_passing_dual, py::arg("counts1"), py::arg("counts2"), py::arg("min_consensus_fraction") = 0.10,
+          py::arg("min_cdf") = 0.001, py::arg("expected_maf") = 0.45);
+
+    py::class_<DiplotypeSettings>(m, "DiplotypeSettings")
+        .def(py::init<>())
+        .def_readwrite("disable_cdna_scoring", &DiplotypeSettings::disable_cdna_scoring)
+        .def_readwrite("hla_require_dna", &DiplotypeSettings::hla_require_dna)
+        .def_readwrite("min_consensus_fraction", &DiplotypeSettings::min_consensus_fraction)
+        .def_readwrite("min_cdf", &DiplotypeSettings::min_cdf)
+        .def_readwrite("expected_maf", &DiplotypeSettings::expected_maf)
+        .def_readwrite("min_dp_score", &DiplotypeSettings::min_dp_score);
+
+    py::class_<GpuAligner>(m, "GpuAligner")
+        .def(py::init<int>(), py::arg("device") = 0)
+        .def("score_batch", &GpuAligner::score_batch)
+        .def("launch_count", &GpuAligner::launch_count)
+        .def("align_pairs", [](GpuAligner &g, const SeqList &t, const SeqList &p, const std::vector<std::pair<int32_t, int32_t>> &pairs) {
+            py::list out;
+            for (const Alignment &a : g.align_pairs(t, p, pairs)) {
+                py::dict d;
+                d["dist"] = a.dist; d["nm"] = a.nm; d["p_start"] = a.p_start; d["p_end"] = a.p_end; d["t_start"] = a.t_start; d["t_end"] = a.t_end;
+                py::list c;
+                for (const auto &e : a.cigar) c.append(py::make_tuple(e.first, static_cast<int>(e.second)));
+                d["cigar"] = c;
+                out.append(d);
+            }
+            return out;
+        });
+
+    // ---- HLA ----
+    using DbRows = std::vector<std::tuple<std::string, std::string, std::vector<std::string>, std::optional<std::string>, std::string>>;
+    m.def("score_read", [](GpuAligner &g, const std::string &dna_target, const std::string &cdna_target, const DbRows &rows,
+                           const std::string &gene, const DiplotypeSettings &s) {
+        const HlaDatabase db = make_db(rows);
+        ScoreReadResult r = score_read(g, dna_target, cdna_target, db, gene, s);
+        py::dict stats;
+        for (const auto &kv : r.stats) {
+            auto tup = [](const std::optional<MappingStats> &x) -> py::object {
+                if (!x) return py::none();
+                return py::make_tuple(x->seq_len, x->nm, x->unmapped);
+            };
+            stats[py::str(kv.first)] = py::make_tuple(tup(kv.second.cdna_stats), tup(kv.second.dna_stats));
+        }
+        return py::make_tuple(stats, r.best_hla_id, r.best_star_allele);
+    });
+    m.def("realign_records", [](GpuAligner &g, const std::vector<std::string> &genes, const DbRows &rows,
+                                const std::vector<std::pair<std::string, std::string>> &reads, int n_candidates) {
+        const HlaDatabase db = make_db(rows);
+        HlaRealigner r(g, genes, db);
+        Json arr = Json::array();
+        for (const auto &d : r.realign_records(reads, n_candidates)) arr.push(d.to_json());
+        return arr;
+    }, py::arg("gpu"), py::arg("gene_list"), py::arg("database"), py::arg("reads"), py::arg("n_candidates") = 5);
+    m.def("diplotype_hla_gene", [](GpuAligner &g, const DbRows &rows, const std::string &gene,
+                                   const std::vector<std::tuple<std::string, std::string, std::string>> &reads, const DiplotypeSettings &s) {
+        const HlaDatabase db = make_db(rows);
+        std::vector<HlaRead> rs;
+        for (const auto &r : reads) rs.push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r)});
+        const HlaGeneCall c = diplotype_hla_gene(g, db, gene, rs, s);
+        py::dict d;
+        d["hla_id1"] = c.hla_id1; d["hla_id2"] = c.hla_id2; d["counts1"] = c.counts1; d["counts2"] = c.counts2;
+        d["pair_score_cdna"] = c.pair_score_cdna; d["pair_score_dna"] = c.pair_score_dna;
+        d["gene_details"] = c.gene_details();
+        return d;
+    });
+
+    // ---- CYP2D6 ----
+    using RegionRows = std::vector<std::tuple<std::string, std::optional<std::string>, std::optional<size_t>>>;
+    m.def("label_ops", [](const std::string &type, const std::optional<std::string> &sub, const std::string &type2,
+                          const std::optional<std::string> &sub2, bool normalize_all) {
+        const Cyp2d6Config cfg = Cyp2d6Config::default_config();
+        Cyp2d6RegionLabel a{region_type_from_name(type), sub}, b{region_type_from_name(type2), sub2};
+        py::dict d;
+        d["full_allele"] = a.full_allele();
+        d["simple"] = a.simplify_allele(false, cfg.cyp_translate);
+        d["detailed"] = a.simplify_allele(true, cfg.cyp_translate);
+        d["allowed"] = a.is_allowed_label();
+        d["allowed_pair"] = a.is_allowed_label_pair(b);
+        d["head"] = a.is_candidate_chain_head(normalize_all);
+        d["normalizing"] = a.is_normalizing_allele(normalize_all);
+        return d;
+    });
+    m.def("convert_chain_to_hap", [](const std::vector<size_t> &chain, const RegionRows &rows, const std::string &level) {
+        const Cyp2d6Config cfg = Cyp2d6Config::default_config();
+        const Cyp2d6DetailLevel lvl = level == "CoreAlleles" ? Cyp2d6DetailLevel::CoreAlleles
+                                      : level == "SubAlleles" ? Cyp2d6DetailLevel::SubAlleles : Cyp2d6DetailLevel::DeepAlleles;
+        return convert_chain_to_hap(chain, make_regions(rows), lvl, cfg.cyp_translate);
+    });
+    m.def("weight_sequences", [](GpuAligner &g, const SeqList &segments, const SeqList &consensuses, const RegionRows &rows) {
+        return weight_sequences(g, segments, consensuses, make_regions(rows));
+    });
+    m.def("build_chains", [](const std::map<std::string, std::vector<SequenceWeights>> &rw, size_t n_haps) {
+        ChainBuild b = build_chains(rw, n_haps);
+        return py::make_tuple(b.qname_chains, b.qname_chain_scores, b.best_allele_mapping_counts);
+    });
+    m.def("find_best_chain_pair", [](GpuAligner &g, const std::map<std::string, std::vector<std::vector<size_t>>> &obs,
+                                     const std::map<std::string, std::vector<SequenceWeights>> &scores, const RegionRows &rows, bool infer,
+                                     bool normalize_all, bool ignore_limits, double lasso, double ln_ed, double unexpected,
+                                     double inferred_edge) {
+        ChainPenalties pen;
+        pen.lasso_penalty = lasso; pen.ln_ed_penalty = ln_ed; pen.unexpected_chain_penalty = unexpected; pen.inferred_edge_penalty = inferred_edge;
+        const ChainPairResult r = find_best_chain_pair(g, Cyp2d6Config::default_config(), obs, scores, make_regions(rows), infer, normalize_all,
+                                                       pen, ignore_limits);
+        py::dict d;
+        d["best_chains"] = r.best_chains; d["dangling"] = r.dangling_alleles; d["score"] = r.score; d["i"] = r.index1; d["j"] = r.index2;
+        d["edit_distance"] = r.edit_distance; d["n_possible_chains"] = r.n_possible_chains; d["n_full_evaluations"] = r.n_full_evaluations;
+        return d;
+    }, py::arg("gpu"), py::arg("obs_chains"), py::arg("chain_scores"), py::arg("regions"), py::arg("infer"), py::arg("normalize_all"),
+          py::arg("ignore_limits") = false, py::arg("lasso_penalty") = 4.0, py::arg("ln_ed_penalty") = 2.0,
+          py::arg("unexpected_chain_penalty") = 10.0, py::arg("inferred_edge_penalty") = 2.0);
+    m.def("call_cyp2d6_chains", [](GpuAligner &g, const SeqList &consensuses, const RegionRows &rows,
+                                   const std::map<std::string, std::vector<std::tuple<size_t, size_t, std::string>>> &roi, bool infer,
+                                   bool normalize_all) {
+        std::map<std::string, std::vector<Cyp2d6ReadRegion>> regions;
+        for (const auto &kv : roi)
+            for (const auto &r : kv.second) regions[kv.first].push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r)});
+        const Cyp2d6Call c = call_cyp2d6_chains(g, Cyp2d6Config::default_config(), consensuses, make_regions(rows), regions, infer, normalize_all);
+        py::dict d;
+        d["best_chains"] = c.chain_pair.best_chains; d["score"] = c.chain_pair.score; d["dangling"] = c.chain_pair.dangling_alleles;
+        d["n_possible_chains"] = c.chain_pair.n_possible_chains; d["n_full_evaluations"] = c.chain_pair.n_full_evaluations;
+        d["gene_details"] = c.gene_details();
+        return d;
+    });
+
+    m.def("starphase_json", &starphase_json);
+}

@@ -1,0 +1,349 @@
+// starphase_host.hpp -- C++ host side above the C ABI (include/starphase_gpu.h).
+//
+// pb-StarPhase's own host is Rust and stays the reference's code (north_star); neither cargo nor rustc
+// exists in this image, so this is the compiled-language mirror of the reference's operator interface for
+// the hot path: same names, argument meaning and error behaviour as the Rust functions cited at each
+// declaration (paths relative to the pb-StarPhase v2.0.1 tree), with every alignment number coming from
+// libstarphase_gpu.so.  Nothing here computes an alignment on the CPU and nothing links the oracle.
+//
+//   src/data_types/mapping.rs, src/hla/mapping.rs   MappingStats, HlaMappingStats, scores
+//   src/util/mapping.rs:22-57                       select_best_mapping
+//   src/hla/processed_match.rs                      process_mm_cigar, HlaProcessedMatch
+//   src/hla/caller.rs:1332-1511                     score_read            (K1 + K4)
+//   src/hla/realigner.rs:98-211                     HlaRealigner::realign_records   (K1 + K4)
+//   north_star (2) + src/hla/caller.rs:889-901, :1225-1247   diplotype_hla_gene (K1 + K2)
+//   src/cyp2d6/chaining.rs:28-103                   weight_sequences      (K3 spans)
+//   src/cyp2d6/caller.rs:430-537                    build_chains
+//   src/cyp2d6/chaining.rs:223-592                  find_best_chain_pair  (K3 chain windows + K2)
+//   src/cyp2d6/caller.rs:907-957                    convert_chain_to_hap
+//   src/data_types/starphase_json.rs, src/util/file_io.rs:37-52   result JSON (serde pretty)
+#pragma once
+#include <cstdint>
+#include <map>
+#include <optional>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/starphase_gpu.h"
+
+namespace starphase {
+
+// Box<dyn Error> of the reference: one exception type carrying the message
+struct HostError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ------------------------------------------------------------------------------------------
+// JSON value with serde_json's pretty printer (2-space indent, insertion-ordered objects)
+// ------------------------------------------------------------------------------------------
+class Json {
+  public:
+    enum Kind { Null, Bool, Int, Str, Arr, Obj };
+    Json() : kind_(Null) {}
+    Json(std::nullptr_t) : kind_(Null) {}
+    Json(bool b) : kind_(Bool), i_(b) {}
+    Json(int v) : kind_(Int), i_(v) {}
+    Json(long v) : kind_(Int), i_(v) {}
+    Json(long long v) : kind_(Int), i_(v) {}
+    Json(unsigned long v) : kind_(Int), i_(static_cast<long long>(v)) {}
+    Json(const char *s) : kind_(Str), s_(s) {}
+    Json(std::string s) : kind_(Str), s_(std::move(s)) {}
+    static Json array() { Json j; j.kind_ = Arr; return j; }
+    static Json object() { Json j; j.kind_ = Obj; return j; }
+    Json &push(Json v) { a_.push_back(std::move(v)); return *this; }
+    Json &set(const std::string &k, Json v) { o_.emplace_back(k, std::move(v)); return *this; }
+    std::string pretty(int indent = 0) const;
+
+  private:
+    Kind kind_;
+    long long i_ = 0;
+    std::string s_;
+    std::vector<Json> a_;
+    std::vector<std::pair<std::string, Json>> o_;
+};
+
+// ------------------------------------------------------------------------------------------
+// scores -- src/data_types/mapping.rs, src/hla/mapping.rs
+// ------------------------------------------------------------------------------------------
+struct MappingStats {  // src/data_types/mapping.rs:7-22
+    size_t seq_len = 0, nm = 0, unmapped = 0;
+    std::optional<size_t> clipped_start, clipped_end;
+    MappingStats() = default;
+    MappingStats(size_t l, size_t n, size_t u) : seq_len(l), nm(n), unmapped(u) {}
+    double custom_score(bool penalize_unmapped) const;  // :69-85
+    double mapping_score() const { return custom_score(true); }
+    Json to_json() const;
+    bool operator==(const MappingStats &o) const {
+        return seq_len == o.seq_len && nm == o.nm && unmapped == o.unmapped && clipped_start == o.clipped_start &&
+               clipped_end == o.clipped_end;
+    }
+};
+
+struct HlaMappingStats {  // src/hla/mapping.rs:9-14
+    std::optional<MappingStats> cdna_stats, dna_stats;
+    std::pair<double, double> mapping_score() const;  // (cDNA, DNA), missing side = 1.0 (:66-83, :111-117)
+    Json to_json() const;
+};
+
+// the fields of minimap2::Mapping the reference reads; produced from sp_align_rec
+struct Mapping {
+    size_t query_start = 0, query_end = 0, query_len = 0;
+    size_t target_start = 0, target_end = 0, target_len = 0;
+    size_t nm = 0;
+    bool forward = true;
+    std::vector<std::pair<uint32_t, uint8_t>> cigar;  // (length, op), minimap2 op codes
+};
+
+// src/util/mapping.rs:22-57: index of the best mapping (or nullopt) and its stats
+std::pair<std::optional<size_t>, MappingStats> select_best_mapping(const std::vector<Mapping> &mappings,
+                                                                   bool unmapped_from_target, bool penalize_unmapped,
+                                                                   std::optional<size_t> base_length_override);
+
+// src/hla/processed_match.rs:210-263; throws HostError("Unexpected cigar type: ..") like the reference bails
+std::vector<size_t> process_mm_cigar(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, size_t target_offset,
+                                     size_t target_len, size_t clip_start, size_t clip_end);
+
+class HlaProcessedMatch {  // src/hla/processed_match.rs:10-184
+  public:
+    explicit HlaProcessedMatch(std::string haplotype) : haplotype_(std::move(haplotype)) {}
+    static HlaProcessedMatch worst_match(size_t num_sequences);
+    void add_mapping(const std::optional<Mapping> &m);
+    bool is_better_match(const HlaProcessedMatch &rhs) const;
+    const std::string &haplotype() const { return haplotype_; }
+    const std::vector<std::optional<MappingStats>> &full_mapping_stats() const { return full_mapping_stats_; }
+    const std::vector<std::optional<std::vector<size_t>>> &processed_cigars() const { return processed_cigars_; }
+    const std::vector<std::pair<size_t, size_t>> &processed_ranges() const { return processed_ranges_; }
+
+  private:
+    std::string haplotype_;
+    std::vector<std::optional<MappingStats>> full_mapping_stats_;
+    std::vector<std::optional<std::vector<size_t>>> processed_cigars_;
+    std::vector<std::pair<size_t, size_t>> processed_ranges_;
+};
+
+// ------------------------------------------------------------------------------------------
+// statistics -- src/util/stats.rs, statrs 0.16 pieces it calls
+// ------------------------------------------------------------------------------------------
+double ln_gamma(double x);
+double ln_factorial(uint64_t x);
+double multinomial_ln_pmf(const std::vector<double> &probs, const std::vector<uint64_t> &obs);  // src/util/stats.rs:11-36
+double binomial_cdf(uint64_t n, double p, uint64_t k);
+// src/hla/caller.rs:1225-1247 (defaults of src/cli/diplotype.rs)
+bool is_passing_dual(size_t counts1, size_t counts2, double min_consensus_fraction = 0.10, double min_cdf = 0.001,
+                     double expected_maf = 0.45);
+
+// ------------------------------------------------------------------------------------------
+// GPU: RAII view of the C ABI; every failure becomes HostError(sp_last_error)
+// ------------------------------------------------------------------------------------------
+using SeqList = std::vector<std::string>;
+
+struct Alignment {  // sp_align_rec + its CIGAR
+    int32_t dist = 0, nm = 0, p_start = 0, p_end = 0, t_start = 0, t_end = 0;
+    std::vector<std::pair<uint32_t, uint8_t>> cigar;
+};
+
+class GpuAligner {
+  public:
+    explicit GpuAligner(int device = 0);
+    ~GpuAligner();
+    GpuAligner(const GpuAligner &) = delete;
+    GpuAligner &operator=(const GpuAligner &) = delete;
+    // D[t * patterns.size() + p]
+    std::vector<int32_t> score_batch(const SeqList &targets, const SeqList &patterns);
+    void score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
+                     std::vector<int32_t> &end);
+    std::vector<Alignment> align_pairs(const SeqList &targets, const SeqList &patterns,
+                                       const std::vector<std::pair<int32_t, int32_t>> &pairs);
+    std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
+                                              int k);
+    // S[i * n_chains + j], j >= i: sum over reads of min(B[i][r], B[j][r]) for the chain-window matrix B
+    std::vector<uint64_t> chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
+                                          const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps);
+    uint64_t launch_count() const;
+    sp_ctx *raw() { return ctx_; }
+
+  private:
+    void check(sp_status st, const char *what);
+    sp_ctx *ctx_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------
+// HLA
+// ------------------------------------------------------------------------------------------
+struct HlaAlleleDefinition {  // the members of src/hla/alleles.rs the path reads
+    std::string hla_id, gene_name;
+    std::vector<std::string> star_allele;
+    std::optional<std::string> dna_sequence;
+    std::string cdna_sequence;
+};
+using HlaDatabase = std::map<std::string, HlaAlleleDefinition>;  // BTreeMap<hla_id, def>: iteration order is semantics
+
+struct DiplotypeSettings {  // the members of src/cli/diplotype.rs the path reads
+    bool disable_cdna_scoring = false;
+    bool hla_require_dna = true;
+    double min_consensus_fraction = 0.10, min_cdf = 0.001, expected_maf = 0.45;
+    // minimap2's "-s" (min_dp_max, 200 for map-hifi) decides whether a mapping exists at all; the exhaustive aligner
+    // always places the allele somewhere, so the same DP score (a=5 b=4 q=6 e=2 q2=26 e2=1, src/hla/caller.rs:1381)
+    // of the reported CIGAR is held against that threshold
+    int min_dp_score = 200;
+};
+
+// minimap2's DP score of a CIGAR under the scoring of src/hla/caller.rs:1370-1381
+long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar);
+
+struct ScoreReadResult {  // score_read's (HashMap<String, HlaMappingStats>, ReadMappingStats::best_match)
+    std::map<std::string, HlaMappingStats> stats;
+    std::string best_hla_id, best_star_allele;
+};
+// src/hla/caller.rs:1332-1511.  dna_target / cdna_target: the consensus on the gene's strand and its spliced cDNA
+// ("N" when empty), prepared by the host exactly as lines 1337-1368.
+ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const std::string &cdna_target, const HlaDatabase &database,
+                           const std::string &gene_name, const DiplotypeSettings &settings);
+
+struct PgxMappingDetails {  // src/data_types/starphase_json.rs:271-283
+    std::string read_qname, best_hla_id, best_star_allele;
+    HlaMappingStats best_mapping_stats;
+    bool is_ignored = false;
+    Json to_json() const;
+};
+
+class HlaRealigner {  // src/hla/realigner.rs:22-211 (database side only: the allele index and the acceptance loop)
+  public:
+    HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database);
+    // one PgxMappingDetails per read, in input order; n_candidates plays the role of minimap2's best_n = 5
+    std::vector<PgxMappingDetails> realign_records(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
+                                                   int n_candidates = 5);
+    // same, with the read x allele distances (row-major, alleles in the index order) already computed by K1
+    std::vector<PgxMappingDetails> realign_records_scored(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
+                                                          const std::vector<int32_t> &D, int n_candidates = 5);
+    size_t n_alleles() const { return alleles_.size(); }
+
+  private:
+    GpuAligner &gpu_;
+    const HlaDatabase &database_;
+    std::vector<const HlaAlleleDefinition *> alleles_;
+    SeqList allele_seqs_;
+};
+
+struct HlaRead {
+    std::string qname, dna_target, cdna_target;
+};
+struct Diplotype {  // src/data_types/pgx_diplotype.rs:9-26
+    std::string hap1, hap2;
+    Json to_json() const;
+};
+struct HlaGeneCall {
+    Diplotype diplotype;
+    std::string hla_id1, hla_id2;
+    uint64_t pair_score_cdna = 0, pair_score_dna = 0;
+    size_t counts1 = 0, counts2 = 0;
+    std::vector<PgxMappingDetails> mapping_details;
+    Json gene_details() const;  // PgxGeneDetails::new_from_mappings, src/data_types/starphase_json.rs:147-161
+};
+// north_star (2): exhaustive read x allele scoring, allele-pair min-sum ranking with the (cDNA, DNA) key, then the
+// reference's het/hom decision (src/hla/caller.rs:889-901) and diplotype strings (:1046-1065)
+HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name,
+                               const std::vector<HlaRead> &reads, const DiplotypeSettings &settings);
+
+// ------------------------------------------------------------------------------------------
+// CYP2D6
+// ------------------------------------------------------------------------------------------
+enum class Cyp2d6RegionType { Unknown, Rep6, Cyp2d6, LinkRegion, Rep7, Spacer, Cyp2d7, Cyp2d6Deletion, Hybrid, FalseAllele };
+
+struct Cyp2d6RegionLabel {  // src/cyp2d6/region_label.rs:72-266
+    Cyp2d6RegionType region_type = Cyp2d6RegionType::Unknown;
+    std::optional<std::string> subtype_label;
+    bool is_cyp2d() const;
+    bool is_rep() const;
+    bool is_reported_allele() const;
+    std::string full_allele() const;
+    std::string simplify_allele(bool detailed, const std::map<std::string, std::string> &cyp_translate) const;
+    bool is_allowed_label() const;
+    bool is_allowed_label_pair(const Cyp2d6RegionLabel &next) const;
+    bool is_normalizing_allele(bool normalize_all) const;
+    bool is_candidate_chain_head(bool normalize_all) const;
+    void mark_false_allele() { region_type = Cyp2d6RegionType::FalseAllele; }
+};
+const char *region_type_name(Cyp2d6RegionType t);
+Cyp2d6RegionType region_type_from_name(const std::string &s);
+
+struct Cyp2d6Region {  // src/cyp2d6/region.rs (label + unique id)
+    Cyp2d6RegionLabel label;
+    std::optional<size_t> unique_id;
+    std::string index_label() const;  // :50-56
+};
+
+struct Cyp2d6Config {  // the members of src/cyp2d6/definitions.rs:128-336 the chaining code reads
+    std::map<std::string, std::string> cyp_translate;
+    std::set<std::pair<std::string, std::string>> inferred_connections;
+    std::set<std::string> unexpected_singletons;
+    static Cyp2d6Config default_config();
+};
+
+enum class Cyp2d6DetailLevel { CoreAlleles, SubAlleles, DeepAlleles };
+// src/cyp2d6/caller.rs:907-957
+std::string convert_chain_to_hap(const std::vector<size_t> &chain, const std::vector<Cyp2d6Region> &hap_regions,
+                                 Cyp2d6DetailLevel level, const std::map<std::string, std::string> &cyp_translate);
+
+using SequenceWeights = std::vector<std::pair<size_t, double>>;  // src/cyp2d6/chaining.rs:18
+// weight_sequence (src/cyp2d6/chaining.rs:28-103) for a batch of read segments against all consensuses: one K3 span
+// launch instead of one aligner per segment.  Result[s] is empty when the best hit misses more than 5 % (:96-102).
+std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &segments, const SeqList &consensuses,
+                                              const std::vector<Cyp2d6Region> &con_regions);
+
+struct ChainBuild {  // src/cyp2d6/caller.rs:430-537
+    std::map<std::string, std::vector<std::vector<size_t>>> qname_chains;
+    std::map<std::string, std::vector<SequenceWeights>> qname_chain_scores;
+    std::vector<size_t> best_allele_mapping_counts;
+};
+// read_weights[qname] = weight_sequence result per region of the read, read order (empty = region skipped)
+ChainBuild build_chains(const std::map<std::string, std::vector<SequenceWeights>> &read_weights, size_t n_haps);
+
+struct ChainPenalties {  // src/cyp2d6/chaining.rs:107-139
+    double lasso_penalty = 4.0, ln_ed_penalty = 2.0, unexpected_chain_penalty = 10.0, inferred_edge_penalty = 2.0;
+};
+struct ChainPairResult {
+    std::vector<std::vector<size_t>> best_chains;  // two chains, sorted
+    std::vector<std::string> dangling_alleles;      // CallerWarning::DanglingAllele names
+    double score = 0.0;
+    size_t index1 = 0, index2 = 0, n_possible_chains = 0, n_full_evaluations = 0;
+    uint64_t edit_distance = 0;
+};
+struct NoChainingHead : HostError { NoChainingHead() : HostError("NoChainingHead") {} };
+struct NoChainsFound : HostError { NoChainsFound() : HostError("NoChainsFound") {} };
+struct NoScorePairs : HostError { NoScorePairs() : HostError("NoScorePairs") {} };
+// src/cyp2d6/chaining.rs:223-592.  The integer ED term of every chain pair comes from the GPU (chain windows + K2);
+// pairs are then visited in increasing lower bound (all other terms are >= 0) and the float terms (hap weights ->
+// multinomial) are evaluated only until the bound passes the best score: the same arg-min (score, i, j) as the
+// reference's exhaustive loop with its 10-entry heap.
+ChainPairResult find_best_chain_pair(GpuAligner &gpu, const Cyp2d6Config &cfg,
+                                     const std::map<std::string, std::vector<std::vector<size_t>>> &obs_chains,
+                                     const std::map<std::string, std::vector<SequenceWeights>> &chain_scores,
+                                     const std::vector<Cyp2d6Region> &hap_regions, bool infer_connections, bool normalize_all_alleles,
+                                     const ChainPenalties &penalties, bool ignore_chain_label_limits);
+
+struct Cyp2d6ReadRegion {
+    size_t start = 0, end = 0;  // coordinates in the read of the extracted sequence
+    std::string sequence;
+};
+struct Cyp2d6Call {
+    ChainPairResult chain_pair;
+    Diplotype diplotype, simple_diplotype, deep_diplotype;
+    std::vector<Cyp2d6Region> hap_regions;  // after FalseAllele marking
+    Json multi_mapping_details = Json::array();
+    Json gene_details() const;  // PgxGeneDetails::new_from_multi_mappings, src/data_types/starphase_json.rs:169-188
+};
+// the chaining half of diplotype_cyp2d6 (src/cyp2d6/caller.rs:430-739): weights, chains, false alleles, best pair, strings
+Cyp2d6Call call_cyp2d6_chains(GpuAligner &gpu, const Cyp2d6Config &cfg, const SeqList &consensuses,
+                              std::vector<Cyp2d6Region> hap_regions,
+                              const std::map<std::string, std::vector<Cyp2d6ReadRegion>> &regions_of_interest,
+                              bool infer_connections, bool normalize_all_alleles);
+
+// StarphaseJson, src/data_types/starphase_json.rs:13-21; metadata order of src/database/pgx_database.rs:359-371
+std::string starphase_json(const std::string &pbstarphase_version, const std::map<std::string, std::string> &database_metadata,
+                           const std::map<std::string, Json> &gene_details);
+
+}  // namespace starphase

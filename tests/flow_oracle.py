@@ -1,0 +1,174 @@
+"""Oracle-side restatement of the host flows (TEST INFRASTRUCTURE ONLY): the same call sequences as
+pb_starphase_b200/host/*.cpp, but every alignment number comes from the CPU oracle (oracle/sp_oracle.c through
+oracle_util.Oracle) and every piece of host logic from oracle/starphase_oracle.py.  The GPU tests compare the C++
+host (GPU-backed) with these flows: identical integers, identical calls, byte-identical JSON."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import starphase_oracle as so  # noqa: E402
+
+DbRow = Tuple[str, str, List[str], Optional[str], str]  # hla_id, gene, star fields, dna, cdna
+
+
+def dp_score(cigar) -> int:
+    """minimap2 DP score under a=5 b=4 q=6 e=2 q2=26 e2=1 (src/hla/caller.rs:1370-1381)."""
+    s = 0
+    for ln, op in cigar:
+        if op == 7:
+            s += 5 * ln
+        elif op == 8:
+            s -= 4 * ln
+        else:
+            s -= min(6 + 2 * ln, 26 + ln)
+    return s
+
+
+def mapping_from_alignment(a: dict, pattern_len: int, text_len: int, min_dp_score: int = 200) -> Optional[so.Mapping]:
+    if not a["cigar"] or dp_score(a["cigar"]) < min_dp_score:
+        return None
+    return so.Mapping(a["p_start"], a["p_end"], pattern_len, a["t_start"], a["t_end"], text_len, a["nm"], True, a["cigar"])
+
+
+def allowed_alleles(db: Sequence[DbRow], gene: str, require_dna: bool = True) -> List[DbRow]:
+    return [r for r in sorted(db, key=lambda r: r[0].encode()) if r[1] == gene and (r[3] is not None or not require_dna)]
+
+
+def score_read(orc, dna_target: bytes, cdna_target: bytes, db: Sequence[DbRow], gene: str, disable_cdna: bool = False):
+    """src/hla/caller.rs:1332-1511 with the oracle's traceback alignment in place of minimap2."""
+    stats, best = {}, so.HlaProcessedMatch.worst_match(2)
+    for hla_id, _, star, dna, cdna in allowed_alleles(db, gene):
+        cur = so.HlaProcessedMatch(hla_id)
+        for target, seq in ((cdna_target, None if disable_cdna else cdna), (dna_target, dna)):
+            m = None
+            if seq is not None:
+                cand = mapping_from_alignment(orc.align(seq.encode(), target), len(seq), len(target))
+                idx, _ = so.select_best_mapping([cand] if cand else [], False, True)
+                m = cand if idx is not None else None
+            cur.add_mapping(m)
+        st = [None if s is None else (s.seq_len, s.nm, s.unmapped) for s in cur.full_mapping_stats]
+        if cur.is_better_match(best):
+            best = cur
+        stats[hla_id] = tuple(st)
+    star = ""
+    if best.haplotype:
+        star = ":".join(next(r[2] for r in db if r[0] == best.haplotype))
+    return stats, best.haplotype, star
+
+
+def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5,
+                    D: Optional[np.ndarray] = None) -> List[dict]:
+    """src/hla/realigner.rs:98-211: candidates = the n best alleles by distance (ties by database order)."""
+    alleles = [r for r in sorted(db, key=lambda r: r[0].encode()) if r[1] in genes and r[3] is not None]
+    seqs = [r[3].encode() for r in alleles]
+    if D is None:
+        D = orc.score_batch([r[1] for r in reads], seqs) if alleles and reads else np.zeros((len(reads), 0), np.int32)
+    out = []
+    for r, (qname, seq) in enumerate(reads):
+        best, best_a = so.MappingStats(len(seq), len(seq), 0), None
+        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        for a in order:
+            al = orc.align(seqs[a], seq)
+            if not al["cigar"] or dp_score(al["cigar"]) < 200:
+                continue
+            tl = len(seqs[a])
+            st = so.MappingStats(tl, al["nm"], tl - (al["p_end"] - al["p_start"]))
+            if st.mapping_score() <= 0.5 and st.custom_score(False) <= 0.03 and st.custom_score(False) < best.custom_score(False):
+                best, best_a = st, a
+        hs = so.HlaMappingStats(None, best)
+        if best_a is None:
+            out.append(so.mapping_details_json(qname, "REFERENCE", "REFERENCE", hs, True))
+        else:
+            row = alleles[best_a]
+            out.append(so.mapping_details_json(qname, row[0], f"{row[1]}*{':'.join(row[2])}", hs, False))
+    return out
+
+
+def diplotype_hla_gene(orc, db: Sequence[DbRow], gene: str, reads: Sequence[Tuple[str, bytes, bytes]]) -> dict:
+    """north_star (2) + src/hla/caller.rs:889-901, :1046-1065."""
+    al = allowed_alleles(db, gene)
+    Dd = orc.score_batch([r[1] for r in reads], [a[3].encode() for a in al])
+    Dc = orc.score_batch([r[2] for r in reads], [a[4].encode() for a in al])
+    score, score2, i, j, c1 = orc.pair_minsum_topk(Dc, 10, D2=Dd)[0]
+    c2 = len(reads) - c1
+    id1, id2 = al[i][0], al[j][0]
+    if i == j:
+        ids = (id1, id1)
+    else:
+        ids = so.choose_diplotype(id1, id2, c1, c2)
+    star = {a[0]: "*" + ":".join(a[2]) for a in al}
+    details = realign_records(orc, [gene], al, [(r[0], r[1]) for r in reads], D=Dd)
+    gd = so.gene_details_from_mappings([so.diplotype_json(star[ids[0]], star[ids[1]])], details)
+    return dict(hla_id1=ids[0], hla_id2=ids[1], counts1=c1, counts2=c2, pair_score_cdna=score, pair_score_dna=score2, gene_details=gd)
+
+
+# ---- CYP2D6 -----------------------------------------------------------------------------------------------
+def labels_from_rows(rows) -> List[so.RegionLabel]:
+    return [so.RegionLabel(t, s) for t, s, _ in rows]
+
+
+def index_label(row) -> str:
+    lab = so.RegionLabel(row[0], row[1])
+    return (f"{row[2]}" if row[2] is not None else "X") + "_" + lab.full_allele()
+
+
+def weight_sequences(orc, segments: Sequence[bytes], consensuses: Sequence[bytes], labels) -> List[list]:
+    """src/cyp2d6/chaining.rs:28-103 per segment; one hit per consensus unless nothing of the segment aligns."""
+    if not segments:
+        return []
+    D, S, E = orc.score_spans(consensuses, segments)  # [consensus (text)][segment (pattern)]
+    out = []
+    for s, seg in enumerate(segments):
+        hits = []
+        for k, con in enumerate(consensuses):
+            if len(con) == 0 or len(seg) == 0 or D[k, s] >= len(seg):
+                hits.append([])
+            else:
+                hits.append([(int(D[k, s]), int(S[k, s]), len(con) - int(E[k, s]), len(con))])
+        out.append(so.weight_sequence_from_hits(len(seg), labels, hits))
+    return out
+
+
+def call_cyp2d6_chains(orc, consensuses: Sequence[bytes], rows, roi: Dict[str, List[Tuple[int, int, bytes]]], infer: bool,
+                       normalize_all: bool) -> dict:
+    """The chaining half of diplotype_cyp2d6, src/cyp2d6/caller.rs:430-739."""
+    labels = labels_from_rows(rows)
+    cfg = so.Cyp2d6Config.default()
+    qnames = sorted(roi)
+    segs = [r[2] for q in qnames for r in roi[q]]
+    ws = weight_sequences(orc, segs, consensuses, labels)
+    rw, k = {}, 0
+    for q in qnames:
+        rw[q] = ws[k:k + len(roi[q])]
+        k += len(roi[q])
+    chains, scores, counts = so.build_chains(rw, len(labels))
+    mm = []
+    for q in sorted(chains):
+        if len(chains[q]) == 1:
+            for con, reg in zip(chains[q][0], roi[q]):
+                mm.append(dict(read_qname=q, read_position=dict(start=reg[0], end=reg[1]), consensus_id=con,
+                               consensus_star_allele=index_label(rows[con])))
+    rows = list(rows)
+    for c, cnt in enumerate(counts):
+        if cnt == 0 and labels[c].region_type not in (so.UNKNOWN, so.FALSE_ALLELE):
+            labels[c] = so.RegionLabel(so.FALSE_ALLELE, labels[c].subtype_label)
+            rows[c] = (so.FALSE_ALLELE, rows[c][1], rows[c][2])
+    best, danglers, dbg = so.find_best_chain_pair(cfg, chains, scores, labels, infer, normalize_all, so.ChainPenalties(), False,
+                                                  return_debug=True)
+    uids = [r[2] for r in rows]
+
+    def hap(k, level):
+        return so.convert_chain_to_hap(best[k], labels, level, cfg.cyp_translate, uids)
+
+    deep = dict(basic_diplotype=so.diplotype_json(hap(0, so.DEEP), hap(1, so.DEEP)), haplotype_1=None, haplotype_2=None)
+    gd = so.gene_details_from_multi_mappings([so.diplotype_json(hap(0, so.SUB), hap(1, so.SUB))],
+                                             [so.diplotype_json(hap(0, so.CORE), hap(1, so.CORE))], [deep], mm)
+    return dict(best_chains=best, score=dbg["best"]["score"], dangling=danglers, n_possible_chains=len(dbg["possible_chains"]),
+                gene_details=gd)

@@ -1,0 +1,254 @@
+"""CPU suite for the C++ host (pb_starphase_b200/host, pybind11 module _starphase_host): the pure host logic is held
+against the known-answer vectors of the reference's own unit tests (same vectors as test_host_logic_cpu.py, which
+pins the Python oracle) and against the Python oracle on seeded random inputs.  Nothing here needs a GPU; the
+GPU-backed functions are covered by test_host_cpp_gpu.py."""
+import math
+import random
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import starphase_oracle as so  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def host():
+    from pb_starphase_b200 import build
+
+    build.build()
+    build.build_host()
+    from pb_starphase_b200 import _starphase_host
+
+    return _starphase_host
+
+
+CIGAR = [(2, 7), (1, 8), (2, 7), (1, 1), (2, 7), (1, 2), (2, 7)]  # ==X==I==D==
+
+
+def test_process_mm_cigar(host):  # src/hla/processed_match.rs:269-328
+    assert host.process_mm_cigar(CIGAR, 0, 10, 0, 0) == [0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 3]
+    assert host.process_mm_cigar(CIGAR, 3, 18, 2, 3) == [0, 0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 5, 5, 5, 6, 7, 8, 8, 8]
+    assert host.process_mm_cigar([(2, 7)], 2, 4, 100, 0) == [0, 1, 2, 2, 2]
+    assert host.process_mm_cigar([(2, 7)], 0, 4, 0, 100) == [0, 0, 0, 1, 2]
+    with pytest.raises(host.HostError, match="Unexpected cigar type: 0"):
+        host.process_mm_cigar([(4, 0)], 0, 4, 0, 0)
+
+
+def test_process_mm_cigar_random_vs_oracle(host):
+    rnd = random.Random(3)
+    for _ in range(300):
+        cig, t_used = [], 0
+        for _ in range(rnd.randint(0, 8)):
+            op = rnd.choice([1, 2, 7, 8])
+            if cig and cig[-1][1] == op:
+                continue
+            ln = rnd.randint(1, 6)
+            cig.append((ln, op))
+            t_used += ln if op != 1 else 0
+        off = rnd.randint(0, 10)
+        tlen = off + t_used + rnd.randint(0, 10)
+        cs, ce = rnd.randint(0, 15), rnd.randint(0, 15)
+        assert host.process_mm_cigar(cig, off, tlen, cs, ce) == so.process_mm_cigar(cig, off, tlen, cs, ce)
+
+
+def test_mapping_scores(host):  # src/data_types/mapping.rs:211-241, src/hla/mapping.rs:181-229
+    assert host.MappingStats(10, 1, 0).mapping_score() == 0.1
+    assert host.MappingStats(10, 0, 0).mapping_score() == 0.01
+    assert host.MappingStats(10, 1, 5).custom_score(False) == 1 / 5
+    s = host.HlaMappingStats()
+    assert s.mapping_score() == (1.0, 1.0)
+    s.cdna_stats, s.dna_stats = host.MappingStats(10, 1, 0), host.MappingStats(20, 0, 1)
+    assert s.mapping_score() == (0.1, 0.05)
+    rnd = random.Random(1)
+    for _ in range(200):
+        l, nm, um = rnd.randint(1, 5000), rnd.randint(0, 50), 0
+        um = rnd.randint(0, l - 1)
+        for pen in (True, False):
+            assert host.MappingStats(l, nm, um).custom_score(pen) == so.MappingStats(l, nm, um).custom_score(pen)
+
+
+def test_select_best_mapping(host):  # src/util/mapping.rs:22-57
+    m1 = host.Mapping(0, 90, 100, 10, 100, 200, nm=2)
+    m2 = host.Mapping(0, 100, 100, 0, 100, 200, nm=3)
+    assert host.select_best_mapping([m1, m2], False, True) == (1, (100, 3, 0))
+    assert host.select_best_mapping([m1, m2], True, False) == (0, (200, 2, 110))
+    assert host.select_best_mapping([], False, True) == (None, (1, 1, 0))
+    assert host.select_best_mapping([m2, m2], False, True)[0] == 0
+    assert host.select_best_mapping([m1], False, True, 400) == (0, (400, 2, 310))
+
+
+def _pm(host, hla_id, cdna, dna):
+    pm = host.HlaProcessedMatch(hla_id)
+    pm.add_mapping(cdna)
+    pm.add_mapping(dna)
+    return pm
+
+
+def test_is_better_match_overlap_rule(host):  # src/hla/processed_match.rs:103-184
+    full = host.Mapping(0, 10, 10, 0, 10, 10, nm=0, cigar=[(10, 7)])
+    one_x = host.Mapping(0, 10, 10, 0, 10, 10, nm=1, cigar=[(4, 7), (1, 8), (5, 7)])
+    a, b = _pm(host, "A", full, full), _pm(host, "B", one_x, full)
+    assert a.is_better_match(b) and not b.is_better_match(a)
+    worst = host.HlaProcessedMatch.worst_match(2)
+    assert a.is_better_match(worst) and not worst.is_better_match(a)
+    assert not _pm(host, "N", None, None).is_better_match(worst)
+    short = host.Mapping(0, 6, 6, 2, 8, 10, nm=0, cigar=[(6, 7)])
+    assert _pm(host, "C", short, None).is_better_match(_pm(host, "D", one_x, None))
+    rev = host.Mapping(0, 10, 10, 0, 10, 10, nm=0, forward=False, cigar=[(10, 7)])
+    with pytest.raises(host.HostError, match="Reverse strand"):
+        host.HlaProcessedMatch("R").add_mapping(rev)
+
+
+def test_is_better_match_random_vs_oracle(host):
+    rnd = random.Random(9)
+
+    def rand_mapping(tlen):
+        qlen = rnd.randint(5, 30)
+        ts = rnd.randint(0, tlen - 1)
+        cig, t, q, nm = [], ts, 0, 0
+        while t < tlen and q < qlen and rnd.random() < 0.9:
+            op = rnd.choice([7, 7, 7, 8, 1, 2])
+            if cig and cig[-1][1] == op:
+                continue
+            ln = rnd.randint(1, 4)
+            if op in (7, 8, 2):
+                ln = min(ln, tlen - t)
+            if op in (7, 8, 1):
+                ln = min(ln, qlen - q)
+            if ln == 0:
+                break
+            cig.append((ln, op))
+            t += ln if op != 1 else 0
+            q += ln if op != 2 else 0
+            nm += ln if op != 7 else 0
+        qs = rnd.randint(0, qlen - q)
+        return dict(query_start=qs, query_end=qs + q, query_len=qlen, target_start=ts, target_end=t, target_len=tlen, nm=nm, cigar=cig)
+
+    for _ in range(300):
+        tl_c, tl_d = rnd.randint(10, 40), rnd.randint(10, 40)
+        pair = []
+        for _side in range(2):
+            kc = rand_mapping(tl_c) if rnd.random() < 0.85 else None
+            kd = rand_mapping(tl_d) if rnd.random() < 0.85 else None
+            cpp = _pm(host, "x", host.Mapping(**kc) if kc else None, host.Mapping(**kd) if kd else None)
+            py = so.HlaProcessedMatch("x")
+            for k in (kc, kd):
+                py.add_mapping(so.Mapping(k["query_start"], k["query_end"], k["query_len"], k["target_start"], k["target_end"],
+                                          k["target_len"], k["nm"], True, k["cigar"]) if k else None)
+            assert cpp.processed_cigars() == py.processed_cigars and [tuple(r) for r in cpp.processed_ranges()] == py.processed_ranges
+            pair.append((cpp, py))
+        (c1, p1), (c2, p2) = pair
+        assert c1.is_better_match(c2) == p1.is_better_match(p2) and c2.is_better_match(c1) == p2.is_better_match(p1)
+
+
+def test_is_passing_dual(host):  # src/hla/caller.rs:1836-1845
+    kw = dict(min_consensus_fraction=0.10, min_cdf=0.001, expected_maf=0.5)
+    assert not host.is_passing_dual(3, 20, **kw) and not host.is_passing_dual(20, 3, **kw)
+    assert host.is_passing_dual(10, 20, **kw) and host.is_passing_dual(20, 10, **kw)
+    for c1 in range(0, 70, 3):
+        for c2 in range(1, 70, 5):
+            assert host.is_passing_dual(c1, c2) == so.is_passing_dual(c1, c2), (c1, c2)
+            assert host.binomial_cdf(c1 + c2, 0.45, min(c1, c2)) == pytest.approx(so.binomial_cdf(c1 + c2, 0.45, min(c1, c2)), rel=1e-9)
+
+
+def test_statistics(host):  # src/util/stats.rs:45-70
+    assert host.multinomial_ln_pmf([1.0], [10]) == pytest.approx(0.0, abs=1e-9)
+    assert host.multinomial_ln_pmf([0.25, 0.75], [1, 3]) == pytest.approx(math.log(4.0 * 0.25 * 0.75 ** 3), abs=1e-6)
+    assert host.multinomial_ln_pmf([0.25, 0.25, 0.5], [2, 2, 0]) == pytest.approx(math.log(6.0 * 0.25 ** 4), abs=1e-6)
+    rnd = random.Random(2)
+    for _ in range(100):
+        k = rnd.randint(1, 5)
+        raw = [rnd.random() + 0.01 for _ in range(k)]
+        probs = [x / sum(raw) for x in raw]
+        obs = [rnd.randint(0, 400) for _ in range(k)]
+        if sum(obs) == 0:
+            continue
+        assert host.multinomial_ln_pmf(probs, obs) == so.multinomial_ln_pmf(probs, obs)  # same operations in the same order
+    for x in (0, 1, 5, 170, 171, 500, 10000):
+        assert host.ln_factorial(x) == so.ln_factorial(x)
+
+
+TYPES = [so.UNKNOWN, so.REP6, so.CYP2D6, so.LINK, so.REP7, so.SPACER, so.CYP2D7, so.DELETION, so.HYBRID, so.FALSE_ALLELE]
+SUBS = [None, "4.001", "10", "1e2", "abc", "CYP2D6::CYP2D7::exon2", "CYP2D7::CYP2D6::intron1", "nan", "-3.5", ".5", "5."]
+
+
+def test_region_labels_vs_oracle(host):  # src/cyp2d6/region_label.rs
+    tr = so.Cyp2d6Config.default().cyp_translate
+    for t1 in TYPES:
+        for s1 in SUBS:
+            a = so.RegionLabel(t1, s1)
+            for t2 in TYPES:
+                b = so.RegionLabel(t2, None)
+                for na in (True, False):
+                    got = host.label_ops(t1, s1, t2, None, na)
+                    assert got == dict(full_allele=a.full_allele(), simple=a.simplify_allele(False, tr), detailed=a.simplify_allele(True, tr),
+                                       allowed=a.is_allowed_label(), allowed_pair=a.is_allowed_label_pair(b),
+                                       head=a.is_candidate_chain_head(na), normalizing=a.is_normalizing_allele(na)), (t1, s1, t2, na)
+
+
+def test_convert_chain_to_hap(host):  # src/cyp2d6/caller.rs:971-1006
+    rows = [("CYP2D7", None, 0), ("CYP2D6", "1.001", 1), ("CYP2D6", "10", 2), ("CYP2D6", "1.002", 3), ("CYP2D6", "1.002", 4)]
+    assert host.convert_chain_to_hap([2, 2, 1, 0], rows, "SubAlleles") == "*1.001 + *10x2"
+    assert host.convert_chain_to_hap([3, 1, 0], rows, "SubAlleles") == "*1.001 + *1.002"
+    assert host.convert_chain_to_hap([3, 1, 0], rows, "CoreAlleles") == "*1x2"
+    assert host.convert_chain_to_hap([3, 4], rows, "SubAlleles") == "*1.002x2"
+    labels = [so.RegionLabel(t, s) for t, s, _ in rows]
+    tr = so.Cyp2d6Config.default().cyp_translate
+    assert host.convert_chain_to_hap([3, 1, 0], rows, "DeepAlleles") == so.convert_chain_to_hap([3, 1, 0], labels, so.DEEP, tr, [0, 1, 2, 3, 4])
+    rows5 = [("CYP2D6*5", None, None), ("CYP2D6", "4", None)]
+    assert host.convert_chain_to_hap([0], rows5, "CoreAlleles") == "*5" and host.convert_chain_to_hap([0, 1], rows5, "CoreAlleles") == "*4"
+    assert host.convert_chain_to_hap([0], rows5, "DeepAlleles") == "(X_CYP2D6*5)"
+
+
+def test_build_chains_vs_oracle(host):  # src/cyp2d6/caller.rs:430-537
+    rnd = random.Random(6)
+    for trial in range(60):
+        n_haps = rnd.randint(2, 6)
+        rw = {}
+        for r in range(rnd.randint(1, 12)):
+            regions = []
+            for _ in range(rnd.randint(0, 4)):
+                if rnd.random() < 0.15:
+                    regions.append([])
+                else:
+                    regions.append([(rnd.randint(0, 3), rnd.random()) for _ in range(n_haps)])
+            rw[f"read_{r:02d}"] = regions
+        try:
+            want = so.build_chains(rw, n_haps)
+        except RuntimeError:
+            with pytest.raises(host.HostError, match="chain collapse"):
+                host.build_chains(rw, n_haps)
+            continue
+        chains, scores, counts = host.build_chains(rw, n_haps)
+        assert chains == want[0] and counts == want[2]
+        assert {k: [[tuple(x) for x in seg] for seg in v] for k, v in scores.items()} == {k: [[tuple(x) for x in seg] for seg in v] for k, v in want[1].items()}
+
+
+def test_json_writer(host):  # src/util/file_io.rs:37-52, src/data_types/starphase_json.rs:13-21
+    s = host.HlaMappingStats()
+    s.dna_stats = host.MappingStats(3502, 2, 0)
+    meta = dict(pbstarphase_version="2.0.1-test", cpic_version="v", hla_version="3.62.0", pharmvar_version="6", build_time="t\n\"x\"")
+    text = host.starphase_json("2.0.1-test", meta, {"HLA-B": s.to_json(), "HLA-A": s.to_json()})
+    want = so.starphase_json("2.0.1-test", meta, {"HLA-A": so.HlaMappingStats(None, so.MappingStats(3502, 2, 0)).to_json(),
+                                                  "HLA-B": so.HlaMappingStats(None, so.MappingStats(3502, 2, 0)).to_json()})
+    assert text == want
+    with pytest.raises(host.HostError, match="lacks"):
+        host.starphase_json("v", {}, {})
+
+
+def test_no_gpu_is_an_error(host):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(host.HostError, match="no CPU fallback"):
+        host.GpuAligner(0)
+
+
+def test_dp_score(host):
+    assert host.dp_score([(40, 7)]) == 200 and host.dp_score([(10, 7), (1, 8), (10, 7)]) == 96
+    assert host.dp_score([(50, 7), (1, 1), (50, 7)]) == 500 - 8 and host.dp_score([(50, 7), (30, 2), (50, 7)]) == 500 - 56

@@ -1,0 +1,315 @@
+"""GPU parity tests for the C++ host above the C ABI (pb_starphase_b200/host): the reference's operator interface
+for the hot path -- score_read, HlaRealigner, the allele-pair diplotype, weight_sequence, find_best_chain_pair, the
+CYP2D6 chain call and the result JSON -- driven through the pybind11 module, against the same flows restated on the
+CPU oracle (tests/flow_oracle.py).  Integers identical, calls identical, JSON byte-identical."""
+import json
+import math
+import random
+
+import numpy as np
+import pytest
+
+import flow_oracle as fo
+from flow_oracle import so
+from test_k3_gpu import noisy, rnd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host():
+    from pb_starphase_b200 import _starphase_host
+
+    return _starphase_host
+
+
+@pytest.fixture(scope="module")
+def gpu(host):
+    return host.GpuAligner(0)
+
+
+def hla_db(seed=5, n_alleles=14, n_reads=10, genes=("HLA-A", "HLA-B")):
+    """Small two-gene database + heterozygous reads per gene (two source alleles), DNA + cDNA."""
+    from pb_starphase_b200 import synth
+
+    rows, reads = [], {}
+    for g, gene in enumerate(genes):
+        alleles, _, _, cdna = synth.hla_gene(seed + g, gene, n_alleles=n_alleles, n_reads=2, with_cdna=True)
+        rng = np.random.default_rng([seed, g])
+        for a in range(n_alleles):
+            star = [f"{1 + a // 4:02d}", f"{1 + a % 4:02d}", "01", f"{a + 1:02d}"]
+            rows.append((f"HLA:HLA{g * 1000 + a:05d}", gene, star, alleles[a].decode(), cdna[a].decode()))
+        i, j = 2, 9
+        rd, src = synth.hifi_reads(rng, [alleles[i], alleles[j]], n_reads)
+        reads[gene] = [(f"read_{gene}_{k:02d}", rd[k], cdna[(i, j)[int(src[k])]]) for k in range(n_reads)]
+    return rows, reads
+
+
+def cpp_reads(reads):
+    return [(q, d.decode(), c.decode()) for q, d, c in reads]
+
+
+# ---- score_read: src/hla/caller.rs:1332-1511; reference tests :1709-1809 -------------------------------------
+def test_score_read_reference_alleles(host, gpu):
+    """test_reference_alleles (src/hla/caller.rs:1709-1773): an exact copy of an allele scores (len, 0, 0) on both
+    sequence types and is the best match."""
+    rows, _ = hla_db()
+    hla_id, gene, star, dna, cdna = rows[3]
+    stats, best_id, best_star = host.score_read(gpu, dna, cdna, rows, gene, host.DiplotypeSettings())
+    assert stats[hla_id] == ((len(cdna), 0, 0), (len(dna), 0, 0))
+    assert best_id == hla_id and best_star == ":".join(star)
+    assert set(stats) == {r[0] for r in rows if r[1] == gene}
+
+
+def test_score_bad_read(host, gpu):
+    """test_score_bad_read (src/hla/caller.rs:1783-1809): a 4-bp junk read maps nowhere => every allele is worst and
+    there is no best id."""
+    rows, _ = hla_db()
+    stats, best_id, best_star = host.score_read(gpu, "ACGT", "N", rows, "HLA-A", host.DiplotypeSettings())
+    assert all(v == (None, None) for v in stats.values()) and best_id == "" and best_star == ""
+
+
+def test_score_read_vs_oracle(host, gpu, oracle):
+    rows, reads = hla_db()
+    for gene in ("HLA-A", "HLA-B"):
+        for q, dna_t, cdna_t in reads[gene][:2]:
+            got = host.score_read(gpu, dna_t.decode(), cdna_t.decode(), rows, gene, host.DiplotypeSettings())
+            want = fo.score_read(oracle, dna_t, cdna_t, rows, gene)
+            assert (dict(got[0]), got[1], got[2]) == want
+    s = host.DiplotypeSettings()
+    s.disable_cdna_scoring = True
+    q, dna_t, cdna_t = reads["HLA-A"][0]
+    got = host.score_read(gpu, dna_t.decode(), cdna_t.decode(), rows, "HLA-A", s)
+    assert (dict(got[0]), got[1], got[2]) == fo.score_read(oracle, dna_t, cdna_t, rows, "HLA-A", disable_cdna=True)
+
+
+# ---- HlaRealigner: src/hla/realigner.rs:98-211 ------------------------------------------------------------------
+def test_realign_records_vs_oracle(host, gpu, oracle):
+    rows, reads = hla_db()
+    rng = np.random.default_rng(3)
+    rs = [(q, d) for gene in reads for q, d, _ in reads[gene][:4]]
+    rs.append(("junk", rnd(rng, 2500)))                 # maps nowhere well: REFERENCE / ignored
+    rs.append(("empty", b""))                           # record without a sequence (realigner.rs:111-114)
+    rs.append(("noisy", noisy(rng, rows[1][3].encode(), 160)))  # > 3 % edits: rejected by max_ed_frac
+    rs.append(("half", rows[2][3].encode()[:1200]))     # most of the allele unmapped: rejected by max_unmapped_frac
+    got = host.realign_records(gpu, ["HLA-A", "HLA-B"], rows, [(q, s.decode()) for q, s in rs]).pretty()
+    want = so.serde_pretty(fo.realign_records(oracle, ["HLA-A", "HLA-B"], rows, rs))
+    assert got == want
+    back = json.loads(got)
+    assert [d["is_ignored"] for d in back[-4:]] == [True, True, True, True] and not any(d["is_ignored"] for d in back[:-4])
+    assert back[0]["best_star_allele"].startswith("HLA-A*") and back[-4]["best_hla_id"] == "REFERENCE"
+
+
+# ---- allele-pair diplotype: north_star (2), src/hla/caller.rs:889-901 -----------------------------------------
+def test_diplotype_hla_gene_vs_oracle(host, gpu, oracle):
+    rows, reads = hla_db()
+    genes = {}
+    for gene in ("HLA-A", "HLA-B"):
+        got = host.diplotype_hla_gene(gpu, rows, gene, cpp_reads(reads[gene]), host.DiplotypeSettings())
+        want = fo.diplotype_hla_gene(oracle, rows, gene, reads[gene])
+        assert {k: got[k] for k in got if k != "gene_details"} == {k: want[k] for k in want if k != "gene_details"}
+        assert got["gene_details"].pretty() == so.serde_pretty(want["gene_details"])
+        genes[gene] = (got["gene_details"], want["gene_details"])
+        ids = {got["hla_id1"], got["hla_id2"]}
+        base = 0 if gene == "HLA-A" else 1000
+        assert ids == {f"HLA:HLA{base + 2:05d}", f"HLA:HLA{base + 9:05d}"}  # the two source alleles of the reads
+    meta = dict(pbstarphase_version="2.0.1-6-gdeadbee", cpic_version="cpic-v1.44", hla_version="3.57.0", pharmvar_version="6.1.2.1",
+                build_time="2024-08-26T00:00:00Z")
+    text = host.starphase_json("2.0.1-6-gdeadbee", meta, {g: v[0] for g, v in genes.items()})
+    assert text == so.starphase_json("2.0.1-6-gdeadbee", meta, {g: v[1] for g, v in genes.items()})
+    assert text.encode() == text.encode("ascii") and text.startswith('{\n  "pbstarphase_version": "2.0.1-6-gdeadbee",')
+
+
+def test_diplotype_homozygous_and_skewed(host, gpu, oracle):
+    from pb_starphase_b200 import synth
+
+    rows, reads = hla_db()
+    a = [r for r in rows if r[1] == "HLA-A"]
+    rng = np.random.default_rng(12)
+    hom, _ = synth.hifi_reads(rng, [a[5][3].encode()], 8)
+    hom_reads = [(f"h{k}", hom[k], a[5][4].encode()) for k in range(8)]
+    got = host.diplotype_hla_gene(gpu, rows, "HLA-A", cpp_reads(hom_reads), host.DiplotypeSettings())
+    want = fo.diplotype_hla_gene(oracle, rows, "HLA-A", hom_reads)
+    assert got["hla_id1"] == got["hla_id2"] == a[5][0] and got["gene_details"].pretty() == so.serde_pretty(want["gene_details"])
+    # 1 read of a second allele among 24: minor fraction below min_consensus_fraction => homozygous for the majority
+    one, _ = synth.hifi_reads(rng, [a[11][3].encode()], 1)
+    maj, _ = synth.hifi_reads(rng, [a[5][3].encode()], 23)
+    sk = [(f"s{k:02d}", maj[k], a[5][4].encode()) for k in range(23)] + [("s99", one[0], a[11][4].encode())]
+    got = host.diplotype_hla_gene(gpu, rows, "HLA-A", cpp_reads(sk), host.DiplotypeSettings())
+    want = fo.diplotype_hla_gene(oracle, rows, "HLA-A", sk)
+    assert got["hla_id1"] == got["hla_id2"] == a[5][0] == want["hla_id1"] and got["counts1"] == want["counts1"]
+    assert got["gene_details"].pretty() == so.serde_pretty(want["gene_details"])
+    empty = host.diplotype_hla_gene(gpu, rows, "HLA-A", [], host.DiplotypeSettings())
+    assert empty["hla_id1"] == "NO_READS"
+
+
+# ---- find_best_chain_pair: the reference's own tests, src/cyp2d6/chaining.rs:949-1195 ---------------------------
+def d6(name):
+    return ("CYP2D6", name, None)
+
+
+def test_find_best_chain_pair(host, gpu):
+    rows = [d6("A"), d6("B"), d6("C"), d6("D")]
+    obs = {"seq_1": [[0, 2]], "seq_2": [[1, 1]]}
+    scores = {"seq_1": [[(0, 1.0), (1, 1.0), (1, 1.0), (1, 1.0)], [(1, 1.0), (1, 1.0), (0, 1.0), (1, 1.0)]],
+              "seq_2": [[(1, 1.0), (0, 1.0), (1, 1.0), (1, 1.0)], [(1, 1.0), (0, 1.0), (1, 1.0), (1, 1.0)]]}
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, False, True, ignore_limits=True)
+    assert r["best_chains"] == [[0, 2], [1, 1]] and r["dangling"] == ["3_CYP2D6*D"]
+
+
+def test_ambiguous_find_best_chain_pair(host, gpu):
+    rows = [d6("A"), d6("B")]
+    obs = {"seq_0": [[1]], "seq_1": [[1, 0]], "seq_2": [[0, 0]], "seq_3": [[0]], "seq_4": [[1]], "seq_5": [[1, 0]], "seq_6": [[0]]}
+    a, b = [(0, 1.0), (10, 1.0)], [(10, 1.0), (0, 1.0)]
+    scores = {"seq_0": [b], "seq_1": [b, a], "seq_2": [a, a], "seq_3": [a], "seq_4": [b], "seq_5": [b, a], "seq_6": [a]}
+    kw = dict(ignore_limits=True, ln_ed_penalty=-math.log(0.01), unexpected_chain_penalty=0.0, inferred_edge_penalty=2.0)
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, False, True, lasso_penalty=0.0, **kw)
+    assert r["best_chains"] == [[1], [1, 0, 0, 0]] and r["dangling"] == []
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, False, True, lasso_penalty=3.0, **kw)
+    assert r["best_chains"] == [[1], [1, 0, 0]] and r["dangling"] == []
+
+
+def pairwise_chains(num_labels, chains):  # create_pairwise_chains, src/cyp2d6/chaining.rs:918-947
+    obs, scores, idx = {}, {}, 0
+    for chain in chains:
+        for a, b in zip(chain, chain[1:]):
+            name = f"read_{idx}"
+            obs[name] = [[a, b]]
+            w = []
+            for h in chain:
+                row = [(100, 1.0)] * num_labels
+                row[h] = (0, 1.0)
+                w.append(row)
+            scores[name] = w
+            idx += 1
+    return obs, scores
+
+
+def test_inferred_alleles(host, gpu):
+    rows = [d6("3"), ("link_region", None, None), ("REP7", None, None), ("spacer", None, None), ("CYP2D7", None, None), d6("4"),
+            ("Hybrid", "CYP2D6::CYP2D7::exon2", None)]
+    obs, scores = pairwise_chains(len(rows), [[0, 1], [2, 3, 4], [5, 1], [2, 3, 6]])
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, False, True)
+    assert r["best_chains"] == [[0, 1], [5, 1]]
+    assert r["dangling"] == ["2_REP7", "3_spacer", "4_CYP2D7", "6_CYP2D6::CYP2D7::exon2"]
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, True, True)
+    assert r["best_chains"] == [[0, 1, 2, 3, 4], [5, 1, 2, 3, 6]] and r["dangling"] == []
+
+
+def test_chaining_errors_and_double5(host, gpu):
+    rows = [("CYP2D7", None, None), ("link_region", None, None), ("spacer", None, None), ("UNKNOWN", None, None)]
+    with pytest.raises(host.NoChainingHead):
+        host.find_best_chain_pair(gpu, {}, {}, rows, False, True)
+    with pytest.raises(host.HostError, match="Lasso"):
+        host.find_best_chain_pair(gpu, {}, {}, rows, False, True, lasso_penalty=-1.0)
+    rows = [("CYP2D6*5", None, None)]
+    obs = {f"read{x}": [[0]] for x in range(2)}
+    scores = {f"read{x}": [[(0, 1.0)]] for x in range(2)}
+    r = host.find_best_chain_pair(gpu, obs, scores, rows, True, False)
+    assert r["best_chains"] == [[0], [0]] and r["dangling"] == []
+
+
+def test_find_best_chain_pair_random_vs_oracle(host, gpu):
+    """Bound-ordered search on GPU edit distances == the reference's exhaustive loop with its 10-entry heap."""
+    import signal
+
+    class TooSlow(Exception):
+        pass
+
+    def on_alarm(*_):
+        raise TooSlow()
+
+    signal.signal(signal.SIGALRM, on_alarm)
+    py_rng = random.Random(77)
+    kinds = [("REP6", None), ("CYP2D6", "1"), ("CYP2D6", "4.001"), ("CYP2D6", "2"), ("link_region", None), ("REP7", None), ("spacer", None),
+             ("CYP2D7", None), ("CYP2D6*5", None), ("Hybrid", "CYP2D6::CYP2D7::exon2"), ("CYP2D6", "10"), ("CYP2D6", "36")]
+    done = 0
+    for trial in range(80):
+        n = py_rng.randint(2, 8)
+        rows = [py_rng.choice(kinds) + (None,) for _ in range(n)]
+        labels = fo.labels_from_rows(rows)
+        obs, scores = {}, {}
+        for r in range(py_rng.randint(1, 14)):
+            w = py_rng.randint(1, 3)
+            chain = [py_rng.randrange(n) for _ in range(w)]
+            obs[f"r{r:02d}"] = [chain] if py_rng.random() < 0.8 else [chain, [py_rng.randrange(n) for _ in range(w)]]
+            seg_rows = []
+            for t in range(w):
+                row = [(py_rng.randint(3, 40), py_rng.choice([1.0, 0.9, 0.5])) for _ in range(n)]
+                row[chain[t]] = (py_rng.randint(0, 2), 1.0)
+                seg_rows.append(row)
+            scores[f"r{r:02d}"] = seg_rows
+        infer, norm_all, ign = py_rng.random() < 0.5, py_rng.random() < 0.5, py_rng.random() < 0.3
+        signal.alarm(2)  # random label soups can have an astronomical number of chains: only instances the oracle finishes count
+        try:
+            want = so.find_best_chain_pair(so.Cyp2d6Config.default(), obs, scores, labels, infer, norm_all, so.ChainPenalties(), ign,
+                                           return_debug=True)
+        except TooSlow:
+            continue
+        except (so.NoChainingHead, so.NoChainsFound, so.NoScorePairs) as e:
+            signal.alarm(0)
+            with pytest.raises(getattr(host, type(e).__name__)):
+                host.find_best_chain_pair(gpu, obs, scores, rows, infer, norm_all, ignore_limits=ign)
+            continue
+        finally:
+            signal.alarm(0)
+        got = host.find_best_chain_pair(gpu, obs, scores, rows, infer, norm_all, ignore_limits=ign)
+        best = want[2]["best"]
+        assert got["best_chains"] == want[0] and got["dangling"] == want[1], trial
+        assert (got["score"], got["i"], got["j"], got["edit_distance"]) == (best["score"], best["i"], best["j"], best["edit_distance"]), trial
+        assert got["n_possible_chains"] == len(want[2]["possible_chains"])
+        done += 1
+    assert done >= 30
+
+
+# ---- weight_sequence + the whole CYP2D6 chain call: src/cyp2d6/chaining.rs:28-103, caller.rs:430-739 --------------
+def cyp_case(seed=1, n_reads=36, scale=320):
+    """Two haplotypes REP6 - D6 - link - REP7 - spacer - D7 (hap B = *4.001 with its own region copies) and HiFi-like
+    reads that span 2-4 consecutive regions of one haplotype."""
+    rng = np.random.default_rng(seed)
+    kinds = ["REP6", "CYP2D6", "link_region", "REP7", "spacer", "CYP2D7"]
+    base = [rnd(rng, int(scale * f)) for f in (0.9, 1.6, 0.8, 0.9, 0.6, 1.5)]
+    cons, rows = [], []
+    for hap, sub in enumerate(("1.001", "4.001")):
+        for k, kind in enumerate(kinds):
+            seq = bytearray(base[k])
+            for pos in rng.choice(len(seq), size=max(4, len(seq) // 60), replace=False):  # ~1.7 % haplotype-specific SNPs
+                seq[pos] = b"ACGT"[(b"ACGT".index(seq[pos]) + 1 + hap) % 4]
+            cons.append(bytes(seq))
+            rows.append((kind, sub if kind == "CYP2D6" else None, len(rows)))
+    roi = {}
+    for r in range(n_reads):
+        hap, start, w = int(rng.integers(0, 2)), int(rng.integers(0, 5)), int(rng.integers(2, 5))
+        pos, regs = int(rng.integers(50, 300)), []
+        for t in range(start, min(start + w, 6)):
+            seg = noisy(rng, cons[hap * 6 + t], int(rng.integers(0, 3))).replace(b"N", b"A")
+            regs.append((pos, pos + len(seg), seg))
+            pos += len(seg)
+        roi[f"m64/{r:03d}/ccs"] = regs
+    return cons, rows, roi
+
+
+def test_weight_sequences_vs_oracle(host, gpu, oracle):
+    cons, rows, roi = cyp_case()
+    segs = [r[2] for q in sorted(roi) for r in roi[q]][:40] + [rnd(np.random.default_rng(4), 300)]  # + one junk segment => []
+    rows2 = list(rows)
+    rows2[7] = ("UNKNOWN", None, 7)  # skipped consensus (chaining.rs:52-55)
+    got = host.weight_sequences(gpu, [s.decode() for s in segs], [c.decode() for c in cons], rows2)
+    want = fo.weight_sequences(oracle, segs, cons, fo.labels_from_rows(rows2))
+    assert [[tuple(x) for x in ws] for ws in got] == [[tuple(x) for x in ws] for ws in want]
+    assert got[-1] == [] and all(ws[7] == (len(s), 0.0) for ws, s in zip(got[:-1], segs))
+
+
+def test_call_cyp2d6_chains_vs_oracle(host, gpu, oracle):
+    for seed, infer in ((1, False), (2, True)):
+        cons, rows, roi = cyp_case(seed)
+        cpp_roi = {q: [(a, b, s.decode()) for a, b, s in regs] for q, regs in roi.items()}
+        got = host.call_cyp2d6_chains(gpu, [c.decode() for c in cons], rows, cpp_roi, infer, True)
+        want = fo.call_cyp2d6_chains(oracle, cons, rows, roi, infer, True)
+        assert got["best_chains"] == want["best_chains"] and got["score"] == want["score"] and got["dangling"] == want["dangling"]
+        assert got["n_possible_chains"] == want["n_possible_chains"]
+        text = got["gene_details"].pretty()
+        assert text == so.serde_pretty(want["gene_details"])
+        back = json.loads(text)
+        assert back["diplotypes"][0]["diplotype"] in ("*1.001/*4.001", "*4.001/*1.001") and back["simple_diplotypes"][0]["diplotype"] in ("*1/*4", "*4/*1")
+        assert back["multi_mapping_details"] and back["multi_mapping_details"][0]["read_position"].keys() == {"start", "end"}
