@@ -46,13 +46,13 @@ struct AlignParams {
 
 // the K1 recurrence over `ncols` text columns T[0 .. ncols) for this warp's bin; STORE keeps (D0, ~Pv) per column
 template <bool STORE>
-__device__ __forceinline__ void k4_forward(const uint32_t *peq_lane, const uint8_t *T, int ncols, const AlignParams &p,
+__device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *T, int ncols, const AlignParams &p,
                                            bool first, bool owns, int m, int &best, int &best_col, uint32_t *scr,
                                            int Wp, int wf4) {
     constexpr int U = ALN_U;
     const int lane = threadIdx.x & 31;
     uint32_t npv[U], mv[U], d0[U];
-    load_row<U>(peq_lane + 5 * (32 * U), npv);
+    load_row<U>(blob + 5 * (32 * U), lane, npv);
 #pragma unroll
     for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; d0[u] = 0; }
     int score = m, col = 0;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void k4_forward(const uint32_t *peq_lane, const uint8
             for (int c = 0; c < K1_CHUNK; ++c) {
                 const int j = idx * K1_CHUNK + c;
                 const uint32_t code = j < ncols ? base_code(T[j]) : 4u;
-                column_step<U, true, STORE>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col,
+                column_step<U, true, STORE>(blob, lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col,
                                             best_col, d0);
                 if (STORE && owns && j < ncols) {
                     uint32_t *dst = scr + static_cast<size_t>(j) * 2 * Wp + (lane * U - wf4);
@@ -92,7 +92,6 @@ __device__ __forceinline__ void k4_forward(const uint32_t *peq_lane, const uint8
 
 __global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
     constexpr int U = ALN_U;
-    constexpr int V = vec_width(U);
     constexpr int BW = blob_words(U);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,14 +124,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
         const int wf4 = (pad >> 5) & ~3, Wp = nl * U - wf4;
         const uint8_t *T = p.tbases + p.toffs[t];
         const int n = static_cast<int>(p.toffs[t + 1] - p.toffs[t]);
-        const uint32_t *peq_lane = blob + lane * V;
-
         int best, best_col;
-        k4_forward<false>(peq_lane, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
+        k4_forward<false>(blob, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
         const int src_lane = __ffs(__ballot_sync(0xffffffffu, last)) - 1;
         const int d = __shfl_sync(0xffffffffu, best, src_lane), e = __shfl_sync(0xffffffffu, best_col, src_lane);
         const int w0 = max(0, e - (m_all + d)), ncols = e - w0;
-        k4_forward<true>(peq_lane, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
+        k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) {
@@ -150,7 +147,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
                     const uint32_t d0w = __ldcg(colp), npvw = __ldcg(colp + Wp);
                     const uint32_t code = base_code(T[w0 + j - 1]);
                     const int wl = w / U, wu = w % U;
-                    const bool match = code < 4 && ((blob[(code * (U / V) + wu / V) * 32 * V + wl * V + (wu % V)] >> b) & 1u);
+                    const bool match = code < 4 && ((blob[code * 32 * U + row_word(U, wl, wu)] >> b) & 1u);
                     const bool d0b = (d0w >> b) & 1u;
                     if (match || !d0b) { op = match ? CIG_EQ : CIG_X; --i; --j; }  // the diagonal explains the cell
                     else if (!((npvw >> b) & 1u)) { op = CIG_I; --i; }             // vertical delta +1

@@ -23,7 +23,19 @@ constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int K1_CHUNK = 8;                 // text columns per chunk (one uint2 of byte codes)
 constexpr int PEQ_ROWS = 6;                 // A,C,G,T, N(other), pv-init
 __host__ __device__ constexpr int blob_words(int U) { return PEQ_ROWS * 32 * U + 64; }
-__host__ __device__ constexpr int vec_width(int U) { return (U % 4 == 0) ? 4 : (U % 2 == 0) ? 2 : 1; }
+// One mask row of a bin is 32 lanes x U words, stored as word groups so that each lane fetches its U words with the
+// fewest conflict-free shared-memory loads: U/4 groups of four (LDS.128), then a pair (LDS.64) if U % 4 >= 2, then a
+// single word (LDS.32) if U is odd.  Inside a group the lanes are contiguous.
+__host__ __device__ constexpr int grp_start(int U, int u) {
+    return u < (U / 4) * 4 ? (u / 4) * 4 : ((U % 4) >= 2 && u < (U / 4) * 4 + 2) ? (U / 4) * 4 : (U / 4) * 4 + ((U % 4) >= 2 ? 2 : 0);
+}
+__host__ __device__ constexpr int grp_width(int U, int u) {
+    return u < (U / 4) * 4 ? 4 : ((U % 4) >= 2 && u < (U / 4) * 4 + 2) ? 2 : 1;
+}
+// word index of (lane, u) inside one mask row
+__host__ __device__ constexpr int row_word(int U, int lane, int u) {
+    return 32 * grp_start(U, u) + lane * grp_width(U, u) + (u - grp_start(U, u));
+}
 // info1 bit layout
 constexpr uint32_t INFO_FIRST = 1u << 30;
 constexpr uint32_t INFO_LAST = 1u << 31;
@@ -100,20 +112,18 @@ __device__ __forceinline__ uint32_t base_code(uint8_t c) {
 // linked by the adder carry (IADD3.X) and funnel shifts (SHF.L.W), 10 ALU ops per word.
 // ------------------------------------------------------------------------------------------
 template <int U>
-__device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)[U]) {
-    constexpr int V = vec_width(U);
+__device__ __forceinline__ void load_row(const uint32_t *row, int lane, uint32_t (&v)[U]) {
+    constexpr int N4 = U / 4;
 #pragma unroll
-    for (int q = 0; q < U / V; ++q) {
-        if (V == 4) {
-            uint4 x = *reinterpret_cast<const uint4 *>(row_lane + q * 128);
-            v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        } else if (V == 2) {
-            uint2 x = *reinterpret_cast<const uint2 *>(row_lane + q * 64);
-            v[2 * q + 0] = x.x; v[2 * q + 1] = x.y;
-        } else {
-            v[q] = row_lane[q * 32];
-        }
+    for (int q = 0; q < N4; ++q) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(row + q * 128 + lane * 4);
+        v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
+    if (U % 4 >= 2) {
+        const uint2 x = *reinterpret_cast<const uint2 *>(row + N4 * 128 + lane * 2);
+        v[4 * N4 + 0] = x.x; v[4 * N4 + 1] = x.y;
+    }
+    if (U % 2) v[U - 1] = row[32 * (U - 1) + lane];
 }
 
 // K1 inner step, "arithmetic form".
@@ -131,12 +141,12 @@ __device__ __forceinline__ void load_row(const uint32_t *row_lane, uint32_t (&v)
 // FMA pipe.  The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
 // The Myers add (Eq & Pv) + Pv becomes t - npv - 1 (borrow chain seeded with 1, SubChain1).
 template <int U, bool TRACK_END, bool KEEP_D0 = false>
-__device__ __forceinline__ void column_step(const uint32_t *peq_lane, uint32_t code, uint32_t one, uint32_t m1,
+__device__ __forceinline__ void column_step(const uint32_t *peq, int lane, uint32_t code, uint32_t one, uint32_t m1,
                                             uint32_t (&npv)[U], uint32_t (&mv)[U], uint32_t &X, uint32_t &Y,
                                             uint32_t &cph, uint32_t &cmh, int &score, int &best, int &col,
                                             int &best_col, uint32_t *d0_keep = nullptr) {
     uint32_t eq[U], xv[U], t[U], sum[U];
-    load_row<U>(peq_lane + code * (32 * U), eq);
+    load_row<U>(peq + code * (32 * U), lane, eq);
     eq[0] |= (Y >> 31);  // hin < 0 (Hyyro): the row above already paid for this column
 #pragma unroll
     for (int u = 0; u < U; ++u) xv[u] = eq[u] | mv[u];
@@ -197,7 +207,6 @@ __device__ __forceinline__ void fill_score_lut(ScoreLut *lut) {
 template <int U, bool TRACK_END>
 __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s_text, int nch, int text0,
                                             const K1Params &p, const ScoreLut *lut) {
-    constexpr int V = vec_width(U);
     const int lane = threadIdx.x & 31;
     const uint32_t pat = blob[PEQ_ROWS * 32 * U + lane];
     if (__all_sync(0xffffffffu, pat == NO_PATTERN)) return;  // filler warp of a partly used group
@@ -205,11 +214,10 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
     const bool first = (info1 & INFO_FIRST) != 0;
     const bool last = (info1 & INFO_LAST) != 0;
     const int m = static_cast<int>(info1 & INFO_LEN_MASK);
-    const uint32_t *peq_lane = blob + lane * V;
     const uint32_t cin_first = p.prefix_mode ? 0x00FFu : 0u;
 
     uint32_t npv[U], mv[U];  // ~Pv, Mv
-    load_row<U>(peq_lane + 5 * (32 * U), npv);
+    load_row<U>(blob + 5 * (32 * U), lane, npv);
 #pragma unroll
     for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
     int score = m, best = m, col = 0, best_col = 0;
@@ -238,7 +246,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
             uint32_t cphA = 0, cmhA = 0, cphB = 0, cmhB = 0;  // columns 0-3 and 4-7
 #pragma unroll
             for (int c = 0; c < K1_CHUNK; ++c)
-                column_step<U, TRACK_END>(peq_lane, codes[c], p.one, p.m1, npv, mv, X, Y, c < 4 ? cphA : cphB,
+                column_step<U, TRACK_END>(blob, lane, codes[c], p.one, p.m1, npv, mv, X, Y, c < 4 ? cphA : cphB,
                                           c < 4 ? cmhA : cmhB, score, best, col, best_col);
             const uint32_t iA = cmhA * p.sixteen + cphA, iB = cmhB * p.sixteen + cphB;  // IMAD: table indices
             carry_out = (cphA * p.sixteen + cphB) | ((iA & 0xF0u) << 8) | ((iB & 0xF0u) << 4);
@@ -256,7 +264,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
                     if (TRACK_END) p.out_end[o] = best_col;
                 }
                 ++tcount;
-                load_row<U>(peq_lane + 5 * (32 * U), npv);
+                load_row<U>(blob + 5 * (32 * U), lane, npv);
 #pragma unroll
                 for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
                 score = m; best = m; col = 0; best_col = 0;
@@ -329,7 +337,6 @@ struct SpanParams {
 
 __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
     constexpr int U = SPAN_U;
-    constexpr int V = vec_width(U);
     constexpr int BW = blob_words(U);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -360,9 +367,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
         const int wlen = min(e, m_all + d);
         const int nch = (wlen + K1_CHUNK - 1) / K1_CHUNK;
         const uint8_t *T = p.tbases + p.toffs[t];
-        const uint32_t *peq_lane = blob + lane * V;
         uint32_t npv[U], mv[U];
-        load_row<U>(peq_lane + 5 * (32 * U), npv);
+        load_row<U>(blob + 5 * (32 * U), lane, npv);
 #pragma unroll
         for (int u = 0; u < U; ++u) { npv[u] = ~npv[u]; mv[u] = 0; }
         int score = m, best = m, col = 0, best_col = 0;
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
                 for (int c = 0; c < K1_CHUNK; ++c) {
                     const int j = idx * K1_CHUNK + c;
                     const uint32_t code = j < wlen ? base_code(T[e - 1 - j]) : 4u;
-                    column_step<U, true>(peq_lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
+                    column_step<U, true>(blob, lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
                 }
                 carry_out = cph | (cmh << 8);
             }
@@ -449,7 +455,6 @@ __global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long
     const int bin = static_cast<int>(idx / (32 * U));
     const int rem = static_cast<int>(idx - static_cast<long long>(bin) * 32 * U);
     const int lane = rem / U, u = rem % U;
-    const int V = vec_width(U);
     const int BW = blob_words(U);
     const int pat = lane_pat[bin * 32 + lane];
     uint32_t mask[PEQ_ROWS] = {0, 0, 0, 0, 0, 0};
@@ -471,7 +476,7 @@ __global__ void pack_patterns(const uint8_t *__restrict__ bases, const long long
     }
     uint32_t *blob = blobs + static_cast<size_t>(bin) * BW;
 #pragma unroll
-    for (int k = 0; k < PEQ_ROWS; ++k) blob[(k * (U / V) + u / V) * 32 * V + lane * V + (u % V)] = mask[k];
+    for (int k = 0; k < PEQ_ROWS; ++k) blob[k * 32 * U + row_word(U, lane, u)] = mask[k];
     if (u == 0) {
         blob[PEQ_ROWS * 32 * U + lane] = pat >= 0 ? static_cast<uint32_t>(pat) : NO_PATTERN;
         blob[PEQ_ROWS * 32 * U + 32 + lane] = pat >= 0 ? lane_info1[bin * 32 + lane] : INFO_FIRST;
