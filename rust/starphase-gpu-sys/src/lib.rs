@@ -21,6 +21,22 @@ pub struct sp_pair_rec {
     pub _pad: u32,
 }
 
+/// One traceback alignment (include/starphase_gpu.h `sp_align_rec`): the minimap2::Mapping fields
+/// HlaProcessedMatch::add_mapping reads (src/hla/processed_match.rs:53-100).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct sp_align_rec {
+    pub dist: i32,
+    pub nm: i32,
+    pub p_start: i32,
+    pub p_end: i32,
+    pub t_start: i32,
+    pub t_end: i32,
+    pub n_cigar: i32,
+    pub _pad: i32,
+    pub cigar_off: i64,
+}
+
 pub enum sp_ctx {}
 pub enum sp_patterns {}
 pub enum sp_targets {}
@@ -45,6 +61,12 @@ extern "C" {
                           dist: *mut i32, end_col: *mut i32) -> c_int;
     pub fn sp_score_spans(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, dist: *mut i32,
                           start_col: *mut i32, end_col: *mut i32) -> c_int;
+    pub fn sp_align_pairs(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, n_pairs: i64,
+                          pair_target: *const i32, pair_pattern: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
+                          cigar_cap: i64, cigar_used: *mut i64) -> c_int;
+    pub fn sp_chain_window_scores(ctx: *mut sp_ctx, n_chains: i64, chain_off: *const i32, chain_items: *const i32, n_reads: i64,
+                                  seg_off: *const i32, w: *const u32, n_haps: i64, out: *mut *mut sp_dmatrix) -> c_int;
+    pub fn sp_pair_minsum_full(ctx: *mut sp_ctx, d: *const sp_dmatrix, s: *mut u64) -> c_int;
     pub fn sp_pair_minsum_topk(ctx: *mut sp_ctx, d: *const sp_dmatrix, d2: *const sp_dmatrix, i_begin: i64,
                                i_end: i64, k: c_int, out: *mut sp_pair_rec, n_out: *mut c_int) -> c_int;
     pub fn sp_pair_minsum_topk_host(ctx: *mut sp_ctx, d: *const i32, d2: *const i32, r: i64, a: i64, k: c_int,
@@ -70,6 +92,7 @@ impl SeqSet {
     }
     pub fn len(&self) -> usize { self.offsets.len() - 1 }
     pub fn is_empty(&self) -> bool { self.len() == 0 }
+    pub fn seq_len(&self, i: usize) -> usize { (self.offsets[i + 1] - self.offsets[i]) as usize }
     fn raw(&self) -> sp_seqset {
         sp_seqset { bases: self.bases.as_ptr(), offsets: self.offsets.as_ptr(), n: self.len() as i64 }
     }
@@ -101,6 +124,28 @@ impl GpuScorer {
         let st = unsafe { sp_score_spans(self.ctx, &targets.raw(), &patterns.raw(), d.as_mut_ptr(), s.as_mut_ptr(), e.as_mut_ptr()) };
         if st != 0 { return Err(Self::err(self.ctx).into()); }
         Ok((d, s, e))
+    }
+    /// Traceback alignment of the listed (target, pattern) pairs: what `aligner.map(..)` + `select_best_mapping` hand to
+    /// `HlaProcessedMatch::add_mapping` (query = pattern = allele, target = text = consensus).  Returns the records and
+    /// the shared CIGAR buffer of `(len << 4) | op` entries (ops 1 = I, 2 = D, 7 = '=', 8 = X).
+    pub fn align_pairs(&self, targets: &SeqSet, patterns: &SeqSet, pairs: &[(i32, i32)])
+        -> Result<(Vec<sp_align_rec>, Vec<u32>), Box<dyn std::error::Error>> {
+        let pt: Vec<i32> = pairs.iter().map(|p| p.0).collect();
+        let pp: Vec<i32> = pairs.iter().map(|p| p.1).collect();
+        let cap: i64 = pairs.iter().map(|&(t, p)| {
+            let (n, m) = (targets.seq_len(t as usize) as i64, patterns.seq_len(p as usize) as i64);
+            m + n.min(2 * m) + 1
+        }).sum();
+        let mut recs = vec![sp_align_rec::default(); pairs.len()];
+        let mut cigar = vec![0u32; cap.max(1) as usize];
+        let mut used: i64 = 0;
+        let st = unsafe {
+            sp_align_pairs(self.ctx, &targets.raw(), &patterns.raw(), pairs.len() as i64, pt.as_ptr(), pp.as_ptr(),
+                           recs.as_mut_ptr(), cigar.as_mut_ptr(), cap, &mut used)
+        };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        cigar.truncate(used as usize);
+        Ok((recs, cigar))
     }
     /// k best allele pairs by (sum_r min(D[r,i], D[r,j]), same on D2, i, j); D, D2 are [R][A] row-major.
     pub fn pair_topk(&self, d: &[i32], d2: Option<&[i32]>, r: usize, a: usize, k: usize) -> Result<Vec<sp_pair_rec>, Box<dyn std::error::Error>> {
