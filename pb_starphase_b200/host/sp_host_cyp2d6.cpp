@@ -182,6 +182,122 @@ std::string convert_chain_to_hap(const std::vector<size_t> &chain, const std::ve
 }
 
 // ------------------------------------------------------------------------------------------
+// template search -- src/cyp2d6/haplotyper.rs:142-315
+// ------------------------------------------------------------------------------------------
+Cyp2d6Extractor::Cyp2d6Extractor(GpuAligner &gpu, std::vector<std::pair<Cyp2d6RegionLabel, std::string>> hybrid_sequences)
+    : gpu_(gpu), templates_(std::move(hybrid_sequences)) {
+    std::stable_sort(templates_.begin(), templates_.end(),
+                     [](const auto &a, const auto &b) { return a.first.full_allele() < b.first.full_allele(); });  // key_order, :175-183
+}
+
+static double overlap_score(size_t s1, size_t e1, size_t s2, size_t e2) {  // :877-893
+    const size_t min_end = std::min(e1, e2), max_start = std::max(s1, s2);
+    if (max_start >= min_end) return 0.0;
+    return static_cast<double>(min_end - max_start) / std::min(static_cast<double>(e1 - s1), static_cast<double>(e2 - s2));
+}
+static size_t get_allele_priority(const Cyp2d6RegionLabel &l) { return l.region_type == RT::Cyp2d6Deletion ? 1 : 0; }  // :898-903
+static bool is_penalized_type(const Cyp2d6RegionLabel &l) {  // :185-191
+    return l.region_type == RT::Cyp2d6Deletion || l.region_type == RT::Rep6 || l.region_type == RT::Rep7;
+}
+
+std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_sequences(const SeqList &seqs, bool penalize_unmapped,
+                                                                                     double max_missing_frac) {
+    (void)penalize_unmapped;  // only changes the reference's debug strings
+    const double max_ed_frac = 0.05;  // :160
+    const size_t nt = templates_.size();
+    struct Hit { size_t start, end; MappingStats stats; size_t tmpl; };
+    std::vector<std::vector<Hit>> uncollapsed(seqs.size());
+    std::vector<std::vector<size_t>> n_hits(seqs.size(), std::vector<size_t>(nt, 0));
+    struct Item { size_t seq, lo, hi, tmpl; };  // search template tmpl in seqs[seq][lo, hi)
+    std::vector<Item> items;
+    SeqList tmpl_seqs;
+    for (const auto &t : templates_) tmpl_seqs.push_back(t.second);
+
+    // round 0: every (sequence, template) through K1; only placements that could pass go to the traceback
+    SeqList texts;
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    std::vector<Item> pair_item;
+    std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
+    if (!seqs.empty() && nt) {
+        std::vector<int32_t> E;
+        const std::vector<int32_t> D = gpu_.score_batch(seqs, tmpl_seqs, &E);
+        for (size_t s = 0; s < seqs.size(); ++s) {
+            if (seqs[s].empty()) continue;  // :148-151
+            for (size_t t = 0; t < nt; ++t) {
+                const size_t m = tmpl_seqs[t].size();
+                const size_t d = static_cast<size_t>(D[s * nt + t]), e = static_cast<size_t>(E[s * nt + t]);
+                if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
+                const size_t w0 = e > m + d ? e - (m + d) : 0;
+                pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(t));
+                texts.push_back(seqs[s].substr(w0, e - w0));
+                pair_item.push_back({s, 0, seqs[s].size(), t});
+                pair_off.push_back(w0);
+            }
+        }
+    }
+    for (int round = 0; round < 5 && !pairs.empty(); ++round) {
+        const std::vector<Alignment> alns = gpu_.align_pairs(texts, tmpl_seqs, pairs);
+        std::vector<Item> next;
+        for (size_t q = 0; q < pairs.size(); ++q) {
+            const Alignment &a = alns[q];
+            const Item &it = pair_item[q];
+            const size_t m = tmpl_seqs[it.tmpl].size();
+            if (a.cigar.empty() || dp_score(a.cigar, 1) < 200) continue;  // no mapping reported
+            const size_t clipped_start = static_cast<size_t>(a.p_start), clipped_end = m - static_cast<size_t>(a.p_end);
+            MappingStats st(m, static_cast<size_t>(a.nm), m - static_cast<size_t>(a.p_end - a.p_start));
+            st.clipped_start = clipped_start; st.clipped_end = clipped_end;  // new_with_clippings, :214-217
+            if (st.custom_score(is_penalized_type(templates_[it.tmpl].first)) > max_ed_frac) continue;  // :221-226
+            const size_t hs = pair_off[q] + static_cast<size_t>(a.t_start), he = pair_off[q] + static_cast<size_t>(a.t_end);
+            uncollapsed[it.seq].push_back({hs, he, st, it.tmpl});
+            if (++n_hits[it.seq][it.tmpl] >= 5) continue;  // best_n = 5 (src/util/mapping.rs:8-14)
+            // the same template may occur again left or right of this hit (duplications)
+            const size_t min_len = static_cast<size_t>(0.9 * (1.0 - std::min(max_missing_frac, 1.0)) * static_cast<double>(m));
+            if (hs > it.lo && hs - it.lo >= std::max<size_t>(min_len, 200)) next.push_back({it.seq, it.lo, hs, it.tmpl});
+            if (it.hi > he && it.hi - he >= std::max<size_t>(min_len, 200)) next.push_back({it.seq, he, it.hi, it.tmpl});
+        }
+        texts.clear(); pairs.clear(); pair_item.clear(); pair_off.clear();
+        for (const Item &it : next) {
+            pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(it.tmpl));
+            texts.push_back(seqs[it.seq].substr(it.lo, it.hi - it.lo));
+            pair_item.push_back(it);
+            pair_off.push_back(it.lo);
+        }
+    }
+
+    std::vector<std::vector<AlleleMapping>> out(seqs.size());
+    for (size_t s = 0; s < seqs.size(); ++s) {
+        std::vector<Hit> &u = uncollapsed[s];
+        // the reference pushes template by template in key order, mappings in the aligner's order (best first)
+        std::stable_sort(u.begin(), u.end(), [](const Hit &a, const Hit &b) {
+            if (a.tmpl != b.tmpl) return a.tmpl < b.tmpl;
+            return a.stats.custom_score(true) < b.stats.custom_score(true);
+        });
+        std::stable_sort(u.begin(), u.end(), [](const Hit &a, const Hit &b) {  // :245-247
+            return std::make_pair(a.start, a.end) < std::make_pair(b.start, b.end);
+        });
+        std::vector<Hit> region_mappings;
+        std::optional<Hit> cur;
+        for (const Hit &h : u) {  // :252-290
+            if (!cur) { cur = h; continue; }
+            if (overlap_score(h.start, h.end, cur->start, cur->end) > 0.9) {
+                const auto &hl = templates_[h.tmpl].first, &cl = templates_[cur->tmpl].first;
+                const bool penalized = is_penalized_type(hl) || is_penalized_type(cl);
+                const size_t hp = get_allele_priority(hl), cp = get_allele_priority(cl);
+                if ((h.stats.custom_score(penalized) < cur->stats.custom_score(penalized) && hp >= cp) || hp > cp) cur = h;
+            } else {
+                region_mappings.push_back(*cur);
+                cur = h;
+            }
+        }
+        if (cur) region_mappings.push_back(*cur);
+        for (const Hit &h : region_mappings)  // :297-312
+            if (!(h.stats.custom_score(true) > max_missing_frac))
+                out[s].push_back({templates_[h.tmpl].first, h.start, h.end, h.stats});
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // weights and chains
 // ------------------------------------------------------------------------------------------
 std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &segments, const SeqList &consensuses,

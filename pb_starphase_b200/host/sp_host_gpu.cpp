@@ -37,11 +37,13 @@ void GpuAligner::check(sp_status st, const char *what) {
 
 uint64_t GpuAligner::launch_count() const { return sp_launch_count(ctx_); }
 
-std::vector<int32_t> GpuAligner::score_batch(const SeqList &targets, const SeqList &patterns) {
+std::vector<int32_t> GpuAligner::score_batch(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> *end_col) {
     Packed t(targets), p(patterns);
     std::vector<int32_t> D(std::max<size_t>(targets.size() * patterns.size(), 1));
-    check(sp_score_batch(ctx_, &t.set, &p.set, SP_INFIX, D.data(), nullptr), "sp_score_batch");
+    if (end_col) end_col->assign(D.size(), 0);
+    check(sp_score_batch(ctx_, &t.set, &p.set, SP_INFIX, D.data(), end_col ? end_col->data() : nullptr), "sp_score_batch");
     D.resize(targets.size() * patterns.size());
+    if (end_col) end_col->resize(D.size());
     return D;
 }
 

@@ -6,12 +6,12 @@
 
 namespace starphase {
 
-long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar) {
+long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match_score) {
     long s = 0;
     for (const auto &op : cigar) {
         const long l = static_cast<long>(op.first);
         switch (op.second) {
-            case 7: s += 5 * l; break;
+            case 7: s += match_score * l; break;
             case 8: s -= 4 * l; break;
             case 1: case 2: s -= std::min(6 + 2 * l, 26 + l); break;
             default: throw HostError("Unexpected cigar type: " + std::to_string(op.second));

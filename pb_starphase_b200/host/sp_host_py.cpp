@@ -72,7 +72,7 @@ PYBIND11_MODULE(_starphase_host, m) {
         return std::make_pair(r.first, std::make_tuple(r.second.seq_len, r.second.nm, r.second.unmapped));
     }, py::arg("mappings"), py::arg("unmapped_from_target"), py::arg("penalize_unmapped"), py::arg("base_length_override") = std::nullopt);
     m.def("process_mm_cigar", &process_mm_cigar);
-    m.def("dp_score", &dp_score);
+    m.def("dp_score", &dp_score, py::arg("cigar"), py::arg("match_score") = 5);
 
     py::class_<HlaProcessedMatch>(m, "HlaProcessedMatch")
         .def(py::init<std::string>())
@@ -101,7 +101,7 @@ PYBIND11_MODULE(_starphase_host, m) {
 
     py::class_<GpuAligner>(m, "GpuAligner")
         .def(py::init<int>(), py::arg("device") = 0)
-        .def("score_batch", &GpuAligner::score_batch)
+        .def("score_batch", [](GpuAligner &g, const SeqList &t, const SeqList &p) { return g.score_batch(t, p); })
         .def("launch_count", &GpuAligner::launch_count)
         .def("align_pairs", [](GpuAligner &g, const SeqList &t, const SeqList &p, const std::vector<std::pair<int32_t, int32_t>> &pairs) {
             py::list out;
@@ -168,6 +168,22 @@ PYBIND11_MODULE(_starphase_host, m) {
         d["head"] = a.is_candidate_chain_head(normalize_all);
         d["normalizing"] = a.is_normalizing_allele(normalize_all);
         return d;
+    });
+    m.def("find_base_type_in_sequences", [](GpuAligner &g, const std::vector<std::tuple<std::string, std::optional<std::string>, std::string>> &templates,
+                                            const SeqList &seqs, bool penalize_unmapped, double max_missing_frac) {
+        std::vector<std::pair<Cyp2d6RegionLabel, std::string>> ts;
+        for (const auto &t : templates) ts.push_back({Cyp2d6RegionLabel{region_type_from_name(std::get<0>(t)), std::get<1>(t)}, std::get<2>(t)});
+        Cyp2d6Extractor ex(g, std::move(ts));
+        py::list out;
+        for (const auto &hits : ex.find_base_type_in_sequences(seqs, penalize_unmapped, max_missing_frac)) {
+            py::list one;
+            for (const AlleleMapping &h : hits)
+                one.append(py::make_tuple(h.allele_label.full_allele(), h.region_start, h.region_end,
+                                          py::make_tuple(h.mapping_stats.seq_len, h.mapping_stats.nm, h.mapping_stats.unmapped,
+                                                         h.mapping_stats.clipped_start, h.mapping_stats.clipped_end)));
+            out.append(one);
+        }
+        return out;
     });
     m.def("convert_chain_to_hap", [](const std::vector<size_t> &chain, const RegionRows &rows, const std::string &level) {
         const Cyp2d6Config cfg = Cyp2d6Config::default_config();

@@ -151,8 +151,8 @@ class GpuAligner {
     ~GpuAligner();
     GpuAligner(const GpuAligner &) = delete;
     GpuAligner &operator=(const GpuAligner &) = delete;
-    // D[t * patterns.size() + p]
-    std::vector<int32_t> score_batch(const SeqList &targets, const SeqList &patterns);
+    // D[t * patterns.size() + p]; end_col (optional) = smallest end column of a best placement
+    std::vector<int32_t> score_batch(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> *end_col = nullptr);
     void score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
                      std::vector<int32_t> &end);
     std::vector<Alignment> align_pairs(const SeqList &targets, const SeqList &patterns,
@@ -191,8 +191,9 @@ struct DiplotypeSettings {  // the members of src/cli/diplotype.rs the path read
     int min_dp_score = 200;
 };
 
-// minimap2's DP score of a CIGAR under the scoring of src/hla/caller.rs:1370-1381
-long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar);
+// minimap2's DP score of a CIGAR: match_score 5 is the scoring of src/hla/caller.rs:1370-1381, 1 the map-hifi default
+// of standard_hifi_aligner (src/util/mapping.rs:8-14); b=4 q=6 e=2 q2=26 e2=1 in both
+long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match_score = 5);
 
 struct ScoreReadResult {  // score_read's (HashMap<String, HlaMappingStats>, ReadMappingStats::best_match)
     std::map<std::string, HlaMappingStats> stats;
@@ -274,6 +275,32 @@ struct Cyp2d6Region {  // src/cyp2d6/region.rs (label + unique id)
     Cyp2d6RegionLabel label;
     std::optional<size_t> unique_id;
     std::string index_label() const;  // :50-56
+};
+
+struct AlleleMapping {  // src/cyp2d6/haplotyper.rs:836-869
+    Cyp2d6RegionLabel allele_label;
+    size_t region_start = 0, region_end = 0;  // coordinates inside the searched sequence
+    MappingStats mapping_stats;               // relative to the template, with clippings
+};
+
+// The search half of Cyp2d6Extractor (src/cyp2d6/haplotyper.rs:142-315): which of the D6 / D7 / hybrid / REP / spacer /
+// link / *5 templates (generate_cyp_hybrids, src/cyp2d6/definitions.rs:346-464) occur where in a sequence.
+class Cyp2d6Extractor {
+  public:
+    // hybrid_sequences: (label, template sequence); iterated in full_allele() string order like :175-183
+    Cyp2d6Extractor(GpuAligner &gpu, std::vector<std::pair<Cyp2d6RegionLabel, std::string>> hybrid_sequences);
+    // find_base_type_in_sequence for a batch of sequences (reads or consensuses).  One K1 launch scores every
+    // (sequence, template) pair; promising pairs get a K4 traceback on the placement window; every accepted hit
+    // re-opens the search in the unexplained remainders left and right of it for the same template (minimap2 reports
+    // up to best_n = 5 mappings per query, e.g. both copies of a duplication), then the reference's overlap collapse
+    // and missing-fraction filter run unchanged.
+    std::vector<std::vector<AlleleMapping>> find_base_type_in_sequences(const SeqList &search_sequences, bool penalize_unmapped,
+                                                                        double max_missing_frac);
+    const std::vector<std::pair<Cyp2d6RegionLabel, std::string>> &hybrid_sequences() const { return templates_; }
+
+  private:
+    GpuAligner &gpu_;
+    std::vector<std::pair<Cyp2d6RegionLabel, std::string>> templates_;
 };
 
 struct Cyp2d6Config {  // the members of src/cyp2d6/definitions.rs:128-336 the chaining code reads

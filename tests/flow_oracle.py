@@ -172,3 +172,84 @@ def call_cyp2d6_chains(orc, consensuses: Sequence[bytes], rows, roi: Dict[str, L
                                              [so.diplotype_json(hap(0, so.CORE), hap(1, so.CORE))], [deep], mm)
     return dict(best_chains=best, score=dbg["best"]["score"], dangling=danglers, n_possible_chains=len(dbg["possible_chains"]),
                 gene_details=gd)
+
+
+# ---- CYP2D6 template search: src/cyp2d6/haplotyper.rs:142-315 -------------------------------------------------
+def dp_score_a1(cigar) -> int:
+    """minimap2 DP score under the map-hifi defaults of standard_hifi_aligner (a=1 b=4 q=6 e=2 q2=26 e2=1)."""
+    s = 0
+    for ln, op in cigar:
+        if op == 7:
+            s += ln
+        elif op == 8:
+            s -= 4 * ln
+        else:
+            s -= min(6 + 2 * ln, 26 + ln)
+    return s
+
+
+def find_base_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missing_frac: float):
+    """templates: [(region_type, subtype, sequence bytes)].  Same search as Cyp2d6Extractor::find_base_type_in_sequences
+    in pb_starphase_b200/host/sp_host_cyp2d6.cpp, but every traceback runs over the whole (sub)segment with the oracle's
+    full-matrix DP instead of the GPU's placement window."""
+    PEN = (so.DELETION, so.REP6, so.REP7)
+    tl = sorted(templates, key=lambda t: so.RegionLabel(t[0], t[1]).full_allele())  # stable, like the host
+    tseqs = [t[2] for t in tl]
+    labels = [so.RegionLabel(t[0], t[1]) for t in tl]
+    out = []
+    D, E = orc.score_batch(list(seqs), tseqs, want_end_col=True) if len(seqs) and tl else (None, None)
+    for s, seq in enumerate(seqs):
+        hits, n_hits = [], [0] * len(tl)
+        items = []
+        if len(seq):
+            for t in range(len(tl)):
+                m, d = len(tseqs[t]), int(D[s, t])
+                if m == 0 or 2 * d > m:
+                    continue
+                items.append((0, len(seq), t))
+        for _round in range(5):
+            nxt = []
+            for lo, hi, t in items:
+                m = len(tseqs[t])
+                a = orc.align(tseqs[t], seq[lo:hi])
+                if not a["cigar"] or dp_score_a1(a["cigar"]) < 200:
+                    continue
+                st = so.MappingStats(m, a["nm"], m - (a["p_end"] - a["p_start"]), a["p_start"], m - a["p_end"])
+                if st.custom_score(labels[t].region_type in PEN) > 0.05:
+                    continue
+                hs, he = lo + a["t_start"], lo + a["t_end"]
+                hits.append((hs, he, st, t))
+                n_hits[t] += 1
+                if n_hits[t] >= 5:
+                    continue
+                min_len = max(int(0.9 * (1.0 - min(max_missing_frac, 1.0)) * float(m)), 200)
+                if hs > lo and hs - lo >= min_len:
+                    nxt.append((lo, hs, t))
+                if hi > he and hi - he >= min_len:
+                    nxt.append((he, hi, t))
+            items = nxt
+            if not items:
+                break
+        hits.sort(key=lambda h: (h[3], h[2].custom_score(True)))
+        hits.sort(key=lambda h: (h[0], h[1]))
+        regions, cur = [], None
+        for h in hits:
+            if cur is None:
+                cur = h
+                continue
+            mn, mx = min(h[1], cur[1]), max(h[0], cur[0])
+            ov = 0.0 if mx >= mn else float(mn - mx) / min(float(h[1] - h[0]), float(cur[1] - cur[0]))
+            if ov > 0.9:
+                pen = labels[h[3]].region_type in PEN or labels[cur[3]].region_type in PEN
+                hp = 1 if labels[h[3]].region_type == so.DELETION else 0
+                cp = 1 if labels[cur[3]].region_type == so.DELETION else 0
+                if (h[2].custom_score(pen) < cur[2].custom_score(pen) and hp >= cp) or hp > cp:
+                    cur = h
+            else:
+                regions.append(cur)
+                cur = h
+        if cur is not None:
+            regions.append(cur)
+        out.append([(labels[t].full_allele(), hs, he, (st.seq_len, st.nm, st.unmapped, st.clipped_start, st.clipped_end))
+                    for hs, he, st, t in regions if not st.custom_score(True) > max_missing_frac])
+    return out

@@ -313,3 +313,53 @@ def test_call_cyp2d6_chains_vs_oracle(host, gpu, oracle):
         back = json.loads(text)
         assert back["diplotypes"][0]["diplotype"] in ("*1.001/*4.001", "*4.001/*1.001") and back["simple_diplotypes"][0]["diplotype"] in ("*1/*4", "*4/*1")
         assert back["multi_mapping_details"] and back["multi_mapping_details"][0]["read_position"].keys() == {"start", "end"}
+
+
+# ---- template search: Cyp2d6Extractor::find_base_type_in_sequence, src/cyp2d6/haplotyper.rs:142-315 -------------
+def cyp_templates(seed=3, scale=260):
+    """Small-scale generate_cyp_hybrids: D6, D7 (97 % identical), two D6::D7 / D7::D6 hybrids, *5 signature, REP6, REP7
+    (near identical), spacer, link."""
+    rng = np.random.default_rng(seed)
+    d6 = rnd(rng, int(scale * 3.0))
+    d7 = bytearray(d6)
+    for pos in rng.choice(len(d7), size=len(d7) // 33, replace=False):
+        d7[pos] = b"ACGT"[(b"ACGT".index(d7[pos]) + 1) % 4]
+    d7 = bytes(d7)
+    h = len(d6) // 2
+    rep6 = rnd(rng, int(scale * 1.4))
+    rep7 = rep6[:-12] + rnd(rng, 12)
+    star5 = rnd(rng, int(scale * 0.9)) + rnd(rng, int(scale * 0.9))
+    return dict(d6=d6, d7=d7, rep6=rep6, rep7=rep7, spacer=rnd(rng, int(scale * 1.1)), link=rnd(rng, int(scale * 1.5)), star5=star5,
+                templates=[("CYP2D6", None, d6), ("CYP2D7", None, d7), ("Hybrid", "CYP2D6::CYP2D7::exon2", d6[:h] + d7[h:]),
+                           ("Hybrid", "CYP2D7::CYP2D6::exon2", d7[:h] + d6[h:]), ("CYP2D6*5", None, star5), ("REP6", None, rep6), ("REP7", None, rep7),
+                           ("spacer", None, None), ("link_region", None, None)])
+
+
+def test_find_base_type_in_sequences_vs_oracle(host, gpu, oracle):
+    c = cyp_templates()
+    templates = [(t, s, (seq if seq is not None else c["spacer" if t == "spacer" else "link"])) for t, s, seq in c["templates"]]
+    rng = np.random.default_rng(8)
+    fl = lambda n: rnd(rng, n)  # noqa: E731
+    hap = c["rep6"] + c["d6"] + c["link"] + c["rep7"] + c["spacer"] + c["d7"]
+    seqs = [
+        fl(150) + noisy(rng, hap, 12).replace(b"N", b"A") + fl(120),                                   # the reference layout
+        fl(80) + noisy(rng, c["rep6"] + c["d6"] + c["link"] + c["rep6"] + c["d6"] + c["link"], 10).replace(b"N", b"A") + fl(90),  # duplication: D6 twice
+        c["d6"][len(c["d6"]) // 3:] + c["link"] + fl(40),                                              # read starts inside D6: clipped template
+        fl(100) + c["star5"] + fl(100),                                                                # *5 signature
+        fl(700),                                                                                       # nothing to find
+        b"",                                                                                           # :148-151
+        fl(50) + templates[2][2] + c["link"] + fl(50),                                                 # a hybrid: must win over D6 / D7
+    ]
+    names = {}
+    for mmf in (0.1, 0.5):
+        got = host.find_base_type_in_sequences(gpu, [(t, s, q.decode()) for t, s, q in templates], [s.decode() for s in seqs], False, mmf)
+        want = fo.find_base_type_in_sequences(oracle, templates, seqs, mmf)
+        assert [[tuple(h[:3]) + (tuple(h[3]),) for h in one] for one in got] == want
+        names[mmf] = [[h[0] for h in one] for one in got]
+    # a third of D6 is missing from the read: reported when half may be missing, dropped at 10 % (haplotyper.rs:297-312)
+    assert names[0.5][2] == ["CYP2D6", "link_region"] and names[0.1][2] == ["link_region"]
+    assert got[2][0][3][3:] == (len(c["d6"]) // 3, 0)  # clipped_start, clipped_end
+    names = names[0.5]
+    assert names[0] == ["REP6", "CYP2D6", "link_region", "REP7", "spacer", "CYP2D7"]
+    assert names[1].count("CYP2D6") == 2 and names[1].count("link_region") == 2
+    assert names[3] == ["CYP2D6*5"] and names[4] == [] and names[5] == [] and "CYP2D6::CYP2D7::exon2" in names[6]
