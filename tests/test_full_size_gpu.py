@@ -78,3 +78,36 @@ def test_full_size_pair_ranking_sharded_equals_unsharded(ctx, workload):
     assert c1 == int(le.sum())
     for h in (dd, dc, T, Tc, P, Pc):
         h.close()
+
+
+def test_panel_scale_shard(ctx, oracle):
+    """BASELINE.json configs[2] ("targeted PGx panel 1000x: ~40k reads x HLA-A/B alleles, allele-sharded on 2/4/8 B200"):
+    what ONE of 8 ranks computes -- all 40,960 reads against its 1/8 allele shard (7e14 cells) -- with a seeded oracle
+    sample, bounds, and shard == slice-of-a-wider-shard on a read subset."""
+    from pb_starphase_b200 import synth
+    from pb_starphase_b200.sharding import shard_range
+
+    g = synth.hla_wgs_workload(synth.DEFAULT_SEED, 40960, 1.0)
+    dna = g["HLA-A"]["dna"] + g["HLA-B"]["dna"]
+    reads = g["HLA-A"]["reads"] + g["HLA-B"]["reads"]
+    assert len(reads) == 40960 and len(dna) == 12451
+    lo, hi, _ = shard_range(len(dna), 2, 8)
+    shard = dna[lo:hi]
+    T, P = ctx.targets(reads), ctx.patterns(shard)
+    d = ctx.score_device(T, P, elem_bits=16)
+    D = d.to_host_u16().astype(np.int64)
+    d.close(); P.close(); T.close()
+    assert D.shape == (40960, hi - lo)
+    lens = np.array([len(a) for a in shard])
+    assert (D <= lens[None, :]).all()
+    rng = np.random.default_rng(3)
+    rows = np.unique(rng.integers(0, len(reads), 12))
+    assert (D[rows] == oracle.score_batch([reads[r] for r in rows], shard)).all()
+    for r, a in zip(rng.integers(0, len(reads), 40), rng.integers(0, len(shard), 40)):
+        assert D[r, a] == oracle.infix(shard[a], reads[r])[0]
+    # the same numbers when the shard is cut differently (2-way shards) on a subset of the reads
+    lo2, hi2, _ = shard_range(len(dna), 0, 2)
+    assert lo2 <= lo and hi <= hi2
+    sub = [int(r) for r in rows]
+    D2 = ctx.score_batch([reads[r] for r in sub], dna[lo2:hi2])
+    assert (D2[:, lo - lo2:hi - lo2] == D[sub]).all()

@@ -61,6 +61,34 @@ def test_score_read_reference_alleles(host, gpu):
     assert set(stats) == {r[0] for r in rows if r[1] == gene}
 
 
+def test_score_read_golden_hla_faux(host, gpu):
+    """The reference's own fixture (test_data/HLA-faux/database.json, committed as tests/golden/hla_faux.json):
+    test_reference_alleles (src/hla/caller.rs:1709-1773) for HLA-A (forward gene) and HLA-B (reverse-strand gene: the read is
+    the reverse complement and the host puts it back on the gene strand, :1343-1350), and test_score_bad_read (:1783-1809)."""
+    from pathlib import Path
+
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "hla_faux.json").read_text())
+    rows = [(hid, d["gene_name"], d["star_allele"], d["dna_sequence"], d["cdna_sequence"]) for hid, d in g["hla_sequences"].items()]
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    for exp in g["expected"]["test_reference_alleles"]:
+        d = g["hla_sequences"][exp["hla_id"]]
+        read = d["dna_sequence"].encode()
+        if exp["read_is_revcomp"]:
+            read = read.translate(comp)[::-1]             # what the BAM holds for a reverse-strand gene
+            read = read.translate(comp)[::-1]             # reverse_complement() of score_read puts it on the gene strand
+        stats, best_id, best_star = host.score_read(gpu, read.decode(), d["cdna_sequence"], rows, exp["gene"], host.DiplotypeSettings())
+        assert best_id == exp["hla_id"] and best_star == exp["star"]
+        assert stats[exp["hla_id"]] == ((len(d["cdna_sequence"]), 0, 0), (len(d["dna_sequence"]), 0, 0))
+        assert set(stats) == {exp["hla_id"]}              # only the alleles of that gene are scored
+    bad = g["expected"]["test_score_bad_read"]
+    s = host.DiplotypeSettings()
+    s.disable_cdna_scoring = True
+    stats, best_id, _ = host.score_read(gpu, bad["read"], "N", rows, bad["gene"], s)
+    assert best_id == "" and all(v == (None, None) for v in stats.values())
+    h = host.HlaMappingStats()
+    assert h.mapping_score() == (bad["worst_score"], bad["worst_score"])
+
+
 def test_score_bad_read(host, gpu):
     """test_score_bad_read (src/hla/caller.rs:1783-1809): a 4-bp junk read maps nowhere => every allele is worst and
     there is no best id."""
