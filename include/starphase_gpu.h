@@ -92,7 +92,7 @@ void sp_ctx_destroy(sp_ctx *ctx);
  * reference's Box<dyn Error> strings.  ctx may be NULL for creation failures. */
 const char *sp_last_error(const sp_ctx *ctx);
 /* Device time in ms of the most recent launch of kernel `which`
- * (0 = K1 scoring, 1 = K2 pair scoring, 2 = pattern pack, 3 = text pack), measured
+ * (0 = K1 scoring, 1 = K2 pair scoring, 2 = pattern pack, 3 = text pack, 4 = K4 alignment), measured
  * with CUDA events on the context stream; < 0 if it has not run.  Synchronises. */
 float sp_last_kernel_ms(sp_ctx *ctx, int which);
 /* Number of kernel launches issued by this context since creation. */

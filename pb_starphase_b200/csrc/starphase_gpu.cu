@@ -3,6 +3,7 @@
 #include "../../include/starphase_gpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -25,8 +26,8 @@ struct sp_ctx {
     int num_sms = 0;
     int smem_optin = 0;
     std::string err;
-    cudaEvent_t ev[4][2] = {};
-    bool ev_valid[4] = {false, false, false, false};
+    cudaEvent_t ev[5][2] = {};
+    bool ev_valid[5] = {false, false, false, false, false};
     uint64_t launches = 0;
     void *scratch = nullptr;  // grow-only device staging buffer (transposed result rows), reused across calls
     size_t scratch_bytes = 0;
@@ -150,7 +151,7 @@ extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
         }
         ctx->own_stream = true;
     }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
     *out = ctx;
     return SP_OK;
@@ -160,7 +161,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->scratch);
@@ -174,7 +175,7 @@ extern "C" sp_status sp_ctx_synchronize(sp_ctx *ctx) {
 }
 
 extern "C" float sp_last_kernel_ms(sp_ctx *ctx, int which) {
-    if (!ctx || which < 0 || which > 3 || !ctx->ev_valid[which]) return -1.0f;
+    if (!ctx || which < 0 || which > 4 || !ctx->ev_valid[which]) return -1.0f;
     if (cudaEventSynchronize(ctx->ev[which][1]) != cudaSuccess) return -1.0f;
     float ms = -1.0f;
     if (cudaEventElapsedTime(&ms, ctx->ev[which][0], ctx->ev[which][1]) != cudaSuccess) return -1.0f;
@@ -890,6 +891,19 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
 // ------------------------------------------------------------------------------------------
 static_assert(sizeof(sp_align_rec) == sizeof(AlignRecDev), "sp_align_rec layout");
 
+// SP_TIMING=1: wall-clock phases of the host side to stderr (diagnostic only)
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer() : on(getenv("SP_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sp_timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int64_t n_pairs,
                                     const int32_t *pair_target, const int32_t *pair_pattern, sp_align_rec *recs,
                                     uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used) {
@@ -904,6 +918,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     if (n_pairs == 0) return SP_OK;
     if (n_pairs > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "sp_align_pairs: too many pairs");
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PhaseTimer tm;
 
     // only the sequences some pair names travel to the device
     std::vector<int32_t> t_local(static_cast<size_t>(targets->n), -1), p_local(static_cast<size_t>(patterns->n), -1);
@@ -948,9 +963,10 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         cig_off[static_cast<size_t>(q) + 1] = cig_off[static_cast<size_t>(q)] + m + ncols + 1;
     }
     max_slot_words = (max_slot_words + 3) / 4 * 4;
-    // one scratch slot per resident warp, capped at 8 GB in total
+    tm.mark("gather + plan");
+    // one scratch slot per resident warp, capped at 4 GB in total (the context's grow-only scratch: no malloc / free per call)
     int64_t n_slots = std::min<int64_t>(n_pairs, 2ll * ctx->num_sms * K1_WARPS);
-    const int64_t budget_words = (8ll << 30) / 4;
+    const int64_t budget_words = (4ll << 30) / 4;
     n_slots = std::max<int64_t>(1, std::min(n_slots, budget_words / max_slot_words));
     if (max_slot_words > (24ll << 30) / 4) return fail(ctx, SP_ERR_NOMEM, "sp_align_pairs: traceback scratch of one pair exceeds 24 GB");
     const int grid = static_cast<int>((n_slots + K1_WARPS - 1) / K1_WARPS);
@@ -964,7 +980,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     auto cleanup = [&]() {
         cudaFree(d_tb); cudaFree(d_pb); cudaFree(d_to); cudaFree(d_po); cudaFree(d_cig_off); cudaFree(d_out_off);
         cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_pt); cudaFree(d_pp); cudaFree(d_lane_info1);
-        cudaFree(d_blobs); cudaFree(d_cigar); cudaFree(d_scratch); cudaFree(d_dense); cudaFree(d_recs);
+        cudaFree(d_blobs); cudaFree(d_cigar); cudaFree(d_dense); cudaFree(d_recs);  // d_scratch belongs to the context
     };
     auto cu = [&](cudaError_t e, const char *what) -> sp_status {
         if (e != cudaSuccess)
@@ -1007,8 +1023,9 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(ALN_U) * 4), "cudaMalloc blobs"));
     SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_cigar), static_cast<size_t>(cig_off.back()) * 4), "cudaMalloc cigar"));
     SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_recs), static_cast<size_t>(n_pairs) * sizeof(AlignRecDev)), "cudaMalloc recs"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_scratch), static_cast<size_t>(grid) * K1_WARPS * max_slot_words * 4),
-              "cudaMalloc traceback scratch"));
+    SP_TRY(cu(ctx_scratch(ctx, static_cast<size_t>(grid) * K1_WARPS * max_slot_words * 4, reinterpret_cast<void **>(&d_scratch)),
+              "traceback scratch"));
+    tm.mark("upload + cudaMalloc");
     {
         const long long total_threads = static_cast<long long>(np) * 32 * ALN_U;
         pack_patterns<<<static_cast<int>((total_threads + 255) / 256), 256, 0, ctx->stream>>>(
@@ -1023,13 +1040,16 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         prm.recs = d_recs; prm.n_pairs = static_cast<int>(n_pairs); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
         const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(ALN_U) * 4;
         SP_TRY(cu(cudaFuncSetAttribute(k4_align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "k4_align smem"));
+        ev_begin(ctx, 4);
         k4_align<<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        ev_end(ctx, 4);
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "k4_align launch"));
     }
     std::vector<AlignRecDev> hrec(static_cast<size_t>(n_pairs));
     SP_TRY(cu(cudaMemcpyAsync(hrec.data(), d_recs, hrec.size() * sizeof(AlignRecDev), cudaMemcpyDeviceToHost, ctx->stream), "D2H recs"));
     SP_TRY(cu(cudaStreamSynchronize(ctx->stream), "k4_align"));
+    tm.mark("pack + k4_align + recs D2H");
     std::vector<long long> out_off(static_cast<size_t>(n_pairs) + 1, 0);
     for (int64_t q = 0; q < n_pairs; ++q) out_off[static_cast<size_t>(q) + 1] = out_off[static_cast<size_t>(q)] + hrec[static_cast<size_t>(q)].n_cigar;
     const int64_t total = out_off.back();
@@ -1054,7 +1074,9 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         o.n_cigar = r.n_cigar; o._pad = 0; o.cigar_off = out_off[static_cast<size_t>(q)];
     }
 #undef SP_TRY
+    tm.mark("compact + cigar D2H");
     cleanup();
+    tm.mark("cudaFree");
     return SP_OK;
 }
 
