@@ -205,6 +205,13 @@ sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
                          const int32_t *pair_target, const int32_t *pair_pattern, sp_align_rec *recs,
                          uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used);
 
+/* ---- K5: candidate lists -------------------------------------------------------------------- */
+/* The k best patterns of every target of a device matrix (k <= 16): idx / dist are [n_targets][k] row-major, ordered
+ * by (distance, pattern index) ascending; entries beyond n_patterns are -1.  Plays the role of minimap2's best_n hit
+ * list in HlaRealigner::realign_record (src/hla/realigner.rs:116-146, best_n = 5 from src/util/mapping.rs:8-14): only
+ * these candidates go on to sp_align_pairs, and R x k records cross PCIe instead of the R x A matrix. */
+sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist);
+
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
  * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;

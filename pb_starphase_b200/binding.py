@@ -77,6 +77,7 @@ SIGNATURES = {
     "sp_score_spans": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), _P, _P, _P]),
     "sp_align_pairs": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                  C.POINTER(C.c_int64)]),
+    "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "sp_chain_window_scores": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(_P)]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
@@ -238,6 +239,13 @@ class Context:
             out.append({"dist": r.dist, "nm": r.nm, "p_start": r.p_start, "p_end": r.p_end, "t_start": r.t_start,
                         "t_end": r.t_end, "cigar": [(int(x) >> 4, int(x) & 15) for x in c]})
         return out
+
+    def row_topk(self, d: "DMatrix", k: int = 5):
+        """K5: (idx, dist), each [n_targets, k] int32: the k best patterns of every target by (distance, index)."""
+        idx = np.zeros((d.n_targets, k), dtype=np.int32)
+        dist = np.zeros((d.n_targets, k), dtype=np.int32)
+        self._check(self._lib.sp_row_topk(self._h, d._h, k, idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
 
     def chain_window_scores(self, chains, read_weights, n_haps: int) -> "DMatrix":
         """K3 chain windows.  chains: list of lists of haplotype indices; read_weights: per read an array

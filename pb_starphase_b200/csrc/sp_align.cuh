@@ -181,4 +181,40 @@ __global__ void k4_compact_cigar(const AlignRecDev *__restrict__ recs, const uin
     for (int i = threadIdx.x; i < r.n_cigar; i += blockDim.x) out[o + i] = cigar[r.cigar_off + i];
 }
 
+// ------------------------------------------------------------------------------------------
+// K5: the k best patterns of every text (row top-k of the distance matrix), ties by lower pattern index.
+// Stands in for minimap2's best_n hit list at the realigner (src/hla/realigner.rs:116-146): only these candidates
+// go on to the traceback, and only R x k records cross PCIe instead of the R x A matrix.
+// One thread per text; the allele-major layout D[p * ld + t] makes the loads of a warp contiguous.
+// ------------------------------------------------------------------------------------------
+template <typename T, int K>
+__global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long long ld, int nt, int np, int k,
+                                                   int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    uint32_t bd[K], bi[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) { bd[q] = 0xFFFFFFFFu; bi[q] = 0xFFFFFFFFu; }
+    for (int a = 0; a < np; ++a) {
+        const uint32_t v = static_cast<uint32_t>(D[static_cast<long long>(a) * ld + t]);
+        if (v < bd[K - 1]) {  // strict: on ties the earlier pattern stays ahead
+            bd[K - 1] = v; bi[K - 1] = static_cast<uint32_t>(a);
+#pragma unroll
+            for (int q = K - 1; q > 0; --q)
+                if (bd[q] < bd[q - 1]) {
+                    const uint32_t xd = bd[q], xi = bi[q];
+                    bd[q] = bd[q - 1]; bi[q] = bi[q - 1];
+                    bd[q - 1] = xd; bi[q - 1] = xi;
+                }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+        if (q < k) {
+            const bool have = bi[q] != 0xFFFFFFFFu;
+            idx[static_cast<long long>(t) * k + q] = have ? static_cast<int32_t>(bi[q]) : -1;
+            dist[static_cast<long long>(t) * k + q] = have ? static_cast<int32_t>(bd[q]) : -1;
+        }
+}
+
 }  // namespace sp

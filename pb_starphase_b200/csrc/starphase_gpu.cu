@@ -1081,6 +1081,37 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
 }
 
 // ------------------------------------------------------------------------------------------
+// K5: row top-k of a device distance matrix
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!d || !idx || !dist) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: NULL argument");
+    if (k < 1 || k > 16) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: k must be in [1, 16]");
+    if (d->nt > 0x7FFFFFF0ll || d->np > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "sp_row_topk: matrix too large");
+    if (d->nt == 0) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = static_cast<size_t>(d->nt) * static_cast<size_t>(k);
+    void *buf = nullptr;
+    SP_CUDA(ctx, ctx_scratch(ctx, 2 * n * sizeof(int32_t), &buf));
+    int32_t *d_idx = static_cast<int32_t *>(buf), *d_dist = d_idx + n;
+    const int nt = static_cast<int>(d->nt), np = static_cast<int>(d->np);
+    const unsigned grid = static_cast<unsigned>((nt + 127) / 128);
+    if (d->elem_bits == 16) {
+        if (k <= 8) k5_row_topk<uint16_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+        else k5_row_topk<uint16_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+    } else {
+        if (k <= 8) k5_row_topk<int32_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+        else k5_row_topk<int32_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+    }
+    ++ctx->launches;
+    SP_CUDA(ctx, cudaGetLastError());
+    SP_CUDA(ctx, cudaMemcpyAsync(idx, d_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // K3 chain windows
 // ------------------------------------------------------------------------------------------
 extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const int32_t *chain_off,

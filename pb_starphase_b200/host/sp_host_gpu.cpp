@@ -96,6 +96,44 @@ std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const std::vector<int32_t>
     return out;
 }
 
+PatternSet::~PatternSet() { sp_patterns_destroy(p_); }
+DeviceMatrix::~DeviceMatrix() { sp_dmatrix_destroy(d_); }
+
+std::shared_ptr<PatternSet> GpuAligner::prepare_patterns(const SeqList &patterns) {
+    std::shared_ptr<PatternSet> ps(new PatternSet());
+    ps->seqs_ = patterns;
+    Packed p(patterns);
+    check(sp_patterns_create(ctx_, &p.set, SP_INFIX, &ps->p_), "sp_patterns_create");
+    return ps;
+}
+
+std::unique_ptr<DeviceMatrix> GpuAligner::score_device(const SeqList &targets, const PatternSet &patterns) {
+    Packed t(targets);
+    sp_targets *tg = nullptr;
+    check(sp_targets_create(ctx_, &t.set, &tg), "sp_targets_create");
+    std::unique_ptr<DeviceMatrix> m(new DeviceMatrix());
+    const sp_status st = sp_score_device(ctx_, tg, patterns.p_, 16, 0, &m->d_);
+    sp_targets_destroy(tg);
+    check(st, "sp_score_device");
+    m->nt_ = static_cast<int64_t>(targets.size());
+    m->np_ = static_cast<int64_t>(patterns.size());
+    return m;
+}
+
+std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k) {
+    std::vector<sp_pair_rec> out(static_cast<size_t>(std::max(k, 1)));
+    int n = 0;
+    check(sp_pair_minsum_topk(ctx_, d.d_, d2 ? d2->d_ : nullptr, 0, d.np_, k, out.data(), &n), "sp_pair_minsum_topk");
+    out.resize(static_cast<size_t>(n));
+    return out;
+}
+
+void GpuAligner::row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist) {
+    const size_t n = std::max<size_t>(static_cast<size_t>(d.nt_) * static_cast<size_t>(k), 1);
+    idx.assign(n, -1); dist.assign(n, -1);
+    check(sp_row_topk(ctx_, d.d_, k, idx.data(), dist.data()), "sp_row_topk");
+}
+
 std::vector<uint64_t> GpuAligner::chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
                                                   const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps) {
     std::vector<int32_t> coff(1, 0), items, soff(1, 0);

@@ -109,50 +109,48 @@ Json Diplotype::to_json() const {
 // ------------------------------------------------------------------------------------------
 // realigner
 // ------------------------------------------------------------------------------------------
-HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database)
-    : gpu_(gpu), database_(database) {
+HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database) : gpu_(gpu) {
     // create_hla_fasta (src/hla/realigner.rs:497-526): every allele of the listed genes that has a DNA sequence
+    SeqList seqs;
     for (const auto &kv : database) {
         if (std::find(gene_list.begin(), gene_list.end(), kv.second.gene_name) == gene_list.end()) continue;
         if (!kv.second.dna_sequence) continue;
         alleles_.push_back(&kv.second);
-        allele_seqs_.push_back(*kv.second.dna_sequence);
+        seqs.push_back(*kv.second.dna_sequence);
     }
-}
-
-// the best_n hits of one read: the alleles with the smallest distance, ties by database order
-static std::vector<int32_t> top_candidates(const int32_t *row, size_t n_alleles, int n_candidates) {
-    std::vector<int32_t> idx(n_alleles);
-    std::iota(idx.begin(), idx.end(), 0);
-    const size_t k = std::min<size_t>(static_cast<size_t>(std::max(n_candidates, 1)), n_alleles);
-    std::partial_sort(idx.begin(), idx.begin() + static_cast<long>(k), idx.end(),
-                      [&](int32_t a, int32_t b) { return row[a] != row[b] ? row[a] < row[b] : a < b; });
-    idx.resize(k);
-    return idx;
+    index_ = gpu.prepare_patterns(seqs);
 }
 
 std::vector<PgxMappingDetails> HlaRealigner::realign_records(const std::vector<std::pair<std::string, std::string>> &reads, int n_candidates) {
     SeqList targets;
     for (const auto &r : reads) targets.push_back(r.second);
-    const std::vector<int32_t> D = alleles_.empty() ? std::vector<int32_t>() : gpu_.score_batch(targets, allele_seqs_);
-    return realign_records_scored(reads, D, n_candidates);
+    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(targets, *index_);
+    return realign_records_scored(reads, *D, n_candidates);
 }
 
 std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::vector<std::pair<std::string, std::string>> &reads,
-                                                                    const std::vector<int32_t> &D, int n_candidates) {
+                                                                    const DeviceMatrix &D, int n_candidates) {
     SeqList targets;
     for (const auto &r : reads) targets.push_back(r.second);
     const size_t A = alleles_.size();
-    if (D.size() != reads.size() * A) throw HostError("realign_records_scored: distance matrix has the wrong shape");
+    if (D.n_targets() != static_cast<int64_t>(reads.size()) || D.n_patterns() != static_cast<int64_t>(A))
+        throw HostError("realign_records_scored: distance matrix has the wrong shape");
+    // the best_n hits of every read: the alleles with the smallest distance, ties by database order (K5)
+    const int k = std::max(1, std::min(n_candidates, 16));
+    std::vector<int32_t> cand, cand_dist;
+    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist);
     std::vector<std::pair<int32_t, int32_t>> pairs;
     std::vector<size_t> first_pair(reads.size() + 1, 0);
     for (size_t r = 0; r < reads.size(); ++r) {
         first_pair[r] = pairs.size();
         if (A && !reads[r].second.empty())
-            for (int32_t a : top_candidates(D.data() + r * A, A, n_candidates)) pairs.emplace_back(static_cast<int32_t>(r), a);
+            for (int q = 0; q < k; ++q)
+                if (cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)] >= 0)
+                    pairs.emplace_back(static_cast<int32_t>(r), cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)]);
     }
     first_pair[reads.size()] = pairs.size();
-    const std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs_, pairs);
+    const SeqList &allele_seqs = index_->sequences();
+    const std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs, pairs);
 
     std::vector<PgxMappingDetails> out;
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -162,7 +160,7 @@ std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::v
         for (size_t q = first_pair[r]; q < first_pair[r + 1]; ++q) {
             const Alignment &a = alns[q];
             if (a.cigar.empty() || dp_score(a.cigar) < 200) continue;  // no hit reported
-            const size_t target_len = allele_seqs_[static_cast<size_t>(pairs[q].second)].size();  // minimap2's target is the allele here
+            const size_t target_len = allele_seqs[static_cast<size_t>(pairs[q].second)].size();  // minimap2's target is the allele here
             const size_t unmapped = target_len - static_cast<size_t>(a.p_end - a.p_start);
             const MappingStats stats(target_len, static_cast<size_t>(a.nm), unmapped);
             if (stats.mapping_score() <= 0.5 && stats.custom_score(false) <= 0.03 &&
@@ -201,36 +199,44 @@ Json HlaGeneCall::gene_details() const {
     return j;
 }
 
-HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const std::vector<HlaRead> &reads,
-                               const DiplotypeSettings &settings) {
-    std::vector<const HlaAlleleDefinition *> allowed;
+HlaGeneIndex::HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const DiplotypeSettings &settings)
+    : gene_name_(gene_name) {
     for (const auto &kv : database)
         if (is_allowed_allele_def(kv.second, gene_name, settings)) {
-            if (!kv.second.dna_sequence) throw HostError("diplotype_hla_gene: allele " + kv.first + " has no DNA sequence (pair ranking needs hla_require_dna)");
-            allowed.push_back(&kv.second);
+            if (!kv.second.dna_sequence)
+                throw HostError("diplotype_hla_gene: allele " + kv.first + " has no DNA sequence (pair ranking needs hla_require_dna)");
+            gene_db_.emplace(kv.first, kv.second);
         }
+    SeqList cdna;
+    for (const auto &kv : gene_db_) { allowed_.push_back(&kv.second); cdna.push_back(kv.second.cdna_sequence); }
+    realigner_.reset(new HlaRealigner(gpu, {gene_name}, gene_db_));  // DNA index, same allele order
+    if (!settings.disable_cdna_scoring) cdna_ = gpu.prepare_patterns(cdna);
+}
+
+HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRead> &reads, const DiplotypeSettings &settings) {
+    const auto &allowed = index.allowed_;
     HlaGeneCall call;
     if (reads.empty() || allowed.empty()) {  // sentinels of src/hla/caller.rs:32-37
         call.hla_id1 = call.hla_id2 = "NO_READS";
         call.diplotype = {"NO_READS", "NO_READS"};
         return call;
     }
-    SeqList dna_targets, cdna_targets, dna, cdna;
+    SeqList dna_targets, cdna_targets;
     for (const auto &r : reads) { dna_targets.push_back(r.dna_target); cdna_targets.push_back(r.cdna_target); }
-    for (const auto *a : allowed) { dna.push_back(*a->dna_sequence); cdna.push_back(a->cdna_sequence); }
-    const int64_t R = static_cast<int64_t>(reads.size()), A = static_cast<int64_t>(allowed.size());
-    const std::vector<int32_t> Dd = gpu.score_batch(dna_targets, dna);
+    const int64_t R = static_cast<int64_t>(reads.size());
+    const std::unique_ptr<DeviceMatrix> Dd = gpu.score_device(dna_targets, index.realigner_->index());
     std::vector<sp_pair_rec> top;
-    if (settings.disable_cdna_scoring) {
-        top = gpu.pair_minsum_topk(Dd, nullptr, R, A, 10);
+    if (settings.disable_cdna_scoring || !index.cdna_) {
+        top = gpu.pair_minsum_topk(*Dd, nullptr, 10);
     } else {
-        const std::vector<int32_t> Dc = gpu.score_batch(cdna_targets, cdna);
-        top = gpu.pair_minsum_topk(Dc, &Dd, R, A, 10);  // (cDNA, DNA) lexicographic: src/hla/mapping.rs:111-117
+        const std::unique_ptr<DeviceMatrix> Dc = gpu.score_device(cdna_targets, *index.cdna_);
+        top = gpu.pair_minsum_topk(*Dc, Dd.get(), 10);  // (cDNA, DNA) lexicographic: src/hla/mapping.rs:111-117
     }
     if (top.empty()) throw HostError("diplotype_hla_gene: pair ranking returned nothing");
+    const bool dual = !(settings.disable_cdna_scoring || !index.cdna_);
     const sp_pair_rec &b = top[0];
-    call.pair_score_cdna = settings.disable_cdna_scoring ? 0 : b.score;
-    call.pair_score_dna = settings.disable_cdna_scoring ? b.score : b.score2;
+    call.pair_score_cdna = dual ? b.score : 0;
+    call.pair_score_dna = dual ? b.score2 : b.score;
     call.counts1 = b.c1;
     call.counts2 = static_cast<size_t>(R) - b.c1;
     const std::string id1 = allowed[b.i]->hla_id, id2 = allowed[b.j]->hla_id;
@@ -243,17 +249,20 @@ HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, con
     } else {
         call.hla_id1 = call.hla_id2 = id2;
     }
-    auto star = [&](const std::string &id) { return "*" + join_star(database.at(id).star_allele); };  // :1046-1065
+    auto star = [&](const std::string &id) { return "*" + join_star(index.gene_db_.at(id).star_allele); };  // :1046-1065
     call.diplotype = {star(call.hla_id1), star(call.hla_id2)};
-
-    // per-read database assignment, as HlaRealigner::realign_record reports it (restricted to this gene)
-    HlaDatabase gene_db;
-    for (const auto *a : allowed) gene_db.emplace(a->hla_id, *a);
-    HlaRealigner realigner(gpu, {gene_name}, gene_db);
+    // per-read database assignment, as HlaRealigner::realign_record reports it (restricted to this gene): the DNA
+    // distances are already on the device
     std::vector<std::pair<std::string, std::string>> qs;
     for (const auto &r : reads) qs.emplace_back(r.qname, r.dna_target);
-    call.mapping_details = realigner.realign_records_scored(qs, Dd);  // same allele order: reuse the DNA distances
+    call.mapping_details = index.realigner_->realign_records_scored(qs, *Dd);
     return call;
+}
+
+HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const std::vector<HlaRead> &reads,
+                               const DiplotypeSettings &settings) {
+    HlaGeneIndex index(gpu, database, gene_name, settings);
+    return diplotype_hla_gene(gpu, index, reads, settings);
 }
 
 }  // namespace starphase

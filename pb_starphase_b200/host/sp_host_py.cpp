@@ -153,6 +153,24 @@ PYBIND11_MODULE(_starphase_host, m) {
         return d;
     });
 
+    py::class_<HlaGeneIndex>(m, "HlaGeneIndex")
+        .def(py::init([](GpuAligner &g, const DbRows &rows, const std::string &gene, const DiplotypeSettings &s) {
+                 return new HlaGeneIndex(g, make_db(rows), gene, s);
+             }), py::keep_alive<1, 2>())
+        .def("n_alleles", &HlaGeneIndex::n_alleles)
+        .def("gene_name", &HlaGeneIndex::gene_name);
+    m.def("diplotype_hla_gene_indexed", [](GpuAligner &g, HlaGeneIndex &index,
+                                           const std::vector<std::tuple<std::string, std::string, std::string>> &reads, const DiplotypeSettings &s) {
+        std::vector<HlaRead> rs;
+        for (const auto &r : reads) rs.push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r)});
+        const HlaGeneCall c = diplotype_hla_gene(g, index, rs, s);
+        py::dict d;
+        d["hla_id1"] = c.hla_id1; d["hla_id2"] = c.hla_id2; d["counts1"] = c.counts1; d["counts2"] = c.counts2;
+        d["pair_score_cdna"] = c.pair_score_cdna; d["pair_score_dna"] = c.pair_score_dna;
+        d["gene_details"] = c.gene_details();
+        return d;
+    });
+
     // ---- CYP2D6 ----
     using RegionRows = std::vector<std::tuple<std::string, std::optional<std::string>, std::optional<size_t>>>;
     m.def("label_ops", [](const std::string &type, const std::optional<std::string> &sub, const std::string &type2,

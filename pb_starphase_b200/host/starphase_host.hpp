@@ -20,6 +20,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <optional>
 #include <set>
 #include <stdexcept>
@@ -145,6 +146,41 @@ struct Alignment {  // sp_align_rec + its CIGAR
     std::vector<std::pair<uint32_t, uint8_t>> cigar;
 };
 
+class GpuAligner;
+
+// device-resident packed pattern set (sp_patterns): the allele database of a gene, built once like HlaRealigner::new builds
+// its index once (src/hla/realigner.rs:42-91)
+class PatternSet {
+  public:
+    ~PatternSet();
+    PatternSet(const PatternSet &) = delete;
+    PatternSet &operator=(const PatternSet &) = delete;
+    size_t size() const { return seqs_.size(); }
+    const SeqList &sequences() const { return seqs_; }
+
+  private:
+    friend class GpuAligner;
+    PatternSet() = default;
+    sp_patterns *p_ = nullptr;
+    SeqList seqs_;
+};
+
+// device-resident distance matrix (sp_dmatrix, u16): stays in HBM between K1, K2 and K5
+class DeviceMatrix {
+  public:
+    ~DeviceMatrix();
+    DeviceMatrix(const DeviceMatrix &) = delete;
+    DeviceMatrix &operator=(const DeviceMatrix &) = delete;
+    int64_t n_targets() const { return nt_; }
+    int64_t n_patterns() const { return np_; }
+
+  private:
+    friend class GpuAligner;
+    DeviceMatrix() = default;
+    sp_dmatrix *d_ = nullptr;
+    int64_t nt_ = 0, np_ = 0;
+};
+
 class GpuAligner {
   public:
     explicit GpuAligner(int device = 0);
@@ -159,6 +195,11 @@ class GpuAligner {
                                        const std::vector<std::pair<int32_t, int32_t>> &pairs);
     std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
                                               int k);
+    // resident path: nothing of size reads x alleles crosses PCIe
+    std::shared_ptr<PatternSet> prepare_patterns(const SeqList &patterns);
+    std::unique_ptr<DeviceMatrix> score_device(const SeqList &targets, const PatternSet &patterns);          // K1
+    std::vector<sp_pair_rec> pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k);           // K2
+    void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist);      // K5
     // S[i * n_chains + j], j >= i: sum over reads of min(B[i][r], B[j][r]) for the chain-window matrix B
     std::vector<uint64_t> chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
                                           const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps);
@@ -213,20 +254,22 @@ struct PgxMappingDetails {  // src/data_types/starphase_json.rs:271-283
 
 class HlaRealigner {  // src/hla/realigner.rs:22-211 (database side only: the allele index and the acceptance loop)
   public:
+    // builds the resident allele index once: every allele of the listed genes that has a DNA sequence (create_hla_fasta, :497-526)
     HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database);
-    // one PgxMappingDetails per read, in input order; n_candidates plays the role of minimap2's best_n = 5
+    // one PgxMappingDetails per read, in input order; n_candidates plays the role of minimap2's best_n = 5.
+    // K1 over the index (matrix stays on the device), K5 candidate lists, K4 traceback of the candidates.
     std::vector<PgxMappingDetails> realign_records(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
                                                    int n_candidates = 5);
-    // same, with the read x allele distances (row-major, alleles in the index order) already computed by K1
+    // same, on a distance matrix K1 already produced for these reads against this index
     std::vector<PgxMappingDetails> realign_records_scored(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
-                                                          const std::vector<int32_t> &D, int n_candidates = 5);
+                                                          const DeviceMatrix &D, int n_candidates = 5);
     size_t n_alleles() const { return alleles_.size(); }
+    const PatternSet &index() const { return *index_; }
 
   private:
     GpuAligner &gpu_;
-    const HlaDatabase &database_;
     std::vector<const HlaAlleleDefinition *> alleles_;
-    SeqList allele_seqs_;
+    std::shared_ptr<PatternSet> index_;
 };
 
 struct HlaRead {
@@ -244,8 +287,26 @@ struct HlaGeneCall {
     std::vector<PgxMappingDetails> mapping_details;
     Json gene_details() const;  // PgxGeneDetails::new_from_mappings, src/data_types/starphase_json.rs:147-161
 };
+// One gene's resident database: the allowed alleles in BTreeMap order with their DNA / cDNA pattern sets on the device
+// and the realigner over the same DNA index.  Built once per database, reused for every sample of a cohort.
+class HlaGeneIndex {
+  public:
+    HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const DiplotypeSettings &settings);
+    const std::string &gene_name() const { return gene_name_; }
+    size_t n_alleles() const { return allowed_.size(); }
+
+  private:
+    friend HlaGeneCall diplotype_hla_gene(GpuAligner &, HlaGeneIndex &, const std::vector<HlaRead> &, const DiplotypeSettings &);
+    std::string gene_name_;
+    HlaDatabase gene_db_;  // owns the allele definitions the realigner points to
+    std::vector<const HlaAlleleDefinition *> allowed_;
+    std::shared_ptr<PatternSet> cdna_;
+    std::unique_ptr<HlaRealigner> realigner_;  // holds the DNA pattern set
+};
 // north_star (2): exhaustive read x allele scoring, allele-pair min-sum ranking with the (cDNA, DNA) key, then the
 // reference's het/hom decision (src/hla/caller.rs:889-901) and diplotype strings (:1046-1065)
+HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRead> &reads, const DiplotypeSettings &settings);
+// convenience: builds the index for this one call
 HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name,
                                const std::vector<HlaRead> &reads, const DiplotypeSettings &settings);
 
