@@ -259,6 +259,68 @@ def run_cohort(ctx, w, n_samples, rank, world):
     return dt, n_samples, cells
 
 
+def run_cohort_host(w, n_samples, rank, world, local_rank):
+    """The same cohort through the C++ host above the C ABI (pb_starphase_b200/host): per sample the complete calls a
+    pb-StarPhase run makes on this path -- HLA-A and HLA-B diplotypes (K1 DNA + cDNA against the resident allele sets, K2 pair
+    ranking, het/hom decision, per-read database assignment via K5 + K4), CYP2D6 (39-template search over the reads with K4
+    tracebacks, weight_sequence spans, chains, find_best_chain_pair) -- ending in the result JSON text of that sample.
+    Returns (seconds, samples, bytes of JSON, one sample's diplotypes)."""
+    from pb_starphase_b200 import _starphase_host as host
+    from pb_starphase_b200 import synth
+
+    gpu = host.GpuAligner(local_rank)
+    settings = host.DiplotypeSettings()
+    genes = list(w["gene_views"].items())
+    rows = []
+    for g, (gene, (drow, crow, na, _, _)) in enumerate(genes):
+        for a in range(na):
+            rows.append((f"HLA:HLA{g * 100000 + a:06d}", gene, [f"{1 + a // 400:02d}", f"{1 + (a // 20) % 20:02d}", f"{1 + a % 20:02d}", "01"],
+                         w["dna"][drow + a].decode(), w["cdna"][crow + a].decode()))
+    index = {gene: host.HlaGeneIndex(gpu, [r for r in rows if r[1] == gene], gene, settings) for gene, _ in genes}
+    per_gene = 64
+    meta = dict(pbstarphase_version="2.0.1", cpic_version="synthetic", hla_version="synthetic", pharmvar_version="synthetic", build_time="n/a")
+
+    dbg = os.environ.get("SP_COHORT_DEBUG") == "1"
+
+    def one_sample(sid, cyp):
+        details, marks = {}, [("start", time.perf_counter())]
+        for gene, (_, _, _, col0, nr) in genes:
+            lo = col0 + (sid * per_gene) % max(nr - per_gene, 1)
+            reads = [(f"s{sid}/{gene}/{k}", w["reads"][lo + k].decode(), w["ctargets"][lo + k].decode()) for k in range(per_gene)]
+            details[gene] = host.diplotype_hla_gene_indexed(gpu, index[gene], reads, settings)["gene_details"]
+            marks.append((gene, time.perf_counter()))
+        hits = host.find_base_type_in_sequences(gpu, cyp["templates"], cyp["reads"], False, 0.5)
+        marks.append(("cyp_template_search", time.perf_counter()))
+        call = host.call_cyp2d6_chains(gpu, cyp["consensuses"], cyp["regions"], cyp["roi"], False, True)
+        marks.append(("cyp_chains", time.perf_counter()))
+        details["CYP2D6"] = call["gene_details"]
+        text = host.starphase_json("2.0.1", meta, details)
+        marks.append(("json", time.perf_counter()))
+        if dbg:
+            print("cohort_host rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+        return text, sum(len(h) for h in hits)
+
+    def cyp_inputs(sid):
+        c = synth.cyp2d6_diploid_sample(2000 + sid)
+        return dict(templates=[(t, s, q.decode()) for (t, s), q in zip(c["template_labels"], c["templates"])],
+                    reads=[r.decode() for r in c["reads"]], consensuses=[x.decode() for x in c["consensuses"]], regions=c["regions"],
+                    roi={q: [(a, b, seq.decode()) for a, b, seq in regs] for q, regs in c["roi"].items()})
+
+    sids = [rank + world * k for k in range(n_samples)]
+    inputs = {sid: cyp_inputs(sid) for sid in sids}
+    for k in range(2):
+        one_sample(sids[k % len(sids)], inputs[sids[k % len(sids)]])
+    t0 = time.perf_counter()
+    nbytes, text, n_hits = 0, "", 0
+    for sid in sids:
+        text, n_hits = one_sample(sid, inputs[sid])
+        nbytes += len(text)
+    dt = time.perf_counter() - t0
+    doc = json.loads(text)
+    calls = {g: d["diplotypes"][0]["diplotype"] for g, d in doc["gene_details"].items()}
+    return dt, n_samples, nbytes, dict(calls=calls, cyp2d6_template_hits=n_hits, kernel_launches=int(gpu.launch_count()))
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -397,11 +459,23 @@ def run_ours(args):
         cohort_s, cohort_n, cohort_cells = run_cohort(ctx, w, args.cohort_samples, rank, world)
         barrier()
 
+    host_s, host_n, host_bytes, host_info = 0.0, 0, 0, None
+    if args.cohort_samples > 0:
+        barrier()
+        try:
+            host_s, host_n, host_bytes, host_info = run_cohort_host(w, max(2, args.cohort_samples // 2), rank, world, local_rank)
+        except Exception as e:  # the contract line must not depend on this leg
+            host_info = dict(error=f"{type(e).__name__}: {e}")
+        barrier()
+
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s, k1_avg_ms, cohort_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, e2e_s, k1_avg_ms, cohort_s, host_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, k1_avg_ms, cohort_s = (float(x) for x in t.cpu())
+        ms_total, e2e_s, k1_avg_ms, cohort_s, host_s = (float(x) for x in t.cpu())
+        hn = torch.tensor([host_n], dtype=torch.int64, device=dev)
+        dist.all_reduce(hn)
+        host_n = int(hn.item())
         ct = torch.tensor([cohort_n, cohort_cells], dtype=torch.int64, device=dev)
         dist.all_reduce(ct)
         cohort_n, cohort_cells = (int(x) for x in ct.cpu())
@@ -441,6 +515,12 @@ def run_ours(args):
                                 "CYP2D6: 256 reads x 39 templates, ~650 segments x 24 consensuses with spans, 200 chains (chain windows + pair "
                                 "top-10); host buffers in, calls out (BASELINE configs[4], SURVEY 8d.5)")
                     if cohort_n else None),
+            cohort_host=(dict(samples_per_s=host_n / host_s, samples=host_n, ms_per_sample_per_gpu=host_s / (host_n / world) * 1e3,
+                              json_bytes_per_sample=host_bytes // max(host_n // world, 1), **host_info,
+                              sample="the same per-sample work through the C++ host (pb_starphase_b200/host): HLA-A + HLA-B diplotype calls "
+                                     "(K1 x2, K2, het/hom, K5 + K4 read assignment), CYP2D6 39-template search with K4 tracebacks + "
+                                     "weight_sequence + chains + find_best_chain_pair on a diploid 96-read case, result JSON text out")
+                         if host_n and host_s > 0 else host_info),
             roofline=dict(bound="int_alu", kernel="k1_infix (DNA launches, all lane-width classes)", achieved=achieved / 1e12,
                           peak=int_peak2 / 1e12, unit="Tops/s (algorithmic INT32 lane-ops, 23/64 per cell, SURVEY 8d)",
                           frac=achieved / int_peak2,

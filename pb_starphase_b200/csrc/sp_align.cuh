@@ -11,10 +11,11 @@
 //   pass 2  the same recurrence over the text window [e - (m + d), e) -- every optimal placement ending at
 //           e lies inside it -- keeping per column the vertical deltas (~Pv, Mv are the state anyway; only
 //           ~Pv is needed) and Hyyro's diagonal-zero vector D0 in HBM scratch
-//   pass 3  lane 0 walks back from (m, e): diagonal when it explains the cell ('=' or 'X'), else up ('I',
+//   pass 3  the warp walks back from (m, e): diagonal when it explains the cell ('=' or 'X'), else up ('I',
 //           a pattern base without a text base), else left ('D').  Taking the diagonal first while walking
-//           backwards left-aligns gaps, the convention of minimap2's ksw2.  Leading / trailing 'I' runs are
-//           the clipped pattern ends (query_start, query_len - query_end).
+//           backwards left-aligns gaps, the convention of minimap2's ksw2.  Lane k inspects the k-th cell down
+//           the diagonal, so a run of up to 32 diagonal steps costs one round of (L2-latency-bound) loads.
+//           Leading / trailing 'I' runs are the clipped pattern ends (query_start, query_len - query_end).
 // The CIGAR is run-length encoded BAM style, (len << 4) | op with op 1 = I, 2 = D, 7 = '=', 8 = X.
 #pragma once
 #include "sp_kernels.cuh"
@@ -132,42 +133,62 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
         k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) {
+        {
+            // pass 3, warp-cooperative: lane k looks at the diagonal cell (i - k, j - k); the leading run of cells the
+            // diagonal explains is taken in one round (HiFi-like pairs are long '=' runs), anything else is one step.
+            // (i, j, cur_op, cur_len, pos) are computed from ballots only, so they stay uniform across the warp.
             const long long cig_end = p.cig_off[q + 1];
             long long pos = cig_end;
             uint32_t cur_op = 0, cur_len = 0;
             int i = m_all, j = ncols;
+            auto emit = [&](uint32_t op, uint32_t n) {
+                if (op == cur_op) { cur_len += n; return; }
+                if (cur_len) { --pos; if (lane == 0) p.cigar[pos] = (cur_len << 4) | cur_op; }
+                cur_op = op; cur_len = n;
+            };
             while (i > 0) {
-                uint32_t op;
-                if (j == 0) {
-                    op = CIG_I; --i;
-                } else {
-                    const int rr = i - 1 + pad, w = rr >> 5, b = rr & 31;
-                    const uint32_t *colp = scr + static_cast<size_t>(j - 1) * 2 * Wp + (w - wf4);
+                if (j == 0) { emit(CIG_I, static_cast<uint32_t>(i)); i = 0; break; }
+                const int ci = i - lane, cj = j - lane;
+                bool diag_ok = false, is_eq = false, pv = false;
+                if (ci >= 1 && cj >= 1) {
+                    const int rr = ci - 1 + pad, w = rr >> 5, b = rr & 31;
+                    const uint32_t *colp = scr + static_cast<size_t>(cj - 1) * 2 * Wp + (w - wf4);
                     const uint32_t d0w = __ldcg(colp), npvw = __ldcg(colp + Wp);
-                    const uint32_t code = base_code(T[w0 + j - 1]);
-                    const int wl = w / U, wu = w % U;
-                    const bool match = code < 4 && ((blob[code * 32 * U + row_word(U, wl, wu)] >> b) & 1u);
-                    const bool d0b = (d0w >> b) & 1u;
-                    if (match || !d0b) { op = match ? CIG_EQ : CIG_X; --i; --j; }  // the diagonal explains the cell
-                    else if (!((npvw >> b) & 1u)) { op = CIG_I; --i; }             // vertical delta +1
-                    else { op = CIG_D; --j; }
+                    const uint32_t code = base_code(T[w0 + cj - 1]);
+                    is_eq = code < 4 && ((blob[code * 32 * U + row_word(U, w / U, w % U)] >> b) & 1u);
+                    diag_ok = is_eq || !((d0w >> b) & 1u);  // the diagonal explains the cell ('=' or a substitution)
+                    pv = !((npvw >> b) & 1u);                // vertical delta +1: the cell above explains it ('I')
                 }
-                if (op == cur_op) ++cur_len;
-                else {
-                    if (cur_len) p.cigar[--pos] = (cur_len << 4) | cur_op;
-                    cur_op = op; cur_len = 1;
+                const uint32_t ok_mask = __ballot_sync(0xffffffffu, diag_ok);
+                const uint32_t eq_mask = __ballot_sync(0xffffffffu, is_eq);
+                const bool pv0 = __shfl_sync(0xffffffffu, pv ? 1 : 0, 0) != 0;
+                const int n_diag = ok_mask == 0xffffffffu ? 32 : __ffs(~ok_mask) - 1;
+                if (n_diag == 0) {
+                    if (pv0) { emit(CIG_I, 1); --i; } else { emit(CIG_D, 1); --j; }
+                    continue;
                 }
+                int done = 0;
+                while (done < n_diag) {  // runs of '=' / 'X' among the first n_diag lanes, in walk order
+                    const bool eq = (eq_mask >> done) & 1u;
+                    const uint32_t rest = (eq ? ~eq_mask : eq_mask) >> done;  // first lane of the other kind
+                    int run = rest ? __ffs(rest) - 1 : 32;
+                    run = min(run, n_diag - done);
+                    emit(eq ? CIG_EQ : CIG_X, static_cast<uint32_t>(run));
+                    done += run;
+                }
+                i -= n_diag; j -= n_diag;
             }
-            if (cur_len) p.cigar[--pos] = (cur_len << 4) | cur_op;
-            int ncig = static_cast<int>(cig_end - pos), clip_s = 0, clip_e = 0;
-            if (ncig > 0 && (p.cigar[pos] & 15u) == CIG_I) { clip_s = static_cast<int>(p.cigar[pos] >> 4); ++pos; --ncig; }
-            if (ncig > 0 && (p.cigar[cig_end - 1] & 15u) == CIG_I) { clip_e = static_cast<int>(p.cigar[cig_end - 1] >> 4); --ncig; }
-            rec.dist = d; rec.nm = d - clip_s - clip_e;
-            rec.p_start = clip_s; rec.p_end = m_all - clip_e;
-            rec.t_start = w0 + j; rec.t_end = e;
-            rec.n_cigar = ncig; rec.cigar_off = pos;
-            p.recs[q] = rec;
+            if (cur_len) { --pos; if (lane == 0) p.cigar[pos] = (cur_len << 4) | cur_op; }
+            if (lane == 0) {
+                int ncig = static_cast<int>(cig_end - pos), clip_s = 0, clip_e = 0;
+                if (ncig > 0 && (p.cigar[pos] & 15u) == CIG_I) { clip_s = static_cast<int>(p.cigar[pos] >> 4); ++pos; --ncig; }
+                if (ncig > 0 && (p.cigar[cig_end - 1] & 15u) == CIG_I) { clip_e = static_cast<int>(p.cigar[cig_end - 1] >> 4); --ncig; }
+                rec.dist = d; rec.nm = d - clip_s - clip_e;
+                rec.p_start = clip_s; rec.p_end = m_all - clip_e;
+                rec.t_start = w0 + j; rec.t_end = e;
+                rec.n_cigar = ncig; rec.cigar_off = pos;
+                p.recs[q] = rec;
+            }
         }
         __syncwarp();
     }

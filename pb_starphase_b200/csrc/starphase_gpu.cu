@@ -29,22 +29,43 @@ struct sp_ctx {
     cudaEvent_t ev[5][2] = {};
     bool ev_valid[5] = {false, false, false, false, false};
     uint64_t launches = 0;
-    void *scratch = nullptr;  // grow-only device staging buffer (transposed result rows), reused across calls
-    size_t scratch_bytes = 0;
+    // grow-only device buffers reused across calls (cudaMalloc / cudaFree of large blocks cost up to a second each):
+    // pool 0 = staging (transposed result rows, K5 lists, K4 traceback scratch), 1 = K4 CIGAR regions, 2 = K4 blobs, 3 = K4 dense CIGAR
+    void *pool[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pool_bytes[4] = {0, 0, 0, 0};
 };
 
 // stream-ordered reuse is safe: every user synchronises the context stream before it returns
-static cudaError_t ctx_scratch(sp_ctx *ctx, size_t bytes, void **out) {
-    if (bytes > ctx->scratch_bytes) {
+static cudaError_t ctx_pool(sp_ctx *ctx, int which, size_t bytes, void **out) {
+    if (bytes > ctx->pool_bytes[which]) {
         cudaStreamSynchronize(ctx->stream);
-        cudaFree(ctx->scratch);
-        ctx->scratch = nullptr; ctx->scratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&ctx->scratch, bytes);
-        if (e != cudaSuccess) return e;
-        ctx->scratch_bytes = bytes;
+        cudaFree(ctx->pool[which]);
+        ctx->pool[which] = nullptr; ctx->pool_bytes[which] = 0;
+        const size_t want = bytes + bytes / 4;  // head-room: sizes creep up from call to call
+        cudaError_t e = cudaMalloc(&ctx->pool[which], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&ctx->pool[which], bytes);
+            if (e != cudaSuccess) return e;
+            ctx->pool_bytes[which] = bytes;
+        } else {
+            ctx->pool_bytes[which] = want;
+        }
     }
-    *out = ctx->scratch;
+    *out = ctx->pool[which];
     return cudaSuccess;
+}
+static cudaError_t ctx_scratch(sp_ctx *ctx, size_t bytes, void **out) { return ctx_pool(ctx, 0, bytes, out); }
+
+// Every other device buffer is stream-ordered (cudaMallocAsync / cudaFreeAsync on the context stream, the device's
+// default memory pool with its release threshold lifted in sp_ctx_create): plain cudaFree synchronises the device and
+// was measured at up to 450 ms per call next to multi-GB allocations.
+template <typename T>
+static cudaError_t dev_malloc(sp_ctx *ctx, T **p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes, ctx->stream);
+}
+static void dev_free(sp_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
 }
 
 static thread_local std::string g_create_err;
@@ -153,6 +174,12 @@ extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
     }
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
+    cudaMemPool_t mempool = nullptr;  // keep freed blocks in the pool instead of returning them to the OS at every sync
+    if (cudaDeviceGetDefaultMemPool(&mempool, device) == cudaSuccess) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(mempool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
     *out = ctx;
     return SP_OK;
 }
@@ -164,7 +191,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    cudaFree(ctx->scratch);
+    for (void *p : ctx->pool) cudaFree(p);
     delete ctx;
 }
 
@@ -206,8 +233,8 @@ static sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_base
     const int64_t nbytes = s->n ? s->offsets[s->n] - base0 : 0;
     std::vector<long long> offs(static_cast<size_t>(s->n) + 1);
     for (int64_t i = 0; i <= s->n; ++i) offs[static_cast<size_t>(i)] = s->n ? s->offsets[i] - base0 : 0;
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(d_bases), static_cast<size_t>(std::max<int64_t>(nbytes, 16))));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(d_offs), offs.size() * sizeof(long long)));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(d_bases), static_cast<size_t>(std::max<int64_t>(nbytes, 16))));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(d_offs), offs.size() * sizeof(long long)));
     if (nbytes)
         SP_CUDA(ctx, cudaMemcpyAsync(*d_bases, s->bases + base0, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice,
                                      ctx->stream));
@@ -410,10 +437,10 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
     uint8_t *d_bases = nullptr; long long *d_offs = nullptr;
     int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr; uint32_t *d_lane_info1 = nullptr;
     auto free_tabs = [&]() {
-        cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
+        dev_free(ctx, d_lane_pat); dev_free(ctx, d_lane_row0); dev_free(ctx, d_lane_info1);
         d_lane_pat = d_lane_row0 = nullptr; d_lane_info1 = nullptr;
     };
-    auto cleanup = [&]() { cudaFree(d_bases); cudaFree(d_offs); free_tabs(); };
+    auto cleanup = [&]() { dev_free(ctx, d_bases); dev_free(ctx, d_offs); free_tabs(); };
 #define SP_TRY(x)                                   \
     do {                                            \
         sp_status s__ = (x);                        \
@@ -438,10 +465,10 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
         plan.lane_pat.resize(tab, -1);
         plan.lane_row0.resize(tab, 0);
         plan.lane_info1.resize(tab, INFO_FIRST);
-        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc lane_pat"));
-        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc lane_row0"));
-        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc lane_info1"));
-        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&pc.d_blobs), static_cast<size_t>(pc.n_bins) * blob_words(U) * 4),
+        SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc lane_pat"));
+        SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc lane_row0"));
+        SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc lane_info1"));
+        SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&pc.d_blobs), static_cast<size_t>(pc.n_bins) * blob_words(U) * 4),
                   "cudaMalloc blobs"));
         p->classes.push_back(pc);  // owned by p from here on
         SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, plan.lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
@@ -468,7 +495,7 @@ extern "C" sp_status sp_patterns_create(sp_ctx *ctx, const sp_seqset *patterns, 
 extern "C" void sp_patterns_destroy(sp_patterns *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    for (auto &c : p->classes) cudaFree(c.d_blobs);
+    for (auto &c : p->classes) dev_free(p->ctx, c.d_blobs);
     delete p;
 }
 extern "C" int64_t sp_patterns_count(const sp_patterns *p) { return p ? p->n : 0; }
@@ -508,9 +535,9 @@ extern "C" void sp_targets_destroy(sp_targets *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     for (auto &kv : t->packs) {
-        cudaFree(kv.second.d_text); cudaFree(kv.second.d_tile_off); cudaFree(kv.second.d_tile_text0);
+        dev_free(t->ctx, kv.second.d_text); dev_free(t->ctx, kv.second.d_tile_off); dev_free(t->ctx, kv.second.d_tile_text0);
     }
-    cudaFree(t->d_bases); cudaFree(t->d_offs);
+    dev_free(t->ctx, t->d_bases); dev_free(t->ctx, t->d_offs);
     delete t;
 }
 extern "C" int64_t sp_targets_count(const sp_targets *t) { return t ? t->n : 0; }
@@ -539,11 +566,11 @@ static sp_status get_text_pack(sp_ctx *ctx, sp_targets *t, int tc, const TextPac
     TextPack pk;
     pk.tc = tc; pk.n_tiles = static_cast<int>(tile_text0.size()); pk.total_chunks = cur;
     int32_t *d_chunk0 = nullptr, *d_nch = nullptr;
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_text), static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_tile_off), tile_off.size() * 4));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&pk.d_tile_text0), std::max<size_t>(tile_text0.size(), 1) * 4));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_chunk0), std::max<size_t>(text_chunk0.size(), 1) * 4));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_nch), std::max<size_t>(t->nch.size(), 1) * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_text), static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_off), tile_off.size() * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_text0), std::max<size_t>(tile_text0.size(), 1) * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_chunk0), std::max<size_t>(text_chunk0.size(), 1) * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_nch), std::max<size_t>(t->nch.size(), 1) * 4));
     SP_CUDA(ctx, cudaMemsetAsync(pk.d_text, 0x04, static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8, ctx->stream));
     SP_CUDA(ctx, cudaMemcpyAsync(pk.d_tile_off, tile_off.data(), tile_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (!tile_text0.empty())
@@ -562,7 +589,7 @@ static sp_status get_text_pack(sp_ctx *ctx, sp_targets *t, int tc, const TextPac
         SP_CUDA(ctx, cudaGetLastError());
     }
     SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
-    cudaFree(d_chunk0); cudaFree(d_nch);
+    dev_free(ctx, d_chunk0); dev_free(ctx, d_nch);
     auto ins = t->packs.emplace(tc, pk);
     *out = &ins.first->second;
     return SP_OK;
@@ -657,10 +684,10 @@ extern "C" sp_status sp_score_device(sp_ctx *ctx, const sp_targets *t_in, const 
     d->ctx = ctx; d->nt = t->n; d->np = p->n; d->elem_bits = elem_bits;
     d->ld = (t->n + 63) / 64 * 64;
     const size_t elems = static_cast<size_t>(std::max<int64_t>(d->np * d->ld, 1));
-    cudaError_t e = cudaMalloc(&d->d, elems * (elem_bits / 8));
+    cudaError_t e = dev_malloc(ctx, &d->d, elems * (elem_bits / 8));
     if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, elems * (elem_bits / 8), ctx->stream);
     if (e == cudaSuccess && want_end_col) {
-        e = cudaMalloc(reinterpret_cast<void **>(&d->d_end), elems * 4);
+        e = dev_malloc(ctx, reinterpret_cast<void **>(&d->d_end), elems * 4);
         if (e == cudaSuccess) e = cudaMemsetAsync(d->d_end, 0, elems * 4, ctx->stream);
     }
     if (e != cudaSuccess) {
@@ -692,8 +719,8 @@ extern "C" void sp_dmatrix_destroy(sp_dmatrix *d) {
     if (d->owned) {
         cudaSetDevice(d->ctx->device);
         cudaStreamSynchronize(d->ctx->stream);
-        cudaFree(d->d);
-        cudaFree(d->d_end);
+        dev_free(d->ctx, d->d);
+        dev_free(d->ctx, d->d_end);
     }
     delete d;
 }
@@ -808,8 +835,8 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
     int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_S = nullptr;
     uint32_t *d_lane_info1 = nullptr, *d_blobs = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_bases); cudaFree(d_offs); cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_lane_info1);
-        cudaFree(d_blobs); cudaFree(d_S);
+        dev_free(ctx, d_bases); dev_free(ctx, d_offs); dev_free(ctx, d_lane_pat); dev_free(ctx, d_lane_row0); dev_free(ctx, d_lane_info1);
+        dev_free(ctx, d_blobs); dev_free(ctx, d_S);
         sp_dmatrix_destroy(d); sp_targets_destroy(t); sp_patterns_destroy(p);
     };
     // forward pass: distances and the smallest end column of a best placement
@@ -845,11 +872,11 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
         }
     }
     SP_TRY(upload_seqset(ctx, patterns, &d_bases, &d_offs));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(SPAN_U) * 4), "cudaMalloc span blobs"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_S), static_cast<size_t>(np * d->ld) * 4), "cudaMalloc span starts"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(SPAN_U) * 4), "cudaMalloc span blobs"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_S), static_cast<size_t>(np * d->ld) * 4), "cudaMalloc span starts"));
     SP_TRY(cu(cudaMemsetAsync(d_S, 0, static_cast<size_t>(np * d->ld) * 4, ctx->stream), "memset"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
@@ -978,9 +1005,9 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     uint32_t *d_lane_info1 = nullptr, *d_blobs = nullptr, *d_cigar = nullptr, *d_scratch = nullptr, *d_dense = nullptr;
     AlignRecDev *d_recs = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_tb); cudaFree(d_pb); cudaFree(d_to); cudaFree(d_po); cudaFree(d_cig_off); cudaFree(d_out_off);
-        cudaFree(d_lane_pat); cudaFree(d_lane_row0); cudaFree(d_pt); cudaFree(d_pp); cudaFree(d_lane_info1);
-        cudaFree(d_blobs); cudaFree(d_cigar); cudaFree(d_dense); cudaFree(d_recs);  // d_scratch belongs to the context
+        dev_free(ctx, d_tb); dev_free(ctx, d_pb); dev_free(ctx, d_to); dev_free(ctx, d_po); dev_free(ctx, d_cig_off); dev_free(ctx, d_out_off);
+        dev_free(ctx, d_lane_pat); dev_free(ctx, d_lane_row0); dev_free(ctx, d_pt); dev_free(ctx, d_pp); dev_free(ctx, d_lane_info1);
+        dev_free(ctx, d_recs);  // d_scratch, d_cigar, d_blobs and d_dense live in the context's pools
     };
     auto cu = [&](cudaError_t e, const char *what) -> sp_status {
         if (e != cudaSuccess)
@@ -994,7 +1021,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         if (s__ != SP_OK) { cleanup(); return s__; } \
     } while (0)
     auto up = [&](void **dst, const void *src, size_t bytes) -> sp_status {
-        sp_status s = cu(cudaMalloc(dst, std::max<size_t>(bytes, 16)), "cudaMalloc");
+        sp_status s = cu(dev_malloc(ctx, dst, std::max<size_t>(bytes, 16)), "cudaMalloc");
         if (s == SP_OK && bytes) s = cu(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
         return s;
     };
@@ -1020,9 +1047,9 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     SP_TRY(up(reinterpret_cast<void **>(&d_pt), pt.data(), pt.size() * 4));
     SP_TRY(up(reinterpret_cast<void **>(&d_pp), pp.data(), pp.size() * 4));
     SP_TRY(up(reinterpret_cast<void **>(&d_cig_off), cig_off.data(), cig_off.size() * sizeof(long long)));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(ALN_U) * 4), "cudaMalloc blobs"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_cigar), static_cast<size_t>(cig_off.back()) * 4), "cudaMalloc cigar"));
-    SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_recs), static_cast<size_t>(n_pairs) * sizeof(AlignRecDev)), "cudaMalloc recs"));
+    SP_TRY(cu(ctx_pool(ctx, 2, static_cast<size_t>(np) * blob_words(ALN_U) * 4, reinterpret_cast<void **>(&d_blobs)), "blob pool"));
+    SP_TRY(cu(ctx_pool(ctx, 1, static_cast<size_t>(cig_off.back()) * 4, reinterpret_cast<void **>(&d_cigar)), "cigar pool"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_recs), static_cast<size_t>(n_pairs) * sizeof(AlignRecDev)), "cudaMalloc recs"));
     SP_TRY(cu(ctx_scratch(ctx, static_cast<size_t>(grid) * K1_WARPS * max_slot_words * 4, reinterpret_cast<void **>(&d_scratch)),
               "traceback scratch"));
     tm.mark("upload + cudaMalloc");
@@ -1060,7 +1087,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     }
     if (total > 0) {
         SP_TRY(up(reinterpret_cast<void **>(&d_out_off), out_off.data(), out_off.size() * sizeof(long long)));
-        SP_TRY(cu(cudaMalloc(reinterpret_cast<void **>(&d_dense), static_cast<size_t>(total) * 4), "cudaMalloc dense cigar"));
+        SP_TRY(cu(ctx_pool(ctx, 3, static_cast<size_t>(total) * 4, reinterpret_cast<void **>(&d_dense)), "dense cigar pool"));
         k4_compact_cigar<<<static_cast<unsigned>(n_pairs), 128, 0, ctx->stream>>>(d_recs, d_cigar, d_out_off, d_dense);
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "k4_compact_cigar launch"));
@@ -1136,14 +1163,14 @@ extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const
     if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
     d->ctx = ctx; d->nt = n_reads; d->np = n_chains; d->elem_bits = 32; d->ld = (n_reads + 63) / 64 * 64;
     int32_t *d_coff = nullptr, *d_items = nullptr, *d_soff = nullptr; uint32_t *d_W = nullptr;
-    auto cleanup = [&]() { cudaFree(d_coff); cudaFree(d_items); cudaFree(d_soff); cudaFree(d_W); };
+    auto cleanup = [&]() { dev_free(ctx, d_coff); dev_free(ctx, d_items); dev_free(ctx, d_soff); dev_free(ctx, d_W); };
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        cudaError_t e = dev_malloc(ctx, dst, std::max<size_t>(bytes, 16));
         if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
         return e;
     };
     const size_t elems = static_cast<size_t>(std::max<int64_t>(d->np * d->ld, 1));
-    cudaError_t e = cudaMalloc(&d->d, elems * 4);
+    cudaError_t e = dev_malloc(ctx, &d->d, elems * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, elems * 4, ctx->stream);
     if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_coff), chain_off, static_cast<size_t>(n_chains + 1) * 4 * (n_chains > 0));
     if (e == cudaSuccess) e = up(reinterpret_cast<void **>(&d_items), chain_items, static_cast<size_t>(n_items) * 4);
@@ -1211,7 +1238,7 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const
     long long n_ctas = 0;
     for (int I = prm.tile_i0; I < tile_i1; ++I) n_ctas += prm.n_tiles_j - I;
     if (n_ctas > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "K2: too many tiles");
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&prm.cand), static_cast<size_t>(n_ctas) * k * sizeof(PairKey)));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&prm.cand), static_cast<size_t>(n_ctas) * k * sizeof(PairKey)));
     ev_begin(ctx, 1);
     if (d->elem_bits == 16) launch_k2_topk<uint16_t>(prm, static_cast<unsigned>(n_ctas), d2 != nullptr, ctx->stream);
     else launch_k2_topk<int32_t>(prm, static_cast<unsigned>(n_ctas), d2 != nullptr, ctx->stream);
@@ -1222,7 +1249,7 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(cand.data(), prm.cand, cand.size() * sizeof(PairKey), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(prm.cand);
+    dev_free(ctx, prm.cand);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2: ") + cudaGetErrorString(e));
     // merge of the per-tile lists: same (score, score2, i, j) order, so any sharding gives the same answer
     auto less = [](const PairKey &a, const PairKey &b) {
@@ -1240,8 +1267,8 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const
         ij[2 * q + 1] = static_cast<uint32_t>(cand[q].ij & 0xFFFFFFFFu);
     }
     uint32_t *d_ij = nullptr, *d_c1 = nullptr;
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_ij), ij.size() * 4));
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_c1), c1.size() * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_ij), ij.size() * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_c1), c1.size() * 4));
     e = cudaMemcpyAsync(d_ij, ij.data(), ij.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         if (d->elem_bits == 16)
@@ -1254,7 +1281,7 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const
         e = cudaMemcpyAsync(c1.data(), d_c1, c1.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_ij); cudaFree(d_c1);
+    dev_free(ctx, d_ij); dev_free(ctx, d_c1);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2 c1: ") + cudaGetErrorString(e));
     for (size_t q = 0; q < kk; ++q) {
         out[q].score = cand[q].score; out[q].score2 = cand[q].score2;
@@ -1279,7 +1306,7 @@ extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint6
     prm.k = 0; prm.cand = nullptr;
     const long long n_ctas = static_cast<long long>(prm.n_tiles_j) * (prm.n_tiles_j + 1) / 2;
     const size_t bytes = static_cast<size_t>(A) * A * sizeof(unsigned long long);
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&prm.S), bytes));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&prm.S), bytes));
     cudaError_t e = cudaMemsetAsync(prm.S, 0, bytes, ctx->stream);
     if (e == cudaSuccess) {
         ev_begin(ctx, 1);
@@ -1291,7 +1318,7 @@ extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint6
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(S, prm.S, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(prm.S);
+    dev_free(ctx, prm.S);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("K2 full: ") + cudaGetErrorString(e));
     return SP_OK;
 }
@@ -1306,8 +1333,8 @@ static sp_status upload_rows(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A
     d->ctx = ctx; d->nt = R; d->np = A; d->ld = (R + 63) / 64 * 64; d->elem_bits = 32;
     int32_t *rows = nullptr;
     const size_t n = static_cast<size_t>(std::max<int64_t>(R * A, 1));
-    cudaError_t e = cudaMalloc(&d->d, static_cast<size_t>(std::max<int64_t>(A * d->ld, 1)) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&rows), n * 4);
+    cudaError_t e = dev_malloc(ctx, &d->d, static_cast<size_t>(std::max<int64_t>(A * d->ld, 1)) * 4);
+    if (e == cudaSuccess) e = dev_malloc(ctx, reinterpret_cast<void **>(&rows), n * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(d->d, 0, static_cast<size_t>(std::max<int64_t>(A * d->ld, 1)) * 4, ctx->stream);
     if (e == cudaSuccess && R * A > 0) {
         e = cudaMemcpyAsync(rows, D, static_cast<size_t>(R * A) * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -1320,7 +1347,7 @@ static sp_status upload_rows(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(rows);
+    dev_free(ctx, rows);
     if (e != cudaSuccess) { sp_dmatrix_destroy(d); return fail(ctx, SP_ERR_CUDA, std::string("K2 host upload: ") + cudaGetErrorString(e)); }
     *out = d;
     return SP_OK;
@@ -1355,7 +1382,7 @@ extern "C" sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s) {
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     const int grid = ctx->num_sms * 8, iters = 8192;
     uint32_t *d_out = nullptr;
-    SP_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d_out), static_cast<size_t>(grid) * 256 * 4));
+    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_out), static_cast<size_t>(grid) * 256 * 4));
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     float best_ms = 1e30f;
@@ -1378,7 +1405,7 @@ extern "C" sp_status sp_int_peak(sp_ctx *ctx, int kind, double *ops_per_s) {
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaError_t e = cudaGetLastError();
-    cudaFree(d_out);
+    dev_free(ctx, d_out);
     if (e != cudaSuccess) return fail(ctx, SP_ERR_CUDA, std::string("sp_int_peak: ") + cudaGetErrorString(e));
     const double ops = static_cast<double>(grid) * 256.0 * iters * 64.0;
     *ops_per_s = ops / (best_ms * 1e-3);

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <limits>
 #include <numeric>
+#include <tuple>
 
 #include "starphase_host.hpp"
 
@@ -212,30 +213,37 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
     std::vector<Item> items;
     SeqList tmpl_seqs;
     for (const auto &t : templates_) tmpl_seqs.push_back(t.second);
+    if (nt == 0) return std::vector<std::vector<AlleleMapping>>(seqs.size());
 
-    // round 0: every (sequence, template) through K1; only placements that could pass go to the traceback
-    SeqList texts;
-    std::vector<std::pair<int32_t, int32_t>> pairs;
-    std::vector<Item> pair_item;
-    std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
-    if (!seqs.empty() && nt) {
-        std::vector<int32_t> E;
-        const std::vector<int32_t> D = gpu_.score_batch(seqs, tmpl_seqs, &E);
-        for (size_t s = 0; s < seqs.size(); ++s) {
-            if (seqs[s].empty()) continue;  // :148-151
-            for (size_t t = 0; t < nt; ++t) {
-                const size_t m = tmpl_seqs[t].size();
-                const size_t d = static_cast<size_t>(D[s * nt + t]), e = static_cast<size_t>(E[s * nt + t]);
-                if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
-                const size_t w0 = e > m + d ? e - (m + d) : 0;
-                pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(t));
-                texts.push_back(seqs[s].substr(w0, e - w0));
-                pair_item.push_back({s, 0, seqs[s].size(), t});
-                pair_off.push_back(w0);
-            }
+    // every round: K1 scores each open (segment, template) item (segment x all templates in one launch; round 0 = the whole
+    // sequences); only placements that could pass go to the K4 traceback, on the placement window
+    for (size_t s = 0; s < seqs.size(); ++s)
+        if (!seqs[s].empty())  // :148-151
+            for (size_t t = 0; t < nt; ++t) items.push_back({s, 0, seqs[s].size(), t});
+    for (int round = 0; round < 5 && !items.empty(); ++round) {
+        std::map<std::tuple<size_t, size_t, size_t>, size_t> seg_index;  // (seq, lo, hi) -> row of the K1 matrix
+        SeqList seg_texts;
+        for (const Item &it : items) {
+            const auto key = std::make_tuple(it.seq, it.lo, it.hi);
+            if (seg_index.emplace(key, seg_texts.size()).second) seg_texts.push_back(seqs[it.seq].substr(it.lo, it.hi - it.lo));
         }
-    }
-    for (int round = 0; round < 5 && !pairs.empty(); ++round) {
+        std::vector<int32_t> E;
+        const std::vector<int32_t> D = gpu_.score_batch(seg_texts, tmpl_seqs, &E);
+        SeqList texts;
+        std::vector<std::pair<int32_t, int32_t>> pairs;
+        std::vector<Item> pair_item;
+        std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
+        for (const Item &it : items) {
+            const size_t row = seg_index.at(std::make_tuple(it.seq, it.lo, it.hi));
+            const size_t m = tmpl_seqs[it.tmpl].size();
+            const size_t d = static_cast<size_t>(D[row * nt + it.tmpl]), e = static_cast<size_t>(E[row * nt + it.tmpl]);
+            if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
+            const size_t w0 = e > m + d ? e - (m + d) : 0;
+            pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(it.tmpl));
+            texts.push_back(seg_texts[row].substr(w0, e - w0));
+            pair_item.push_back(it);
+            pair_off.push_back(it.lo + w0);
+        }
         const std::vector<Alignment> alns = gpu_.align_pairs(texts, tmpl_seqs, pairs);
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {
@@ -255,13 +263,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             if (hs > it.lo && hs - it.lo >= std::max<size_t>(min_len, 200)) next.push_back({it.seq, it.lo, hs, it.tmpl});
             if (it.hi > he && it.hi - he >= std::max<size_t>(min_len, 200)) next.push_back({it.seq, he, it.hi, it.tmpl});
         }
-        texts.clear(); pairs.clear(); pair_item.clear(); pair_off.clear();
-        for (const Item &it : next) {
-            pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(it.tmpl));
-            texts.push_back(seqs[it.seq].substr(it.lo, it.hi - it.lo));
-            pair_item.push_back(it);
-            pair_off.push_back(it.lo);
-        }
+        items = std::move(next);
     }
 
     std::vector<std::vector<AlleleMapping>> out(seqs.size());

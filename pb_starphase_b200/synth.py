@@ -183,3 +183,48 @@ def cyp2d6_sample(seed: int, n_reads: int = 256, n_consensus: int = 24, n_chains
         chains.append([int(rng.choice(by_kind[order[(start + t) % len(order)]])) for t in range(ln)])
     return dict(templates=templates, consensuses=cons, reads=reads, segments=segments,
                 seg_read=np.asarray(seg_read, dtype=np.int32), chains=chains)
+
+
+# labels of the 39 templates in the order cyp2d6_templates returns them (src/cyp2d6/definitions.rs:346-464)
+_HYBRID_PARTS = ["intron1", "exon2", "intron2", "exon3", "intron3", "exon4", "intron4", "exon5", "intron5", "exon6", "intron6",
+                 "exon7", "intron7", "exon8", "intron8", "exon9"]
+
+
+def cyp2d6_template_labels():
+    labels = [("CYP2D6", None), ("CYP2D7", None), ("CYP2D6*5", None)]
+    for part in _HYBRID_PARTS:
+        labels.append(("Hybrid", f"CYP2D6::CYP2D7::{part}"))
+        labels.append(("Hybrid", f"CYP2D7::CYP2D6::{part}"))
+    return labels + [("REP6", None), ("REP7", None), ("spacer", None), ("link_region", None)]
+
+
+def cyp2d6_diploid_sample(seed: int, n_reads: int = 96, star_alleles=("1.001", "4.001")):
+    """One diploid CYP2D6 sample at the reference's region lengths: two haplotypes REP6 - CYP2D6*x - link - REP7 -
+    spacer - CYP2D7 whose region copies differ by ~0.5 % (so reads assign uniquely), consensus sequences + labels for
+    both, and HiFi-like reads spanning 2-4 consecutive regions of one haplotype with the region coordinates inside
+    each read (what Cyp2d6Extractor + the consensus step hand to the chaining code, src/cyp2d6/caller.rs:430-537).
+    Returns dict(templates, template_labels, consensuses, regions [(type, subtype, unique_id)], reads, roi)."""
+    rng = np.random.default_rng([seed, 2, 66])
+    regions, templates = cyp2d6_templates(rng)
+    order = ["rep6", "d6", "link", "rep7", "spacer", "d7"]
+    kinds = dict(rep6="REP6", d6="CYP2D6", link="link_region", rep7="REP7", spacer="spacer", d7="CYP2D7")
+    cons, rows = [], []
+    for hap, sub in enumerate(star_alleles):
+        for kind in order:
+            base = regions[kind]
+            cons.append(mutate(rng, base, max(6, len(base) // 200), 1).tobytes())
+            rows.append((kinds[kind], sub if kind == "d6" else None, len(rows)))
+    reads, roi = [], {}
+    for r in range(n_reads):
+        hap, start, w = int(rng.integers(0, 2)), int(rng.integers(0, 5)), int(rng.integers(2, 5))
+        lead = random_seq(rng, int(rng.integers(100, 400))).tobytes()
+        pos, parts, regs = len(lead), [lead], []
+        for t in range(start, min(start + w, 6)):
+            seg, _ = hifi_reads(rng, [cons[hap * 6 + t]], 1, flank=0, lo=0, hi=1 << 30)
+            regs.append((pos, pos + len(seg[0]), seg[0]))
+            parts.append(seg[0])
+            pos += len(seg[0])
+        parts.append(random_seq(rng, int(rng.integers(100, 400))).tobytes())
+        reads.append(b"".join(parts))
+        roi[f"m84/{seed}/{r:04d}/ccs"] = regs
+    return dict(templates=templates, template_labels=cyp2d6_template_labels(), consensuses=cons, regions=rows, reads=reads, roi=roi)

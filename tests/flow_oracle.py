@@ -197,20 +197,16 @@ def find_base_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missi
     tseqs = [t[2] for t in tl]
     labels = [so.RegionLabel(t[0], t[1]) for t in tl]
     out = []
-    D, E = orc.score_batch(list(seqs), tseqs, want_end_col=True) if len(seqs) and tl else (None, None)
     for s, seq in enumerate(seqs):
         hits, n_hits = [], [0] * len(tl)
-        items = []
-        if len(seq):
-            for t in range(len(tl)):
-                m, d = len(tseqs[t]), int(D[s, t])
-                if m == 0 or 2 * d > m:
-                    continue
-                items.append((0, len(seq), t))
+        items = [(0, len(seq), t) for t in range(len(tl))] if len(seq) else []
         for _round in range(5):
             nxt = []
             for lo, hi, t in items:
                 m = len(tseqs[t])
+                d, _ = orc.infix(tseqs[t], seq[lo:hi])  # the K1 prefilter of every round
+                if m == 0 or 2 * d > m:
+                    continue
                 a = orc.align(tseqs[t], seq[lo:hi])
                 if not a["cigar"] or dp_score_a1(a["cigar"]) < 200:
                     continue
