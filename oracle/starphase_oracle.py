@@ -814,6 +814,35 @@ def _json_str(s: str) -> str:
     return "".join(out)
 
 
+def format_f64(v: float) -> str:
+    """serde_json's f64: ryu's shortest round-trip digits (Python's repr yields the same digit string) in the layout
+    of ryu::pretty::format64 -- decimals for a decimal-point position in (-5, 16], scientific otherwise, ".0" on
+    integral values; non-finite -> null."""
+    if math.isnan(v) or math.isinf(v):
+        return "null"
+    if v == 0.0:
+        return "-0.0" if math.copysign(1.0, v) < 0 else "0.0"
+    from decimal import Decimal
+
+    sign, digs, exp = Decimal(repr(abs(v))).as_tuple()
+    digits = "".join(map(str, digs)).lstrip("0")
+    stripped = digits.rstrip("0")
+    exp += len(digits) - len(stripped)
+    digits = stripped
+    length, k = len(digits), exp
+    kk = length + k
+    out = "-" if v < 0 else ""
+    if 0 <= k and kk <= 16:
+        return out + digits + "0" * k + ".0"
+    if 0 < kk <= 16:
+        return out + digits[:kk] + "." + digits[kk:]
+    if -5 < kk <= 0:
+        return out + "0." + "0" * (-kk) + digits
+    if length == 1:
+        return out + digits + "e" + str(kk - 1)
+    return out + digits[0] + "." + digits[1:] + "e" + str(kk - 1)
+
+
 def serde_pretty(v, indent: int = 0) -> str:
     """serde_json PrettyFormatter: empty containers print as [] / {}, otherwise one item per line."""
     pad = "  " * (indent + 1)
@@ -827,7 +856,7 @@ def serde_pretty(v, indent: int = 0) -> str:
     if isinstance(v, int):
         return str(v)
     if isinstance(v, float):
-        raise TypeError("no floats appear in the main result JSON (SURVEY.md §8b)")
+        return format_f64(v)  # only hla_debug.json holds floats; the main result JSON has none
     if isinstance(v, str):
         return _json_str(v)
     if isinstance(v, (list, tuple)):
@@ -872,3 +901,191 @@ def starphase_json(pbstarphase_version: str, database_metadata: dict, gene_detai
     doc = dict(pbstarphase_version=pbstarphase_version, database_metadata=md,
                gene_details={k: gene_details[k] for k in sorted(gene_details)})
     return serde_pretty(doc)
+
+
+# ==========================================================================================
+# hla_debug.json -- src/hla/debug.rs (HlaDebug, ReadMappingStats, DetailedMappingStats, DualPassingStats)
+# ==========================================================================================
+_CIGAR_OPS = "MIDNSHP=XB"
+
+
+def cigar_string(cigar: Sequence[Tuple[int, int]]) -> str:
+    """minimap2 crate `cigar_str`: length + op letter per entry."""
+    return "".join(f"{ln}{_CIGAR_OPS[op]}" for ln, op in cigar)
+
+
+def _nt4(c: int) -> int:
+    return {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}.get(c, 4)
+
+
+def md_string(cigar: Sequence[Tuple[int, int]], target: bytes, t_off: int, query: bytes, q_off: int) -> str:
+    """minimap2 2.28 format.c write_MD_core (unvendored dependency, restated from its published source): counts of equal
+    bases, mismatches as the target base, deletions as ^bases, no trailing zero."""
+    out, run = [], 0
+    for ln, op in cigar:
+        if op in (0, 7, 8):
+            for j in range(ln):
+                tq = _nt4(target[t_off + j])
+                if _nt4(query[q_off + j]) != tq:
+                    out.append(f"{run}{'ACGTN'[tq]}")
+                    run = 0
+                else:
+                    run += 1
+            t_off += ln
+            q_off += ln
+        elif op == 1:
+            q_off += ln
+        elif op == 2:
+            out.append(f"{run}^" + "".join("ACGTN"[_nt4(target[t_off + j])] for j in range(ln)))
+            run = 0
+            t_off += ln
+        elif op == 3:
+            t_off += ln
+        else:
+            raise ValueError(f"Unexpected cigar type: {op}")
+    if run > 0:
+        out.append(str(run))
+    return "".join(out)
+
+
+def detailed_mapping_stats(m: Mapping, target: bytes, query: bytes) -> dict:
+    """DetailedMappingStats::from_mapping, src/hla/debug.rs:161-181 (match_len = mm_reg1_t::mlen = bases under '=')."""
+    return dict(query_len=m.query_len, target_len=m.target_len, match_len=sum(ln for ln, op in m.cigar if op == 7), nm=m.nm,
+                query_unmapped=m.query_len - (m.query_end - m.query_start), target_unmapped=m.target_len - (m.target_end - m.target_start),
+                cigar=cigar_string(m.cigar), md=md_string(m.cigar, target, m.target_start, query, m.query_start))
+
+
+def read_mapping_stats_json(best_id: Optional[str], best_star: Optional[str], mapping_stats: Dict[str, Tuple[Optional[dict], Optional[dict]]]) -> dict:
+    """ReadMappingStats, src/hla/debug.rs:64-73 (BTreeMap: keys sorted bytewise)."""
+    return dict(best_match_id=best_id, best_match_star=best_star,
+                mapping_stats={k: dict(cdna_mapping=mapping_stats[k][0], dna_mapping=mapping_stats[k][1])
+                               for k in sorted(mapping_stats, key=lambda x: x.encode())})
+
+
+def dual_passing_stats(is_dual: bool, counts1: int = 0, counts2: int = 0, min_consensus_fraction: float = 0.10, min_cdf: float = 0.001,
+                       expected_maf: float = 0.45) -> dict:
+    """is_passing_dual's DualPassingStats, src/hla/caller.rs:1225-1247 + src/hla/debug.rs:186-226."""
+    if not is_dual:
+        return dict(is_passing=False, is_dual=False, counts1=None, counts2=None, maf=None, cdf=None)
+    total, minor = counts1 + counts2, min(counts1, counts2)
+    maf = float(minor) / float(total)
+    cdf = binomial_cdf(total, expected_maf, minor)
+    return dict(is_passing=maf >= min_consensus_fraction and cdf >= min_cdf, is_dual=True, counts1=counts1, counts2=counts2, maf=maf, cdf=cdf)
+
+
+def hla_debug_json(read_mapping_stats: Dict[str, Dict[str, dict]], dual_passing: Optional[Dict[str, dict]]) -> str:
+    """HlaDebug through save_json, src/hla/debug.rs:6-12."""
+    doc = dict(read_mapping_stats={g: {q: read_mapping_stats[g][q] for q in sorted(read_mapping_stats[g], key=lambda x: x.encode())}
+                                   for g in sorted(read_mapping_stats, key=lambda x: x.encode())},
+               dual_passing_stats=None if dual_passing is None else {g: dual_passing[g] for g in sorted(dual_passing, key=lambda x: x.encode())})
+    return serde_pretty(doc)
+
+
+# ==========================================================================================
+# consensus preparation in front of score_read -- src/hla/caller.rs:1337-1368, :1518-1576, src/util/sequence.rs:9-23
+# ==========================================================================================
+def reverse_complement(seq: bytes) -> bytes:
+    comp = {65: 84, 67: 71, 71: 67, 84: 65, 78: 78}
+    out = bytearray()
+    for c in reversed(seq):
+        if c not in comp:
+            raise ValueError(f"Unexpected character for reverse-complement: {c}")
+        out.append(comp[c])
+    return bytes(out)
+
+
+def aligned_pairs(pos: int, cigar: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """rust-htslib bam::Record::aligned_pairs: [read index, reference position] for every M / = / X column."""
+    out, q, r = [], 0, pos
+    for ln, op in cigar:
+        if op in (0, 7, 8):
+            out.extend((q + k, r + k) for k in range(ln))
+            q += ln
+            r += ln
+        elif op in (1, 4):
+            q += ln
+        elif op in (2, 3):
+            r += ln
+        elif op in (5, 6):
+            pass
+        else:
+            raise ValueError(f"Unexpected cigar type: {op}")
+    return out
+
+
+def splice_read(sequence: bytes, pos: int, cigar: Sequence[Tuple[int, int]], exons: Sequence[Tuple[int, int]]) -> Tuple[bytes, int]:
+    """src/hla/caller.rs:1518-1576."""
+    lookup = {}
+    for qi, ri in aligned_pairs(pos, cigar):
+        lookup[ri] = qi
+    offset, segments = 0, []
+    for start, end in exons:
+        first, last = start, end - 1
+        while first not in lookup and first <= last:
+            first += 1
+        while last not in lookup and first <= last:
+            last -= 1
+        if not segments:
+            offset += first - start
+        if first <= last:
+            segments.append((lookup[first], lookup[last] + 1))
+    return b"".join(sequence[a:b] for a, b in segments), offset
+
+
+def prepare_score_read_targets(read_sequence: bytes, pos: int, cigar, exons, is_forward_strand: bool, disable_cdna_scoring: bool = False):
+    """src/hla/caller.rs:1337-1368: (DNA target, cDNA target)."""
+    dna = read_sequence if is_forward_strand else reverse_complement(read_sequence)
+    if disable_cdna_scoring:
+        return dna, b"N"
+    fw, _ = splice_read(read_sequence, pos, cigar, exons)
+    if not fw:
+        return dna, b"N"
+    return dna, (fw if is_forward_strand else reverse_complement(fw))
+
+
+# ==========================================================================================
+# hemizygous test -- src/hla/caller.rs:1583-1653 (statrs 0.16 Normal::ln_pdf, Binomial::ln_pmf restated)
+# ==========================================================================================
+LN_SQRT_2PI = 0.91893853320467274178032973640561763986139747363778341281715
+
+
+def normal_ln_pdf(mean: float, std_dev: float, x: float) -> float:
+    d = (x - mean) / std_dev
+    return (-0.5 * d * d) - LN_SQRT_2PI - math.log(std_dev)
+
+
+def binomial_ln_pmf(n: int, p: float, x: int) -> float:
+    if x > n:
+        return -math.inf
+    if p == 0.0:
+        return 0.0 if x == 0 else -math.inf
+    if p == 1.0:
+        return 0.0 if x == n else -math.inf
+    return (ln_factorial(n) - ln_factorial(x) - ln_factorial(n - x)) + float(x) * math.log(p) + float(n - x) * math.log(1.0 - p)
+
+
+def is_hemizygous_better(scores1: Sequence[Optional[int]], scores2: Sequence[Optional[int]], is_consensus1: Sequence[bool], is_dual: bool,
+                         dual_max_ed_delta: int, normalized_coverage: Optional[float]) -> bool:
+    read_count = len(is_consensus1)
+    min_ed = 0
+    if is_dual:
+        c1 = c2 = 0
+        for o1, o2 in zip(scores1, scores2):
+            assert o1 is not None or o2 is not None
+            s1 = o1 if o1 is not None else (o2 or 0) + dual_max_ed_delta
+            s2 = o2 if o2 is not None else (o1 or 0) + dual_max_ed_delta
+            mn = min(s1, s2)
+            c1 += s1 - mn
+            c2 += s2 - mn
+        min_ed = min(c1, c2)
+    haploid_ed_cost = 2.0 * float(min_ed)
+    nc_hap = normalized_coverage if normalized_coverage is not None else float(read_count)
+    nc_dev = nc_hap * 0.1
+    if not nc_dev > 0.0:
+        raise ValueError("Bad distribution parameters")
+    haploid_cost = haploid_ed_cost + abs(normal_ln_pdf(nc_hap, nc_dev, float(read_count)))
+    obs1 = sum(1 for b in is_consensus1 if b)
+    balance = 2.0 * abs(binomial_ln_pmf(read_count, 0.5, obs1)) if is_dual else 0.0
+    nc_dip = 2.0 * nc_hap
+    diploid_cost = balance + abs(normal_ln_pdf(nc_dip, nc_dev, float(read_count)))
+    return haploid_cost < diploid_cost

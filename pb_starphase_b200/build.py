@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 # ---------------------------------------------------------------------------------------------
 HOST = HERE / "host"
 HOST_LIB = HERE / "libstarphase_host.so"
-HOST_SOURCES = ["sp_host_core.cpp", "sp_host_gpu.cpp", "sp_host_hla.cpp", "sp_host_cyp2d6.cpp"]
+HOST_SOURCES = ["sp_host_core.cpp", "sp_host_gpu.cpp", "sp_host_hla.cpp", "sp_host_cyp2d6.cpp", "sp_host_debug.cpp"]
 
 
 def host_module_path() -> Path:

@@ -1,8 +1,10 @@
 // sp_host_core.cpp -- scores, mapping selection, processed CIGARs, statistics, JSON writer.
 // Each function follows the reference file:line named in starphase_host.hpp.
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 
 #include "starphase_host.hpp"
@@ -36,6 +38,38 @@ static void json_escape(const std::string &s, std::string &out) {
     out.push_back('"');
 }
 
+// f64 the way serde_json prints it: ryu's shortest round-trip digits (std::to_chars gives the same digit string) laid
+// out by ryu::pretty::format64 -- plain decimals for exponents in (-5, 16], scientific otherwise, always with ".0" on
+// integral values; NaN / infinity become null (serde_json::ser::Formatter::write_f64 via Value)
+static std::string format_f64(double v) {
+    if (!std::isfinite(v)) return "null";
+    if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[64];
+    const auto res = std::to_chars(buf, buf + sizeof buf, std::fabs(v), std::chars_format::scientific);
+    const std::string sci(buf, res.ptr);  // d[.ddd]e[+-]xx
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t i = 0; i < epos; ++i)
+        if (sci[i] != '.') digits.push_back(sci[i]);
+    const int exp10 = std::atoi(sci.c_str() + epos + 1);
+    const int length = static_cast<int>(digits.size());
+    const int kk = exp10 + 1;       // position of the decimal point relative to the digit string
+    const int k = kk - length;      // value = digits * 10^k
+    std::string out = std::signbit(v) ? "-" : "";
+    if (0 <= k && kk <= 16) {
+        out += digits + std::string(static_cast<size_t>(k), '0') + ".0";
+    } else if (0 < kk && kk <= 16) {
+        out += digits.substr(0, static_cast<size_t>(kk)) + "." + digits.substr(static_cast<size_t>(kk));
+    } else if (-5 < kk && kk <= 0) {
+        out += "0." + std::string(static_cast<size_t>(-kk), '0') + digits;
+    } else if (length == 1) {
+        out += digits + "e" + std::to_string(kk - 1);
+    } else {
+        out += digits.substr(0, 1) + "." + digits.substr(1) + "e" + std::to_string(kk - 1);
+    }
+    return out;
+}
+
 std::string Json::pretty(int indent) const {
     const std::string pad(static_cast<size_t>(2 * (indent + 1)), ' '), end(static_cast<size_t>(2 * indent), ' ');
     std::string out;
@@ -43,6 +77,7 @@ std::string Json::pretty(int indent) const {
         case Null: return "null";
         case Bool: return i_ ? "true" : "false";
         case Int: return std::to_string(i_);
+        case Float: return format_f64(f_);
         case Str: json_escape(s_, out); return out;
         case Arr:
             if (a_.empty()) return "[]";
@@ -244,15 +279,47 @@ double multinomial_ln_pmf(const std::vector<double> &probs, const std::vector<ui
     return coeff + acc;
 }
 
-double binomial_cdf(uint64_t n, double p, uint64_t k) {
-    if (k >= n) return 1.0;
-    const double lp = std::log(p), lq = std::log1p(-p);
-    long double acc = 0.0L;
-    for (uint64_t x = 0; x <= k; ++x) {
-        const double ln_c = ln_factorial(n) - ln_factorial(x) - ln_factorial(n - x);
-        acc += std::exp(static_cast<long double>(ln_c + static_cast<double>(x) * lp + static_cast<double>(n - x) * lq));
+// statrs 0.16 function::beta::beta_reg: regularized incomplete beta by the modified Lentz continued fraction
+// (Math.NET's BetaRegularized), 140 iterations at most, symmetry transform above (a + 1) / (a + b + 2)
+double beta_reg(double a, double b, double x) {
+    if (!(a > 0.0) || !(b > 0.0) || !(x >= 0.0 && x <= 1.0)) throw HostError("beta_reg: arguments out of range");
+    const double bt = (x == 0.0 || x == 1.0)
+                          ? 0.0
+                          : std::exp(ln_gamma(a + b) - ln_gamma(a) - ln_gamma(b) + a * std::log(x) + b * std::log(1.0 - x));
+    const bool symm = x >= (a + 1.0) / (a + b + 2.0);
+    const double eps = 0.00000000000000011102230246251565;  // prec::F64_PREC
+    const double fpmin = std::numeric_limits<double>::min() / eps;
+    if (symm) { const double swap = a; x = 1.0 - x; a = b; b = swap; }
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (std::fabs(d) < fpmin) d = fpmin;
+    d = 1.0 / d;
+    double h = d;
+    for (int mi = 1; mi < 141; ++mi) {
+        const double m = static_cast<double>(mi), m2 = m * 2.0;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (std::fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c;
+        if (std::fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        h = h * d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (std::fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c;
+        if (std::fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (std::fabs(del - 1.0) <= eps) break;
     }
-    return static_cast<double>(std::min<long double>(acc, 1.0L));
+    return symm ? 1.0 - bt * h / a : bt * h / a;
+}
+
+double binomial_cdf(uint64_t n, double p, uint64_t k) {  // statrs 0.16 Binomial::cdf
+    if (k >= n) return 1.0;
+    return beta_reg(static_cast<double>(n) - static_cast<double>(k), static_cast<double>(k) + 1.0, 1.0 - p);
 }
 
 bool is_passing_dual(size_t counts1, size_t counts2, double min_consensus_fraction, double min_cdf, double expected_maf) {

@@ -69,19 +69,24 @@ ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const
     HlaProcessedMatch best_match = HlaProcessedMatch::worst_match(2);
     for (size_t a = 0; a < allowed.size(); ++a) {  // BTreeMap order: the scan order is part of the semantics
         HlaProcessedMatch current(allowed[a]->hla_id);
+        std::optional<DetailedMappingStats> detail[2];  // full_mappings()[0..1] as src/hla/debug.rs records them
         for (int which = 0; which < 2; ++which) {
             const int q = which == 0 ? cdna_pair[a] : dna_pair[a];
             std::optional<Mapping> best_mapping;
             if (q >= 0) {
-                const size_t plen = patterns[static_cast<size_t>(pairs[static_cast<size_t>(q)].second)].size();
+                const std::string &pattern = patterns[static_cast<size_t>(pairs[static_cast<size_t>(q)].second)];
                 std::vector<Mapping> mappings;
-                if (auto m = mapping_from_alignment(alns[static_cast<size_t>(q)], plen, targets[static_cast<size_t>(which)].size(), settings.min_dp_score))
+                if (auto m = mapping_from_alignment(alns[static_cast<size_t>(q)], pattern.size(), targets[static_cast<size_t>(which)].size(), settings.min_dp_score))
                     mappings.push_back(*m);
                 const auto sel = select_best_mapping(mappings, false, true, std::nullopt);  // :1448-1452
-                if (sel.first) best_mapping = mappings[*sel.first];
+                if (sel.first) {
+                    best_mapping = mappings[*sel.first];
+                    detail[which] = detailed_mapping_stats(*best_mapping, targets[static_cast<size_t>(which)], pattern);
+                }
             }
             current.add_mapping(best_mapping);
         }
+        ret.read_mapping_stats.add_mapping(join_star(allowed[a]->star_allele), detail[0], detail[1]);  // :1471-1477
         HlaMappingStats stats;
         stats.cdna_stats = current.full_mapping_stats()[0];
         stats.dna_stats = current.full_mapping_stats()[1];
@@ -89,7 +94,10 @@ ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const
         ret.stats.emplace(allowed[a]->hla_id, stats);
     }
     ret.best_hla_id = best_match.haplotype();
-    if (!ret.best_hla_id.empty()) ret.best_star_allele = join_star(database.at(ret.best_hla_id).star_allele);
+    if (!ret.best_hla_id.empty()) {
+        ret.best_star_allele = join_star(database.at(ret.best_hla_id).star_allele);
+        ret.read_mapping_stats.set_best_match(ret.best_hla_id, ret.best_star_allele);  // :1502-1509
+    }
     return ret;
 }
 

@@ -90,6 +90,26 @@ PYBIND11_MODULE(_starphase_host, m) {
     m.def("is_passing_dual", &is_passing_dual, py::arg("counts1"), py::arg("counts2"), py::arg("min_consensus_fraction") = 0.10,
           py::arg("min_cdf") = 0.001, py::arg("expected_maf") = 0.45);
 
+    m.def("beta_reg", &beta_reg);
+    m.def("binomial_ln_pmf", &binomial_ln_pmf);
+    m.def("normal_ln_pdf", &normal_ln_pdf);
+    m.def("json_f64", [](double v) { return Json::number(v).pretty(); });
+    m.def("dual_passing_stats_json", [](bool is_dual, size_t c1, size_t c2, double min_fraction, double min_cdf, double expected_maf) {
+        return dual_passing_stats(is_dual, c1, c2, min_fraction, min_cdf, expected_maf).to_json().pretty();
+    }, py::arg("is_dual"), py::arg("counts1"), py::arg("counts2"), py::arg("min_consensus_fraction") = 0.10, py::arg("min_cdf") = 0.001,
+          py::arg("expected_maf") = 0.45);
+    m.def("is_hemizygous_better", &is_hemizygous_better, py::arg("scores1"), py::arg("scores2"), py::arg("is_consensus1"), py::arg("is_dual"),
+          py::arg("dual_max_ed_delta"), py::arg("normalized_coverage"));
+    m.def("cigar_string", &cigar_string);
+    m.def("md_string", &md_string, py::arg("cigar"), py::arg("target"), py::arg("target_start"), py::arg("query"), py::arg("query_start"));
+    m.def("reverse_complement", &reverse_complement);
+    m.def("splice_read", &splice_read, py::arg("sequence"), py::arg("pos"), py::arg("cigar"), py::arg("exons"));
+    m.def("prepare_score_read_targets", [](const std::string &seq, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                           const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool fwd, const DiplotypeSettings &s) {
+        const ScoreReadTargets t = prepare_score_read_targets(seq, pos, cigar, exons, fwd, s);
+        return py::make_tuple(t.dna_target, t.cdna_target);
+    });
+
     py::class_<DiplotypeSettings>(m, "DiplotypeSettings")
         .def(py::init<>())
         .def_readwrite("disable_cdna_scoring", &DiplotypeSettings::disable_cdna_scoring)
@@ -131,6 +151,18 @@ PYBIND11_MODULE(_starphase_host, m) {
             stats[py::str(kv.first)] = py::make_tuple(tup(kv.second.cdna_stats), tup(kv.second.dna_stats));
         }
         return py::make_tuple(stats, r.best_hla_id, r.best_star_allele);
+    });
+    // hla_debug.json of one gene scored like diplotype_hla_batch does it (src/hla/caller.rs:805, :877, :914): one score_read per
+    // consensus under the names consensus1 / consensus2 + the gene's DualPassingStats
+    m.def("hla_debug_json", [](GpuAligner &g, const DbRows &rows, const std::string &gene,
+                               const std::vector<std::tuple<std::string, std::string, std::string>> &consensuses /* qname, dna target, cdna target */,
+                               bool is_dual, size_t counts1, size_t counts2, const DiplotypeSettings &s) {
+        const HlaDatabase db = make_db(rows);
+        HlaDebug dbg;
+        for (const auto &c : consensuses)
+            dbg.add_read(gene, std::get<0>(c), score_read(g, std::get<1>(c), std::get<2>(c), db, gene, s).read_mapping_stats);
+        dbg.add_dual_passing_stats(gene, dual_passing_stats(is_dual, counts1, counts2, s.min_consensus_fraction, s.min_cdf, s.expected_maf));
+        return dbg.pretty();
     });
     m.def("realign_records", [](GpuAligner &g, const std::vector<std::string> &genes, const DbRows &rows,
                                 const std::vector<std::pair<std::string, std::string>> &reads, int n_candidates) {

@@ -17,6 +17,9 @@
 //   src/cyp2d6/chaining.rs:223-592                  find_best_chain_pair  (K3 chain windows + K2)
 //   src/cyp2d6/caller.rs:907-957                    convert_chain_to_hap
 //   src/data_types/starphase_json.rs, src/util/file_io.rs:37-52   result JSON (serde pretty)
+//   src/hla/debug.rs                                HlaDebug / ReadMappingStats / DualPassingStats (hla_debug.json)
+//   src/hla/caller.rs:1259-1319, :1337-1368, :1518-1576   score_consensus target preparation, splice_read
+//   src/hla/caller.rs:1583-1653                     is_hemizygous_better
 #pragma once
 #include <cstdint>
 #include <map>
@@ -42,7 +45,7 @@ struct HostError : std::runtime_error {
 // ------------------------------------------------------------------------------------------
 class Json {
   public:
-    enum Kind { Null, Bool, Int, Str, Arr, Obj };
+    enum Kind { Null, Bool, Int, Float, Str, Arr, Obj };
     Json() : kind_(Null) {}
     Json(std::nullptr_t) : kind_(Null) {}
     Json(bool b) : kind_(Bool), i_(b) {}
@@ -52,6 +55,8 @@ class Json {
     Json(unsigned long v) : kind_(Int), i_(static_cast<long long>(v)) {}
     Json(const char *s) : kind_(Str), s_(s) {}
     Json(std::string s) : kind_(Str), s_(std::move(s)) {}
+    // f64 as serde_json writes it: ryu's shortest round-trip digits and notation, non-finite -> null
+    static Json number(double v) { Json j; j.kind_ = Float; j.f_ = v; return j; }
     static Json array() { Json j; j.kind_ = Arr; return j; }
     static Json object() { Json j; j.kind_ = Obj; return j; }
     Json &push(Json v) { a_.push_back(std::move(v)); return *this; }
@@ -61,6 +66,7 @@ class Json {
   private:
     Kind kind_;
     long long i_ = 0;
+    double f_ = 0.0;
     std::string s_;
     std::vector<Json> a_;
     std::vector<std::pair<std::string, Json>> o_;
@@ -132,9 +138,31 @@ double ln_gamma(double x);
 double ln_factorial(uint64_t x);
 double multinomial_ln_pmf(const std::vector<double> &probs, const std::vector<uint64_t> &obs);  // src/util/stats.rs:11-36
 double binomial_cdf(uint64_t n, double p, uint64_t k);
+double beta_reg(double a, double b, double x);  // statrs 0.16 function::beta::beta_reg (continued fraction)
+double binomial_ln_pmf(uint64_t n, double p, uint64_t x);          // statrs 0.16 Binomial::ln_pmf
+double normal_ln_pdf(double mean, double std_dev, double x);       // statrs 0.16 Normal::ln_pdf
 // src/hla/caller.rs:1225-1247 (defaults of src/cli/diplotype.rs)
 bool is_passing_dual(size_t counts1, size_t counts2, double min_consensus_fraction = 0.10, double min_cdf = 0.001,
                      double expected_maf = 0.45);
+
+struct DualPassingStats {  // src/hla/debug.rs:186-226
+    bool is_passing = false, is_dual = false;
+    std::optional<size_t> counts1, counts2;
+    std::optional<double> maf, cdf;
+    static DualPassingStats new_dual(bool is_passing, size_t c1, size_t c2, double maf, double cdf);
+    static DualPassingStats new_non_dual() { return DualPassingStats(); }
+    Json to_json() const;
+};
+// is_passing_dual with everything it reports (src/hla/caller.rs:1225-1247); is_dual = false gives new_non_dual()
+DualPassingStats dual_passing_stats(bool is_dual, size_t counts1, size_t counts2, double min_consensus_fraction = 0.10,
+                                    double min_cdf = 0.001, double expected_maf = 0.45);
+
+// src/hla/caller.rs:1583-1653.  scores1 / scores2: per read, the edit distance to consensus 1 / 2 (nullopt = not
+// scored: the other score + dual_max_ed_delta is assumed, :1597-1599); is_consensus1: the read's assignment.  In the
+// north_star form the scores are the K1 columns D[r, allele1], D[r, allele2] of the called pair.
+bool is_hemizygous_better(const std::vector<std::optional<size_t>> &scores1, const std::vector<std::optional<size_t>> &scores2,
+                          const std::vector<bool> &is_consensus1, bool is_dual, size_t dual_max_ed_delta,
+                          std::optional<double> normalized_coverage);
 
 // ------------------------------------------------------------------------------------------
 // GPU: RAII view of the C ABI; every failure becomes HostError(sp_last_error)
@@ -236,10 +264,69 @@ struct DiplotypeSettings {  // the members of src/cli/diplotype.rs the path read
 // of standard_hifi_aligner (src/util/mapping.rs:8-14); b=4 q=6 e=2 q2=26 e2=1 in both
 long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match_score = 5);
 
-struct ScoreReadResult {  // score_read's (HashMap<String, HlaMappingStats>, ReadMappingStats::best_match)
+// ---- hla_debug.json (src/hla/debug.rs): the artefact to diff against a reference run with --debug-folder ----
+struct DetailedMappingStats {  // src/hla/debug.rs:135-183 (DetailedMappingStats::from_mapping)
+    size_t query_len = 0, target_len = 0, match_len = 0, nm = 0, query_unmapped = 0, target_unmapped = 0;
+    std::string cigar, md;
+    Json to_json() const;
+};
+// minimap2's cigar_str ("12=1X3I..") and MD string (format.c write_MD_core: match runs, mismatched / deleted target
+// bases) of an alignment of `query` (the pattern) inside `target` (the text)
+std::string cigar_string(const std::vector<std::pair<uint32_t, uint8_t>> &cigar);
+std::string md_string(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, const std::string &target, size_t target_start,
+                      const std::string &query, size_t query_start);
+DetailedMappingStats detailed_mapping_stats(const Mapping &m, const std::string &target, const std::string &query);
+
+struct PairedMappingStats {  // src/hla/debug.rs:126-132
+    std::optional<DetailedMappingStats> cdna_mapping, dna_mapping;
+    Json to_json() const;
+};
+class ReadMappingStats {  // src/hla/debug.rs:64-123
+  public:
+    void set_best_match(std::string id, std::string star) { best_match_id_ = std::move(id); best_match_star_ = std::move(star); }
+    const std::optional<std::string> &best_match_id() const { return best_match_id_; }
+    const std::optional<std::string> &best_match_star() const { return best_match_star_; }
+    const std::map<std::string, PairedMappingStats> &mapping_stats() const { return mapping_stats_; }
+    // throws HostError("Entry {hla_id} is already occupied!") like the reference bails
+    void add_mapping(const std::string &hla_id, std::optional<DetailedMappingStats> cdna, std::optional<DetailedMappingStats> dna);
+    Json to_json() const;
+
+  private:
+    std::optional<std::string> best_match_id_, best_match_star_;
+    std::map<std::string, PairedMappingStats> mapping_stats_;
+};
+class HlaDebug {  // src/hla/debug.rs:6-62
+  public:
+    void add_read(const std::string &gene, const std::string &qname, ReadMappingStats stats);
+    void add_dual_passing_stats(const std::string &gene, DualPassingStats stats);
+    Json to_json() const;
+    std::string pretty() const { return to_json().pretty(); }  // save_json, src/util/file_io.rs:37-52
+
+  private:
+    std::map<std::string, std::map<std::string, ReadMappingStats>> read_mapping_stats_;
+    std::optional<std::map<std::string, DualPassingStats>> dual_passing_stats_;
+};
+
+struct ScoreReadResult {  // score_read's (HashMap<String, HlaMappingStats>, ReadMappingStats)
     std::map<std::string, HlaMappingStats> stats;
     std::string best_hla_id, best_star_allele;
+    ReadMappingStats read_mapping_stats;  // keyed by star allele (all_hla_targets = true, src/hla/caller.rs:1397, :1473-1477)
 };
+
+// ---- what score_consensus / score_read do to a consensus before the allele loop ----
+// src/hla/caller.rs:1518-1576 on plain values: `sequence` aligned at reference position `pos` (0-based) with `cigar`
+// (BAM op codes: 0 M, 1 I, 2 D, 3 N, 4 S, 5 H, 7 =, 8 X); exons = half-open reference ranges in the gene
+// definition's order.  Returns (spliced bases, offset of the first covered exon base).
+std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                           const std::vector<std::pair<uint64_t, uint64_t>> &exons);
+std::string reverse_complement(const std::string &s);  // src/util/sequence.rs; throws on a non-ACGTN byte like the reference
+struct ScoreReadTargets {
+    std::string dna_target, cdna_target;
+};
+// src/hla/caller.rs:1337-1368: gene-strand DNA target and spliced cDNA target ("N" when nothing splices or cDNA scoring is off)
+ScoreReadTargets prepare_score_read_targets(const std::string &read_sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                            const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand,
+                                            const DiplotypeSettings &settings);
 // src/hla/caller.rs:1332-1511.  dna_target / cdna_target: the consensus on the gene's strand and its spliced cDNA
 // ("N" when empty), prepared by the host exactly as lines 1337-1368.
 ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const std::string &cdna_target, const HlaDatabase &database,

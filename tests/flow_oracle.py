@@ -63,6 +63,38 @@ def score_read(orc, dna_target: bytes, cdna_target: bytes, db: Sequence[DbRow], 
     return stats, best.haplotype, star
 
 
+def score_read_debug(orc, dna_target: bytes, cdna_target: bytes, db: Sequence[DbRow], gene: str, disable_cdna: bool = False) -> dict:
+    """The ReadMappingStats score_read returns next to the scores (src/hla/caller.rs:1397, :1464-1477, :1502-1509, src/hla/debug.rs):
+    per allele, keyed by star allele, the DetailedMappingStats of the best cDNA / DNA mapping."""
+    per_allele, best = {}, so.HlaProcessedMatch.worst_match(2)
+    for hla_id, _, star, dna, cdna in allowed_alleles(db, gene):
+        cur, detail = so.HlaProcessedMatch(hla_id), []
+        for target, seq in ((cdna_target, None if disable_cdna else cdna), (dna_target, dna)):
+            m = None
+            if seq is not None:
+                cand = mapping_from_alignment(orc.align(seq.encode(), target), len(seq), len(target))
+                idx, _ = so.select_best_mapping([cand] if cand else [], False, True)
+                m = cand if idx is not None else None
+            cur.add_mapping(m)
+            detail.append(None if m is None else so.detailed_mapping_stats(m, target, seq.encode()))
+        key = ":".join(star)
+        if key in per_allele:
+            raise ValueError(f"Entry {key} is already occupied!")
+        per_allele[key] = tuple(detail)
+        if cur.is_better_match(best):
+            best = cur
+    best_id = best.haplotype or None
+    best_star = ":".join(next(r[2] for r in db if r[0] == best_id)) if best_id else None
+    return so.read_mapping_stats_json(best_id, best_star, per_allele)
+
+
+def hla_debug_json(orc, db: Sequence[DbRow], gene: str, consensuses: Sequence[Tuple[str, bytes, bytes]], is_dual: bool, counts1: int,
+                   counts2: int) -> str:
+    """hla_debug.json of one gene as diplotype_hla_batch fills it (src/hla/caller.rs:805, :877, :914)."""
+    reads = {gene: {q: score_read_debug(orc, d, c, db, gene) for q, d, c in consensuses}}
+    return so.hla_debug_json(reads, {gene: so.dual_passing_stats(is_dual, counts1, counts2)})
+
+
 def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5,
                     D: Optional[np.ndarray] = None) -> List[dict]:
     """src/hla/realigner.rs:98-211: candidates = the n best alleles by distance (ties by database order)."""

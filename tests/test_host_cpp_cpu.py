@@ -252,3 +252,138 @@ def test_no_gpu_is_an_error(host):
 def test_dp_score(host):
     assert host.dp_score([(40, 7)]) == 200 and host.dp_score([(10, 7), (1, 8), (10, 7)]) == 96
     assert host.dp_score([(50, 7), (1, 1), (50, 7)]) == 500 - 8 and host.dp_score([(50, 7), (30, 2), (50, 7)]) == 500 - 56
+
+
+# ---- hla_debug.json pieces, consensus preparation, hemizygous test (pb_starphase_b200/host/sp_host_debug.cpp) ----
+def test_json_f64_matches_ryu_layout(host):
+    known = {0.1: "0.1", 1e-5: "0.00001", 1e-6: "1e-6", 1.0: "1.0", 1e15: "1000000000000000.0", 1e16: "1e16", 0.45: "0.45",
+             123456.789: "123456.789", 1.5e-7: "1.5e-7", 1 / 3: "0.3333333333333333", 1.2345678901234568e17: "1.2345678901234568e17",
+             5e-324: "5e-324", -2.5: "-2.5", 0.0: "0.0", float("nan"): "null", float("inf"): "null"}
+    for v, text in known.items():
+        assert host.json_f64(v) == text == so.format_f64(v)
+    rnd = random.Random(11)
+    import struct
+
+    for _ in range(20000):
+        v = struct.unpack("d", struct.pack("Q", rnd.getrandbits(64)))[0] if rnd.random() < 0.5 else rnd.uniform(-10, 10) * 10 ** rnd.randint(-8, 20)
+        assert host.json_f64(v) == so.format_f64(v)
+
+
+def test_is_hemizygous_better_reference_vectors(host):  # src/hla/caller.rs:1847-1899
+    def run(c1, c2, nc, delta):
+        ic = [True] * c1 + [False] * c2
+        s1, s2 = [0] * c1 + [delta] * c2, [delta] * c1 + [0] * c2
+        a = host.is_hemizygous_better(s1, s2, ic, c2 != 0, 20, nc)
+        assert a == so.is_hemizygous_better(s1, s2, ic, c2 != 0, 20, nc)
+        return a
+
+    assert run(20, 0, 20.0, 1)
+    assert not run(40, 0, 20.0, 1)
+    assert run(18, 2, 20.0, 1)
+    assert not run(18, 17, 20.0, 1)
+    assert not run(15, 6, 20.0, 20)
+    # unscored reads take the other score + dual_max_ed_delta (:1597-1599); no coverage -> read count
+    rnd = random.Random(5)
+    for _ in range(300):
+        n = rnd.randint(1, 60)
+        s1 = [rnd.choice([None, rnd.randint(0, 40)]) for _ in range(n)]
+        s2 = [rnd.randint(0, 40) if a is None or rnd.random() < 0.8 else None for a in s1]
+        ic = [rnd.random() < 0.6 for _ in range(n)]
+        nc = rnd.choice([None, rnd.uniform(5, 60)])
+        dual = rnd.random() < 0.8
+        assert host.is_hemizygous_better(s1, s2, ic, dual, 20, nc) == so.is_hemizygous_better(s1, s2, ic, dual, 20, nc)
+    with pytest.raises(host.HostError, match="Bad distribution parameters"):
+        host.is_hemizygous_better([], [], [], False, 20, None)
+
+
+def test_dual_passing_stats(host):  # src/hla/caller.rs:1225-1247, tests :1837-1845
+    import json
+
+    for c1, c2, passing in ((3, 20, False), (20, 3, False), (10, 20, True), (20, 10, True)):
+        got = json.loads(host.dual_passing_stats_json(True, c1, c2, expected_maf=0.5))  # the settings of run_passing_test (:1812-1817)
+        want = so.dual_passing_stats(True, c1, c2, expected_maf=0.5)
+        assert got["is_passing"] is passing is want["is_passing"]
+        assert (got["counts1"], got["counts2"], got["maf"], got["is_dual"]) == (c1, c2, want["maf"], True)
+        assert got["cdf"] == pytest.approx(want["cdf"], rel=1e-12)  # statrs' beta_reg vs the exact rational sum
+    assert host.dual_passing_stats_json(False, 0, 0) == so.serde_pretty(so.dual_passing_stats(False))
+    rnd = random.Random(9)
+    for _ in range(150):  # beta_reg (continued fraction) against the exact sum
+        n = rnd.randint(1, 200)
+        k = rnd.randint(0, n)
+        p = rnd.choice([0.45, 0.5, rnd.uniform(0.01, 0.99)])
+        assert host.binomial_cdf(n, p, k) == pytest.approx(so.binomial_cdf(n, p, k), rel=1e-10, abs=1e-300)
+
+
+def test_reverse_complement(host):  # src/util/sequence.rs:25-36
+    assert host.reverse_complement("ACCGGGTN") == "NACCCGGT" == so.reverse_complement(b"ACCGGGTN").decode()
+    with pytest.raises(host.HostError, match="Unexpected character for reverse-complement: 97"):
+        host.reverse_complement("ACa")
+
+
+def test_cigar_and_md_strings(host):
+    #            target  ACGTACGTAC  query ACGAACTTTGTAC: 3= 1X 2= 3I(TTT) 1= ... built by hand below
+    target, query = "GGACGTACGTACGG", "ACGAACTTTGAC"
+    cigar = [(3, 7), (1, 8), (2, 7), (3, 1), (1, 7), (1, 2), (2, 7)]  # ACG A AC [TTT] G ^T AC
+    assert host.cigar_string(cigar) == "3=1X2=3I1=1D2=" == so.cigar_string(cigar)
+    assert host.md_string(cigar, target, 2, query, 0) == "3T3^T2" == so.md_string(cigar, target.encode(), 2, query.encode(), 0)
+    assert host.md_string([(4, 7)], "ACGT", 0, "ACGT", 0) == "4"
+    assert host.md_string([(1, 8), (3, 7)], "ACGT", 0, "TCGT", 0) == "0A3"
+    assert host.md_string([(3, 7), (1, 8)], "ACGT", 0, "ACGA", 0) == "3T"       # no trailing zero (write_MD_core)
+    assert host.md_string([(2, 2), (2, 7)], "ACGT", 0, "GT", 0) == "0^AC2"
+    rnd = random.Random(4)
+    for _ in range(300):
+        t = "".join(rnd.choice("ACGTN") for _ in range(60))
+        cig, ti, q = [], 5, []
+        for _ in range(rnd.randint(1, 8)):
+            op = rnd.choice([7, 8, 1, 2])
+            ln = rnd.randint(1, 5)
+            if ti + ln > 55:
+                break
+            if op == 7:
+                q.append(t[ti:ti + ln]); ti += ln
+            elif op == 8:
+                q.append("".join(rnd.choice([c for c in "ACGT" if c != x]) for x in t[ti:ti + ln])); ti += ln
+            elif op == 1:
+                q.append("".join(rnd.choice("ACGT") for _ in range(ln)))
+            else:
+                ti += ln
+            cig.append((ln, op))
+        qs = "xx" + "".join(q)
+        assert host.md_string(cig, t, 5, qs, 2) == so.md_string(cig, t.encode(), 5, qs.encode(), 2)
+
+
+def test_splice_read(host):  # src/hla/caller.rs:1518-1576
+    seq = "AAAACCCCGGGGTTTTACGTACGT"
+    # read starts at reference 100: 4 soft-clipped, 8 aligned (100..108), 2 inserted, 3 deleted (108..111), 10 aligned (111..121)
+    cigar = [(4, 4), (8, 0), (2, 1), (3, 2), (10, 7)]
+    exons = [(90, 104), (106, 112), (118, 130), (200, 210)]
+    got = host.splice_read(seq, 100, cigar, exons)
+    want = so.splice_read(seq.encode(), 100, cigar, exons)
+    assert got == (want[0].decode(), want[1])
+    # exon 1 covers reference 100..103 -> read 4..7; exon 2 covers 106, 107 and 111 (108..110 deleted) -> read 10..14 (spans the insertion);
+    # exon 3 covers 118..120 -> read 21..23; exon 4 is not covered; offset = 100 - 90
+    assert got == (seq[4:8] + seq[10:15] + seq[21:24], 10)
+    assert host.splice_read(seq, 100, cigar, [(300, 310)]) == ("", 10)
+    s = host.DiplotypeSettings()
+    assert host.prepare_score_read_targets(seq, 100, cigar, exons, True, s) == (seq, got[0])
+    assert host.prepare_score_read_targets(seq, 100, cigar, exons, False, s) == (host.reverse_complement(seq), host.reverse_complement(got[0]))
+    assert host.prepare_score_read_targets(seq, 100, cigar, [(300, 310)], False, s)[1] == "N"
+    s.disable_cdna_scoring = True
+    assert host.prepare_score_read_targets(seq, 100, cigar, exons, True, s)[1] == "N"
+    rnd = random.Random(8)
+    for _ in range(200):
+        cig, qlen = [], 0
+        for _ in range(rnd.randint(1, 7)):
+            op = rnd.choice([0, 1, 2, 3, 4, 7, 8])
+            ln = rnd.randint(1, 9)
+            cig.append((ln, op))
+            qlen += ln if op in (0, 1, 4, 7, 8) else 0
+        sq = "".join(rnd.choice("ACGT") for _ in range(qlen))
+        ex, p = [], 40
+        for _ in range(rnd.randint(1, 4)):
+            p += rnd.randint(0, 12)
+            e = p + rnd.randint(1, 15)
+            ex.append((p, e))
+            p = e
+        w = so.splice_read(sq.encode(), 50, cig, ex)
+        assert host.splice_read(sq, 50, cig, ex) == (w[0].decode(), w[1])
