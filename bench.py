@@ -33,6 +33,9 @@ INT_OPS_PER_CELL = 23.0 / 64.0  # Hyyro block step = 23 INT32-
 TOPK = 16
 
 
+K1_DNA_DRAM_BYTES_PER_STEP = 167551829  # profiles/r01e_k1_traffic.csv
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -528,7 +531,12 @@ def run_ours(args):
                           peak_alu_pipe_only=int_peak / 1e12, frac_alu_pipe_only=achieved / int_peak,
                           note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one, ~97 % busy in ncu) and 6 "
                                "as IMAD on the FMA pipe, so the algorithmic count can exceed the ALU-pipe-only peak (DESIGN.md 4.1)",
-                          k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12, traffic=None,
+                          k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12,
+                          # dram__bytes_read.sum + dram__bytes_write.sum of the DNA launches of one step (ncu, B200, this workload at N = 1,
+                          # scale 1.0: profiles/r01e_k1_traffic.csv, mean of 3 steps; lts__t_bytes.sum = 12.9 GB: the per-item blob / text
+                          # re-reads are served by L2); not measured for other shapes
+                          traffic=(K1_DNA_DRAM_BYTES_PER_STEP if world == 1 and args.scale == 1.0 else None),
+                          traffic_unit="bytes per step (both DNA launches), algorithmic bytes = %d" % hbm_bytes,
                           hbm=dict(achieved=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
                                    frac=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9 / hbm_peak,
                                    peak_source="MEASURED_PEAKS.json" if peaks else "fallback")),

@@ -91,13 +91,14 @@ __device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
+__global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
     constexpr int U = ALN_U;
     constexpr int BW = blob_words(U);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *blob = reinterpret_cast<uint32_t *>(smem_raw) + warp * BW;
-    const int slot = blockIdx.x * K1_WARPS + warp, n_slots = gridDim.x * K1_WARPS;
+    const int warps_per_cta = blockDim.x >> 5;  // the host spreads the slots over all SMs: 1..K1_WARPS warps per CTA
+    const int slot = blockIdx.x * warps_per_cta + warp, n_slots = gridDim.x * warps_per_cta;
     uint32_t *scr = p.scratch + static_cast<size_t>(slot) * p.slot_words;
     int cur_blob = -1;
     for (int q = slot; q < p.n_pairs; q += n_slots) {
@@ -126,11 +127,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k4_align(const AlignParams p) {
         const uint8_t *T = p.tbases + p.toffs[t];
         const int n = static_cast<int>(p.toffs[t + 1] - p.toffs[t]);
         int best, best_col;
-        k4_forward<false>(blob, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
         const int src_lane = __ffs(__ballot_sync(0xffffffffu, last)) - 1;
-        const int d = __shfl_sync(0xffffffffu, best, src_lane), e = __shfl_sync(0xffffffffu, best_col, src_lane);
-        const int w0 = max(0, e - (m_all + d)), ncols = e - w0;
-        k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
+        int d, e, w0, ncols;
+        if (n <= 2 * m_all) {
+            // the whole text fits the pair's scratch slot (the host sizes it for min(n, 2m) columns): one pass that both
+            // finds (d, e) and keeps the columns -- the consensus-sized texts of score_read and the placement windows of
+            // the template search take this path
+            k4_forward<true>(blob, T, n, p, first, owns, m, best, best_col, scr, Wp, wf4);
+            d = __shfl_sync(0xffffffffu, best, src_lane); e = __shfl_sync(0xffffffffu, best_col, src_lane);
+            w0 = 0; ncols = e;
+        } else {
+            k4_forward<false>(blob, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
+            d = __shfl_sync(0xffffffffu, best, src_lane); e = __shfl_sync(0xffffffffu, best_col, src_lane);
+            w0 = max(0, e - (m_all + d)); ncols = e - w0;
+            k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
+        }
         __threadfence_block();
         __syncwarp();
         {

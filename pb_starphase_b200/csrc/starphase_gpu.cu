@@ -991,12 +991,17 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     }
     max_slot_words = (max_slot_words + 3) / 4 * 4;
     tm.mark("gather + plan");
-    // one scratch slot per resident warp, capped at 4 GB in total (the context's grow-only scratch: no malloc / free per call)
+    // one scratch slot per warp in flight (the context's grow-only scratch: no malloc / free per call), capped at a quarter of
+    // the free HBM and 16 GB; the slots are spread over all SMs, 1..K1_WARPS warps per CTA
     int64_t n_slots = std::min<int64_t>(n_pairs, 2ll * ctx->num_sms * K1_WARPS);
-    const int64_t budget_words = (4ll << 30) / 4;
+    size_t free_b = 0, total_b = 0;
+    SP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const int64_t budget_bytes = std::max<int64_t>(4ll << 30, std::min<int64_t>(16ll << 30, static_cast<int64_t>((free_b + ctx->pool_bytes[0]) / 4)));
+    const int64_t budget_words = budget_bytes / 4;
     n_slots = std::max<int64_t>(1, std::min(n_slots, budget_words / max_slot_words));
     if (max_slot_words > (24ll << 30) / 4) return fail(ctx, SP_ERR_NOMEM, "sp_align_pairs: traceback scratch of one pair exceeds 24 GB");
-    const int grid = static_cast<int>((n_slots + K1_WARPS - 1) / K1_WARPS);
+    const int warps_per_cta = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(K1_WARPS, (n_slots + ctx->num_sms - 1) / ctx->num_sms)));
+    const int grid = static_cast<int>((n_slots + warps_per_cta - 1) / warps_per_cta);
 
     sp_seqset tset = {tb.data(), to.data(), static_cast<int64_t>(t_ids.size())};
     sp_seqset pset = {pbs.data(), po.data(), np};
@@ -1050,7 +1055,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     SP_TRY(cu(ctx_pool(ctx, 2, static_cast<size_t>(np) * blob_words(ALN_U) * 4, reinterpret_cast<void **>(&d_blobs)), "blob pool"));
     SP_TRY(cu(ctx_pool(ctx, 1, static_cast<size_t>(cig_off.back()) * 4, reinterpret_cast<void **>(&d_cigar)), "cigar pool"));
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_recs), static_cast<size_t>(n_pairs) * sizeof(AlignRecDev)), "cudaMalloc recs"));
-    SP_TRY(cu(ctx_scratch(ctx, static_cast<size_t>(grid) * K1_WARPS * max_slot_words * 4, reinterpret_cast<void **>(&d_scratch)),
+    SP_TRY(cu(ctx_scratch(ctx, static_cast<size_t>(grid) * warps_per_cta * max_slot_words * 4, reinterpret_cast<void **>(&d_scratch)),
               "traceback scratch"));
     tm.mark("upload + cudaMalloc");
     {
@@ -1065,10 +1070,10 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         prm.blobs = d_blobs; prm.tbases = d_tb; prm.toffs = d_to; prm.pair_t = d_pt; prm.pair_p = d_pp;
         prm.cig_off = d_cig_off; prm.cigar = d_cigar; prm.scratch = d_scratch; prm.slot_words = max_slot_words;
         prm.recs = d_recs; prm.n_pairs = static_cast<int>(n_pairs); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
-        const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(ALN_U) * 4;
-        SP_TRY(cu(cudaFuncSetAttribute(k4_align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "k4_align smem"));
+        const size_t smem = static_cast<size_t>(warps_per_cta) * blob_words(ALN_U) * 4;
+        SP_TRY(cu(cudaFuncSetAttribute(k4_align, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_WARPS * blob_words(ALN_U) * 4), "k4_align smem"));
         ev_begin(ctx, 4);
-        k4_align<<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        k4_align<<<grid, 32 * warps_per_cta, smem, ctx->stream>>>(prm);
         ev_end(ctx, 4);
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "k4_align launch"));

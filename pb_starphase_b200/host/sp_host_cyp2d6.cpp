@@ -5,6 +5,10 @@
 #include <numeric>
 #include <tuple>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "starphase_host.hpp"
 
 namespace starphase {
@@ -220,6 +224,15 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
     for (size_t s = 0; s < seqs.size(); ++s)
         if (!seqs[s].empty())  // :148-151
             for (size_t t = 0; t < nt; ++t) items.push_back({s, 0, seqs[s].size(), t});
+    const bool timing = getenv("SP_TIMING") != nullptr;  // diagnostic only: wall-clock phases to stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what, int round, size_t n) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sp_timing] template search round %d %-18s %8.2f ms (%zu)\n", round, what,
+                std::chrono::duration<double, std::milli>(t1 - t_prev).count(), n);
+        t_prev = t1;
+    };
     for (int round = 0; round < 5 && !items.empty(); ++round) {
         std::map<std::tuple<size_t, size_t, size_t>, size_t> seg_index;  // (seq, lo, hi) -> row of the K1 matrix
         SeqList seg_texts;
@@ -227,8 +240,10 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const auto key = std::make_tuple(it.seq, it.lo, it.hi);
             if (seg_index.emplace(key, seg_texts.size()).second) seg_texts.push_back(seqs[it.seq].substr(it.lo, it.hi - it.lo));
         }
+        mark("segments", round, seg_texts.size());
         std::vector<int32_t> E;
         const std::vector<int32_t> D = gpu_.score_batch(seg_texts, tmpl_seqs, &E);
+        mark("K1 score_batch", round, items.size());
         SeqList texts;
         std::vector<std::pair<int32_t, int32_t>> pairs;
         std::vector<Item> pair_item;
@@ -244,7 +259,9 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             pair_item.push_back(it);
             pair_off.push_back(it.lo + w0);
         }
+        mark("windows", round, pairs.size());
         const std::vector<Alignment> alns = gpu_.align_pairs(texts, tmpl_seqs, pairs);
+        mark("K4 align_pairs", round, pairs.size());
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {
             const Alignment &a = alns[q];
@@ -264,6 +281,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             if (it.hi > he && it.hi - he >= std::max<size_t>(min_len, 200)) next.push_back({it.seq, he, it.hi, it.tmpl});
         }
         items = std::move(next);
+        mark("accept", round, items.size());
     }
 
     std::vector<std::vector<AlleleMapping>> out(seqs.size());
