@@ -212,6 +212,16 @@ sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
  * these candidates go on to sp_align_pairs, and R x k records cross PCIe instead of the R x A matrix. */
 sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist);
 
+/* ---- K6: CYP2D6 allele-vector match (row N3 of SURVEY.md 8f) ------------------------------- */
+/* Replaces the haplotype loop of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:470-517): for every
+ * (sequence s, haplotype h) the number of variant sites whose observed state agrees with the haplotype definition,
+ * over all sites (all_match) and over the VI sites only (vi_match).  seq_alleles[s][v]: 0 = REF, 1 = ALT,
+ * 2 = ambiguous (agrees with anything), 3 = unset (agrees with nothing); hap_alleles[h][v]: 0 / 1; is_vi[v]: 0 / 1.
+ * Other values fail with SP_ERR_INVALID (the reference panics on them, :489, :496).  Outputs are [n_seq][n_hap]
+ * row-major.  The host keeps the reference's (vi_match, all_match) arg-max and its tie handling. */
+sp_status sp_variant_match(sp_ctx *ctx, int64_t n_seq, int64_t n_hap, int64_t n_var, const uint8_t *seq_alleles,
+                           const uint8_t *hap_alleles, const uint8_t *is_vi, uint32_t *vi_match, uint32_t *all_match);
+
 /* ---- K2: pair scoring -------------------------------------------------------------------- */
 /* S[i,j] = sum_r min(D[r,i], D[r,j]) for i in [i_begin, i_end), j in [i, n_patterns);
  * d2 (may be NULL) is a secondary matrix of the same geometry giving S2 the same way;

@@ -1089,3 +1089,72 @@ def is_hemizygous_better(scores1: Sequence[Optional[int]], scores2: Sequence[Opt
     nc_dip = 2.0 * nc_hap
     diploid_cost = balance + abs(normal_ln_pdf(nc_dip, nc_dev, float(read_count)))
     return haploid_cost < diploid_cost
+
+
+# ==========================================================================================
+# CYP2D6 allele-vector typing -- src/cyp2d6/haplotyper.rs:452-601 (the in-tree half of assign_haplotype; the WFA graph
+# traversal that produces `traversed nodes` is hiphase / waffle_con code and not restated)
+# ==========================================================================================
+def alleles_from_traversal(num_variants: int, traversed_nodes: Sequence[int], node_to_alleles: Dict[int, List[Tuple[int, int]]]) -> List[int]:
+    """:454-468: 3 = unset, first assignment wins, a conflicting second one turns the site into 2 (ambiguous)."""
+    alleles = [3] * num_variants
+    for node in traversed_nodes:
+        for var_index, assignment in node_to_alleles.get(node, []):
+            if alleles[var_index] == 3:
+                alleles[var_index] = assignment
+            elif alleles[var_index] != assignment:
+                alleles[var_index] = 2
+    return alleles
+
+
+def variant_match(alleles: Sequence[int], hap: Sequence[int], is_vi: Sequence[bool]) -> Tuple[int, int]:
+    """:475-506: (vi_match, all_match) of one observed vector against one haplotype definition."""
+    assert len(alleles) == len(hap)
+    vi_match = all_match = 0
+    for i, (sv, hv) in enumerate(zip(alleles, hap)):
+        assert hv in (0, 1)
+        if sv in (0, 1):
+            ok = hv == sv
+        elif sv == 2:
+            ok = True
+        elif sv == 3:
+            ok = False
+        else:
+            raise ValueError(f"Unexpected seq_value={sv}")
+        if ok:
+            all_match += 1
+            if is_vi[i]:
+                vi_match += 1
+    return vi_match, all_match
+
+
+_VARIANT_STATE = {(0, 0): "Match", (0, 1): "Unexpected", (0, 2): "AmbiguousUnexpected", (0, 3): "UnknownUnexpected",
+                  (1, 0): "Missing", (1, 1): "Match", (1, 2): "AmbiguousMissing", (1, 3): "UnknownMissing"}
+
+
+def assign_haplotype_from_alleles(alleles: Sequence[int], haplotype_lookup: Dict[str, Sequence[int]], labels: Sequence[str],
+                                  is_vi: Sequence[bool], force_assignment: bool):
+    """:470-601 for star alleles `haplotype_lookup` (key = the subtype label of a Cyp2d6 region label; BTreeMap order =
+    bytewise key order).  Returns (best star allele or None for Unknown, region variants or None, best (vi, all) score)."""
+    best_set, best_score = {None}, (0, 0)
+    for star in sorted(haplotype_lookup, key=lambda x: x.encode()):
+        score = variant_match(alleles, haplotype_lookup[star], is_vi)
+        if score > best_score:
+            best_set, best_score = {star}, score
+        elif score == best_score:
+            best_set.add(star)
+    if len(best_set) == 1:
+        best = next(iter(best_set))
+    else:
+        # full_allele(): "Unknown" for the initial entry, "CYP2D6*{star}" for star alleles (src/cyp2d6/region_label.rs:140-168)
+        ordered = sorted(best_set, key=lambda x: (RegionLabel(UNKNOWN) if x is None else RegionLabel(CYP2D6, x)).full_allele().encode())
+        best = ordered[0] if force_assignment else None
+    if best is None:
+        return None, None, best_score
+    rv = []
+    for i, (sv, hv) in enumerate(zip(alleles, haplotype_lookup[best])):
+        state = _VARIANT_STATE[(hv, sv)]
+        if state == "Match" and hv == 0:
+            continue
+        rv.append(dict(label=labels[i], is_vi=bool(is_vi[i]), variant_state=state))
+    return best, rv, best_score

@@ -78,6 +78,7 @@ SIGNATURES = {
     "sp_align_pairs": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                  C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "sp_variant_match": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sp_chain_window_scores": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(_P)]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
@@ -246,6 +247,20 @@ class Context:
         dist = np.zeros((d.n_targets, k), dtype=np.int32)
         self._check(self._lib.sp_row_topk(self._h, d._h, k, idx.ctypes.data, dist.ctypes.data))
         return idx, dist
+
+    def variant_match(self, seq_alleles, hap_alleles, is_vi):
+        """K6: (vi_match, all_match), each [n_seq, n_hap] uint32, for site-state rows seq_alleles [n_seq, n_var] (0 REF, 1 ALT,
+        2 ambiguous, 3 unset), haplotype definitions hap_alleles [n_hap, n_var] (0 / 1) and the VI flags is_vi [n_var]."""
+        sa = np.ascontiguousarray(seq_alleles, dtype=np.uint8)
+        ha = np.ascontiguousarray(hap_alleles, dtype=np.uint8)
+        vi = np.ascontiguousarray(is_vi, dtype=np.uint8)
+        if sa.ndim != 2 or ha.ndim != 2 or vi.ndim != 1 or sa.shape[1] != vi.shape[0] or ha.shape[1] != vi.shape[0]:
+            raise ValueError("variant_match: expected [n_seq, n_var], [n_hap, n_var], [n_var]")
+        vm = np.zeros((sa.shape[0], ha.shape[0]), dtype=np.uint32)
+        am = np.zeros((sa.shape[0], ha.shape[0]), dtype=np.uint32)
+        self._check(self._lib.sp_variant_match(self._h, sa.shape[0], ha.shape[0], vi.shape[0], sa.ctypes.data, ha.ctypes.data,
+                                               vi.ctypes.data, vm.ctypes.data, am.ctypes.data))
+        return vm, am
 
     def chain_window_scores(self, chains, read_weights, n_haps: int) -> "DMatrix":
         """K3 chain windows.  chains: list of lists of haplotype indices; read_weights: per read an array

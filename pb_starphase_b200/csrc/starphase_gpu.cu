@@ -1144,6 +1144,78 @@ extern "C" sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_
 }
 
 // ------------------------------------------------------------------------------------------
+// K6: allele-vector match
+// ------------------------------------------------------------------------------------------
+extern "C" sp_status sp_variant_match(sp_ctx *ctx, int64_t n_seq, int64_t n_hap, int64_t n_var, const uint8_t *seq_alleles,
+                                      const uint8_t *hap_alleles, const uint8_t *is_vi, uint32_t *vi_match, uint32_t *all_match) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (n_seq < 0 || n_hap < 0 || n_var < 0) return fail(ctx, SP_ERR_INVALID, "sp_variant_match: negative size");
+    if (n_seq * n_hap > 0 && (!vi_match || !all_match)) return fail(ctx, SP_ERR_INVALID, "sp_variant_match: NULL output");
+    if (n_var > 0 && ((n_seq > 0 && !seq_alleles) || (n_hap > 0 && !hap_alleles) || !is_vi))
+        return fail(ctx, SP_ERR_INVALID, "sp_variant_match: NULL input");
+    if (n_seq > 0x3FFFFFFFll || n_hap > 0x3FFFFFFFll || n_var > 0x3FFFFFFFll || n_seq * n_hap > 0x7FFFFFFF0ll)
+        return fail(ctx, SP_ERR_RANGE, "sp_variant_match: problem too large");
+    if (n_seq == 0 || n_hap == 0) return SP_OK;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = static_cast<int>((n_var + 31) / 32);
+    const size_t cells = static_cast<size_t>(n_seq) * static_cast<size_t>(n_hap);
+    if (W == 0) {  // no sites: nothing matches
+        std::fill(vi_match, vi_match + cells, 0u);
+        std::fill(all_match, all_match + cells, 0u);
+        return SP_OK;
+    }
+    uint8_t *d_seq = nullptr, *d_hap = nullptr, *d_vi = nullptr;
+    uint32_t *d_sp = nullptr, *d_hp = nullptr, *d_vp = nullptr, *d_out = nullptr;
+    int *d_bad = nullptr;
+    auto cleanup = [&]() {
+        dev_free(ctx, d_seq); dev_free(ctx, d_hap); dev_free(ctx, d_vi); dev_free(ctx, d_sp); dev_free(ctx, d_hp); dev_free(ctx, d_vp);
+        dev_free(ctx, d_out); dev_free(ctx, d_bad);
+    };
+    auto cu = [&](cudaError_t e, const char *what) -> sp_status {
+        if (e != cudaSuccess)
+            return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA,
+                        std::string("sp_variant_match: ") + what + ": " + cudaGetErrorString(e));
+        return SP_OK;
+    };
+#define SP_TRY(x)                                   \
+    do {                                            \
+        sp_status s__ = (x);                        \
+        if (s__ != SP_OK) { cleanup(); return s__; } \
+    } while (0)
+    auto up = [&](uint8_t **dst, const uint8_t *src, size_t bytes) -> sp_status {
+        sp_status st = cu(dev_malloc(ctx, dst, bytes), "cudaMalloc");
+        if (st == SP_OK) st = cu(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        return st;
+    };
+    SP_TRY(up(&d_seq, seq_alleles, static_cast<size_t>(n_seq) * n_var));
+    SP_TRY(up(&d_hap, hap_alleles, static_cast<size_t>(n_hap) * n_var));
+    SP_TRY(up(&d_vi, is_vi, static_cast<size_t>(n_var)));
+    SP_TRY(cu(dev_malloc(ctx, &d_sp, static_cast<size_t>(n_seq) * 3 * W * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, &d_hp, static_cast<size_t>(n_hap) * 2 * W * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, &d_vp, static_cast<size_t>(2) * W * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, &d_out, 2 * cells * 4), "cudaMalloc"));
+    SP_TRY(cu(dev_malloc(ctx, &d_bad, sizeof(int)), "cudaMalloc"));
+    SP_TRY(cu(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream), "memset"));
+    const int nv = static_cast<int>(n_var);
+    k6_pack_states<<<static_cast<unsigned>((n_seq + 7) / 8), 256, 0, ctx->stream>>>(d_seq, static_cast<int>(n_seq), nv, W, 3, 3, d_sp, d_bad);
+    k6_pack_states<<<static_cast<unsigned>((n_hap + 7) / 8), 256, 0, ctx->stream>>>(d_hap, static_cast<int>(n_hap), nv, W, 2, 1, d_hp, d_bad);
+    k6_pack_states<<<1, 256, 0, ctx->stream>>>(d_vi, 1, nv, W, 2, 1, d_vp, d_bad);
+    k6_variant_match<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, ctx->stream>>>(d_sp, d_hp, d_vp, static_cast<int>(n_seq),
+                                                                                        static_cast<int>(n_hap), W, d_out, d_out + cells);
+    ctx->launches += 4;
+    SP_TRY(cu(cudaGetLastError(), "k6 launch"));
+    int bad = 0;
+    SP_TRY(cu(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H"));
+    SP_TRY(cu(cudaMemcpyAsync(vi_match, d_out, cells * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H"));
+    SP_TRY(cu(cudaMemcpyAsync(all_match, d_out + cells, cells * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H"));
+    SP_TRY(cu(cudaStreamSynchronize(ctx->stream), "k6_variant_match"));
+#undef SP_TRY
+    cleanup();
+    if (bad) return fail(ctx, SP_ERR_INVALID, "sp_variant_match: site state outside 0..3 (sequences) or 0..1 (haplotypes, is_vi)");
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // K3 chain windows
 // ------------------------------------------------------------------------------------------
 extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const int32_t *chain_off,

@@ -318,6 +318,99 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
 }
 
 // ------------------------------------------------------------------------------------------
+// allele-vector typing (src/cyp2d6/haplotyper.rs:452-601)
+// ------------------------------------------------------------------------------------------
+const char *variant_state_name(VariantAlleleRelationship v) {
+    switch (v) {
+        case VariantAlleleRelationship::Unknown: return "Unknown";
+        case VariantAlleleRelationship::Match: return "Match";
+        case VariantAlleleRelationship::Unexpected: return "Unexpected";
+        case VariantAlleleRelationship::Missing: return "Missing";
+        case VariantAlleleRelationship::AmbiguousUnexpected: return "AmbiguousUnexpected";
+        case VariantAlleleRelationship::AmbiguousMissing: return "AmbiguousMissing";
+        case VariantAlleleRelationship::UnknownUnexpected: return "UnknownUnexpected";
+        case VariantAlleleRelationship::UnknownMissing: return "UnknownMissing";
+    }
+    return "Unknown";
+}
+
+Json RegionVariant::to_json() const {
+    Json j = Json::object();
+    j.set("label", label).set("is_vi", is_vi).set("variant_state", variant_state_name(variant_state));
+    return j;
+}
+
+std::vector<uint8_t> alleles_from_traversal(size_t num_variants, const std::vector<size_t> &traversed_nodes,
+                                            const std::map<size_t, std::vector<std::pair<size_t, uint8_t>>> &node_to_alleles) {
+    std::vector<uint8_t> alleles(num_variants, 3);
+    for (size_t node : traversed_nodes) {
+        const auto it = node_to_alleles.find(node);
+        if (it == node_to_alleles.end()) continue;
+        for (const auto &va : it->second) {
+            if (va.first >= num_variants) throw HostError("index out of bounds: variant index " + std::to_string(va.first));
+            if (alleles[va.first] == 3) alleles[va.first] = va.second;
+            else if (alleles[va.first] != va.second) alleles[va.first] = 2;
+        }
+    }
+    return alleles;
+}
+
+std::vector<HaplotypeAssignment> assign_haplotypes_from_alleles(GpuAligner &gpu, const std::vector<std::vector<uint8_t>> &alleles,
+                                                                const std::map<std::string, std::vector<uint8_t>> &haplotype_lookup,
+                                                                const std::vector<VariantMetadata> &variants, bool force_assignment) {
+    const size_t nv = variants.size(), nh = haplotype_lookup.size();
+    std::vector<std::vector<uint8_t>> haps;
+    std::vector<const std::string *> stars;  // BTreeMap<Cyp2d6RegionLabel, _> order: all keys are (Cyp2d6, Some(star)) -> bytewise by star
+    for (const auto &kv : haplotype_lookup) { stars.push_back(&kv.first); haps.push_back(kv.second); }
+    std::vector<uint8_t> is_vi(nv);
+    for (size_t v = 0; v < nv; ++v) is_vi[v] = variants[v].is_vi ? 1 : 0;
+    for (const auto &a : alleles)
+        if (a.size() != nv) throw HostError("assertion `left == right` failed: alleles.len() vs haplotype_vec.len()");
+    std::vector<uint32_t> vi_match, all_match;
+    gpu.variant_match(alleles, haps, is_vi, vi_match, all_match);  // K6
+
+    std::vector<HaplotypeAssignment> out(alleles.size());
+    for (size_t s = 0; s < alleles.size(); ++s) {
+        // :471-517: start from {Unknown} at (0, 0); strictly greater replaces, equal joins the set
+        std::vector<int> best_set = {-1};  // -1 = the Unknown label
+        std::pair<size_t, size_t> best_score(0, 0);
+        for (size_t h = 0; h < nh; ++h) {
+            const std::pair<size_t, size_t> score(vi_match[s * nh + h], all_match[s * nh + h]);
+            if (score > best_score) { best_set.assign(1, static_cast<int>(h)); best_score = score; }
+            else if (score == best_score) best_set.push_back(static_cast<int>(h));
+        }
+        auto label_of = [&](int h) {
+            Cyp2d6RegionLabel l;
+            if (h >= 0) { l.region_type = Cyp2d6RegionType::Cyp2d6; l.subtype_label = *stars[static_cast<size_t>(h)]; }
+            return l;
+        };
+        int best = -1;
+        if (best_set.size() == 1) {
+            best = best_set[0];
+        } else if (force_assignment) {  // :523-534: sorted by full_allele, first candidate
+            std::stable_sort(best_set.begin(), best_set.end(), [&](int a, int b) { return label_of(a).full_allele() < label_of(b).full_allele(); });
+            best = best_set[0];
+        }
+        HaplotypeAssignment &r = out[s];
+        r.label = label_of(best);
+        r.vi_match = best_score.first; r.all_match = best_score.second;
+        if (best < 0) continue;  // Unknown: no variant list (:545, :596-599)
+        std::vector<RegionVariant> rv;
+        const std::vector<uint8_t> &hv = haps[static_cast<size_t>(best)];
+        for (size_t i = 0; i < nv; ++i) {
+            using V = VariantAlleleRelationship;
+            static const V ref_states[4] = {V::Match, V::Unexpected, V::AmbiguousUnexpected, V::UnknownUnexpected};
+            static const V alt_states[4] = {V::Missing, V::Match, V::AmbiguousMissing, V::UnknownMissing};
+            const V state = hv[i] == 0 ? ref_states[alleles[s][i]] : alt_states[alleles[s][i]];
+            if (state == V::Match && hv[i] == 0) continue;  // REF matching REF is not reported (:581-583)
+            rv.push_back({variants[i].label, variants[i].is_vi, state});
+        }
+        r.variants = std::move(rv);
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // weights and chains
 // ------------------------------------------------------------------------------------------
 std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &segments, const SeqList &consensuses,

@@ -98,6 +98,30 @@ std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const std::vector<int32_t>
     return out;
 }
 
+void GpuAligner::variant_match(const std::vector<std::vector<uint8_t>> &seq_alleles, const std::vector<std::vector<uint8_t>> &hap_alleles,
+                               const std::vector<uint8_t> &is_vi, std::vector<uint32_t> &vi_match, std::vector<uint32_t> &all_match) {
+    const size_t nv = is_vi.size();
+    auto flat = [&](const std::vector<std::vector<uint8_t>> &rows, const char *what) {
+        std::vector<uint8_t> out;
+        out.reserve(rows.size() * nv + 1);
+        for (const auto &r : rows) {
+            if (r.size() != nv) throw HostError(std::string("variant_match: a ") + what + " row differs in length from is_vi");
+            out.insert(out.end(), r.begin(), r.end());
+        }
+        if (out.empty()) out.push_back(0);
+        return out;
+    };
+    const std::vector<uint8_t> s = flat(seq_alleles, "sequence"), h = flat(hap_alleles, "haplotype");
+    std::vector<uint8_t> vi = is_vi;
+    if (vi.empty()) vi.push_back(0);
+    const size_t cells = seq_alleles.size() * hap_alleles.size();
+    vi_match.assign(std::max<size_t>(cells, 1), 0); all_match.assign(std::max<size_t>(cells, 1), 0);
+    check(sp_variant_match(ctx_, static_cast<int64_t>(seq_alleles.size()), static_cast<int64_t>(hap_alleles.size()), static_cast<int64_t>(nv),
+                           s.data(), h.data(), vi.data(), vi_match.data(), all_match.data()),
+          "sp_variant_match");
+    vi_match.resize(cells); all_match.resize(cells);
+}
+
 PatternSet::~PatternSet() { sp_patterns_destroy(p_); }
 DeviceMatrix::~DeviceMatrix() { sp_dmatrix_destroy(d_); }
 

@@ -235,6 +235,25 @@ PYBIND11_MODULE(_starphase_host, m) {
         }
         return out;
     });
+    m.def("alleles_from_traversal", &alleles_from_traversal);
+    m.def("assign_haplotypes_from_alleles", [](GpuAligner &g, const std::vector<std::vector<uint8_t>> &alleles,
+                                               const std::map<std::string, std::vector<uint8_t>> &lookup,
+                                               const std::vector<std::pair<std::string, bool>> &variants, bool force) {
+        std::vector<VariantMetadata> meta;
+        for (const auto &v : variants) meta.push_back({v.first, v.second});
+        py::list out;
+        for (const HaplotypeAssignment &a : assign_haplotypes_from_alleles(g, alleles, lookup, meta, force)) {
+            py::object star = a.label.region_type == Cyp2d6RegionType::Unknown ? py::object(py::none()) : py::object(py::str(*a.label.subtype_label));
+            py::object rv = py::none();
+            if (a.variants) {
+                Json arr = Json::array();
+                for (const RegionVariant &v : *a.variants) arr.push(v.to_json());
+                rv = py::str(arr.pretty());
+            }
+            out.append(py::make_tuple(star, rv, py::make_tuple(a.vi_match, a.all_match), a.label.full_allele()));
+        }
+        return out;
+    });
     m.def("convert_chain_to_hap", [](const std::vector<size_t> &chain, const RegionRows &rows, const std::string &level) {
         const Cyp2d6Config cfg = Cyp2d6Config::default_config();
         const Cyp2d6DetailLevel lvl = level == "CoreAlleles" ? Cyp2d6DetailLevel::CoreAlleles

@@ -231,6 +231,9 @@ class GpuAligner {
     // S[i * n_chains + j], j >= i: sum over reads of min(B[i][r], B[j][r]) for the chain-window matrix B
     std::vector<uint64_t> chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
                                           const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps);
+    // K6: (vi_match, all_match)[s * n_hap + h] for site-state rows (0 REF, 1 ALT, 2 ambiguous, 3 unset) against 0/1 haplotype rows
+    void variant_match(const std::vector<std::vector<uint8_t>> &seq_alleles, const std::vector<std::vector<uint8_t>> &hap_alleles,
+                       const std::vector<uint8_t> &is_vi, std::vector<uint32_t> &vi_match, std::vector<uint32_t> &all_match);
     uint64_t launch_count() const;
     sp_ctx *raw() { return ctx_; }
 
@@ -450,6 +453,36 @@ class Cyp2d6Extractor {
     GpuAligner &gpu_;
     std::vector<std::pair<Cyp2d6RegionLabel, std::string>> templates_;
 };
+
+// ---- allele-vector typing: the in-tree half of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:452-601) ----
+enum class VariantAlleleRelationship {  // src/data_types/region_variants.rs:5-23
+    Unknown, Match, Unexpected, Missing, AmbiguousUnexpected, AmbiguousMissing, UnknownUnexpected, UnknownMissing
+};
+const char *variant_state_name(VariantAlleleRelationship s);
+struct RegionVariant {  // src/data_types/region_variants.rs:26-34
+    std::string label;
+    bool is_vi = false;
+    VariantAlleleRelationship variant_state = VariantAlleleRelationship::Unknown;
+    Json to_json() const;
+};
+struct VariantMetadata {  // the members of LoadedVariants the typing reads (src/cyp2d6/haplotyper.rs:617-640, :812)
+    std::string label;
+    bool is_vi = false;
+};
+// :454-468: per-site state from the nodes a WFA-graph traversal visited (3 = unset, conflicting assignments -> 2)
+std::vector<uint8_t> alleles_from_traversal(size_t num_variants, const std::vector<size_t> &traversed_nodes,
+                                            const std::map<size_t, std::vector<std::pair<size_t, uint8_t>>> &node_to_alleles);
+struct HaplotypeAssignment {
+    Cyp2d6RegionLabel label;                              // Unknown when ambiguous and not forced
+    std::optional<std::vector<RegionVariant>> variants;   // None for Unknown
+    size_t vi_match = 0, all_match = 0;                   // best_score
+};
+// :470-601 for a batch of observed vectors: K6 scores every (vector, haplotype) pair on the GPU, the host keeps the
+// reference's arg-max over (vi_match, all_match) in BTreeMap order, its tie handling (sorted by full_allele, first one
+// if force_assignment else Unknown) and the RegionVariant list.  haplotype_lookup: star allele -> 0/1 vector.
+std::vector<HaplotypeAssignment> assign_haplotypes_from_alleles(GpuAligner &gpu, const std::vector<std::vector<uint8_t>> &alleles,
+                                                                const std::map<std::string, std::vector<uint8_t>> &haplotype_lookup,
+                                                                const std::vector<VariantMetadata> &variants, bool force_assignment);
 
 struct Cyp2d6Config {  // the members of src/cyp2d6/definitions.rs:128-336 the chaining code reads
     std::map<std::string, std::string> cyp_translate;

@@ -387,3 +387,25 @@ def test_splice_read(host):  # src/hla/caller.rs:1518-1576
             p = e
         w = so.splice_read(sq.encode(), 50, cig, ex)
         assert host.splice_read(sq, 50, cig, ex) == (w[0].decode(), w[1])
+
+
+def test_alleles_from_traversal(host):  # src/cyp2d6/haplotyper.rs:454-468
+    node_to_alleles = {0: [(0, 0), (1, 1)], 2: [(1, 1), (2, 0)], 5: [(2, 1), (3, 1)], 9: [(0, 1)]}
+    for nodes in ([0, 2, 5], [5, 2, 0], [1, 3], [0, 9, 9], []):
+        assert host.alleles_from_traversal(5, nodes, node_to_alleles) == so.alleles_from_traversal(5, nodes, node_to_alleles)
+    assert host.alleles_from_traversal(5, [0, 2, 5], node_to_alleles) == [0, 1, 2, 1, 3]
+    assert host.alleles_from_traversal(5, [0, 9], node_to_alleles) == [2, 1, 3, 3, 3]
+
+
+def test_variant_match_oracle_known_answers():  # the match rule of src/cyp2d6/haplotyper.rs:486-506
+    alleles, hap, vi = [0, 1, 2, 3, 1, 0], [0, 1, 1, 1, 0, 1], [True, False, True, True, True, False]
+    assert so.variant_match(alleles, hap, vi) == (2, 3)      # sites 0, 1, 2 agree; of those 0 and 2 are VI
+    with pytest.raises(ValueError, match="Unexpected seq_value=4"):
+        so.variant_match([4], [0], [True])
+    star, rv, score = so.assign_haplotype_from_alleles(alleles, {"1": [1, 0, 0, 0, 0, 1], "2": hap}, list("abcdef"), vi, False)
+    assert (star, score) == ("2", (2, 3))
+    # an all-REF definition ties at (2, 3) (sites 0, 2, 5): Unknown unless forced, then the first by full_allele
+    assert so.assign_haplotype_from_alleles(alleles, {"1": [0] * 6, "2": hap}, list("abcdef"), vi, False)[0] is None
+    assert so.assign_haplotype_from_alleles(alleles, {"1": [0] * 6, "2": hap}, list("abcdef"), vi, True)[0] == "1"
+    assert [(v["label"], v["variant_state"]) for v in rv] == [("b", "Match"), ("c", "AmbiguousMissing"), ("d", "UnknownMissing"),
+                                                             ("e", "Unexpected"), ("f", "Missing")]
