@@ -42,7 +42,7 @@ struct AlignParams {
     long long slot_words;
     AlignRecDev *recs;
     int n_pairs;
-    uint32_t one, m1;
+    uint32_t one, m1, seed_a, seed_b;
 };
 
 // the K1 recurrence over `ncols` text columns T[0 .. ncols) for this warp's bin; STORE keeps (D0, ~Pv) per column
@@ -72,7 +72,7 @@ __device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *
             for (int c = 0; c < K1_CHUNK; ++c) {
                 const int j = idx * K1_CHUNK + c;
                 const uint32_t code = j < ncols ? base_code(T[j]) : 4u;
-                column_step<U, true, STORE>(blob, lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col,
+                column_step<U, true, STORE>(blob, lane, code, p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, cph, cmh, score, best, col,
                                             best_col, d0);
                 if (STORE && owns && j < ncols) {
                     uint32_t *dst = scr + static_cast<size_t>(j) * 2 * Wp + (lane * U - wf4);

@@ -54,6 +54,9 @@ struct K1Params {
     int out16;
     int prefix_mode;                // SP_PREFIX: top row delta +1
     uint32_t one, m1, sixteen;      // +1, -1 (0xFFFFFFFF), 16: passed at run time so `x * one + y` stays an IMAD (FMA pipe)
+    uint32_t seed_a, seed_b;        // 1, 0xFFFFFFFF again: `seed_a - seed_b` sets the borrow that seeds the Myers add chain.  Separate
+                                    // parameters on purpose: inline-asm operands live in R registers, and sharing them with one / m1
+                                    // turned every IMAD multiplier from a uniform register into a third R operand (K1 -10 %)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -142,21 +145,24 @@ __device__ __forceinline__ void load_row(const uint32_t *row, int lane, uint32_t
 // The Myers add (Eq & Pv) + Pv becomes t - npv - 1 (borrow chain seeded with 1, SubChain1).
 template <int U, bool TRACK_END, bool KEEP_D0 = false>
 __device__ __forceinline__ void column_step(const uint32_t *peq, int lane, uint32_t code, uint32_t one, uint32_t m1,
+                                            uint32_t seed_a, uint32_t seed_b,
                                             uint32_t (&npv)[U], uint32_t (&mv)[U], uint32_t &X, uint32_t &Y,
                                             uint32_t &cph, uint32_t &cmh, int &score, int &best, int &col,
                                             int &best_col, uint32_t *d0_keep = nullptr) {
-    uint32_t eq[U], xv[U], t[U], sum[U];
+    uint32_t eq[U], t[U], sum[U];
     load_row<U>(peq + code * (32 * U), lane, eq);
-    eq[0] |= (Y >> 31);  // hin < 0 (Hyyro): the row above already paid for this column
+    // hin < 0 (Hyyro): the row above already paid for this column, i.e. Eq bit 0 is forced.  The bit is folded into the two
+    // 3-input LOP3s of word 0 that consume Eq instead of being OR-ed into eq[0] first (one ALU-pipe instruction per column)
+    const uint32_t ybit = Y >> 31;
+    t[0] = (eq[0] | ybit) & ~npv[0];
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = eq[u] | mv[u];
-#pragma unroll
-    for (int u = 0; u < U; ++u) t[u] = eq[u] & ~npv[u];
-    SubChain1<U>::run(sum, t, npv);
+    for (int u = 1; u < U; ++u) t[u] = eq[u] & ~npv[u];
+    SubChain1<U>::run(sum, t, npv, seed_a, seed_b);
     uint32_t ph[U], mh[U], d0[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        d0[u] = ~(sum[u] ^ npv[u]) | xv[u];
+        const uint32_t xh = ~(sum[u] ^ npv[u]) | eq[u];
+        d0[u] = u == 0 ? (xh | mv[u] | ybit) : (xh | mv[u]);
         const uint32_t a1 = npv[u] * m1 + d0[u];   // D0 - npv          (IMAD)
         const uint32_t ng = ~d0[u] & npv[u];       // ~(D0 | Pv)        (LOP3)
         mh[u] = ng * one + a1;                     //                   (IMAD)
@@ -246,7 +252,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
             uint32_t cphA = 0, cmhA = 0, cphB = 0, cmhB = 0;  // columns 0-3 and 4-7
 #pragma unroll
             for (int c = 0; c < K1_CHUNK; ++c)
-                column_step<U, TRACK_END>(blob, lane, codes[c], p.one, p.m1, npv, mv, X, Y, c < 4 ? cphA : cphB,
+                column_step<U, TRACK_END>(blob, lane, codes[c], p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, c < 4 ? cphA : cphB,
                                           c < 4 ? cmhA : cmhB, score, best, col, best_col);
             const uint32_t iA = cmhA * p.sixteen + cphA, iB = cmhB * p.sixteen + cphB;  // IMAD: table indices
             carry_out = (cphA * p.sixteen + cphB) | ((iA & 0xF0u) << 8) | ((iB & 0xF0u) << 4);
@@ -332,7 +338,7 @@ struct SpanParams {
     int32_t *S;              // out: start columns  [p * ld + t]
     long long ld;
     int nt, np;
-    uint32_t one, m1;
+    uint32_t one, m1, seed_a, seed_b;
 };
 
 __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
                 for (int c = 0; c < K1_CHUNK; ++c) {
                     const int j = idx * K1_CHUNK + c;
                     const uint32_t code = j < wlen ? base_code(T[e - 1 - j]) : 4u;
-                    column_step<U, true>(blob, lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
+                    column_step<U, true>(blob, lane, code, p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
                 }
                 carry_out = cph | (cmh << 8);
             }

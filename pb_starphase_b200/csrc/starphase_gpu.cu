@@ -658,7 +658,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         prm.ld = ld;
         prm.n_groups = pc.n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
         prm.prefix_mode = p->mode == SP_PREFIX;
-        prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.sixteen = 16u;
+        prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu; prm.sixteen = 16u;
         const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
         if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
         const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
@@ -892,7 +892,7 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
         SpanParams prm;
         prm.blobs = d_blobs; prm.tbases = t->d_bases; prm.toffs = t->d_offs;
         prm.D = static_cast<const int32_t *>(d->d); prm.E = d->d_end; prm.S = d_S; prm.ld = d->ld;
-        prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
+        prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
         const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(SPAN_U) * 4;
         SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "k3_span_starts smem"));
@@ -1069,7 +1069,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
         AlignParams prm;
         prm.blobs = d_blobs; prm.tbases = d_tb; prm.toffs = d_to; prm.pair_t = d_pt; prm.pair_p = d_pp;
         prm.cig_off = d_cig_off; prm.cigar = d_cigar; prm.scratch = d_scratch; prm.slot_words = max_slot_words;
-        prm.recs = d_recs; prm.n_pairs = static_cast<int>(n_pairs); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
+        prm.recs = d_recs; prm.n_pairs = static_cast<int>(n_pairs); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
         const size_t smem = static_cast<size_t>(warps_per_cta) * blob_words(ALN_U) * 4;
         SP_TRY(cu(cudaFuncSetAttribute(k4_align, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_WARPS * blob_words(ALN_U) * 4), "k4_align smem"));
         ev_begin(ctx, 4);
