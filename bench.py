@@ -35,6 +35,28 @@ TOPK = 16
 
 K1_DNA_DRAM_BYTES_PER_STEP = 167551829  # profiles/r01e_k1_traffic.csv
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first communicator
+# when NCCL_DEBUG=VERSION is set in the environment), so the process's fd 1 is pointed at stderr for its whole life and the
+# result line goes to a private duplicate of the original stdout.
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -166,7 +188,7 @@ def run_reference(args):
                             "OpenMP); the Rust reference + minimap2 cannot be built here"),
                 cpu_baseline=dict(value=res["gcups"], unit=UNIT, cores=res["cores"], kind="port", sample=res["sample"]),
                 e2e=dict(value=res["gcups"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_name(n):
@@ -542,7 +564,7 @@ def run_ours(args):
                                    peak_source="MEASURED_PEAKS.json" if peaks else "fallback")),
             cpu_baseline=(dict(value=cpu["gcups"], unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"]) if cpu else None),
         )
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -550,6 +572,7 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

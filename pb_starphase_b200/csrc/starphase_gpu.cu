@@ -636,6 +636,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
         const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
         int64_t tc = 4096;
+        if (const char *force_tc = getenv("SP_FORCE_TC")) tc = std::max<int64_t>(64, atoll(force_tc));  // experiment hook: tile capacity in chunks
         const int64_t want_items = 4ll * ctx->num_sms;
         if (static_cast<int64_t>(pc.n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
             const int64_t want_tiles = (want_items + pc.n_groups - 1) / pc.n_groups;
