@@ -210,8 +210,10 @@ void sp_oracle_span_batch(const uint8_t *tbases, const int64_t *toffs, int64_t n
  * CIGAR that process_mm_cigar (processed_match.rs:210-263) walks (1 = I, 2 = D, 7 = '=', 8 = X; clips are the
  * unaligned pattern ends and are not CIGAR entries).  Full (m+1) x (n+1) int32 matrix, then the canonical walk
  * back from (m, e), e = smallest end column of a best placement: diagonal if D[i-1][j-1] + cost == D[i][j],
- * else up if D[i-1][j] + 1 == D[i][j] ('I'), else left ('D'); column 0 only goes up.  Leading / trailing 'I'
- * runs become p_start / |P| - p_end.  rec = {dist, nm, p_start, p_end, t_start, t_end, n_cigar}; returns the
+ * else up if D[i-1][j] + 1 == D[i][j] ('I'), else left ('D'); column 0 only goes up.  Before the first diagonal or
+ * 'D' step, up is preferred whenever it is optimal: a pattern end hanging over the text end (a read that stops inside
+ * the allele) then comes out as one trailing 'I' run = clip, the way a local aligner reports it, instead of being
+ * interleaved with chance matches.  Leading / trailing 'I' runs become p_start / |P| - p_end.  rec = {dist, nm, p_start, p_end, t_start, t_end, n_cigar}; returns the
  * number of run-length entries written to cigar (forward order), or -1 if cap is too small.
  */
 int64_t sp_oracle_align(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, int32_t *rec, uint32_t *cigar,
@@ -237,12 +239,15 @@ int64_t sp_oracle_align(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n
     uint32_t *ops = (uint32_t *)malloc((size_t)(m + n + 2) * sizeof(uint32_t)); /* backward run-length list */
     int64_t nops = 0, i = m, j = e;
     uint32_t cur_op = 0, cur_len = 0;
+    int started = 0; /* a diagonal or 'D' step has been taken */
     while (i > 0) {
         uint32_t op;
         if (j == 0) { op = 1; --i; }
+        else if (!started && D[(i - 1) * W + j] + 1 == D[i * W + j]) { op = 1; --i; }
         else {
             int match = sp_code(P[i - 1]) == sp_code(T[j - 1]) && sp_code(P[i - 1]) < 4;
             int32_t v = D[i * W + j];
+            started = 1;
             if (D[(i - 1) * W + j - 1] + (match ? 0 : 1) == v) { op = match ? 7 : 8; --i; --j; }
             else if (D[(i - 1) * W + j] + 1 == v) { op = 1; --i; }
             else { op = 2; --j; }

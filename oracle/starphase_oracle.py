@@ -1158,3 +1158,29 @@ def assign_haplotype_from_alleles(alleles: Sequence[int], haplotype_lookup: Dict
             continue
         rv.append(dict(label=labels[i], is_vi=bool(is_vi[i]), variant_state=state))
     return best, rv, best_score
+
+
+# ==========================================================================================
+# homopolymer compression -- src/util/homopolymers.rs:18-42
+# ==========================================================================================
+def hpc(seq: bytes) -> bytes:
+    out = bytearray()
+    for c in seq:
+        if not out or out[-1] != c:
+            out.append(c)
+    return bytes(out)
+
+
+def hpc_pos(seq: bytes, position: int) -> int:
+    total = offset = 0
+    i = 0
+    while i < len(seq):
+        j = i
+        while j < len(seq) and seq[j] == seq[i]:
+            j += 1
+        total += j - i
+        if position < total:
+            break
+        offset += 1
+        i = j
+    return offset

@@ -12,7 +12,8 @@
 //           e lies inside it -- keeping per column the vertical deltas (~Pv, Mv are the state anyway; only
 //           ~Pv is needed) and Hyyro's diagonal-zero vector D0 in HBM scratch
 //   pass 3  the warp walks back from (m, e): diagonal when it explains the cell ('=' or 'X'), else up ('I',
-//           a pattern base without a text base), else left ('D').  Taking the diagonal first while walking
+//           a pattern base without a text base), else left ('D'); before the first diagonal / 'D' step up wins ties,
+//           so a pattern end hanging over the text end is one trailing 'I' run (a clip), not 'I's between chance matches.  Taking the diagonal first while walking
 //           backwards left-aligns gaps, the convention of minimap2's ksw2.  Lane k inspects the k-th cell down
 //           the diagonal, so a run of up to 32 diagonal steps costs one round of (L2-latency-bound) loads.
 //           Leading / trailing 'I' runs are the clipped pattern ends (query_start, query_len - query_end).
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
             long long pos = cig_end;
             uint32_t cur_op = 0, cur_len = 0;
             int i = m_all, j = ncols;
+            bool started = false;  // a diagonal or 'D' step has been taken: until then 'I' wins ties (trailing clip in one run)
             auto emit = [&](uint32_t op, uint32_t n) {
                 if (op == cur_op) { cur_len += n; return; }
                 if (cur_len) { --pos; if (lane == 0) p.cigar[pos] = (cur_len << 4) | cur_op; }
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
                 const uint32_t ok_mask = __ballot_sync(0xffffffffu, diag_ok);
                 const uint32_t eq_mask = __ballot_sync(0xffffffffu, is_eq);
                 const bool pv0 = __shfl_sync(0xffffffffu, pv ? 1 : 0, 0) != 0;
+                if (!started && pv0) { emit(CIG_I, 1); --i; continue; }
+                started = true;
                 const int n_diag = ok_mask == 0xffffffffu ? 32 : __ffs(~ok_mask) - 1;
                 if (n_diag == 0) {
                     if (pv0) { emit(CIG_I, 1); --i; } else { emit(CIG_D, 1); --j; }

@@ -250,7 +250,10 @@ static sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_base
 // lane widths compiled into the library
 static const int kUmin = 4, kUmax = 16;
 // modelled ALU-pipe instructions per text column of one warp (8 per word + per-column bookkeeping)
-static double warp_cost(int U) { return 8.0 * U + 17.0; }
+static double warp_cost(int U) {
+    static const double book = getenv("SP_PLAN_BOOK") ? atof(getenv("SP_PLAN_BOOK")) : 17.0;  // experiment hook
+    return 8.0 * U + book;
+}
 
 struct BinPlan {
     int U = 0;
@@ -364,7 +367,8 @@ static bool choose_classes(const std::vector<int64_t> &lens, int max_classes, st
             if (!bestU || c < bestc) { bestU = U; bestc = c; }
         }
         if (!bestU) break;
-        if (!set.empty() && bestc > 0.99 * cur) break;
+        static const double min_gain = getenv("SP_PLAN_GAIN") ? atof(getenv("SP_PLAN_GAIN")) : 0.99;  // experiment hook
+        if (!set.empty() && bestc > min_gain * cur) break;
         set.push_back(bestU);
         cur = bestc;
     }

@@ -172,6 +172,29 @@ Json HlaDebug::to_json() const {
 }
 
 // ------------------------------------------------------------------------------------------
+// homopolymer compression (src/util/homopolymers.rs:18-42)
+// ------------------------------------------------------------------------------------------
+std::string hpc(const std::string &sequence) {
+    std::string out;
+    for (char c : sequence)
+        if (out.empty() || out.back() != c) out.push_back(c);
+    return out;
+}
+
+size_t hpc_pos(const std::string &sequence, size_t position) {
+    size_t total = 0, offset = 0, i = 0;
+    while (i < sequence.size()) {
+        size_t j = i;
+        while (j < sequence.size() && sequence[j] == sequence[i]) ++j;
+        total += j - i;
+        if (position < total) break;
+        ++offset;
+        i = j;
+    }
+    return offset;
+}
+
+// ------------------------------------------------------------------------------------------
 // consensus preparation
 // ------------------------------------------------------------------------------------------
 std::string reverse_complement(const std::string &s) {

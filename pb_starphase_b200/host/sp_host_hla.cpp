@@ -136,8 +136,27 @@ std::vector<PgxMappingDetails> HlaRealigner::realign_records(const std::vector<s
     return realign_records_scored(reads, *D, n_candidates);
 }
 
-std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::vector<std::pair<std::string, std::string>> &reads,
-                                                                    const DeviceMatrix &D, int n_candidates) {
+HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database,
+                           const std::map<std::string, HlaGeneDefinition> &gene_definitions)
+    : gpu_(gpu), gene_definitions_(gene_definitions) {
+    for (const std::string &g : gene_list)
+        if (!gene_definitions_.count(g)) throw HostError("Gene definition for " + g + " not found.");  // :64-67
+    SeqList seqs;
+    for (const auto &kv : database) {
+        if (std::find(gene_list.begin(), gene_list.end(), kv.second.gene_name) == gene_list.end()) continue;
+        if (!kv.second.dna_sequence) continue;
+        alleles_.push_back(&kv.second);
+        const bool fwd = gene_definitions_.at(kv.second.gene_name).is_forward_strand;
+        seqs.push_back(fwd ? *kv.second.dna_sequence : reverse_complement(*kv.second.dna_sequence));  // :511-515
+    }
+    index_ = gpu.prepare_patterns(seqs);
+}
+
+// The selection loop of realign_record (src/hla/realigner.rs:116-146) for every read: the n best alleles by distance (K5)
+// get a traceback (K4); minimap2's target is the allele here, so `unmapped` is allele-side.  The db_aligner is the plain
+// map-hifi preset (a = 1, src/util/mapping.rs:8-14), which is what decides whether a hit would have been reported at all.
+std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std::pair<std::string, std::string>> &reads,
+                                                           const DeviceMatrix &D, int n_candidates) {
     SeqList targets;
     for (const auto &r : reads) targets.push_back(r.second);
     const size_t A = alleles_.size();
@@ -158,37 +177,182 @@ std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::v
     }
     first_pair[reads.size()] = pairs.size();
     const SeqList &allele_seqs = index_->sequences();
-    const std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs, pairs);
+    std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs, pairs);
 
-    std::vector<PgxMappingDetails> out;
+    std::vector<BestHit> out(reads.size());
     for (size_t r = 0; r < reads.size(); ++r) {
         const size_t read_len = reads[r].second.size();
-        MappingStats best_stats(read_len, read_len, 0);  // src/hla/realigner.rs:124
-        int best_allele = -1;
+        BestHit &b = out[r];
+        b.stats = MappingStats(read_len, read_len, 0);  // src/hla/realigner.rs:124
         for (size_t q = first_pair[r]; q < first_pair[r + 1]; ++q) {
-            const Alignment &a = alns[q];
-            if (a.cigar.empty() || dp_score(a.cigar) < 200) continue;  // no hit reported
-            const size_t target_len = allele_seqs[static_cast<size_t>(pairs[q].second)].size();  // minimap2's target is the allele here
+            Alignment &a = alns[q];
+            if (a.cigar.empty() || dp_score(a.cigar, 1) < 200) continue;  // no hit reported
+            const size_t target_len = allele_seqs[static_cast<size_t>(pairs[q].second)].size();
             const size_t unmapped = target_len - static_cast<size_t>(a.p_end - a.p_start);
             const MappingStats stats(target_len, static_cast<size_t>(a.nm), unmapped);
             if (stats.mapping_score() <= 0.5 && stats.custom_score(false) <= 0.03 &&
-                stats.custom_score(false) < best_stats.custom_score(false)) {  // :137-146
-                best_stats = stats;
-                best_allele = pairs[q].second;
+                stats.custom_score(false) < b.stats.custom_score(false)) {  // :137-146
+                b.stats = stats;
+                b.allele = pairs[q].second;
+                b.aln = std::move(a);
             }
         }
+    }
+    return out;
+}
+
+std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::vector<std::pair<std::string, std::string>> &reads,
+                                                                    const DeviceMatrix &D, int n_candidates) {
+    const std::vector<BestHit> hits = best_hits(reads, D, n_candidates);
+    std::vector<PgxMappingDetails> out;
+    for (size_t r = 0; r < reads.size(); ++r) {
         PgxMappingDetails d;
         d.read_qname = reads[r].first;
-        d.best_mapping_stats.dna_stats = best_stats;
-        if (best_allele < 0) {  // :149-162
+        d.best_mapping_stats.dna_stats = hits[r].stats;
+        if (hits[r].allele < 0) {  // :149-162
             d.best_hla_id = "REFERENCE"; d.best_star_allele = "REFERENCE"; d.is_ignored = true;
         } else {
-            const HlaAlleleDefinition *def = alleles_[static_cast<size_t>(best_allele)];
+            const HlaAlleleDefinition *def = alleles_[static_cast<size_t>(hits[r].allele)];
             d.best_hla_id = def->hla_id;
             d.best_star_allele = def->gene_name + "*" + join_star(def->star_allele);  // :204-211
             d.is_ignored = false;
         }
         out.push_back(std::move(d));
+    }
+    return out;
+}
+
+// K4 reports (pattern, text) = (allele, read); minimap2's view at this call site is (query, target) = (read, allele), so
+// the roles and the insertion / deletion letters swap
+static Mapping read_vs_allele_mapping(const Alignment &a, size_t read_len, size_t allele_len) {
+    Mapping m;
+    m.query_start = static_cast<size_t>(a.t_start); m.query_end = static_cast<size_t>(a.t_end); m.query_len = read_len;
+    m.target_start = static_cast<size_t>(a.p_start); m.target_end = static_cast<size_t>(a.p_end); m.target_len = allele_len;
+    m.nm = static_cast<size_t>(a.nm);
+    m.forward = true;
+    for (const auto &op : a.cigar) m.cigar.emplace_back(op.first, op.second == 1 ? uint8_t(2) : op.second == 2 ? uint8_t(1) : op.second);
+    return m;
+}
+
+std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vector<std::pair<std::string, std::string>> &reads,
+                                                                  int n_candidates) {
+    if (gene_definitions_.empty()) throw HostError("realign_records_full: the realigner was built without gene definitions");
+    SeqList targets;
+    for (const auto &r : reads) targets.push_back(r.second);
+    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(targets, *index_);
+    const std::vector<BestHit> hits = best_hits(reads, *D, n_candidates);
+    const SeqList &allele_seqs = index_->sequences();  // hg38 orientation
+
+    std::vector<RealignmentResult> out(reads.size());
+    // second batch: the buffered read segment of every accepted read against its gene's hg38 sequence (:216-231)
+    SeqList ref_texts, seg_patterns;
+    std::map<std::string, int32_t> ref_index;
+    std::vector<std::pair<int32_t, int32_t>> seg_pairs;
+    std::vector<size_t> seg_read, seg_buffered_start;
+    for (size_t r = 0; r < reads.size(); ++r) {
+        RealignmentResult &res = out[r];
+        PgxMappingDetails &d = res.mapping_details;
+        d.read_qname = reads[r].first;
+        d.best_mapping_stats.dna_stats = hits[r].stats;
+        if (hits[r].allele < 0) {  // :149-162: RealignmentResult::failure
+            d.best_hla_id = "REFERENCE"; d.best_star_allele = "REFERENCE"; d.is_ignored = true;
+            continue;
+        }
+        const HlaAlleleDefinition *def = alleles_[static_cast<size_t>(hits[r].allele)];
+        const std::string best_star = join_star(def->star_allele);
+        d.best_hla_id = def->hla_id;
+        d.best_star_allele = def->gene_name + "*" + best_star;
+        d.is_ignored = false;
+        res.gene_name = def->gene_name;
+        const std::string &allele_seq = allele_seqs[static_cast<size_t>(hits[r].allele)];
+        const Mapping bm = read_vs_allele_mapping(hits[r].aln, reads[r].second.size(), allele_seq.size());
+        res.read_mapping_stats.add_mapping(def->hla_id, std::nullopt, detailed_mapping_stats(bm, allele_seq, reads[r].second));  // :199-201
+        res.read_mapping_stats.set_best_match(def->hla_id, best_star);
+        const size_t buffer = 1000;  // :221-224
+        const size_t bs = bm.query_start > buffer ? bm.query_start - buffer : 0;
+        const size_t be = std::min(bm.query_end + buffer, reads[r].second.size());
+        auto it = ref_index.find(def->gene_name);
+        if (it == ref_index.end()) {
+            it = ref_index.emplace(def->gene_name, static_cast<int32_t>(ref_texts.size())).first;
+            ref_texts.push_back(gene_definitions_.at(def->gene_name).reference_sequence);
+        }
+        seg_pairs.emplace_back(it->second, static_cast<int32_t>(seg_patterns.size()));
+        seg_patterns.push_back(reads[r].second.substr(bs, be - bs));
+        seg_read.push_back(r);
+        seg_buffered_start.push_back(bs);
+    }
+    const std::vector<Alignment> seg_alns = gpu_.align_pairs(ref_texts, seg_patterns, seg_pairs);
+
+    // third batch: the best allele against hg38 for the reads whose hg38 mapping starts no earlier than the allele mapping (:268-290)
+    struct Pending { size_t r; Mapping ref_mapping; size_t hg38_start, hg38_end; int32_t allele_pair = -1; };
+    std::vector<Pending> pending;
+    SeqList allele_patterns;
+    std::vector<std::pair<int32_t, int32_t>> allele_pairs;
+    for (size_t q = 0; q < seg_pairs.size(); ++q) {
+        const size_t r = seg_read[q];
+        const std::string &ref = ref_texts[static_cast<size_t>(seg_pairs[q].first)];
+        std::vector<Mapping> mappings;
+        const Alignment &a = seg_alns[q];
+        if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {  // (query, target) = (read segment, hg38) = (pattern, text)
+            Mapping m;
+            m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = seg_patterns[q].size();
+            m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = ref.size();
+            m.nm = static_cast<size_t>(a.nm); m.forward = true; m.cigar = a.cigar;
+            mappings.push_back(std::move(m));
+        }
+        const auto sel = select_best_mapping(mappings, true, true, std::nullopt);  // :234-238
+        if (!sel.first) continue;  // "Remapping of {qname} to reference failed, ignoring." (:337-339)
+        Pending p;
+        p.r = r;
+        p.ref_mapping = mappings[*sel.first];
+        p.hg38_start = seg_buffered_start[q] + p.ref_mapping.query_start;  // :257-258
+        p.hg38_end = seg_buffered_start[q] + p.ref_mapping.query_end;
+        const size_t db_start = static_cast<size_t>(hits[r].aln.t_start);
+        if (!(p.hg38_start < db_start)) {
+            p.allele_pair = static_cast<int32_t>(allele_pairs.size());
+            allele_pairs.emplace_back(seg_pairs[q].first, static_cast<int32_t>(allele_patterns.size()));
+            allele_patterns.push_back(allele_seqs[static_cast<size_t>(hits[r].allele)]);  // hg38 orientation (:276-282)
+        }
+        pending.push_back(std::move(p));
+    }
+    const std::vector<Alignment> allele_alns = gpu_.align_pairs(ref_texts, allele_patterns, allele_pairs);
+
+    for (const Pending &p : pending) {
+        const size_t r = p.r;
+        const HlaAlleleDefinition *def = alleles_[static_cast<size_t>(hits[r].allele)];
+        const std::string &ref = gene_definitions_.at(def->gene_name).reference_sequence;
+        const size_t db_start = static_cast<size_t>(hits[r].aln.t_start), db_end = static_cast<size_t>(hits[r].aln.t_end);
+        const size_t bm_target_start = static_cast<size_t>(hits[r].aln.p_start);
+        RealignedHlaRecord rec;
+        rec.segment_start = std::min(db_start, p.hg38_start);  // :263-264
+        rec.segment_end = std::max(db_end, p.hg38_end);
+        size_t d = p.ref_mapping.target_start, h = 0;
+        bool from_ref = true;
+        if (p.allele_pair >= 0) {
+            const Alignment &a = allele_alns[static_cast<size_t>(p.allele_pair)];
+            std::vector<Mapping> mappings;
+            if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {
+                Mapping m;
+                m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end);
+                m.query_len = allele_patterns[static_cast<size_t>(allele_pairs[static_cast<size_t>(p.allele_pair)].second)].size();
+                m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = ref.size();
+                m.nm = static_cast<size_t>(a.nm); m.forward = true; m.cigar = a.cigar;
+                mappings.push_back(std::move(m));
+            }
+            const auto sel = select_best_mapping(mappings, false, true, std::nullopt);  // :296-300
+            if (sel.first) {
+                const Mapping &am = mappings[*sel.first];
+                const long added = std::max(0l, static_cast<long>(am.target_start) - static_cast<long>(am.query_start));  // :304
+                d = static_cast<size_t>(added) + bm_target_start;                                                       // :310
+                h = hpc_pos(ref, static_cast<size_t>(added)) + hpc_pos(*def->dna_sequence, bm_target_start);          // :312
+                from_ref = false;
+            }  // else: "Failed to map allele ... ignoring offset adjustment" (:315-319)
+        }
+        if (from_ref) h = hpc_pos(ref, d);  // :269-272, :317-318
+        rec.dna_offset = d; rec.hpc_offset = h;
+        rec.dna_sequence = reads[r].second.substr(rec.segment_start, rec.segment_end - rec.segment_start);  // RealignedHlaRecord::new
+        rec.hpc_sequence = hpc(rec.dna_sequence);
+        out[r].realigned_record = std::move(rec);
     }
     return out;
 }

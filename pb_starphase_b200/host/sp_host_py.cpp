@@ -172,6 +172,31 @@ PYBIND11_MODULE(_starphase_host, m) {
         for (const auto &d : r.realign_records(reads, n_candidates)) arr.push(d.to_json());
         return arr;
     }, py::arg("gpu"), py::arg("gene_list"), py::arg("database"), py::arg("reads"), py::arg("n_candidates") = 5);
+    m.def("hpc", &hpc);
+    m.def("hpc_pos", &hpc_pos);
+    m.def("realign_records_full", [](GpuAligner &g, const std::vector<std::string> &genes, const DbRows &rows,
+                                     const std::map<std::string, std::pair<bool, std::string>> &gene_defs,
+                                     const std::vector<std::pair<std::string, std::string>> &reads, int n_candidates) {
+        const HlaDatabase db = make_db(rows);
+        std::map<std::string, HlaGeneDefinition> defs;
+        for (const auto &kv : gene_defs) defs[kv.first] = HlaGeneDefinition{kv.second.first, kv.second.second};
+        HlaRealigner r(g, genes, db, defs);
+        py::list out;
+        for (const RealignmentResult &res : r.realign_records_full(reads, n_candidates)) {
+            py::dict d;
+            d["gene_name"] = res.gene_name;
+            d["read_mapping_stats"] = res.read_mapping_stats.to_json().pretty();
+            d["mapping_details"] = res.mapping_details.to_json().pretty();
+            if (res.realigned_record) {
+                const RealignedHlaRecord &x = *res.realigned_record;
+                d["realigned_record"] = py::make_tuple(x.segment_start, x.segment_end, x.dna_offset, x.hpc_offset, x.dna_sequence, x.hpc_sequence);
+            } else {
+                d["realigned_record"] = py::none();
+            }
+            out.append(d);
+        }
+        return out;
+    }, py::arg("gpu"), py::arg("gene_list"), py::arg("database"), py::arg("gene_definitions"), py::arg("reads"), py::arg("n_candidates") = 5);
     m.def("diplotype_hla_gene", [](GpuAligner &g, const DbRows &rows, const std::string &gene,
                                    const std::vector<std::tuple<std::string, std::string, std::string>> &reads, const DiplotypeSettings &s) {
         const HlaDatabase db = make_db(rows);

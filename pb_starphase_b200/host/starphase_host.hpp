@@ -342,10 +342,37 @@ struct PgxMappingDetails {  // src/data_types/starphase_json.rs:271-283
     Json to_json() const;
 };
 
-class HlaRealigner {  // src/hla/realigner.rs:22-211 (database side only: the allele index and the acceptance loop)
+// src/util/homopolymers.rs:18-42
+std::string hpc(const std::string &sequence);
+size_t hpc_pos(const std::string &sequence, size_t position);
+
+struct HlaGeneDefinition {  // the members of src/hla/alleles.rs' gene definition the realigner reads
+    bool is_forward_strand = true;
+    // hg38 forward-strand sequence of the gene region +- 100 bp (src/hla/realigner.rs:72-77, `gene_ref_sequence`)
+    std::string reference_sequence;
+};
+struct RealignedHlaRecord {  // src/hla/realigner.rs:417-478 (without the cloned bam::Record)
+    size_t segment_start = 0, segment_end = 0;  // the part of the read handed to the consensus step
+    std::string dna_sequence, hpc_sequence;
+    size_t dna_offset = 0, hpc_offset = 0;
+};
+struct RealignmentResult {  // src/hla/realigner.rs:358-414
+    std::string gene_name;
+    ReadMappingStats read_mapping_stats;
+    PgxMappingDetails mapping_details;
+    std::optional<RealignedHlaRecord> realigned_record;
+    bool is_realigned() const { return realigned_record.has_value(); }
+};
+
+class HlaRealigner {  // src/hla/realigner.rs:22-350
   public:
-    // builds the resident allele index once: every allele of the listed genes that has a DNA sequence (create_hla_fasta, :497-526)
+    // builds the resident allele index once: every allele of the listed genes that has a DNA sequence (create_hla_fasta, :497-526);
+    // sequences are taken as stored (database side only: realign_records)
     HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database);
+    // HlaRealigner::new (:42-91): alleles of reverse-strand genes are reverse-complemented into hg38 orientation
+    // (create_hla_fasta :511-515) and every gene keeps its buffered hg38 sequence for the offset step (realign_records_full)
+    HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database,
+                 const std::map<std::string, HlaGeneDefinition> &gene_definitions);
     // one PgxMappingDetails per read, in input order; n_candidates plays the role of minimap2's best_n = 5.
     // K1 over the index (matrix stays on the device), K5 candidate lists, K4 traceback of the candidates.
     std::vector<PgxMappingDetails> realign_records(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
@@ -353,13 +380,21 @@ class HlaRealigner {  // src/hla/realigner.rs:22-211 (database side only: the al
     // same, on a distance matrix K1 already produced for these reads against this index
     std::vector<PgxMappingDetails> realign_records_scored(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
                                                           const DeviceMatrix &D, int n_candidates = 5);
+    // realign_record in full (:98-350) for a batch of reads (hg38 forward strand): best database allele as above, then the
+    // buffered read segment against the gene's hg38 sequence and, when that starts later than the allele mapping, the allele
+    // against hg38 (two more K4 batches) for the segment range and the DNA / HPC offsets the consensus step consumes
+    std::vector<RealignmentResult> realign_records_full(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
+                                                        int n_candidates = 5);
     size_t n_alleles() const { return alleles_.size(); }
     const PatternSet &index() const { return *index_; }
 
   private:
+    struct BestHit { int allele = -1; MappingStats stats; Alignment aln; };
+    std::vector<BestHit> best_hits(const std::vector<std::pair<std::string, std::string>> &reads, const DeviceMatrix &D, int n_candidates);
     GpuAligner &gpu_;
     std::vector<const HlaAlleleDefinition *> alleles_;
     std::shared_ptr<PatternSet> index_;
+    std::map<std::string, HlaGeneDefinition> gene_definitions_;
 };
 
 struct HlaRead {

@@ -108,7 +108,7 @@ def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Seque
         order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
             al = orc.align(seqs[a], seq)
-            if not al["cigar"] or dp_score(al["cigar"]) < 200:
+            if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:  # db_aligner is the plain map-hifi preset (a = 1)
                 continue
             tl = len(seqs[a])
             st = so.MappingStats(tl, al["nm"], tl - (al["p_end"] - al["p_start"]))
@@ -120,6 +120,71 @@ def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Seque
         else:
             row = alleles[best_a]
             out.append(so.mapping_details_json(qname, row[0], f"{row[1]}*{':'.join(row[2])}", hs, False))
+    return out
+
+
+def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_defs: Dict[str, Tuple[bool, bytes]],
+                         reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5) -> List[dict]:
+    """HlaRealigner::new + realign_record in full (src/hla/realigner.rs:42-91, :98-350) on the oracle's alignments."""
+    alleles = [r for r in sorted(db, key=lambda r: r[0].encode()) if r[1] in genes and r[3] is not None]
+    seqs = [r[3].encode() if gene_defs[r[1]][0] else so.reverse_complement(r[3].encode()) for r in alleles]  # create_hla_fasta :511-515
+    D = orc.score_batch([r[1] for r in reads], seqs) if alleles and reads else np.zeros((len(reads), 0), np.int32)
+    out = []
+    for r, (qname, seq) in enumerate(reads):
+        best, best_a, best_al = so.MappingStats(len(seq), len(seq), 0), None, None
+        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        for a in order:
+            al = orc.align(seqs[a], seq)
+            if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:
+                continue
+            tl = len(seqs[a])
+            st = so.MappingStats(tl, al["nm"], tl - (al["p_end"] - al["p_start"]))
+            if st.mapping_score() <= 0.5 and st.custom_score(False) <= 0.03 and st.custom_score(False) < best.custom_score(False):
+                best, best_a, best_al = st, a, al
+        hs = so.HlaMappingStats(None, best)
+        if best_a is None:
+            out.append(dict(gene_name="", read_mapping_stats=so.read_mapping_stats_json(None, None, {}),
+                            mapping_details=so.mapping_details_json(qname, "REFERENCE", "REFERENCE", hs, True), realigned_record=None))
+            continue
+        row = alleles[best_a]
+        gene, star = row[1], ":".join(row[2])
+        fwd, ref = gene_defs[gene]
+        # minimap2's view: query = read, target = allele -> roles and I / D letters swap relative to the oracle's (pattern, text)
+        swap = {1: 2, 2: 1}
+        bm = so.Mapping(best_al["t_start"], best_al["t_end"], len(seq), best_al["p_start"], best_al["p_end"], len(seqs[best_a]), best_al["nm"],
+                        True, [(ln, swap.get(op, op)) for ln, op in best_al["cigar"]])
+        rms = so.read_mapping_stats_json(row[0], star, {row[0]: (None, so.detailed_mapping_stats(bm, seqs[best_a], seq))})
+        res = dict(gene_name=gene, read_mapping_stats=rms,
+                   mapping_details=so.mapping_details_json(qname, row[0], f"{gene}*{star}", hs, False), realigned_record=None)
+        out.append(res)
+        db_start, db_end = bm.query_start, bm.query_end
+        bs, be = max(db_start - 1000, 0), min(db_end + 1000, len(seq))
+        sal = orc.align(seq[bs:be], ref)
+        cand = []
+        if sal["cigar"] and dp_score_a1(sal["cigar"]) >= 200:
+            cand.append(so.Mapping(sal["p_start"], sal["p_end"], be - bs, sal["t_start"], sal["t_end"], len(ref), sal["nm"], True, sal["cigar"]))
+        idx, _ = so.select_best_mapping(cand, True, True)
+        if idx is None:
+            continue
+        rm = cand[idx]
+        hg_start, hg_end = bs + rm.query_start, bs + rm.query_end
+        seg = (min(db_start, hg_start), max(db_end, hg_end))
+        d = rm.target_start
+        h = so.hpc_pos(ref, d)
+        if not hg_start < db_start:
+            aal = orc.align(seqs[best_a], ref)
+            acand = []
+            if aal["cigar"] and dp_score_a1(aal["cigar"]) >= 200:
+                acand.append(so.Mapping(aal["p_start"], aal["p_end"], len(seqs[best_a]), aal["t_start"], aal["t_end"], len(ref), aal["nm"], True,
+                                        aal["cigar"]))
+            aidx, _ = so.select_best_mapping(acand, False, True)
+            if aidx is not None:
+                am = acand[aidx]
+                added = max(am.target_start - am.query_start, 0)
+                d = added + bm.target_start
+                h = so.hpc_pos(ref, added) + so.hpc_pos(row[3].encode(), bm.target_start)  # the stored (gene-strand) allele, as :312 does
+        dna = seq[seg[0]:seg[1]]
+        res["realigned_record"] = (seg[0], seg[1], d, h, dna, so.hpc(dna))
     return out
 
 

@@ -409,3 +409,13 @@ def test_variant_match_oracle_known_answers():  # the match rule of src/cyp2d6/h
     assert so.assign_haplotype_from_alleles(alleles, {"1": [0] * 6, "2": hap}, list("abcdef"), vi, True)[0] == "1"
     assert [(v["label"], v["variant_state"]) for v in rv] == [("b", "Match"), ("c", "AmbiguousMissing"), ("d", "UnknownMissing"),
                                                              ("e", "Unexpected"), ("f", "Missing")]
+
+
+def test_hpc_reference_vectors(host):  # src/util/homopolymers.rs:71-104, src/hla/realigner.rs:534-556
+    assert host.hpc("AACAAAAAAGGGTAACAA") == "ACAGTACA" == so.hpc(b"AACAAAAAAGGGTAACAA").decode()
+    seq = "AACCCGTTTT"
+    for i, c in enumerate(seq):
+        assert host.hpc_pos(seq, i) == "ACGT".index(c) == so.hpc_pos(seq.encode(), i)
+    assert host.hpc_pos("ATTGGGGGAACCCGTTTT", 6) == 2 and host.hpc("GAACCCGTTTT") == "GACGT"   # test_hpc_guide
+    assert host.hpc("AACCGGTTAACCGGTTAACCGGTT"[4:10]) == "GTA"                                    # test_realigned_record
+    assert host.hpc_pos(seq, 100) == 4 == so.hpc_pos(seq.encode(), 100) and host.hpc("") == ""

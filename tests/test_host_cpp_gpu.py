@@ -152,6 +152,54 @@ def test_realign_records_vs_oracle(host, gpu, oracle):
     assert back[0]["best_star_allele"].startswith("HLA-A*") and back[-4]["best_hla_id"] == "REFERENCE"
 
 
+def test_realign_records_full_vs_oracle(host, gpu, oracle):
+    """realign_record in full (src/hla/realigner.rs:98-350): the best database allele, then the buffered read segment against the
+    gene's hg38 sequence and -- when that mapping does not start before the allele mapping -- the allele against hg38, giving the
+    segment range and the DNA / HPC offsets; reverse-strand gene (HLA-B) alleles are flipped into hg38 orientation first."""
+    rows, _ = hla_db()
+    rng = np.random.default_rng(17)
+    fw = {}
+    for hid, gene, star, dna, cdna in rows:  # hg38-oriented allele sequences
+        fw[hid] = dna.encode() if gene == "HLA-A" else so.reverse_complement(dna.encode())
+    root = {g: next(fw[r[0]] for r in rows if r[1] == g) for g in ("HLA-A", "HLA-B")}
+    flank = {g: (rnd(rng, 1300), rnd(rng, 1300)) for g in root}
+    gene_defs = {g: (g == "HLA-A", flank[g][0] + root[g] + flank[g][1]) for g in root}
+    reads = []
+    for g in ("HLA-A", "HLA-B"):
+        ids = [r[0] for r in rows if r[1] == g]
+        L, R = flank[g]
+        reads.append((f"{g}_flanked", noisy(rng, L[-600:] + fw[ids[3]] + R[:600], 12)))      # hg38 mapping starts first: offsets from it
+        reads.append((f"{g}_inner", fw[ids[5]][300:2900]))                                   # starts inside the allele: allele-vs-hg38 path
+        reads.append((f"{g}_right_only", noisy(rng, fw[ids[7]][700:] + R[:900], 8)))
+        reads.append((f"{g}_long_flanks", L[-1250:] + fw[ids[1]] + R[:1250]))                # buffer of 1000 clips the flanks
+    reads.append(("junk", rnd(rng, 3000)))
+    reads.append(("empty", b""))
+    got = host.realign_records_full(gpu, ["HLA-A", "HLA-B"], rows, {g: (f, r.decode()) for g, (f, r) in gene_defs.items()},
+                                    [(q, s_.decode()) for q, s_ in reads])
+    want = fo.realign_records_full(oracle, ["HLA-A", "HLA-B"], rows, gene_defs, reads)
+    assert len(got) == len(want) == len(reads)
+    n_realigned = 0
+    for g_, w_, (q, s_) in zip(got, want, reads):
+        assert g_["gene_name"] == w_["gene_name"], q
+        assert g_["mapping_details"] == so.serde_pretty(w_["mapping_details"]), q
+        assert g_["read_mapping_stats"] == so.serde_pretty(w_["read_mapping_stats"]), q
+        if w_["realigned_record"] is None:
+            assert g_["realigned_record"] is None, q
+        else:
+            ws = w_["realigned_record"]
+            assert g_["realigned_record"] == (ws[0], ws[1], ws[2], ws[3], ws[4].decode(), ws[5].decode()), q
+            n_realigned += 1
+    assert n_realigned == 8 and got[-1]["realigned_record"] is None and got[-2]["realigned_record"] is None
+    by = {q: g_ for g_, (q, _) in zip(got, reads)}
+    # the flanked read: the segment covers allele + the 600 bp flanks, its offset is where the left flank piece sits in the gene sequence
+    seg = by["HLA-A_flanked"]["realigned_record"]
+    assert seg[2] == 1300 - 600 and seg[1] - seg[0] >= len(fw[[r[0] for r in rows if r[1] == "HLA-A"][3]]) + 1100
+    # the inner read has no flank: offset = allele start in hg38 (1300) + 300 into the allele, give or take the allele's indels
+    # (the best allele may be a shorter one lying inside the read: candidates are ranked by nm + unmapped, like best_n hits by score)
+    assert abs(by["HLA-A_inner"]["realigned_record"][2] - 1600) <= 12
+    assert json.loads(by["HLA-B_inner"]["mapping_details"])["best_star_allele"].startswith("HLA-B*")
+
+
 # ---- allele-pair diplotype: north_star (2), src/hla/caller.rs:889-901 -----------------------------------------
 def test_diplotype_hla_gene_vs_oracle(host, gpu, oracle):
     rows, reads = hla_db()
