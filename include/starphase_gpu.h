@@ -211,6 +211,11 @@ sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
  * list in HlaRealigner::realign_record (src/hla/realigner.rs:116-146, best_n = 5 from src/util/mapping.rs:8-14): only
  * these candidates go on to sp_align_pairs, and R x k records cross PCIe instead of the R x A matrix. */
 sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist);
+/* Same, ranked by distance + pattern_bias[p] (bias in [0, 2^30), NULL = none); dist still returns the plain distance.
+ * With bias = max |P| - |P_p| the order is "most pattern bases explained first" (|P_p| - distance descending), the stand-in
+ * for minimap2 ranking its hits by alignment score: a read that covers only part of a long allele then keeps that allele
+ * ahead of short alleles lying wholly inside the read (src/hla/realigner.rs:116-146 picks among the reported hits). */
+sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const int32_t *pattern_bias, int k, int32_t *idx, int32_t *dist);
 
 /* ---- K6: CYP2D6 allele-vector match (row N3 of SURVEY.md 8f) ------------------------------- */
 /* Replaces the haplotype loop of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:470-517): for every

@@ -218,13 +218,15 @@ __global__ void k4_compact_cigar(const AlignRecDev *__restrict__ recs, const uin
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: the k best patterns of every text (row top-k of the distance matrix), ties by lower pattern index.
+// K5: the k best patterns of every text (row top-k of the distance matrix, optionally of distance + a per-pattern bias),
+// ties by lower pattern index.
 // Stands in for minimap2's best_n hit list at the realigner (src/hla/realigner.rs:116-146): only these candidates
 // go on to the traceback, and only R x k records cross PCIe instead of the R x A matrix.
 // One thread per text; the allele-major layout D[p * ld + t] makes the loads of a warp contiguous.
 // ------------------------------------------------------------------------------------------
 template <typename T, int K>
 __global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long long ld, int nt, int np, int k,
+                                                   const int32_t *__restrict__ bias,  // optional per-pattern addend of the ranking key
                                                    int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long
 #pragma unroll
     for (int q = 0; q < K; ++q) { bd[q] = 0xFFFFFFFFu; bi[q] = 0xFFFFFFFFu; }
     for (int a = 0; a < np; ++a) {
-        const uint32_t v = static_cast<uint32_t>(D[static_cast<long long>(a) * ld + t]);
+        const uint32_t v = static_cast<uint32_t>(D[static_cast<long long>(a) * ld + t]) + (bias ? static_cast<uint32_t>(bias[a]) : 0u);
         if (v < bd[K - 1]) {  // strict: on ties the earlier pattern stays ahead
             bd[K - 1] = v; bi[K - 1] = static_cast<uint32_t>(a);
 #pragma unroll
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long
         if (q < k) {
             const bool have = bi[q] != 0xFFFFFFFFu;
             idx[static_cast<long long>(t) * k + q] = have ? static_cast<int32_t>(bi[q]) : -1;
-            dist[static_cast<long long>(t) * k + q] = have ? static_cast<int32_t>(bd[q]) : -1;
+            dist[static_cast<long long>(t) * k + q] = have ? static_cast<int32_t>(D[static_cast<long long>(bi[q]) * ld + t]) : -1;
         }
 }
 

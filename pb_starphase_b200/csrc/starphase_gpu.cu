@@ -1120,32 +1120,48 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
 // ------------------------------------------------------------------------------------------
 // K5: row top-k of a device distance matrix
 // ------------------------------------------------------------------------------------------
-extern "C" sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist) {
+extern "C" sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const int32_t *pattern_bias, int k, int32_t *idx,
+                                        int32_t *dist) {
     if (!ctx) return SP_ERR_INVALID;
     if (!d || !idx || !dist) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: NULL argument");
     if (k < 1 || k > 16) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: k must be in [1, 16]");
     if (d->nt > 0x7FFFFFF0ll || d->np > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "sp_row_topk: matrix too large");
     if (d->nt == 0) return SP_OK;
+    if (pattern_bias)
+        for (int64_t p = 0; p < d->np; ++p)
+            if (pattern_bias[p] < 0 || pattern_bias[p] > 0x3FFFFFFF) return fail(ctx, SP_ERR_INVALID, "sp_row_topk_biased: bias must be in [0, 2^30)");
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = static_cast<size_t>(d->nt) * static_cast<size_t>(k);
     void *buf = nullptr;
     SP_CUDA(ctx, ctx_scratch(ctx, 2 * n * sizeof(int32_t), &buf));
     int32_t *d_idx = static_cast<int32_t *>(buf), *d_dist = d_idx + n;
+    int32_t *d_bias = nullptr;
+    if (pattern_bias && d->np > 0) {
+        SP_CUDA(ctx, dev_malloc(ctx, &d_bias, static_cast<size_t>(d->np) * sizeof(int32_t)));
+        cudaError_t e = cudaMemcpyAsync(d_bias, pattern_bias, static_cast<size_t>(d->np) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { dev_free(ctx, d_bias); SP_CUDA(ctx, e); }
+    }
     const int nt = static_cast<int>(d->nt), np = static_cast<int>(d->np);
     const unsigned grid = static_cast<unsigned>((nt + 127) / 128);
     if (d->elem_bits == 16) {
-        if (k <= 8) k5_row_topk<uint16_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
-        else k5_row_topk<uint16_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+        if (k <= 8) k5_row_topk<uint16_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
+        else k5_row_topk<uint16_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
     } else {
-        if (k <= 8) k5_row_topk<int32_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
-        else k5_row_topk<int32_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_idx, d_dist);
+        if (k <= 8) k5_row_topk<int32_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
+        else k5_row_topk<int32_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
     }
     ++ctx->launches;
-    SP_CUDA(ctx, cudaGetLastError());
-    SP_CUDA(ctx, cudaMemcpyAsync(idx, d_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SP_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dist, d_dist, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d_bias);
+    SP_CUDA(ctx, e);
     return SP_OK;
+}
+
+extern "C" sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int32_t *dist) {
+    return sp_row_topk_biased(ctx, d, nullptr, k, idx, dist);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -154,10 +154,12 @@ std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const DeviceMatrix &d, con
     return out;
 }
 
-void GpuAligner::row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist) {
+void GpuAligner::row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
+                          const std::vector<int32_t> *pattern_bias) {
     const size_t n = std::max<size_t>(static_cast<size_t>(d.nt_) * static_cast<size_t>(k), 1);
     idx.assign(n, -1); dist.assign(n, -1);
-    check(sp_row_topk(ctx_, d.d_, k, idx.data(), dist.data()), "sp_row_topk");
+    if (pattern_bias && pattern_bias->size() != static_cast<size_t>(d.np_)) throw HostError("row_topk: one bias per pattern expected");
+    check(sp_row_topk_biased(ctx_, d.d_, pattern_bias ? pattern_bias->data() : nullptr, k, idx.data(), dist.data()), "sp_row_topk");
 }
 
 std::vector<uint64_t> GpuAligner::chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,

@@ -162,10 +162,17 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
     const size_t A = alleles_.size();
     if (D.n_targets() != static_cast<int64_t>(reads.size()) || D.n_patterns() != static_cast<int64_t>(A))
         throw HostError("realign_records_scored: distance matrix has the wrong shape");
-    // the best_n hits of every read: the alleles with the smallest distance, ties by database order (K5)
+    // the best_n hits of every read (K5): the alleles with the most bases explained, |allele| - (nm + unmapped), ties by
+    // database order -- minimap2 ranks its hits by alignment score, so a read covering part of a long allele keeps that
+    // allele ahead of short alleles that lie wholly inside the read
     const int k = std::max(1, std::min(n_candidates, 16));
+    const SeqList &allele_seqs = index_->sequences();
+    size_t max_len = 0;
+    for (const std::string &a : allele_seqs) max_len = std::max(max_len, a.size());
+    std::vector<int32_t> bias(A);
+    for (size_t a = 0; a < A; ++a) bias[a] = static_cast<int32_t>(max_len - allele_seqs[a].size());
     std::vector<int32_t> cand, cand_dist;
-    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist);
+    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist, &bias);
     std::vector<std::pair<int32_t, int32_t>> pairs;
     std::vector<size_t> first_pair(reads.size() + 1, 0);
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -176,7 +183,6 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
                     pairs.emplace_back(static_cast<int32_t>(r), cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)]);
     }
     first_pair[reads.size()] = pairs.size();
-    const SeqList &allele_seqs = index_->sequences();
     std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs, pairs);
 
     std::vector<BestHit> out(reads.size());

@@ -227,7 +227,9 @@ class GpuAligner {
     std::shared_ptr<PatternSet> prepare_patterns(const SeqList &patterns);
     std::unique_ptr<DeviceMatrix> score_device(const SeqList &targets, const PatternSet &patterns);          // K1
     std::vector<sp_pair_rec> pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k);           // K2
-    void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist);      // K5
+    // K5; pattern_bias (optional, one entry per pattern) is added to the distance for ranking only
+    void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
+                  const std::vector<int32_t> *pattern_bias = nullptr);
     // S[i * n_chains + j], j >= i: sum over reads of min(B[i][r], B[j][r]) for the chain-window matrix B
     std::vector<uint64_t> chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
                                           const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps);

@@ -65,6 +65,8 @@ extern "C" {
                           pair_target: *const i32, pair_pattern: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
                           cigar_cap: i64, cigar_used: *mut i64) -> c_int;
     pub fn sp_row_topk(ctx: *mut sp_ctx, d: *const sp_dmatrix, k: c_int, idx: *mut i32, dist: *mut i32) -> c_int;
+    pub fn sp_row_topk_biased(ctx: *mut sp_ctx, d: *const sp_dmatrix, pattern_bias: *const i32, k: c_int, idx: *mut i32,
+                              dist: *mut i32) -> c_int;
     pub fn sp_variant_match(ctx: *mut sp_ctx, n_seq: i64, n_hap: i64, n_var: i64, seq_alleles: *const u8, hap_alleles: *const u8,
                             is_vi: *const u8, vi_match: *mut u32, all_match: *mut u32) -> c_int;
     pub fn sp_chain_window_scores(ctx: *mut sp_ctx, n_chains: i64, chain_off: *const i32, chain_items: *const i32, n_reads: i64,

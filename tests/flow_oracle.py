@@ -97,7 +97,7 @@ def hla_debug_json(orc, db: Sequence[DbRow], gene: str, consensuses: Sequence[Tu
 
 def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5,
                     D: Optional[np.ndarray] = None) -> List[dict]:
-    """src/hla/realigner.rs:98-211: candidates = the n best alleles by distance (ties by database order)."""
+    """src/hla/realigner.rs:98-211: candidates = the n alleles with the most bases explained, |allele| - (nm + unmapped), ties by database order."""
     alleles = [r for r in sorted(db, key=lambda r: r[0].encode()) if r[1] in genes and r[3] is not None]
     seqs = [r[3].encode() for r in alleles]
     if D is None:
@@ -105,7 +105,8 @@ def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Seque
     out = []
     for r, (qname, seq) in enumerate(reads):
         best, best_a = so.MappingStats(len(seq), len(seq), 0), None
-        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        # candidates = the n alleles with the most bases explained (|allele| - D), ties by database order
+        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
             al = orc.align(seqs[a], seq)
             if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:  # db_aligner is the plain map-hifi preset (a = 1)
@@ -132,7 +133,8 @@ def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_de
     out = []
     for r, (qname, seq) in enumerate(reads):
         best, best_a, best_al = so.MappingStats(len(seq), len(seq), 0), None, None
-        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        # candidates = the n alleles with the most bases explained (|allele| - D), ties by database order
+        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
             al = orc.align(seqs[a], seq)
             if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:

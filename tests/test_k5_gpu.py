@@ -30,6 +30,17 @@ def test_row_topk_vs_numpy(ctx, bits):
         idx, dist = ctx.row_topk(d, k)
         eidx, edist = expect(D, k)
         assert (idx == eidx).all() and (dist == edist).all(), k
+    # sp_row_topk_biased with bias = max |P| - |P|: "most pattern bases explained first"; dist stays the plain distance
+    lens = np.array([len(p) for p in pats], dtype=np.int64)
+    bias = (lens.max() - lens).astype(np.int32)
+    for k in (1, 5, 16):
+        idx, dist = ctx.row_topk(d, k, bias=bias)
+        order = np.argsort(D + bias[None, :], axis=1, kind="stable")[:, :k]
+        assert (idx == order).all() and (dist == np.take_along_axis(D, order, axis=1)).all(), k
+    import pb_starphase_b200 as sp
+
+    with pytest.raises(sp.SpError):
+        ctx.row_topk(d, 5, bias=-np.ones(len(pats), dtype=np.int32))
     d.close(); T.close(); P.close()
 
 
