@@ -551,7 +551,7 @@ def run_ours(args):
                           frac=achieved / int_peak2,
                           peak_source="measured live: dependent-free LOP3+IMAD loop = ALU and FMA pipes together (sp_int_peak kind 2)",
                           peak_alu_pipe_only=int_peak / 1e12, frac_alu_pipe_only=achieved / int_peak,
-                          note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one, ~97 % busy in ncu) and 6 "
+                          note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one, ~92 % busy in ncu) and 6 "
                                "as IMAD on the FMA pipe, so the algorithmic count can exceed the ALU-pipe-only peak (DESIGN.md 4.1)",
                           k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12,
                           # dram__bytes_read.sum + dram__bytes_write.sum of the DNA launches of one step (ncu, B200, this workload at N = 1,

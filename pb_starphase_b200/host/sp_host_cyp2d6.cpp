@@ -195,7 +195,7 @@ Cyp2d6Extractor::Cyp2d6Extractor(GpuAligner &gpu, std::vector<std::pair<Cyp2d6Re
                      [](const auto &a, const auto &b) { return a.first.full_allele() < b.first.full_allele(); });  // key_order, :175-183
 }
 
-static double overlap_score(size_t s1, size_t e1, size_t s2, size_t e2) {  // :877-893
+double overlap_score(size_t s1, size_t e1, size_t s2, size_t e2) {  // :877-893
     const size_t min_end = std::min(e1, e2), max_start = std::max(s1, s2);
     if (max_start >= min_end) return 0.0;
     return static_cast<double>(min_end - max_start) / std::min(static_cast<double>(e1 - s1), static_cast<double>(e2 - s2));
@@ -332,6 +332,12 @@ const char *variant_state_name(VariantAlleleRelationship v) {
         case VariantAlleleRelationship::UnknownMissing: return "UnknownMissing";
     }
     return "Unknown";
+}
+
+std::string RegionVariant::to_string() const {  // Display, src/data_types/region_variants.rs:56-74
+    const char *pre = variant_state == VariantAlleleRelationship::Match ? "=" : variant_state == VariantAlleleRelationship::Unexpected ? "+"
+                    : variant_state == VariantAlleleRelationship::Missing ? "-" : "?";
+    return pre + label;
 }
 
 Json RegionVariant::to_json() const {

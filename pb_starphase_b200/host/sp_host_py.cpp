@@ -260,6 +260,10 @@ PYBIND11_MODULE(_starphase_host, m) {
         }
         return out;
     });
+    m.def("overlap_score", &overlap_score);
+    m.def("region_variant_string", [](const std::string &label, bool is_vi, int state) {
+        return RegionVariant{label, is_vi, static_cast<VariantAlleleRelationship>(state)}.to_string();
+    });
     m.def("alleles_from_traversal", &alleles_from_traversal);
     m.def("assign_haplotypes_from_alleles", [](GpuAligner &g, const std::vector<std::vector<uint8_t>> &alleles,
                                                const std::map<std::string, std::vector<uint8_t>> &lookup,

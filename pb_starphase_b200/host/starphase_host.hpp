@@ -471,6 +471,9 @@ struct AlleleMapping {  // src/cyp2d6/haplotyper.rs:836-869
     MappingStats mapping_stats;               // relative to the template, with clippings
 };
 
+// src/cyp2d6/haplotyper.rs:877-893: shared length over the shorter of the two ranges [s1, e1), [s2, e2)
+double overlap_score(size_t s1, size_t e1, size_t s2, size_t e2);
+
 // The search half of Cyp2d6Extractor (src/cyp2d6/haplotyper.rs:142-315): which of the D6 / D7 / hybrid / REP / spacer /
 // link / *5 templates (generate_cyp_hybrids, src/cyp2d6/definitions.rs:346-464) occur where in a sequence.
 class Cyp2d6Extractor {
@@ -500,6 +503,7 @@ struct RegionVariant {  // src/data_types/region_variants.rs:26-34
     std::string label;
     bool is_vi = false;
     VariantAlleleRelationship variant_state = VariantAlleleRelationship::Unknown;
+    std::string to_string() const;  // "=label" / "+label" / "-label" / "?label"
     Json to_json() const;
 };
 struct VariantMetadata {  // the members of LoadedVariants the typing reads (src/cyp2d6/haplotyper.rs:617-640, :812)

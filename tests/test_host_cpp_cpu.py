@@ -419,3 +419,13 @@ def test_hpc_reference_vectors(host):  # src/util/homopolymers.rs:71-104, src/hl
     assert host.hpc_pos("ATTGGGGGAACCCGTTTT", 6) == 2 and host.hpc("GAACCCGTTTT") == "GACGT"   # test_hpc_guide
     assert host.hpc("AACCGGTTAACCGGTTAACCGGTT"[4:10]) == "GTA"                                    # test_realigned_record
     assert host.hpc_pos(seq, 100) == 4 == so.hpc_pos(seq.encode(), 100) and host.hpc("") == ""
+
+
+def test_overlap_score_and_region_variant_display(host):  # src/cyp2d6/haplotyper.rs:935-941, src/data_types/region_variants.rs:80-110
+    assert host.overlap_score(0, 1, 1, 2) == 0.0        # no overlap
+    assert host.overlap_score(0, 10, 1, 5) == 1.0       # fully contained
+    assert host.overlap_score(0, 10, 5, 100) == 0.5     # half shared of first
+    assert host.overlap_score(15, 100, 0, 20) == 0.25   # quarter shared of second
+    states = ["Unknown", "Match", "Unexpected", "Missing", "AmbiguousUnexpected", "AmbiguousMissing", "UnknownUnexpected", "UnknownMissing"]
+    shown = [host.region_variant_string("rs123", True, k) for k in range(len(states))]
+    assert shown == ["?rs123", "=rs123", "+rs123", "-rs123", "?rs123", "?rs123", "?rs123", "?rs123"]
