@@ -253,7 +253,7 @@ def run_cohort(ctx, w, n_samples, rank, world):
         Dt = ctx.score_batch(c["reads"], c["templates"])                      # find_base_type_in_sequence
         cells += sum(map(len, c["reads"])) * sum(map(len, c["templates"]))
         mark("cyp_templates")
-        Dw, Sw, Ew = ctx.score_spans(c["consensuses"], c["segments"])          # weight_sequence (+ overlap spans)
+        Dw, Sw, Ew = ctx.score_spans(c["consensuses"], c["segments"], max_dist_permille=350)  # weight_sequence (+ overlap spans of the pairs an aligner would report)
         cells += 2 * sum(map(len, c["consensuses"])) * sum(map(len, c["segments"]))
         mark("cyp_spans")
         Wt = np.ascontiguousarray(Dw.T.astype(np.uint32))                       # [segment][consensus]

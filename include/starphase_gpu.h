@@ -165,6 +165,12 @@ sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
  * [n_targets][n_patterns] row-major int32, caller-allocated.  Meant for CYP2D6-sized batches (one warp per pair). */
 sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int32_t *D,
                          int32_t *start_col, int32_t *end_col);
+/* Same; pairs whose distance exceeds max_dist_permille / 1000 of the pattern length get start_col = -1 and cost no
+ * second pass (D and end_col are still written).  weight_sequence uses 350: sequences that far apart (unrelated DNA sits
+ * near 500) are pairs for which the reference's aligner returns no mapping at all (src/cyp2d6/chaining.rs:58-62 then
+ * leaves the default (|S|, 0.0)).  A negative value disables the filter. */
+sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int max_dist_permille,
+                                  int32_t *D, int32_t *start_col, int32_t *end_col);
 
 /* K3 (seam S4, src/cyp2d6/chaining.rs:683-731): the window scan of containment_score hoisted out of the pair loop.
  * Chains are CSR lists of haplotype (consensus) indices; read r owns segments seg_off[r] .. seg_off[r+1]) and

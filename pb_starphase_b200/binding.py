@@ -75,6 +75,7 @@ SIGNATURES = {
     "sp_dmatrix_wrap": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "sp_score_batch": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P]),
     "sp_score_spans": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), _P, _P, _P]),
+    "sp_score_spans_filtered": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P, _P]),
     "sp_align_pairs": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                  C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
@@ -205,15 +206,17 @@ class Context:
                                              E.ctypes.data if E is not None else None))
         return (D, E) if want_end_col else D
 
-    def score_spans(self, targets, patterns):
+    def score_spans(self, targets, patterns, max_dist_permille: int = -1):
         """K3: (D, start_col, end_col), each [n_targets, n_patterns] int32; the optimal placement of pattern p
-        covers text columns [start, end) of target t."""
+        covers text columns [start, end) of target t.  With max_dist_permille >= 0, pairs with D * 1000 > |P| * that
+        get start_col = -1 (no reverse pass)."""
         tb, to = targets if isinstance(targets, tuple) else pack_sequences(targets)
         pb, po = patterns if isinstance(patterns, tuple) else pack_sequences(patterns)
         nt, np_ = len(to) - 1, len(po) - 1
         D, S, E = (np.zeros((nt, np_), dtype=np.int32) for _ in range(3))
         ts, ps = _seqset(tb, to), _seqset(pb, po)
-        self._check(self._lib.sp_score_spans(self._h, C.byref(ts), C.byref(ps), D.ctypes.data, S.ctypes.data, E.ctypes.data))
+        self._check(self._lib.sp_score_spans_filtered(self._h, C.byref(ts), C.byref(ps), int(max_dist_permille), D.ctypes.data,
+                                                      S.ctypes.data, E.ctypes.data))
         return D, S, E
 
     def align_pairs(self, targets, patterns, pairs):

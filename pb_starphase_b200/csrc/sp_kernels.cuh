@@ -339,6 +339,9 @@ struct SpanParams {
     long long ld;
     int nt, np;
     uint32_t one, m1, seed_a, seed_b;
+    int max_dist_permille;   // pairs with D * 1000 > |P| * this get S = -1 and no reverse pass; < 0: every pair
+    const int32_t *plen;     // [np] pattern lengths
+    unsigned long long *next_pair;  // work counter (zeroed by the host): pairs are handed out one at a time
 };
 
 __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
@@ -348,13 +351,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *blob = reinterpret_cast<uint32_t *>(smem_raw) + warp * BW;
     const long long total = static_cast<long long>(p.nt) * p.np;
-    const long long n_warps = static_cast<long long>(gridDim.x) * K1_WARPS;
-    const long long per = (total + n_warps - 1) / n_warps;
-    const long long q0 = (static_cast<long long>(blockIdx.x) * K1_WARPS + warp) * per;
-    const long long q1 = min(total, q0 + per);
     int cur_pat = -1;
-    for (long long q = q0; q < q1; ++q) {  // pattern-major so the blob is reloaded rarely
+    for (;;) {  // dynamic hand-out, pattern-major: the pass lengths differ by orders of magnitude between pairs
+        unsigned long long qq = 0;
+        if (lane == 0) qq = atomicAdd(p.next_pair, 1ull);
+        const long long q = static_cast<long long>(__shfl_sync(0xffffffffu, qq, 0));
+        if (q >= total) break;
         const int pat = static_cast<int>(q / p.nt), t = static_cast<int>(q - static_cast<long long>(pat) * p.nt);
+        {
+            const long long o0 = static_cast<long long>(pat) * p.ld + t;
+            const long long mlen = p.plen[pat];
+            if (p.max_dist_permille >= 0 && static_cast<long long>(p.D[o0]) * 1000 > mlen * p.max_dist_permille) {
+                if (lane == 0) p.S[o0] = -1;  // too far apart for an aligner to have reported anything: no span
+                continue;
+            }
+        }
         if (pat != cur_pat) {
             __syncwarp();
             const uint32_t *src = p.blobs + static_cast<size_t>(pat) * BW;

@@ -833,15 +833,22 @@ extern "C" sp_status sp_score_batch(sp_ctx *ctx, const sp_seqset *targets, const
 // ------------------------------------------------------------------------------------------
 extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int32_t *D,
                                     int32_t *start_col, int32_t *end_col) {
+    return sp_score_spans_filtered(ctx, targets, patterns, -1, D, start_col, end_col);
+}
+
+extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int max_dist_permille,
+                                             int32_t *D, int32_t *start_col, int32_t *end_col) {
     if (!ctx) return SP_ERR_INVALID;
     if (!D || !start_col || !end_col) return fail(ctx, SP_ERR_INVALID, "sp_score_spans: NULL output");
+    if (max_dist_permille > 1000) return fail(ctx, SP_ERR_INVALID, "sp_score_spans_filtered: max_dist_permille must be <= 1000 (or negative: no filter)");
     sp_patterns *p = nullptr; sp_targets *t = nullptr; sp_dmatrix *d = nullptr;
     uint8_t *d_bases = nullptr; long long *d_offs = nullptr;
-    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_S = nullptr;
+    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_S = nullptr, *d_plen = nullptr;
     uint32_t *d_lane_info1 = nullptr, *d_blobs = nullptr;
+    unsigned long long *d_next = nullptr;
     auto cleanup = [&]() {
         dev_free(ctx, d_bases); dev_free(ctx, d_offs); dev_free(ctx, d_lane_pat); dev_free(ctx, d_lane_row0); dev_free(ctx, d_lane_info1);
-        dev_free(ctx, d_blobs); dev_free(ctx, d_S);
+        dev_free(ctx, d_blobs); dev_free(ctx, d_S); dev_free(ctx, d_plen); dev_free(ctx, d_next);
         sp_dmatrix_destroy(d); sp_targets_destroy(t); sp_patterns_destroy(p);
     };
     // forward pass: distances and the smallest end column of a best placement
@@ -883,6 +890,12 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(SPAN_U) * 4), "cudaMalloc span blobs"));
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_S), static_cast<size_t>(np * d->ld) * 4), "cudaMalloc span starts"));
     SP_TRY(cu(cudaMemsetAsync(d_S, 0, static_cast<size_t>(np * d->ld) * 4, ctx->stream), "memset"));
+    std::vector<int32_t> plen(static_cast<size_t>(np));
+    for (int64_t i = 0; i < np; ++i) plen[static_cast<size_t>(i)] = static_cast<int32_t>(patterns->offsets[i + 1] - patterns->offsets[i]);
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_plen), static_cast<size_t>(np) * 4), "cudaMalloc"));
+    SP_TRY(cu(cudaMemcpyAsync(d_plen, plen.data(), static_cast<size_t>(np) * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_next), sizeof(unsigned long long)), "cudaMalloc"));
+    SP_TRY(cu(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream), "memset"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_pat, lane_pat.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
@@ -898,6 +911,7 @@ extern "C" sp_status sp_score_spans(sp_ctx *ctx, const sp_seqset *targets, const
         prm.blobs = d_blobs; prm.tbases = t->d_bases; prm.toffs = t->d_offs;
         prm.D = static_cast<const int32_t *>(d->d); prm.E = d->d_end; prm.S = d_S; prm.ld = d->ld;
         prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
+        prm.max_dist_permille = max_dist_permille; prm.plen = d_plen; prm.next_pair = d_next;
         const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(SPAN_U) * 4;
         SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "k3_span_starts smem"));

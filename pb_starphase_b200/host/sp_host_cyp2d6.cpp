@@ -425,8 +425,11 @@ std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &se
     std::vector<SequenceWeights> out(segments.size());
     if (segments.empty()) return out;
     // pattern = read segment (must be explained completely, chaining.rs:66), text = consensus (free ends, its clips form the overlap)
+    // minimap2 reports nothing for sequences that far apart (unrelated DNA sits near 50 % unit-cost distance); the exhaustive
+    // aligner always finds some placement, so pairs above 35 % count as "no mapping" and keep the default (|S|, 0.0) of :41
+    const int kNoMappingPermille = 350;
     std::vector<int32_t> D, S, E;
-    gpu.score_spans(consensuses, segments, D, S, E);
+    gpu.score_spans(consensuses, segments, D, S, E, kNoMappingPermille);
     const size_t ns = segments.size(), nc = consensuses.size();
     for (size_t s = 0; s < ns; ++s) {
         const size_t seq_len = segments[s].size();
@@ -438,6 +441,7 @@ std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &se
             const size_t o = k * ns + s;                              // [target = consensus][pattern = segment]
             const size_t match_score = static_cast<size_t>(D[o]);
             if (match_score >= seq_len) continue;                     // nothing aligned: the aligner reports no hit
+            if (S[o] < 0 || match_score * 1000 > seq_len * static_cast<size_t>(kNoMappingPermille)) continue;  // too far apart: no hit
             const size_t con_len = consensuses[k].size();
             const size_t clipped = static_cast<size_t>(S[o]) + (con_len - static_cast<size_t>(E[o]));
             const double overlap = 1.0 - static_cast<double>(clipped) / static_cast<double>(con_len);  // :81

@@ -48,11 +48,11 @@ std::vector<int32_t> GpuAligner::score_batch(const SeqList &targets, const SeqLi
 }
 
 void GpuAligner::score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
-                             std::vector<int32_t> &end) {
+                             std::vector<int32_t> &end, int max_dist_permille) {
     Packed t(targets), p(patterns);
     const size_t n = std::max<size_t>(targets.size() * patterns.size(), 1);
     D.assign(n, 0); start.assign(n, 0); end.assign(n, 0);
-    check(sp_score_spans(ctx_, &t.set, &p.set, D.data(), start.data(), end.data()), "sp_score_spans");
+    check(sp_score_spans_filtered(ctx_, &t.set, &p.set, max_dist_permille, D.data(), start.data(), end.data()), "sp_score_spans");
 }
 
 std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const SeqList &patterns,

@@ -217,8 +217,9 @@ class GpuAligner {
     GpuAligner &operator=(const GpuAligner &) = delete;
     // D[t * patterns.size() + p]; end_col (optional) = smallest end column of a best placement
     std::vector<int32_t> score_batch(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> *end_col = nullptr);
+    // start = -1 where D * 1000 > |pattern| * max_dist_permille (no span computed); negative = every pair
     void score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
-                     std::vector<int32_t> &end);
+                     std::vector<int32_t> &end, int max_dist_permille = -1);
     std::vector<Alignment> align_pairs(const SeqList &targets, const SeqList &patterns,
                                        const std::vector<std::pair<int32_t, int32_t>> &pairs);
     std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,

@@ -61,6 +61,8 @@ extern "C" {
                           dist: *mut i32, end_col: *mut i32) -> c_int;
     pub fn sp_score_spans(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, dist: *mut i32,
                           start_col: *mut i32, end_col: *mut i32) -> c_int;
+    pub fn sp_score_spans_filtered(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, max_dist_permille: c_int,
+                                   dist: *mut i32, start_col: *mut i32, end_col: *mut i32) -> c_int;
     pub fn sp_align_pairs(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, n_pairs: i64,
                           pair_target: *const i32, pair_pattern: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
                           cigar_cap: i64, cigar_used: *mut i64) -> c_int;

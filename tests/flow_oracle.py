@@ -218,6 +218,9 @@ def index_label(row) -> str:
     return (f"{row[2]}" if row[2] is not None else "X") + "_" + lab.full_allele()
 
 
+NO_MAPPING_PERMILLE = 350  # unit-cost distance above which a (segment, consensus) pair counts as "no mapping"
+
+
 def weight_sequences(orc, segments: Sequence[bytes], consensuses: Sequence[bytes], labels) -> List[list]:
     """src/cyp2d6/chaining.rs:28-103 per segment; one hit per consensus unless nothing of the segment aligns."""
     if not segments:
@@ -227,8 +230,8 @@ def weight_sequences(orc, segments: Sequence[bytes], consensuses: Sequence[bytes
     for s, seg in enumerate(segments):
         hits = []
         for k, con in enumerate(consensuses):
-            if len(con) == 0 or len(seg) == 0 or D[k, s] >= len(seg):
-                hits.append([])
+            if len(con) == 0 or len(seg) == 0 or D[k, s] >= len(seg) or int(D[k, s]) * 1000 > len(seg) * NO_MAPPING_PERMILLE:
+                hits.append([])  # nothing aligns, or so far apart that an aligner reports no mapping
             else:
                 hits.append([(int(D[k, s]), int(S[k, s]), len(con) - int(E[k, s]), len(con))])
         out.append(so.weight_sequence_from_hits(len(seg), labels, hits))

@@ -75,6 +75,14 @@ def test_weight_sequence_shapes(ctx, oracle):
     seg_len = np.array([len(s) for s in segs])[None, :]
     assert (np.abs((E - S) - seg_len) <= D).all()
     assert (S >= 0).all() and (E <= np.array([len(c) for c in cons])[:, None]).all() and (S <= E).all()
+    # sp_score_spans_filtered: the same numbers, but pairs further apart than 35 % of the segment get start = -1 (no reverse pass):
+    # the unrelated (segment, consensus) pairs of this set, for which the reference's aligner would report no mapping
+    Df, Sf, Ef = ctx.score_spans(cons, segs, max_dist_permille=350)
+    far = D * 1000 > seg_len * 350
+    assert far.any() and (~far).any()
+    assert (Df == D).all() and (Ef == E).all() and (Sf[~far] == S[~far]).all() and (Sf[far] == -1).all()
+    D0, S0, E0 = ctx.score_spans(cons, segs, max_dist_permille=0)   # only exact placements keep a span
+    assert ((S0 == -1) == (D > 0)).all() and (S0[D == 0] == S[D == 0]).all()
     # golden: exact copy wins, N at the differing base ties all three (src/cyp2d6/chaining.rs:1050-1080)
     g = json.loads((GOLDEN / "weight_sequence.json").read_text())
     Dg, Sg, Eg = ctx.score_spans([c.encode() for c in g["consensuses"]], [q.encode() for q in g["queries"]])
