@@ -54,6 +54,7 @@ struct K1Params {
     int out16;
     int prefix_mode;                // SP_PREFIX: top row delta +1
     uint32_t one, m1, sixteen;      // +1, -1 (0xFFFFFFFF), 16: passed at run time so `x * one + y` stays an IMAD (FMA pipe)
+    int *next_item;                 // work counter (zeroed by the host before the launch): items are handed out dynamically
     uint32_t seed_a, seed_b;        // 1, 0xFFFFFFFF again: `seed_a - seed_b` sets the borrow that seeds the Myers add chain.  Separate
                                     // parameters on purpose: inline-asm operands live in R registers, and sharing them with one / m1
                                     // turned every IMAD multiplier from a uniform register into a third R operand (K1 -10 %)
@@ -299,7 +300,14 @@ __global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K
 
     uint32_t parity = 0;
     const int n_items = p.n_groups * p.n_tiles;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    __shared__ int s_item;
+    // items (pattern group x text tile) are handed out from an atomic counter: tiles hold whole texts and differ in length,
+    // and with few reads per call (the cohort's 64 per gene) a static round-robin left the last round a fifth full
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(p.next_item, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
         const int g = item / p.n_tiles;
         const int tile = item - g * p.n_tiles;
         const int c0 = p.tile_chunk_off[tile];

@@ -33,6 +33,7 @@ struct sp_ctx {
     // pool 0 = staging (transposed result rows, K5 lists, K4 traceback scratch), 1 = K4 CIGAR regions, 2 = K4 blobs, 3 = K4 dense CIGAR
     void *pool[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pool_bytes[4] = {0, 0, 0, 0};
+    int *d_counter = nullptr;  // K1's work counter
 };
 
 // stream-ordered reuse is safe: every user synchronises the context stream before it returns
@@ -180,6 +181,10 @@ extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
         cudaMemPoolSetAttribute(mempool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
     cudaGetLastError();
+    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) {
+        sp_ctx_destroy(ctx);
+        return fail(nullptr, SP_ERR_NOMEM, "cudaMalloc failed");
+    }
     *out = ctx;
     return SP_OK;
 }
@@ -192,6 +197,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (void *p : ctx->pool) cudaFree(p);
+    cudaFree(ctx->d_counter);
     delete ctx;
 }
 
@@ -611,6 +617,7 @@ static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_
     // persistent CTAs: a multiple of the SM count, each looping over (pattern-group, text-tile) items
     const int grid = std::min(n_items, ctx->num_sms * occ);
     if (first) ev_begin(ctx, 0);  // the K1 timer spans the launches of all lane-width classes of one call
+    SP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
     k1_infix<U, TE><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
     if (last) ev_end(ctx, 0);
     ++ctx->launches;
@@ -639,13 +646,25 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         const int U = pc.U;
         const size_t blob_bytes = static_cast<size_t>(K1_WARPS) * blob_words(U) * 4;
         const int64_t max_tc = (static_cast<int64_t>(ctx->smem_optin) - static_cast<int64_t>(blob_bytes) - 1024) / 8 / 2 * 2;
+        // Tile capacity (chunks).  Tiles hold whole texts; an item costs (chunks in the tile + 31 fill/drain steps) and the
+        // persistent grid finishes about half an item late on average, so model  time ~ (tile + 31) * (items / grid + 1/2)
+        // and take the best of a few capacities: big tiles when there is plenty of work (bench: 87 k items), small ones when
+        // a call brings few reads (cohort: 64 reads per gene -> 1,246 items at 4,096 chunks was 4.2 rounds of 296 CTAs)
         int64_t tc = 4096;
-        if (const char *force_tc = getenv("SP_FORCE_TC")) tc = std::max<int64_t>(64, atoll(force_tc));  // experiment hook: tile capacity in chunks
-        const int64_t want_items = 4ll * ctx->num_sms;
-        if (static_cast<int64_t>(pc.n_groups) * ((t->sum_nch + tc - 1) / tc) < want_items) {
-            const int64_t want_tiles = (want_items + pc.n_groups - 1) / pc.n_groups;
-            tc = std::max<int64_t>(64, (t->sum_nch + want_tiles - 1) / want_tiles);
+        {
+            const double avg = static_cast<double>(t->sum_nch) / static_cast<double>(std::max<int64_t>(t->n, 1));
+            const double grid_ctas = 2.0 * ctx->num_sms;
+            double best_cost = 0;
+            for (int64_t cand : {4096, 3072, 2048, 1536, 1024, 768, 512, 384, 256}) {
+                if (cand < t->max_nch && cand != 4096) continue;
+                const double per_tile = std::max(1.0, std::floor(static_cast<double>(cand) / std::max(avg, 1.0)));
+                const double tiles = std::ceil(static_cast<double>(t->n) / per_tile);
+                const double tile_nch = std::min(per_tile, static_cast<double>(t->n)) * avg;
+                const double cost = (tile_nch + 31.0) * (tiles * pc.n_groups / grid_ctas + 0.5);
+                if (best_cost == 0 || cost < best_cost) { best_cost = cost; tc = cand; }
+            }
         }
+        if (const char *force_tc = getenv("SP_FORCE_TC")) tc = std::max<int64_t>(64, atoll(force_tc));  // experiment hook: tile capacity in chunks
         tc = std::max<int64_t>(tc, t->max_nch);
         tc = (tc + 1) / 2 * 2;
         if (tc > max_tc)
@@ -664,6 +683,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         prm.n_groups = pc.n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
         prm.prefix_mode = p->mode == SP_PREFIX;
         prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu; prm.sixteen = 16u;
+        prm.next_item = ctx->d_counter;
         const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
         if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
         const size_t smem = blob_bytes + static_cast<size_t>(tc + 2) * 8;
