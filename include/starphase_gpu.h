@@ -211,6 +211,16 @@ sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset 
                          const int32_t *pair_target, const int32_t *pair_pattern, sp_align_rec *recs,
                          uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used);
 
+/* Same for windows of the texts: pair q is aligned inside targets[pair_target[q]][win_begin[q], win_end[q]) only, and
+ * t_start / t_end of its record are relative to win_begin[q].  The template search of find_base_type_in_sequence
+ * (src/cyp2d6/haplotyper.rs:193-249) aligns 39 templates per read on the placement windows K1 reported: thousands of
+ * overlapping windows of ~100 reads, which this call takes as (read, begin, end) instead of as copied sub-strings.
+ * win_begin == win_end == NULL is sp_align_pairs. */
+sp_status sp_align_windows(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int64_t n_pairs,
+                           const int32_t *pair_target, const int32_t *pair_pattern, const int32_t *win_begin,
+                           const int32_t *win_end, sp_align_rec *recs, uint32_t *cigar, int64_t cigar_cap,
+                           int64_t *cigar_used);
+
 /* ---- K5: candidate lists -------------------------------------------------------------------- */
 /* The k best patterns of every target of a device matrix (k <= 16): idx / dist are [n_targets][k] row-major, ordered
  * by (distance, pattern index) ascending; entries beyond n_patterns are -1.  Plays the role of minimap2's best_n hit

@@ -78,6 +78,8 @@ SIGNATURES = {
     "sp_score_spans_filtered": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int, _P, _P, _P]),
     "sp_align_pairs": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                  C.POINTER(C.c_int64)]),
+    "sp_align_windows": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
+                                   C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "sp_row_topk_biased": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "sp_variant_match": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
@@ -219,11 +221,12 @@ class Context:
                                                       S.ctypes.data, E.ctypes.data))
         return D, S, E
 
-    def align_pairs(self, targets, patterns, pairs):
+    def align_pairs(self, targets, patterns, pairs, windows=None):
         """K4: traceback alignment of the listed (target index, pattern index) pairs.  Returns one dict per pair with
         the minimap2::Mapping fields the reference reads (src/hla/processed_match.rs:53-100): dist, nm,
         p_start/p_end (pattern = minimap2's query), t_start/t_end (text = its target) and cigar = [(len, op), ...]
-        with BAM op codes 1 = I, 2 = D, 7 = '=', 8 = X."""
+        with BAM op codes 1 = I, 2 = D, 7 = '=', 8 = X.  windows (optional, [n_pairs, 2] = begin, end): align inside that
+        part of the text only (sp_align_windows); t_start / t_end are then relative to begin."""
         tb, to = targets if isinstance(targets, tuple) else pack_sequences(targets)
         pb, po = patterns if isinstance(patterns, tuple) else pack_sequences(patterns)
         pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
@@ -231,13 +234,21 @@ class Context:
         pt, pp = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
         tl, pl = np.diff(to), np.diff(po)
         ok = n and pt.min() >= 0 and pt.max() < len(tl) and pp.min() >= 0 and pp.max() < len(pl)  # else the library rejects it
-        cap = int((pl[pp] + np.minimum(tl[pt], 2 * pl[pp]) + 1).sum()) if ok else 0
+        wb = we = None
+        if windows is not None:
+            w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32).reshape(-1, 2))
+            if len(w) != n:
+                raise ValueError("align_pairs: one window per pair expected")
+            wb, we = np.ascontiguousarray(w[:, 0]), np.ascontiguousarray(w[:, 1])
+        nl = (we - wb).astype(np.int64) if wb is not None else (tl[pt] if ok else None)
+        cap = int((pl[pp] + np.minimum(np.maximum(nl, 0), 2 * pl[pp]) + 1).sum()) if ok else 0
         recs = (AlignRec * max(n, 1))()
         cig = np.zeros(max(cap, 1), dtype=np.uint32)
         used = C.c_int64(0)
         ts, ps = _seqset(tb, to), _seqset(pb, po)
-        self._check(self._lib.sp_align_pairs(self._h, C.byref(ts), C.byref(ps), n, pt.ctypes.data, pp.ctypes.data, recs,
-                                             cig.ctypes.data, cap, C.byref(used)))
+        self._check(self._lib.sp_align_windows(self._h, C.byref(ts), C.byref(ps), n, pt.ctypes.data, pp.ctypes.data,
+                                               wb.ctypes.data if wb is not None else None, we.ctypes.data if we is not None else None,
+                                               recs, cig.ctypes.data, cap, C.byref(used)))
         out = []
         for r in recs[:n]:
             c = cig[r.cigar_off:r.cigar_off + r.n_cigar]

@@ -36,6 +36,8 @@ struct AlignParams {
     const uint8_t *tbases;     // ASCII texts
     const long long *toffs;
     const int32_t *pair_t;     // text index of each pair
+    const int32_t *win_begin;  // optional [n_pairs]: the pair is aligned inside T[win_begin, win_end) only (coordinates in the
+    const int32_t *win_end;    //   records are relative to win_begin); nullptr = the whole text
     const int32_t *pair_p;     // blob index of each pair
     const long long *cig_off;  // [n_pairs + 1] region of each pair in `cigar`
     uint32_t *cigar;
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
         const int pad = nl * 32 * U - m_all;
         const int wf4 = (pad >> 5) & ~3, Wp = nl * U - wf4;
         const uint8_t *T = p.tbases + p.toffs[t];
-        const int n = static_cast<int>(p.toffs[t + 1] - p.toffs[t]);
+        int n = static_cast<int>(p.toffs[t + 1] - p.toffs[t]);
+        if (p.win_begin) { T += p.win_begin[q]; n = p.win_end[q] - p.win_begin[q]; }
         int best, best_col;
         const int src_lane = __ffs(__ballot_sync(0xffffffffu, last)) - 1;
         int d, e, w0, ncols;

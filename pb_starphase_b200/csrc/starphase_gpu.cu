@@ -973,7 +973,15 @@ struct PhaseTimer {
 extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int64_t n_pairs,
                                     const int32_t *pair_target, const int32_t *pair_pattern, sp_align_rec *recs,
                                     uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used) {
+    return sp_align_windows(ctx, targets, patterns, n_pairs, pair_target, pair_pattern, nullptr, nullptr, recs, cigar, cigar_cap, cigar_used);
+}
+
+extern "C" sp_status sp_align_windows(sp_ctx *ctx, const sp_seqset *targets, const sp_seqset *patterns, int64_t n_pairs,
+                                      const int32_t *pair_target, const int32_t *pair_pattern, const int32_t *win_begin,
+                                      const int32_t *win_end, sp_align_rec *recs, uint32_t *cigar, int64_t cigar_cap,
+                                      int64_t *cigar_used) {
     if (!ctx) return SP_ERR_INVALID;
+    if ((win_begin == nullptr) != (win_end == nullptr)) return fail(ctx, SP_ERR_INVALID, "sp_align_windows: win_begin and win_end go together");
     if (n_pairs < 0 || (n_pairs > 0 && (!pair_target || !pair_pattern || !recs)) || cigar_cap < 0 ||
         (cigar_cap > 0 && !cigar))
         return fail(ctx, SP_ERR_INVALID, "sp_align_pairs: bad argument");
@@ -1020,8 +1028,13 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
             return fail(ctx, SP_ERR_TOO_LONG, "sp_align_pairs: pattern exceeds SP_MAX_PATTERN_LEN");
     for (int64_t q = 0; q < n_pairs; ++q) {
         const int64_t m = po[static_cast<size_t>(pp[static_cast<size_t>(q)]) + 1] - po[static_cast<size_t>(pp[static_cast<size_t>(q)])];
-        const int64_t n = to[static_cast<size_t>(pt[static_cast<size_t>(q)]) + 1] - to[static_cast<size_t>(pt[static_cast<size_t>(q)])];
+        int64_t n = to[static_cast<size_t>(pt[static_cast<size_t>(q)]) + 1] - to[static_cast<size_t>(pt[static_cast<size_t>(q)])];
         if (n > 0x7FFFFF00ll) return fail(ctx, SP_ERR_TOO_LONG, "sp_align_pairs: text too long");
+        if (win_begin) {
+            if (win_begin[q] < 0 || win_end[q] < win_begin[q] || win_end[q] > n)
+                return fail(ctx, SP_ERR_INVALID, "sp_align_windows: window outside its text");
+            n = win_end[q] - win_begin[q];
+        }
         const int64_t ncols = std::min(n, 2 * m);  // window = m + d columns, d <= m
         const int64_t nl = (m + rows - 1) / rows, pad = nl * rows - m;
         const int64_t Wp = nl * ALN_U - ((pad >> 5) & ~3ll);
@@ -1038,6 +1051,12 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     const int64_t budget_bytes = std::max<int64_t>(4ll << 30, std::min<int64_t>(16ll << 30, static_cast<int64_t>((free_b + ctx->pool_bytes[0]) / 4)));
     const int64_t budget_words = budget_bytes / 4;
     n_slots = std::max<int64_t>(1, std::min(n_slots, budget_words / max_slot_words));
+    // hysteresis: the budget follows the free memory, which moves with the stream-ordered pool; re-growing a multi-GB scratch
+    // costs ~100 ms (cudaFree + cudaMalloc), so a pool that already holds at least half of the wanted slots is used as it is
+    {
+        const int64_t have_slots = static_cast<int64_t>(ctx->pool_bytes[0] / 4) / max_slot_words;
+        if (have_slots < n_slots && have_slots * 2 >= n_slots) n_slots = have_slots;
+    }
     if (max_slot_words > (24ll << 30) / 4) return fail(ctx, SP_ERR_NOMEM, "sp_align_pairs: traceback scratch of one pair exceeds 24 GB");
     const int warps_per_cta = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(K1_WARPS, (n_slots + ctx->num_sms - 1) / ctx->num_sms)));
     const int grid = static_cast<int>((n_slots + warps_per_cta - 1) / warps_per_cta);
@@ -1045,10 +1064,11 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     sp_seqset tset = {tb.data(), to.data(), static_cast<int64_t>(t_ids.size())};
     sp_seqset pset = {pbs.data(), po.data(), np};
     uint8_t *d_tb = nullptr, *d_pb = nullptr; long long *d_to = nullptr, *d_po = nullptr, *d_cig_off = nullptr, *d_out_off = nullptr;
-    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_pt = nullptr, *d_pp = nullptr;
+    int32_t *d_lane_pat = nullptr, *d_lane_row0 = nullptr, *d_pt = nullptr, *d_pp = nullptr, *d_wb = nullptr, *d_we = nullptr;
     uint32_t *d_lane_info1 = nullptr, *d_blobs = nullptr, *d_cigar = nullptr, *d_scratch = nullptr, *d_dense = nullptr;
     AlignRecDev *d_recs = nullptr;
     auto cleanup = [&]() {
+        dev_free(ctx, d_wb); dev_free(ctx, d_we);
         dev_free(ctx, d_tb); dev_free(ctx, d_pb); dev_free(ctx, d_to); dev_free(ctx, d_po); dev_free(ctx, d_cig_off); dev_free(ctx, d_out_off);
         dev_free(ctx, d_lane_pat); dev_free(ctx, d_lane_row0); dev_free(ctx, d_pt); dev_free(ctx, d_pp); dev_free(ctx, d_lane_info1);
         dev_free(ctx, d_recs);  // d_scratch, d_cigar, d_blobs and d_dense live in the context's pools
@@ -1090,6 +1110,10 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     SP_TRY(up(reinterpret_cast<void **>(&d_lane_info1), lane_info1.data(), tab * 4));
     SP_TRY(up(reinterpret_cast<void **>(&d_pt), pt.data(), pt.size() * 4));
     SP_TRY(up(reinterpret_cast<void **>(&d_pp), pp.data(), pp.size() * 4));
+    if (win_begin) {
+        SP_TRY(up(reinterpret_cast<void **>(&d_wb), win_begin, static_cast<size_t>(n_pairs) * 4));
+        SP_TRY(up(reinterpret_cast<void **>(&d_we), win_end, static_cast<size_t>(n_pairs) * 4));
+    }
     SP_TRY(up(reinterpret_cast<void **>(&d_cig_off), cig_off.data(), cig_off.size() * sizeof(long long)));
     SP_TRY(cu(ctx_pool(ctx, 2, static_cast<size_t>(np) * blob_words(ALN_U) * 4, reinterpret_cast<void **>(&d_blobs)), "blob pool"));
     SP_TRY(cu(ctx_pool(ctx, 1, static_cast<size_t>(cig_off.back()) * 4, reinterpret_cast<void **>(&d_cigar)), "cigar pool"));
@@ -1107,6 +1131,7 @@ extern "C" sp_status sp_align_pairs(sp_ctx *ctx, const sp_seqset *targets, const
     {
         AlignParams prm;
         prm.blobs = d_blobs; prm.tbases = d_tb; prm.toffs = d_to; prm.pair_t = d_pt; prm.pair_p = d_pp;
+        prm.win_begin = d_wb; prm.win_end = d_we;
         prm.cig_off = d_cig_off; prm.cigar = d_cigar; prm.scratch = d_scratch; prm.slot_words = max_slot_words;
         prm.recs = d_recs; prm.n_pairs = static_cast<int>(n_pairs); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
         const size_t smem = static_cast<size_t>(warps_per_cta) * blob_words(ALN_U) * 4;

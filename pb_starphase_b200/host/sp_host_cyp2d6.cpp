@@ -244,8 +244,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
         std::vector<int32_t> E;
         const std::vector<int32_t> D = gpu_.score_batch(seg_texts, tmpl_seqs, &E);
         mark("K1 score_batch", round, items.size());
-        SeqList texts;
-        std::vector<std::pair<int32_t, int32_t>> pairs;
+        std::vector<std::pair<int32_t, int32_t>> pairs, windows;  // (segment row, template), [w0, e) inside the segment
         std::vector<Item> pair_item;
         std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
         for (const Item &it : items) {
@@ -254,13 +253,13 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const size_t d = static_cast<size_t>(D[row * nt + it.tmpl]), e = static_cast<size_t>(E[row * nt + it.tmpl]);
             if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
             const size_t w0 = e > m + d ? e - (m + d) : 0;
-            pairs.emplace_back(static_cast<int32_t>(texts.size()), static_cast<int32_t>(it.tmpl));
-            texts.push_back(seg_texts[row].substr(w0, e - w0));
+            pairs.emplace_back(static_cast<int32_t>(row), static_cast<int32_t>(it.tmpl));
+            windows.emplace_back(static_cast<int32_t>(w0), static_cast<int32_t>(e));
             pair_item.push_back(it);
             pair_off.push_back(it.lo + w0);
         }
         mark("windows", round, pairs.size());
-        const std::vector<Alignment> alns = gpu_.align_pairs(texts, tmpl_seqs, pairs);
+        const std::vector<Alignment> alns = gpu_.align_pairs(seg_texts, tmpl_seqs, pairs, &windows);  // sp_align_windows: no sub-string copies
         mark("K4 align_pairs", round, pairs.size());
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {

@@ -11,6 +11,10 @@ struct Packed {
     std::vector<int64_t> offs;
     sp_seqset set;
     explicit Packed(const SeqList &seqs) {
+        size_t total = 0;
+        for (const auto &s : seqs) total += s.size();
+        bases.reserve(total + 1);
+        offs.reserve(seqs.size() + 1);
         offs.assign(1, 0);
         for (const auto &s : seqs) {
             bases += s;
@@ -56,16 +60,26 @@ void GpuAligner::score_spans(const SeqList &targets, const SeqList &patterns, st
 }
 
 std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const SeqList &patterns,
-                                               const std::vector<std::pair<int32_t, int32_t>> &pairs) {
+                                               const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                               const std::vector<std::pair<int32_t, int32_t>> *windows) {
+    if (windows && windows->size() != pairs.size()) throw HostError("align_pairs: one window per pair expected");
     Packed t(targets), p(patterns);
-    std::vector<int32_t> pt(pairs.size()), pp(pairs.size());
+    std::vector<int32_t> pt(pairs.size()), pp(pairs.size()), wb, we;
+    if (windows) {
+        wb.resize(pairs.size()); we.resize(pairs.size());
+        for (size_t q = 0; q < pairs.size(); ++q) { wb[q] = (*windows)[q].first; we[q] = (*windows)[q].second; }
+    }
     int64_t cap = 0;
     for (size_t q = 0; q < pairs.size(); ++q) {
         pt[q] = pairs[q].first; pp[q] = pairs[q].second;
         if (pt[q] < 0 || pp[q] < 0 || static_cast<size_t>(pt[q]) >= targets.size() || static_cast<size_t>(pp[q]) >= patterns.size())
             throw HostError("align_pairs: pair index outside the sequence sets");
         const int64_t m = static_cast<int64_t>(patterns[static_cast<size_t>(pp[q])].size());
-        const int64_t n = static_cast<int64_t>(targets[static_cast<size_t>(pt[q])].size());
+        int64_t n = static_cast<int64_t>(targets[static_cast<size_t>(pt[q])].size());
+        if (windows) {
+            if (wb[q] < 0 || we[q] < wb[q] || we[q] > n) throw HostError("align_pairs: window outside its text");
+            n = we[q] - wb[q];
+        }
         cap += m + std::min(n, 2 * m) + 1;
     }
     std::vector<sp_align_rec> recs(std::max<size_t>(pairs.size(), 1));
@@ -73,7 +87,8 @@ std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const Seq
     // CIGARs really use are ever touched (a zero-filled vector cost ~60 ms for the 3,744 windows of a CYP2D6 template search)
     const std::unique_ptr<uint32_t[]> cig(new uint32_t[static_cast<size_t>(std::max<int64_t>(cap, 1))]);
     int64_t used = 0;
-    check(sp_align_pairs(ctx_, &t.set, &p.set, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(), recs.data(), cig.get(), cap, &used),
+    check(sp_align_windows(ctx_, &t.set, &p.set, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(), windows ? wb.data() : nullptr,
+                           windows ? we.data() : nullptr, recs.data(), cig.get(), cap, &used),
           "sp_align_pairs");
     std::vector<Alignment> out(pairs.size());
     for (size_t q = 0; q < pairs.size(); ++q) {

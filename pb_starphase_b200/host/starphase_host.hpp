@@ -220,8 +220,10 @@ class GpuAligner {
     // start = -1 where D * 1000 > |pattern| * max_dist_permille (no span computed); negative = every pair
     void score_spans(const SeqList &targets, const SeqList &patterns, std::vector<int32_t> &D, std::vector<int32_t> &start,
                      std::vector<int32_t> &end, int max_dist_permille = -1);
+    // windows (optional, one [begin, end) per pair): align inside that part of the text only; t_start / t_end are relative to begin
     std::vector<Alignment> align_pairs(const SeqList &targets, const SeqList &patterns,
-                                       const std::vector<std::pair<int32_t, int32_t>> &pairs);
+                                       const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr);
     std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
                                               int k);
     // resident path: nothing of size reads x alleles crosses PCIe

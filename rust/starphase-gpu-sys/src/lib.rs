@@ -66,6 +66,9 @@ extern "C" {
     pub fn sp_align_pairs(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, n_pairs: i64,
                           pair_target: *const i32, pair_pattern: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
                           cigar_cap: i64, cigar_used: *mut i64) -> c_int;
+    pub fn sp_align_windows(ctx: *mut sp_ctx, targets: *const sp_seqset, patterns: *const sp_seqset, n_pairs: i64,
+                            pair_target: *const i32, pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32,
+                            recs: *mut sp_align_rec, cigar: *mut u32, cigar_cap: i64, cigar_used: *mut i64) -> c_int;
     pub fn sp_row_topk(ctx: *mut sp_ctx, d: *const sp_dmatrix, k: c_int, idx: *mut i32, dist: *mut i32) -> c_int;
     pub fn sp_row_topk_biased(ctx: *mut sp_ctx, d: *const sp_dmatrix, pattern_bias: *const i32, k: c_int, idx: *mut i32,
                               dist: *mut i32) -> c_int;

@@ -70,6 +70,31 @@ def test_align_long_text_window(ctx, oracle):
     check_against_oracle(ctx, oracle, [read, read2], [allele], [(0, 0), (1, 0)])
 
 
+def test_align_windows_vs_oracle(ctx, oracle):
+    """sp_align_windows: the pair is aligned inside T[begin, end) only and the record is relative to begin -- identical to
+    aligning the copied sub-string (what the template search of find_base_type_in_sequence did before)."""
+    rng = np.random.default_rng(23)
+    pats = [rnd(rng, m) for m in (40, 300, 700, 1500)]
+    texts = [rnd(rng, 500) + noisy(rng, pats[k % 4], 5) + rnd(rng, 800) + noisy(rng, pats[(k + 1) % 4], 9) + rnd(rng, 300) for k in range(6)]
+    pairs, wins = [], []
+    for t in range(len(texts)):
+        for p in range(len(pats)):
+            n = len(texts[t])
+            b = int(rng.integers(0, n // 2))
+            e = int(rng.integers(b, n + 1))
+            pairs.append((t, p)); wins.append((b, e))
+    pairs += [(0, 1), (1, 2), (2, 0)]
+    wins += [(0, len(texts[0])), (100, 100), (len(texts[2]), len(texts[2]))]   # the whole text, two empty windows
+    got = ctx.align_pairs(texts, pats, pairs, windows=wins)
+    for (t, p), (b, e), g in zip(pairs, wins, got):
+        assert g == oracle.align(pats[p], texts[t][b:e]), (t, p, b, e)
+    import pb_starphase_b200 as sp
+
+    for bad in ((-1, 10), (10, 5), (0, len(texts[0]) + 1)):
+        with pytest.raises(sp.SpError):
+            ctx.align_pairs(texts, pats, [(0, 0)], windows=[bad])
+
+
 def test_align_cyp_sized_pattern(ctx, oracle):
     rng = np.random.default_rng(9)
     d6 = rnd(rng, 6165)
