@@ -50,11 +50,14 @@ struct AlignParams {
 
 // the K1 recurrence over `ncols` text columns T[0 .. ncols) for this warp's bin; STORE keeps (D0, ~Pv) per column
 template <bool STORE>
+// band_lo / band_hi (STORE only): a column j keeps the words of this lane only if some row i of the lane has
+// band_lo <= i - j <= band_hi (cell coordinates, 1-based); the walk back never leaves that diagonal band
 __device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *T, int ncols, const AlignParams &p,
                                            bool first, bool owns, int m, int &best, int &best_col, uint32_t *scr,
-                                           int Wp, int wf4) {
+                                           int Wp, int wf4, int row_lo = 0, int band_lo = -0x40000000, int band_hi = 0x40000000) {
     constexpr int U = ALN_U;
     const int lane = threadIdx.x & 31;
+    const int row_hi = row_lo + 32 * U - 1;
     uint32_t npv[U], mv[U], d0[U];
     load_row<U>(blob + 5 * (32 * U), lane, npv);
 #pragma unroll
@@ -77,7 +80,7 @@ __device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *
                 const uint32_t code = j < ncols ? base_code(T[j]) : 4u;
                 column_step<U, true, STORE>(blob, lane, code, p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, cph, cmh, score, best, col,
                                             best_col, d0);
-                if (STORE && owns && j < ncols) {
+                if (STORE && owns && j < ncols && row_hi >= j + 1 + band_lo && row_lo <= j + 1 + band_hi) {
                     uint32_t *dst = scr + static_cast<size_t>(j) * 2 * Wp + (lane * U - wf4);
 #pragma unroll
                     for (int q = 0; q < U / 4; ++q) {
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
         int best, best_col;
         const int src_lane = __ffs(__ballot_sync(0xffffffffu, last)) - 1;
         int d, e, w0, ncols;
+        const int row_lo = lane * 32 * U - pad + 1;  // first pattern row (cell coordinates) of this lane
         if (n <= 2 * m_all) {
             // the whole text fits the pair's scratch slot (the host sizes it for min(n, 2m) columns): one pass that both
             // finds (d, e) and keeps the columns -- the consensus-sized texts of score_read and the placement windows of
@@ -144,7 +148,13 @@ __global__ void __launch_bounds__(K1_THREADS) k4_align(const AlignParams p) {
             k4_forward<false>(blob, T, n, p, first, owns, m, best, best_col, nullptr, 0, 0);
             d = __shfl_sync(0xffffffffu, best, src_lane); e = __shfl_sync(0xffffffffu, best_col, src_lane);
             w0 = max(0, e - (m_all + d)); ncols = e - w0;
-            k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4);
+            // d is known here: the walk back cannot leave the diagonal band |i - j - (m - ncols)| <= d (each edit moves i - j by
+            // at most one), so only the lanes touching the band keep their columns.  (Measured: the kernel is bound by the
+            // forward recurrence, not by these stores -- a 6 kb template costs the same with one full-store pass as with a
+            // compute-only pass plus a banded-store pass -- so short texts stay on the single pass above.)
+            const int delta_end = m_all - ncols;
+            k4_forward<true>(blob, T + w0, ncols, p, first, owns, m, best, best_col, scr, Wp, wf4, row_lo, delta_end - d - 1,
+                             delta_end + d + 1);
         }
         __threadfence_block();
         __syncwarp();
