@@ -217,9 +217,8 @@ def realign_select(read_len: int, hits: Sequence[Mapping]) -> Tuple[Optional[int
 # ==========================================================================================
 # het / hom decision -- src/hla/caller.rs:1225-1247, :889-901
 # ==========================================================================================
-def binomial_cdf(n: int, p: float, k: int) -> float:
-    """P[X <= k], X ~ Binomial(n, p).  statrs evaluates this through the regularised incomplete beta
-    function; the oracle sums the exact rational pmf, so only the >= min_cdf decision is compared."""
+def binomial_cdf_exact(n: int, p: float, k: int) -> float:
+    """P[X <= k], X ~ Binomial(n, p) from the exact rational pmf (independent check of binomial_cdf below)."""
     if k >= n:
         return 1.0
     pf = Fraction(p)
@@ -228,6 +227,58 @@ def binomial_cdf(n: int, p: float, k: int) -> float:
     for x in range(0, k + 1):
         acc += math.comb(n, x) * pf ** x * q ** (n - x)
     return float(acc)
+
+
+def beta_reg(a: float, b: float, x: float) -> float:
+    """statrs 0.16 function::beta::beta_reg (Math.NET's BetaRegularized: modified Lentz continued fraction, at most 140
+    iterations, symmetry transform above (a + 1) / (a + b + 2)).  Pinned by the reference's own documentation: the example
+    hla_debug.json of docs/debug_outputs.md:128-135 (counts 27 / 10 -> cdf 0.019406414321609413) is reproduced digit for digit
+    (tests/test_host_logic_cpu.py), which the exact sum (...60988) is not."""
+    bt = 0.0 if x == 0.0 or x == 1.0 else math.exp(ln_gamma(a + b) - ln_gamma(a) - ln_gamma(b) + a * math.log(x) + b * math.log(1.0 - x))
+    symm = x >= (a + 1.0) / (a + b + 2.0)
+    eps = 0.00000000000000011102230246251565
+    fpmin = 2.2250738585072014e-308 / eps
+    if symm:
+        a, b, x = b, a, 1.0 - x
+    qab, qap, qam = a + b, a + 1.0, a - 1.0
+    c = 1.0
+    d = 1.0 - qab * x / qap
+    if abs(d) < fpmin:
+        d = fpmin
+    d = 1.0 / d
+    h = d
+    for mi in range(1, 141):
+        m = float(mi)
+        m2 = m * 2.0
+        aa = m * (b - m) * x / ((qam + m2) * (a + m2))
+        d = 1.0 + aa * d
+        if abs(d) < fpmin:
+            d = fpmin
+        c = 1.0 + aa / c
+        if abs(c) < fpmin:
+            c = fpmin
+        d = 1.0 / d
+        h = h * d * c
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2))
+        d = 1.0 + aa * d
+        if abs(d) < fpmin:
+            d = fpmin
+        c = 1.0 + aa / c
+        if abs(c) < fpmin:
+            c = fpmin
+        d = 1.0 / d
+        dl = d * c
+        h *= dl
+        if abs(dl - 1.0) <= eps:
+            break
+    return 1.0 - bt * h / a if symm else bt * h / a
+
+
+def binomial_cdf(n: int, p: float, k: int) -> float:
+    """statrs 0.16 Binomial::cdf: 1.0 for k >= n, else beta_reg(n - k, k + 1, 1 - p)."""
+    if k >= n:
+        return 1.0
+    return beta_reg(float(n) - float(k), float(k) + 1.0, 1.0 - p)
 
 
 def is_passing_dual(counts1: int, counts2: int, min_consensus_fraction: float = 0.10, min_cdf: float = 0.001,

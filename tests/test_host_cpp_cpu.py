@@ -304,14 +304,19 @@ def test_dual_passing_stats(host):  # src/hla/caller.rs:1225-1247, tests :1837-1
         want = so.dual_passing_stats(True, c1, c2, expected_maf=0.5)
         assert got["is_passing"] is passing is want["is_passing"]
         assert (got["counts1"], got["counts2"], got["maf"], got["is_dual"]) == (c1, c2, want["maf"], True)
-        assert got["cdf"] == pytest.approx(want["cdf"], rel=1e-12)  # statrs' beta_reg vs the exact rational sum
+        assert got["cdf"] == want["cdf"]                                 # both restate statrs' beta_reg
+        assert got["cdf"] == pytest.approx(so.binomial_cdf_exact(c1 + c2, 0.5, min(c1, c2)), rel=1e-12)
     assert host.dual_passing_stats_json(False, 0, 0) == so.serde_pretty(so.dual_passing_stats(False))
+    # the reference's documented example (docs/debug_outputs.md:128-135), byte for byte
+    assert host.dual_passing_stats_json(True, 27, 10) == so.serde_pretty(so.dual_passing_stats(True, 27, 10))
+    assert '"cdf": 0.019406414321609413' in host.dual_passing_stats_json(True, 27, 10)
     rnd = random.Random(9)
     for _ in range(150):  # beta_reg (continued fraction) against the exact sum
         n = rnd.randint(1, 200)
         k = rnd.randint(0, n)
         p = rnd.choice([0.45, 0.5, rnd.uniform(0.01, 0.99)])
-        assert host.binomial_cdf(n, p, k) == pytest.approx(so.binomial_cdf(n, p, k), rel=1e-10, abs=1e-300)
+        assert host.binomial_cdf(n, p, k) == so.binomial_cdf(n, p, k)
+        assert host.binomial_cdf(n, p, k) == pytest.approx(so.binomial_cdf_exact(n, p, k), rel=1e-10, abs=1e-300)
 
 
 def test_reverse_complement(host):  # src/util/sequence.rs:25-36
@@ -326,6 +331,9 @@ def test_cigar_and_md_strings(host):
     cigar = [(3, 7), (1, 8), (2, 7), (3, 1), (1, 7), (1, 2), (2, 7)]  # ACG A AC [TTT] G ^T AC
     assert host.cigar_string(cigar) == "3=1X2=3I1=1D2=" == so.cigar_string(cigar)
     assert host.md_string(cigar, target, 2, query, 0) == "3T3^T2" == so.md_string(cigar, target.encode(), 2, query.encode(), 0)
+    # docs/debug_outputs.md:96-118: an exact match of a 1,098 bp cDNA inside a 1,535 bp consensus reads "1098=" / "1098"
+    q = "".join(random.Random(1).choice("ACGT") for _ in range(1098))
+    assert host.cigar_string([(1098, 7)]) == "1098=" and host.md_string([(1098, 7)], "T" * 200 + q + "A" * 237, 200, q, 0) == "1098"
     assert host.md_string([(4, 7)], "ACGT", 0, "ACGT", 0) == "4"
     assert host.md_string([(1, 8), (3, 7)], "ACGT", 0, "TCGT", 0) == "0A3"
     assert host.md_string([(3, 7), (1, 8)], "ACGT", 0, "ACGA", 0) == "3T"       # no trailing zero (write_MD_core)

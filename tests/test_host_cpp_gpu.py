@@ -114,19 +114,15 @@ def test_score_read_vs_oracle(host, gpu, oracle):
 def test_hla_debug_json_vs_oracle(host, gpu, oracle):
     """hla_debug.json (src/hla/debug.rs): per consensus and allele the DetailedMappingStats of the best cDNA / DNA mapping
     (lengths, match_len, nm, unmapped on both sides, EQX CIGAR string, MD string) + DualPassingStats -- the artefact a
-    maintainer diffs against `pbstarphase diplotype --debug-folder`.  Byte-identical to the oracle flow apart from the
-    digits of `cdf` (statrs' continued fraction vs the oracle's exact sum)."""
+    maintainer diffs against `pbstarphase diplotype --debug-folder`.  Byte-identical to the oracle flow."""
     rows, reads = hla_db()
     for gene, fwd in (("HLA-A", True), ("HLA-B", False)):
         cons = [(f"consensus{k + 1}", d, c) for k, (_, d, c) in enumerate(reads[gene][:2])]
         cons.append(("junk", b"ACGT", b"N"))
         got = host.hla_debug_json(gpu, rows, gene, [(q, d.decode(), c.decode()) for q, d, c in cons], True, 7, 5, host.DiplotypeSettings())
         want = fo.hla_debug_json(oracle, rows, gene, cons, True, 7, 5)
-        gj, wj = json.loads(got), json.loads(want)
-        assert gj["dual_passing_stats"][gene].pop("cdf") == pytest.approx(wj["dual_passing_stats"][gene].pop("cdf"), rel=1e-12)
-        assert gj == wj
-        strip = lambda t: "\n".join(l for l in t.split("\n") if '"cdf"' not in l)
-        assert strip(got) == strip(want)
+        assert got == want  # byte for byte, floats included (statrs' beta_reg restated on both sides, pinned by docs/debug_outputs.md)
+        gj = json.loads(got)
         per = gj["read_mapping_stats"][gene]
         assert list(per) == ["consensus1", "consensus2", "junk"] and per["junk"]["best_match_id"] is None
         d = next(iter(per["consensus1"]["mapping_stats"].values()))["dna_mapping"]

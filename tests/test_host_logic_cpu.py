@@ -104,6 +104,22 @@ def test_is_passing_dual():
     assert so.is_passing_dual(10, 20, **kw) and so.is_passing_dual(20, 10, **kw)
 
 
+def test_dual_passing_stats_reference_docs_vector():
+    """docs/debug_outputs.md:128-135: the reference's own example hla_debug.json (default settings, expected MAF 0.45)."""
+    want = """{
+  "is_passing": true,
+  "is_dual": true,
+  "counts1": 27,
+  "counts2": 10,
+  "maf": 0.2702702702702703,
+  "cdf": 0.019406414321609413
+}"""
+    assert so.serde_pretty(so.dual_passing_stats(True, 27, 10)) == want
+    # the continued fraction against the exact rational sum
+    for n, p, k in ((37, 0.45, 10), (23, 0.5, 3), (200, 0.45, 60), (5, 0.1, 0), (64, 0.45, 63)):
+        assert so.binomial_cdf(n, p, k) == pytest.approx(so.binomial_cdf_exact(n, p, k), rel=1e-11)
+
+
 # ---- src/util/stats.rs:45-70 -------------------------------------------------------------------------
 def test_multinomial():
     assert so.multinomial_ln_pmf([1.0], [10]) == pytest.approx(0.0, abs=1e-9)
