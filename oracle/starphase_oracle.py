@@ -459,10 +459,21 @@ class Cyp2d6Config:
 CORE, SUB, DEEP = "CoreAlleles", "SubAlleles", "DeepAlleles"
 
 
+def deep_label(label: "RegionLabel", unique_id: Optional[int], variants: Optional[Sequence[dict]]) -> str:
+    """Cyp2d6Region::deep_label, src/cyp2d6/region.rs:60-95: index label + the variants that differ from the assigned allele."""
+    parts = [(f"{unique_id}_" if unique_id is not None else "X_") + label.full_allele()]
+    for v in variants or []:
+        st = v["variant_state"]
+        if st in ("Match", "UnknownUnexpected"):
+            continue
+        parts.append({"Unexpected": "+", "Missing": "-"}.get(st, "?") + v["label"])
+    return " ".join(parts)
+
+
 def convert_chain_to_hap(chain: Sequence[int], labels: Sequence[RegionLabel], detail_level: str,
-                         cyp_translate: Dict[str, str], unique_ids: Optional[Sequence[Optional[int]]] = None) -> str:
-    """src/cyp2d6/caller.rs:907-957.  DeepAlleles uses Cyp2d6Region::deep_label without variants
-    (src/cyp2d6/region.rs:47-94)."""
+                         cyp_translate: Dict[str, str], unique_ids: Optional[Sequence[Optional[int]]] = None,
+                         variants: Optional[Sequence[Optional[Sequence[dict]]]] = None) -> str:
+    """src/cyp2d6/caller.rs:907-957.  DeepAlleles uses Cyp2d6Region::deep_label (src/cyp2d6/region.rs:60-95)."""
     num_non_deletion = 0
     reportable = []
     for c in reversed(chain):
@@ -483,7 +494,7 @@ def convert_chain_to_hap(chain: Sequence[int], labels: Sequence[RegionLabel], de
             names.append(lab.simplify_allele(True, cyp_translate))
         else:
             uid = unique_ids[c] if unique_ids is not None else None
-            names.append("(" + (f"{uid}_" if uid is not None else "X_") + lab.full_allele() + ")")
+            names.append("(" + deep_label(lab, uid, variants[c] if variants is not None else None) + ")")
     out = []
     i = 0
     while i < len(names):
@@ -1235,3 +1246,23 @@ def hpc_pos(seq: bytes, position: int) -> int:
         offset += 1
         i = j
     return offset
+
+
+def cyp2d6_alleles_json(best: Sequence[Sequence[int]], labels: Sequence[RegionLabel], unique_ids: Sequence[Optional[int]],
+                        variants: Sequence[Optional[Sequence[dict]]], cyp_translate: Dict[str, str]) -> str:
+    """DeeplotypeDebug through save_json, src/cyp2d6/debug.rs:8-71 (cyp2d6_alleles.json)."""
+    assert len(best) == 2
+
+    def hap(chain):
+        return dict(deep_form=convert_chain_to_hap(chain, labels, DEEP, cyp_translate, unique_ids, variants),
+                    suballele_form=convert_chain_to_hap(chain, labels, SUB, cyp_translate, unique_ids, variants),
+                    core_form=convert_chain_to_hap(chain, labels, CORE, cyp_translate, unique_ids, variants))
+
+    alleles = {}
+    for lab, uid, var in zip(labels, unique_ids, variants):
+        if var is None:
+            continue
+        key = (f"{uid}_" if uid is not None else "X_") + lab.full_allele()
+        assert key not in alleles
+        alleles[key] = [dict(label=v["label"], is_vi=bool(v["is_vi"]), variant_state=v["variant_state"]) for v in var]
+    return serde_pretty(dict(hap1=hap(best[0]), hap2=hap(best[1]), alleles={k: alleles[k] for k in sorted(alleles, key=lambda x: x.encode())}))

@@ -172,7 +172,7 @@ std::string convert_chain_to_hap(const std::vector<size_t> &chain, const std::ve
         switch (level) {
             case Cyp2d6DetailLevel::CoreAlleles: names.push_back(lab.simplify_allele(false, cyp_translate)); break;
             case Cyp2d6DetailLevel::SubAlleles: names.push_back(lab.simplify_allele(true, cyp_translate)); break;
-            case Cyp2d6DetailLevel::DeepAlleles: names.push_back("(" + hap_regions[c].index_label() + ")"); break;
+            case Cyp2d6DetailLevel::DeepAlleles: names.push_back("(" + hap_regions[c].deep_label() + ")"); break;
         }
     }
     std::string out;
@@ -337,6 +337,44 @@ std::string RegionVariant::to_string() const {  // Display, src/data_types/regio
     const char *pre = variant_state == VariantAlleleRelationship::Match ? "=" : variant_state == VariantAlleleRelationship::Unexpected ? "+"
                     : variant_state == VariantAlleleRelationship::Missing ? "-" : "?";
     return pre + label;
+}
+
+std::string Cyp2d6Region::deep_label() const {  // src/cyp2d6/region.rs:60-95
+    std::string out = index_label();
+    if (variants)
+        for (const RegionVariant &v : *variants) {
+            switch (v.variant_state) {
+                case VariantAlleleRelationship::Match: case VariantAlleleRelationship::UnknownUnexpected: break;
+                case VariantAlleleRelationship::Unexpected: out += " +" + v.label; break;
+                case VariantAlleleRelationship::Missing: out += " -" + v.label; break;
+                default: out += " ?" + v.label; break;
+            }
+        }
+    return out;
+}
+
+std::string cyp2d6_alleles_json(const std::vector<std::vector<size_t>> &best, const std::vector<Cyp2d6Region> &hap_regions,
+                                const std::map<std::string, std::string> &cyp_translate) {
+    if (best.size() != 2) throw HostError("assertion failed: best_diplotype_indices.len() == 2");
+    auto hap = [&](const std::vector<size_t> &chain) {
+        Json j = Json::object();
+        j.set("deep_form", convert_chain_to_hap(chain, hap_regions, Cyp2d6DetailLevel::DeepAlleles, cyp_translate));
+        j.set("suballele_form", convert_chain_to_hap(chain, hap_regions, Cyp2d6DetailLevel::SubAlleles, cyp_translate));
+        j.set("core_form", convert_chain_to_hap(chain, hap_regions, Cyp2d6DetailLevel::CoreAlleles, cyp_translate));
+        return j;
+    };
+    std::map<std::string, Json> alleles;  // BTreeMap<index_label, Vec<RegionVariant>>
+    for (const Cyp2d6Region &r : hap_regions) {
+        if (!r.variants) continue;
+        Json arr = Json::array();
+        for (const RegionVariant &v : *r.variants) arr.push(v.to_json());
+        if (!alleles.emplace(r.index_label(), arr).second) throw HostError("assertion failed: alleles.insert(core_label, vec_variants).is_none()");
+    }
+    Json al = Json::object();
+    for (const auto &kv : alleles) al.set(kv.first, kv.second);
+    Json doc = Json::object();
+    doc.set("hap1", hap(best[0])).set("hap2", hap(best[1])).set("alleles", al);
+    return doc.pretty();
 }
 
 Json RegionVariant::to_json() const {

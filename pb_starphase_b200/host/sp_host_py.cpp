@@ -264,6 +264,25 @@ PYBIND11_MODULE(_starphase_host, m) {
     m.def("region_variant_string", [](const std::string &label, bool is_vi, int state) {
         return RegionVariant{label, is_vi, static_cast<VariantAlleleRelationship>(state)}.to_string();
     });
+    // rows: (region type, subtype label, unique id, variants or None); variants: (label, is_vi, state index)
+    m.def("cyp2d6_alleles_json", [](const std::vector<std::vector<size_t>> &best,
+                                    const std::vector<std::tuple<std::string, std::optional<std::string>, std::optional<size_t>,
+                                                                 std::optional<std::vector<std::tuple<std::string, bool, int>>>>> &rows) {
+        std::vector<Cyp2d6Region> regions;
+        for (const auto &r : rows) {
+            Cyp2d6Region g;
+            g.label.region_type = region_type_from_name(std::get<0>(r));
+            g.label.subtype_label = std::get<1>(r);
+            g.unique_id = std::get<2>(r);
+            if (std::get<3>(r)) {
+                g.variants.emplace();
+                for (const auto &v : *std::get<3>(r))
+                    g.variants->push_back({std::get<0>(v), std::get<1>(v), static_cast<VariantAlleleRelationship>(std::get<2>(v))});
+            }
+            regions.push_back(std::move(g));
+        }
+        return cyp2d6_alleles_json(best, regions, Cyp2d6Config::default_config().cyp_translate);
+    });
     m.def("alleles_from_traversal", &alleles_from_traversal);
     m.def("assign_haplotypes_from_alleles", [](GpuAligner &g, const std::vector<std::vector<uint8_t>> &alleles,
                                                const std::map<std::string, std::vector<uint8_t>> &lookup,

@@ -462,10 +462,28 @@ struct Cyp2d6RegionLabel {  // src/cyp2d6/region_label.rs:72-266
 const char *region_type_name(Cyp2d6RegionType t);
 Cyp2d6RegionType region_type_from_name(const std::string &s);
 
-struct Cyp2d6Region {  // src/cyp2d6/region.rs (label + unique id)
+// ---- allele-vector typing: the in-tree half of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:452-601) ----
+enum class VariantAlleleRelationship {  // src/data_types/region_variants.rs:5-23
+    Unknown, Match, Unexpected, Missing, AmbiguousUnexpected, AmbiguousMissing, UnknownUnexpected, UnknownMissing
+};
+const char *variant_state_name(VariantAlleleRelationship s);
+struct RegionVariant {  // src/data_types/region_variants.rs:26-34
+    std::string label;
+    bool is_vi = false;
+    VariantAlleleRelationship variant_state = VariantAlleleRelationship::Unknown;
+    std::string to_string() const;  // "=label" / "+label" / "-label" / "?label"
+    Json to_json() const;
+};
+struct VariantMetadata {  // the members of LoadedVariants the typing reads (src/cyp2d6/haplotyper.rs:617-640, :812)
+    std::string label;
+    bool is_vi = false;
+};
+struct Cyp2d6Region {  // src/cyp2d6/region.rs:17-25
     Cyp2d6RegionLabel label;
     std::optional<size_t> unique_id;
+    std::optional<std::vector<RegionVariant>> variants;  // set by the allele-vector typing (assign_haplotypes_from_alleles)
     std::string index_label() const;  // :50-56
+    std::string deep_label() const;   // :60-95: index label + "+rs.." (unexpected) / "-rs.." (missing) / "?rs.." (ambiguous) deltas
 };
 
 struct AlleleMapping {  // src/cyp2d6/haplotyper.rs:836-869
@@ -497,22 +515,6 @@ class Cyp2d6Extractor {
     std::vector<std::pair<Cyp2d6RegionLabel, std::string>> templates_;
 };
 
-// ---- allele-vector typing: the in-tree half of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:452-601) ----
-enum class VariantAlleleRelationship {  // src/data_types/region_variants.rs:5-23
-    Unknown, Match, Unexpected, Missing, AmbiguousUnexpected, AmbiguousMissing, UnknownUnexpected, UnknownMissing
-};
-const char *variant_state_name(VariantAlleleRelationship s);
-struct RegionVariant {  // src/data_types/region_variants.rs:26-34
-    std::string label;
-    bool is_vi = false;
-    VariantAlleleRelationship variant_state = VariantAlleleRelationship::Unknown;
-    std::string to_string() const;  // "=label" / "+label" / "-label" / "?label"
-    Json to_json() const;
-};
-struct VariantMetadata {  // the members of LoadedVariants the typing reads (src/cyp2d6/haplotyper.rs:617-640, :812)
-    std::string label;
-    bool is_vi = false;
-};
 // :454-468: per-site state from the nodes a WFA-graph traversal visited (3 = unset, conflicting assignments -> 2)
 std::vector<uint8_t> alleles_from_traversal(size_t num_variants, const std::vector<size_t> &traversed_nodes,
                                             const std::map<size_t, std::vector<std::pair<size_t, uint8_t>>> &node_to_alleles);
@@ -593,6 +595,10 @@ Cyp2d6Call call_cyp2d6_chains(GpuAligner &gpu, const Cyp2d6Config &cfg, const Se
                               std::vector<Cyp2d6Region> hap_regions,
                               const std::map<std::string, std::vector<Cyp2d6ReadRegion>> &regions_of_interest,
                               bool infer_connections, bool normalize_all_alleles);
+
+// cyp2d6_alleles.json (DeeplotypeDebug, src/cyp2d6/debug.rs:8-71): the three forms of both haplotypes + the variants of every typed allele
+std::string cyp2d6_alleles_json(const std::vector<std::vector<size_t>> &best_diplotype_indices, const std::vector<Cyp2d6Region> &hap_regions,
+                                const std::map<std::string, std::string> &cyp_translate);
 
 // StarphaseJson, src/data_types/starphase_json.rs:13-21; metadata order of src/database/pgx_database.rs:359-371
 std::string starphase_json(const std::string &pbstarphase_version, const std::map<std::string, std::string> &database_metadata,

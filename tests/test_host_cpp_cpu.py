@@ -437,3 +437,29 @@ def test_overlap_score_and_region_variant_display(host):  # src/cyp2d6/haplotype
     states = ["Unknown", "Match", "Unexpected", "Missing", "AmbiguousUnexpected", "AmbiguousMissing", "UnknownUnexpected", "UnknownMissing"]
     shown = [host.region_variant_string("rs123", True, k) for k in range(len(states))]
     assert shown == ["?rs123", "=rs123", "+rs123", "-rs123", "?rs123", "?rs123", "?rs123", "?rs123"]
+
+
+def test_cyp2d6_alleles_json_reference_docs_vector(host):
+    """docs/debug_outputs.md:27-54: the reference's documented cyp2d6_alleles.json -- the deep / sub-allele / core forms of
+    (*41.004 with an unexpected rs28735595) and (*68 + *4.001 with the same extra variant), allele keys {index}_{label}."""
+    states = ["Unknown", "Match", "Unexpected", "Missing", "AmbiguousUnexpected", "AmbiguousMissing", "UnknownUnexpected", "UnknownMissing"]
+    regions = [("Hybrid", "CYP2D6::CYP2D7::exon2", 0, None), ("CYP2D7", None, 1, None),
+               ("CYP2D6", "4.001", 2, [("rs28371738", False, "Match"), ("rs28735595", False, "Unexpected")]),
+               ("REP6", None, 3, None),
+               ("CYP2D6", "41.004", 4, [("rs16947", True, "Match"), ("rs28735595", False, "Unexpected"), ("rs1", False, "UnknownUnexpected")])]
+    best = [[4], [2, 0]]
+    got = host.cyp2d6_alleles_json(best, [(t, s, u, None if v is None else [(l, vi, states.index(st)) for l, vi, st in v])
+                                          for t, s, u, v in regions])
+    doc = __import__("json").loads(got)
+    assert doc["hap1"] == {"deep_form": "(4_CYP2D6*41.004 +rs28735595)", "suballele_form": "*41.004", "core_form": "*41"}
+    assert doc["hap2"] == {"deep_form": "(0_CYP2D6::CYP2D7::exon2) + (2_CYP2D6*4.001 +rs28735595)", "suballele_form": "*68 + *4.001",
+                           "core_form": "*68 + *4"}
+    assert list(doc["alleles"]) == ["2_CYP2D6*4.001", "4_CYP2D6*41.004"]
+    assert doc["alleles"]["2_CYP2D6*4.001"][0] == {"label": "rs28371738", "is_vi": False, "variant_state": "Match"}
+    labels = [so.RegionLabel(t, s) for t, s, _, _ in regions]
+    variants = [None if v is None else [dict(label=l, is_vi=vi, variant_state=st) for l, vi, st in v] for _, _, _, v in regions]
+    want = so.cyp2d6_alleles_json(best, labels, [u for _, _, u, _ in regions], variants, so.Cyp2d6Config.default().cyp_translate)
+    assert got == want
+    # the other deltas of deep_label (src/cyp2d6/region.rs:60-95)
+    assert so.deep_label(so.RegionLabel("CYP2D6", "1.001"), None, [dict(label="a", variant_state="Missing"), dict(label="b", variant_state="AmbiguousMissing"),
+                                                                 dict(label="c", variant_state="Match")]) == "X_CYP2D6*1.001 -a ?b"
