@@ -48,6 +48,27 @@ pub const SP_PREFIX: c_int = 1;
 extern "C" {
     pub fn sp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut sp_ctx) -> c_int;
     pub fn sp_ctx_destroy(ctx: *mut sp_ctx);
+    pub fn sp_ctx_synchronize(ctx: *mut sp_ctx) -> c_int;
+    pub fn sp_version() -> *const c_char;
+    pub fn sp_launch_count(ctx: *const sp_ctx) -> u64;
+    pub fn sp_last_kernel_ms(ctx: *mut sp_ctx, which: c_int) -> f32;
+    pub fn sp_int_peak(ctx: *mut sp_ctx, kind: c_int, ops_per_s: *mut f64) -> c_int;
+    pub fn sp_host_alloc(ctx: *mut sp_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn sp_host_free(ctx: *mut sp_ctx, ptr: *mut c_void);
+    pub fn sp_plan_lane_classes(lens: *const i64, n: i64, max_classes: c_int, n_classes: *mut c_int, widths: *mut c_int,
+                                n_patterns: *mut i64, n_warps: *mut i64, padded_rows: *mut i64) -> c_int;
+    pub fn sp_patterns_count(p: *const sp_patterns) -> i64;
+    pub fn sp_patterns_total_len(p: *const sp_patterns) -> i64;
+    pub fn sp_patterns_padded_rows(p: *const sp_patterns) -> i64;
+    pub fn sp_targets_count(t: *const sp_targets) -> i64;
+    pub fn sp_targets_total_len(t: *const sp_targets) -> i64;
+    pub fn sp_score_into(ctx: *mut sp_ctx, t: *const sp_targets, p: *const sp_patterns, dst: *mut sp_dmatrix, pattern_row0: i64) -> c_int;
+    pub fn sp_dmatrix_to_host_u16(ctx: *mut sp_ctx, d: *const sp_dmatrix, dist: *mut u16) -> c_int;
+    pub fn sp_dmatrix_device_ptr(d: *const sp_dmatrix) -> *mut c_void;
+    pub fn sp_dmatrix_ld(d: *const sp_dmatrix) -> i64;
+    pub fn sp_dmatrix_elem_bits(d: *const sp_dmatrix) -> c_int;
+    pub fn sp_dmatrix_wrap(ctx: *mut sp_ctx, dev_ptr: *mut c_void, n_targets: i64, n_patterns: i64, ld: i64, elem_bits: c_int,
+                           out: *mut *mut sp_dmatrix) -> c_int;
     pub fn sp_last_error(ctx: *const sp_ctx) -> *const c_char;
     pub fn sp_patterns_create(ctx: *mut sp_ctx, p: *const sp_seqset, mode: c_int, out: *mut *mut sp_patterns) -> c_int;
     pub fn sp_patterns_destroy(p: *mut sp_patterns);

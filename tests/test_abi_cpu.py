@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert sorted(binding.SIGNATURES) == syms
 
 
+def test_rust_ffi_crate_declares_every_symbol():
+    """rust/starphase-gpu-sys (the crate a pb-StarPhase maintainer adds; not compiled here: no Rust toolchain) mirrors the header."""
+    text = (ROOT / "rust/starphase-gpu-sys/src/lib.rs").read_text()
+    declared = sorted(set(re.findall(r"pub fn (sp_[a-z0-9_]+)\s*\(", text)))
+    assert declared == header_symbols()
+
+
 def test_no_cpu_fallback():
     import torch
 
