@@ -156,6 +156,33 @@ impl GpuScorer {
         if st != 0 { return Err(Self::err(self.ctx).into()); }
         Ok((d, s, e))
     }
+    /// `score_spans` for the pairs an aligner would report: `start < 0` where the distance exceeds `max_dist_permille` / 1000 of
+    /// the pattern length (weight_sequence uses 350; src/cyp2d6/chaining.rs:58-62 then keeps the default weight).
+    pub fn score_spans_filtered(&self, targets: &SeqSet, patterns: &SeqSet, max_dist_permille: i32)
+        -> Result<(Vec<i32>, Vec<i32>, Vec<i32>), Box<dyn std::error::Error>> {
+        let n = targets.len() * patterns.len();
+        let (mut d, mut s, mut e) = (vec![0i32; n], vec![0i32; n], vec![0i32; n]);
+        let st = unsafe {
+            sp_score_spans_filtered(self.ctx, &targets.raw(), &patterns.raw(), max_dist_permille as c_int, d.as_mut_ptr(), s.as_mut_ptr(),
+                                    e.as_mut_ptr())
+        };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        Ok((d, s, e))
+    }
+    /// (vi_match, all_match) of every (observed allele vector, star-allele definition) pair, `[n_seq][n_hap]` row-major: the
+    /// haplotype loop of `Cyp2d6Extractor::assign_haplotype` (src/cyp2d6/haplotyper.rs:470-517).
+    pub fn variant_match(&self, seq_alleles: &[u8], n_seq: usize, hap_alleles: &[u8], n_hap: usize, is_vi: &[u8])
+        -> Result<(Vec<u32>, Vec<u32>), Box<dyn std::error::Error>> {
+        let n_var = is_vi.len();
+        assert!(seq_alleles.len() == n_seq * n_var && hap_alleles.len() == n_hap * n_var);
+        let (mut vi, mut all) = (vec![0u32; n_seq * n_hap], vec![0u32; n_seq * n_hap]);
+        let st = unsafe {
+            sp_variant_match(self.ctx, n_seq as i64, n_hap as i64, n_var as i64, seq_alleles.as_ptr(), hap_alleles.as_ptr(), is_vi.as_ptr(),
+                             vi.as_mut_ptr(), all.as_mut_ptr())
+        };
+        if st != 0 { return Err(Self::err(self.ctx).into()); }
+        Ok((vi, all))
+    }
     /// Traceback alignment of the listed (target, pattern) pairs: what `aligner.map(..)` + `select_best_mapping` hand to
     /// `HlaProcessedMatch::add_mapping` (query = pattern = allele, target = text = consensus).  Returns the records and
     /// the shared CIGAR buffer of `(len << 4) | op` entries (ops 1 = I, 2 = D, 7 = '=', 8 = X).
