@@ -108,6 +108,11 @@ Json PgxMappingDetails::to_json() const {
     return j;
 }
 
+std::string Diplotype::pharmcat_diplotype() const {
+    auto wrap = [](const std::string &h) { return h.find('+') != std::string::npos ? "[" + h + "]" : h; };
+    return wrap(hap1) + "/" + wrap(hap2);
+}
+
 Json Diplotype::to_json() const {
     Json j = Json::object();
     j.set("hap1", hap1).set("hap2", hap2).set("diplotype", hap1 + "/" + hap2);

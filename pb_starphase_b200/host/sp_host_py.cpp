@@ -172,6 +172,10 @@ PYBIND11_MODULE(_starphase_host, m) {
         for (const auto &d : r.realign_records(reads, n_candidates)) arr.push(d.to_json());
         return arr;
     }, py::arg("gpu"), py::arg("gene_list"), py::arg("database"), py::arg("reads"), py::arg("n_candidates") = 5);
+    m.def("diplotype_strings", [](const std::string &h1, const std::string &h2) {
+        const Diplotype d{h1, h2};
+        return py::make_tuple(d.diplotype(), d.pharmcat_diplotype(), d.to_json().pretty());
+    });
     m.def("hpc", &hpc);
     m.def("hpc_pos", &hpc_pos);
     m.def("realign_records_full", [](GpuAligner &g, const std::vector<std::string> &genes, const DbRows &rows,

@@ -405,8 +405,10 @@ class HlaRealigner {  // src/hla/realigner.rs:22-350
 struct HlaRead {
     std::string qname, dna_target, cdna_target;
 };
-struct Diplotype {  // src/data_types/pgx_diplotype.rs:9-26
+struct Diplotype {  // src/data_types/pgx_diplotype.rs:9-66
     std::string hap1, hap2;
+    std::string diplotype() const { return hap1 + "/" + hap2; }
+    std::string pharmcat_diplotype() const;  // :51-65: a haplotype holding a '+' goes into brackets ("[*4 + *68]/*1")
     Json to_json() const;
 };
 struct HlaGeneCall {

@@ -463,3 +463,11 @@ def test_cyp2d6_alleles_json_reference_docs_vector(host):
     # the other deltas of deep_label (src/cyp2d6/region.rs:60-95)
     assert so.deep_label(so.RegionLabel("CYP2D6", "1.001"), None, [dict(label="a", variant_state="Missing"), dict(label="b", variant_state="AmbiguousMissing"),
                                                                  dict(label="c", variant_state="Match")]) == "X_CYP2D6*1.001 -a ?b"
+
+
+def test_diplotype_strings_reference_vectors(host):  # src/data_types/pgx_diplotype.rs:236-256
+    assert host.diplotype_strings("B", "A")[0] == "B/A"
+    assert host.diplotype_strings("*4", "*1")[1] == "*4/*1"
+    assert host.diplotype_strings("*4x2", "*1")[1] == "*4x2/*1"
+    assert host.diplotype_strings("*4 + *68", "*1")[1] == "[*4 + *68]/*1"
+    assert host.diplotype_strings("*68 + *4.001", "*4.001")[2] == so.serde_pretty(so.diplotype_json("*68 + *4.001", "*4.001"))
