@@ -101,6 +101,36 @@ ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const
     return ret;
 }
 
+ScoreReadResult score_consensus(GpuAligner &gpu, const std::string &reference_sequence, int64_t ref_start, const std::string &consensus,
+                                const HlaDatabase &database, const std::string &gene_name,
+                                const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand,
+                                const DiplotypeSettings &settings) {
+    if (consensus.empty()) return ScoreReadResult();  // :1264-1268
+    // target = reference, query = consensus (:1277-1280); the ref_aligner is the plain map-hifi preset (a = 1)
+    const std::vector<Alignment> alns = gpu.align_pairs({reference_sequence}, {consensus}, {{0, 0}});
+    std::vector<Mapping> mappings;
+    const Alignment &a = alns.at(0);
+    if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {
+        Mapping m;
+        m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = consensus.size();
+        m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = reference_sequence.size();
+        m.nm = static_cast<size_t>(a.nm); m.forward = true; m.cigar = a.cigar;
+        mappings.push_back(std::move(m));
+    }
+    if (mappings.empty()) return ScoreReadResult();  // "Failed to align consensus to reference genome" (:1283-1288)
+    const auto sel = select_best_mapping(mappings, true, true, std::nullopt);  // :1291-1295
+    if (!sel.first) throw HostError("called `Option::unwrap()` on a `None` value");  // :1298: best_mapping.unwrap()
+    const Mapping &d_map = mappings[*sel.first];
+    // convert_mapping_to_cigar(d_map, None, None): alignment ops + soft clips for the unaligned consensus ends
+    std::vector<std::pair<uint32_t, uint8_t>> cigar;
+    if (d_map.query_start > 0) cigar.emplace_back(static_cast<uint32_t>(d_map.query_start), uint8_t(4));
+    cigar.insert(cigar.end(), d_map.cigar.begin(), d_map.cigar.end());
+    if (d_map.query_len > d_map.query_end) cigar.emplace_back(static_cast<uint32_t>(d_map.query_len - d_map.query_end), uint8_t(4));
+    const int64_t start_align = ref_start + static_cast<int64_t>(d_map.target_start);  // :1315-1316
+    const ScoreReadTargets t = prepare_score_read_targets(consensus, start_align, cigar, exons, is_forward_strand, settings);
+    return score_read(gpu, t.dna_target, t.cdna_target, database, gene_name, settings);
+}
+
 Json PgxMappingDetails::to_json() const {
     Json j = Json::object();
     j.set("read_qname", read_qname).set("best_hla_id", best_hla_id).set("best_star_allele", best_star_allele);

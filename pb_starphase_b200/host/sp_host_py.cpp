@@ -152,6 +152,21 @@ PYBIND11_MODULE(_starphase_host, m) {
         }
         return py::make_tuple(stats, r.best_hla_id, r.best_star_allele);
     });
+    m.def("score_consensus", [](GpuAligner &g, const std::string &reference_sequence, int64_t ref_start, const std::string &consensus,
+                                const DbRows &rows, const std::string &gene, const std::vector<std::pair<uint64_t, uint64_t>> &exons,
+                                bool is_forward_strand, const DiplotypeSettings &s) {
+        const HlaDatabase db = make_db(rows);
+        ScoreReadResult r = score_consensus(g, reference_sequence, ref_start, consensus, db, gene, exons, is_forward_strand, s);
+        py::dict stats;
+        for (const auto &kv : r.stats) {
+            auto tup = [](const std::optional<MappingStats> &x) -> py::object {
+                if (!x) return py::none();
+                return py::make_tuple(x->seq_len, x->nm, x->unmapped);
+            };
+            stats[py::str(kv.first)] = py::make_tuple(tup(kv.second.cdna_stats), tup(kv.second.dna_stats));
+        }
+        return py::make_tuple(stats, r.best_hla_id, r.best_star_allele, r.read_mapping_stats.to_json().pretty());
+    });
     // hla_debug.json of one gene scored like diplotype_hla_batch does it (src/hla/caller.rs:805, :877, :914): one score_read per
     // consensus under the names consensus1 / consensus2 + the gene's DualPassingStats
     m.def("hla_debug_json", [](GpuAligner &g, const DbRows &rows, const std::string &gene,

@@ -340,6 +340,16 @@ ScoreReadTargets prepare_score_read_targets(const std::string &read_sequence, in
 ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const std::string &cdna_target, const HlaDatabase &database,
                            const std::string &gene_name, const DiplotypeSettings &settings);
 
+// src/hla/caller.rs:1259-1319: the consensus (hg38 forward strand) is aligned to the gene's reference region (K4 in place of
+// ref_aligner.map), the mapping becomes the CIGAR of an artificial record at ref_start + target_start with the unaligned consensus
+// ends soft-clipped (convert_mapping_to_cigar, src/visualization/debug_bam_writer.rs:310-344), and that record goes through
+// splice_read / the strand handling into score_read.  exons: absolute reference coordinates.  An empty consensus or one that does
+// not align gives the empty result of :1264-1268 / :1283-1288.
+ScoreReadResult score_consensus(GpuAligner &gpu, const std::string &reference_sequence, int64_t ref_start, const std::string &consensus,
+                                const HlaDatabase &database, const std::string &gene_name,
+                                const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand,
+                                const DiplotypeSettings &settings);
+
 struct PgxMappingDetails {  // src/data_types/starphase_json.rs:271-283
     std::string read_qname, best_hla_id, best_star_allele;
     HlaMappingStats best_mapping_stats;

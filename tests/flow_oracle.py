@@ -95,6 +95,29 @@ def hla_debug_json(orc, db: Sequence[DbRow], gene: str, consensuses: Sequence[Tu
     return so.hla_debug_json(reads, {gene: so.dual_passing_stats(is_dual, counts1, counts2)})
 
 
+def score_consensus(orc, reference_sequence: bytes, ref_start: int, consensus: bytes, db: Sequence[DbRow], gene: str,
+                    exons: Sequence[Tuple[int, int]], is_forward_strand: bool):
+    """src/hla/caller.rs:1259-1319 on the oracle's alignment: consensus -> reference mapping -> soft-clipped CIGAR -> splice -> score_read.
+    Returns (stats, best id, best star, ReadMappingStats JSON dict), all empty for an empty / unalignable consensus."""
+    empty = ({}, "", "", so.read_mapping_stats_json(None, None, {}))
+    if not consensus:
+        return empty
+    al = orc.align(consensus, reference_sequence)
+    cand = []
+    if al["cigar"] and dp_score_a1(al["cigar"]) >= 200:
+        cand.append(so.Mapping(al["p_start"], al["p_end"], len(consensus), al["t_start"], al["t_end"], len(reference_sequence), al["nm"], True,
+                               al["cigar"]))
+    if not cand:
+        return empty
+    idx, _ = so.select_best_mapping(cand, True, True)
+    assert idx is not None
+    m = cand[idx]
+    cigar = ([(m.query_start, 4)] if m.query_start > 0 else []) + list(m.cigar) + ([(m.query_len - m.query_end, 4)] if m.query_len > m.query_end else [])
+    dna_t, cdna_t = so.prepare_score_read_targets(consensus, ref_start + m.target_start, cigar, exons, is_forward_strand)
+    stats, best_id, best_star = score_read(orc, dna_t, cdna_t, db, gene)
+    return stats, best_id, best_star, score_read_debug(orc, dna_t, cdna_t, db, gene)
+
+
 def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5,
                     D: Optional[np.ndarray] = None) -> List[dict]:
     """src/hla/realigner.rs:98-211: candidates = the n alleles with the most bases explained, |allele| - (nm + unmapped), ties by database order."""

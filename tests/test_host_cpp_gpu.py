@@ -111,6 +111,41 @@ def test_score_read_vs_oracle(host, gpu, oracle):
     assert (dict(got[0]), got[1], got[2]) == fo.score_read(oracle, dna_t, cdna_t, rows, "HLA-A", disable_cdna=True)
 
 
+def test_score_consensus_vs_oracle(host, gpu, oracle):
+    """score_consensus (src/hla/caller.rs:1259-1319): consensus -> reference mapping (K4) -> soft-clipped CIGAR -> splice_read and the
+    strand handling -> score_read, for a forward-strand and a reverse-strand gene, against the same flow on the oracle."""
+    rng = np.random.default_rng(29)
+    ref_start, exon_rel = 10_000, [(300, 600), (1000, 1300), (2000, 2400)]
+    for gene, fwd in (("HLA-A", True), ("HLA-B", False)):
+        root = rnd(rng, 3000)                       # hg38 orientation
+        hg = [root]
+        for k in range(1, 9):                       # substitutions only: the exon coordinates stay put
+            a = bytearray(root)
+            for pos in rng.choice(len(a), size=4 + k, replace=False):
+                a[pos] = ord(rng.choice([c for c in "ACGT" if c != chr(a[pos])]))
+            hg.append(bytes(a))
+        splice = lambda s_: b"".join(s_[a:b] for a, b in exon_rel)
+        rows = []
+        for k, a in enumerate(hg):
+            dna = a if fwd else so.reverse_complement(a)
+            cdna = splice(a) if fwd else so.reverse_complement(splice(a))
+            rows.append((f"HLA:HLA{k:05d}", gene, ["01", f"{k + 1:02d}", "01", "01"], dna.decode(), cdna.decode()))
+        L, R = rnd(rng, 500), rnd(rng, 500)
+        reference = L + root + R
+        exons = [(ref_start + 500 + a, ref_start + 500 + b) for a, b in exon_rel]
+        cases = [("exact_5", L[-150:] + hg[5] + R[:150]), ("noisy_2", noisy(rng, L[-80:] + hg[2] + R[:60], 6)),
+                 ("with_junk_ends", rnd(rng, 40) + hg[7] + rnd(rng, 30)), ("empty", b""), ("junk", rnd(rng, 1500))]
+        for name, cons in cases:
+            got = host.score_consensus(gpu, reference.decode(), ref_start, cons.decode(), rows, gene, exons, fwd, host.DiplotypeSettings())
+            want = fo.score_consensus(oracle, reference, ref_start, cons, rows, gene, exons, fwd)
+            assert (dict(got[0]), got[1], got[2]) == want[:3], (gene, name)
+            assert got[3] == so.serde_pretty(want[3]), (gene, name)
+        got = host.score_consensus(gpu, reference.decode(), ref_start, cases[0][1].decode(), rows, gene, exons, fwd, host.DiplotypeSettings())
+        assert got[1] == rows[5][0] and got[0][rows[5][0]] == ((len(rows[5][4]), 0, 0), (len(rows[5][3]), 0, 0))
+        assert host.score_consensus(gpu, reference.decode(), ref_start, "", rows, gene, exons, fwd, host.DiplotypeSettings())[:3] == ({}, "", "")
+        assert host.score_consensus(gpu, reference.decode(), ref_start, cases[4][1].decode(), rows, gene, exons, fwd, host.DiplotypeSettings())[1] == ""
+
+
 def test_hla_debug_json_vs_oracle(host, gpu, oracle):
     """hla_debug.json (src/hla/debug.rs): per consensus and allele the DetailedMappingStats of the best cDNA / DNA mapping
     (lengths, match_len, nm, unmapped on both sides, EQX CIGAR string, MD string) + DualPassingStats -- the artefact a
