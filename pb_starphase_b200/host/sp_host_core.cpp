@@ -110,6 +110,15 @@ static double score_value(size_t mapping_len, size_t nm, size_t unmapped) {  // 
     return std::max(static_cast<double>(nm + unmapped), 0.1) / static_cast<double>(mapping_len);
 }
 
+double harmonic_mean(const std::vector<double> &scores) {
+    double sum = 0.0;
+    for (double v : scores) {
+        if (!(v > 0.0)) throw HostError("dna_score must be > 0.0");
+        sum += 1.0 / v;
+    }
+    return sum > 0.0 ? static_cast<double>(scores.size()) / sum : 0.0;
+}
+
 double MappingStats::custom_score(bool penalize_unmapped) const {
     if (penalize_unmapped) return score_value(seq_len, nm, unmapped);
     return score_value(seq_len - unmapped, nm, 0);

@@ -191,6 +191,7 @@ PYBIND11_MODULE(_starphase_host, m) {
         const Diplotype d{h1, h2};
         return py::make_tuple(d.diplotype(), d.pharmcat_diplotype(), d.to_json().pretty());
     });
+    m.def("harmonic_mean", &harmonic_mean);
     m.def("hpc", &hpc);
     m.def("hpc_pos", &hpc_pos);
     m.def("realign_records_full", [](GpuAligner &g, const std::vector<std::string> &genes, const DbRows &rows,

@@ -89,6 +89,9 @@ struct MappingStats {  // src/data_types/mapping.rs:7-22
     }
 };
 
+// MappingScore::harmonic_mean, src/data_types/mapping.rs:172-183; throws on a score <= 0 ("dna_score must be > 0.0")
+double harmonic_mean(const std::vector<double> &scores);
+
 struct HlaMappingStats {  // src/hla/mapping.rs:9-14
     std::optional<MappingStats> cdna_stats, dna_stats;
     std::pair<double, double> mapping_score() const;  // (cDNA, DNA), missing side = 1.0 (:66-83, :111-117)

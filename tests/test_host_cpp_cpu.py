@@ -471,3 +471,10 @@ def test_diplotype_strings_reference_vectors(host):  # src/data_types/pgx_diplot
     assert host.diplotype_strings("*4x2", "*1")[1] == "*4x2/*1"
     assert host.diplotype_strings("*4 + *68", "*1")[1] == "[*4 + *68]/*1"
     assert host.diplotype_strings("*68 + *4.001", "*4.001")[2] == so.serde_pretty(so.diplotype_json("*68 + *4.001", "*4.001"))
+
+
+def test_harmonic_mean_reference_vector(host):  # src/data_types/mapping.rs:230-241
+    assert host.harmonic_mean([0.2, 0.4, 0.2]) == 3.0 / (5.0 + 2.5 + 5.0) == so.harmonic_mean([0.2, 0.4, 0.2])
+    assert host.harmonic_mean([]) == 0.0
+    with pytest.raises(host.HostError, match="dna_score must be > 0.0"):
+        host.harmonic_mean([0.1, 0.0])
