@@ -259,6 +259,44 @@ sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, const int32_t 
                                    sp_pair_rec *out, int *n_out);
 sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S);
 
+/* ---- multi-GPU: the path over the GPUs of one box ------------------------ */
+/* The reference is one process on one thread (src/cli/diplotype.rs:185-191) and has no distributed code; the north_star
+ * partitions this path as: allele set sharded for K1, read set broadcast, allele-pair row blocks sharded for K2, per-shard
+ * top-k merged with NCCL.  One sp_comm per (sp_ctx, GPU).  The ranks of a communicator are processes (one per GPU) or
+ * threads of one process, each driving its own context; every sp_comm_* call below is a collective: all ranks make it, in
+ * the same order.  NCCL is loaded with dlopen on first use ($SP_NCCL_LIB, else libnccl.so.2): hosts that use one GPU
+ * never need it.  world == 1 communicators work without NCCL. */
+typedef struct sp_comm sp_comm;
+#define SP_COMM_ID_BYTES 128
+/* Rank 0 draws the id (ncclGetUniqueId) and the host program carries the bytes to the other ranks. */
+sp_status sp_comm_unique_id(uint8_t *id /* SP_COMM_ID_BYTES */);
+sp_status sp_comm_create(sp_ctx *ctx, const uint8_t *id, int rank, int world, sp_comm **out);
+void sp_comm_destroy(sp_comm *c);
+int sp_comm_rank(const sp_comm *c);
+int sp_comm_world(const sp_comm *c);
+/* Returns when every rank has made the call and this rank's stream has drained. */
+sp_status sp_comm_barrier(sp_comm *c);
+
+/* Host-only.  Which patterns of a set (lengths lens[0..n)) rank `rank` of `world` owns: dealt in length order so that every
+ * shard packs into the same lane-width classes as the whole set (equal K1 cost per rank).  idx has room for n entries and
+ * receives the owned indices in ascending order. */
+sp_status sp_shard_plan(const int64_t *lens, int64_t n, int world, int rank, int64_t *idx, int64_t *n_idx);
+/* Host-only.  Row range [lo, hi) of the pair triangle i <= j < n that `rank` scores in sp_comm_pair_minsum_topk
+ * (equal pair counts per rank). */
+sp_status sp_triangle_rows(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);
+
+/* Read-set broadcast: `targets` is read on `root` only (may be NULL elsewhere); every rank gets device-resident targets. */
+sp_status sp_comm_bcast_targets(sp_comm *c, const sp_seqset *targets, int root, sp_targets **out);
+/* K1 over the sharded database: `shard` holds this rank's patterns (created with sp_patterns_create from the sequences
+ * sp_shard_plan selected, in that order), shard_idx[i] = database index of its i-th pattern, n_total = size of the database.
+ * Every rank scores its shard, the shards are all-gathered and the rows put into database order: *out is the full
+ * [n_total patterns x targets] matrix (same layout as sp_score_device) on every rank, bit-identical for any world size. */
+sp_status sp_comm_score_allgather(sp_comm *c, const sp_targets *t, const sp_patterns *shard, const int64_t *shard_idx,
+                                  int64_t n_total, int elem_bits, sp_dmatrix **out);
+/* K2 over the pair triangle, rows split by sp_triangle_rows, per-rank lists all-gathered and merged by
+ * (score, score2, i, j): every rank returns the list sp_pair_minsum_topk(0, n) would give on one GPU. */
+sp_status sp_comm_pair_minsum_topk(sp_comm *c, const sp_dmatrix *d, const sp_dmatrix *d2, int k, sp_pair_rec *out, int *n_out);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 /* Integer-ALU microbenchmark used for the roofline denominator: runs a
  * dependent-free loop on every SM and returns achieved 32-bit lane-ops per second.

@@ -9,6 +9,7 @@ fallback: importing works anywhere, but every compute call needs the built
 libstarphase_gpu.so and a B200.
 """
 from .binding import (  # noqa: F401
+    Comm,
     Context,
     DMatrix,
     PatternSet,

@@ -88,6 +88,17 @@ SIGNATURES = {
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
     "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    "sp_comm_unique_id": (C.c_int, [_P]),
+    "sp_comm_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "sp_comm_destroy": (None, [_P]),
+    "sp_comm_rank": (C.c_int, [_P]),
+    "sp_comm_world": (C.c_int, [_P]),
+    "sp_comm_barrier": (C.c_int, [_P]),
+    "sp_shard_plan": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.POINTER(C.c_int64)]),
+    "sp_triangle_rows": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sp_comm_bcast_targets": (C.c_int, [_P, C.POINTER(SeqSet), C.c_int, C.POINTER(_P)]),
+    "sp_comm_score_allgather": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "sp_comm_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_int_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "sp_version": (C.c_char_p, []),
 }
@@ -136,6 +147,38 @@ def plan_lane_classes(lens, max_classes: int = 4):
     if st != 0:
         raise SpError(st, "sp_plan_lane_classes failed")
     return [(int(w[k]), int(npat[k]), int(nw[k])) for k in range(nc.value)], int(padded.value)
+
+
+def shard_plan(lens, world: int, rank: int) -> np.ndarray:
+    """Host-only (sp_shard_plan): ascending database indices of the patterns rank `rank` of `world` owns."""
+    lib = load_library()
+    a = np.ascontiguousarray(lens, dtype=np.int64)
+    idx = np.zeros(max(len(a), 1), dtype=np.int64)
+    n = C.c_int64(0)
+    st = lib.sp_shard_plan(a.ctypes.data, len(a), world, rank, idx.ctypes.data, C.byref(n))
+    if st != 0:
+        raise SpError(st, "sp_shard_plan failed")
+    return idx[: n.value].copy()
+
+
+def triangle_rows(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Host-only (sp_triangle_rows): row range of the pair triangle scored by `rank`."""
+    lib = load_library()
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    st = lib.sp_triangle_rows(n, world, rank, C.byref(lo), C.byref(hi))
+    if st != 0:
+        raise SpError(st, "sp_triangle_rows failed")
+    return int(lo.value), int(hi.value)
+
+
+def comm_unique_id() -> bytes:
+    """sp_comm_unique_id: 128 bytes drawn on rank 0, to be carried to the other ranks by the host program."""
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    st = lib.sp_comm_unique_id(buf)
+    if st != 0:
+        raise SpError(st, lib.sp_last_error(None).decode())
+    return bytes(buf)
 
 
 def _seqset(bases: np.ndarray, offs: np.ndarray) -> SeqSet:
@@ -360,6 +403,55 @@ class Context:
         return DMatrix(self, h, n_targets, n_patterns, False)
 
 
+class Comm:
+    """sp_comm: this rank's end of a communicator over the GPUs of one box; every method is a collective."""
+
+    def __init__(self, ctx: Context, unique_id: bytes, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id).ljust(128, b"\0")[:128])
+        h = _P()
+        ctx._check(ctx._lib.sp_comm_create(ctx._h, buf, rank, world, C.byref(h)))
+        self._h = h
+
+    def barrier(self):
+        self.ctx._check(self.ctx._lib.sp_comm_barrier(self._h))
+
+    def bcast_targets(self, seqs, root: int = 0) -> "TargetSet":
+        """seqs is read on `root` only (None elsewhere)."""
+        ss = None
+        if self.rank == root:
+            bases, offs = seqs if isinstance(seqs, tuple) else pack_sequences(seqs)
+            ss = _seqset(bases, offs)
+        h = _P()
+        self.ctx._check(self.ctx._lib.sp_comm_bcast_targets(self._h, C.byref(ss) if ss is not None else None, root, C.byref(h)))
+        return TargetSet._adopt(self.ctx, h)
+
+    def score_allgather(self, targets: "TargetSet", shard: "PatternSet", shard_idx, n_total: int, elem_bits: int = 16) -> "DMatrix":
+        idx = np.ascontiguousarray(shard_idx, dtype=np.int64)
+        h = _P()
+        self.ctx._check(self.ctx._lib.sp_comm_score_allgather(self._h, targets._h, shard._h, idx.ctypes.data, n_total, elem_bits, C.byref(h)))
+        return DMatrix(self.ctx, h, targets.n, n_total, False)
+
+    def pair_minsum_topk(self, d: "DMatrix", k: int = 10, d2: Optional["DMatrix"] = None):
+        recs = (PairRec * k)()
+        n = C.c_int(0)
+        self.ctx._check(self.ctx._lib.sp_comm_pair_minsum_topk(self._h, d._h, d2._h if d2 is not None else None, k, recs, C.byref(n)))
+        if d2 is None:
+            return [(int(r.score), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
+        return [(int(r.score), int(r.score2), int(r.i), int(r.j), int(r.c1)) for r in recs[: n.value]]
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sp_comm_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PatternSet:
     def __init__(self, ctx: Context, seqs, mode: int = SP_INFIX):
         self.ctx = ctx
@@ -394,6 +486,14 @@ class TargetSet:
         self._h = h
         self.n = len(offs) - 1
         self.total_len = int(ctx._lib.sp_targets_total_len(h))
+
+    @classmethod
+    def _adopt(cls, ctx: Context, h) -> "TargetSet":
+        self = cls.__new__(cls)
+        self.ctx, self._h = ctx, h
+        self.n = int(ctx._lib.sp_targets_count(h))
+        self.total_len = int(ctx._lib.sp_targets_total_len(h))
+        return self
 
     def close(self):
         if getattr(self, "_h", None) and self.ctx._h:

@@ -10,13 +10,19 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libstarphase_gpu.so"
-SOURCES = ["starphase_gpu.cu", "sp_kernels.cuh", "sp_align.cuh", "sp_addchain.inc", "../../include/starphase_gpu.h"]
+# translation units of the library and the headers each one depends on
+HEADERS = ["sp_internal.cuh", "sp_kernels.cuh", "sp_addchain.inc", "../../include/starphase_gpu.h"]
+UNITS = {
+    "starphase_gpu.cu": HEADERS + ["sp_misc.cuh"],   # context, K1 / K2 / K3 / K5 / K6
+    "sp_align.cu": HEADERS + ["sp_align.cuh"],       # K4
+    "sp_comm.cu": HEADERS + ["sp_comm_kernels.cuh"],  # multi-GPU (NCCL, loaded with dlopen at run time)
+}
+OBJDIR = CSRC / "build"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -27,22 +33,40 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libstarphase_gpu.so")
 
 
-def needs_build() -> bool:
-    if not LIB.exists():
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
         return True
-    t = LIB.stat().st_mtime
-    return any((CSRC / s).resolve().stat().st_mtime > t for s in SOURCES)
+    t = target.stat().st_mtime
+    return any((CSRC / d).resolve().stat().st_mtime > t for d in deps)
+
+
+def needs_build() -> bool:
+    return any(_stale(LIB, [u] + deps) for u, deps in UNITS.items())
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -c per translation unit (objects cached under csrc/build/, rebuilt when the unit or one of its headers changed),
+    then one shared-library link with the static CUDA runtime."""
     if not force and not needs_build():
         return LIB
     subprocess.check_call([sys.executable, str(CSRC / "gen_addchain.py")], cwd=CSRC)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "starphase_gpu.cu")]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-        print(" ".join(cmd))
-    subprocess.check_call(cmd, cwd=CSRC)
+    OBJDIR.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    objs, procs = [], []
+    for unit, deps in UNITS.items():
+        obj = OBJDIR / (Path(unit).stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [unit] + deps):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(CSRC / unit)]
+            if verbose:
+                cmd[1:1] = ["-Xptxas", "-v"]
+                print(" ".join(cmd))
+            procs.append((unit, subprocess.Popen(cmd, cwd=CSRC)))
+    for unit, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, f"nvcc {unit}")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", str(LIB),
+                           *map(str, objs), "-ldl"], cwd=CSRC)
     return LIB
 
 

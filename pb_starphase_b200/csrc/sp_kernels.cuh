@@ -352,6 +352,7 @@ struct SpanParams {
     unsigned long long *next_pair;  // work counter (zeroed by the host): pairs are handed out one at a time
 };
 
+#ifndef SP_NO_GLOBAL_KERNELS
 __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
     constexpr int U = SPAN_U;
     constexpr int BW = blob_words(U);
@@ -420,6 +421,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
     }
 }
 
+#endif  // SP_NO_GLOBAL_KERNELS
+
 // ------------------------------------------------------------------------------------------
 // K3 chain windows: B[c][r] = min over windows s of chain c of sum_t W[r][t][chain_c[s + t]], or 2 * worst_r
 // when the chain is shorter than the read's segment count -- the inner loop of containment_score
@@ -437,6 +440,7 @@ struct ChainWinParams {
     int n_chains, n_reads, n_haps;
 };
 
+#ifndef SP_NO_GLOBAL_KERNELS
 __global__ void __launch_bounds__(256) k3_chain_windows(const ChainWinParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
@@ -531,6 +535,8 @@ __global__ void pack_texts(const uint8_t *__restrict__ bases, const long long *_
     }
 }
 
+#endif  // SP_NO_GLOBAL_KERNELS
+
 // D[p*ld + t] (u16 / i32) -> host-order rows[t * np + p] (int32, or u16 for the 16-bit read-back)
 template <typename T, typename O>
 __global__ void dmatrix_to_rows(const T *__restrict__ D, long long ld, int nt, int np, O *__restrict__ rows) {
@@ -548,6 +554,7 @@ __global__ void dmatrix_to_rows(const T *__restrict__ D, long long ld, int nt, i
 }
 
 // host-order int32 rows[r * A + a] -> D[a*ld + r] int32 (for the *_host K2 entry points)
+#ifndef SP_NO_GLOBAL_KERNELS
 __global__ void rows_to_dmatrix(const int32_t *__restrict__ rows, int R, int A, long long ld, int32_t *__restrict__ D) {
     __shared__ int32_t tile[32][33];
     const int a0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -561,6 +568,8 @@ __global__ void rows_to_dmatrix(const int32_t *__restrict__ rows, int R, int A, 
         if (a < A && r < R) D[static_cast<long long>(a) * ld + r] = tile[threadIdx.x][i];
     }
 }
+
+#endif  // SP_NO_GLOBAL_KERNELS
 
 // ------------------------------------------------------------------------------------------
 // K2: pair min-sum.  CTA = 64 x 64 pair tile (i-tile I, j-tile J >= I), 256 threads x (4 x 4).

@@ -4,7 +4,7 @@
 // exists in this image, so this is the compiled-language mirror of the reference's operator interface for
 // the hot path: same names, argument meaning and error behaviour as the Rust functions cited at each
 // declaration (paths relative to the pb-StarPhase v2.0.1 tree), with every alignment number coming from
-// libstarphase_gpu.so.  Nothing here computes an alignment on the CPU and nothing links the oracle.
+// libstarphase_gpu.so.  Nothing here computes an alignment on the CPU.
 //
 //   src/data_types/mapping.rs, src/hla/mapping.rs   MappingStats, HlaMappingStats, scores
 //   src/util/mapping.rs:22-57                       select_best_mapping

@@ -41,6 +41,8 @@ pub enum sp_ctx {}
 pub enum sp_patterns {}
 pub enum sp_targets {}
 pub enum sp_dmatrix {}
+pub enum sp_comm {}
+pub const SP_COMM_ID_BYTES: usize = 128;
 
 pub const SP_INFIX: c_int = 0;
 pub const SP_PREFIX: c_int = 1;
@@ -103,6 +105,20 @@ extern "C" {
     pub fn sp_pair_minsum_topk_host(ctx: *mut sp_ctx, d: *const i32, d2: *const i32, r: i64, a: i64, k: c_int,
                                     out: *mut sp_pair_rec, n_out: *mut c_int) -> c_int;
     pub fn sp_pair_minsum_full_host(ctx: *mut sp_ctx, d: *const i32, r: i64, a: i64, s: *mut u64) -> c_int;
+    // multi-GPU (one sp_comm per context; ranks are processes or threads, every call below is a collective)
+    pub fn sp_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn sp_comm_create(ctx: *mut sp_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut sp_comm) -> c_int;
+    pub fn sp_comm_destroy(c: *mut sp_comm);
+    pub fn sp_comm_rank(c: *const sp_comm) -> c_int;
+    pub fn sp_comm_world(c: *const sp_comm) -> c_int;
+    pub fn sp_comm_barrier(c: *mut sp_comm) -> c_int;
+    pub fn sp_shard_plan(lens: *const i64, n: i64, world: c_int, rank: c_int, idx: *mut i64, n_idx: *mut i64) -> c_int;
+    pub fn sp_triangle_rows(n: i64, world: c_int, rank: c_int, lo: *mut i64, hi: *mut i64) -> c_int;
+    pub fn sp_comm_bcast_targets(c: *mut sp_comm, targets: *const sp_seqset, root: c_int, out: *mut *mut sp_targets) -> c_int;
+    pub fn sp_comm_score_allgather(c: *mut sp_comm, t: *const sp_targets, shard: *const sp_patterns, shard_idx: *const i64,
+                                   n_total: i64, elem_bits: c_int, out: *mut *mut sp_dmatrix) -> c_int;
+    pub fn sp_comm_pair_minsum_topk(c: *mut sp_comm, d: *const sp_dmatrix, d2: *const sp_dmatrix, k: c_int, out: *mut sp_pair_rec,
+                                    n_out: *mut c_int) -> c_int;
 }
 
 /// Concatenated sequences in the layout of `sp_seqset`.

@@ -19,8 +19,8 @@ class PairRec(C.Structure):
 
 
 def build_oracle(force: bool = False) -> Path:
-    src = ORACLE_DIR / "sp_oracle.c"
-    if force or not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
+    newest = max((ORACLE_DIR / f).stat().st_mtime for f in ("sp_oracle.c", "sp_oracle_affine.c", "Makefile"))
+    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
         subprocess.check_call(["make", "-C", str(ORACLE_DIR), "-B" if force else "-s"])
     return LIB
 
@@ -129,3 +129,75 @@ class Oracle:
         S = np.zeros((D.shape[1], D.shape[1]), dtype=np.uint64)
         self.lib.sp_oracle_pair_minsum_full(D.ctypes.data, D.shape[0], D.shape[1], nthreads, S.ctypes.data)
         return S
+
+
+# minimap2 cost sets at the reference's call sites: {a, b, q, e, q2, e2}
+COSTS_MAP_HIFI = (1, 4, 6, 2, 26, 1)      # standard_hifi_aligner(), src/util/mapping.rs:8-14 (realigner, CYP2D6, consensus -> reference)
+COSTS_ALLELE_SCORING = (5, 4, 6, 2, 26, 1)  # mapopt.a = 5 in score_read, src/hla/caller.rs:1370-1381
+
+
+class AffineOracle:
+    """Second-opinion oracle (oracle/sp_oracle_affine.c): best local alignment under minimap2's two-piece affine cost model.
+    `.align(pattern, text)` returns the dict shape of Oracle.align plus `score`, so tests/flow_oracle.py runs unchanged on it;
+    `prefetch` fills the cache for many pairs with OpenMP over pairs."""
+
+    def __init__(self, costs=COSTS_ALLELE_SCORING):
+        self.lib = C.CDLL(str(build_oracle()))
+        self.costs = np.asarray(costs, dtype=np.int32)
+        L = self.lib
+        L.sp_oracle_affine_local.restype = C.c_int64
+        L.sp_oracle_affine_local.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.sp_oracle_affine_batch.restype = C.c_int64
+        L.sp_oracle_affine_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        self.cache = {}
+
+    @staticmethod
+    def _rec(rec, cig):
+        return {"dist": int(rec[7]), "nm": int(rec[1]), "p_start": int(rec[2]), "p_end": int(rec[3]), "t_start": int(rec[4]),
+                "t_end": int(rec[5]), "cigar": [(int(x) >> 4, int(x) & 15) for x in cig], "score": int(rec[0])}
+
+    def align(self, pattern: bytes, text: bytes) -> dict:
+        key = (bytes(pattern), bytes(text))
+        hit = self.cache.get(key)
+        if hit is not None:
+            return hit
+        rec = np.zeros(8, dtype=np.int32)
+        cap = len(pattern) + len(text) + 2
+        cig = np.zeros(cap, dtype=np.uint32)
+        n = self.lib.sp_oracle_affine_local(key[0], len(key[0]), key[1], len(key[1]), self.costs.ctypes.data, rec.ctypes.data,
+                                            cig.ctypes.data, cap)
+        assert n >= 0
+        out = self.cache[key] = self._rec(rec, cig[:n])
+        return out
+
+    def align_batch(self, targets, patterns, pairs, nthreads: int = 0, want_cigar: bool = True):
+        """pairs = [(target index, pattern index)]; returns the list of dicts (cigar = None when not wanted)."""
+        tb, to = _pack(targets)
+        pb, po = _pack(patterns)
+        pt = np.ascontiguousarray([t for t, _ in pairs], dtype=np.int32)
+        pp = np.ascontiguousarray([p for _, p in pairs], dtype=np.int32)
+        n = len(pairs)
+        recs = np.zeros((n, 8), dtype=np.int32)
+        offs = np.zeros(n, dtype=np.int64)
+        cap = int(sum(min(len(patterns[p]) + len(targets[t]) + 2, 4096) for t, p in pairs)) if want_cigar else 0
+        cig = np.zeros(max(cap, 1), dtype=np.uint32)
+        self.lib.sp_oracle_affine_batch(tb.ctypes.data, to.ctypes.data, pb.ctypes.data, po.ctypes.data, n, pt.ctypes.data, pp.ctypes.data,
+                                        self.costs.ctypes.data, nthreads, recs.ctypes.data, offs.ctypes.data,
+                                        cig.ctypes.data if want_cigar else None, cap)
+        out = []
+        for k in range(n):
+            if want_cigar:
+                assert offs[k] >= 0, "affine CIGAR pool overflow"
+                out.append(self._rec(recs[k], cig[offs[k]:offs[k] + recs[k][6]]))
+            else:
+                d = self._rec(recs[k], [])
+                d["cigar"] = None
+                out.append(d)
+        return out
+
+    def prefetch(self, patterns, text: bytes, nthreads: int = 0):
+        """Aligns every pattern against one text in parallel and keeps the results for .align()."""
+        todo = [p for p in dict.fromkeys(bytes(p) for p in patterns) if (p, bytes(text)) not in self.cache]
+        for p, r in zip(todo, self.align_batch([text], todo, [(0, k) for k in range(len(todo))], nthreads)):
+            self.cache[(p, bytes(text))] = r

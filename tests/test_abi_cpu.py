@@ -50,8 +50,8 @@ def test_no_cpu_fallback():
 
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing in the package may reference it."""
-    for p in (ROOT / "pb_starphase_b200").rglob("*"):
-        if p.suffix in {".py", ".cu", ".cuh", ".h", ".cpp", ".inc"}:
+    for p in list((ROOT / "pb_starphase_b200").rglob("*")) + list((ROOT / "rust").rglob("*")) + list((ROOT / "include").rglob("*")):
+        if p.suffix in {".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".inc", ".rs"}:
             assert "oracle" not in p.read_text().lower(), p
 
 
