@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200 scoring path (contract: see the task statement / DESIGN.md §6).
 
-Metric (BASELINE.json): HLA read-allele GCUPS.  Workload: BASELINE.json configs[1], "HLA-A/HLA-B WGS 30x:
-~2k synthetic HiFi reads x full IMGT/HLA allele set" (SURVEY.md §8(d).2): 2,048 reads per GPU against
-12,451 DNA + 19,629 cDNA alleles.  One step = K1(DNA) + K1(cDNA) + K2 (cDNA,DNA)-lexicographic pair
-scoring per gene + top-k merge.  N > 1: reads = 2,048 x N (broadcast), alleles sharded N ways (weak
-scaling), D shards all-gathered over NCCL for K2, per-shard top-k merged.
+Metric (BASELINE.json): HLA read-allele GCUPS (+ samples/s).  Main leg = BASELINE.json configs[1], "HLA-A/HLA-B WGS 30x:
+~2k synthetic HiFi reads x full IMGT/HLA allele set" (SURVEY.md §8(d).2): 2,048 reads per GPU against 12,451 DNA +
+19,629 cDNA alleles.  One step = K1(DNA) + K1(cDNA) + K2 (cDNA,DNA)-lexicographic pair scoring per gene + top-k merge.
+N > 1: reads = 2,048 x N (weak scaling), broadcast from rank 0; alleles dealt to the ranks by sp_shard_plan, D shards
+all-gathered into database order, K2 row blocks per rank, per-rank top-k merged -- all through the library's own multi-GPU
+C ABI (sp_comm_*, NCCL inside libstarphase_gpu.so); torch.distributed only carries the communicator id and the final timings.
+Two more legs ride in the same JSON line: `panel` = configs[2] (40,960 fixed reads, alleles sharded N ways: STRONG scaling)
+and `cohort` = configs[4] (independent samples through the C++ host, 125 per GPU = 1,000 on 8 GPUs; `samples_per_s`).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--panel-reads R] [--cohort-samples S]
 """
 from __future__ import annotations
 
@@ -33,7 +36,8 @@ INT_OPS_PER_CELL = 23.0 / 64.0  # Hyyro block step = 23 INT32-
 TOPK = 16
 
 
-K1_DNA_DRAM_BYTES_PER_STEP = 167551829  # profiles/r01e_k1_traffic.csv
+PANEL_READS = 40960      # BASELINE configs[2]
+COHORT_PER_GPU = 125     # BASELINE configs[4]: 1,000 samples on 8 GPUs
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first communicator
 # when NCCL_DEBUG=VERSION is set in the environment), so the process's fd 1 is pointed at stderr for its whole life and the
@@ -67,18 +71,21 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SP_BENCH_SCALE", "1.0")),
                     help="debug only: shrink the allele set (a scaled run is NOT a valid bench number)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
-    ap.add_argument("--cohort-samples", type=int, default=6,
-                    help="samples per GPU for the cohort leg (BASELINE configs[4], reported under `cohort`); 0 disables it")
+    ap.add_argument("--cohort-samples", type=int, default=COHORT_PER_GPU,
+                    help="samples per GPU for the cohort leg (BASELINE configs[4]: 125 x 8 GPUs = 1,000 samples); 0 disables it")
+    ap.add_argument("--panel-reads", type=int, default=PANEL_READS,
+                    help="reads of the strong-scaling panel leg (BASELINE configs[2]: 40,960); 0 disables it")
+    ap.add_argument("--panel-steps", type=int, default=1, help="timed steps of the panel leg (one step is ~110 s on one GPU)")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
-def build_workload(n_gpus: int, scale: float):
+def build_workload(n_gpus: int, scale: float, n_reads: int | None = None):
     from pb_starphase_b200 import synth
 
-    genes = synth.hla_wgs_workload(synth.DEFAULT_SEED, READS_PER_GPU * n_gpus, scale)
+    genes = synth.hla_wgs_workload(synth.DEFAULT_SEED, READS_PER_GPU * n_gpus if n_reads is None else n_reads, scale)
     A, B = genes["HLA-A"], genes["HLA-B"]
     w = dict(
         dna=A["dna"] + B["dna"], cdna=A["cdna"] + B["cdna"],
@@ -171,6 +178,19 @@ def cpu_sample(w, budget_s: float, steps: int = 1):
 
 
 # ---------------------------------------------------------------------------------------------
+# shared pieces of the JSON line
+# ---------------------------------------------------------------------------------------------
+def workload_name(n):
+    return f"hla_wgs30x: {READS_PER_GPU * n} reads x 12,451 DNA + 19,629 cDNA alleles (BASELINE configs[1]" + (")" if n == 1 else f", reads x{n}, alleles sharded {n} ways)")
+
+
+def bench_config(n, scale):
+    """`config` of the line; identical for both arms (the reference arm times a bounded sample of it, see cpu_baseline.sample)."""
+    return dict(workload=workload_name(n), seed=20251106, l2="flushed between timed steps (256 MB write)",
+                step="K1 DNA + K1 cDNA + K2 (cDNA,DNA) pair top-%d per gene" % TOPK, scale=scale)
+
+
+# ---------------------------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
@@ -181,115 +201,28 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         cpu_sample(w, 1.0)
     res = cpu_sample(w, max(3.0, args.cpu_seconds / max(args.steps, 1)), steps=args.steps)
+    cells_total = w["cells_dna"] + w["cells_cdna"]
     line = dict(metric=METRIC, value=res["gcups"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
-                data="synthetic", impl="reference",
-                config=dict(workload=workload_name(args.gpus), note="oracle port of the reference's CPU path (64-bit Myers, "
-                            "OpenMP); the Rust reference + minimap2 cannot be built here"),
-                cpu_baseline=dict(value=res["gcups"], unit=UNIT, cores=res["cores"], kind="port", sample=res["sample"]),
+                data="synthetic", impl="reference", config=bench_config(args.gpus, args.scale),
+                cpu_baseline=dict(value=res["gcups"], unit=UNIT, cores=res["cores"], kind="port", sample=res["sample"],
+                                  note="oracle port of the reference's CPU path (64-bit Myers, OpenMP over pairs); the Rust reference + "
+                                       "minimap2 cannot be built here.  Each step times the bounded sample and reports its rate",
+                                  extrapolated_full_step_s=cells_total / (res["gcups"] * 1e9)),
                 e2e=dict(value=res["gcups"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     _emit(line)
 
 
-def workload_name(n):
-    return f"hla_wgs30x: {READS_PER_GPU * n} reads x 12,451 DNA + 19,629 cDNA alleles (BASELINE configs[1]" + (")" if n == 1 else f", reads x{n}, alleles sharded {n} ways)")
-
-
 # ---------------------------------------------------------------------------------------------
-# cohort leg (BASELINE configs[4]): independent samples, one at a time per GPU
+# cohort leg (BASELINE configs[4]): independent samples through the C++ host, one at a time per GPU
 # ---------------------------------------------------------------------------------------------
-def run_cohort(ctx, w, n_samples, rank, world):
-    """Each sample = 64 HLA-A + 64 HLA-B reads (DNA + cDNA targets) against the full resident allele sets (K1 x2, K2
-    per gene, per-read best allele read back) + one CYP2D6 case (39-template search over 256 reads, weight_sequence
-    spans for ~650 segments x 24 consensuses, chain windows + pair top-10 over 200 chains).  Samples are independent:
-    ranks work through disjoint samples with no exchange (replicas).  Returns (seconds, samples, cells)."""
-    import pb_starphase_b200 as sp
-    from pb_starphase_b200 import synth
-
-    pack = sp.binding.pack_sequences
-    P_dna, P_cdna = ctx.patterns(w["dna"]), ctx.patterns(w["cdna"])  # the whole database on every rank
-    per_gene = 64
-    genes = list(w["gene_views"].items())
-
-    dbg = os.environ.get("SP_COHORT_DEBUG") == "1"
-    marks = []
-
-    def mark(name):
-        if dbg:
-            ctx.synchronize()
-            marks.append((name, time.perf_counter()))
-
-    def one_sample(sid):
-        cells = 0
-        sel = []
-        marks.clear()
-        mark("start")
-        for _, (_, _, _, col0, nr) in genes:
-            lo = col0 + (sid * per_gene) % max(nr - per_gene, 1)
-            sel += list(range(lo, lo + per_gene))
-        reads = [w["reads"][i] for i in sel]
-        ctg = [w["ctargets"][i] for i in sel]
-        T, Tc = ctx.targets(pack(reads)), ctx.targets(pack(ctg))
-        mark("hla_targets")
-        dd = ctx.score_device(T, P_dna, elem_bits=16)
-        if dbg:
-            marks.append((f"k1dna_kernel={ctx.last_kernel_ms(0):.1f}ms;wall", time.perf_counter()))
-        dc = ctx.score_device(Tc, P_cdna, elem_bits=16)
-        if dbg:
-            marks.append((f"k1cdna_kernel={ctx.last_kernel_ms(0):.1f}ms;wall", time.perf_counter()))
-        cells += sum(map(len, reads)) * P_dna.total_len + sum(map(len, ctg)) * P_cdna.total_len
-        calls = {}
-        for g, (gene, (drow, crow, na, _, _)) in enumerate(genes):
-            vd = ctx.wrap_dmatrix(dd.device_ptr + 2 * (drow * dd.ld + g * per_gene), per_gene, na, dd.ld, 16)
-            vc = ctx.wrap_dmatrix(dc.device_ptr + 2 * (crow * dc.ld + g * per_gene), per_gene, na, dc.ld, 16)
-            calls[gene] = ctx.pair_minsum_topk(vc, 10, d2=vd)
-            vd.close(); vc.close()
-        mark("hla_k1_k2")
-        best_allele = dd.to_host_u16().argmin(axis=1)  # realign_record-style per-read assignment
-        mark("hla_readback")
-        for h in (dd, dc, T, Tc):
-            h.close()
-        c = cyp_inputs[sid]
-        Dt = ctx.score_batch(c["reads"], c["templates"])                      # find_base_type_in_sequence
-        cells += sum(map(len, c["reads"])) * sum(map(len, c["templates"]))
-        mark("cyp_templates")
-        Dw, Sw, Ew = ctx.score_spans(c["consensuses"], c["segments"], max_dist_permille=350)  # weight_sequence (+ overlap spans of the pairs an aligner would report)
-        cells += 2 * sum(map(len, c["consensuses"])) * sum(map(len, c["segments"]))
-        mark("cyp_spans")
-        Wt = np.ascontiguousarray(Dw.T.astype(np.uint32))                       # [segment][consensus]
-        order = np.argsort(c["seg_read"], kind="stable")
-        bounds = np.searchsorted(c["seg_read"][order], np.arange(len(c["reads"]) + 1))
-        Wr = [Wt[order[bounds[r]:bounds[r + 1]]] for r in range(len(c["reads"])) if bounds[r + 1] > bounds[r]]
-        B = ctx.chain_window_scores(c["chains"], Wr, len(c["consensuses"]))
-        calls["CYP2D6"] = ctx.pair_minsum_topk(B, 10)
-        B.close()
-        mark("cyp_chains")
-        if dbg:
-            print("cohort rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
-        return cells, (calls, int(best_allele[0]), int(Dt[0, 0]), int(Sw[0, 0]), int(Ew[0, 0]))
-
-    sids = [rank + world * k for k in range(n_samples)]
-    cyp_inputs = {sid: synth.cyp2d6_sample(1000 + sid) for sid in sids}  # host-side inputs exist before the clock starts
-    for k in range(3):  # warm-up: first-use allocations, module loading, and (N > 1) the other ranks' start-up traffic on the box
-        one_sample(sids[k % len(sids)])
-    ctx.synchronize()
-    t0 = time.perf_counter()
-    cells = 0
-    for sid in sids:
-        c, _ = one_sample(sid)
-        cells += c
-    ctx.synchronize()
-    dt = time.perf_counter() - t0
-    P_dna.close(); P_cdna.close()
-    return dt, n_samples, cells
-
-
-def run_cohort_host(w, n_samples, rank, world, local_rank):
-    """The same cohort through the C++ host above the C ABI (pb_starphase_b200/host): per sample the complete calls a
-    pb-StarPhase run makes on this path -- HLA-A and HLA-B diplotypes (K1 DNA + cDNA against the resident allele sets, K2 pair
-    ranking, het/hom decision, per-read database assignment via K5 + K4), CYP2D6 (39-template search over the reads with K4
-    tracebacks, weight_sequence spans, chains, find_best_chain_pair) -- ending in the result JSON text of that sample.
-    Returns (seconds, samples, bytes of JSON, one sample's diplotypes)."""
+def run_cohort(w, n_samples, rank, world, local_rank):
+    """Per sample the complete calls a pb-StarPhase run makes on this path, through the C++ host above the C ABI
+    (pb_starphase_b200/host): HLA-A and HLA-B diplotypes (64 reads per gene, DNA + cDNA, against that gene's resident allele
+    set: K1 x2, K2 pair ranking, het/hom decision, per-read database assignment via K5 + K4), CYP2D6 (39-template search over
+    96 reads with K4 tracebacks, weight_sequence spans, chains, find_best_chain_pair) -- ending in the result JSON text of
+    that sample.  Samples are independent: ranks work through disjoint samples with no exchange (replicas).
+    Returns (seconds, samples, bytes of JSON, info)."""
     from pb_starphase_b200 import _starphase_host as host
     from pb_starphase_b200 import synth
 
@@ -304,7 +237,6 @@ def run_cohort_host(w, n_samples, rank, world, local_rank):
     index = {gene: host.HlaGeneIndex(gpu, [r for r in rows if r[1] == gene], gene, settings) for gene, _ in genes}
     per_gene = 64
     meta = dict(pbstarphase_version="2.0.1", cpic_version="synthetic", hla_version="synthetic", pharmvar_version="synthetic", build_time="n/a")
-
     dbg = os.environ.get("SP_COHORT_DEBUG") == "1"
 
     def one_sample(sid, cyp):
@@ -322,7 +254,7 @@ def run_cohort_host(w, n_samples, rank, world, local_rank):
         text = host.starphase_json("2.0.1", meta, details)
         marks.append(("json", time.perf_counter()))
         if dbg:
-            print("cohort_host rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+            print("cohort rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
         return text, sum(len(h) for h in hits)
 
     def cyp_inputs(sid):
@@ -332,7 +264,7 @@ def run_cohort_host(w, n_samples, rank, world, local_rank):
                     roi={q: [(a, b, seq.decode()) for a, b, seq in regs] for q, regs in c["roi"].items()})
 
     sids = [rank + world * k for k in range(n_samples)]
-    inputs = {sid: cyp_inputs(sid) for sid in sids}
+    inputs = {sid: cyp_inputs(sid) for sid in sids}  # host-side inputs exist before the clock starts
     for k in range(2):
         one_sample(sids[k % len(sids)], inputs[sids[k % len(sids)]])
     t0 = time.perf_counter()
@@ -343,7 +275,7 @@ def run_cohort_host(w, n_samples, rank, world, local_rank):
     dt = time.perf_counter() - t0
     doc = json.loads(text)
     calls = {g: d["diplotypes"][0]["diplotype"] for g, d in doc["gene_details"].items()}
-    return dt, n_samples, nbytes, dict(calls=calls, cyp2d6_template_hits=n_hits, kernel_launches=int(gpu.launch_count()))
+    return dt, n_samples, nbytes, dict(last_sample_calls=calls, cyp2d6_template_hits=n_hits, kernel_launches=int(gpu.launch_count()))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -354,7 +286,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import pb_starphase_b200 as sp
-    from pb_starphase_b200.sharding import all_gather_topk, broadcast_bytes, shard_range, triangle_rows
+    from pb_starphase_b200 import binding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -368,76 +300,75 @@ def run_ours(args):
     n = max(args.gpus, world)
     w = build_workload(n, args.scale)
 
-    # one explicit stream for everything: the library's kernels, torch's fills/events and the NCCL hand-offs.
+    # one explicit stream for everything: the library's kernels and collectives, torch's fills and events.
     # (The legacy default stream has handle 0 == NULL, which sp_ctx_create reads as "make a private stream".)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = sp.Context(local_rank, stream=stream.cuda_stream)
     assert stream.cuda_stream != 0
+    # the library's own communicator: rank 0 draws the id, torch.distributed only carries the 128 bytes
+    uid = [binding.comm_unique_id() if rank == 0 and world > 1 else bytes(128)]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0, device=dev)
+    comm = sp.Comm(ctx, uid[0], rank, world)
     int_peak = ctx.int_peak(0)       # ALU pipe alone (LOP3)
     int_peak2 = ctx.int_peak(2)      # ALU + FMA pipes (LOP3 + IMAD alternating)
 
     # ---- resident database: this rank's allele shards (prepared once, like HlaRealigner::new) ----
-    d_lo, d_hi, d_S = shard_range(len(w["dna"]), rank, world)
-    c_lo, c_hi, c_S = shard_range(len(w["cdna"]), rank, world)
-    P_dna = ctx.patterns(w["dna"][d_lo:d_hi])
-    P_cdna = ctx.patterns(w["cdna"][c_lo:c_hi])
-    R = len(w["reads"])
-    ld = (R + 63) // 64 * 64
-    cells_local = (sum(map(len, w["dna"][d_lo:d_hi])) * sum(map(len, w["reads"]))
-                   + sum(map(len, w["cdna"][c_lo:c_hi])) * sum(map(len, w["ctargets"])))
-    cells_dna_local = sum(map(len, w["dna"][d_lo:d_hi])) * sum(map(len, w["reads"]))
-    cells_total = w["cells_dna"] + w["cells_cdna"]
+    n_dna, n_cdna = len(w["dna"]), len(w["cdna"])
+    idx_d = binding.shard_plan([len(a) for a in w["dna"]], world, rank)
+    idx_c = binding.shard_plan([len(a) for a in w["cdna"]], world, rank)
+    P_dna = ctx.patterns([w["dna"][i] for i in idx_d])
+    P_cdna = ctx.patterns([w["cdna"][i] for i in idx_c])
+    sum_dna, sum_cdna = sum(map(len, w["dna"])), sum(map(len, w["cdna"]))
+    sum_dna_local = sum(len(w["dna"][i]) for i in idx_d)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # the read set is generated on rank 0 and broadcast (it is identical by construction; this is the real exchange)
     def pinned(arr):
         out = ctx.pinned_empty(arr.shape, arr.dtype)
         out[...] = arr
         return out
 
-    reads_pack = tuple(pinned(broadcast_bytes(a, 0, dev)) for a in sp.binding.pack_sequences(w["reads"]))
-    ct_pack = tuple(pinned(broadcast_bytes(a, 0, dev)) for a in sp.binding.pack_sequences(w["ctargets"]))
-
-    # gather buffers: [world * S][ld] u16, this rank scores straight into its slot
-    full_dna = torch.zeros((world * d_S, ld), dtype=torch.int16, device=dev)
-    full_cdna = torch.zeros((world * c_S, ld), dtype=torch.int16, device=dev)
-    gat_dna, gat_cdna = full_dna.view(torch.uint8), full_cdna.view(torch.uint8)
-    M_dna = ctx.wrap_dmatrix(full_dna.data_ptr(), R, world * d_S, ld, 16)
-    M_cdna = ctx.wrap_dmatrix(full_cdna.data_ptr(), R, world * c_S, ld, 16)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    views = {}
-    for gene, (drow, crow, na, col0, nr) in w["gene_views"].items():
-        vd = ctx.wrap_dmatrix(full_dna.data_ptr() + 2 * (drow * ld + col0), nr, na, ld, 16)
-        vc = ctx.wrap_dmatrix(full_cdna.data_ptr() + 2 * (crow * ld + col0), nr, na, ld, 16)
-        views[gene] = (vc, vd, triangle_rows(na, rank, world))
-
     k1_ms = []
 
-    def device_step(T_dna, T_cdna):
-        ctx.score_into(T_dna, P_dna, M_dna, rank * d_S)
-        k1_ms.append(ctx.last_kernel_ms(0))
-        ctx.score_into(T_cdna, P_cdna, M_cdna, rank * c_S)
-        if world > 1:
-            # NCCL has no int16: the shards travel as bytes
-            dist.all_gather_into_tensor(gat_dna, gat_dna[rank * d_S:(rank + 1) * d_S])
-            dist.all_gather_into_tensor(gat_cdna, gat_cdna[rank * c_S:(rank + 1) * c_S])
+    def gene_views(Dd, Dc, gv):
+        """K2 inputs per gene: blocks of the gathered matrices (database order: one gene's alleles are consecutive rows)."""
         out = {}
-        for gene, (vc, vd, (lo, hi)) in views.items():
-            recs = ctx.pair_minsum_topk(vc, TOPK, lo, hi, d2=vd)
-            out[gene] = all_gather_topk(recs, TOPK, dev) if world > 1 else recs
+        for gene, (drow, crow, na, col0, nr) in gv.items():
+            vd = ctx.wrap_dmatrix(Dd.device_ptr + 2 * (drow * Dd.ld + col0), nr, na, Dd.ld, 16)
+            vc = ctx.wrap_dmatrix(Dc.device_ptr + 2 * (crow * Dc.ld + col0), nr, na, Dc.ld, 16)
+            out[gene] = (vc, vd)
+        return out
+
+    def device_step(T_dna, T_cdna, gv, keep=False):
+        Dd = comm.score_allgather(T_dna, P_dna, idx_d, n_dna, 16)      # K1 on this rank's shard + ncclAllGather + row permutation
+        k1_ms.append(ctx.last_kernel_ms(0))
+        Dc = comm.score_allgather(T_cdna, P_cdna, idx_c, n_cdna, 16)
+        out = {}
+        views = gene_views(Dd, Dc, gv)
+        for gene, (vc, vd) in views.items():
+            out[gene] = comm.pair_minsum_topk(vc, TOPK, d2=vd)         # K2 on this rank's row block + record all-gather + merge
+            vc.close(); vd.close()
+        if keep:
+            return out, Dd, Dc
+        Dd.close(); Dc.close()
         return out
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
-    # ---- `value`: inputs resident in HBM ----
-    T_dna, T_cdna = ctx.targets(reads_pack), ctx.targets(ct_pack)
+    # ---- `value`: inputs resident in HBM.  The read set lives on rank 0 and is broadcast (the path's real exchange) ----
+    reads_pack = tuple(pinned(a) for a in sp.binding.pack_sequences(w["reads"])) if rank == 0 else None
+    ct_pack = tuple(pinned(a) for a in sp.binding.pack_sequences(w["ctargets"])) if rank == 0 else None
+    T_dna, T_cdna = comm.bcast_targets(reads_pack, 0), comm.bcast_targets(ct_pack, 0)
+    cells_dna, cells_cdna = sum_dna * T_dna.total_len, sum_cdna * T_cdna.total_len
+    cells_total = cells_dna + cells_cdna
+    cells_dna_local = sum_dna_local * T_dna.total_len
+    gv = w["gene_views"]
     result = None
     for _ in range(args.warmup):
-        result = device_step(T_dna, T_cdna)
+        result = device_step(T_dna, T_cdna, gv)
     k1_ms.clear()
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
@@ -447,7 +378,7 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (256 MB > 126 MB L2)
-        result = device_step(T_dna, T_cdna)
+        result = device_step(T_dna, T_cdna, gv)
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -456,16 +387,20 @@ def run_ours(args):
     k1_avg_ms = float(np.mean(k1_ms))
 
     # ---- `e2e`: pinned host buffers in, host results out, through the C-ABI calls a host program makes ----
-    host_dd = ctx.pinned_empty((R, d_hi - d_lo), np.uint16)
-    host_dc = ctx.pinned_empty((R, c_hi - c_lo), np.uint16)
+    lo_d, hi_d = rank * n_dna // world, (rank + 1) * n_dna // world      # this rank hands back its block of rows: the whole
+    lo_c, hi_c = rank * n_cdna // world, (rank + 1) * n_cdna // world    # matrix reaches host memory once per step
+    R = T_dna.n
+    host_dd = ctx.pinned_empty((R, hi_d - lo_d), np.uint16)
+    host_dc = ctx.pinned_empty((R, hi_c - lo_c), np.uint16)
 
     def e2e_step():
-        Td, Tc = ctx.targets(reads_pack), ctx.targets(ct_pack)  # H2D of the read set + pack
-        res = device_step(Td, Tc)
-        own_d = ctx.wrap_dmatrix(full_dna.data_ptr() + 2 * rank * d_S * ld, R, d_hi - d_lo, ld, 16)
-        own_c = ctx.wrap_dmatrix(full_cdna.data_ptr() + 2 * rank * c_S * ld, R, c_hi - c_lo, ld, 16)
-        own_d.to_host_u16(host_dd); own_c.to_host_u16(host_dc)  # D2H of this rank's distance matrices [read][allele]
-        own_d.close(); own_c.close(); Td.close(); Tc.close()
+        Td, Tc = comm.bcast_targets(reads_pack, 0), comm.bcast_targets(ct_pack, 0)  # H2D of the read set on rank 0 + broadcast
+        res, Dd, Dc = device_step(Td, Tc, gv, keep=True)
+        own_d = ctx.wrap_dmatrix(Dd.device_ptr + 2 * lo_d * Dd.ld, R, hi_d - lo_d, Dd.ld, 16)
+        own_c = ctx.wrap_dmatrix(Dc.device_ptr + 2 * lo_c * Dc.ld, R, hi_c - lo_c, Dc.ld, 16)
+        own_d.to_host_u16(host_dd); own_c.to_host_u16(host_dc)  # D2H of the distance matrices [read][allele]
+        for h in (own_d, own_c, Dd, Dc, Td, Tc):
+            h.close()
         return res, host_dd.nbytes + host_dc.nbytes
 
     e2e_step()
@@ -477,94 +412,135 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     assert res_e2e == result, "e2e and device-resident runs disagree"
+    h2d = int(sum(a.nbytes for a in reads_pack) + sum(a.nbytes for a in ct_pack)) if rank == 0 else 0
+    T_dna.close(); T_cdna.close()
 
-    cohort_s, cohort_n, cohort_cells = 0.0, 0, 0
-    if args.cohort_samples > 0:
+    # ---- panel leg: BASELINE configs[2], a FIXED read set, alleles sharded N ways (strong scaling) ----
+    panel = None
+    if args.panel_reads > 0:
+        pr = args.panel_reads
+        if rank == 0:
+            # reads of the same two genes against the SAME database as the main leg (drawn from its alleles)
+            rng = np.random.default_rng([synth.DEFAULT_SEED, 40960])
+            p_reads, p_ct = [], []
+            for gi, gene in enumerate(("HLA-A", "HLA-B")):
+                drow, crow, na, _, _ = gv[gene]
+                nr = pr // 2 if gi == 0 else pr - pr // 2
+                rd, src = synth.hifi_reads(rng, w["dna"][drow:drow + na], nr)
+                p_reads += rd
+                p_ct += [synth.hifi_reads(rng, [w["cdna"][crow + int(s)]], 1, flank=50, lo=0, hi=1400)[0][0] for s in src]
+            pp_r, pp_c = sp.binding.pack_sequences(p_reads), sp.binding.pack_sequences(p_ct)
+        else:
+            pp_r = pp_c = None
+        Tp, Tpc = comm.bcast_targets(pp_r, 0), comm.bcast_targets(pp_c, 0)
+        pgv = {"HLA-A": (gv["HLA-A"][0], gv["HLA-A"][1], gv["HLA-A"][2], 0, pr // 2),
+               "HLA-B": (gv["HLA-B"][0], gv["HLA-B"][1], gv["HLA-B"][2], pr // 2, pr - pr // 2)}
+        p_cells = sum_dna * Tp.total_len + sum_cdna * Tpc.total_len
+        k1_keep = list(k1_ms)
         barrier()
-        cohort_s, cohort_n, cohort_cells = run_cohort(ctx, w, args.cohort_samples, rank, world)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record(stream)
+        for _ in range(args.panel_steps):
+            flush.fill_(1)
+            p_res = device_step(Tp, Tpc, pgv)
+        pe1.record(stream)
         barrier()
+        p_ms = pe0.elapsed_time(pe1)
+        p_k1 = float(np.mean(k1_ms[len(k1_keep):]))
+        del k1_ms[len(k1_keep):]
+        panel = dict(ms=p_ms, cells=p_cells, k1_ms=p_k1, best_pairs={g: (r[0][:4] if r else None) for g, r in p_res.items()},
+                     launches=0)
+        Tp.close(); Tpc.close()
 
+    # ---- cohort leg ----
     host_s, host_n, host_bytes, host_info = 0.0, 0, 0, None
     if args.cohort_samples > 0:
         barrier()
         try:
-            host_s, host_n, host_bytes, host_info = run_cohort_host(w, max(2, args.cohort_samples // 2), rank, world, local_rank)
+            host_s, host_n, host_bytes, host_info = run_cohort(w, args.cohort_samples, rank, world, local_rank)
         except Exception as e:  # the contract line must not depend on this leg
             host_info = dict(error=f"{type(e).__name__}: {e}")
         barrier()
 
-    # max over ranks
+    # max over ranks of every time, sums of the counts
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s, k1_avg_ms, cohort_s, host_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, e2e_s, k1_avg_ms, host_s, panel["ms"] if panel else 0.0, panel["k1_ms"] if panel else 0.0],
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, k1_avg_ms, cohort_s, host_s = (float(x) for x in t.cpu())
-        hn = torch.tensor([host_n], dtype=torch.int64, device=dev)
-        dist.all_reduce(hn)
-        host_n = int(hn.item())
-        ct = torch.tensor([cohort_n, cohort_cells], dtype=torch.int64, device=dev)
-        dist.all_reduce(ct)
-        cohort_n, cohort_cells = (int(x) for x in ct.cpu())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+        ms_total, e2e_s, k1_avg_ms, host_s, p_ms_max, p_k1_max = (float(x) for x in t.cpu())
+        if panel:
+            panel["ms"], panel["k1_ms"] = p_ms_max, p_k1_max
+        cnt = torch.tensor([host_n, launches, h2d, d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        host_n, launches, h2d, d2h = (int(x) for x in cnt.cpu())
 
     if rank == 0:
         value = cells_total * args.steps / (ms_total * 1e-3) / 1e9
         e2e_val = cells_total * args.steps / e2e_s / 1e9
         achieved = INT_OPS_PER_CELL * cells_dna_local / (k1_avg_ms * 1e-3)
-        hbm_bytes = (sum(map(len, w["reads"])) + P_dna.padded_rows * 0.75 + 2.0 * (d_hi - d_lo) * R)
-        peaks = {}
+        hbm_bytes = (T_dna.total_len + P_dna.padded_rows * 0.75 + 2.0 * len(idx_d) * R)
+        peaks, traffic = {}, {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of the K1 DNA launches of one step, from a committed ncu capture
+            traffic = json.loads((ROOT / "profiles" / "k1_dram_traffic.json").read_text())
+        except Exception:
+            pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         cpu = cpu_sample(w, args.cpu_seconds) if world == 1 else None  # the CPU baseline is an N=1 figure
+        cohort = None
+        if host_n and host_s > 0:
+            cohort = dict(samples_per_s=host_n / host_s, samples=host_n, ms_per_sample_per_gpu=host_s / (host_n / world) * 1e3,
+                          json_bytes_per_sample=host_bytes // max(host_n // world, 1), **host_info,
+                          scaling="replicas: independent samples round-robin over ranks, no exchange (%d per GPU; 1,000 at 8 GPUs)" % (host_n // world),
+                          sample="per sample, through the C++ host above the C ABI: HLA-A + HLA-B diplotype calls (64 reads per gene, DNA + cDNA, "
+                                 "against that gene's full allele set: K1 x2, K2, het/hom, K5 + K4 read assignment), CYP2D6 39-template search with "
+                                 "K4 tracebacks + weight_sequence + chains + find_best_chain_pair on a diploid 96-read case, result JSON text out "
+                                 "(BASELINE configs[4], SURVEY 8d.5)")
+        elif host_info:
+            cohort = host_info
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="u32", data="synthetic",
-            config=dict(workload=workload_name(world), seed=20251106, l2="flushed between timed steps (256 MB write)",
-                        step="K1 DNA + K1 cDNA + K2 (cDNA,DNA) pair top-%d per gene" % TOPK,
-                        scale=args.scale, best_pairs={g: (r[0][:4] if r else None) for g, r in result.items()}),
+            config=bench_config(world, args.scale),
+            best_pairs={g: (r[0][:4] if r else None) for g, r in result.items()},
             clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"]),
-            e2e=dict(value=e2e_val, unit=UNIT,
-                     h2d_bytes_per_step=int(sum(a.nbytes for a in reads_pack) + sum(a.nbytes for a in ct_pack)),
-                     d2h_bytes_per_step=int(d2h),
-                     note="per step: sp_targets_create x2 from pinned host sequences, K1 x2, K2 per gene, u16 distance matrices "
-                          "[reads x alleles] + top-k records back to pinned host memory"),
+            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                     note="per step: read set from pinned host memory on rank 0 (sp_comm_bcast_targets x2), K1 x2 + all-gather, K2 per gene + "
+                          "merge, u16 distance matrices [reads x alleles] (each rank its row block) + top-k records back to pinned host memory"),
             gpu_launches=int(launches),
-            cohort=(dict(samples_per_s=cohort_n / cohort_s, samples=cohort_n, ms_per_sample_per_gpu=cohort_s / (cohort_n / world) * 1e3,
-                         gcups=cohort_cells / cohort_s / 1e9, scaling="replicas: independent samples round-robin over ranks, no exchange",
-                         sample="64 HLA-A + 64 HLA-B reads (DNA + cDNA) x full allele sets (K1, K2 top-10 per gene, per-read best allele) + "
-                                "CYP2D6: 256 reads x 39 templates, ~650 segments x 24 consensuses with spans, 200 chains (chain windows + pair "
-                                "top-10); host buffers in, calls out (BASELINE configs[4], SURVEY 8d.5)")
-                    if cohort_n else None),
-            cohort_host=(dict(samples_per_s=host_n / host_s, samples=host_n, ms_per_sample_per_gpu=host_s / (host_n / world) * 1e3,
-                              json_bytes_per_sample=host_bytes // max(host_n // world, 1), **host_info,
-                              sample="the same per-sample work through the C++ host (pb_starphase_b200/host): HLA-A + HLA-B diplotype calls "
-                                     "(K1 x2, K2, het/hom, K5 + K4 read assignment), CYP2D6 39-template search with K4 tracebacks + "
-                                     "weight_sequence + chains + find_best_chain_pair on a diploid 96-read case, result JSON text out")
-                         if host_n and host_s > 0 else host_info),
+            multi_gpu="sp_comm_* (NCCL inside libstarphase_gpu.so): bcast_targets, score_allgather, pair_minsum_topk" if world > 1 else None,
+            samples_per_s=(cohort or {}).get("samples_per_s"),
+            cohort=cohort,
+            panel=(dict(gcups=panel["cells"] * args.panel_steps / (panel["ms"] * 1e-3) / 1e9, ms_per_step=panel["ms"] / args.panel_steps,
+                        steps=args.panel_steps, scaling="strong", reads=args.panel_reads, cells_per_step=panel["cells"],
+                        k1_dna_ms=panel["k1_ms"], best_pairs=panel["best_pairs"],
+                        workload="panel_1000x: %d reads (fixed) x 12,451 DNA + 19,629 cDNA alleles, alleles sharded %d ways "
+                                 "(BASELINE configs[2]); same step as the main leg" % (args.panel_reads, world))
+                   if panel else None),
             roofline=dict(bound="int_alu", kernel="k1_infix (DNA launches, all lane-width classes)", achieved=achieved / 1e12,
                           peak=int_peak2 / 1e12, unit="Tops/s (algorithmic INT32 lane-ops, 23/64 per cell, SURVEY 8d)",
                           frac=achieved / int_peak2,
-                          peak_source="measured live: dependent-free LOP3+IMAD loop = ALU and FMA pipes together (sp_int_peak kind 2)",
+                          peak_source="measured live: dependent-free LOP3+IMAD loop = ALU and FMA pipes together (sp_int_peak kind 2); "
+                                      "MEASURED_PEAKS.json holds no integer peak",
                           peak_alu_pipe_only=int_peak / 1e12, frac_alu_pipe_only=achieved / int_peak,
-                          note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one, ~92 % busy in ncu) and 6 "
+                          peak_theoretical=148 * 128 * 1.965e9 / 1e12,
+                          note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one) and 6 "
                                "as IMAD on the FMA pipe, so the algorithmic count can exceed the ALU-pipe-only peak (DESIGN.md 4.1)",
                           k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12,
-                          # dram__bytes_read.sum + dram__bytes_write.sum of the DNA launches of one step (ncu, B200, this workload at N = 1,
-                          # scale 1.0: profiles/r01e_k1_traffic.csv, mean of 3 steps; lts__t_bytes.sum = 12.9 GB: the per-item blob / text
-                          # re-reads are served by L2); not measured for other shapes
-                          traffic=(K1_DNA_DRAM_BYTES_PER_STEP if world == 1 and args.scale == 1.0 else None),
-                          traffic_unit="bytes per step (both DNA launches), algorithmic bytes = %d" % hbm_bytes,
+                          traffic=(traffic.get("bytes_per_step") if world == 1 and args.scale == 1.0 else None),
+                          traffic_source=traffic.get("source") if traffic else None,
+                          traffic_unit="bytes per step (all K1 DNA launches), algorithmic bytes = %d" % hbm_bytes,
                           hbm=dict(achieved=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
                                    frac=hbm_bytes / (k1_avg_ms * 1e-3) / 1e9 / hbm_peak,
                                    peak_source="MEASURED_PEAKS.json" if peaks else "fallback")),
             cpu_baseline=(dict(value=cpu["gcups"], unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"]) if cpu else None),
         )
         _emit(line)
+    comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
