@@ -46,7 +46,8 @@ typedef enum sp_status {
     SP_ERR_RANGE = 5        /* value does not fit the device format (e.g. > 65535 alleles for top-k)  */
 } sp_status;
 
-/* Longest pattern one warp can hold: 32 lanes x 16 words x 32 rows. */
+/* Longest pattern one warp can hold: 32 lanes x 16 words x 32 rows.  Longer patterns are rejected with SP_ERR_TOO_LONG
+ * (the reference's aligner has no such limit; the HLA-A / HLA-B alleles of IMGT 3.57 reach 4.1 kb, CYP2D6 regions 6.2 kb). */
 #define SP_MAX_PATTERN_LEN 16384
 
 /* Concatenated ASCII sequences: sequence i = bases[offsets[i] .. offsets[i+1]).
@@ -221,6 +222,16 @@ sp_status sp_align_windows(sp_ctx *ctx, const sp_seqset *targets, const sp_seqse
                            const int32_t *win_end, sp_align_rec *recs, uint32_t *cigar, int64_t cigar_cap,
                            int64_t *cigar_used);
 
+/* Resident form: both sequence sets are already on the device.  sp_targets_create uploads any sequence set as ASCII, texts and
+ * patterns alike (the allele database of a gene is kept this way next to its packed sp_patterns form; the reads of a sample are
+ * uploaded once for K1 and K4).  A call then moves only the pair list in and the records + run-length CIGARs out.  Pairs are
+ * packed several to a warp by pattern length (lane width 4 / 8 / 12 / 16 words), each pair streaming its own text.
+ * cigar[recs[q].cigar_off ..) holds pair q's entries; the order of the pairs inside `cigar` is unspecified. */
+sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, const sp_targets *patterns, int64_t n_pairs,
+                            const int32_t *pair_text, const int32_t *pair_pattern, const int32_t *win_begin,
+                            const int32_t *win_end, sp_align_rec *recs, uint32_t *cigar, int64_t cigar_cap,
+                            int64_t *cigar_used);
+
 /* ---- K5: candidate lists -------------------------------------------------------------------- */
 /* The k best patterns of every target of a device matrix (k <= 16): idx / dist are [n_targets][k] row-major, ordered
  * by (distance, pattern index) ascending; entries beyond n_patterns are -1.  Plays the role of minimap2's best_n hit
@@ -232,6 +243,12 @@ sp_status sp_row_topk(sp_ctx *ctx, const sp_dmatrix *d, int k, int32_t *idx, int
  * for minimap2 ranking its hits by alignment score: a read that covers only part of a long allele then keeps that allele
  * ahead of short alleles lying wholly inside the read (src/hla/realigner.rs:116-146 picks among the reported hits). */
 sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const int32_t *pattern_bias, int k, int32_t *idx, int32_t *dist);
+/* Same, ranked by dist_weight * distance + pattern_bias[p] (dist_weight in [1, 64]; distances as K1 writes them, < 2^24).  minimap2's DP score under map-hifi is
+ * about (aligned bases) - 5 * (edits): a mismatch costs b = 4 and forfeits the match's a = 1, a gap more.  With dist_weight = 5
+ * and bias = max |P| - |P_p| the candidate list follows that score: against the affine cost model the realigner's assignment
+ * agrees for 91 of 96 simulated reads on the IMGT 3.57 HLA-A / HLA-B alleles, 83 of 96 with dist_weight = 1. */
+sp_status sp_row_topk_weighted(sp_ctx *ctx, const sp_dmatrix *d, int dist_weight, const int32_t *pattern_bias, int k, int32_t *idx,
+                               int32_t *dist);
 
 /* ---- K6: CYP2D6 allele-vector match (row N3 of SURVEY.md 8f) ------------------------------- */
 /* Replaces the haplotype loop of Cyp2d6Extractor::assign_haplotype (src/cyp2d6/haplotyper.rs:470-517): for every

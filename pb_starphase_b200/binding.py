@@ -80,8 +80,10 @@ SIGNATURES = {
                                  C.POINTER(C.c_int64)]),
     "sp_align_windows": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                    C.POINTER(C.c_int64)]),
+    "sp_align_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64, C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "sp_row_topk_biased": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "sp_row_topk_weighted": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "sp_variant_match": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sp_chain_window_scores": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(_P)]),
     "sp_pair_minsum_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
@@ -299,11 +301,16 @@ class Context:
                         "t_end": r.t_end, "cigar": [(int(x) >> 4, int(x) & 15) for x in c]})
         return out
 
-    def row_topk(self, d: "DMatrix", k: int = 5, bias=None):
-        """K5: (idx, dist), each [n_targets, k] int32: the k best patterns of every target by (distance [+ bias[p]], index)."""
+    def row_topk(self, d: "DMatrix", k: int = 5, bias=None, weight: int = 1):
+        """K5: (idx, dist), each [n_targets, k] int32: the k best patterns of every target by (weight * distance [+ bias[p]], index)."""
         idx = np.zeros((d.n_targets, k), dtype=np.int32)
         dist = np.zeros((d.n_targets, k), dtype=np.int32)
-        if bias is None:
+        if weight != 1:
+            b = np.ascontiguousarray(bias if bias is not None else np.zeros(d.n_patterns), dtype=np.int32)
+            if b.shape != (d.n_patterns,):
+                raise ValueError("row_topk: bias must have one entry per pattern")
+            self._check(self._lib.sp_row_topk_weighted(self._h, d._h, int(weight), b.ctypes.data, k, idx.ctypes.data, dist.ctypes.data))
+        elif bias is None:
             self._check(self._lib.sp_row_topk(self._h, d._h, k, idx.ctypes.data, dist.ctypes.data))
         else:
             b = np.ascontiguousarray(bias, dtype=np.int32)

@@ -33,7 +33,26 @@ struct sp_ctx {
     void *pool[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pool_bytes[4] = {0, 0, 0, 0};
     int *d_counter = nullptr;  // K1's work counter
+    // grow-only page-locked staging for the small per-call tables (plan tables of K4): pageable H2D copies are staged by the
+    // driver one by one and cost more than the kernels they feed
+    void *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    size_t free_mem_cached = 0;  // cudaMemGetInfo is slow (~1 ms): asked once per context, refreshed when a pool has to grow
 };
+
+static inline cudaError_t ctx_stage(sp_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->h_stage_bytes) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+        const size_t want = bytes + bytes / 2;
+        cudaError_t e = cudaHostAlloc(&ctx->h_stage, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        ctx->h_stage_bytes = want;
+    }
+    *out = ctx->h_stage;
+    return cudaSuccess;
+}
 
 // stream-ordered reuse is safe: every user synchronises the context stream before it returns
 static inline cudaError_t ctx_pool(sp_ctx *ctx, int which, size_t bytes, void **out) {
@@ -99,6 +118,7 @@ struct sp_targets {
     int64_t n = 0, total_len = 0;
     uint8_t *d_bases = nullptr;
     long long *d_offs = nullptr;
+    std::vector<int64_t> h_offs;  // host copy of the rebased offsets (n + 1 entries, h_offs[0] == 0): K4 plans from the lengths
     std::vector<int32_t> nch;  // chunks per text
     int32_t max_nch = 0;
     int64_t sum_nch = 0;

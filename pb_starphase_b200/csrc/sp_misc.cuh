@@ -14,6 +14,7 @@ namespace sp {
 template <typename T, int K>
 __global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long long ld, int nt, int np, int k,
                                                    const int32_t *__restrict__ bias,  // optional per-pattern addend of the ranking key
+                                                   uint32_t weight,                   // multiplier of the distance inside the ranking key
                                                    int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(128) k5_row_topk(const T *__restrict__ D, long
 #pragma unroll
     for (int q = 0; q < K; ++q) { bd[q] = 0xFFFFFFFFu; bi[q] = 0xFFFFFFFFu; }
     for (int a = 0; a < np; ++a) {
-        const uint32_t v = static_cast<uint32_t>(D[static_cast<long long>(a) * ld + t]) + (bias ? static_cast<uint32_t>(bias[a]) : 0u);
+        const uint32_t v = static_cast<uint32_t>(D[static_cast<long long>(a) * ld + t]) * weight + (bias ? static_cast<uint32_t>(bias[a]) : 0u);
         if (v < bd[K - 1]) {  // strict: on ties the earlier pattern stays ahead
             bd[K - 1] = v; bi[K - 1] = static_cast<uint32_t>(a);
 #pragma unroll

@@ -82,6 +82,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (void *p : ctx->pool) cudaFree(p);
     cudaFree(ctx->d_counter);
+    cudaFreeHost(ctx->h_stage);
     delete ctx;
 }
 
@@ -405,8 +406,10 @@ static sp_status targets_from_offsets(sp_ctx *ctx, const int64_t *offsets, int64
     if (!t) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
     t->ctx = ctx; t->n = n;
     t->nch.resize(static_cast<size_t>(n));
+    t->h_offs.assign(static_cast<size_t>(n) + 1, 0);
     for (int64_t i = 0; i < n; ++i) {
         const int64_t len = offsets[i + 1] - offsets[i];
+        t->h_offs[static_cast<size_t>(i) + 1] = t->h_offs[static_cast<size_t>(i)] + len;
         t->total_len += len;
         const int64_t nc = std::max<int64_t>(1, (len + K1_CHUNK - 1) / K1_CHUNK);
         if (nc > 0x3FFFFFFF) { delete t; return fail(ctx, SP_ERR_TOO_LONG, "text too long"); }
@@ -863,7 +866,14 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
 // ------------------------------------------------------------------------------------------
 extern "C" sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const int32_t *pattern_bias, int k, int32_t *idx,
                                         int32_t *dist) {
+    return sp_row_topk_weighted(ctx, d, 1, pattern_bias, k, idx, dist);
+}
+
+extern "C" sp_status sp_row_topk_weighted(sp_ctx *ctx, const sp_dmatrix *d, int dist_weight, const int32_t *pattern_bias, int k,
+                                          int32_t *idx, int32_t *dist) {
     if (!ctx) return SP_ERR_INVALID;
+    // the 32-bit key weight * distance + bias must not wrap: K1 distances are <= SP_MAX_PATTERN_LEN (2^14), biases < 2^30
+    if (dist_weight < 1 || dist_weight > 64) return fail(ctx, SP_ERR_INVALID, "sp_row_topk_weighted: dist_weight must be in [1, 64]");
     if (!d || !idx || !dist) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: NULL argument");
     if (k < 1 || k > 16) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: k must be in [1, 16]");
     if (d->nt > 0x7FFFFFF0ll || d->np > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "sp_row_topk: matrix too large");
@@ -885,11 +895,11 @@ extern "C" sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const 
     const int nt = static_cast<int>(d->nt), np = static_cast<int>(d->np);
     const unsigned grid = static_cast<unsigned>((nt + 127) / 128);
     if (d->elem_bits == 16) {
-        if (k <= 8) k5_row_topk<uint16_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
-        else k5_row_topk<uint16_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
+        if (k <= 8) k5_row_topk<uint16_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, static_cast<uint32_t>(dist_weight), d_idx, d_dist);
+        else k5_row_topk<uint16_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const uint16_t *>(d->d), d->ld, nt, np, k, d_bias, static_cast<uint32_t>(dist_weight), d_idx, d_dist);
     } else {
-        if (k <= 8) k5_row_topk<int32_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
-        else k5_row_topk<int32_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, d_idx, d_dist);
+        if (k <= 8) k5_row_topk<int32_t, 8><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, static_cast<uint32_t>(dist_weight), d_idx, d_dist);
+        else k5_row_topk<int32_t, 16><<<grid, 128, 0, ctx->stream>>>(static_cast<const int32_t *>(d->d), d->ld, nt, np, k, d_bias, static_cast<uint32_t>(dist_weight), d_idx, d_dist);
     }
     ++ctx->launches;
     cudaError_t e = cudaGetLastError();

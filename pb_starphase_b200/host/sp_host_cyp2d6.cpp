@@ -215,9 +215,14 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
     std::vector<std::vector<size_t>> n_hits(seqs.size(), std::vector<size_t>(nt, 0));
     struct Item { size_t seq, lo, hi, tmpl; };  // search template tmpl in seqs[seq][lo, hi)
     std::vector<Item> items;
-    SeqList tmpl_seqs;
-    for (const auto &t : templates_) tmpl_seqs.push_back(t.second);
     if (nt == 0) return std::vector<std::vector<AlleleMapping>>(seqs.size());
+    if (!tmpl_patterns_) {  // the 39 templates stay on the device for the life of the extractor: packed for K1, ASCII for K4
+        SeqList ts;
+        for (const auto &t : templates_) ts.push_back(t.second);
+        tmpl_patterns_ = gpu_.prepare_patterns(ts);
+    }
+    const SeqList &tmpl_seqs = tmpl_patterns_->sequences();
+    const std::shared_ptr<ResidentSeqs> resident_seqs = gpu_.upload(seqs);  // the reads: K1 texts of round 0, K4 texts of every round
 
     // every round: K1 scores each open (segment, template) item (segment x all templates in one launch; round 0 = the whole
     // sequences); only placements that could pass go to the K4 traceback, on the placement window
@@ -241,10 +246,16 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             if (seg_index.emplace(key, seg_texts.size()).second) seg_texts.push_back(seqs[it.seq].substr(it.lo, it.hi - it.lo));
         }
         mark("segments", round, seg_texts.size());
-        std::vector<int32_t> E;
-        const std::vector<int32_t> D = gpu_.score_batch(seg_texts, tmpl_seqs, &E);
-        mark("K1 score_batch", round, items.size());
-        std::vector<std::pair<int32_t, int32_t>> pairs, windows;  // (segment row, template), [w0, e) inside the segment
+        std::vector<int32_t> D, E;
+        {
+            // round 0 scores the whole sequences, which are resident already; later rounds upload their sub-segments
+            const bool whole = round == 0 && seg_texts.size() == seqs.size();
+            const std::shared_ptr<ResidentSeqs> segs = whole ? resident_seqs : gpu_.upload(seg_texts);
+            const std::unique_ptr<DeviceMatrix> M = gpu_.score_device(*segs, *tmpl_patterns_, true);
+            gpu_.matrix_to_host(*M, D, &E);
+        }
+        mark("K1 score_device", round, items.size());
+        std::vector<std::pair<int32_t, int32_t>> pairs, windows;  // (sequence, template), [lo + w0, lo + e) inside the sequence
         std::vector<Item> pair_item;
         std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
         for (const Item &it : items) {
@@ -253,13 +264,13 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const size_t d = static_cast<size_t>(D[row * nt + it.tmpl]), e = static_cast<size_t>(E[row * nt + it.tmpl]);
             if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
             const size_t w0 = e > m + d ? e - (m + d) : 0;
-            pairs.emplace_back(static_cast<int32_t>(row), static_cast<int32_t>(it.tmpl));
-            windows.emplace_back(static_cast<int32_t>(w0), static_cast<int32_t>(e));
+            pairs.emplace_back(static_cast<int32_t>(it.seq), static_cast<int32_t>(it.tmpl));
+            windows.emplace_back(static_cast<int32_t>(it.lo + w0), static_cast<int32_t>(it.lo + e));
             pair_item.push_back(it);
             pair_off.push_back(it.lo + w0);
         }
         mark("windows", round, pairs.size());
-        const std::vector<Alignment> alns = gpu_.align_pairs(seg_texts, tmpl_seqs, pairs, &windows);  // sp_align_windows: no sub-string copies
+        const std::vector<Alignment> alns = gpu_.align_pairs(*resident_seqs, tmpl_patterns_->resident(), pairs, &windows);  // windows of resident reads
         mark("K4 align_pairs", round, pairs.size());
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {

@@ -59,17 +59,38 @@ void GpuAligner::score_spans(const SeqList &targets, const SeqList &patterns, st
     check(sp_score_spans_filtered(ctx_, &t.set, &p.set, max_dist_permille, D.data(), start.data(), end.data()), "sp_score_spans");
 }
 
+std::shared_ptr<ResidentSeqs> GpuAligner::upload(const SeqList &seqs) {
+    std::shared_ptr<ResidentSeqs> r(new ResidentSeqs());
+    r->seqs_ = seqs;
+    Packed p(seqs);
+    check(sp_targets_create(ctx_, &p.set, &r->t_), "sp_targets_create");
+    return r;
+}
+
+ResidentSeqs::~ResidentSeqs() { sp_targets_destroy(t_); }
+
+// host sequence lists: uploaded for this call only
 std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const SeqList &patterns,
                                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
                                                const std::vector<std::pair<int32_t, int32_t>> *windows) {
+    if (pairs.empty()) return {};
+    const std::shared_ptr<ResidentSeqs> t = upload(targets), p = upload(patterns);
+    return align_pairs(*t, *p, pairs, windows);
+}
+
+std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const ResidentSeqs &pats,
+                                               const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                               const std::vector<std::pair<int32_t, int32_t>> *windows) {
     if (windows && windows->size() != pairs.size()) throw HostError("align_pairs: one window per pair expected");
-    Packed t(targets), p(patterns);
+    const SeqList &targets = texts.sequences(), &patterns = pats.sequences();
     std::vector<int32_t> pt(pairs.size()), pp(pairs.size()), wb, we;
     if (windows) {
         wb.resize(pairs.size()); we.resize(pairs.size());
         for (size_t q = 0; q < pairs.size(); ++q) { wb[q] = (*windows)[q].first; we[q] = (*windows)[q].second; }
     }
-    int64_t cap = 0;
+    // capacity of the run-length CIGAR pool: HiFi-like pairs need a few dozen entries each; start from a generous guess and
+    // retry once with the exact need the library reports (SP_ERR_RANGE leaves *cigar_used = entries needed)
+    int64_t worst = 0;
     for (size_t q = 0; q < pairs.size(); ++q) {
         pt[q] = pairs[q].first; pp[q] = pairs[q].second;
         if (pt[q] < 0 || pp[q] < 0 || static_cast<size_t>(pt[q]) >= targets.size() || static_cast<size_t>(pp[q]) >= patterns.size())
@@ -80,16 +101,20 @@ std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const Seq
             if (wb[q] < 0 || we[q] < wb[q] || we[q] > n) throw HostError("align_pairs: window outside its text");
             n = we[q] - wb[q];
         }
-        cap += m + std::min(n, 2 * m) + 1;
+        worst += m + std::min(n, 2 * m) + 1;
     }
     std::vector<sp_align_rec> recs(std::max<size_t>(pairs.size(), 1));
-    // worst-case capacity (one entry per row and column); left uninitialised so that only the few pages the run-length
-    // CIGARs really use are ever touched (a zero-filled vector cost ~60 ms for the 3,744 windows of a CYP2D6 template search)
-    const std::unique_ptr<uint32_t[]> cig(new uint32_t[static_cast<size_t>(std::max<int64_t>(cap, 1))]);
+    int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(1 << 16, static_cast<int64_t>(pairs.size()) * 256));
+    std::unique_ptr<uint32_t[]> cig;
     int64_t used = 0;
-    check(sp_align_windows(ctx_, &t.set, &p.set, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(), windows ? wb.data() : nullptr,
-                           windows ? we.data() : nullptr, recs.data(), cig.get(), cap, &used),
-          "sp_align_pairs");
+    for (int attempt = 0;; ++attempt) {
+        cig.reset(new uint32_t[static_cast<size_t>(std::max<int64_t>(cap, 1))]);  // uninitialised: only the used entries are ever touched
+        const sp_status st = sp_align_resident(ctx_, texts.t_, pats.t_, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(),
+                                               windows ? wb.data() : nullptr, windows ? we.data() : nullptr, recs.data(), cig.get(), cap, &used);
+        if (st == SP_ERR_RANGE && attempt == 0 && used > cap) { cap = used; continue; }
+        check(st, "sp_align_resident");
+        break;
+    }
     std::vector<Alignment> out(pairs.size());
     for (size_t q = 0; q < pairs.size(); ++q) {
         const sp_align_rec &r = recs[q];
@@ -142,23 +167,32 @@ DeviceMatrix::~DeviceMatrix() { sp_dmatrix_destroy(d_); }
 
 std::shared_ptr<PatternSet> GpuAligner::prepare_patterns(const SeqList &patterns) {
     std::shared_ptr<PatternSet> ps(new PatternSet());
-    ps->seqs_ = patterns;
+    ps->ascii_ = upload(patterns);
     Packed p(patterns);
     check(sp_patterns_create(ctx_, &p.set, SP_INFIX, &ps->p_), "sp_patterns_create");
     return ps;
 }
 
 std::unique_ptr<DeviceMatrix> GpuAligner::score_device(const SeqList &targets, const PatternSet &patterns) {
-    Packed t(targets);
-    sp_targets *tg = nullptr;
-    check(sp_targets_create(ctx_, &t.set, &tg), "sp_targets_create");
+    const std::shared_ptr<ResidentSeqs> t = upload(targets);
+    return score_device(*t, patterns);
+}
+
+std::unique_ptr<DeviceMatrix> GpuAligner::score_device(const ResidentSeqs &targets, const PatternSet &patterns, bool want_end_col) {
     std::unique_ptr<DeviceMatrix> m(new DeviceMatrix());
-    const sp_status st = sp_score_device(ctx_, tg, patterns.p_, 16, 0, &m->d_);
-    sp_targets_destroy(tg);
-    check(st, "sp_score_device");
+    check(sp_score_device(ctx_, targets.t_, patterns.p_, want_end_col ? 32 : 16, want_end_col ? 1 : 0, &m->d_), "sp_score_device");
     m->nt_ = static_cast<int64_t>(targets.size());
     m->np_ = static_cast<int64_t>(patterns.size());
     return m;
+}
+
+void GpuAligner::matrix_to_host(const DeviceMatrix &d, std::vector<int32_t> &D, std::vector<int32_t> *end_col) {
+    const size_t n = std::max<size_t>(static_cast<size_t>(d.nt_) * static_cast<size_t>(d.np_), 1);
+    D.assign(n, 0);
+    if (end_col) end_col->assign(n, 0);
+    check(sp_dmatrix_to_host(ctx_, d.d_, D.data(), end_col ? end_col->data() : nullptr), "sp_dmatrix_to_host");
+    D.resize(static_cast<size_t>(d.nt_) * static_cast<size_t>(d.np_));
+    if (end_col) end_col->resize(D.size());
 }
 
 std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k) {
@@ -170,11 +204,11 @@ std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const DeviceMatrix &d, con
 }
 
 void GpuAligner::row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
-                          const std::vector<int32_t> *pattern_bias) {
+                          const std::vector<int32_t> *pattern_bias, int dist_weight) {
     const size_t n = std::max<size_t>(static_cast<size_t>(d.nt_) * static_cast<size_t>(k), 1);
     idx.assign(n, -1); dist.assign(n, -1);
     if (pattern_bias && pattern_bias->size() != static_cast<size_t>(d.np_)) throw HostError("row_topk: one bias per pattern expected");
-    check(sp_row_topk_biased(ctx_, d.d_, pattern_bias ? pattern_bias->data() : nullptr, k, idx.data(), dist.data()), "sp_row_topk");
+    check(sp_row_topk_weighted(ctx_, d.d_, dist_weight, pattern_bias ? pattern_bias->data() : nullptr, k, idx.data(), dist.data()), "sp_row_topk");
 }
 
 std::vector<uint64_t> GpuAligner::chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,

@@ -167,8 +167,9 @@ HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene
 std::vector<PgxMappingDetails> HlaRealigner::realign_records(const std::vector<std::pair<std::string, std::string>> &reads, int n_candidates) {
     SeqList targets;
     for (const auto &r : reads) targets.push_back(r.second);
-    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(targets, *index_);
-    return realign_records_scored(reads, *D, n_candidates);
+    const std::shared_ptr<ResidentSeqs> T = gpu_.upload(targets);  // one upload for K1 and the K4 tracebacks
+    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(*T, *index_);
+    return realign_records_scored(reads, *D, n_candidates, T.get());
 }
 
 HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene_list, const HlaDatabase &database,
@@ -187,19 +188,28 @@ HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene
     index_ = gpu.prepare_patterns(seqs);
 }
 
+constexpr int kCandidateEditWeight = 5;  // b + a of the map-hifi preset: what one edit costs in alignment score, relative to a match
+
 // The selection loop of realign_record (src/hla/realigner.rs:116-146) for every read: the n best alleles by distance (K5)
 // get a traceback (K4); minimap2's target is the allele here, so `unmapped` is allele-side.  The db_aligner is the plain
 // map-hifi preset (a = 1, src/util/mapping.rs:8-14), which is what decides whether a hit would have been reported at all.
 std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std::pair<std::string, std::string>> &reads,
-                                                           const DeviceMatrix &D, int n_candidates) {
-    SeqList targets;
-    for (const auto &r : reads) targets.push_back(r.second);
+                                                           const DeviceMatrix &D, int n_candidates, const ResidentSeqs *resident_reads) {
+    std::shared_ptr<ResidentSeqs> own;
+    if (!resident_reads) {
+        SeqList targets;
+        for (const auto &r : reads) targets.push_back(r.second);
+        own = gpu_.upload(targets);
+        resident_reads = own.get();
+    }
     const size_t A = alleles_.size();
     if (D.n_targets() != static_cast<int64_t>(reads.size()) || D.n_patterns() != static_cast<int64_t>(A))
         throw HostError("realign_records_scored: distance matrix has the wrong shape");
-    // the best_n hits of every read (K5): the alleles with the most bases explained, |allele| - (nm + unmapped), ties by
-    // database order -- minimap2 ranks its hits by alignment score, so a read covering part of a long allele keeps that
-    // allele ahead of short alleles that lie wholly inside the read
+    // the best_n hits of every read (K5): minimap2 ranks its hits by alignment score, which under map-hifi (a = 1, b = 4, gaps
+    // dearer) is about (allele bases aligned) - 5 x edits; the candidates are therefore the alleles with the smallest
+    // kCandidateEditWeight * (nm + unmapped) - |allele|, ties by database order.  A read covering part of a long allele keeps that
+    // allele ahead of short alleles lying wholly inside the read, and an allele with fewer edits ahead of a longer one with more.
+    // Measured against the affine cost model: weight 5 -> 91 of 96 read assignments agree, weight 1 -> 83 of 96.
     const int k = std::max(1, std::min(n_candidates, 16));
     const SeqList &allele_seqs = index_->sequences();
     size_t max_len = 0;
@@ -207,7 +217,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
     std::vector<int32_t> bias(A);
     for (size_t a = 0; a < A; ++a) bias[a] = static_cast<int32_t>(max_len - allele_seqs[a].size());
     std::vector<int32_t> cand, cand_dist;
-    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist, &bias);
+    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist, &bias, kCandidateEditWeight);
     std::vector<std::pair<int32_t, int32_t>> pairs;
     std::vector<size_t> first_pair(reads.size() + 1, 0);
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -218,7 +228,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
                     pairs.emplace_back(static_cast<int32_t>(r), cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)]);
     }
     first_pair[reads.size()] = pairs.size();
-    std::vector<Alignment> alns = gpu_.align_pairs(targets, allele_seqs, pairs);
+    std::vector<Alignment> alns = gpu_.align_pairs(*resident_reads, index_->resident(), pairs);  // both sides already on the device
 
     std::vector<BestHit> out(reads.size());
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -243,8 +253,8 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
 }
 
 std::vector<PgxMappingDetails> HlaRealigner::realign_records_scored(const std::vector<std::pair<std::string, std::string>> &reads,
-                                                                    const DeviceMatrix &D, int n_candidates) {
-    const std::vector<BestHit> hits = best_hits(reads, D, n_candidates);
+                                                                    const DeviceMatrix &D, int n_candidates, const ResidentSeqs *resident_reads) {
+    const std::vector<BestHit> hits = best_hits(reads, D, n_candidates, resident_reads);
     std::vector<PgxMappingDetails> out;
     for (size_t r = 0; r < reads.size(); ++r) {
         PgxMappingDetails d;
@@ -280,8 +290,9 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
     if (gene_definitions_.empty()) throw HostError("realign_records_full: the realigner was built without gene definitions");
     SeqList targets;
     for (const auto &r : reads) targets.push_back(r.second);
-    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(targets, *index_);
-    const std::vector<BestHit> hits = best_hits(reads, *D, n_candidates);
+    const std::shared_ptr<ResidentSeqs> T = gpu_.upload(targets);
+    const std::unique_ptr<DeviceMatrix> D = gpu_.score_device(*T, *index_);
+    const std::vector<BestHit> hits = best_hits(reads, *D, n_candidates, T.get());
     const SeqList &allele_seqs = index_->sequences();  // hg38 orientation
 
     std::vector<RealignmentResult> out(reads.size());
@@ -437,7 +448,8 @@ HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::
     SeqList dna_targets, cdna_targets;
     for (const auto &r : reads) { dna_targets.push_back(r.dna_target); cdna_targets.push_back(r.cdna_target); }
     const int64_t R = static_cast<int64_t>(reads.size());
-    const std::unique_ptr<DeviceMatrix> Dd = gpu.score_device(dna_targets, index.realigner_->index());
+    const std::shared_ptr<ResidentSeqs> Td = gpu.upload(dna_targets);  // K1 now, K4 of the per-read assignment below
+    const std::unique_ptr<DeviceMatrix> Dd = gpu.score_device(*Td, index.realigner_->index());
     std::vector<sp_pair_rec> top;
     if (settings.disable_cdna_scoring || !index.cdna_) {
         top = gpu.pair_minsum_topk(*Dd, nullptr, 10);
@@ -468,7 +480,7 @@ HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::
     // distances are already on the device
     std::vector<std::pair<std::string, std::string>> qs;
     for (const auto &r : reads) qs.emplace_back(r.qname, r.dna_target);
-    call.mapping_details = index.realigner_->realign_records_scored(qs, *Dd);
+    call.mapping_details = index.realigner_->realign_records_scored(qs, *Dd, 5, Td.get());
     return call;
 }
 

@@ -179,21 +179,39 @@ struct Alignment {  // sp_align_rec + its CIGAR
 
 class GpuAligner;
 
-// device-resident packed pattern set (sp_patterns): the allele database of a gene, built once like HlaRealigner::new builds
-// its index once (src/hla/realigner.rs:42-91)
-class PatternSet {
+// sequences uploaded once as ASCII (sp_targets): the texts of K1 and either side of K4 (sp_align_resident) without another
+// host -> device copy -- the reads of a sample, the 39 CYP2D6 templates, the allele database next to its packed form
+class ResidentSeqs {
   public:
-    ~PatternSet();
-    PatternSet(const PatternSet &) = delete;
-    PatternSet &operator=(const PatternSet &) = delete;
+    ~ResidentSeqs();
+    ResidentSeqs(const ResidentSeqs &) = delete;
+    ResidentSeqs &operator=(const ResidentSeqs &) = delete;
     size_t size() const { return seqs_.size(); }
     const SeqList &sequences() const { return seqs_; }
 
   private:
     friend class GpuAligner;
+    ResidentSeqs() = default;
+    sp_targets *t_ = nullptr;
+    SeqList seqs_;
+};
+
+// device-resident packed pattern set (sp_patterns): the allele database of a gene, built once like HlaRealigner::new builds
+// its index once (src/hla/realigner.rs:42-91); its ASCII form stays on the device too, for the K4 tracebacks
+class PatternSet {
+  public:
+    ~PatternSet();
+    PatternSet(const PatternSet &) = delete;
+    PatternSet &operator=(const PatternSet &) = delete;
+    size_t size() const { return ascii_->size(); }
+    const SeqList &sequences() const { return ascii_->sequences(); }
+    const ResidentSeqs &resident() const { return *ascii_; }
+
+  private:
+    friend class GpuAligner;
     PatternSet() = default;
     sp_patterns *p_ = nullptr;
-    SeqList seqs_;
+    std::shared_ptr<ResidentSeqs> ascii_;
 };
 
 // device-resident distance matrix (sp_dmatrix, u16): stays in HBM between K1, K2 and K5
@@ -229,13 +247,20 @@ class GpuAligner {
                                        const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr);
     std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
                                               int k);
-    // resident path: nothing of size reads x alleles crosses PCIe
+    // resident path: nothing of size reads x alleles crosses PCIe, no sequence is uploaded twice
+    std::shared_ptr<ResidentSeqs> upload(const SeqList &seqs);
     std::shared_ptr<PatternSet> prepare_patterns(const SeqList &patterns);
     std::unique_ptr<DeviceMatrix> score_device(const SeqList &targets, const PatternSet &patterns);          // K1
+    std::unique_ptr<DeviceMatrix> score_device(const ResidentSeqs &targets, const PatternSet &patterns, bool want_end_col = false);
+    // D[t * n_patterns + p] (and end columns) of a device matrix scored with 32-bit elements / end columns
+    void matrix_to_host(const DeviceMatrix &d, std::vector<int32_t> &D, std::vector<int32_t> *end_col);
+    std::vector<Alignment> align_pairs(const ResidentSeqs &texts, const ResidentSeqs &patterns,
+                                       const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr);                  // K4
     std::vector<sp_pair_rec> pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k);           // K2
-    // K5; pattern_bias (optional, one entry per pattern) is added to the distance for ranking only
+    // K5; ranking key = dist_weight * distance + pattern_bias[p] (bias optional, one entry per pattern); dist returns the plain distance
     void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
-                  const std::vector<int32_t> *pattern_bias = nullptr);
+                  const std::vector<int32_t> *pattern_bias = nullptr, int dist_weight = 1);
     // S[i * n_chains + j], j >= i: sum over reads of min(B[i][r], B[j][r]) for the chain-window matrix B
     std::vector<uint64_t> chain_pair_sums(const std::vector<std::vector<int32_t>> &chains,
                                           const std::vector<std::vector<std::vector<uint32_t>>> &read_weights, int64_t n_haps);
@@ -397,7 +422,8 @@ class HlaRealigner {  // src/hla/realigner.rs:22-350
                                                    int n_candidates = 5);
     // same, on a distance matrix K1 already produced for these reads against this index
     std::vector<PgxMappingDetails> realign_records_scored(const std::vector<std::pair<std::string, std::string>> &qname_and_sequence,
-                                                          const DeviceMatrix &D, int n_candidates = 5);
+                                                          const DeviceMatrix &D, int n_candidates = 5,
+                                                          const ResidentSeqs *resident_reads = nullptr);
     // realign_record in full (:98-350) for a batch of reads (hg38 forward strand): best database allele as above, then the
     // buffered read segment against the gene's hg38 sequence and, when that starts later than the allele mapping, the allele
     // against hg38 (two more K4 batches) for the segment range and the DNA / HPC offsets the consensus step consumes
@@ -408,7 +434,9 @@ class HlaRealigner {  // src/hla/realigner.rs:22-350
 
   private:
     struct BestHit { int allele = -1; MappingStats stats; Alignment aln; };
-    std::vector<BestHit> best_hits(const std::vector<std::pair<std::string, std::string>> &reads, const DeviceMatrix &D, int n_candidates);
+    // resident_reads: the reads as already uploaded for K1 (nullptr: uploaded here)
+    std::vector<BestHit> best_hits(const std::vector<std::pair<std::string, std::string>> &reads, const DeviceMatrix &D, int n_candidates,
+                                   const ResidentSeqs *resident_reads = nullptr);
     GpuAligner &gpu_;
     std::vector<const HlaAlleleDefinition *> alleles_;
     std::shared_ptr<PatternSet> index_;
@@ -528,6 +556,7 @@ class Cyp2d6Extractor {
   private:
     GpuAligner &gpu_;
     std::vector<std::pair<Cyp2d6RegionLabel, std::string>> templates_;
+    std::shared_ptr<PatternSet> tmpl_patterns_;  // built at the first search
 };
 
 // :454-468: per-site state from the nodes a WFA-graph traversal visited (3 = unset, conflicting assignments -> 2)

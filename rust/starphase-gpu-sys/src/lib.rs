@@ -95,6 +95,8 @@ extern "C" {
     pub fn sp_row_topk(ctx: *mut sp_ctx, d: *const sp_dmatrix, k: c_int, idx: *mut i32, dist: *mut i32) -> c_int;
     pub fn sp_row_topk_biased(ctx: *mut sp_ctx, d: *const sp_dmatrix, pattern_bias: *const i32, k: c_int, idx: *mut i32,
                               dist: *mut i32) -> c_int;
+    pub fn sp_row_topk_weighted(ctx: *mut sp_ctx, d: *const sp_dmatrix, dist_weight: c_int, pattern_bias: *const i32, k: c_int, idx: *mut i32,
+                                dist: *mut i32) -> c_int;
     pub fn sp_variant_match(ctx: *mut sp_ctx, n_seq: i64, n_hap: i64, n_var: i64, seq_alleles: *const u8, hap_alleles: *const u8,
                             is_vi: *const u8, vi_match: *mut u32, all_match: *mut u32) -> c_int;
     pub fn sp_chain_window_scores(ctx: *mut sp_ctx, n_chains: i64, chain_off: *const i32, chain_items: *const i32, n_reads: i64,
@@ -105,6 +107,9 @@ extern "C" {
     pub fn sp_pair_minsum_topk_host(ctx: *mut sp_ctx, d: *const i32, d2: *const i32, r: i64, a: i64, k: c_int,
                                     out: *mut sp_pair_rec, n_out: *mut c_int) -> c_int;
     pub fn sp_pair_minsum_full_host(ctx: *mut sp_ctx, d: *const i32, r: i64, a: i64, s: *mut u64) -> c_int;
+    pub fn sp_align_resident(ctx: *mut sp_ctx, texts: *const sp_targets, patterns: *const sp_targets, n_pairs: i64, pair_text: *const i32,
+                             pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
+                             cigar_cap: i64, cigar_used: *mut i64) -> c_int;
     // multi-GPU (one sp_comm per context; ranks are processes or threads, every call below is a collective)
     pub fn sp_comm_unique_id(id: *mut u8) -> c_int;
     pub fn sp_comm_create(ctx: *mut sp_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut sp_comm) -> c_int;

@@ -165,7 +165,7 @@ def realign_flips(orc, aff_orc: AffineFlowOracle, db, genes, reads: Sequence[Tup
         out["assignment_differs"] += prod[r]["best_hla_id"] != model_id
         ps = prod[r]["best_mapping_stats"]["dna_stats"]
         out["stats_differ"] += prod[r]["best_hla_id"] == model_id and (ps["seq_len"], ps["nm"], ps["unmapped"]) != (best.seq_len, best.nm, best.unmapped)
-        cand = sorted(range(len(seqs)), key=lambda a: (int(D[r, a]) - len(seqs[a]), a))[:n_candidates]
+        cand = sorted(range(len(seqs)), key=lambda a: (fo.CANDIDATE_EDIT_WEIGHT * int(D[r, a]) - len(seqs[a]), a))[:n_candidates]
         out["model_best_not_in_product_candidates"] += best_a is not None and best_a not in cand
     return out
 

@@ -118,9 +118,13 @@ def score_consensus(orc, reference_sequence: bytes, ref_start: int, consensus: b
     return stats, best_id, best_star, score_read_debug(orc, dna_t, cdna_t, db, gene)
 
 
+CANDIDATE_EDIT_WEIGHT = 5  # kCandidateEditWeight of pb_starphase_b200/host/sp_host_hla.cpp
+
+
 def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Sequence[Tuple[str, bytes]], n_candidates: int = 5,
                     D: Optional[np.ndarray] = None) -> List[dict]:
-    """src/hla/realigner.rs:98-211: candidates = the n alleles with the most bases explained, |allele| - (nm + unmapped), ties by database order."""
+    """src/hla/realigner.rs:98-211: candidates = the n alleles with the smallest 5 * (nm + unmapped) - |allele| (minimap2 ranks hits by
+    alignment score: about aligned bases - 5 * edits under map-hifi), ties by database order."""
     alleles = [r for r in sorted(db, key=lambda r: r[0].encode()) if r[1] in genes and r[3] is not None]
     seqs = [r[3].encode() for r in alleles]
     if D is None:
@@ -128,8 +132,7 @@ def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Seque
     out = []
     for r, (qname, seq) in enumerate(reads):
         best, best_a = so.MappingStats(len(seq), len(seq), 0), None
-        # candidates = the n alleles with the most bases explained (|allele| - D), ties by database order
-        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        order = sorted(range(len(alleles)), key=lambda a: (CANDIDATE_EDIT_WEIGHT * int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
             al = orc.align(seqs[a], seq)
             if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:  # db_aligner is the plain map-hifi preset (a = 1)
@@ -156,8 +159,7 @@ def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_de
     out = []
     for r, (qname, seq) in enumerate(reads):
         best, best_a, best_al = so.MappingStats(len(seq), len(seq), 0), None, None
-        # candidates = the n alleles with the most bases explained (|allele| - D), ties by database order
-        order = sorted(range(len(alleles)), key=lambda a: (int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
+        order = sorted(range(len(alleles)), key=lambda a: (CANDIDATE_EDIT_WEIGHT * int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
             al = orc.align(seqs[a], seq)
             if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:

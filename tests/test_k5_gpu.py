@@ -37,10 +37,17 @@ def test_row_topk_vs_numpy(ctx, bits):
         idx, dist = ctx.row_topk(d, k, bias=bias)
         order = np.argsort(D + bias[None, :], axis=1, kind="stable")[:, :k]
         assert (idx == order).all() and (dist == np.take_along_axis(D, order, axis=1)).all(), k
+    # sp_row_topk_weighted: key = 5 * distance + bias, the realigner's stand-in for minimap2's score ranking
+    for k in (1, 5, 16):
+        idx, dist = ctx.row_topk(d, k, bias=bias, weight=5)
+        order = np.argsort(5 * D + bias[None, :], axis=1, kind="stable")[:, :k]
+        assert (idx == order).all() and (dist == np.take_along_axis(D, order, axis=1)).all(), k
     import pb_starphase_b200 as sp
 
     with pytest.raises(sp.SpError):
         ctx.row_topk(d, 5, bias=-np.ones(len(pats), dtype=np.int32))
+    with pytest.raises(sp.SpError):
+        ctx.row_topk(d, 5, bias=bias, weight=65)
     d.close(); T.close(); P.close()
 
 
