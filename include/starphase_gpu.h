@@ -276,6 +276,36 @@ sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, const int32_t 
                                    sp_pair_rec *out, int *n_out);
 sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S);
 
+/* ---- K7: consensus extension (row N1 of SURVEY.md 8f) ---------------------------------------- */
+/* The reference builds consensus sequences with waffle_con's dynamic-WFA search (DualConsensusDWFA / ConsensusDWFA /
+ * PriorityConsensusDWFA: src/hla/caller.rs:1097-1219, :727-755, src/cyp2d6/caller.rs:145-280): candidate consensus prefixes
+ * grow one symbol at a time, every read keeps its edit distance to the prefix, and the reads vote for the next symbol.  The
+ * data-parallel step -- extend candidate X by symbol s for all reads -- is what these calls put on the device; the search
+ * policy (queue, vote thresholds, dual split) stays with the host (pb_starphase_b200/host/sp_host_consensus.cpp).
+ * A handle owns `max_tracks` tracks; a track = the DP column of every read against one consensus prefix, banded
+ * (`band` rows either side of the read's diagonal, widened by offset_window / 2).  offsets[r] >= 0 is where read r is expected to
+ * start inside the consensus (waffle_con's add_sequence_offset(.., Some(offset))): the read may start anywhere within
+ * offset_window / 2 of it for free and is inactive before; offsets[r] < 0 (or offsets == NULL) anchors the read at the start of
+ * the consensus (add_sequence / offset None). */
+typedef struct sp_consensus sp_consensus;
+sp_status sp_consensus_create(sp_ctx *ctx, const sp_seqset *reads, const int32_t *offsets, int32_t offset_window, int32_t band,
+                              int32_t max_tracks, sp_consensus **out);
+void sp_consensus_destroy(sp_consensus *c);
+int32_t sp_consensus_num_reads(const sp_consensus *c);
+int32_t sp_consensus_num_tracks(const sp_consensus *c);
+/* Track `track` becomes the empty consensus. */
+sp_status sp_consensus_reset(sp_consensus *c, int32_t track);
+/* n_tasks extensions in one launch: track dst[q] = track src[q] with symbols[q] appended ('A' 'C' 'G' 'T'; any other byte matches
+ * nothing; 0 = no extension, just report the state of src[q], copied to dst[q]).  dst entries are distinct; a track written by
+ * one task may not be read by another (src[q] == dst[q] is fine).  Outputs, [n_tasks][n_reads]:
+ *   ed    = min over read prefixes of the edit distance to the extended consensus (0 while the read is inactive)
+ *   votes = bit 0..3: A / C / G / T follows a prefix reaching that minimum, bit 4: another byte follows, bit 5: the whole read
+ *           reaches it, bit 6: the read is not active yet
+ *   full  = min over the columns so far of the distance with the whole read consumed (0x3FFFFFFF: never reached): the read's
+ *           cost once the consensus has grown past its end. */
+sp_status sp_consensus_extend(sp_consensus *c, int32_t n_tasks, const int32_t *src, const uint8_t *symbols, const int32_t *dst,
+                              int32_t *ed, uint8_t *votes, int32_t *full);
+
 /* ---- multi-GPU: the path over the GPUs of one box ------------------------ */
 /* The reference is one process on one thread (src/cli/diplotype.rs:185-191) and has no distributed code; the north_star
  * partitions this path as: allele set sharded for K1, read set broadcast, allele-pair row blocks sharded for K2, per-shard

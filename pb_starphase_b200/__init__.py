@@ -10,6 +10,7 @@ libstarphase_gpu.so and a B200.
 """
 from .binding import (  # noqa: F401
     Comm,
+    Consensus,
     Context,
     DMatrix,
     PatternSet,

@@ -90,6 +90,12 @@ SIGNATURES = {
     "sp_pair_minsum_full": (C.c_int, [_P, _P, _P]),
     "sp_pair_minsum_topk_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(PairRec), C.POINTER(C.c_int)]),
     "sp_pair_minsum_full_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    "sp_consensus_create": (C.c_int, [_P, C.POINTER(SeqSet), _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "sp_consensus_destroy": (None, [_P]),
+    "sp_consensus_num_reads": (C.c_int32, [_P]),
+    "sp_consensus_num_tracks": (C.c_int32, [_P]),
+    "sp_consensus_reset": (C.c_int, [_P, C.c_int32]),
+    "sp_consensus_extend": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "sp_comm_unique_id": (C.c_int, [_P]),
     "sp_comm_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "sp_comm_destroy": (None, [_P]),
@@ -408,6 +414,47 @@ class Context:
         h = _P()
         self._check(self._lib.sp_dmatrix_wrap(self._h, _P(dev_ptr), n_targets, n_patterns, ld, elem_bits, C.byref(h)))
         return DMatrix(self, h, n_targets, n_patterns, False)
+
+
+class Consensus:
+    """sp_consensus (K7): device-resident banded DP columns of a read set against growing consensus prefixes ("tracks")."""
+
+    def __init__(self, ctx: Context, reads, offsets=None, offset_window: int = 0, band: int = 32, max_tracks: int = 64):
+        self.ctx = ctx
+        bases, offs = reads if isinstance(reads, tuple) else pack_sequences(reads)
+        ss = _seqset(bases, offs)
+        o = np.ascontiguousarray([-1 if x is None else int(x) for x in offsets], dtype=np.int32) if offsets is not None else None  # None / < 0: anchored at the start
+        h = _P()
+        ctx._check(ctx._lib.sp_consensus_create(ctx._h, C.byref(ss), o.ctypes.data if o is not None else None, offset_window, band, max_tracks,
+                                                C.byref(h)))
+        self._h, self.n_reads, self.n_tracks = h, len(offs) - 1, max_tracks
+
+    def reset(self, track: int):
+        self.ctx._check(self.ctx._lib.sp_consensus_reset(self._h, track))
+
+    def extend(self, src, symbols, dst):
+        """symbols: bytes / list of ints, 0 = report only.  Returns (ed, votes, full), each [n_tasks, n_reads]."""
+        s = np.ascontiguousarray(src, dtype=np.int32)
+        d = np.ascontiguousarray(dst, dtype=np.int32)
+        y = np.ascontiguousarray(list(symbols), dtype=np.uint8)
+        n = len(s)
+        ed = np.zeros((n, self.n_reads), dtype=np.int32)
+        full = np.zeros((n, self.n_reads), dtype=np.int32)
+        votes = np.zeros((n, self.n_reads), dtype=np.uint8)
+        self.ctx._check(self.ctx._lib.sp_consensus_extend(self._h, n, s.ctypes.data, y.ctypes.data, d.ctypes.data, ed.ctypes.data,
+                                                          votes.ctypes.data, full.ctypes.data))
+        return ed, votes, full
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sp_consensus_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Comm:

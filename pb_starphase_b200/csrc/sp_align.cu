@@ -186,20 +186,25 @@ extern "C" sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, con
         if (!o) o = U == 4 ? class_occupancy<4>() : U == 8 ? class_occupancy<8>() : U == 12 ? class_occupancy<12>() : class_occupancy<16>();
         return o;
     };
-    // scratch need of this call: one slot per warp in flight
-    int64_t want_words = 0;
-    for (auto &kv : classes) {
-        ClassPlan &c = kv.second;
-        const int64_t n_slots = std::min<int64_t>(c.n_bins, static_cast<int64_t>(ctx->num_sms) * occupancy(c.U) * K4_WARPS);
-        want_words = std::max(want_words, n_slots * c.slot_words);
-    }
-    if (static_cast<size_t>(want_words) * 4 > ctx->pool_bytes[0] || !ctx->free_mem_cached) {
+    // scratch budget: a quarter of the memory that was free when the pool last had to grow, within [4, 16] GB.  cudaMemGetInfo
+    // costs milliseconds next to multi-GB allocations, so it is asked again only when this call would grow the pool.
+    auto budget_of = [&]() { return std::max<int64_t>(4ll << 30, std::min<int64_t>(16ll << 30, static_cast<int64_t>(ctx->free_mem_cached / 4))) / 4; };
+    auto need_words = [&](int64_t budget_words) {
+        int64_t need = 0;
+        for (auto &kv : classes) {
+            ClassPlan &c = kv.second;
+            int64_t n_slots = std::min<int64_t>(c.n_bins, static_cast<int64_t>(ctx->num_sms) * occupancy(c.U) * K4_WARPS);
+            n_slots = std::max<int64_t>(1, std::min(n_slots, budget_words / c.slot_words));
+            need = std::max(need, n_slots * c.slot_words);
+        }
+        return need;
+    };
+    if (!ctx->free_mem_cached || static_cast<size_t>(need_words(budget_of())) * 4 > 2 * ctx->pool_bytes[0]) {
         size_t free_b = 0, total_b = 0;
         SP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
         ctx->free_mem_cached = free_b + ctx->pool_bytes[0];
     }
-    // budget: a quarter of the memory that was free when the pool last had to grow, within [4, 16] GB
-    const int64_t budget_words = std::max<int64_t>(4ll << 30, std::min<int64_t>(16ll << 30, static_cast<int64_t>(ctx->free_mem_cached / 4))) / 4;
+    const int64_t budget_words = budget_of();
     uint32_t *d_blobs = nullptr, *d_cigar = nullptr, *d_dense = nullptr, *d_scratch = nullptr;
     AlignRecDev *d_recs = nullptr;
     unsigned long long *d_used = nullptr;

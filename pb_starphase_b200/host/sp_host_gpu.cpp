@@ -104,7 +104,7 @@ std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const 
         worst += m + std::min(n, 2 * m) + 1;
     }
     std::vector<sp_align_rec> recs(std::max<size_t>(pairs.size(), 1));
-    int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(1 << 16, static_cast<int64_t>(pairs.size()) * 256));
+    int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(1 << 16, static_cast<int64_t>(pairs.size()) * cigar_entries_per_pair_));
     std::unique_ptr<uint32_t[]> cig;
     int64_t used = 0;
     for (int attempt = 0;; ++attempt) {
@@ -115,6 +115,8 @@ std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const 
         check(st, "sp_align_resident");
         break;
     }
+    // remember how long the CIGARs of this workload are (divergent CYP2D6 templates need ~400 entries, HLA alleles a few dozen)
+    cigar_entries_per_pair_ = std::max<int64_t>(cigar_entries_per_pair_, 2 * used / static_cast<int64_t>(pairs.size()) + 64);
     std::vector<Alignment> out(pairs.size());
     for (size_t q = 0; q < pairs.size(); ++q) {
         const sp_align_rec &r = recs[q];

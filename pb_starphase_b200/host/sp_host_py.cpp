@@ -40,6 +40,41 @@ PYBIND11_MODULE(_starphase_host, m) {
 
     py::class_<Json>(m, "Json").def("pretty", [](const Json &j) { return j.pretty(); });
 
+    // consensus (K7 + host search): (sequences, offsets or None, config dict) -> solutions
+    auto cfg_from = [](const py::dict &d) {
+        CdwfaConfig c;
+        if (d.contains("min_count")) c.min_count = d["min_count"].cast<size_t>();
+        if (d.contains("min_af")) c.min_af = d["min_af"].cast<double>();
+        if (d.contains("allow_early_termination")) c.allow_early_termination = d["allow_early_termination"].cast<bool>();
+        if (d.contains("max_queue_size")) c.max_queue_size = d["max_queue_size"].cast<size_t>();
+        if (d.contains("max_capacity_per_size")) c.max_capacity_per_size = d["max_capacity_per_size"].cast<size_t>();
+        if (d.contains("offset_window")) c.offset_window = d["offset_window"].cast<size_t>();
+        if (d.contains("band")) c.band = d["band"].cast<size_t>();
+        return c;
+    };
+    m.def("consensus", [cfg_from](GpuAligner &g, const SeqList &reads, const std::vector<std::optional<size_t>> &offsets, const py::dict &cfg) {
+        ConsensusDWFA c(g, cfg_from(cfg));
+        for (size_t r = 0; r < reads.size(); ++r) c.add_sequence_offset(reads[r], r < offsets.size() ? offsets[r] : std::nullopt);
+        py::list out;
+        for (const Consensus &s : c.consensus()) out.append(py::make_tuple(py::bytes(s.sequence), s.scores));
+        return py::make_tuple(out, c.n_extension_calls());
+    });
+    m.def("dual_consensus", [cfg_from](GpuAligner &g, const SeqList &reads, const std::vector<std::optional<size_t>> &offsets, const py::dict &cfg) {
+        DualConsensusDWFA c(g, cfg_from(cfg));
+        for (size_t r = 0; r < reads.size(); ++r) c.add_sequence_offset(reads[r], r < offsets.size() ? offsets[r] : std::nullopt);
+        py::list out;
+        for (const DualConsensus &s : c.consensus()) {
+            py::dict d;
+            d["consensus1"] = py::bytes(s.consensus1);
+            d["consensus2"] = s.consensus2 ? py::object(py::bytes(*s.consensus2)) : py::object(py::none());
+            d["is_consensus1"] = s.is_consensus1;
+            d["scores1"] = s.scores1;
+            d["scores2"] = s.scores2;
+            out.append(d);
+        }
+        return py::make_tuple(out, c.n_extension_calls());
+    });
+
     py::class_<MappingStats>(m, "MappingStats")
         .def(py::init<size_t, size_t, size_t>())
         .def_readwrite("seq_len", &MappingStats::seq_len)

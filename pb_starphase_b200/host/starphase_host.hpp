@@ -273,6 +273,7 @@ class GpuAligner {
   private:
     void check(sp_status st, const char *what);
     sp_ctx *ctx_ = nullptr;
+    int64_t cigar_entries_per_pair_ = 256;  // first guess of the CIGAR pool size; grows with what the calls really needed
 };
 
 // ------------------------------------------------------------------------------------------
@@ -643,6 +644,62 @@ Cyp2d6Call call_cyp2d6_chains(GpuAligner &gpu, const Cyp2d6Config &cfg, const Se
 // cyp2d6_alleles.json (DeeplotypeDebug, src/cyp2d6/debug.rs:8-71): the three forms of both haplotypes + the variants of every typed allele
 std::string cyp2d6_alleles_json(const std::vector<std::vector<size_t>> &best_diplotype_indices, const std::vector<Cyp2d6Region> &hap_regions,
                                 const std::map<std::string, std::string> &cyp_translate);
+
+// ------------------------------------------------------------------------------------------
+// consensus (row N1 of SURVEY.md 8f) -- the interface of waffle_con's ConsensusDWFA / DualConsensusDWFA as the reference uses it
+// (src/hla/caller.rs:1097-1219, :727-755), the per-read extension step on the device (K7, sp_consensus_extend), the search policy
+// here.  The policy restates the published outline of waffle_con's search, not its code (parity unpinned).
+// ------------------------------------------------------------------------------------------
+struct CdwfaConfig {  // the members the reference sets at src/hla/caller.rs:1103-1116
+    size_t min_count = 3;
+    double min_af = 0.10;
+    bool allow_early_termination = false;
+    size_t max_queue_size = 20;
+    size_t max_capacity_per_size = 10;
+    size_t offset_window = 0;
+    size_t band = 32;  // rows either side of a read's diagonal kept on the device (HiFi drift); widened by offset_window / 2
+    // accepted for interface compatibility, not modelled: dual_max_ed_delta, weighted_by_ed (the reference sets false),
+    // consensus_cost (the reference sets L1Distance, which is what is implemented), offset_compare_length
+    size_t dual_max_ed_delta = 20;
+};
+struct Consensus {  // waffle_con::consensus::Consensus
+    std::string sequence;
+    std::vector<size_t> scores;  // per read, in insertion order
+};
+struct DualConsensus {  // waffle_con::dual_consensus::DualConsensus
+    std::string consensus1;
+    std::optional<std::string> consensus2;
+    std::vector<bool> is_consensus1;
+    std::vector<std::optional<size_t>> scores1, scores2;
+    bool is_dual() const { return consensus2.has_value(); }
+};
+class ConsensusDWFA {
+  public:
+    ConsensusDWFA(GpuAligner &gpu, CdwfaConfig config) : gpu_(gpu), config_(config) {}
+    void add_sequence(const std::string &sequence) { add_sequence_offset(sequence, std::nullopt); }
+    void add_sequence_offset(const std::string &sequence, std::optional<size_t> offset);
+    std::vector<Consensus> consensus();  // every best solution, first = the one the reference takes
+    size_t n_extension_calls() const { return n_calls_; }
+
+  protected:
+    friend class DualConsensusDWFA;
+    GpuAligner &gpu_;
+    CdwfaConfig config_;
+    SeqList reads_;
+    std::vector<int32_t> offsets_;
+    size_t n_calls_ = 0;
+};
+class DualConsensusDWFA {
+  public:
+    DualConsensusDWFA(GpuAligner &gpu, CdwfaConfig config) : inner_(gpu, config) {}
+    void add_sequence(const std::string &sequence) { inner_.add_sequence(sequence); }
+    void add_sequence_offset(const std::string &sequence, std::optional<size_t> offset) { inner_.add_sequence_offset(sequence, offset); }
+    std::vector<DualConsensus> consensus();
+    size_t n_extension_calls() const { return inner_.n_calls_; }
+
+  private:
+    ConsensusDWFA inner_;
+};
 
 // StarphaseJson, src/data_types/starphase_json.rs:13-21; metadata order of src/database/pgx_database.rs:359-371
 std::string starphase_json(const std::string &pbstarphase_version, const std::map<std::string, std::string> &database_metadata,

@@ -42,6 +42,7 @@ pub enum sp_patterns {}
 pub enum sp_targets {}
 pub enum sp_dmatrix {}
 pub enum sp_comm {}
+pub enum sp_consensus {}
 pub const SP_COMM_ID_BYTES: usize = 128;
 
 pub const SP_INFIX: c_int = 0;
@@ -110,6 +111,15 @@ extern "C" {
     pub fn sp_align_resident(ctx: *mut sp_ctx, texts: *const sp_targets, patterns: *const sp_targets, n_pairs: i64, pair_text: *const i32,
                              pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
                              cigar_cap: i64, cigar_used: *mut i64) -> c_int;
+    // K7: consensus extension
+    pub fn sp_consensus_create(ctx: *mut sp_ctx, reads: *const sp_seqset, offsets: *const i32, offset_window: i32, band: i32, max_tracks: i32,
+                               out: *mut *mut sp_consensus) -> c_int;
+    pub fn sp_consensus_destroy(c: *mut sp_consensus);
+    pub fn sp_consensus_num_reads(c: *const sp_consensus) -> i32;
+    pub fn sp_consensus_num_tracks(c: *const sp_consensus) -> i32;
+    pub fn sp_consensus_reset(c: *mut sp_consensus, track: i32) -> c_int;
+    pub fn sp_consensus_extend(c: *mut sp_consensus, n_tasks: i32, src: *const i32, symbols: *const u8, dst: *const i32, ed: *mut i32,
+                               votes: *mut u8, full: *mut i32) -> c_int;
     // multi-GPU (one sp_comm per context; ranks are processes or threads, every call below is a collective)
     pub fn sp_comm_unique_id(id: *mut u8) -> c_int;
     pub fn sp_comm_create(ctx: *mut sp_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut sp_comm) -> c_int;

@@ -1,0 +1,115 @@
+"""GPU suite, row N1: K7 (sp_consensus_extend, through the C ABI) against the oracle's banded recurrence, bit for bit, and the
+C++ host search (ConsensusDWFA / DualConsensusDWFA above K7) against the oracle's search: same consensus sequences, same per-read
+scores, same read split.  Parity with waffle_con itself is unpinned; the properties of tests/test_consensus_cpu.py
+are re-checked here at HLA size."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import consensus_oracle as co  # noqa: E402
+from pb_starphase_b200 import synth  # noqa: E402
+from test_consensus_cpu import het_pair, rnd  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_k7_extend_vs_oracle(ctx):
+    import pb_starphase_b200 as sp
+
+    rng = np.random.default_rng(5)
+    src = rnd(rng, 180)
+    reads, _ = synth.hifi_reads(rng, [src], 9, err=0.02, flank=0, lo=0, hi=1 << 20)
+    reads += [src[60:], src[75:160], b"", b"ACGTNACGT", src[:50]]
+    offsets = [-1] * 9 + [60, 80, -1, 10, 0]
+    for band, window in ((8, 0), (32, 0), (16, 30), (100, 64)):
+        cfg = co.Config(band=band, offset_window=window)
+        cons = sp.Consensus(ctx, reads, offsets, offset_window=window, band=band, max_tracks=6)
+        tracks = {0: co.Track(len(reads))}
+        cons.reset(0)
+        ed, votes, full = cons.extend([0], [0], [0])
+        tracks[0], e0, v0, f0 = co.extend(reads, offsets, cfg, tracks[0], 0)  # the report also folds column 0 into best_full
+        assert ed[0].tolist() == e0 and votes[0].tolist() == v0 and full[0].tolist() == f0
+        # walk the true sequence with a detour: two children per step (the right symbol and a wrong one), parent = the right child
+        cur = 0
+        for pos, base in enumerate(src[:150]):
+            wrong = b"ACGT"[(b"ACGT".index(base) + 1 + pos % 3) % 4]
+            free = [t for t in range(6) if t != cur][:2]
+            ed, votes, full = cons.extend([cur, cur], [base, wrong], free)
+            for q, symbol in enumerate((base, wrong)):
+                t, e, v, f = co.extend(reads, offsets, cfg, tracks[cur], symbol)
+                assert ed[q].tolist() == e, (band, window, pos, q)
+                assert votes[q].tolist() == v and full[q].tolist() == f, (band, window, pos, q)
+                tracks[free[q]] = t
+            cur = free[0]
+        # in place (src == dst), and a report of the result
+        ed, votes, full = cons.extend([cur], [src[150]], [cur])
+        t, e, v, f = co.extend(reads, offsets, cfg, tracks[cur], src[150])
+        assert ed[0].tolist() == e and votes[0].tolist() == v and full[0].tolist() == f
+        ed, votes, full = cons.extend([cur], [0], [cur])
+        assert ed[0].tolist() == e and votes[0].tolist() == v and full[0].tolist() == f
+        with pytest.raises(sp.SpError):
+            cons.extend([0, 1], [65, 65], [2, 2])  # two tasks writing one track
+        cons.close()
+
+
+def host_consensus(reads, offsets=None, **cfg):
+    from pb_starphase_b200 import _starphase_host as host
+
+    gpu = host.GpuAligner(0)
+    offs = list(offsets) if offsets is not None else []
+    return gpu, host, [r.decode() for r in reads], offs, cfg
+
+
+def test_host_search_equals_oracle_search():
+    rng = np.random.default_rng(6)
+    for case in range(4):
+        a, b = het_pair(rng, 260 + 20 * case, (30, 131, 222))
+        na, nb = int(rng.integers(4, 9)), int(rng.integers(0, 7))
+        ra, _ = synth.hifi_reads(rng, [a], na, err=0.006, flank=0, lo=0, hi=1 << 20)
+        rb, _ = synth.hifi_reads(rng, [b], nb, err=0.006, flank=0, lo=0, hi=1 << 20) if nb else ([], None)
+        reads = ra + rb
+        gpu, host, rs, offs, _ = host_consensus(reads)
+        got, calls = host.consensus(gpu, rs, offs, {})
+        want = co.consensus(reads)
+        assert [(s, list(sc)) for s, sc in got] == [(s, sc) for s, sc in want], case
+        gotd, calls = host.dual_consensus(gpu, rs, offs, {})
+        wantd = co.dual_consensus(reads)
+        assert len(gotd) == len(wantd)
+        for g, w in zip(gotd, wantd):
+            assert g["consensus1"] == w["consensus1"] and g["consensus2"] == w["consensus2"], case
+            assert list(g["is_consensus1"]) == w["is_consensus1"] and list(g["scores1"]) == w["scores1"] and list(g["scores2"]) == w["scores2"], case
+        assert calls > 200  # one device call per expanded node
+
+
+def test_host_search_offsets_and_windows():
+    rng = np.random.default_rng(7)
+    src = rnd(rng, 420)
+    reads = [src[:300], src[:330], src[:310], src[100:], src[125:], src[90:], src]
+    offsets = [None, None, None, 112, 120, 90, None]
+    cfg = dict(allow_early_termination=True, offset_window=40)
+    gpu, host, rs, offs, _ = host_consensus(reads, offsets)
+    got, _ = host.consensus(gpu, rs, offs, cfg)
+    want = co.consensus(reads, offsets, co.Config(**cfg))
+    assert [(s, list(sc)) for s, sc in got] == want and got[0][0] == src
+
+
+def test_hla_sized_dual_consensus_properties():
+    """30 HiFi-like reads of two 3.3 kb alleles differing at five sites: both alleles come back exactly, every read on its side."""
+    rng = np.random.default_rng(8)
+    a, b = het_pair(rng, 3300, (200, 900, 1700, 2500, 3100))
+    ra, _ = synth.hifi_reads(rng, [a], 16, err=0.002, flank=0, lo=0, hi=1 << 20)
+    rb, _ = synth.hifi_reads(rng, [b], 14, err=0.002, flank=0, lo=0, hi=1 << 20)
+    reads = ra + rb
+    gpu, host, rs, offs, _ = host_consensus(reads)
+    got, calls = host.dual_consensus(gpu, rs, offs, {})
+    d = got[0]
+    assert {d["consensus1"], d["consensus2"]} == {a, b}
+    first_is_a = d["consensus1"] == a
+    assert list(d["is_consensus1"]) == [first_is_a] * 16 + [not first_is_a] * 14
+    single, _ = host.consensus(gpu, [r.decode() for r in ra], [], {})
+    assert single[0][0] == a
