@@ -46,9 +46,11 @@ typedef enum sp_status {
     SP_ERR_RANGE = 5        /* value does not fit the device format (e.g. > 65535 alleles for top-k)  */
 } sp_status;
 
-/* Longest pattern one warp can hold: 32 lanes x 16 words x 32 rows.  Longer patterns are rejected with SP_ERR_TOO_LONG
- * (the reference's aligner has no such limit; the HLA-A / HLA-B alleles of IMGT 3.57 reach 4.1 kb, CYP2D6 regions 6.2 kb). */
-#define SP_MAX_PATTERN_LEN 16384
+/* Longest pattern one warp can hold: 32 lanes x 24 words x 32 rows (lane widths above 16 words are compiled for sets that hold
+ * such a pattern only).  Longer patterns are rejected with SP_ERR_TOO_LONG -- the reference's aligner has no such limit; the
+ * HLA-A / HLA-B alleles of IMGT 3.57 reach 4.1 kb, CYP2D6 regions 6.2 kb, the longest class II genomic alleles (DRB1) ~17 kb.
+ * The C++ host skips over-long alleles one by one (they score as "no mapping") instead of failing the gene. */
+#define SP_MAX_PATTERN_LEN 24576
 
 /* Concatenated ASCII sequences: sequence i = bases[offsets[i] .. offsets[i+1]).
  * Mirrors how the reference hands `&[u8]` sequences to Aligner::with_seq / map. */

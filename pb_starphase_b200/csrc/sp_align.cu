@@ -37,7 +37,7 @@ struct ClassPlan {
     int64_t slot_words = 4;
 };
 
-int lane_width_for(int64_t m) { return m <= 4096 ? 4 : m <= 8192 ? 8 : m <= 12288 ? 12 : 16; }
+int lane_width_for(int64_t m) { return m <= 4096 ? 4 : m <= 8192 ? 8 : m <= 12288 ? 12 : m <= 16384 ? 16 : m <= 20480 ? 20 : 24; }
 
 // best-fit decreasing over lane counts; pairs of equal lane count stay in order of decreasing text length, so the pairs
 // sharing a warp have similar pass lengths
@@ -180,10 +180,12 @@ extern "C" sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, con
     if (max_slot_words > (24ll << 30) / 4) return fail(ctx, SP_ERR_NOMEM, "sp_align_pairs: traceback scratch of one warp exceeds 24 GB");
 
     // ---- device buffers: scratch / CIGAR regions / blobs / dense pool live in the context's grow-only pools ----
-    static int occ_cache[4] = {0, 0, 0, 0};  // resident CTAs per SM of k4_align<4 / 8 / 12 / 16>
+    static int occ_cache[6] = {0, 0, 0, 0, 0, 0};  // resident CTAs per SM of k4_align<4 / 8 / 12 / 16 / 20 / 24>
     auto occupancy = [&](int U) -> int {
         int &o = occ_cache[U / 4 - 1];
-        if (!o) o = U == 4 ? class_occupancy<4>() : U == 8 ? class_occupancy<8>() : U == 12 ? class_occupancy<12>() : class_occupancy<16>();
+        if (!o)
+            o = U == 4 ? class_occupancy<4>() : U == 8 ? class_occupancy<8>() : U == 12 ? class_occupancy<12>() : U == 16 ? class_occupancy<16>()
+                : U == 20 ? class_occupancy<20>() : class_occupancy<24>();
         return o;
     };
     // scratch budget: a quarter of the memory that was free when the pool last had to grow, within [4, 16] GB.  cudaMemGetInfo
@@ -285,7 +287,9 @@ extern "C" sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, con
             case 4: SP_TRY(launch_class<4>(ctx, prm, grid)); break;
             case 8: SP_TRY(launch_class<8>(ctx, prm, grid)); break;
             case 12: SP_TRY(launch_class<12>(ctx, prm, grid)); break;
-            default: SP_TRY(launch_class<16>(ctx, prm, grid)); break;
+            case 16: SP_TRY(launch_class<16>(ctx, prm, grid)); break;
+            case 20: SP_TRY(launch_class<20>(ctx, prm, grid)); break;
+            default: SP_TRY(launch_class<24>(ctx, prm, grid)); break;
         }
     }
     ev_end(ctx, 4);

@@ -283,9 +283,11 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
 #ifndef SP_K1_MIN_BLOCKS
 #define SP_K1_MIN_BLOCKS 2
 #endif
+// lane widths above 16 exist for patterns longer than 16,384 rows only (DRB1-sized genomic alleles): one CTA per SM, ~190 registers
+__host__ __device__ constexpr int k1_min_blocks(int U) { return U <= 16 ? SP_K1_MIN_BLOCKS : 1; }
 
 template <int U, bool TRACK_END>
-__global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K1Params p) {
+__global__ void __launch_bounds__(K1_THREADS, k1_min_blocks(U)) k1_infix(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ ScoreLut lut;
@@ -335,7 +337,8 @@ __global__ void __launch_bounds__(K1_THREADS, SP_K1_MIN_BLOCKS) k1_infix(const K
 // src/cyp2d6/chaining.rs:69-81 and src/cyp2d6/haplotyper.rs:203-249.  One warp per pair, one pattern
 // per bin (lane width SPAN_U), text bytes read straight from global memory (the pair count is small).
 // ------------------------------------------------------------------------------------------
-constexpr int SPAN_U = 16;
+constexpr int SPAN_U = 16;       // patterns up to 16,384 rows
+constexpr int SPAN_U_LONG = 24;  // up to 24,576
 
 struct SpanParams {
     const uint32_t *blobs;   // [np] bins, reversed rows, prefix pad rows
@@ -352,9 +355,8 @@ struct SpanParams {
     unsigned long long *next_pair;  // work counter (zeroed by the host): pairs are handed out one at a time
 };
 
-#ifndef SP_NO_GLOBAL_KERNELS
+template <int U>
 __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams p) {
-    constexpr int U = SPAN_U;
     constexpr int BW = blob_words(U);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -420,8 +422,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
         if (nch == 0 && lane == 0) p.S[o] = e;  // empty window: the placement is empty, start == end
     }
 }
-
-#endif  // SP_NO_GLOBAL_KERNELS
 
 // ------------------------------------------------------------------------------------------
 // K3 chain windows: B[c][r] = min over windows s of chain c of sum_t W[r][t][chain_c[s + t]], or 2 * worst_r

@@ -140,6 +140,7 @@ sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_bases, long
 // ------------------------------------------------------------------------------------------
 // lane widths compiled into the library
 static const int kUmin = 4, kUmax = 16;
+static const int kULong[2] = {20, 24};  // only for pattern sets holding a pattern of more than 16,384 rows
 // modelled ALU-pipe instructions per text column of one warp (8 per word + per-column bookkeeping)
 static double warp_cost(int U) {
     static const double book = getenv("SP_PLAN_BOOK") ? atof(getenv("SP_PLAN_BOOK")) : 17.0;  // experiment hook
@@ -241,6 +242,11 @@ static bool choose_classes(const std::vector<int64_t> &lens, int max_classes, st
     const char *forceU = getenv("SP_FORCE_U");  // test hook: one fixed lane width
     for (int U = kUmin; U <= kUmax; ++U)
         if (!forceU || atoi(forceU) == U) cand.push_back(U);
+    int64_t longest = 0;
+    for (int64_t x : lens) longest = std::max(longest, x);
+    if (longest > 32ll * 32 * kUmax)
+        for (int U : kULong)
+            if (!forceU || atoi(forceU) == U) cand.push_back(U);
     if (forceU) max_classes = 1;
     std::vector<int> set;
     std::vector<std::vector<int32_t>> mem;
@@ -539,7 +545,7 @@ static sp_status dispatch_k1(sp_ctx *ctx, int U, const K1Params &prm, size_t sme
     switch (U) {
 #define SP_CASE(u) case u: return launch_k1<u, TE>(ctx, prm, smem, n_items, first, last)
         SP_CASE(4); SP_CASE(5); SP_CASE(6); SP_CASE(7); SP_CASE(8); SP_CASE(9); SP_CASE(10); SP_CASE(11);
-        SP_CASE(12); SP_CASE(13); SP_CASE(14); SP_CASE(15); SP_CASE(16);
+        SP_CASE(12); SP_CASE(13); SP_CASE(14); SP_CASE(15); SP_CASE(16); SP_CASE(20); SP_CASE(24);
 #undef SP_CASE
         default: return fail(ctx, SP_ERR_INVALID, "unsupported lane width");
     }
@@ -797,7 +803,10 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
         if (s__ != SP_OK) { cleanup(); return s__; } \
     } while (0)
     // reversed patterns, one per bin, anchored (prefix) pad rows
-    const int64_t rows = 32ll * SPAN_U;
+    int64_t longest = 0;
+    for (int64_t i = 0; i < np; ++i) longest = std::max(longest, patterns->offsets[i + 1] - patterns->offsets[i]);
+    const int span_u = longest > 32ll * 32 * SPAN_U ? SPAN_U_LONG : SPAN_U;
+    const int64_t rows = 32ll * span_u;
     const size_t tab = static_cast<size_t>(np) * 32;
     std::vector<int32_t> lane_pat(tab, -1), lane_row0(tab, 0);
     std::vector<uint32_t> lane_info1(tab, INFO_FIRST);
@@ -816,7 +825,7 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_pat), tab * 4), "cudaMalloc"));
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_row0), tab * 4), "cudaMalloc"));
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_lane_info1), tab * 4), "cudaMalloc"));
-    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(SPAN_U) * 4), "cudaMalloc span blobs"));
+    SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_blobs), static_cast<size_t>(np) * blob_words(span_u) * 4), "cudaMalloc span blobs"));
     SP_TRY(cu(dev_malloc(ctx, reinterpret_cast<void **>(&d_S), static_cast<size_t>(np * d->ld) * 4), "cudaMalloc span starts"));
     SP_TRY(cu(cudaMemsetAsync(d_S, 0, static_cast<size_t>(np * d->ld) * 4, ctx->stream), "memset"));
     std::vector<int32_t> plen(static_cast<size_t>(np));
@@ -829,9 +838,9 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
     SP_TRY(cu(cudaMemcpyAsync(d_lane_row0, lane_row0.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
     SP_TRY(cu(cudaMemcpyAsync(d_lane_info1, lane_info1.data(), tab * 4, cudaMemcpyHostToDevice, ctx->stream), "H2D"));
     {
-        const long long total_threads = static_cast<long long>(np) * 32 * SPAN_U;
+        const long long total_threads = static_cast<long long>(np) * 32 * span_u;
         pack_patterns<<<static_cast<int>((total_threads + 255) / 256), 256, 0, ctx->stream>>>(
-            d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1, d_blobs, static_cast<int>(np), SPAN_U, 1, 1);
+            d_bases, d_offs, d_lane_pat, d_lane_row0, d_lane_info1, d_blobs, static_cast<int>(np), span_u, 1, 1);
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "pack_patterns (reversed)"));
     }
@@ -841,12 +850,16 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
         prm.D = static_cast<const int32_t *>(d->d); prm.E = d->d_end; prm.S = d_S; prm.ld = d->ld;
         prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
         prm.max_dist_permille = max_dist_permille; prm.plen = d_plen; prm.next_pair = d_next;
-        const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(SPAN_U) * 4;
-        SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
-                  "k3_span_starts smem"));
+        const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(span_u) * 4;
         const long long total = nt * np;
         const int grid = static_cast<int>(std::min<long long>(2ll * ctx->num_sms, (total + K1_WARPS - 1) / K1_WARPS));
-        k3_span_starts<<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        if (span_u == SPAN_U) {
+            SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts<SPAN_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "k3_span_starts smem"));
+            k3_span_starts<SPAN_U><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        } else {
+            SP_TRY(cu(cudaFuncSetAttribute(k3_span_starts<SPAN_U_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "k3_span_starts smem"));
+            k3_span_starts<SPAN_U_LONG><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+        }
         ++ctx->launches;
         SP_TRY(cu(cudaGetLastError(), "k3_span_starts launch"));
     }
@@ -872,7 +885,7 @@ extern "C" sp_status sp_row_topk_biased(sp_ctx *ctx, const sp_dmatrix *d, const 
 extern "C" sp_status sp_row_topk_weighted(sp_ctx *ctx, const sp_dmatrix *d, int dist_weight, const int32_t *pattern_bias, int k,
                                           int32_t *idx, int32_t *dist) {
     if (!ctx) return SP_ERR_INVALID;
-    // the 32-bit key weight * distance + bias must not wrap: K1 distances are <= SP_MAX_PATTERN_LEN (2^14), biases < 2^30
+    // the 32-bit key weight * distance + bias must not wrap: K1 distances are <= SP_MAX_PATTERN_LEN (< 2^15), biases < 2^30
     if (dist_weight < 1 || dist_weight > 64) return fail(ctx, SP_ERR_INVALID, "sp_row_topk_weighted: dist_weight must be in [1, 64]");
     if (!d || !idx || !dist) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: NULL argument");
     if (k < 1 || k > 16) return fail(ctx, SP_ERR_INVALID, "sp_row_topk: k must be in [1, 16]");

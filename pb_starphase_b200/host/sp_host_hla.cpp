@@ -158,6 +158,7 @@ HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene
     for (const auto &kv : database) {
         if (std::find(gene_list.begin(), gene_list.end(), kv.second.gene_name) == gene_list.end()) continue;
         if (!kv.second.dna_sequence) continue;
+        if (kv.second.dna_sequence->size() > SP_MAX_PATTERN_LEN) { skipped_.push_back(kv.first); continue; }  // see HlaGeneIndex
         alleles_.push_back(&kv.second);
         seqs.push_back(*kv.second.dna_sequence);
     }
@@ -181,6 +182,7 @@ HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene
     for (const auto &kv : database) {
         if (std::find(gene_list.begin(), gene_list.end(), kv.second.gene_name) == gene_list.end()) continue;
         if (!kv.second.dna_sequence) continue;
+        if (kv.second.dna_sequence->size() > SP_MAX_PATTERN_LEN) { skipped_.push_back(kv.first); continue; }
         alleles_.push_back(&kv.second);
         const bool fwd = gene_definitions_.at(kv.second.gene_name).is_forward_strand;
         seqs.push_back(fwd ? *kv.second.dna_sequence : reverse_complement(*kv.second.dna_sequence));  // :511-515
@@ -429,6 +431,12 @@ HlaGeneIndex::HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const s
         if (is_allowed_allele_def(kv.second, gene_name, settings)) {
             if (!kv.second.dna_sequence)
                 throw HostError("diplotype_hla_gene: allele " + kv.first + " has no DNA sequence (pair ranking needs hla_require_dna)");
+            if (kv.second.dna_sequence->size() > SP_MAX_PATTERN_LEN || kv.second.cdna_sequence.size() > SP_MAX_PATTERN_LEN) {
+                // the device formats hold patterns up to SP_MAX_PATTERN_LEN rows; a longer allele is left out of the index (it
+                // cannot be called) instead of failing the whole gene -- the reference's aligner has no such limit
+                skipped_.push_back(kv.first);
+                continue;
+            }
             gene_db_.emplace(kv.first, kv.second);
         }
     SeqList cdna;

@@ -432,8 +432,10 @@ class HlaRealigner {  // src/hla/realigner.rs:22-350
                                                         int n_candidates = 5);
     size_t n_alleles() const { return alleles_.size(); }
     const PatternSet &index() const { return *index_; }
+    const std::vector<std::string> &skipped_alleles() const { return skipped_; }  // longer than SP_MAX_PATTERN_LEN: not in the index
 
   private:
+    std::vector<std::string> skipped_;
     struct BestHit { int allele = -1; MappingStats stats; Alignment aln; };
     // resident_reads: the reads as already uploaded for K1 (nullptr: uploaded here)
     std::vector<BestHit> best_hits(const std::vector<std::pair<std::string, std::string>> &reads, const DeviceMatrix &D, int n_candidates,
@@ -468,8 +470,11 @@ class HlaGeneIndex {
     HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const DiplotypeSettings &settings);
     const std::string &gene_name() const { return gene_name_; }
     size_t n_alleles() const { return allowed_.size(); }
+    // alleles longer than SP_MAX_PATTERN_LEN: left out of the index (cannot be called), listed here for the caller's warning
+    const std::vector<std::string> &skipped_alleles() const { return skipped_; }
 
   private:
+    std::vector<std::string> skipped_;
     friend HlaGeneCall diplotype_hla_gene(GpuAligner &, HlaGeneIndex &, const std::vector<HlaRead> &, const DiplotypeSettings &);
     std::string gene_name_;
     HlaDatabase gene_db_;  // owns the allele definitions the realigner points to

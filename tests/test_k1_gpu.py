@@ -152,8 +152,26 @@ def test_empty_inputs(ctx):
 
 def test_too_long_pattern_is_an_error(ctx):
     with pytest.raises(sp.SpError) as ei:
-        ctx.score_batch([b"ACGT"], [b"A" * 20000])
+        ctx.score_batch([b"ACGT"], [b"A" * 24577])
     assert ei.value.status == 3
+
+
+def test_class_ii_sized_alleles(ctx, oracle):
+    """ADVICE r1: DRB1-sized genomic alleles (11-17 kb) next to ordinary ones.  Lane widths 20 / 24 hold patterns up to 24,576 rows;
+    K1 distances and end columns, K3 spans and K4 tracebacks stay bit-exact against the oracle."""
+    rng = np.random.default_rng(41)
+    big = rnd(rng, 17011)
+    pats = [big, noisy_copy(rng, big, 40)[:16385], noisy_copy(rng, big, 9), rnd(rng, 3100), big[2000:14000], rnd(rng, 24576)]
+    texts = [rnd(rng, 300) + noisy_copy(rng, big, 25) + rnd(rng, 200), big[500:16000], rnd(rng, 5000)]
+    D, E = ctx.score_batch(texts, pats, want_end_col=True)
+    Dw, Ew = oracle.score_batch(texts, pats, want_end_col=True)
+    assert (D == Dw).all() and (E == Ew).all()
+    got = ctx.score_spans(texts[:2], pats[:3])
+    for g, w, name in zip(got, oracle.score_spans(texts[:2], pats[:3]), ("distance", "start", "end")):
+        assert (g == w).all(), name
+    pairs = [(0, 0), (0, 1), (1, 2), (0, 3), (1, 4)]
+    for (t, p), g in zip(pairs, ctx.align_pairs(texts, pats, pairs)):
+        assert g == oracle.align(pats[p], texts[t]), (t, p)
 
 
 def test_cyp2d6_shapes_roles_swapped(ctx, oracle):

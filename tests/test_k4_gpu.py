@@ -123,5 +123,5 @@ def test_align_bad_arguments(ctx):
     with pytest.raises(sp.SpError):
         ctx.align_pairs([b"ACGT"], [b"AC"], [(1, 0)])
     with pytest.raises(sp.SpError):
-        ctx.align_pairs([b"ACGT"], [b"A" * 20000], [(0, 0)])
+        ctx.align_pairs([b"ACGT"], [b"A" * 24577], [(0, 0)])
     assert ctx.align_pairs([b"ACGT"], [b"AC"], []) == []
