@@ -33,6 +33,7 @@ struct sp_ctx {
     void *pool[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pool_bytes[4] = {0, 0, 0, 0};
     int *d_counter = nullptr;  // K1's work counter
+    cudaMemPool_t mempool = nullptr;  // private stream-ordered pool (release threshold lifted on it, not on the device's default pool)
     // grow-only page-locked staging for the small per-call tables (plan tables of K4): pageable H2D copies are staged by the
     // driver one by one and cost more than the kernels they feed
     void *h_stage = nullptr;
@@ -76,11 +77,13 @@ static inline cudaError_t ctx_pool(sp_ctx *ctx, int which, size_t bytes, void **
 }
 static inline cudaError_t ctx_scratch(sp_ctx *ctx, size_t bytes, void **out) { return ctx_pool(ctx, 0, bytes, out); }
 
-// Every other device buffer is stream-ordered (cudaMallocAsync / cudaFreeAsync on the context stream, the device's
-// default memory pool with its release threshold lifted in sp_ctx_create): plain cudaFree synchronises the device and
-// was measured at up to 450 ms per call next to multi-GB allocations.
+// Every other device buffer is stream-ordered (cudaMallocFromPoolAsync / cudaFreeAsync on the context stream, from a memory
+// pool the context owns, its release threshold lifted in sp_ctx_create): plain cudaFree synchronises the device and was
+// measured at up to 450 ms per call next to multi-GB allocations.
 template <typename T>
 static inline cudaError_t dev_malloc(sp_ctx *ctx, T **p, size_t bytes) {
+    // the context's own pool when it could be created (freed blocks stay with this library and nobody else's pool is touched)
+    if (ctx->mempool) return cudaMallocFromPoolAsync(reinterpret_cast<void **>(p), bytes, ctx->mempool, ctx->stream);
     return cudaMallocAsync(reinterpret_cast<void **>(p), bytes, ctx->stream);
 }
 static inline void dev_free(sp_ctx *ctx, void *p) {

@@ -443,9 +443,9 @@ struct ChainWinParams {
 #ifndef SP_NO_GLOBAL_KERNELS
 __global__ void __launch_bounds__(256) k3_chain_windows(const ChainWinParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
     if (r >= p.n_reads) return;
     const int s0 = p.seg_off[r], w = p.seg_off[r + 1] - s0;
+    for (int c = blockIdx.y; c < p.n_chains; c += gridDim.y) {  // grid.y is capped at 65,535: stride over the chains
     const int c0 = p.chain_off[c], len = p.chain_off[c + 1] - c0;
     uint32_t best;
     if (len < w) {
@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(256) k3_chain_windows(const ChainWinParams p) 
         best = min(best, 0x7FFFFFFFu);
     }
     p.B[static_cast<long long>(c) * p.ld + r] = static_cast<int32_t>(best);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -59,10 +59,20 @@ extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
     }
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
-    cudaMemPool_t mempool = nullptr;  // keep freed blocks in the pool instead of returning them to the OS at every sync
-    if (cudaDeviceGetDefaultMemPool(&mempool, device) == cudaSuccess) {
-        unsigned long long threshold = ~0ull;
-        cudaMemPoolSetAttribute(mempool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    // a private pool: freed blocks stay here instead of going back to the OS at every synchronisation, and the default pool of
+    // the embedding process (torch, NCCL, the Rust host) keeps its own settings
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->mempool, &props) == cudaSuccess) {
+            unsigned long long threshold = ~0ull;
+            cudaMemPoolSetAttribute(ctx->mempool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        } else {
+            ctx->mempool = nullptr;  // falls back to the device's default pool, untouched
+        }
     }
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) {
@@ -83,6 +93,7 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     for (void *p : ctx->pool) cudaFree(p);
     cudaFree(ctx->d_counter);
     cudaFreeHost(ctx->h_stage);
+    if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     delete ctx;
 }
 
@@ -124,14 +135,18 @@ sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_bases, long
     const int64_t nbytes = s->n ? s->offsets[s->n] - base0 : 0;
     std::vector<long long> offs(static_cast<size_t>(s->n) + 1);
     for (int64_t i = 0; i <= s->n; ++i) offs[static_cast<size_t>(i)] = s->n ? s->offsets[i] - base0 : 0;
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(d_bases), static_cast<size_t>(std::max<int64_t>(nbytes, 16))));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(d_offs), offs.size() * sizeof(long long)));
-    if (nbytes)
-        SP_CUDA(ctx, cudaMemcpyAsync(*d_bases, s->bases + base0, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice,
-                                     ctx->stream));
-    SP_CUDA(ctx, cudaMemcpyAsync(*d_offs, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice,
-                                 ctx->stream));
-    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a stack-owned vector
+    *d_bases = nullptr; *d_offs = nullptr;
+    cudaError_t e = dev_malloc(ctx, reinterpret_cast<void **>(d_bases), static_cast<size_t>(std::max<int64_t>(nbytes, 16)));
+    if (e == cudaSuccess) e = dev_malloc(ctx, reinterpret_cast<void **>(d_offs), offs.size() * sizeof(long long));
+    if (e == cudaSuccess && nbytes)
+        e = cudaMemcpyAsync(*d_bases, s->bases + base0, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*d_offs, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // offs is a stack-owned vector
+    if (e != cudaSuccess) {  // nothing stays behind on the error path
+        dev_free(ctx, *d_bases); dev_free(ctx, *d_offs);
+        *d_bases = nullptr; *d_offs = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA, std::string("sequence upload: ") + cudaGetErrorString(e));
+    }
     return SP_OK;
 }
 
@@ -491,33 +506,45 @@ static sp_status get_text_pack(sp_ctx *ctx, sp_targets *t, int tc, const TextPac
     TextPack pk;
     pk.tc = tc; pk.n_tiles = static_cast<int>(tile_text0.size()); pk.total_chunks = cur;
     int32_t *d_chunk0 = nullptr, *d_nch = nullptr;
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_text), static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_off), tile_off.size() * 4));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_text0), std::max<size_t>(tile_text0.size(), 1) * 4));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_chunk0), std::max<size_t>(text_chunk0.size(), 1) * 4));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_nch), std::max<size_t>(t->nch.size(), 1) * 4));
-    SP_CUDA(ctx, cudaMemsetAsync(pk.d_text, 0x04, static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8, ctx->stream));
-    SP_CUDA(ctx, cudaMemcpyAsync(pk.d_tile_off, tile_off.data(), tile_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // on any CUDA error below nothing stays allocated (the pack is not cached either)
+#define SP_PACK_CUDA(call)                                                                                       \
+    do {                                                                                                         \
+        cudaError_t e__ = (call);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            dev_free(ctx, pk.d_text); dev_free(ctx, pk.d_tile_off); dev_free(ctx, pk.d_tile_text0);              \
+            dev_free(ctx, d_chunk0); dev_free(ctx, d_nch);                                                       \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA,                      \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                                    \
+        }                                                                                                        \
+    } while (0)
+    SP_PACK_CUDA(dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_text), static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8));
+    SP_PACK_CUDA(dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_off), tile_off.size() * 4));
+    SP_PACK_CUDA(dev_malloc(ctx, reinterpret_cast<void **>(&pk.d_tile_text0), std::max<size_t>(tile_text0.size(), 1) * 4));
+    SP_PACK_CUDA(dev_malloc(ctx, reinterpret_cast<void **>(&d_chunk0), std::max<size_t>(text_chunk0.size(), 1) * 4));
+    SP_PACK_CUDA(dev_malloc(ctx, reinterpret_cast<void **>(&d_nch), std::max<size_t>(t->nch.size(), 1) * 4));
+    SP_PACK_CUDA(cudaMemsetAsync(pk.d_text, 0x04, static_cast<size_t>(std::max<int64_t>(cur, 2)) * 8, ctx->stream));
+    SP_PACK_CUDA(cudaMemcpyAsync(pk.d_tile_off, tile_off.data(), tile_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (!tile_text0.empty())
-        SP_CUDA(ctx, cudaMemcpyAsync(pk.d_tile_text0, tile_text0.data(), tile_text0.size() * 4, cudaMemcpyHostToDevice,
+        SP_PACK_CUDA(cudaMemcpyAsync(pk.d_tile_text0, tile_text0.data(), tile_text0.size() * 4, cudaMemcpyHostToDevice,
                                      ctx->stream));
     if (t->n) {
-        SP_CUDA(ctx, cudaMemcpyAsync(d_chunk0, text_chunk0.data(), text_chunk0.size() * 4, cudaMemcpyHostToDevice,
+        SP_PACK_CUDA(cudaMemcpyAsync(d_chunk0, text_chunk0.data(), text_chunk0.size() * 4, cudaMemcpyHostToDevice,
                                      ctx->stream));
-        SP_CUDA(ctx, cudaMemcpyAsync(d_nch, t->nch.data(), t->nch.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SP_PACK_CUDA(cudaMemcpyAsync(d_nch, t->nch.data(), t->nch.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         const int blocks = static_cast<int>(std::min<int64_t>(t->n, 65535));
         ev_begin(ctx, 3);
         pack_texts<<<blocks, 128, 0, ctx->stream>>>(t->d_bases, t->d_offs, d_chunk0, d_nch, pk.d_text,
                                                     static_cast<int>(t->n));
         ev_end(ctx, 3);
         ++ctx->launches;
-        SP_CUDA(ctx, cudaGetLastError());
+        SP_PACK_CUDA(cudaGetLastError());
     }
-    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    SP_PACK_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     dev_free(ctx, d_chunk0); dev_free(ctx, d_nch);
     auto ins = t->packs.emplace(tc, pk);
     *out = &ins.first->second;
     return SP_OK;
+#undef SP_PACK_CUDA
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1011,7 +1038,7 @@ extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const
         (n_reads > 0 && (!seg_off || !W)))
         return fail(ctx, SP_ERR_INVALID, "sp_chain_window_scores: bad argument");
     *out = nullptr;
-    if (n_chains > 65535 * 32ll || n_reads > 0x7FFFFFF0ll || n_haps > 0x7FFFFFF0ll)
+    if (n_chains > 0x7FFFFFF0ll || n_reads > 0x7FFFFFF0ll || n_haps > 0x7FFFFFF0ll)
         return fail(ctx, SP_ERR_RANGE, "sp_chain_window_scores: too many chains / reads");
     const int64_t n_items = n_chains ? chain_off[n_chains] : 0, n_segs = n_reads ? seg_off[n_reads] : 0;
     for (int64_t c = 0; c < n_chains; ++c)
@@ -1043,7 +1070,7 @@ extern "C" sp_status sp_chain_window_scores(sp_ctx *ctx, int64_t n_chains, const
         prm.chain_off = d_coff; prm.chain_items = d_items; prm.seg_off = d_soff; prm.W = d_W;
         prm.B = static_cast<int32_t *>(d->d); prm.ld = d->ld;
         prm.n_chains = static_cast<int>(n_chains); prm.n_reads = static_cast<int>(n_reads); prm.n_haps = static_cast<int>(n_haps);
-        const dim3 grid(static_cast<unsigned>((n_reads + 255) / 256), static_cast<unsigned>(n_chains));
+        const dim3 grid(static_cast<unsigned>((n_reads + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n_chains, 65535)));
         k3_chain_windows<<<grid, 256, 0, ctx->stream>>>(prm);
         ++ctx->launches;
         e = cudaGetLastError();
@@ -1129,9 +1156,9 @@ extern "C" sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const
         ij[2 * q + 1] = static_cast<uint32_t>(cand[q].ij & 0xFFFFFFFFu);
     }
     uint32_t *d_ij = nullptr, *d_c1 = nullptr;
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_ij), ij.size() * 4));
-    SP_CUDA(ctx, dev_malloc(ctx, reinterpret_cast<void **>(&d_c1), c1.size() * 4));
-    e = cudaMemcpyAsync(d_ij, ij.data(), ij.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    e = dev_malloc(ctx, reinterpret_cast<void **>(&d_ij), ij.size() * 4);
+    if (e == cudaSuccess) e = dev_malloc(ctx, reinterpret_cast<void **>(&d_c1), c1.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ij, ij.data(), ij.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         if (d->elem_bits == 16)
             k2_count_c1<uint16_t><<<static_cast<unsigned>(kk), 256, 0, ctx->stream>>>(

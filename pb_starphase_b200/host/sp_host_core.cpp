@@ -11,6 +11,12 @@
 
 namespace starphase {
 
+AlignerStandIns &aligner_stand_ins() {
+    static AlignerStandIns s;
+    return s;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Json: serde_json::ser::PrettyFormatter (empty containers print as [] / {})
 // ------------------------------------------------------------------------------------------

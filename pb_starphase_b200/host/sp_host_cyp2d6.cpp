@@ -262,7 +262,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const size_t row = seg_index.at(std::make_tuple(it.seq, it.lo, it.hi));
             const size_t m = tmpl_seqs[it.tmpl].size();
             const size_t d = static_cast<size_t>(D[row * nt + it.tmpl]), e = static_cast<size_t>(E[row * nt + it.tmpl]);
-            if (m == 0 || 2 * d > m) continue;  // more than half of the template unexplained: nothing minimap2 would report
+            if (m == 0 || (aligner_stand_ins().template_half_prefilter && 2 * d > m)) continue;  // more than half of the template unexplained: nothing minimap2 would report
             const size_t w0 = e > m + d ? e - (m + d) : 0;
             pairs.emplace_back(static_cast<int32_t>(it.seq), static_cast<int32_t>(it.tmpl));
             windows.emplace_back(static_cast<int32_t>(it.lo + w0), static_cast<int32_t>(it.lo + e));
@@ -277,7 +277,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const Alignment &a = alns[q];
             const Item &it = pair_item[q];
             const size_t m = tmpl_seqs[it.tmpl].size();
-            if (a.cigar.empty() || dp_score(a.cigar, 1) < 200) continue;  // no mapping reported
+            if (a.cigar.empty() || dp_score(a.cigar, 1) < aligner_stand_ins().min_dp_score) continue;  // no mapping reported
             const size_t clipped_start = static_cast<size_t>(a.p_start), clipped_end = m - static_cast<size_t>(a.p_end);
             MappingStats st(m, static_cast<size_t>(a.nm), m - static_cast<size_t>(a.p_end - a.p_start));
             st.clipped_start = clipped_start; st.clipped_end = clipped_end;  // new_with_clippings, :214-217
@@ -475,7 +475,7 @@ std::vector<SequenceWeights> weight_sequences(GpuAligner &gpu, const SeqList &se
     // pattern = read segment (must be explained completely, chaining.rs:66), text = consensus (free ends, its clips form the overlap)
     // minimap2 reports nothing for sequences that far apart (unrelated DNA sits near 50 % unit-cost distance); the exhaustive
     // aligner always finds some placement, so pairs above 35 % count as "no mapping" and keep the default (|S|, 0.0) of :41
-    const int kNoMappingPermille = 350;
+    const int kNoMappingPermille = aligner_stand_ins().no_mapping_permille;
     std::vector<int32_t> D, S, E;
     gpu.score_spans(consensuses, segments, D, S, E, kNoMappingPermille);
     const size_t ns = segments.size(), nc = consensuses.size();

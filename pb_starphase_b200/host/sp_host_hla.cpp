@@ -110,7 +110,7 @@ ScoreReadResult score_consensus(GpuAligner &gpu, const std::string &reference_se
     const std::vector<Alignment> alns = gpu.align_pairs({reference_sequence}, {consensus}, {{0, 0}});
     std::vector<Mapping> mappings;
     const Alignment &a = alns.at(0);
-    if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {
+    if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {
         Mapping m;
         m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = consensus.size();
         m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = reference_sequence.size();
@@ -190,7 +190,6 @@ HlaRealigner::HlaRealigner(GpuAligner &gpu, const std::vector<std::string> &gene
     index_ = gpu.prepare_patterns(seqs);
 }
 
-constexpr int kCandidateEditWeight = 5;  // b + a of the map-hifi preset: what one edit costs in alignment score, relative to a match
 
 // The selection loop of realign_record (src/hla/realigner.rs:116-146) for every read: the n best alleles by distance (K5)
 // get a traceback (K4); minimap2's target is the allele here, so `unmapped` is allele-side.  The db_aligner is the plain
@@ -209,7 +208,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
         throw HostError("realign_records_scored: distance matrix has the wrong shape");
     // the best_n hits of every read (K5): minimap2 ranks its hits by alignment score, which under map-hifi (a = 1, b = 4, gaps
     // dearer) is about (allele bases aligned) - 5 x edits; the candidates are therefore the alleles with the smallest
-    // kCandidateEditWeight * (nm + unmapped) - |allele|, ties by database order.  A read covering part of a long allele keeps that
+    // candidate_edit_weight (5 = b + a) * (nm + unmapped) - |allele|, ties by database order.  A read covering part of a long allele keeps that
     // allele ahead of short alleles lying wholly inside the read, and an allele with fewer edits ahead of a longer one with more.
     // Measured against the affine cost model: weight 5 -> 91 of 96 read assignments agree, weight 1 -> 83 of 96.
     const int k = std::max(1, std::min(n_candidates, 16));
@@ -219,7 +218,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
     std::vector<int32_t> bias(A);
     for (size_t a = 0; a < A; ++a) bias[a] = static_cast<int32_t>(max_len - allele_seqs[a].size());
     std::vector<int32_t> cand, cand_dist;
-    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist, &bias, kCandidateEditWeight);
+    if (A && !reads.empty()) gpu_.row_topk(D, k, cand, cand_dist, &bias, aligner_stand_ins().candidate_edit_weight);
     std::vector<std::pair<int32_t, int32_t>> pairs;
     std::vector<size_t> first_pair(reads.size() + 1, 0);
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -239,7 +238,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
         b.stats = MappingStats(read_len, read_len, 0);  // src/hla/realigner.rs:124
         for (size_t q = first_pair[r]; q < first_pair[r + 1]; ++q) {
             Alignment &a = alns[q];
-            if (a.cigar.empty() || dp_score(a.cigar, 1) < 200) continue;  // no hit reported
+            if (a.cigar.empty() || dp_score(a.cigar, 1) < aligner_stand_ins().min_dp_score) continue;  // no hit reported
             const size_t target_len = allele_seqs[static_cast<size_t>(pairs[q].second)].size();
             const size_t unmapped = target_len - static_cast<size_t>(a.p_end - a.p_start);
             const MappingStats stats(target_len, static_cast<size_t>(a.nm), unmapped);
@@ -347,7 +346,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         const std::string &ref = ref_texts[static_cast<size_t>(seg_pairs[q].first)];
         std::vector<Mapping> mappings;
         const Alignment &a = seg_alns[q];
-        if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {  // (query, target) = (read segment, hg38) = (pattern, text)
+        if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {  // (query, target) = (read segment, hg38) = (pattern, text)
             Mapping m;
             m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = seg_patterns[q].size();
             m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = ref.size();
@@ -385,7 +384,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         if (p.allele_pair >= 0) {
             const Alignment &a = allele_alns[static_cast<size_t>(p.allele_pair)];
             std::vector<Mapping> mappings;
-            if (!a.cigar.empty() && dp_score(a.cigar, 1) >= 200) {
+            if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {
                 Mapping m;
                 m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end);
                 m.query_len = allele_patterns[static_cast<size_t>(allele_pairs[static_cast<size_t>(p.allele_pair)].second)].size();

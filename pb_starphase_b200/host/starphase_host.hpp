@@ -277,6 +277,20 @@ class GpuAligner {
 };
 
 // ------------------------------------------------------------------------------------------
+// Stand-ins for decisions minimap2 makes inside the reference and an exhaustive aligner cannot copy: whether a mapping is
+// reported at all, and which five hits of an index come back.  They have no counterpart in the reference's own code; each is
+// measured against the affine cost model in DESIGN.md 3 and listed as a known deviation in INTEGRATION.md.  One process-wide
+// set, adjustable by the embedding host.
+// ------------------------------------------------------------------------------------------
+struct AlignerStandIns {
+    long min_dp_score = 200;        // minimap2 -s of map-hifi: a K4 path scoring less (a=1|5 b=4 q=6 e=2 q2=26 e2=1) counts as "no mapping"
+    int no_mapping_permille = 350;  // weight_sequence: (segment, consensus) pairs further apart than this share of the segment have no hit
+    int candidate_edit_weight = 5;  // realigner candidates: smallest weight * (nm + unmapped) - |allele| (map-hifi: one edit ~ b + a = 5)
+    bool template_half_prefilter = true;  // template search: pairs with more than half the template unexplained skip the traceback
+};
+AlignerStandIns &aligner_stand_ins();
+
+// ------------------------------------------------------------------------------------------
 // HLA
 // ------------------------------------------------------------------------------------------
 struct HlaAlleleDefinition {  // the members of src/hla/alleles.rs the path reads
