@@ -340,15 +340,30 @@ def run_ours(args):
             out[gene] = (vc, vd)
         return out
 
+    phases = os.environ.get("SP_BENCH_PHASES") == "1"  # debug: wall-clock phases of every step to stderr (synchronises each phase)
+
     def device_step(T_dna, T_cdna, gv, keep=False):
+        marks = [time.perf_counter()]
+
+        def mark():
+            if phases:
+                ctx.synchronize()
+                marks.append(time.perf_counter())
+
         Dd = comm.score_allgather(T_dna, P_dna, idx_d, n_dna, 16)      # K1 on this rank's shard + ncclAllGather + row permutation
         k1_ms.append(ctx.last_kernel_ms(0))
+        mark()
         Dc = comm.score_allgather(T_cdna, P_cdna, idx_c, n_cdna, 16)
+        mark()
         out = {}
         views = gene_views(Dd, Dc, gv)
         for gene, (vc, vd) in views.items():
             out[gene] = comm.pair_minsum_topk(vc, TOPK, d2=vd)         # K2 on this rank's row block + record all-gather + merge
             vc.close(); vd.close()
+            mark()
+        if phases:
+            print(f"rank {rank} step phases ms: dna+gather {1e3 * (marks[1] - marks[0]):.1f} (k1 {k1_ms[-1]:.1f}) cdna+gather {1e3 * (marks[2] - marks[1]):.1f} "
+                  + " ".join(f"k2[{g}] {1e3 * (b - a):.1f}" for g, a, b in zip(views, marks[2:], marks[3:])), file=sys.stderr)
         if keep:
             return out, Dd, Dc
         Dd.close(); Dc.close()
