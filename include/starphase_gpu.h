@@ -308,6 +308,20 @@ sp_status sp_consensus_reset(sp_consensus *c, int32_t track);
 sp_status sp_consensus_extend(sp_consensus *c, int32_t n_tasks, const int32_t *src, const uint8_t *symbols, const int32_t *dst,
                               int32_t *ed, uint8_t *votes, int32_t *full);
 
+/* ---- K8: sequence-to-variant-graph alignment (row N3 of SURVEY.md 8f) ------------------------- */
+/* The forward half of what Cyp2d6Extractor::assign_haplotype gets from hiphase's WFAGraph::edit_distance_with_pruning
+ * (src/cyp2d6/haplotyper.rs:430-450): the unit-cost end-to-end alignment of a sequence to a graph of the CYP2D6 backbone with one
+ * bubble per database variant, for a batch of (graph, sequence) problems.  Graphs arrive linearised (host/sp_host_graph.cpp
+ * builds them): position = one character; preds[pred_off[q] .. pred_off[q+1]) = the problem-local positions a path can come
+ * from (-1 = before the first character), all smaller than q; diag[q] = the sequence row the position is expected to align to
+ * (band centre); ends = positions at which a path may end.  Offsets are global over the concatenated problems and start at 0.
+ * score[p] = the edit distance (0x3FFFFFFF when the band excludes every path); columns (optional, host memory,
+ * [total positions][2 * band + 1] int32) = the DP matrix, row i of position q at index i - diag[q] + band, from which the host
+ * marks the cells and nodes on optimal alignments (`traversed_nodes`, :454-468). */
+sp_status sp_graph_align(sp_ctx *ctx, int32_t n_problems, const uint8_t *gchars, const int64_t *gchar_off, const int32_t *pred_off,
+                         const int32_t *preds, const int32_t *diag, const int32_t *end_off, const int32_t *ends, const uint8_t *seqs,
+                         const int64_t *seq_off, int32_t band, int32_t *score, int32_t *columns);
+
 /* ---- multi-GPU: the path over the GPUs of one box ------------------------ */
 /* The reference is one process on one thread (src/cli/diplotype.rs:185-191) and has no distributed code; the north_star
  * partitions this path as: allele set sharded for K1, read set broadcast, allele-pair row blocks sharded for K2, per-shard

@@ -17,6 +17,7 @@ UNITS = {
     "sp_align.cu": HEADERS + ["sp_align.cuh"],       # K4
     "sp_comm.cu": HEADERS + ["sp_comm_kernels.cuh"],  # multi-GPU (NCCL, loaded with dlopen at run time)
     "sp_consensus.cu": HEADERS + ["sp_consensus.cuh"],  # K7
+    "sp_graph.cu": HEADERS + ["sp_graph.cuh"],  # K8
 }
 OBJDIR = CSRC / "build"
 
@@ -76,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 # ---------------------------------------------------------------------------------------------
 HOST = HERE / "host"
 HOST_LIB = HERE / "libstarphase_host.so"
-HOST_SOURCES = ["sp_host_core.cpp", "sp_host_gpu.cpp", "sp_host_hla.cpp", "sp_host_cyp2d6.cpp", "sp_host_debug.cpp", "sp_host_consensus.cpp"]
+HOST_SOURCES = ["sp_host_core.cpp", "sp_host_gpu.cpp", "sp_host_hla.cpp", "sp_host_cyp2d6.cpp", "sp_host_debug.cpp", "sp_host_consensus.cpp", "sp_host_graph.cpp"]
 
 
 def host_module_path() -> Path:

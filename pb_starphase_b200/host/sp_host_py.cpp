@@ -40,6 +40,21 @@ PYBIND11_MODULE(_starphase_host, m) {
 
     py::class_<Json>(m, "Json").def("pretty", [](const Json &j) { return j.pretty(); });
 
+    // variant graph typing (K8 + host walk back): (backbone, region_start, [(pos, ref, alt)], sequences, band)
+    m.def("graph_typing", [](GpuAligner &g, const std::string &backbone, size_t region_start,
+                             const std::vector<std::tuple<size_t, std::string, std::string>> &variants, const SeqList &sequences, size_t band) {
+        std::vector<GraphVariant> vs;
+        for (const auto &v : variants) vs.push_back({std::get<0>(v), std::get<1>(v), std::get<2>(v)});
+        const VariantGraph graph = VariantGraph::from_reference_variants(backbone, region_start, vs);
+        std::vector<const VariantGraph *> gs(sequences.size(), &graph);
+        py::list out;
+        for (const GraphAlignment &a : graph_edit_distance(g, gs, sequences, band))
+            out.append(py::make_tuple(a.found, a.score, a.traversed_nodes, graph_alleles(graph, a, vs.size())));
+        py::list nodes;
+        for (size_t k = 0; k < graph.seqs.size(); ++k) nodes.append(py::make_tuple(py::bytes(graph.seqs[k]), graph.preds[k], graph.coord[k]));
+        return py::make_tuple(out, nodes, graph.node_to_alleles, graph.sink);
+    });
+
     // consensus (K7 + host search): (sequences, offsets or None, config dict) -> solutions
     auto cfg_from = [](const py::dict &d) {
         CdwfaConfig c;

@@ -22,6 +22,7 @@
 //   src/hla/caller.rs:1583-1653                     is_hemizygous_better
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <optional>
@@ -663,6 +664,37 @@ Cyp2d6Call call_cyp2d6_chains(GpuAligner &gpu, const Cyp2d6Config &cfg, const Se
 // cyp2d6_alleles.json (DeeplotypeDebug, src/cyp2d6/debug.rs:8-71): the three forms of both haplotypes + the variants of every typed allele
 std::string cyp2d6_alleles_json(const std::vector<std::vector<size_t>> &best_diplotype_indices, const std::vector<Cyp2d6Region> &hap_regions,
                                 const std::map<std::string, std::string> &cyp_translate);
+
+// ------------------------------------------------------------------------------------------
+// variant graph typing (row N3 of SURVEY.md 8f) -- what assign_haplotype gets from hiphase's WFAGraph
+// (src/cyp2d6/haplotyper.rs:430-468): graph of the backbone with one bubble per variant, end-to-end edit distance of a consensus
+// (forward DP on the device, K8), the nodes on optimal alignments, and from them the 0 / 1 / 2 / 3 allele vector K6 scores.
+// ------------------------------------------------------------------------------------------
+struct GraphVariant {  // position in reference coordinates, VCF-style alleles; the order of the list defines the variant indices
+    size_t position = 0;
+    std::string ref_allele, alt_allele;
+};
+struct VariantGraph {
+    std::vector<std::string> seqs;            // node sequences (only the unlabelled source / sink may be empty)
+    std::vector<std::vector<size_t>> preds;   // predecessor nodes
+    std::vector<size_t> coord;                // backbone offset at which the node starts
+    std::map<size_t, std::vector<std::pair<size_t, uint8_t>>> node_to_alleles;  // NodeAlleleMap of the reference (:431)
+    size_t sink = 0;
+    // WFAGraph::from_reference_variants(chrom_seq, variants, start, end) (:432-441): backbone = reference[region_start, +len)
+    static VariantGraph from_reference_variants(const std::string &backbone, size_t region_start, const std::vector<GraphVariant> &variants);
+    size_t get_num_nodes() const { return seqs.size(); }
+    size_t add(std::string seq, std::vector<size_t> preds, size_t coord);
+};
+struct GraphAlignment {  // WFAResult: score() and traversed_nodes()
+    bool found = false;   // false: the band excluded every path
+    size_t score = 0;
+    std::vector<size_t> traversed_nodes;
+};
+// edit_distance_with_pruning for a batch: one (graph, sequence) problem per entry, one device call
+std::vector<GraphAlignment> graph_edit_distance(GpuAligner &gpu, const std::vector<const VariantGraph *> &graphs, const SeqList &sequences,
+                                                size_t band = 128);
+// :452-468: the allele of every variant from the traversed nodes (3 unset, 2 both alleles on optimal alignments)
+std::vector<uint8_t> graph_alleles(const VariantGraph &g, const GraphAlignment &aln, size_t num_variants);
 
 // ------------------------------------------------------------------------------------------
 // consensus (row N1 of SURVEY.md 8f) -- the interface of waffle_con's ConsensusDWFA / DualConsensusDWFA as the reference uses it

@@ -120,6 +120,10 @@ extern "C" {
     pub fn sp_consensus_reset(c: *mut sp_consensus, track: i32) -> c_int;
     pub fn sp_consensus_extend(c: *mut sp_consensus, n_tasks: i32, src: *const i32, symbols: *const u8, dst: *const i32, ed: *mut i32,
                                votes: *mut u8, full: *mut i32) -> c_int;
+    // K8: sequence-to-variant-graph alignment
+    pub fn sp_graph_align(ctx: *mut sp_ctx, n_problems: i32, gchars: *const u8, gchar_off: *const i64, pred_off: *const i32, preds: *const i32,
+                          diag: *const i32, end_off: *const i32, ends: *const i32, seqs: *const u8, seq_off: *const i64, band: i32,
+                          score: *mut i32, columns: *mut i32) -> c_int;
     // multi-GPU (one sp_comm per context; ranks are processes or threads, every call below is a collective)
     pub fn sp_comm_unique_id(id: *mut u8) -> c_int;
     pub fn sp_comm_create(ctx: *mut sp_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut sp_comm) -> c_int;
