@@ -234,6 +234,24 @@ sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, const sp_targe
                             const int32_t *win_end, sp_align_rec *recs, uint32_t *cigar, int64_t cigar_cap,
                             int64_t *cigar_used);
 
+/* ---- K9: the reference's cost model for selected pairs ------------------------------------------ */
+/* minimap2's two-piece affine costs as the reference configures them: match +a, mismatch -b, ambiguous base -1, a gap of k bases
+ * -min(q + k e, q2 + k e2).  map-hifi: {1, 4, 6, 2, 26, 1} (src/util/mapping.rs:8-14); allele scoring sets a = 5
+ * (src/hla/caller.rs:1370-1381). */
+typedef struct sp_affine_costs { int32_t a, b, q, e, q2, e2; } sp_affine_costs;
+/* Best-scoring LOCAL alignment of pattern q inside its text window under `costs`, restricted to the diagonal band
+ * |(j - i) - band_centre[q]| <= band (i = pattern base, j = window column, both 1-based; band <= 255; band_centre NULL = 0): what
+ * minimap2 reports for one co-linear chain.  The host centres the band on the placement K4 found (t_start - p_start).  recs as for
+ * sp_align_pairs (dist = nm + clipped pattern bases; p_start / p_end = minimap2's query_start / query_end; t_start / t_end relative to
+ * the window), scores[q] = the DP score minimap2 compares with -s (0 and an empty record when nothing scores above 0).  Ties: the
+ * diagonal, then the short-gap deletion, short-gap insertion, long-gap deletion, long-gap insertion (ksw2's order); the first best
+ * end cell in anti-diagonal order; the walk back stops at the first zero.  Inside the band the result equals the unbanded optimum
+ * (tests/test_affine_gpu.py). */
+sp_status sp_align_affine_resident(sp_ctx *ctx, const sp_targets *texts, const sp_targets *patterns, int64_t n_pairs,
+                                   const int32_t *pair_text, const int32_t *pair_pattern, const int32_t *win_begin,
+                                   const int32_t *win_end, const int32_t *band_centre, int32_t band, const sp_affine_costs *costs,
+                                   sp_align_rec *recs, int32_t *scores, uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used);
+
 /* ---- K5: candidate lists -------------------------------------------------------------------- */
 /* The k best patterns of every target of a device matrix (k <= 16): idx / dist are [n_targets][k] row-major, ordered
  * by (distance, pattern index) ascending; entries beyond n_patterns are -1.  Plays the role of minimap2's best_n hit

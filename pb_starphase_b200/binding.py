@@ -81,6 +81,8 @@ SIGNATURES = {
     "sp_align_windows": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                    C.POINTER(C.c_int64)]),
     "sp_align_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "sp_align_affine_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P, C.POINTER(AlignRec), _P, _P, C.c_int64,
+                                           C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "sp_row_topk_biased": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "sp_row_topk_weighted": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
@@ -306,6 +308,40 @@ class Context:
             c = cig[r.cigar_off:r.cigar_off + r.n_cigar]
             out.append({"dist": r.dist, "nm": r.nm, "p_start": r.p_start, "p_end": r.p_end, "t_start": r.t_start,
                         "t_end": r.t_end, "cigar": [(int(x) >> 4, int(x) & 15) for x in c]})
+        return out
+
+    def align_affine(self, texts: "TargetSet", patterns: "TargetSet", pairs, costs, band: int = 64, centres=None, windows=None):
+        """K9: best local alignment of each (text index, pattern index) pair under two-piece affine costs (a, b, q, e, q2, e2), inside
+        the diagonal band |(j - i) - centre| <= band.  Returns dicts like align_pairs plus `score`."""
+        pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        n = len(pairs)
+        pt, pp = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        cen = np.ascontiguousarray(centres, dtype=np.int32) if centres is not None else None
+        wb = we = None
+        if windows is not None:
+            w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32).reshape(-1, 2))
+            wb, we = np.ascontiguousarray(w[:, 0]), np.ascontiguousarray(w[:, 1])
+        cst = np.ascontiguousarray(costs, dtype=np.int32)
+        recs = (AlignRec * max(n, 1))()
+        scores = np.zeros(max(n, 1), dtype=np.int32)
+        cap = max(1 << 16, n * 1024)
+        for _ in range(2):
+            cig = np.zeros(cap, dtype=np.uint32)
+            used = C.c_int64(0)
+            st = self._lib.sp_align_affine_resident(self._h, texts._h, patterns._h, n, pt.ctypes.data, pp.ctypes.data,
+                                                    wb.ctypes.data if wb is not None else None, we.ctypes.data if we is not None else None,
+                                                    cen.ctypes.data if cen is not None else None, band, cst.ctypes.data, recs, scores.ctypes.data,
+                                                    cig.ctypes.data, cap, C.byref(used))
+            if st == 5 and used.value > cap:
+                cap = used.value
+                continue
+            self._check(st)
+            break
+        out = []
+        for q, r in enumerate(recs[:n]):
+            c = cig[r.cigar_off:r.cigar_off + r.n_cigar]
+            out.append({"dist": r.dist, "nm": r.nm, "p_start": r.p_start, "p_end": r.p_end, "t_start": r.t_start, "t_end": r.t_end,
+                        "cigar": [(int(x) >> 4, int(x) & 15) for x in c], "score": int(scores[q])})
         return out
 
     def row_topk(self, d: "DMatrix", k: int = 5, bias=None, weight: int = 1):

@@ -18,6 +18,7 @@ UNITS = {
     "sp_comm.cu": HEADERS + ["sp_comm_kernels.cuh"],  # multi-GPU (NCCL, loaded with dlopen at run time)
     "sp_consensus.cu": HEADERS + ["sp_consensus.cuh"],  # K7
     "sp_graph.cu": HEADERS + ["sp_graph.cuh"],  # K8
+    "sp_affine.cu": HEADERS + ["sp_affine.cuh", "sp_align.cuh"],  # K9
 }
 OBJDIR = CSRC / "build"
 

@@ -37,6 +37,17 @@ pub struct sp_align_rec {
     pub cigar_off: i64,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct sp_affine_costs {
+    pub a: i32,
+    pub b: i32,
+    pub q: i32,
+    pub e: i32,
+    pub q2: i32,
+    pub e2: i32,
+}
+
 pub enum sp_ctx {}
 pub enum sp_patterns {}
 pub enum sp_targets {}
@@ -111,6 +122,11 @@ extern "C" {
     pub fn sp_align_resident(ctx: *mut sp_ctx, texts: *const sp_targets, patterns: *const sp_targets, n_pairs: i64, pair_text: *const i32,
                              pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32, recs: *mut sp_align_rec, cigar: *mut u32,
                              cigar_cap: i64, cigar_used: *mut i64) -> c_int;
+    // K9: the reference's affine cost model for selected pairs
+    pub fn sp_align_affine_resident(ctx: *mut sp_ctx, texts: *const sp_targets, patterns: *const sp_targets, n_pairs: i64, pair_text: *const i32,
+                                    pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32, band_centre: *const i32, band: i32,
+                                    costs: *const sp_affine_costs, recs: *mut sp_align_rec, scores: *mut i32, cigar: *mut u32, cigar_cap: i64,
+                                    cigar_used: *mut i64) -> c_int;
     // K7: consensus extension
     pub fn sp_consensus_create(ctx: *mut sp_ctx, reads: *const sp_seqset, offsets: *const i32, offset_window: i32, band: i32, max_tracks: i32,
                                out: *mut *mut sp_consensus) -> c_int;
