@@ -62,8 +62,21 @@ enum { SRC_DIAG = 0, SRC_E1 = 1, SRC_F1 = 2, SRC_E2 = 3, SRC_F2 = 4, SRC_START =
  * small / memory ran out.  An alignment of score 0 (nothing matches) is the empty alignment:
  * p_start = p_end = t_start = t_end = 0, dist = m.
  */
+int64_t sp_oracle_affine_local_banded(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, const int32_t *costs, int64_t centre,
+                                      int64_t band, int32_t *rec, uint32_t *cigar, int64_t cap);
+
 int64_t sp_oracle_affine_local(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, const int32_t *costs,
                                int32_t *rec, uint32_t *cigar, int64_t cap) {
+    return sp_oracle_affine_local_banded(P, m, T, n, costs, 0, -1, rec, cigar, cap);
+}
+
+/*
+ * The same with the DP restricted to the diagonal band |(j - i) - centre| <= band (1-based cells), the way the product's K9
+ * kernel computes it: a cell outside the band counts as H = 0 with no open gap (so alignments may start at the band edge and a
+ * gap may open from the cell left of it).  band < 0: no band.
+ */
+int64_t sp_oracle_affine_local_banded(const uint8_t *P, int64_t m, const uint8_t *T, int64_t n, const int32_t *costs, int64_t centre,
+                                      int64_t band, int32_t *rec, uint32_t *cigar, int64_t cap) {
     const int a = costs[0], b = costs[1], q = costs[2], e = costs[3], q2 = costs[4], e2 = costs[5];
     memset(rec, 0, 8 * sizeof(int32_t));
     rec[7] = (int32_t)m;
@@ -86,6 +99,13 @@ int64_t sp_oracle_affine_local(const uint8_t *P, int64_t m, const uint8_t *T, in
         uint8_t *trow = tr + (size_t)(i - 1) * (size_t)n;
         for (int64_t j = 1; j <= n; ++j) {
             uint8_t t = 0;
+            if (band >= 0 && ((j - i) - centre > band || (j - i) - centre < -band)) {  /* outside the band: H = 0, no open gap */
+                hdiag = H[j];
+                H[j] = 0; F1[j] = AFF_NEG; F2[j] = AFF_NEG;
+                hleft = 0; e1 = AFF_NEG; e2s = AFF_NEG;
+                trow[j - 1] = (uint8_t)SRC_START;
+                continue;
+            }
             /* horizontal (deletion) states from H[i][j-1] */
             int32_t o = hleft - q - e, x = e1 - e;
             if (x > o) { e1 = x; t |= 1u << 3; } else e1 = o;
@@ -130,6 +150,7 @@ int64_t sp_oracle_affine_local(const uint8_t *P, int64_t m, const uint8_t *T, in
         else { if (cur_len) rev[nrev++] = (cur_len << 4) | cur_op; cur_op = (op); cur_len = 1; } \
     } while (0)
     while (i > 0 && j > 0) {
+        if (band >= 0 && ((j - i) - centre > band || (j - i) - centre < -band)) break;  /* left the band: the alignment starts here */
         const uint8_t t = tr[(size_t)(i - 1) * (size_t)n + (size_t)(j - 1)];
         if (state == 0) {
             const int src = t & 7;

@@ -255,9 +255,8 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             gpu_.matrix_to_host(*M, D, &E);
         }
         mark("K1 score_device", round, items.size());
-        std::vector<std::pair<int32_t, int32_t>> pairs, windows;  // (sequence, template), [lo + w0, lo + e) inside the sequence
+        std::vector<std::pair<int32_t, int32_t>> pairs, windows, bounds;  // (sequence, template), [lo + w0, lo + e) inside the sequence, [lo, hi)
         std::vector<Item> pair_item;
-        std::vector<size_t> pair_off;  // where the aligned text starts inside the sequence
         for (const Item &it : items) {
             const size_t row = seg_index.at(std::make_tuple(it.seq, it.lo, it.hi));
             const size_t m = tmpl_seqs[it.tmpl].size();
@@ -266,23 +265,23 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             const size_t w0 = e > m + d ? e - (m + d) : 0;
             pairs.emplace_back(static_cast<int32_t>(it.seq), static_cast<int32_t>(it.tmpl));
             windows.emplace_back(static_cast<int32_t>(it.lo + w0), static_cast<int32_t>(it.lo + e));
+            bounds.emplace_back(static_cast<int32_t>(it.lo), static_cast<int32_t>(it.hi));
             pair_item.push_back(it);
-            pair_off.push_back(it.lo + w0);
         }
         mark("windows", round, pairs.size());
-        const std::vector<Alignment> alns = gpu_.align_pairs(*resident_seqs, tmpl_patterns_->resident(), pairs, &windows);  // windows of resident reads
+        const std::vector<Alignment> alns = gpu_.align_pairs(*resident_seqs, tmpl_patterns_->resident(), pairs, &windows, 1, &bounds);  // windows of resident reads
         mark("K4 align_pairs", round, pairs.size());
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {
             const Alignment &a = alns[q];
             const Item &it = pair_item[q];
             const size_t m = tmpl_seqs[it.tmpl].size();
-            if (a.cigar.empty() || dp_score(a.cigar, 1) < aligner_stand_ins().min_dp_score) continue;  // no mapping reported
+            if (a.cigar.empty() || a.score < aligner_stand_ins().min_dp_score) continue;  // no mapping reported
             const size_t clipped_start = static_cast<size_t>(a.p_start), clipped_end = m - static_cast<size_t>(a.p_end);
             MappingStats st(m, static_cast<size_t>(a.nm), m - static_cast<size_t>(a.p_end - a.p_start));
             st.clipped_start = clipped_start; st.clipped_end = clipped_end;  // new_with_clippings, :214-217
             if (st.custom_score(is_penalized_type(templates_[it.tmpl].first)) > max_ed_frac) continue;  // :221-226
-            const size_t hs = pair_off[q] + static_cast<size_t>(a.t_start), he = pair_off[q] + static_cast<size_t>(a.t_end);
+            const size_t hs = static_cast<size_t>(a.t_base + a.t_start), he = static_cast<size_t>(a.t_base + a.t_end);  // t_base: K4's window or K9's
             uncollapsed[it.seq].push_back({hs, he, st, it.tmpl});
             if (++n_hits[it.seq][it.tmpl] >= 5) continue;  // best_n = 5 (src/util/mapping.rs:8-14)
             // the same template may occur again left or right of this hit (duplications)

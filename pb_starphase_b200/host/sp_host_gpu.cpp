@@ -72,15 +72,89 @@ ResidentSeqs::~ResidentSeqs() { sp_targets_destroy(t_); }
 // host sequence lists: uploaded for this call only
 std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const SeqList &patterns,
                                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
-                                               const std::vector<std::pair<int32_t, int32_t>> *windows) {
+                                               const std::vector<std::pair<int32_t, int32_t>> *windows, int match_score) {
     if (pairs.empty()) return {};
     const std::shared_ptr<ResidentSeqs> t = upload(targets), p = upload(patterns);
-    return align_pairs(*t, *p, pairs, windows);
+    return align_pairs(*t, *p, pairs, windows, match_score);
 }
+
+long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match_score);
 
 std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const ResidentSeqs &pats,
                                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
-                                               const std::vector<std::pair<int32_t, int32_t>> *windows) {
+                                               const std::vector<std::pair<int32_t, int32_t>> *windows, int match_score,
+                                               const std::vector<std::pair<int32_t, int32_t>> *bounds) {
+    std::vector<Alignment> out = align_pairs_unit(texts, pats, pairs, windows);
+    if (match_score <= 0) return out;
+    for (size_t q = 0; q < out.size(); ++q) {
+        out[q].score = out[q].cigar.empty() ? 0 : dp_score(out[q].cigar, match_score);
+        out[q].t_base = windows ? (*windows)[q].first : 0;
+    }
+    if (!aligner_stand_ins().affine_refine) return out;
+    if (bounds && bounds->size() != pairs.size()) throw HostError("align_pairs: one bounds entry per pair expected");
+    // K9: band classes by the half width each placement needs
+    static const int kBands[4] = {47, 79, 143, 255};
+    const SeqList &targets = texts.sequences(), &patterns = pats.sequences();
+    for (int cls = 0; cls < 4; ++cls) {
+        std::vector<size_t> sel;
+        std::vector<int32_t> pt, pp, wb, we, centre;
+        for (size_t q = 0; q < out.size(); ++q) {
+            const Alignment &u = out[q];
+            if (u.cigar.empty()) continue;
+            const int64_t base = u.t_base;
+            const int64_t d0 = base + u.t_start - u.p_start, d1 = base + u.t_end - u.p_end;  // absolute diagonals of the placement's ends
+            const int64_t w = (std::llabs(d1 - d0) + 1) / 2 + u.nm + 24;
+            if (w > kBands[3] || w > kBands[cls] || (cls > 0 && w <= kBands[cls - 1])) continue;
+            const int64_t c_abs = (d0 + d1 >= 0) ? (d0 + d1) / 2 : -((-(d0 + d1) + 1) / 2);  // floor: independent of the coordinate origin
+            const int64_t m = static_cast<int64_t>(patterns[static_cast<size_t>(pairs[q].second)].size());
+            const int64_t n = static_cast<int64_t>(targets[static_cast<size_t>(pairs[q].first)].size());
+            const int64_t lo = bounds ? (*bounds)[q].first : 0, hi = bounds ? (*bounds)[q].second : n;
+            // the text window that holds every band cell: columns (1-based) i + c - W .. i + c + W for i = 1 .. m
+            const int64_t b = std::max<int64_t>(lo, std::min<int64_t>(hi, c_abs - kBands[cls]));
+            const int64_t e = std::min<int64_t>(hi, std::max<int64_t>(b, m + c_abs + kBands[cls] + 1));
+            sel.push_back(q);
+            pt.push_back(pairs[q].first); pp.push_back(pairs[q].second);
+            wb.push_back(static_cast<int32_t>(b)); we.push_back(static_cast<int32_t>(e));
+            centre.push_back(static_cast<int32_t>(c_abs - b));
+        }
+        if (sel.empty()) continue;
+        const sp_affine_costs costs = {match_score, 4, 6, 2, 26, 1};
+        std::vector<sp_align_rec> recs(sel.size());
+        std::vector<int32_t> scores(sel.size());
+        int64_t cap = std::max<int64_t>(1 << 16, static_cast<int64_t>(sel.size()) * cigar_entries_per_pair_), used = 0;
+        std::unique_ptr<uint32_t[]> cig;
+        for (int attempt = 0;; ++attempt) {
+            cig.reset(new uint32_t[static_cast<size_t>(cap)]);
+            const sp_status st = sp_align_affine_resident(ctx_, texts.t_, pats.t_, static_cast<int64_t>(sel.size()), pt.data(), pp.data(), wb.data(),
+                                                          we.data(), centre.data(), kBands[cls], &costs, recs.data(), scores.data(), cig.get(), cap, &used);
+            if (st == SP_ERR_RANGE && attempt == 0 && used > cap) { cap = used; continue; }
+            check(st, "sp_align_affine_resident");
+            break;
+        }
+        for (size_t k = 0; k < sel.size(); ++k) {
+            Alignment &a = out[sel[k]];
+            const sp_align_rec &r = recs[k];
+            a.refined = true;
+            a.score = scores[k];
+            a.t_base = wb[k];
+            a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
+            if (!windows) {  // callers without windows read text coordinates from the start of the text
+                a.t_start += static_cast<int32_t>(a.t_base); a.t_end += static_cast<int32_t>(a.t_base);
+                a.t_base = 0;
+            }
+            a.cigar.clear();
+            for (int32_t x = 0; x < r.n_cigar; ++x) {
+                const uint32_t en = cig[static_cast<size_t>(r.cigar_off + x)];
+                a.cigar.emplace_back(en >> 4, static_cast<uint8_t>(en & 15u));
+            }
+        }
+    }
+    return out;
+}
+
+std::vector<Alignment> GpuAligner::align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &pats,
+                                                    const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                                    const std::vector<std::pair<int32_t, int32_t>> *windows) {
     if (windows && windows->size() != pairs.size()) throw HostError("align_pairs: one window per pair expected");
     const SeqList &targets = texts.sequences(), &patterns = pats.sequences();
     std::vector<int32_t> pt(pairs.size()), pp(pairs.size()), wb, we;

@@ -22,7 +22,7 @@ long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match
 
 // sp_align_rec -> the Mapping of (query = pattern, target = text); nullopt when minimap2 would not have reported one
 static std::optional<Mapping> mapping_from_alignment(const Alignment &a, size_t pattern_len, size_t text_len, int min_dp_score) {
-    if (a.cigar.empty() || dp_score(a.cigar) < min_dp_score) return std::nullopt;
+    if (a.cigar.empty() || a.score < min_dp_score) return std::nullopt;
     Mapping m;
     m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = pattern_len;
     m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = text_len;
@@ -63,7 +63,7 @@ ScoreReadResult score_read(GpuAligner &gpu, const std::string &dna_target, const
             patterns.push_back(*allowed[a]->dna_sequence);
         }
     }
-    const std::vector<Alignment> alns = gpu.align_pairs(targets, patterns, pairs);
+    const std::vector<Alignment> alns = gpu.align_pairs(targets, patterns, pairs, nullptr, 5);  // a = 5: src/hla/caller.rs:1370-1379
 
     ScoreReadResult ret;
     HlaProcessedMatch best_match = HlaProcessedMatch::worst_match(2);
@@ -107,10 +107,10 @@ ScoreReadResult score_consensus(GpuAligner &gpu, const std::string &reference_se
                                 const DiplotypeSettings &settings) {
     if (consensus.empty()) return ScoreReadResult();  // :1264-1268
     // target = reference, query = consensus (:1277-1280); the ref_aligner is the plain map-hifi preset (a = 1)
-    const std::vector<Alignment> alns = gpu.align_pairs({reference_sequence}, {consensus}, {{0, 0}});
+    const std::vector<Alignment> alns = gpu.align_pairs({reference_sequence}, {consensus}, {{0, 0}}, nullptr, 1);
     std::vector<Mapping> mappings;
     const Alignment &a = alns.at(0);
-    if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {
+    if (!a.cigar.empty() && a.score >= aligner_stand_ins().min_dp_score) {
         Mapping m;
         m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = consensus.size();
         m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = reference_sequence.size();
@@ -229,7 +229,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
                     pairs.emplace_back(static_cast<int32_t>(r), cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)]);
     }
     first_pair[reads.size()] = pairs.size();
-    std::vector<Alignment> alns = gpu_.align_pairs(*resident_reads, index_->resident(), pairs);  // both sides already on the device
+    std::vector<Alignment> alns = gpu_.align_pairs(*resident_reads, index_->resident(), pairs, nullptr, 1);  // both sides already on the device
 
     std::vector<BestHit> out(reads.size());
     for (size_t r = 0; r < reads.size(); ++r) {
@@ -238,7 +238,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
         b.stats = MappingStats(read_len, read_len, 0);  // src/hla/realigner.rs:124
         for (size_t q = first_pair[r]; q < first_pair[r + 1]; ++q) {
             Alignment &a = alns[q];
-            if (a.cigar.empty() || dp_score(a.cigar, 1) < aligner_stand_ins().min_dp_score) continue;  // no hit reported
+            if (a.cigar.empty() || a.score < aligner_stand_ins().min_dp_score) continue;  // no hit reported
             const size_t target_len = allele_seqs[static_cast<size_t>(pairs[q].second)].size();
             const size_t unmapped = target_len - static_cast<size_t>(a.p_end - a.p_start);
             const MappingStats stats(target_len, static_cast<size_t>(a.nm), unmapped);
@@ -334,7 +334,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         seg_read.push_back(r);
         seg_buffered_start.push_back(bs);
     }
-    const std::vector<Alignment> seg_alns = gpu_.align_pairs(ref_texts, seg_patterns, seg_pairs);
+    const std::vector<Alignment> seg_alns = gpu_.align_pairs(ref_texts, seg_patterns, seg_pairs, nullptr, 1);
 
     // third batch: the best allele against hg38 for the reads whose hg38 mapping starts no earlier than the allele mapping (:268-290)
     struct Pending { size_t r; Mapping ref_mapping; size_t hg38_start, hg38_end; int32_t allele_pair = -1; };
@@ -346,7 +346,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         const std::string &ref = ref_texts[static_cast<size_t>(seg_pairs[q].first)];
         std::vector<Mapping> mappings;
         const Alignment &a = seg_alns[q];
-        if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {  // (query, target) = (read segment, hg38) = (pattern, text)
+        if (!a.cigar.empty() && a.score >= aligner_stand_ins().min_dp_score) {  // (query, target) = (read segment, hg38) = (pattern, text)
             Mapping m;
             m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end); m.query_len = seg_patterns[q].size();
             m.target_start = static_cast<size_t>(a.t_start); m.target_end = static_cast<size_t>(a.t_end); m.target_len = ref.size();
@@ -368,7 +368,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         }
         pending.push_back(std::move(p));
     }
-    const std::vector<Alignment> allele_alns = gpu_.align_pairs(ref_texts, allele_patterns, allele_pairs);
+    const std::vector<Alignment> allele_alns = gpu_.align_pairs(ref_texts, allele_patterns, allele_pairs, nullptr, 1);
 
     for (const Pending &p : pending) {
         const size_t r = p.r;
@@ -384,7 +384,7 @@ std::vector<RealignmentResult> HlaRealigner::realign_records_full(const std::vec
         if (p.allele_pair >= 0) {
             const Alignment &a = allele_alns[static_cast<size_t>(p.allele_pair)];
             std::vector<Mapping> mappings;
-            if (!a.cigar.empty() && dp_score(a.cigar, 1) >= aligner_stand_ins().min_dp_score) {
+            if (!a.cigar.empty() && a.score >= aligner_stand_ins().min_dp_score) {
                 Mapping m;
                 m.query_start = static_cast<size_t>(a.p_start); m.query_end = static_cast<size_t>(a.p_end);
                 m.query_len = allele_patterns[static_cast<size_t>(allele_pairs[static_cast<size_t>(p.allele_pair)].second)].size();

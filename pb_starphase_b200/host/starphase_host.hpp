@@ -176,6 +176,9 @@ using SeqList = std::vector<std::string>;
 struct Alignment {  // sp_align_rec + its CIGAR
     int32_t dist = 0, nm = 0, p_start = 0, p_end = 0, t_start = 0, t_end = 0;
     std::vector<std::pair<uint32_t, uint8_t>> cigar;
+    long score = 0;       // DP score under the reference's costs (what minimap2 compares with -s); set by align_pairs(.., match_score > 0)
+    int64_t t_base = 0;   // text coordinate t_start / t_end are relative to (the window begin; moves when K9 widened the window)
+    bool refined = false; // the record is K9's (affine cost model) rather than K4's (unit-cost placement)
 };
 
 class GpuAligner;
@@ -245,7 +248,7 @@ class GpuAligner {
     // windows (optional, one [begin, end) per pair): align inside that part of the text only; t_start / t_end are relative to begin
     std::vector<Alignment> align_pairs(const SeqList &targets, const SeqList &patterns,
                                        const std::vector<std::pair<int32_t, int32_t>> &pairs,
-                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr);
+                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr, int match_score = 0);
     std::vector<sp_pair_rec> pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,
                                               int k);
     // resident path: nothing of size reads x alleles crosses PCIe, no sequence is uploaded twice
@@ -255,9 +258,14 @@ class GpuAligner {
     std::unique_ptr<DeviceMatrix> score_device(const ResidentSeqs &targets, const PatternSet &patterns, bool want_end_col = false);
     // D[t * n_patterns + p] (and end columns) of a device matrix scored with 32-bit elements / end columns
     void matrix_to_host(const DeviceMatrix &d, std::vector<int32_t> &D, std::vector<int32_t> *end_col);
+    // K4; with match_score > 0 (the `a` of the call site: 5 for allele scoring, 1 elsewhere) followed by K9: every placement whose
+    // diagonal band fits (half width = half the start / end diagonal difference + nm + 24 <= 255) is re-aligned under the
+    // reference's two-piece affine costs inside that band, within `bounds` (optional, per pair [lo, hi) of the text; default the
+    // whole text), and `score` is filled for every pair
     std::vector<Alignment> align_pairs(const ResidentSeqs &texts, const ResidentSeqs &patterns,
                                        const std::vector<std::pair<int32_t, int32_t>> &pairs,
-                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr);                  // K4
+                                       const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr, int match_score = 0,
+                                       const std::vector<std::pair<int32_t, int32_t>> *bounds = nullptr);
     std::vector<sp_pair_rec> pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k);           // K2
     // K5; ranking key = dist_weight * distance + pattern_bias[p] (bias optional, one entry per pattern); dist returns the plain distance
     void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
@@ -272,6 +280,9 @@ class GpuAligner {
     sp_ctx *raw() { return ctx_; }
 
   private:
+    std::vector<Alignment> align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &patterns,
+                                            const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                            const std::vector<std::pair<int32_t, int32_t>> *windows);  // K4 alone
     void check(sp_status st, const char *what);
     sp_ctx *ctx_ = nullptr;
     int64_t cigar_entries_per_pair_ = 256;  // first guess of the CIGAR pool size; grows with what the calls really needed
@@ -288,6 +299,7 @@ struct AlignerStandIns {
     int no_mapping_permille = 350;  // weight_sequence: (segment, consensus) pairs further apart than this share of the segment have no hit
     int candidate_edit_weight = 5;  // realigner candidates: smallest weight * (nm + unmapped) - |allele| (map-hifi: one edit ~ b + a = 5)
     bool template_half_prefilter = true;  // template search: pairs with more than half the template unexplained skip the traceback
+    bool affine_refine = true;      // K9 after K4: mapping fields (nm, clips, spans, CIGAR, DP score) from the affine cost model where the band fits
 };
 AlignerStandIns &aligner_stand_ins();
 

@@ -31,8 +31,45 @@ def dp_score(cigar) -> int:
     return s
 
 
+# ---- K4 then K9, as GpuAligner::align_pairs(.., match_score) runs them ---------------------------------------
+AFFINE_REFINE = True   # AlignerStandIns::affine_refine of the C++ host
+REFINE_SLACK, REFINE_MAX_BAND = 24, 255
+_AFFINE = {}
+
+
+def dp_score_generic(cigar, match_score: int) -> int:
+    s = 0
+    for ln, op in cigar:
+        s += match_score * ln if op == 7 else -4 * ln if op == 8 else -min(6 + 2 * ln, 26 + ln)
+    return s
+
+
+def align_scored(orc, pattern: bytes, text: bytes, match_score: int) -> dict:
+    """The alignment a host flow works with: the unit-cost placement (K4), re-aligned under the reference's affine costs
+    (a = match_score, b=4 q=6 e=2 q2=26 e2=1) inside a diagonal band around that placement (K9) when the band fits; `score` is the
+    DP score compared with minimap2's -s floor.  An `orc` that already answers from the affine model is used as it is."""
+    u = dict(orc.align(pattern, text))
+    if "score" in u:
+        return u
+    u["score"] = dp_score_generic(u["cigar"], match_score)
+    if not AFFINE_REFINE or not u["cigar"]:
+        return u
+    d0, d1 = u["t_start"] - u["p_start"], u["t_end"] - u["p_end"]
+    w = (abs(d1 - d0) + 1) // 2 + u["nm"] + REFINE_SLACK
+    if w > REFINE_MAX_BAND:
+        return u
+    import oracle_util
+
+    aff = _AFFINE.setdefault(match_score, oracle_util.AffineOracle((match_score, 4, 6, 2, 26, 1)))
+    band = 47 if w <= 47 else 79 if w <= 79 else 143 if w <= 143 else 255   # the band classes of the host
+    a = dict(aff.align(pattern, text, centre=(d0 + d1) // 2, band=band))  # floor: independent of the coordinate origin
+    if a["score"] == 0:
+        a["dist"] = len(pattern)
+    return a
+
+
 def mapping_from_alignment(a: dict, pattern_len: int, text_len: int, min_dp_score: int = 200) -> Optional[so.Mapping]:
-    if not a["cigar"] or dp_score(a["cigar"]) < min_dp_score:
+    if not a["cigar"] or a["score"] < min_dp_score:
         return None
     return so.Mapping(a["p_start"], a["p_end"], pattern_len, a["t_start"], a["t_end"], text_len, a["nm"], True, a["cigar"])
 
@@ -49,7 +86,7 @@ def score_read(orc, dna_target: bytes, cdna_target: bytes, db: Sequence[DbRow], 
         for target, seq in ((cdna_target, None if disable_cdna else cdna), (dna_target, dna)):
             m = None
             if seq is not None:
-                cand = mapping_from_alignment(orc.align(seq.encode(), target), len(seq), len(target))
+                cand = mapping_from_alignment(align_scored(orc, seq.encode(), target, 5), len(seq), len(target))
                 idx, _ = so.select_best_mapping([cand] if cand else [], False, True)
                 m = cand if idx is not None else None
             cur.add_mapping(m)
@@ -72,7 +109,7 @@ def score_read_debug(orc, dna_target: bytes, cdna_target: bytes, db: Sequence[Db
         for target, seq in ((cdna_target, None if disable_cdna else cdna), (dna_target, dna)):
             m = None
             if seq is not None:
-                cand = mapping_from_alignment(orc.align(seq.encode(), target), len(seq), len(target))
+                cand = mapping_from_alignment(align_scored(orc, seq.encode(), target, 5), len(seq), len(target))
                 idx, _ = so.select_best_mapping([cand] if cand else [], False, True)
                 m = cand if idx is not None else None
             cur.add_mapping(m)
@@ -102,9 +139,9 @@ def score_consensus(orc, reference_sequence: bytes, ref_start: int, consensus: b
     empty = ({}, "", "", so.read_mapping_stats_json(None, None, {}))
     if not consensus:
         return empty
-    al = orc.align(consensus, reference_sequence)
+    al = align_scored(orc, consensus, reference_sequence, 1)
     cand = []
-    if al["cigar"] and dp_score_a1(al["cigar"]) >= 200:
+    if al["cigar"] and al["score"] >= 200:
         cand.append(so.Mapping(al["p_start"], al["p_end"], len(consensus), al["t_start"], al["t_end"], len(reference_sequence), al["nm"], True,
                                al["cigar"]))
     if not cand:
@@ -134,8 +171,8 @@ def realign_records(orc, genes: Sequence[str], db: Sequence[DbRow], reads: Seque
         best, best_a = so.MappingStats(len(seq), len(seq), 0), None
         order = sorted(range(len(alleles)), key=lambda a: (CANDIDATE_EDIT_WEIGHT * int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
-            al = orc.align(seqs[a], seq)
-            if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:  # db_aligner is the plain map-hifi preset (a = 1)
+            al = align_scored(orc, seqs[a], seq, 1)
+            if not al["cigar"] or al["score"] < 200:  # db_aligner is the plain map-hifi preset (a = 1)
                 continue
             tl = len(seqs[a])
             st = so.MappingStats(tl, al["nm"], tl - (al["p_end"] - al["p_start"]))
@@ -161,8 +198,8 @@ def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_de
         best, best_a, best_al = so.MappingStats(len(seq), len(seq), 0), None, None
         order = sorted(range(len(alleles)), key=lambda a: (CANDIDATE_EDIT_WEIGHT * int(D[r, a]) - len(seqs[a]), a))[:max(n_candidates, 1)] if len(seq) else []
         for a in order:
-            al = orc.align(seqs[a], seq)
-            if not al["cigar"] or dp_score_a1(al["cigar"]) < 200:
+            al = align_scored(orc, seqs[a], seq, 1)
+            if not al["cigar"] or al["score"] < 200:
                 continue
             tl = len(seqs[a])
             st = so.MappingStats(tl, al["nm"], tl - (al["p_end"] - al["p_start"]))
@@ -186,9 +223,9 @@ def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_de
         out.append(res)
         db_start, db_end = bm.query_start, bm.query_end
         bs, be = max(db_start - 1000, 0), min(db_end + 1000, len(seq))
-        sal = orc.align(seq[bs:be], ref)
+        sal = align_scored(orc, seq[bs:be], ref, 1)
         cand = []
-        if sal["cigar"] and dp_score_a1(sal["cigar"]) >= 200:
+        if sal["cigar"] and sal["score"] >= 200:
             cand.append(so.Mapping(sal["p_start"], sal["p_end"], be - bs, sal["t_start"], sal["t_end"], len(ref), sal["nm"], True, sal["cigar"]))
         idx, _ = so.select_best_mapping(cand, True, True)
         if idx is None:
@@ -199,9 +236,9 @@ def realign_records_full(orc, genes: Sequence[str], db: Sequence[DbRow], gene_de
         d = rm.target_start
         h = so.hpc_pos(ref, d)
         if not hg_start < db_start:
-            aal = orc.align(seqs[best_a], ref)
+            aal = align_scored(orc, seqs[best_a], ref, 1)
             acand = []
-            if aal["cigar"] and dp_score_a1(aal["cigar"]) >= 200:
+            if aal["cigar"] and aal["score"] >= 200:
                 acand.append(so.Mapping(aal["p_start"], aal["p_end"], len(seqs[best_a]), aal["t_start"], aal["t_end"], len(ref), aal["nm"], True,
                                         aal["cigar"]))
             aidx, _ = so.select_best_mapping(acand, False, True)
@@ -334,8 +371,8 @@ def find_base_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missi
                 d, _ = orc.infix(tseqs[t], seq[lo:hi])  # the K1 prefilter of every round
                 if m == 0 or 2 * d > m:
                     continue
-                a = orc.align(tseqs[t], seq[lo:hi])
-                if not a["cigar"] or dp_score_a1(a["cigar"]) < 200:
+                a = align_scored(orc, tseqs[t], seq[lo:hi], 1)
+                if not a["cigar"] or a["score"] < 200:
                     continue
                 st = so.MappingStats(m, a["nm"], m - (a["p_end"] - a["p_start"]), a["p_start"], m - a["p_end"])
                 if st.custom_score(labels[t].region_type in PEN) > 0.05:

@@ -147,6 +147,9 @@ class AffineOracle:
         L = self.lib
         L.sp_oracle_affine_local.restype = C.c_int64
         L.sp_oracle_affine_local.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.sp_oracle_affine_local_banded.restype = C.c_int64
+        L.sp_oracle_affine_local_banded.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                                    C.c_void_p, C.c_int64]
         L.sp_oracle_affine_batch.restype = C.c_int64
         L.sp_oracle_affine_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -157,16 +160,17 @@ class AffineOracle:
         return {"dist": int(rec[7]), "nm": int(rec[1]), "p_start": int(rec[2]), "p_end": int(rec[3]), "t_start": int(rec[4]),
                 "t_end": int(rec[5]), "cigar": [(int(x) >> 4, int(x) & 15) for x in cig], "score": int(rec[0])}
 
-    def align(self, pattern: bytes, text: bytes) -> dict:
-        key = (bytes(pattern), bytes(text))
+    def align(self, pattern: bytes, text: bytes, centre: int = 0, band: int = -1) -> dict:
+        """band < 0: the unbanded model; else the DP restricted to |(j - i) - centre| <= band, as the product's K9 computes it."""
+        key = (bytes(pattern), bytes(text)) if band < 0 else (bytes(pattern), bytes(text), centre, band)
         hit = self.cache.get(key)
         if hit is not None:
             return hit
         rec = np.zeros(8, dtype=np.int32)
         cap = len(pattern) + len(text) + 2
         cig = np.zeros(cap, dtype=np.uint32)
-        n = self.lib.sp_oracle_affine_local(key[0], len(key[0]), key[1], len(key[1]), self.costs.ctypes.data, rec.ctypes.data,
-                                            cig.ctypes.data, cap)
+        n = self.lib.sp_oracle_affine_local_banded(key[0], len(key[0]), key[1], len(key[1]), self.costs.ctypes.data, centre, band,
+                                                   rec.ctypes.data, cig.ctypes.data, cap)
         assert n >= 0
         out = self.cache[key] = self._rec(rec, cig[:n])
         return out
