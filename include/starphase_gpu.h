@@ -102,6 +102,11 @@ float sp_last_kernel_ms(sp_ctx *ctx, int which);
 uint64_t sp_launch_count(const sp_ctx *ctx);
 /* Block until all work queued on the context stream has finished. */
 sp_status sp_ctx_synchronize(sp_ctx *ctx);
+/* Page-locked host memory for result buffers (CIGAR pools, matrices): every entry point accepts pageable memory, but device ->
+ * host copies into page-locked memory run at PCIe speed and skip the first-touch page faults of a fresh allocation.  The caller
+ * owns the block and releases it with sp_pinned_free (NULL is ignored). */
+sp_status sp_pinned_alloc(sp_ctx *ctx, size_t bytes, void **out);
+void sp_pinned_free(sp_ctx *ctx, void *p);
 
 /* ---- K1: batched infix edit distance ---------------------------------------------------- */
 /* Upload + 2-bit/Peq-pack a pattern set (the allele database of one gene, or the read
@@ -241,7 +246,9 @@ sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, const sp_targe
 typedef struct sp_affine_costs { int32_t a, b, q, e, q2, e2; } sp_affine_costs;
 /* Best-scoring LOCAL alignment of pattern q inside its text window under `costs`, restricted to the diagonal band
  * |(j - i) - band_centre[q]| <= band (i = pattern base, j = window column, both 1-based; band <= 255; band_centre NULL = 0): what
- * minimap2 reports for one co-linear chain.  The host centres the band on the placement K4 found (t_start - p_start).  recs as for
+ * minimap2 reports for one co-linear chain.  pair_band (optional) gives every pair its own half width in [1, 255] and `band` is
+ * ignored; pairs are grouped by width class (<= 31, 63, 127, 255) and the classes run side by side.  The host centres the band on
+ * the diagonal hull of the placement K4 found.  recs as for
  * sp_align_pairs (dist = nm + clipped pattern bases; p_start / p_end = minimap2's query_start / query_end; t_start / t_end relative to
  * the window), scores[q] = the DP score minimap2 compares with -s (0 and an empty record when nothing scores above 0).  Ties: the
  * diagonal, then the short-gap deletion, short-gap insertion, long-gap deletion, long-gap insertion (ksw2's order); the first best
@@ -249,8 +256,9 @@ typedef struct sp_affine_costs { int32_t a, b, q, e, q2, e2; } sp_affine_costs;
  * (tests/test_affine_gpu.py). */
 sp_status sp_align_affine_resident(sp_ctx *ctx, const sp_targets *texts, const sp_targets *patterns, int64_t n_pairs,
                                    const int32_t *pair_text, const int32_t *pair_pattern, const int32_t *win_begin,
-                                   const int32_t *win_end, const int32_t *band_centre, int32_t band, const sp_affine_costs *costs,
-                                   sp_align_rec *recs, int32_t *scores, uint32_t *cigar, int64_t cigar_cap, int64_t *cigar_used);
+                                   const int32_t *win_end, const int32_t *band_centre, int32_t band, const int32_t *pair_band,
+                                   const sp_affine_costs *costs, sp_align_rec *recs, int32_t *scores, uint32_t *cigar,
+                                   int64_t cigar_cap, int64_t *cigar_used);
 
 /* ---- K5: candidate lists -------------------------------------------------------------------- */
 /* The k best patterns of every target of a device matrix (k <= 16): idx / dist are [n_targets][k] row-major, ordered

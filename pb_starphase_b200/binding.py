@@ -52,6 +52,8 @@ SIGNATURES = {
     "sp_last_kernel_ms": (C.c_float, [_P, C.c_int]),
     "sp_launch_count": (C.c_uint64, [_P]),
     "sp_ctx_synchronize": (C.c_int, [_P]),
+    "sp_pinned_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "sp_pinned_free": (None, [_P, _P]),
     "sp_patterns_create": (C.c_int, [_P, C.POINTER(SeqSet), C.c_int, C.POINTER(_P)]),
     "sp_patterns_destroy": (None, [_P]),
     "sp_patterns_count": (C.c_int64, [_P]),
@@ -81,7 +83,7 @@ SIGNATURES = {
     "sp_align_windows": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64,
                                    C.POINTER(C.c_int64)]),
     "sp_align_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.POINTER(AlignRec), _P, C.c_int64, C.POINTER(C.c_int64)]),
-    "sp_align_affine_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P, C.POINTER(AlignRec), _P, _P, C.c_int64,
+    "sp_align_affine_resident": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P, _P, C.POINTER(AlignRec), _P, _P, C.c_int64,
                                            C.POINTER(C.c_int64)]),
     "sp_row_topk": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "sp_row_topk_biased": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
@@ -310,13 +312,17 @@ class Context:
                         "t_end": r.t_end, "cigar": [(int(x) >> 4, int(x) & 15) for x in c]})
         return out
 
-    def align_affine(self, texts: "TargetSet", patterns: "TargetSet", pairs, costs, band: int = 64, centres=None, windows=None):
+    def align_affine(self, texts: "TargetSet", patterns: "TargetSet", pairs, costs, band: int = 64, centres=None, windows=None, bands=None):
         """K9: best local alignment of each (text index, pattern index) pair under two-piece affine costs (a, b, q, e, q2, e2), inside
-        the diagonal band |(j - i) - centre| <= band.  Returns dicts like align_pairs plus `score`."""
+        the diagonal band |(j - i) - centre| <= band (`bands`: one half width per pair instead).  Returns dicts like align_pairs
+        plus `score`."""
         pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         n = len(pairs)
         pt, pp = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
         cen = np.ascontiguousarray(centres, dtype=np.int32) if centres is not None else None
+        pb = np.ascontiguousarray(bands, dtype=np.int32) if bands is not None else None
+        if pb is not None and pb.shape != (n,):
+            raise ValueError("align_affine: one band per pair expected")
         wb = we = None
         if windows is not None:
             w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32).reshape(-1, 2))
@@ -330,7 +336,8 @@ class Context:
             used = C.c_int64(0)
             st = self._lib.sp_align_affine_resident(self._h, texts._h, patterns._h, n, pt.ctypes.data, pp.ctypes.data,
                                                     wb.ctypes.data if wb is not None else None, we.ctypes.data if we is not None else None,
-                                                    cen.ctypes.data if cen is not None else None, band, cst.ctypes.data, recs, scores.ctypes.data,
+                                                    cen.ctypes.data if cen is not None else None, band, pb.ctypes.data if pb is not None else None,
+                                                    cst.ctypes.data, recs, scores.ctypes.data,
                                                     cig.ctypes.data, cap, C.byref(used))
             if st == 5 and used.value > cap:
                 cap = used.value

@@ -39,7 +39,22 @@ struct sp_ctx {
     void *h_stage = nullptr;
     size_t h_stage_bytes = 0;
     size_t free_mem_cached = 0;  // cudaMemGetInfo is slow (~1 ms): asked once per context, refreshed when a pool has to grow
+    // side streams for kernels that are independent of each other inside one call (K9's band classes): forked from and joined
+    // back into `stream` with events, created on first use
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
 };
+
+static inline cudaError_t ctx_aux(sp_ctx *ctx) {
+    if (ctx->aux_fork) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+    return e;
+}
 
 static inline cudaError_t ctx_stage(sp_ctx *ctx, size_t bytes, void **out) {
     if (bytes > ctx->h_stage_bytes) {

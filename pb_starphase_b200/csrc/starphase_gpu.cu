@@ -89,12 +89,37 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+        if (ctx->aux_join[i]) cudaEventDestroy(ctx->aux_join[i]);
+    }
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (void *p : ctx->pool) cudaFree(p);
     cudaFree(ctx->d_counter);
     cudaFreeHost(ctx->h_stage);
     if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     delete ctx;
+}
+
+extern "C" sp_status sp_pinned_alloc(sp_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out) return fail(ctx, SP_ERR_INVALID, "sp_pinned_alloc: NULL argument");
+    *out = nullptr;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(ctx, SP_ERR_NOMEM, std::string("sp_pinned_alloc: ") + cudaGetErrorString(e));
+    }
+    return SP_OK;
+}
+
+extern "C" void sp_pinned_free(sp_ctx *ctx, void *p) {
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
 }
 
 extern "C" sp_status sp_ctx_synchronize(sp_ctx *ctx) {

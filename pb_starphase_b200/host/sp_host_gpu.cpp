@@ -33,7 +33,22 @@ GpuAligner::GpuAligner(int device) {
     if (st != SP_OK) throw HostError(std::string("sp_ctx_create: ") + sp_last_error(nullptr));
 }
 
-GpuAligner::~GpuAligner() { sp_ctx_destroy(ctx_); }
+GpuAligner::~GpuAligner() {
+    for (uint32_t *b : cig_buf_) sp_pinned_free(ctx_, b);
+    sp_ctx_destroy(ctx_);
+}
+
+uint32_t *GpuAligner::cigar_buffer(int slot, int64_t entries) {
+    if (entries > cig_cap_[slot]) {
+        sp_pinned_free(ctx_, cig_buf_[slot]);
+        cig_buf_[slot] = nullptr; cig_cap_[slot] = 0;
+        const int64_t want = entries + entries / 4;
+        void *p = nullptr;
+        check(sp_pinned_alloc(ctx_, static_cast<size_t>(want) * 4, &p), "sp_pinned_alloc");
+        cig_buf_[slot] = static_cast<uint32_t *>(p); cig_cap_[slot] = want;
+    }
+    return cig_buf_[slot];
+}
 
 void GpuAligner::check(sp_status st, const char *what) {
     if (st != SP_OK) throw HostError(std::string(what) + ": " + sp_last_error(ctx_));
@@ -78,81 +93,114 @@ std::vector<Alignment> GpuAligner::align_pairs(const SeqList &targets, const Seq
     return align_pairs(*t, *p, pairs, windows, match_score);
 }
 
-long dp_score(const std::vector<std::pair<uint32_t, uint8_t>> &cigar, long match_score);
+// DP score of a run-length CIGAR under (a, b = 4, q = 6, e = 2, q2 = 26, e2 = 1): dp_score (sp_host_core.cpp) on raw pool entries
+static long raw_dp_score(const uint32_t *cig, int32_t n, long a) {
+    long s = 0;
+    for (int32_t k = 0; k < n; ++k) {
+        const long len = cig[k] >> 4;
+        const uint32_t op = cig[k] & 15u;
+        if (op == 7) s += a * len;
+        else if (op == 8) s -= 4 * len;
+        else s -= std::min(6 + 2 * len, 26 + len);
+    }
+    return s;
+}
 
 std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const ResidentSeqs &pats,
                                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
                                                const std::vector<std::pair<int32_t, int32_t>> *windows, int match_score,
                                                const std::vector<std::pair<int32_t, int32_t>> *bounds) {
-    std::vector<Alignment> out = align_pairs_unit(texts, pats, pairs, windows);
-    if (match_score <= 0) return out;
-    for (size_t q = 0; q < out.size(); ++q) {
-        out[q].score = out[q].cigar.empty() ? 0 : dp_score(out[q].cigar, match_score);
-        out[q].t_base = windows ? (*windows)[q].first : 0;
-    }
-    if (!aligner_stand_ins().affine_refine) return out;
+    if (pairs.empty()) return {};
     if (bounds && bounds->size() != pairs.size()) throw HostError("align_pairs: one bounds entry per pair expected");
-    // K9: band classes by the half width each placement needs
-    static const int kBands[4] = {47, 79, 143, 255};
+    const UnitResult unit = align_pairs_unit(texts, pats, pairs, windows);
     const SeqList &targets = texts.sequences(), &patterns = pats.sequences();
-    for (int cls = 0; cls < 4; ++cls) {
-        std::vector<size_t> sel;
-        std::vector<int32_t> pt, pp, wb, we, centre;
-        for (size_t q = 0; q < out.size(); ++q) {
-            const Alignment &u = out[q];
-            if (u.cigar.empty()) continue;
-            const int64_t base = u.t_base;
-            const int64_t d0 = base + u.t_start - u.p_start, d1 = base + u.t_end - u.p_end;  // absolute diagonals of the placement's ends
-            const int64_t w = (std::llabs(d1 - d0) + 1) / 2 + u.nm + 24;
-            if (w > kBands[3] || w > kBands[cls] || (cls > 0 && w <= kBands[cls - 1])) continue;
-            const int64_t c_abs = (d0 + d1 >= 0) ? (d0 + d1) / 2 : -((-(d0 + d1) + 1) / 2);  // floor: independent of the coordinate origin
+    const bool refine = match_score > 0 && aligner_stand_ins().affine_refine;
+    // K9 for every placement whose band fits: half width = half the diagonal hull of the unit-cost path (text column - pattern
+    // row along the CIGAR, absolute text coordinates) + 24, centre = the middle of the hull
+    std::vector<size_t> sel;
+    std::vector<int32_t> pt, pp, wb, we, centre, bandw;
+    if (refine) {
+        for (size_t q = 0; q < pairs.size(); ++q) {
+            const sp_align_rec &r = unit.recs[q];
+            if (r.n_cigar == 0) continue;
+            const int64_t base = windows ? (*windows)[q].first : 0;
+            int64_t d = base + r.t_start - r.p_start, lo = d, hi = d;
+            const uint32_t *cg = unit.cigar + r.cigar_off;
+            for (int32_t k = 0; k < r.n_cigar; ++k) {
+                const uint32_t op = cg[k] & 15u;
+                if (op == 1) d -= cg[k] >> 4;       // I: pattern bases without text
+                else if (op == 2) d += cg[k] >> 4;  // D: text bases without pattern
+                else continue;
+                lo = std::min(lo, d); hi = std::max(hi, d);
+            }
+            const int64_t w = (hi - lo + 1) / 2 + 24;
+            if (w > 255) continue;
+            const int64_t c_abs = (lo + hi >= 0) ? (lo + hi) / 2 : -((-(lo + hi) + 1) / 2);  // floor: independent of the coordinate origin
+            const int64_t W = w <= 31 ? 31 : w <= 63 ? 63 : w <= 127 ? 127 : 255;            // the width classes of the library
             const int64_t m = static_cast<int64_t>(patterns[static_cast<size_t>(pairs[q].second)].size());
             const int64_t n = static_cast<int64_t>(targets[static_cast<size_t>(pairs[q].first)].size());
-            const int64_t lo = bounds ? (*bounds)[q].first : 0, hi = bounds ? (*bounds)[q].second : n;
+            const int64_t blo = bounds ? (*bounds)[q].first : 0, bhi = bounds ? (*bounds)[q].second : n;
             // the text window that holds every band cell: columns (1-based) i + c - W .. i + c + W for i = 1 .. m
-            const int64_t b = std::max<int64_t>(lo, std::min<int64_t>(hi, c_abs - kBands[cls]));
-            const int64_t e = std::min<int64_t>(hi, std::max<int64_t>(b, m + c_abs + kBands[cls] + 1));
+            const int64_t b = std::max<int64_t>(blo, std::min<int64_t>(bhi, c_abs - W));
+            const int64_t e = std::min<int64_t>(bhi, std::max<int64_t>(b, m + c_abs + W + 1));
             sel.push_back(q);
             pt.push_back(pairs[q].first); pp.push_back(pairs[q].second);
             wb.push_back(static_cast<int32_t>(b)); we.push_back(static_cast<int32_t>(e));
             centre.push_back(static_cast<int32_t>(c_abs - b));
+            bandw.push_back(static_cast<int32_t>(W));
         }
-        if (sel.empty()) continue;
+    }
+    std::vector<sp_align_rec> arecs(std::max<size_t>(sel.size(), 1));
+    std::vector<int32_t> ascores(std::max<size_t>(sel.size(), 1));
+    const uint32_t *acig = nullptr;
+    if (!sel.empty()) {
         const sp_affine_costs costs = {match_score, 4, 6, 2, 26, 1};
-        std::vector<sp_align_rec> recs(sel.size());
-        std::vector<int32_t> scores(sel.size());
-        int64_t cap = std::max<int64_t>(1 << 16, static_cast<int64_t>(sel.size()) * cigar_entries_per_pair_), used = 0;
-        std::unique_ptr<uint32_t[]> cig;
+        int64_t cap = std::max<int64_t>(1 << 16, static_cast<int64_t>(sel.size()) * affine_entries_per_pair_), used = 0;
         for (int attempt = 0;; ++attempt) {
-            cig.reset(new uint32_t[static_cast<size_t>(cap)]);
+            uint32_t *buf = cigar_buffer(1, cap);
             const sp_status st = sp_align_affine_resident(ctx_, texts.t_, pats.t_, static_cast<int64_t>(sel.size()), pt.data(), pp.data(), wb.data(),
-                                                          we.data(), centre.data(), kBands[cls], &costs, recs.data(), scores.data(), cig.get(), cap, &used);
+                                                          we.data(), centre.data(), 0, bandw.data(), &costs, arecs.data(), ascores.data(), buf, cap,
+                                                          &used);
             if (st == SP_ERR_RANGE && attempt == 0 && used > cap) { cap = used; continue; }
             check(st, "sp_align_affine_resident");
+            acig = buf;
             break;
         }
-        for (size_t k = 0; k < sel.size(); ++k) {
-            Alignment &a = out[sel[k]];
-            const sp_align_rec &r = recs[k];
+        affine_entries_per_pair_ = std::max<int64_t>(affine_entries_per_pair_, 2 * used / static_cast<int64_t>(sel.size()) + 64);
+    }
+    std::vector<Alignment> out(pairs.size());
+    auto fill = [](Alignment &a, const sp_align_rec &r, const uint32_t *pool) {
+        a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
+        a.cigar.reserve(static_cast<size_t>(r.n_cigar));
+        const uint32_t *cg = pool + r.cigar_off;
+        for (int32_t k = 0; k < r.n_cigar; ++k) a.cigar.emplace_back(cg[k] >> 4, static_cast<uint8_t>(cg[k] & 15u));
+    };
+    size_t k = 0;
+    for (size_t q = 0; q < pairs.size(); ++q) {
+        Alignment &a = out[q];
+        if (k < sel.size() && sel[k] == q) {  // the mapping fields come from the affine alignment
+            fill(a, arecs[k], acig);
             a.refined = true;
-            a.score = scores[k];
+            a.score = ascores[k];
             a.t_base = wb[k];
-            a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
             if (!windows) {  // callers without windows read text coordinates from the start of the text
                 a.t_start += static_cast<int32_t>(a.t_base); a.t_end += static_cast<int32_t>(a.t_base);
                 a.t_base = 0;
             }
-            a.cigar.clear();
-            for (int32_t x = 0; x < r.n_cigar; ++x) {
-                const uint32_t en = cig[static_cast<size_t>(r.cigar_off + x)];
-                a.cigar.emplace_back(en >> 4, static_cast<uint8_t>(en & 15u));
+            ++k;
+        } else {
+            const sp_align_rec &r = unit.recs[q];
+            fill(a, r, unit.cigar);
+            if (match_score > 0) {
+                a.score = r.n_cigar ? raw_dp_score(unit.cigar + r.cigar_off, r.n_cigar, match_score) : 0;
+                a.t_base = windows ? (*windows)[q].first : 0;
             }
         }
     }
     return out;
 }
 
-std::vector<Alignment> GpuAligner::align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &pats,
+GpuAligner::UnitResult GpuAligner::align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &pats,
                                                     const std::vector<std::pair<int32_t, int32_t>> &pairs,
                                                     const std::vector<std::pair<int32_t, int32_t>> *windows) {
     if (windows && windows->size() != pairs.size()) throw HostError("align_pairs: one window per pair expected");
@@ -177,32 +225,22 @@ std::vector<Alignment> GpuAligner::align_pairs_unit(const ResidentSeqs &texts, c
         }
         worst += m + std::min(n, 2 * m) + 1;
     }
-    std::vector<sp_align_rec> recs(std::max<size_t>(pairs.size(), 1));
+    UnitResult res;
+    res.recs.resize(std::max<size_t>(pairs.size(), 1));
     int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(1 << 16, static_cast<int64_t>(pairs.size()) * cigar_entries_per_pair_));
-    std::unique_ptr<uint32_t[]> cig;
     int64_t used = 0;
     for (int attempt = 0;; ++attempt) {
-        cig.reset(new uint32_t[static_cast<size_t>(std::max<int64_t>(cap, 1))]);  // uninitialised: only the used entries are ever touched
+        uint32_t *buf = cigar_buffer(0, std::max<int64_t>(cap, 1));
         const sp_status st = sp_align_resident(ctx_, texts.t_, pats.t_, static_cast<int64_t>(pairs.size()), pt.data(), pp.data(),
-                                               windows ? wb.data() : nullptr, windows ? we.data() : nullptr, recs.data(), cig.get(), cap, &used);
+                                               windows ? wb.data() : nullptr, windows ? we.data() : nullptr, res.recs.data(), buf, cap, &used);
         if (st == SP_ERR_RANGE && attempt == 0 && used > cap) { cap = used; continue; }
         check(st, "sp_align_resident");
+        res.cigar = buf;
         break;
     }
     // remember how long the CIGARs of this workload are (divergent CYP2D6 templates need ~400 entries, HLA alleles a few dozen)
     cigar_entries_per_pair_ = std::max<int64_t>(cigar_entries_per_pair_, 2 * used / static_cast<int64_t>(pairs.size()) + 64);
-    std::vector<Alignment> out(pairs.size());
-    for (size_t q = 0; q < pairs.size(); ++q) {
-        const sp_align_rec &r = recs[q];
-        Alignment &a = out[q];
-        a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
-        a.cigar.reserve(static_cast<size_t>(r.n_cigar));
-        for (int32_t k = 0; k < r.n_cigar; ++k) {
-            const uint32_t e = cig[static_cast<size_t>(r.cigar_off + k)];
-            a.cigar.emplace_back(e >> 4, static_cast<uint8_t>(e & 15u));
-        }
-    }
-    return out;
+    return res;
 }
 
 std::vector<sp_pair_rec> GpuAligner::pair_minsum_topk(const std::vector<int32_t> &D, const std::vector<int32_t> *D2, int64_t R, int64_t A,

@@ -169,22 +169,45 @@ PYBIND11_MODULE(_starphase_host, m) {
         .def_readwrite("expected_maf", &DiplotypeSettings::expected_maf)
         .def_readwrite("min_dp_score", &DiplotypeSettings::min_dp_score);
 
+    // the process-wide aligner stand-ins (starphase_host.hpp): stand_ins() reads them, set_stand_ins(name=value, ...) changes them
+    m.def("stand_ins", []() {
+        const AlignerStandIns &s = aligner_stand_ins();
+        py::dict d;
+        d["min_dp_score"] = s.min_dp_score; d["no_mapping_permille"] = s.no_mapping_permille;
+        d["candidate_edit_weight"] = s.candidate_edit_weight; d["template_half_prefilter"] = s.template_half_prefilter;
+        d["affine_refine"] = s.affine_refine;
+        return d;
+    });
+    m.def("set_stand_ins", [](const py::kwargs &kw) {
+        AlignerStandIns &s = aligner_stand_ins();
+        for (auto item : kw) {
+            const std::string k = py::cast<std::string>(item.first);
+            if (k == "min_dp_score") s.min_dp_score = py::cast<long>(item.second);
+            else if (k == "no_mapping_permille") s.no_mapping_permille = py::cast<int>(item.second);
+            else if (k == "candidate_edit_weight") s.candidate_edit_weight = py::cast<int>(item.second);
+            else if (k == "template_half_prefilter") s.template_half_prefilter = py::cast<bool>(item.second);
+            else if (k == "affine_refine") s.affine_refine = py::cast<bool>(item.second);
+            else throw std::invalid_argument("set_stand_ins: unknown setting " + k);
+        }
+    });
+
     py::class_<GpuAligner>(m, "GpuAligner")
         .def(py::init<int>(), py::arg("device") = 0)
         .def("score_batch", [](GpuAligner &g, const SeqList &t, const SeqList &p) { return g.score_batch(t, p); })
         .def("launch_count", &GpuAligner::launch_count)
-        .def("align_pairs", [](GpuAligner &g, const SeqList &t, const SeqList &p, const std::vector<std::pair<int32_t, int32_t>> &pairs) {
+        .def("align_pairs", [](GpuAligner &g, const SeqList &t, const SeqList &p, const std::vector<std::pair<int32_t, int32_t>> &pairs, int match_score) {
             py::list out;
-            for (const Alignment &a : g.align_pairs(t, p, pairs)) {
+            for (const Alignment &a : g.align_pairs(t, p, pairs, nullptr, match_score)) {
                 py::dict d;
                 d["dist"] = a.dist; d["nm"] = a.nm; d["p_start"] = a.p_start; d["p_end"] = a.p_end; d["t_start"] = a.t_start; d["t_end"] = a.t_end;
+                d["score"] = a.score; d["refined"] = a.refined;
                 py::list c;
                 for (const auto &e : a.cigar) c.append(py::make_tuple(e.first, static_cast<int>(e.second)));
                 d["cigar"] = c;
                 out.append(d);
             }
             return out;
-        });
+        }, py::arg("texts"), py::arg("patterns"), py::arg("pairs"), py::arg("match_score") = 0);
 
     // ---- HLA ----
     using DbRows = std::vector<std::tuple<std::string, std::string, std::vector<std::string>, std::optional<std::string>, std::string>>;

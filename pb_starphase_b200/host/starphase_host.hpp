@@ -259,7 +259,7 @@ class GpuAligner {
     // D[t * n_patterns + p] (and end columns) of a device matrix scored with 32-bit elements / end columns
     void matrix_to_host(const DeviceMatrix &d, std::vector<int32_t> &D, std::vector<int32_t> *end_col);
     // K4; with match_score > 0 (the `a` of the call site: 5 for allele scoring, 1 elsewhere) followed by K9: every placement whose
-    // diagonal band fits (half width = half the start / end diagonal difference + nm + 24 <= 255) is re-aligned under the
+    // diagonal band fits (half width = half the diagonal hull of the unit-cost path + 24 <= 255) is re-aligned under the
     // reference's two-piece affine costs inside that band, within `bounds` (optional, per pair [lo, hi) of the text; default the
     // whole text), and `score` is filled for every pair
     std::vector<Alignment> align_pairs(const ResidentSeqs &texts, const ResidentSeqs &patterns,
@@ -280,12 +280,21 @@ class GpuAligner {
     sp_ctx *raw() { return ctx_; }
 
   private:
-    std::vector<Alignment> align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &patterns,
-                                            const std::vector<std::pair<int32_t, int32_t>> &pairs,
-                                            const std::vector<std::pair<int32_t, int32_t>> *windows);  // K4 alone
+    // K4 alone: records + the run-length CIGAR pool (page-locked buffer `slot`, valid until that slot is used again)
+    struct UnitResult {
+        std::vector<sp_align_rec> recs;
+        const uint32_t *cigar = nullptr;
+    };
+    UnitResult align_pairs_unit(const ResidentSeqs &texts, const ResidentSeqs &patterns,
+                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
+                                const std::vector<std::pair<int32_t, int32_t>> *windows);
+    uint32_t *cigar_buffer(int slot, int64_t entries);  // grow-only, page-locked (sp_pinned_alloc)
     void check(sp_status st, const char *what);
     sp_ctx *ctx_ = nullptr;
+    uint32_t *cig_buf_[2] = {nullptr, nullptr};
+    int64_t cig_cap_[2] = {0, 0};
     int64_t cigar_entries_per_pair_ = 256;  // first guess of the CIGAR pool size; grows with what the calls really needed
+    int64_t affine_entries_per_pair_ = 64;  // the same for K9's pool
 };
 
 // ------------------------------------------------------------------------------------------

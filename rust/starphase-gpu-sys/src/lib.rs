@@ -63,6 +63,8 @@ extern "C" {
     pub fn sp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut sp_ctx) -> c_int;
     pub fn sp_ctx_destroy(ctx: *mut sp_ctx);
     pub fn sp_ctx_synchronize(ctx: *mut sp_ctx) -> c_int;
+    pub fn sp_pinned_alloc(ctx: *mut sp_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn sp_pinned_free(ctx: *mut sp_ctx, p: *mut c_void);
     pub fn sp_version() -> *const c_char;
     pub fn sp_launch_count(ctx: *const sp_ctx) -> u64;
     pub fn sp_last_kernel_ms(ctx: *mut sp_ctx, which: c_int) -> f32;
@@ -125,7 +127,7 @@ extern "C" {
     // K9: the reference's affine cost model for selected pairs
     pub fn sp_align_affine_resident(ctx: *mut sp_ctx, texts: *const sp_targets, patterns: *const sp_targets, n_pairs: i64, pair_text: *const i32,
                                     pair_pattern: *const i32, win_begin: *const i32, win_end: *const i32, band_centre: *const i32, band: i32,
-                                    costs: *const sp_affine_costs, recs: *mut sp_align_rec, scores: *mut i32, cigar: *mut u32, cigar_cap: i64,
+                                    pair_band: *const i32, costs: *const sp_affine_costs, recs: *mut sp_align_rec, scores: *mut i32, cigar: *mut u32, cigar_cap: i64,
                                     cigar_used: *mut i64) -> c_int;
     // K7: consensus extension
     pub fn sp_consensus_create(ctx: *mut sp_ctx, reads: *const sp_seqset, offsets: *const i32, offset_window: i32, band: i32, max_tracks: i32,

@@ -54,15 +54,19 @@ def align_scored(orc, pattern: bytes, text: bytes, match_score: int) -> dict:
     u["score"] = dp_score_generic(u["cigar"], match_score)
     if not AFFINE_REFINE or not u["cigar"]:
         return u
-    d0, d1 = u["t_start"] - u["p_start"], u["t_end"] - u["p_end"]
-    w = (abs(d1 - d0) + 1) // 2 + u["nm"] + REFINE_SLACK
+    # the band: the diagonal hull of the unit-cost path (text column - pattern row along the CIGAR) widened by the slack
+    d = lo = hi = u["t_start"] - u["p_start"]
+    for ln, op in u["cigar"]:
+        d += -ln if op == 1 else ln if op == 2 else 0
+        lo, hi = min(lo, d), max(hi, d)
+    w = (hi - lo + 1) // 2 + REFINE_SLACK
     if w > REFINE_MAX_BAND:
         return u
     import oracle_util
 
     aff = _AFFINE.setdefault(match_score, oracle_util.AffineOracle((match_score, 4, 6, 2, 26, 1)))
-    band = 47 if w <= 47 else 79 if w <= 79 else 143 if w <= 143 else 255   # the band classes of the host
-    a = dict(aff.align(pattern, text, centre=(d0 + d1) // 2, band=band))  # floor: independent of the coordinate origin
+    band = 31 if w <= 31 else 63 if w <= 63 else 127 if w <= 127 else 255   # the band classes of the host
+    a = dict(aff.align(pattern, text, centre=(lo + hi) // 2, band=band))  # floor: independent of the coordinate origin
     if a["score"] == 0:
         a["dist"] = len(pattern)
     return a

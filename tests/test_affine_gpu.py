@@ -81,3 +81,30 @@ def test_affine_windows_and_nothing_to_align(ctx):
     with pytest.raises(sp.SpError):
         ctx.align_affine(T, P, [(0, 0)], ou.COSTS_MAP_HIFI, band=256)
     T.close(); P.close()
+
+
+def test_affine_band_per_pair(ctx, oracle):
+    """pair_band: every pair inside its own band (all four width classes in one call, run side by side), each equal to the CPU
+    model banded the same way -- including bands too narrow for the optimum, where the band decides the answer."""
+    alleles, reads, src, cdna = synth.hla_gene(synth.DEFAULT_SEED, "HLA-B", n_alleles=20, n_reads=4, with_cdna=True)
+    texts, pats = list(reads), list(alleles) + list(cdna[:6])
+    pairs = [(t, p) for t in range(len(texts)) for p in range(len(pats))]
+    widths = [3, 20, 31, 32, 63, 64, 100, 127, 128, 200, 255]
+    bands = [widths[k % len(widths)] for k in range(len(pairs))]
+    centres = []
+    for t, p in pairs:
+        u = oracle.align(pats[p], texts[t])
+        centres.append((u["t_start"] - u["p_start"] + u["t_end"] - u["p_end"]) // 2)
+    aff = ou.AffineOracle(ou.COSTS_ALLELE_SCORING)
+    T, P = ctx.targets(texts), ctx.targets(pats)
+    got = ctx.align_affine(T, P, pairs, ou.COSTS_ALLELE_SCORING, centres=centres, bands=bands)
+    for (t, p), c, b, g in zip(pairs, centres, bands, got):
+        want = aff.align(pats[p], texts[t], centre=c, band=b)
+        if want["score"] == 0:
+            want = dict(want, dist=len(pats[p]))
+        assert g == want, (t, p, c, b, {k: (g[k], want[k]) for k in g if g[k] != want[k] and k != "cigar"})
+    import pb_starphase_b200 as sp
+
+    with pytest.raises(sp.SpError):
+        ctx.align_affine(T, P, pairs[:2], ou.COSTS_ALLELE_SCORING, bands=[10, 256])
+    T.close(); P.close()
