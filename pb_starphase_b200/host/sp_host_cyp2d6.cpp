@@ -269,7 +269,7 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
             pair_item.push_back(it);
         }
         mark("windows", round, pairs.size());
-        const std::vector<Alignment> alns = gpu_.align_pairs(*resident_seqs, tmpl_patterns_->resident(), pairs, &windows, 1, &bounds);  // windows of resident reads
+        const std::vector<Alignment> alns = gpu_.align_pairs(*resident_seqs, tmpl_patterns_->resident(), pairs, &windows, 1, &bounds, aligner_stand_ins().min_dp_score);  // windows of resident reads
         mark("K4 align_pairs", round, pairs.size());
         std::vector<Item> next;
         for (size_t q = 0; q < pairs.size(); ++q) {

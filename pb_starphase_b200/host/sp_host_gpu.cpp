@@ -109,7 +109,7 @@ static long raw_dp_score(const uint32_t *cig, int32_t n, long a) {
 std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const ResidentSeqs &pats,
                                                const std::vector<std::pair<int32_t, int32_t>> &pairs,
                                                const std::vector<std::pair<int32_t, int32_t>> *windows, int match_score,
-                                               const std::vector<std::pair<int32_t, int32_t>> *bounds) {
+                                               const std::vector<std::pair<int32_t, int32_t>> *bounds, long report_floor) {
     if (pairs.empty()) return {};
     if (bounds && bounds->size() != pairs.size()) throw HostError("align_pairs: one bounds entry per pair expected");
     const UnitResult unit = align_pairs_unit(texts, pats, pairs, windows);
@@ -169,8 +169,9 @@ std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const 
         affine_entries_per_pair_ = std::max<int64_t>(affine_entries_per_pair_, 2 * used / static_cast<int64_t>(sel.size()) + 64);
     }
     std::vector<Alignment> out(pairs.size());
-    auto fill = [](Alignment &a, const sp_align_rec &r, const uint32_t *pool) {
+    auto fill = [](Alignment &a, const sp_align_rec &r, const uint32_t *pool, bool with_cigar) {
         a.dist = r.dist; a.nm = r.nm; a.p_start = r.p_start; a.p_end = r.p_end; a.t_start = r.t_start; a.t_end = r.t_end;
+        if (!with_cigar) return;
         a.cigar.reserve(static_cast<size_t>(r.n_cigar));
         const uint32_t *cg = pool + r.cigar_off;
         for (int32_t k = 0; k < r.n_cigar; ++k) a.cigar.emplace_back(cg[k] >> 4, static_cast<uint8_t>(cg[k] & 15u));
@@ -179,7 +180,7 @@ std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const 
     for (size_t q = 0; q < pairs.size(); ++q) {
         Alignment &a = out[q];
         if (k < sel.size() && sel[k] == q) {  // the mapping fields come from the affine alignment
-            fill(a, arecs[k], acig);
+            fill(a, arecs[k], acig, ascores[k] >= report_floor);
             a.refined = true;
             a.score = ascores[k];
             a.t_base = wb[k];
@@ -190,11 +191,11 @@ std::vector<Alignment> GpuAligner::align_pairs(const ResidentSeqs &texts, const 
             ++k;
         } else {
             const sp_align_rec &r = unit.recs[q];
-            fill(a, r, unit.cigar);
             if (match_score > 0) {
                 a.score = r.n_cigar ? raw_dp_score(unit.cigar + r.cigar_off, r.n_cigar, match_score) : 0;
                 a.t_base = windows ? (*windows)[q].first : 0;
             }
+            fill(a, r, unit.cigar, match_score <= 0 || a.score >= report_floor);
         }
     }
     return out;

@@ -229,7 +229,7 @@ std::vector<HlaRealigner::BestHit> HlaRealigner::best_hits(const std::vector<std
                     pairs.emplace_back(static_cast<int32_t>(r), cand[r * static_cast<size_t>(k) + static_cast<size_t>(q)]);
     }
     first_pair[reads.size()] = pairs.size();
-    std::vector<Alignment> alns = gpu_.align_pairs(*resident_reads, index_->resident(), pairs, nullptr, 1);  // both sides already on the device
+    std::vector<Alignment> alns = gpu_.align_pairs(*resident_reads, index_->resident(), pairs, nullptr, 1, nullptr, aligner_stand_ins().min_dp_score);  // both sides already on the device
 
     std::vector<BestHit> out(reads.size());
     for (size_t r = 0; r < reads.size(); ++r) {

@@ -261,11 +261,12 @@ class GpuAligner {
     // K4; with match_score > 0 (the `a` of the call site: 5 for allele scoring, 1 elsewhere) followed by K9: every placement whose
     // diagonal band fits (half width = half the diagonal hull of the unit-cost path + 24 <= 255) is re-aligned under the
     // reference's two-piece affine costs inside that band, within `bounds` (optional, per pair [lo, hi) of the text; default the
-    // whole text), and `score` is filled for every pair
+    // whole text), and `score` is filled for every pair; pairs scoring below report_floor come back without their CIGAR (callers
+    // that treat them as "no mapping" anyway save the decode of long junk CIGARs)
     std::vector<Alignment> align_pairs(const ResidentSeqs &texts, const ResidentSeqs &patterns,
                                        const std::vector<std::pair<int32_t, int32_t>> &pairs,
                                        const std::vector<std::pair<int32_t, int32_t>> *windows = nullptr, int match_score = 0,
-                                       const std::vector<std::pair<int32_t, int32_t>> *bounds = nullptr);
+                                       const std::vector<std::pair<int32_t, int32_t>> *bounds = nullptr, long report_floor = -(1l << 62));
     std::vector<sp_pair_rec> pair_minsum_topk(const DeviceMatrix &d, const DeviceMatrix *d2, int k);           // K2
     // K5; ranking key = dist_weight * distance + pattern_bias[p] (bias optional, one entry per pattern); dist returns the plain distance
     void row_topk(const DeviceMatrix &d, int k, std::vector<int32_t> &idx, std::vector<int32_t> &dist,
