@@ -326,6 +326,68 @@ std::vector<std::vector<AlleleMapping>> Cyp2d6Extractor::find_base_type_in_seque
     return out;
 }
 
+// src/cyp2d6/haplotyper.rs:326-361 + :371-468, batched
+std::vector<std::optional<Cyp2d6Region>> Cyp2d6Extractor::find_full_type_in_sequences(const SeqList &seqs, double max_missing_frac,
+                                                                                      bool force_assignment, const Cyp2d6TypingDb &db,
+                                                                                      size_t graph_band) {
+    const bool penalize_unmapped = true;  // :332
+    const std::vector<std::vector<AlleleMapping>> matches = find_base_type_in_sequences(seqs, penalize_unmapped, max_missing_frac);
+    std::vector<std::optional<Cyp2d6Region>> out(seqs.size());
+    std::vector<size_t> deep;  // sequences that go through assign_haplotype
+    for (size_t s = 0; s < seqs.size(); ++s) {
+        if (matches[s].empty()) continue;  // :340-342 "no matches found"
+        const AlleleMapping *best = &matches[s][0];  // :345-350: min_by keeps the first of equal minima
+        for (const AlleleMapping &m : matches[s])
+            if (m.mapping_stats.custom_score(penalize_unmapped) < best->mapping_stats.custom_score(penalize_unmapped)) best = &m;
+        bool is_mapped = false;
+        for (const Cyp2d6RegionLabel &l : db.mapped_hybrids)
+            is_mapped = is_mapped || (l.region_type == best->allele_label.region_type && l.subtype_label == best->allele_label.subtype_label);
+        if (is_mapped) {
+            deep.push_back(s);
+        } else {
+            Cyp2d6Region r;
+            r.label = best->allele_label;
+            out[s] = r;
+        }
+    }
+    if (deep.empty()) return out;
+    // :383-420: the consensus (query) on the backbone (target); one co-linear mapping per consensus here, where the reference
+    // takes the longest of minimap2's mappings
+    SeqList deep_seqs;
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    for (size_t k = 0; k < deep.size(); ++k) {
+        deep_seqs.push_back(seqs[deep[k]]);
+        pairs.emplace_back(0, static_cast<int32_t>(k));
+    }
+    const std::vector<Alignment> alns = gpu_.align_pairs(SeqList{db.backbone}, deep_seqs, pairs, nullptr, 1);
+    std::vector<VariantGraph> graphs(deep.size());
+    std::vector<const VariantGraph *> graph_ptrs;
+    SeqList sub_sequences;
+    for (size_t k = 0; k < deep.size(); ++k) {
+        const Alignment &a = alns[k];
+        if (a.cigar.empty() || a.score < aligner_stand_ins().min_dp_score)  // :398 assert!(!mappings.is_empty())
+            throw HostError("find_full_type_in_sequences: a consensus does not map onto the CYP2D6 backbone");
+        const size_t ts = static_cast<size_t>(a.t_start), te = static_cast<size_t>(a.t_end);
+        graphs[k] = VariantGraph::from_reference_variants(db.backbone.substr(ts, te - ts), db.backbone_start + ts, db.variants);  // :432-441
+        graph_ptrs.push_back(&graphs[k]);
+        sub_sequences.push_back(deep_seqs[k].substr(static_cast<size_t>(a.p_start), static_cast<size_t>(a.p_end - a.p_start)));  // :422-425
+    }
+    const std::vector<GraphAlignment> walks = graph_edit_distance(gpu_, graph_ptrs, sub_sequences, graph_band);  // :445
+    std::vector<std::vector<uint8_t>> vectors;
+    for (size_t k = 0; k < deep.size(); ++k) {
+        if (!walks[k].found) throw HostError("find_full_type_in_sequences: no graph alignment inside the band");
+        vectors.push_back(graph_alleles(graphs[k], walks[k], db.variants.size()));  // :452-468
+    }
+    const std::vector<HaplotypeAssignment> assigned = assign_haplotypes_from_alleles(gpu_, vectors, db.haplotype_lookup, db.metadata, force_assignment);
+    for (size_t k = 0; k < deep.size(); ++k) {
+        Cyp2d6Region r;
+        r.label = assigned[k].label;
+        r.variants = assigned[k].variants;
+        out[deep[k]] = r;
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------
 // allele-vector typing (src/cyp2d6/haplotyper.rs:452-601)
 // ------------------------------------------------------------------------------------------

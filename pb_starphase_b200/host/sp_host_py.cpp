@@ -353,6 +353,38 @@ PYBIND11_MODULE(_starphase_host, m) {
         }
         return out;
     });
+    // find_full_type_in_sequences: db = (backbone, backbone_start, variants [(pos, ref, alt)], metadata [(label, is_vi)],
+    // haplotype lookup {star: 0/1 vector}, mapped hybrids [(type, subtype)]); per sequence None or (type, subtype, variants JSON or None)
+    m.def("find_full_type_in_sequences", [](GpuAligner &g, const std::vector<std::tuple<std::string, std::optional<std::string>, std::string>> &templates,
+                                            const SeqList &seqs, double max_missing_frac, bool force_assignment, const std::string &backbone,
+                                            size_t backbone_start, const std::vector<std::tuple<size_t, std::string, std::string>> &variants,
+                                            const std::vector<std::pair<std::string, bool>> &metadata,
+                                            const std::map<std::string, std::vector<uint8_t>> &lookup,
+                                            const std::vector<std::pair<std::string, std::optional<std::string>>> &mapped_hybrids, size_t graph_band) {
+        std::vector<std::pair<Cyp2d6RegionLabel, std::string>> ts;
+        for (const auto &t : templates) ts.push_back({Cyp2d6RegionLabel{region_type_from_name(std::get<0>(t)), std::get<1>(t)}, std::get<2>(t)});
+        Cyp2d6Extractor ex(g, std::move(ts));
+        Cyp2d6TypingDb db;
+        db.backbone = backbone; db.backbone_start = backbone_start; db.haplotype_lookup = lookup;
+        for (const auto &v : variants) db.variants.push_back({std::get<0>(v), std::get<1>(v), std::get<2>(v)});
+        for (const auto &v : metadata) db.metadata.push_back({v.first, v.second});
+        for (const auto &h : mapped_hybrids) db.mapped_hybrids.push_back(Cyp2d6RegionLabel{region_type_from_name(h.first), h.second});
+        py::list out;
+        for (const std::optional<Cyp2d6Region> &r : ex.find_full_type_in_sequences(seqs, max_missing_frac, force_assignment, db, graph_band)) {
+            if (!r) { out.append(py::none()); continue; }
+            py::object rv = py::none();
+            if (r->variants) {
+                Json arr = Json::array();
+                for (const RegionVariant &v : *r->variants) arr.push(v.to_json());
+                rv = py::str(arr.pretty());
+            }
+            py::object sub = r->label.subtype_label ? py::object(py::str(*r->label.subtype_label)) : py::object(py::none());
+            out.append(py::make_tuple(region_type_name(r->label.region_type), sub, rv));
+        }
+        return out;
+    }, py::arg("gpu"), py::arg("templates"), py::arg("sequences"), py::arg("max_missing_frac"), py::arg("force_assignment"), py::arg("backbone"),
+       py::arg("backbone_start"), py::arg("variants"), py::arg("metadata"), py::arg("haplotype_lookup"), py::arg("mapped_hybrids"),
+       py::arg("graph_band") = 128);
     m.def("overlap_score", &overlap_score);
     m.def("region_variant_string", [](const std::string &label, bool is_vi, int state) {
         return RegionVariant{label, is_vi, static_cast<VariantAlleleRelationship>(state)}.to_string();

@@ -583,6 +583,7 @@ double overlap_score(size_t s1, size_t e1, size_t s2, size_t e2);
 
 // The search half of Cyp2d6Extractor (src/cyp2d6/haplotyper.rs:142-315): which of the D6 / D7 / hybrid / REP / spacer /
 // link / *5 templates (generate_cyp_hybrids, src/cyp2d6/definitions.rs:346-464) occur where in a sequence.
+struct Cyp2d6TypingDb;
 class Cyp2d6Extractor {
   public:
     // hybrid_sequences: (label, template sequence); iterated in full_allele() string order like :175-183
@@ -595,6 +596,14 @@ class Cyp2d6Extractor {
     std::vector<std::vector<AlleleMapping>> find_base_type_in_sequences(const SeqList &search_sequences, bool penalize_unmapped,
                                                                         double max_missing_frac);
     const std::vector<std::pair<Cyp2d6RegionLabel, std::string>> &hybrid_sequences() const { return templates_; }
+    // find_full_type_in_sequence (:326-361) for a batch of consensuses: template search with unmapped bases penalised, the
+    // lowest-scoring match (first on ties); a match listed in db.mapped_hybrids goes through assign_haplotype (:371-601):
+    // the consensus is mapped onto the backbone (K4 + K9, a = 1), the variant graph of the aligned backbone stretch is built
+    // and the aligned part of the consensus aligned to it end to end (K8), the traversed nodes give the allele vector, K6
+    // scores it against every haplotype definition.  nullopt = "no matches found" (the reference's error).
+    std::vector<std::optional<Cyp2d6Region>> find_full_type_in_sequences(const SeqList &search_sequences, double max_missing_frac,
+                                                                         bool force_assignment, const Cyp2d6TypingDb &db,
+                                                                         size_t graph_band = 128);
 
   private:
     GpuAligner &gpu_;
@@ -711,6 +720,15 @@ struct GraphAlignment {  // WFAResult: score() and traversed_nodes()
     bool found = false;   // false: the band excluded every path
     size_t score = 0;
     std::vector<size_t> traversed_nodes;
+};
+// what assign_haplotype reads from the config, the reference genome and the database (src/cyp2d6/haplotyper.rs:40-130, :371-452)
+struct Cyp2d6TypingDb {
+    std::string backbone;                 // reference[backbone_start, backbone_start + |backbone|): cyp_coordinates["CYP2D6_wfa_backbone"]
+    size_t backbone_start = 0;
+    std::vector<GraphVariant> variants;   // loaded_variants.ordered_variants(), reference coordinates
+    std::vector<VariantMetadata> metadata;                            // same order
+    std::map<std::string, std::vector<uint8_t>> haplotype_lookup;     // star allele -> 0/1 vector (:40-70)
+    std::vector<Cyp2d6RegionLabel> mapped_hybrids;                    // labels that go through deep genotyping (:117-124)
 };
 // edit_distance_with_pruning for a batch: one (graph, sequence) problem per entry, one device call
 std::vector<GraphAlignment> graph_edit_distance(GpuAligner &gpu, const std::vector<const VariantGraph *> &graphs, const SeqList &sequences,

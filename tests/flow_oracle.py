@@ -356,6 +356,38 @@ def dp_score_a1(cigar) -> int:
     return s
 
 
+def find_full_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missing_frac: float, force_assignment: bool, db: dict,
+                                graph_band: int = 128):
+    """find_full_type_in_sequence + assign_haplotype (src/cyp2d6/haplotyper.rs:326-361, :371-601) as
+    Cyp2d6Extractor::find_full_type_in_sequences runs them.  db: backbone (bytes), backbone_start, variants [(pos, ref, alt)],
+    metadata [(label, is_vi)], haplotype_lookup {star: 0/1 list}, mapped_hybrids [(type, subtype)].
+    Per sequence: None ("no matches found") or ((region type, subtype), region variants or None)."""
+    import graph_oracle as go
+
+    by_name = {so.RegionLabel(t[0], t[1]).full_allele(): (t[0], t[1]) for t in templates}
+    out = []
+    for seq, hits in zip(seqs, find_base_type_in_sequences(orc, templates, seqs, max_missing_frac)):
+        if not hits:
+            out.append(None)
+            continue
+        best = min(hits, key=lambda h: so.MappingStats(*h[3]).custom_score(True))  # the first of equal minima, like min_by
+        label = by_name[best[0]]
+        if label not in [tuple(x) for x in db["mapped_hybrids"]]:
+            out.append((label, None))
+            continue
+        a = align_scored(orc, seq, db["backbone"], 1)  # the consensus (query) on the backbone (target)
+        assert a["cigar"] and a["score"] >= 200
+        ts, te = a["t_start"], a["t_end"]
+        g = go.build_graph(db["backbone"][ts:te], db["backbone_start"] + ts, db["variants"])
+        score, nodes = go.align(g, seq[a["p_start"]:a["p_end"]], band=graph_band)
+        assert score < go.INF
+        vec = so.alleles_from_traversal(len(db["variants"]), nodes, g.node_to_alleles)
+        star, rv, _ = so.assign_haplotype_from_alleles(vec, db["haplotype_lookup"], [m[0] for m in db["metadata"]],
+                                                       [m[1] for m in db["metadata"]], force_assignment)
+        out.append(((so.UNKNOWN, None) if star is None else (so.CYP2D6, star), rv))
+    return out
+
+
 def find_base_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missing_frac: float):
     """templates: [(region_type, subtype, sequence bytes)].  Same search as Cyp2d6Extractor::find_base_type_in_sequences
     in pb_starphase_b200/host/sp_host_cyp2d6.cpp, but every traceback runs over the whole (sub)segment with the oracle's

@@ -106,3 +106,61 @@ def test_cyp2d6_sized_typing_and_k6_handoff():
     for o, vec in zip(out, vectors):
         want = so.assign_haplotype_from_alleles(vec, haps, [m[0] for m in meta], [m[1] for m in meta], True)
         assert (o[0], tuple(o[2])) == (want[0], want[2])
+
+
+def test_find_full_type_in_sequences_vs_oracle(oracle):
+    """find_full_type_in_sequence end to end (src/cyp2d6/haplotyper.rs:326-361, :371-601): template search, consensus -> backbone
+    mapping (K4 + K9), variant graph of the aligned stretch, K8, allele vector, K6 -- the C++ host against the same flow on
+    oracle numbers; consensuses built from known haplotypes come back as those haplotypes."""
+    import json
+
+    import flow_oracle as fo
+    from pb_starphase_b200 import _starphase_host as host
+    from pb_starphase_b200 import synth
+
+    c = synth.cyp2d6_diploid_sample(2001)
+    templates = [(t, s, q) for (t, s), q in zip(c["template_labels"], c["templates"])]
+    d6 = next(q for t, s, q in templates if t == "CYP2D6" and s is None)
+    d7 = next(q for t, s, q in templates if t == "CYP2D7" and s is None)
+    rng = np.random.default_rng(9)
+    start = 42_100_000
+    backbone = rnd(rng, 300) + d6 + rnd(rng, 300)
+    pos = sorted(int(x) for x in rng.choice(np.arange(60, len(d6) - 60, 16), size=120, replace=False))
+    variants = []
+    for k, p in enumerate(pos):
+        if k % 6 == 5:
+            variants.append((start + 300 + p, d6[p:p + 3], d6[p:p + 1]))
+        elif k % 6 == 4:
+            variants.append((start + 300 + p, d6[p:p + 1], d6[p:p + 1] + b"TC"))
+        else:
+            variants.append((start + 300 + p, d6[p:p + 1], bytes([b"ACGT"[(b"ACGT".index(d6[p]) + 1 + k % 3) % 4]])))
+    haps = {f"{h + 2}.001": [int(x) for x in (rng.random(len(variants)) < 0.03 * (h + 1))] for h in range(3)}
+    haps["1.001"] = [0] * len(variants)
+    seqs, truth = [], []
+    for name, vec in haps.items():
+        s = d6
+        for (p, r, a), on in sorted(zip(variants, vec), reverse=True):
+            if on:
+                q = p - start - 300
+                assert s[q:q + len(r)] == r
+                s = s[:q] + a + s[q + len(r):]
+        noisy, _ = synth.hifi_reads(rng, [s], 1, err=0.0005, flank=0, lo=0, hi=1 << 20)
+        seqs.append(noisy[0])
+        truth.append(("CYP2D6", name))
+    seqs += [d7, rnd(rng, 3000), seqs[1][400:5200]]  # a D7 consensus, junk, an incomplete D6 consensus
+    meta = [(f"rs{k}", k % 5 == 0) for k in range(len(variants))]
+    mapped = [("CYP2D6", None), ("Hybrid", "CYP2D6::CYP2D7::exon9")]
+    db = dict(backbone=backbone, backbone_start=start, variants=variants, metadata=meta, haplotype_lookup=haps, mapped_hybrids=mapped)
+    want = fo.find_full_type_in_sequences(oracle, templates, seqs, 0.5, True, db, 96)
+    gpu = host.GpuAligner(0)
+    got = host.find_full_type_in_sequences(gpu, [(t, s, q.decode()) for t, s, q in templates], [s.decode() for s in seqs], 0.5, True,
+                                           backbone.decode(), start, [(p, r.decode(), a.decode()) for p, r, a in variants], meta, haps, mapped, 96)
+    assert len(got) == len(want) == len(seqs)
+    for g, w in zip(got, want):
+        if w is None:
+            assert g is None
+            continue
+        assert (g[0], g[1]) == w[0]
+        assert (json.loads(g[2]) if g[2] is not None else None) == w[1]
+    assert [w[0] for w in want[:len(truth)]] == truth
+    assert want[len(truth)][0] == ("CYP2D7", None) and want[len(truth) + 1] is None
