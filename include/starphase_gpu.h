@@ -333,6 +333,24 @@ sp_status sp_consensus_reset(sp_consensus *c, int32_t track);
  *           cost once the consensus has grown past its end. */
 sp_status sp_consensus_extend(sp_consensus *c, int32_t n_tasks, const int32_t *src, const uint8_t *symbols, const int32_t *dst,
                               int32_t *ed, uint8_t *votes, int32_t *full);
+/* The extension step in a loop on the device, for the stretches of a search where the reads agree (most of a consensus): starting
+ * from a node -- one consensus (n_sides = 1) or a dual pair (2), tracks src[], with the per-read state ed / votes / full
+ * ([n_sides][n_reads]) the step that made it returned -- keep appending while every side has at most one symbol with the votes and
+ * at least one side has one, the extended node orders before the best competitor of the caller's search -- cost < cost_limit, or
+ * cost == cost_limit and total length > size_limit -- its cost is <= cost_cap, and fewer than max_steps rounds were done.
+ * Vote rule: a read votes when it is active and not already consumed at a better column (full >= ed), one vote split evenly over
+ * its candidate symbols; in a dual node a read counts towards, and votes for, the side(s) it is closest to (cost = 0 while
+ * inactive, else min(ed, full)); a symbol passes with >= min_count votes and >= min_af_permille / 1000 of its side's votes; when
+ * none passes the first best-voted symbol does; a side nobody votes on is finished and stays as it is.  Node cost = sum over reads
+ * of the cost to the closest side.  On return dst[] hold the tracks of the last node, ed / votes / full its state, steps[q] the
+ * symbols of round q (low nibble: code 0..3 = ACGT appended to side 0, high nibble: side 1; 15 = side not extended) and *n_steps
+ * the number of rounds (0: the start node does not qualify; dst[] are then copies of src[]).  The read set has to fit on chip:
+ * sp_consensus_run_supported() tells (<= 2,048 read-sides, band <= 255 + window, reads <= 60,000 bases); SP_ERR_RANGE otherwise.
+ * src / dst as for sp_consensus_extend (dst[s] may equal src[s]). */
+int32_t sp_consensus_run_supported(const sp_consensus *c, int32_t n_sides);
+sp_status sp_consensus_run(sp_consensus *c, int32_t n_sides, const int32_t *src, const int32_t *dst, int32_t *ed, uint8_t *votes,
+                           int32_t *full, int32_t min_count, int32_t min_af_permille, int64_t cost_limit, int64_t size_limit,
+                           int64_t cost_cap, int32_t max_steps, uint8_t *steps, int32_t *n_steps);
 
 /* ---- K8: sequence-to-variant-graph alignment (row N3 of SURVEY.md 8f) ------------------------- */
 /* The forward half of what Cyp2d6Extractor::assign_haplotype gets from hiphase's WFAGraph::edit_distance_with_pruning

@@ -100,6 +100,9 @@ SIGNATURES = {
     "sp_consensus_num_tracks": (C.c_int32, [_P]),
     "sp_consensus_reset": (C.c_int, [_P, C.c_int32]),
     "sp_consensus_extend": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "sp_consensus_run_supported": (C.c_int32, [_P, C.c_int32]),
+    "sp_consensus_run": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P,
+                         C.POINTER(C.c_int32)]),
     "sp_graph_align": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "sp_comm_unique_id": (C.c_int, [_P]),
     "sp_comm_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),

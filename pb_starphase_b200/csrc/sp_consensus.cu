@@ -1,6 +1,8 @@
 // sp_consensus.cu -- K7 host side: sp_consensus_* (include/starphase_gpu.h), row N1 of SURVEY.md 8f.
 #include "sp_internal.cuh"
 
+#include <cstring>
+
 #include "sp_consensus.cuh"
 
 using namespace sp;
@@ -15,6 +17,12 @@ struct sp_consensus {
     int32_t *d_src = nullptr, *d_dst = nullptr, *d_ed = nullptr, *d_full = nullptr;
     uint8_t *d_sym = nullptr, *d_votes = nullptr;
     int task_cap = 0;
+    // sp_consensus_run: node state in / out, step log, step count
+    // one device block and its page-locked mirror: [n_steps, pad x 3 | ed | full | votes] for 2 x n_reads read-sides; the log apart
+    uint8_t *d_run = nullptr, *h_run = nullptr, *d_run_log = nullptr, *h_run_log = nullptr;
+    int run_log_cap = 0;
+    bool run_attr_set[4] = {false, false, false, false};
+    int max_read_len = 0;
 };
 
 static uint8_t code_of(uint8_t c) {
@@ -43,6 +51,7 @@ extern "C" sp_status sp_consensus_create(sp_ctx *ctx, const sp_seqset *reads, co
     if (!c) return fail(ctx, SP_ERR_NOMEM, "out of host memory");
     c->ctx = ctx; c->n_reads = static_cast<int>(reads->n); c->n_tracks = max_tracks; c->W = W; c->half_window = offset_window / 2;
     c->cells = (2 * W + 1 + 31) / 32;
+    for (int64_t i = 0; i < reads->n; ++i) c->max_read_len = std::max<int>(c->max_read_len, static_cast<int>(std::min<int64_t>(reads->offsets[i + 1] - reads->offsets[i], 0x7FFFFFFF)));
     const int64_t base0 = reads->n ? reads->offsets[0] : 0, nbytes = reads->n ? reads->offsets[reads->n] - base0 : 0;
     std::vector<uint8_t> codes(static_cast<size_t>(std::max<int64_t>(nbytes, 1)));
     for (int64_t i = 0; i < nbytes; ++i) codes[static_cast<size_t>(i)] = code_of(reads->bases[base0 + i]);
@@ -85,6 +94,8 @@ extern "C" void sp_consensus_destroy(sp_consensus *c) {
     dev_free(ctx, c->d_codes); dev_free(ctx, c->d_roffs); dev_free(ctx, c->d_offset); dev_free(ctx, c->d_band);
     dev_free(ctx, c->d_best_full); dev_free(ctx, c->d_track_len);
     dev_free(ctx, c->d_src); dev_free(ctx, c->d_dst); dev_free(ctx, c->d_ed); dev_free(ctx, c->d_full); dev_free(ctx, c->d_sym); dev_free(ctx, c->d_votes);
+    dev_free(ctx, c->d_run); dev_free(ctx, c->d_run_log);
+    cudaFreeHost(c->h_run); cudaFreeHost(c->h_run_log);
     delete c;
 }
 
@@ -165,5 +176,124 @@ extern "C" sp_status sp_consensus_extend(sp_consensus *c, int32_t n_tasks, const
     SP_CUDA(ctx, cudaMemcpyAsync(full, c->d_full, per * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SP_CUDA(ctx, cudaMemcpyAsync(votes, c->d_votes, per, cudaMemcpyDeviceToHost, ctx->stream));
     SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SP_OK;
+}
+
+// ---- sp_consensus_run: K7 in a loop on the device (k7_run) ----
+namespace {
+struct RunPlan {
+    int cells = 0, n_cta = 0;
+    size_t smem = 0, smem_max = 0;  // of this launch; of the larger of the 1- and 2-sided launches (the attribute is set once)
+};
+// cells per lane rounded up to {2, 4, 8, 16}; cluster size and shared memory of one CTA; n_cta = 0: does not fit
+RunPlan plan_run(const sp_consensus *c, int n_sides) {
+    RunPlan pl;
+    const int nb = 2 * c->W + 1, items = c->n_reads * n_sides;
+    if (nb > 511 || items < 1 || items > 2048 || c->max_read_len > 60000) return pl;  // columns are kept as u16
+    pl.cells = nb < 64 ? 2 : nb < 128 ? 4 : nb < 256 ? 8 : 16;
+    const int nwarps = K7_RUN_THREADS / 32;
+    int n_cta = 1;
+    while (n_cta < 8 && n_cta * nwarps < items) n_cta *= 2;
+    if (const char *force = getenv("SP_K7_RUN_CTAS")) n_cta = std::max(1, std::min(8, atoi(force)));  // measurement hook
+    const int per_warp = (items + n_cta * nwarps - 1) / (n_cta * nwarps);
+    // K7Item + column (u16) + code ring (2 bytes per cell) per slot; ed / full / votes double-buffered per item
+    pl.smem = static_cast<size_t>(nwarps) * per_warp * (sizeof(K7Item) + static_cast<size_t>(pl.cells) * 32 * 4) + static_cast<size_t>(items) * 18 + 16;
+    const size_t room = static_cast<size_t>(std::max(c->ctx->smem_optin - 1024, 0));  // the kernel's few static bytes come out of the same budget
+    if (pl.smem > room) return pl;
+    pl.smem_max = room;
+    pl.n_cta = n_cta;
+    return pl;
+}
+template <int CELLS>
+cudaError_t launch_run(const ConsRunParams &prm, const RunPlan &pl, cudaStream_t stream, bool &attr_set) {
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(k7_run<CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_max));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(pl.n_cta)); cfg.blockDim = dim3(K7_RUN_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(pl.n_cta); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k7_run<CELLS>, prm);
+}
+}  // namespace
+
+extern "C" int32_t sp_consensus_run_supported(const sp_consensus *c, int32_t n_sides) {
+    if (!c || n_sides < 1 || n_sides > 2) return 0;
+    return plan_run(c, n_sides).n_cta > 0 ? 1 : 0;
+}
+
+extern "C" sp_status sp_consensus_run(sp_consensus *c, int32_t n_sides, const int32_t *src, const int32_t *dst, int32_t *ed, uint8_t *votes,
+                                      int32_t *full, int32_t min_count, int32_t min_af_permille, int64_t cost_limit, int64_t size_limit,
+                                      int64_t cost_cap, int32_t max_steps, uint8_t *steps, int32_t *n_steps) {
+    if (!c) return SP_ERR_INVALID;
+    sp_ctx *ctx = c->ctx;
+    if (n_sides < 1 || n_sides > 2 || !src || !dst || !ed || !votes || !full || !steps || !n_steps || max_steps < 1 || min_count < 0 ||
+        min_af_permille < 0 || min_af_permille > 1000)
+        return fail(ctx, SP_ERR_INVALID, "sp_consensus_run: bad argument");
+    *n_steps = 0;
+    for (int s = 0; s < n_sides; ++s)
+        if (src[s] < 0 || src[s] >= c->n_tracks || dst[s] < 0 || dst[s] >= c->n_tracks) return fail(ctx, SP_ERR_INVALID, "sp_consensus_run: track out of range");
+    if (n_sides == 2 && (dst[0] == dst[1] || dst[0] == src[1] || dst[1] == src[0]))
+        return fail(ctx, SP_ERR_INVALID, "sp_consensus_run: the two sides need separate destination tracks");
+    if (c->n_reads == 0) return SP_OK;
+    const RunPlan pl = plan_run(c, n_sides);
+    if (pl.n_cta == 0) return fail(ctx, SP_ERR_RANGE, "sp_consensus_run: the read set does not fit on chip (sp_consensus_run_supported)");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t items = static_cast<size_t>(c->n_reads) * n_sides, cap = static_cast<size_t>(c->n_reads) * 2;
+    const size_t o_ed = 16, o_full = o_ed + cap * 4, o_votes = o_full + cap * 4, block = o_votes + (cap + 3) / 4 * 4;
+    constexpr int kLogHead = 256;  // log bytes fetched with the state; longer runs take one more copy
+    if (!c->d_run) {
+        SP_CUDA(ctx, dev_malloc(ctx, &c->d_run, block));
+        SP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&c->h_run), block, cudaHostAllocDefault));
+    }
+    if (max_steps > c->run_log_cap) {
+        cudaStreamSynchronize(ctx->stream);
+        dev_free(ctx, c->d_run_log);
+        cudaFreeHost(c->h_run_log);
+        c->d_run_log = nullptr; c->h_run_log = nullptr; c->run_log_cap = 0;
+        const int want = std::max(max_steps, kLogHead);
+        SP_CUDA(ctx, dev_malloc(ctx, &c->d_run_log, static_cast<size_t>(want)));
+        SP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&c->h_run_log), static_cast<size_t>(want), cudaHostAllocDefault));
+        c->run_log_cap = want;
+    }
+    std::memset(c->h_run, 0, 16);
+    std::memcpy(c->h_run + o_ed, ed, items * 4);
+    std::memcpy(c->h_run + o_full, full, items * 4);
+    std::memcpy(c->h_run + o_votes, votes, items);
+    SP_CUDA(ctx, cudaMemcpyAsync(c->d_run, c->h_run, block, cudaMemcpyHostToDevice, ctx->stream));
+    ConsRunParams prm;
+    prm.codes = c->d_codes; prm.roffs = c->d_roffs; prm.offset = c->d_offset; prm.band = c->d_band; prm.best_full = c->d_best_full;
+    prm.track_len = c->d_track_len; prm.n_reads = c->n_reads; prm.W = c->W; prm.half_window = c->half_window; prm.n_sides = n_sides;
+    for (int s = 0; s < 2; ++s) { prm.src[s] = src[s < n_sides ? s : 0]; prm.dst[s] = dst[s < n_sides ? s : 0]; }
+    prm.ed = reinterpret_cast<int32_t *>(c->d_run + o_ed); prm.full = reinterpret_cast<int32_t *>(c->d_run + o_full); prm.votes = c->d_run + o_votes;
+    prm.min_units = 12 * min_count; prm.permille = min_af_permille; prm.cost_limit = cost_limit; prm.size_limit = size_limit; prm.cost_cap = cost_cap; prm.max_steps = max_steps;
+    prm.log = c->d_run_log; prm.n_steps = reinterpret_cast<int *>(c->d_run);
+    const int ci = pl.cells == 2 ? 0 : pl.cells == 4 ? 1 : pl.cells == 8 ? 2 : 3;
+    ev_begin(ctx, 4);
+    cudaError_t e = ci == 0 ? launch_run<2>(prm, pl, ctx->stream, c->run_attr_set[0]) : ci == 1 ? launch_run<4>(prm, pl, ctx->stream, c->run_attr_set[1])
+                    : ci == 2 ? launch_run<8>(prm, pl, ctx->stream, c->run_attr_set[2]) : launch_run<16>(prm, pl, ctx->stream, c->run_attr_set[3]);
+    SP_CUDA(ctx, e);
+    ++ctx->launches;
+    ev_end(ctx, 4);
+    const int head = std::min(max_steps, kLogHead);
+    SP_CUDA(ctx, cudaMemcpyAsync(c->h_run, c->d_run, block, cudaMemcpyDeviceToHost, ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(c->h_run_log, c->d_run_log, static_cast<size_t>(head), cudaMemcpyDeviceToHost, ctx->stream));
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int done = 0;
+    std::memcpy(&done, c->h_run, sizeof(int));
+    if (done > head) {
+        SP_CUDA(ctx, cudaMemcpyAsync(c->h_run_log + head, c->d_run_log + head, static_cast<size_t>(done - head), cudaMemcpyDeviceToHost, ctx->stream));
+        SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    std::memcpy(ed, c->h_run + o_ed, items * 4);
+    std::memcpy(full, c->h_run + o_full, items * 4);
+    std::memcpy(votes, c->h_run + o_votes, items);
+    if (done > 0) std::memcpy(steps, c->h_run_log, static_cast<size_t>(done));
+    if (getenv("SP_TIMING")) fprintf(stderr, "[sp_timing] k7_run %d sides %d steps %.1f us\n", n_sides, done, 1e3 * sp_last_kernel_ms(ctx, 4));
+    *n_steps = done;
     return SP_OK;
 }

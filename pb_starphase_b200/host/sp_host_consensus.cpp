@@ -10,10 +10,18 @@
 // the consensus it is closer to; at most max_capacity_per_size nodes are expanded per total length and the queue keeps the
 // max_queue_size best nodes; a node nobody votes on is complete, and the cheapest complete nodes are the answer (a dual
 // answer needs min_count reads and a min_af share on its minor side).  Every expansion is ONE device call covering all
-// (consensus, symbol) extensions of the node.  This restates the published outline of waffle_con's search, not its code.
+// (consensus, symbol) extensions of the node -- and a node with a single way forward (one symbol with the votes per side, which is
+// most of a consensus) is handed to the device together with the cost of the best competitor: sp_consensus_run keeps extending it
+// on chip for as long as this loop would have popped its child next, and returns the last child (identical search, ~1 us instead
+// of ~25 us per symbol).  This restates the published outline of waffle_con's search, not its code.
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <map>
 #include <memory>
 #include <set>
 
@@ -101,7 +109,9 @@ struct Search {
     const SeqList &reads;
     sp_consensus *h = nullptr;
     TrackPool pool;
-    size_t n_calls = 0;
+    size_t n_calls = 0, n_run_steps = 0;
+    double run_seconds = 0.0;  // inside sp_consensus_run (diagnostic)
+    bool can_run[3] = {false, false, false};  // sp_consensus_run fits for 1 / 2 sides
     Search(GpuAligner &g, const CdwfaConfig &c, const SeqList &r, const std::vector<int32_t> &offsets)
         : gpu(g), cfg(c), reads(r), pool(256) {
         std::string bases;
@@ -112,8 +122,71 @@ struct Search {
         const sp_status st = sp_consensus_create(gpu.raw(), &set, offsets.data(), static_cast<int32_t>(cfg.offset_window), static_cast<int32_t>(cfg.band),
                                                  256, &h);
         if (st != SP_OK) throw HostError(std::string("sp_consensus_create: ") + sp_last_error(gpu.raw()));
+        const bool on = getenv("SP_CONSENSUS_NO_RUN") == nullptr;  // A/B switch for measurements: step every symbol from the host
+        can_run[1] = on && sp_consensus_run_supported(h, 1) != 0;
+        can_run[2] = on && sp_consensus_run_supported(h, 2) != 0;
     }
-    ~Search() { sp_consensus_destroy(h); }
+    ~Search() {
+        if (getenv("SP_TIMING"))
+            fprintf(stderr, "[sp_timing] consensus search: %zu device calls, %zu symbols appended on the device in %.1f ms\n", n_calls, n_run_steps,
+                    1e3 * run_seconds);
+        sp_consensus_destroy(h);
+    }
+
+    // the node has one way forward: let the device follow it (see the header of this file).  Returns the last child, or nullptr
+    // when the device took no step; `expanded` gets the nodes expanded on the way.
+    std::shared_ptr<Node> run_on_device(const Node &node, long cost_limit, long size_limit, long cost_cap, std::map<size_t, size_t> &expanded) {
+        static const char kSym[4] = {'A', 'C', 'G', 'T'};
+        const int ns = node.dual ? 2 : 1;
+        const size_t R = reads.size(), s0 = node.size();
+        // every node expanded on the way must be below the per-size capacity: stop before the first size that is full
+        size_t first_full = static_cast<size_t>(-1);
+        for (auto it = expanded.upper_bound(s0); it != expanded.end(); ++it)
+            if (it->second >= cfg.max_capacity_per_size) { first_full = it->first; break; }
+        size_t max_steps = 1 << 16;
+        if (first_full != static_cast<size_t>(-1)) max_steps = std::min<size_t>(max_steps, node.dual ? (first_full - s0 - 1) / 2 + 1 : first_full - s0);
+        SidePtr out[2];
+        int32_t src[2] = {0, 0}, dst[2] = {0, 0};
+        std::vector<int32_t> ed(R * static_cast<size_t>(ns)), full(R * static_cast<size_t>(ns));
+        std::vector<uint8_t> votes(R * static_cast<size_t>(ns)), log(max_steps);
+        for (int s = 0; s < ns; ++s) {
+            const Side &from = s == 0 ? *node.s1 : *node.s2;
+            out[s] = std::make_shared<Side>();
+            out[s]->pool = &pool;
+            out[s]->track = pool.take();
+            src[s] = from.track; dst[s] = out[s]->track;
+            std::copy(from.ed.begin(), from.ed.end(), ed.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R));
+            std::copy(from.full.begin(), from.full.end(), full.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R));
+            std::copy(from.votes.begin(), from.votes.end(), votes.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R));
+        }
+        int32_t n = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        const sp_status st = sp_consensus_run(h, ns, src, dst, ed.data(), votes.data(), full.data(), static_cast<int32_t>(cfg.min_count),
+                                              static_cast<int32_t>(std::lround(cfg.min_af * 1000.0)), static_cast<int64_t>(cost_limit),
+                                              static_cast<int64_t>(size_limit), static_cast<int64_t>(cost_cap), static_cast<int32_t>(max_steps),
+                                              log.data(), &n);
+        run_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (st != SP_OK) throw HostError(std::string("sp_consensus_run: ") + sp_last_error(gpu.raw()));
+        ++n_calls;
+        if (getenv("SP_CONSENSUS_DEBUG"))
+            fprintf(stderr, "[consensus] run: dual %d size %zu cost %ld limit (%ld, %ld) cap %ld max_steps %zu -> %d steps\n", node.dual ? 1 : 0, s0,
+                    node.cost, cost_limit, size_limit, cost_cap, max_steps, n);
+        if (n == 0) return nullptr;
+        n_run_steps += static_cast<size_t>(n);
+        std::string c1 = node.c1, c2 = node.c2;
+        for (int32_t q = 0; q < n; ++q) {
+            if (q > 0) ++expanded[c1.size() + (node.dual ? c2.size() : 0)];  // the node this round expanded (round 0: counted by the caller)
+            const int a = log[static_cast<size_t>(q)] & 15, b = log[static_cast<size_t>(q)] >> 4;
+            if (a < 4) c1.push_back(kSym[a]);
+            if (node.dual && b < 4) c2.push_back(kSym[b]);
+        }
+        for (int s = 0; s < ns; ++s) {
+            out[s]->ed.assign(ed.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R), ed.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s + 1) * R));
+            out[s]->full.assign(full.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R), full.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s + 1) * R));
+            out[s]->votes.assign(votes.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s) * R), votes.begin() + static_cast<std::ptrdiff_t>(static_cast<size_t>(s + 1) * R));
+        }
+        return make(std::move(c1), out[0], node.dual, std::move(c2), node.dual ? out[1] : nullptr);
+    }
 
     // one device call: every (parent side, symbol) of the list; symbol 0 = report the fresh track
     std::vector<SidePtr> extend(const std::vector<std::pair<const Side *, char>> &tasks) {
@@ -200,6 +273,21 @@ struct Search {
             size_t &cnt = expanded[node->size()];
             if (cnt >= cfg.max_capacity_per_size) continue;
             ++cnt;
+            const bool one_way = node->dual ? (p1.size() <= 1 && p2.size() <= 1) : p1.size() == 1;
+            if (one_way && can_run[node->dual ? 2 : 1]) {
+                // the child is popped next for as long as it orders before every other node (cheaper, or as cheap and longer; equal
+                // on both: the strings decide, here) and is not dearer than the best answer
+                const long kMax = std::numeric_limits<long>::max();
+                const long limit_cost = queue.empty() ? kMax : (*queue.begin())->cost;
+                const long limit_size = queue.empty() ? 0 : static_cast<long>((*queue.begin())->size());
+                if (const std::shared_ptr<Node> child = run_on_device(*node, limit_cost, limit_size, have_best ? best_cost : kMax, expanded)) {
+                    queue.insert(child);
+                    continue;
+                }
+            }
+            if (getenv("SP_CONSENSUS_DEBUG"))
+                fprintf(stderr, "[consensus] host: dual %d size %zu cost %ld p1 %zu p2 %zu queue %zu\n", node->dual ? 1 : 0, node->size(), node->cost, p1.size(),
+                        p2.size(), queue.size());
             std::vector<std::pair<const Side *, char>> tasks;
             for (int k : p1) tasks.emplace_back(node->s1.get(), kSym[k]);
             for (int k : p2) tasks.emplace_back(node->s2.get(), kSym[k]);
@@ -273,6 +361,103 @@ std::vector<DualConsensus> DualConsensusDWFA::consensus() {
         out.push_back(std::move(d));
     }
     inner_.n_calls_ = s.n_calls;
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// the consensus step of the HLA caller
+// ------------------------------------------------------------------------------------------
+CdwfaConfig dwfa_config_from_cli(const DiplotypeSettings &cli, bool allow_early_termination) {  // src/hla/caller.rs:1097-1116
+    CdwfaConfig c;
+    c.min_count = cli.min_consensus_count;
+    c.min_af = cli.min_consensus_fraction;
+    c.dual_max_ed_delta = cli.dual_max_ed_delta;
+    c.allow_early_termination = allow_early_termination;
+    c.max_queue_size = 20;
+    c.max_capacity_per_size = 10;
+    c.offset_window = 400;
+    return c;
+}
+
+DualPassingStats is_passing_dual(const DualConsensus &d, const DiplotypeSettings &cli) {  // :1225-1247
+    size_t counts1 = 0;
+    for (bool b : d.is_consensus1) counts1 += b;
+    return dual_passing_stats(d.is_dual(), counts1, d.is_consensus1.size() - counts1, cli.min_consensus_fraction, cli.min_cdf, cli.expected_maf);
+}
+
+DualConsensus run_dual_consensus(GpuAligner &gpu, const std::map<std::string, std::string> &segments, const DiplotypeSettings &cli) {  // :1126-1139
+    DualConsensusDWFA dwfa(gpu, dwfa_config_from_cli(cli, false));
+    for (const auto &kv : segments) dwfa.add_sequence(kv.second);
+    std::vector<DualConsensus> list = dwfa.consensus();
+    if (list.empty()) throw HostError("run_dual_consensus: no consensus found");
+    return list[0];  // "Found multiple solutions, selecting first."
+}
+
+namespace {
+// one pass of :1163-1177 / :1196-1211: every record's sequence with its offset relative to the smallest (+ half the window; the
+// smallest anchored); which = the HPC or the full-length members of RealignedHlaRecord
+DualConsensus dual_pass(GpuAligner &gpu, const std::map<std::string, RealignmentResult> &segments, const CdwfaConfig &config, bool hpc) {
+    const size_t half_window = config.offset_window / 2;
+    size_t min_offset = static_cast<size_t>(-1);
+    for (const auto &kv : segments) {
+        if (!kv.second.realigned_record) throw HostError("run_dual_consensus_with_offsets: a record was not realigned");
+        min_offset = std::min(min_offset, hpc ? kv.second.realigned_record->hpc_offset : kv.second.realigned_record->dna_offset);
+    }
+    DualConsensusDWFA dwfa(gpu, config);
+    for (const auto &kv : segments) {
+        const RealignedHlaRecord &rec = *kv.second.realigned_record;
+        const size_t o = hpc ? rec.hpc_offset : rec.dna_offset;
+        dwfa.add_sequence_offset(hpc ? rec.hpc_sequence : rec.dna_sequence, o == min_offset ? std::nullopt : std::optional<size_t>(o - min_offset + half_window));
+    }
+    std::vector<DualConsensus> list = dwfa.consensus();
+    if (list.empty()) throw HostError("run_dual_consensus_with_offsets: no consensus found");
+    return list[0];
+}
+}  // namespace
+
+DualConsensus run_dual_consensus_with_offsets(GpuAligner &gpu, const std::map<std::string, RealignmentResult> &segments,
+                                              const DiplotypeSettings &cli) {  // :1151-1219
+    if (segments.empty()) throw HostError("run_dual_consensus_with_offsets: no records");
+    const CdwfaConfig config = dwfa_config_from_cli(cli, true);
+    const DualConsensus hpc = dual_pass(gpu, segments, config, true);
+    if (is_passing_dual(hpc, cli).is_passing) return hpc;  // :1180-1190
+    return dual_pass(gpu, segments, config, false);         // HPC did not find a difference: full-length DNA
+}
+
+std::pair<std::string, std::optional<std::string>> consensus_per_group(GpuAligner &gpu, const std::map<std::string, RealignmentResult> &segments,
+                                                                       const std::vector<bool> &is_consensus1, bool is_dual,
+                                                                       const DiplotypeSettings &cli) {  // :706-760, :817-836
+    if (is_consensus1.size() != segments.size()) throw HostError("consensus_per_group: one assignment per record expected");
+    const CdwfaConfig config = dwfa_config_from_cli(cli, true);
+    const size_t half_window = config.offset_window / 2;
+    size_t min1 = static_cast<size_t>(-1), min2 = static_cast<size_t>(-1), r = 0;
+    for (const auto &kv : segments) {
+        if (!kv.second.realigned_record) throw HostError("consensus_per_group: a record was not realigned");
+        size_t &m = is_consensus1[r++] ? min1 : min2;
+        m = std::min(m, kv.second.realigned_record->dna_offset);
+    }
+    ConsensusDWFA d1(gpu, config), d2(gpu, config);
+    size_t n1 = 0, n2 = 0;
+    r = 0;
+    for (const auto &kv : segments) {
+        const RealignedHlaRecord &rec = *kv.second.realigned_record;
+        const bool first = is_consensus1[r++];
+        const size_t mn = first ? min1 : min2;
+        (first ? d1 : d2).add_sequence_offset(rec.dna_sequence, rec.dna_offset == mn ? std::nullopt : std::optional<size_t>(rec.dna_offset - mn + half_window));
+        ++(first ? n1 : n2);
+    }
+    auto first_or_empty = [](ConsensusDWFA &d, size_t n) -> std::string {  // a failed consensus is the empty string (:735-749)
+        if (n == 0) return std::string();
+        try {
+            const std::vector<Consensus> list = d.consensus();
+            return list.empty() ? std::string() : list[0].sequence;
+        } catch (const HostError &) {
+            return std::string();
+        }
+    };
+    std::pair<std::string, std::optional<std::string>> out;
+    out.first = first_or_empty(d1, n1);
+    if (is_dual) out.second = first_or_empty(d2, n2);
     return out;
 }
 

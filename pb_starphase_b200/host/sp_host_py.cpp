@@ -137,7 +137,7 @@ PYBIND11_MODULE(_starphase_host, m) {
     m.def("ln_factorial", &ln_factorial);
     m.def("multinomial_ln_pmf", &multinomial_ln_pmf);
     m.def("binomial_cdf", &binomial_cdf);
-    m.def("is_passing_dual", &is_passing_dual, py::arg("counts1"), py::arg("counts2"), py::arg("min_consensus_fraction") = 0.10,
+    m.def("is_passing_dual", static_cast<bool (*)(size_t, size_t, double, double, double)>(&is_passing_dual), py::arg("counts1"), py::arg("counts2"), py::arg("min_consensus_fraction") = 0.10,
           py::arg("min_cdf") = 0.001, py::arg("expected_maf") = 0.45);
 
     m.def("beta_reg", &beta_reg);
@@ -167,7 +167,33 @@ PYBIND11_MODULE(_starphase_host, m) {
         .def_readwrite("min_consensus_fraction", &DiplotypeSettings::min_consensus_fraction)
         .def_readwrite("min_cdf", &DiplotypeSettings::min_cdf)
         .def_readwrite("expected_maf", &DiplotypeSettings::expected_maf)
-        .def_readwrite("min_dp_score", &DiplotypeSettings::min_dp_score);
+        .def_readwrite("min_dp_score", &DiplotypeSettings::min_dp_score)
+        .def_readwrite("min_consensus_count", &DiplotypeSettings::min_consensus_count)
+        .def_readwrite("dual_max_ed_delta", &DiplotypeSettings::dual_max_ed_delta);
+
+    // the consensus step of the HLA caller: records = (qname, dna_sequence, hpc_sequence, dna_offset, hpc_offset), taken in qname order
+    // -> (dual consensus of run_dual_consensus_with_offsets, is_passing, (consensus 1, consensus 2 or None) of the per-group re-consensus)
+    m.def("hla_consensus_step", [](GpuAligner &g, const std::vector<std::tuple<std::string, std::string, std::string, size_t, size_t>> &records,
+                                   const DiplotypeSettings &s) {
+        std::map<std::string, RealignmentResult> segs;
+        for (const auto &r : records) {
+            RealignmentResult rr;
+            RealignedHlaRecord rec;
+            rec.dna_sequence = std::get<1>(r); rec.hpc_sequence = std::get<2>(r); rec.dna_offset = std::get<3>(r); rec.hpc_offset = std::get<4>(r);
+            rr.realigned_record = rec;
+            segs[std::get<0>(r)] = rr;
+        }
+        const DualConsensus d = run_dual_consensus_with_offsets(g, segs, s);
+        py::dict out;
+        out["consensus1"] = py::bytes(d.consensus1);
+        out["consensus2"] = d.consensus2 ? py::object(py::bytes(*d.consensus2)) : py::object(py::none());
+        out["is_consensus1"] = d.is_consensus1;
+        out["scores1"] = d.scores1;
+        out["scores2"] = d.scores2;
+        const auto groups = consensus_per_group(g, segs, d.is_consensus1, d.is_dual(), s);
+        py::object g2 = groups.second ? py::object(py::bytes(*groups.second)) : py::object(py::none());
+        return py::make_tuple(out, is_passing_dual(d, s).is_passing, py::make_tuple(py::bytes(groups.first), g2));
+    });
 
     // the process-wide aligner stand-ins (starphase_host.hpp): stand_ins() reads them, set_stand_ins(name=value, ...) changes them
     m.def("stand_ins", []() {

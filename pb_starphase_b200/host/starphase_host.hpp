@@ -328,6 +328,7 @@ struct DiplotypeSettings {  // the members of src/cli/diplotype.rs the path read
     bool disable_cdna_scoring = false;
     bool hla_require_dna = true;
     double min_consensus_fraction = 0.10, min_cdf = 0.001, expected_maf = 0.45;
+    size_t min_consensus_count = 3, dual_max_ed_delta = 100;  // src/cli/diplotype.rs:172-183
     // minimap2's "-s" (min_dp_max, 200 for map-hifi) decides whether a mapping exists at all; the exhaustive aligner
     // always places the allele somewhere, so the same DP score (a=5 b=4 q=6 e=2 q2=26 e2=1, src/hla/caller.rs:1381)
     // of the reported CIGAR is held against that threshold
@@ -791,6 +792,23 @@ class DualConsensusDWFA {
   private:
     ConsensusDWFA inner_;
 };
+
+// ---- the consensus step of the HLA caller (src/hla/caller.rs:1097-1247) ----
+// dwfa_config_from_cli (:1097-1116): min_count / min_af / dual_max_ed_delta from the CLI, queue 20, capacity 10, offset_window 400
+CdwfaConfig dwfa_config_from_cli(const DiplotypeSettings &cli_settings, bool allow_early_termination);
+// is_passing_dual on a DualConsensus (:1225-1247): counts from is_consensus1
+DualPassingStats is_passing_dual(const DualConsensus &dual_consensus, const DiplotypeSettings &cli_settings);
+// run_dual_consensus (:1126-1139): segments in key order, first solution
+DualConsensus run_dual_consensus(GpuAligner &gpu, const std::map<std::string, std::string> &segments, const DiplotypeSettings &cli_settings);
+// run_dual_consensus_with_offsets (:1151-1219): on the homopolymer-compressed sequences first (offsets relative to the smallest,
+// + half the window; the smallest itself anchored); when that result does not pass is_passing_dual, on the full-length DNA
+DualConsensus run_dual_consensus_with_offsets(GpuAligner &gpu, const std::map<std::string, RealignmentResult> &segments,
+                                              const DiplotypeSettings &cli_settings);
+// the re-consensus of the two read groups on full-length DNA (:706-760): (consensus 1, consensus 2 or nullopt); a group whose
+// consensus fails comes back as the empty string (tagged unknown downstream)
+std::pair<std::string, std::optional<std::string>> consensus_per_group(GpuAligner &gpu, const std::map<std::string, RealignmentResult> &segments,
+                                                                       const std::vector<bool> &is_consensus1, bool is_dual,
+                                                                       const DiplotypeSettings &cli_settings);
 
 // StarphaseJson, src/data_types/starphase_json.rs:13-21; metadata order of src/database/pgx_database.rs:359-371
 std::string starphase_json(const std::string &pbstarphase_version, const std::map<std::string, std::string> &database_metadata,

@@ -138,6 +138,10 @@ extern "C" {
     pub fn sp_consensus_reset(c: *mut sp_consensus, track: i32) -> c_int;
     pub fn sp_consensus_extend(c: *mut sp_consensus, n_tasks: i32, src: *const i32, symbols: *const u8, dst: *const i32, ed: *mut i32,
                                votes: *mut u8, full: *mut i32) -> c_int;
+    pub fn sp_consensus_run_supported(c: *const sp_consensus, n_sides: i32) -> i32;
+    pub fn sp_consensus_run(c: *mut sp_consensus, n_sides: i32, src: *const i32, dst: *const i32, ed: *mut i32, votes: *mut u8, full: *mut i32,
+                            min_count: i32, min_af_permille: i32, cost_limit: i64, size_limit: i64, cost_cap: i64, max_steps: i32, steps: *mut u8,
+                            n_steps: *mut i32) -> c_int;
     // K8: sequence-to-variant-graph alignment
     pub fn sp_graph_align(ctx: *mut sp_ctx, n_problems: i32, gchars: *const u8, gchar_off: *const i64, pred_off: *const i32, preds: *const i32,
                           diag: *const i32, end_off: *const i32, ends: *const i32, seqs: *const u8, seq_off: *const i64, band: i32,

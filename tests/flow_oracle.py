@@ -356,6 +356,43 @@ def dp_score_a1(cigar) -> int:
     return s
 
 
+def hla_consensus_step(records, min_consensus_count: int = 3, min_consensus_fraction: float = 0.10, min_cdf: float = 0.001,
+                       expected_maf: float = 0.45):
+    """run_dual_consensus_with_offsets (src/hla/caller.rs:1151-1219) + the per-group re-consensus (:706-760) on the oracle's search
+    (oracle/consensus_oracle.py).  records: (qname, dna_sequence, hpc_sequence, dna_offset, hpc_offset); taken in qname order.
+    Returns (dual consensus dict, is_passing, (consensus 1, consensus 2 or None))."""
+    import consensus_oracle as co
+
+    recs = sorted(records, key=lambda r: r[0].encode())
+    cfg = co.Config(min_count=min_consensus_count, min_af=min_consensus_fraction, allow_early_termination=True, max_queue_size=20,
+                    max_capacity_per_size=10, offset_window=400)
+    half = cfg.offset_window // 2
+
+    def offsets(vals):
+        lo = min(vals)
+        return [None if v == lo else v - lo + half for v in vals]
+
+    def passing(d):
+        if d["consensus2"] is None:
+            return False
+        c1 = sum(d["is_consensus1"])
+        return so.is_passing_dual(c1, len(d["is_consensus1"]) - c1, min_consensus_fraction, min_cdf, expected_maf)
+
+    d = co.dual_consensus([r[2] for r in recs], offsets([r[4] for r in recs]), cfg)[0]  # HPC first
+    if not passing(d):
+        d = co.dual_consensus([r[1] for r in recs], offsets([r[3] for r in recs]), cfg)[0]
+    groups = []
+    for want in (True, False):
+        sel = [r for r, first in zip(recs, d["is_consensus1"]) if first == want]
+        if not want and d["consensus2"] is None:
+            groups.append(None)
+        elif not sel:
+            groups.append(b"")
+        else:
+            groups.append(co.consensus([r[1] for r in sel], offsets([r[3] for r in sel]), cfg)[0][0])
+    return d, passing(d), tuple(groups)
+
+
 def find_full_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missing_frac: float, force_assignment: bool, db: dict,
                                 graph_band: int = 128):
     """find_full_type_in_sequence + assign_haplotype (src/cyp2d6/haplotyper.rs:326-361, :371-601) as

@@ -65,7 +65,12 @@ def host_consensus(reads, offsets=None, **cfg):
     return gpu, host, [r.decode() for r in reads], offs, cfg
 
 
-def test_host_search_equals_oracle_search():
+@pytest.mark.parametrize("on_device", [True, False])
+def test_host_search_equals_oracle_search(on_device, monkeypatch):
+    """on_device: stretches with one way forward run on the device (sp_consensus_run); off: every symbol is stepped from the host
+    (SP_CONSENSUS_NO_RUN).  Same answers either way, and the same as the oracle's search."""
+    if not on_device:
+        monkeypatch.setenv("SP_CONSENSUS_NO_RUN", "1")
     rng = np.random.default_rng(6)
     for case in range(4):
         a, b = het_pair(rng, 260 + 20 * case, (30, 131, 222))
@@ -74,7 +79,7 @@ def test_host_search_equals_oracle_search():
         rb, _ = synth.hifi_reads(rng, [b], nb, err=0.006, flank=0, lo=0, hi=1 << 20) if nb else ([], None)
         reads = ra + rb
         gpu, host, rs, offs, _ = host_consensus(reads)
-        got, calls = host.consensus(gpu, rs, offs, {})
+        got, calls1 = host.consensus(gpu, rs, offs, {})
         want = co.consensus(reads)
         assert [(s, list(sc)) for s, sc in got] == [(s, sc) for s, sc in want], case
         gotd, calls = host.dual_consensus(gpu, rs, offs, {})
@@ -83,7 +88,9 @@ def test_host_search_equals_oracle_search():
         for g, w in zip(gotd, wantd):
             assert g["consensus1"] == w["consensus1"] and g["consensus2"] == w["consensus2"], case
             assert list(g["is_consensus1"]) == w["is_consensus1"] and list(g["scores1"]) == w["scores1"] and list(g["scores2"]) == w["scores2"], case
-        assert calls > 200  # one device call per expanded node
+        print(f"case {case}: on_device={on_device} device calls: single {calls1}, dual {calls}")
+        if not on_device:
+            assert calls > 200  # one device call per expanded node
 
 
 def test_host_search_offsets_and_windows():
@@ -91,11 +98,15 @@ def test_host_search_offsets_and_windows():
     src = rnd(rng, 420)
     reads = [src[:300], src[:330], src[:310], src[100:], src[125:], src[90:], src]
     offsets = [None, None, None, 112, 120, 90, None]
-    cfg = dict(allow_early_termination=True, offset_window=40)
-    gpu, host, rs, offs, _ = host_consensus(reads, offsets)
-    got, _ = host.consensus(gpu, rs, offs, cfg)
-    want = co.consensus(reads, offsets, co.Config(**cfg))
-    assert [(s, list(sc)) for s, sc in got] == want and got[0][0] == src
+    for window in (40, 400):  # 400: the reference's setting (src/hla/caller.rs:1113), the widest band class
+        cfg = dict(allow_early_termination=True, offset_window=window)
+        gpu, host, rs, offs, _ = host_consensus(reads, offsets)
+        got, _ = host.consensus(gpu, rs, offs, cfg)
+        want = co.consensus(reads, offsets, co.Config(**cfg))
+        assert [(s, list(sc)) for s, sc in got] == want and got[0][0] == src
+        gotd, _ = host.dual_consensus(gpu, rs, offs, cfg)
+        wantd = co.dual_consensus(reads, offsets, co.Config(**cfg))
+        assert [(g["consensus1"], g["consensus2"], list(g["scores1"])) for g in gotd] == [(w["consensus1"], w["consensus2"], w["scores1"]) for w in wantd]
 
 
 def test_hla_sized_dual_consensus_properties():
@@ -106,10 +117,50 @@ def test_hla_sized_dual_consensus_properties():
     rb, _ = synth.hifi_reads(rng, [b], 14, err=0.002, flank=0, lo=0, hi=1 << 20)
     reads = ra + rb
     gpu, host, rs, offs, _ = host_consensus(reads)
+    import time
+
+    t0 = time.perf_counter()
     got, calls = host.dual_consensus(gpu, rs, offs, {})
+    print(f"dual consensus of 30 reads x 3.3 kb: {1e3 * (time.perf_counter() - t0):.1f} ms, {calls} device calls")
     d = got[0]
     assert {d["consensus1"], d["consensus2"]} == {a, b}
     first_is_a = d["consensus1"] == a
     assert list(d["is_consensus1"]) == [first_is_a] * 16 + [not first_is_a] * 14
     single, _ = host.consensus(gpu, [r.decode() for r in ra], [], {})
     assert single[0][0] == a
+
+
+@pytest.mark.parametrize("hpc_only", [False, True])
+def test_hla_consensus_step_vs_oracle(hpc_only):
+    """run_dual_consensus_with_offsets + the per-group re-consensus (src/hla/caller.rs:1151-1219, :706-760) through the C++ host
+    against the same flow on the oracle's search.  hpc_only: the alleles differ only in a homopolymer length, so the
+    homopolymer-compressed pass sees one allele and the full-length DNA pass has to split the reads."""
+    import flow_oracle as fo
+    import starphase_oracle as so
+    from pb_starphase_b200 import _starphase_host as host
+
+    rng = np.random.default_rng(12 + hpc_only)
+    a = rnd(rng, 800)  # the differences lie behind the offset window of the partial reads (400, src/hla/caller.rs:1113)
+    if hpc_only:
+        q = 600
+        b = a[:q] + a[q:q + 1] * 2 + a[q:]  # one homopolymer two bases longer
+    else:
+        b = bytearray(a)
+        for q in (520, 640, 730):
+            b[q] = b"ACGT"[(b"ACGT".index(bytes([a[q]])) + 1) % 4]
+        b = bytes(b)
+    records = []
+    for k in range(10):
+        src = a if k % 2 == 0 else b
+        start = 0 if k < 6 else int(rng.integers(20, 120))
+        end = len(src) if k % 3 else len(src) - int(rng.integers(0, 40))
+        seq = src[start:end]
+        records.append((f"read{k:02d}", seq, so.hpc(seq), start, so.hpc_pos(src, start)))
+    want_d, want_pass, want_groups = fo.hla_consensus_step(records)
+    gpu = host.GpuAligner(0)
+    got_d, got_pass, got_groups = host.hla_consensus_step(gpu, [(q, s.decode(), h.decode(), o, ho) for q, s, h, o, ho in records], host.DiplotypeSettings())
+    assert got_d["consensus1"] == want_d["consensus1"] and got_d["consensus2"] == want_d["consensus2"]
+    assert list(got_d["is_consensus1"]) == want_d["is_consensus1"] and list(got_d["scores1"]) == want_d["scores1"] and list(got_d["scores2"]) == want_d["scores2"]
+    assert got_pass == want_pass and tuple(got_groups) == want_groups
+    assert want_pass and set(want_groups) == {a, b}
+    assert want_d["is_consensus1"] in ([k % 2 == 0 for k in range(10)], [k % 2 == 1 for k in range(10)])  # the reads split by source allele
