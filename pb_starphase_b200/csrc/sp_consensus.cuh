@@ -47,13 +47,14 @@ struct ConsParams {
 
 // Column L0 of a read at band index k: CONS_INF outside the band / the read; the activating column (L0 == start) is E[i] = i by
 // definition -- read bases before the window start are unaligned -- and is synthesised instead of stored, so a fresh track needs
-// no initial columns.  stored(k): the kept value, asked only for cells of the band when L0 > start.
+// no initial columns.  stored(c, ln): the kept value of band cell ln * CELLS + c (= k), asked only for cells of the band when
+// L0 > start; the caller names the cell by owner lane and slot so that the address needs no division.
 template <typename Stored>
-__device__ __forceinline__ int k7_old_at(int k, int nb, int W, int L0, int off, int start, int m, Stored stored) {
+__device__ __forceinline__ int k7_old_at(int k, int c, int ln, int nb, int W, int L0, int off, int start, int m, Stored stored) {
     if (k < 0 || k >= nb) return CONS_INF;
     const int i_old = (L0 - off) + (k - W);
     if (i_old < 0 || i_old > m) return CONS_INF;
-    return L0 == start ? i_old : stored(k);
+    return L0 == start ? i_old : stored(c, ln);
 }
 
 // Column L = L0 + 1 (>= start) of one read after appending symbol code s: e[c] = band cell lane * CELLS + c.
@@ -80,8 +81,9 @@ __device__ __forceinline__ void k7_next_column(int (&e)[CELLS], int lane, int W,
             if (i == 0) {
                 v = row0_cost;
             } else {
-                const int diag = k7_old_at(k, nb, W, L0, off, start, m, stored);       // E[i-1] of column L0 has the same band index
-                const int horiz = k7_old_at(k + 1, nb, W, L0, off, start, m, stored);  // E[i]   of column L0
+                const int diag = k7_old_at(k, c, lane, nb, W, L0, off, start, m, stored);  // E[i-1] of column L0 has the same band index
+                const int horiz = c + 1 < CELLS ? k7_old_at(k + 1, c + 1, lane, nb, W, L0, off, start, m, stored)
+                                                : k7_old_at(k + 1, 0, lane + 1, nb, W, L0, off, start, m, stored);  // E[i] of column L0
                 const int sub = (s < 4u && base(i - 1) == s) ? 0 : 1;
                 v = min(diag < CONS_INF ? diag + sub : CONS_INF, horiz < CONS_INF ? horiz + 1 : CONS_INF);
             }
@@ -174,11 +176,11 @@ __global__ void __launch_bounds__(128) k7_extend(const ConsParams p) {
     const int k0 = lane * CELLS;
     const int ibase = (L - off) - p.W;  // row index of band cell k at column L:  i = ibase + k
     // column L0 of the parent track as stored (asked only for 0 <= k < nb when L0 > start)
-    auto stored = [&](int k) -> int { return old[k]; };
+    auto stored = [&](int c, int ln) -> int { return old[ln * CELLS + c]; };
     auto base = [&](int x) -> uint32_t { return R[x]; };
     if (!extend) {  // report the state of column L0 (>= start here)
 #pragma unroll
-        for (int c = 0; c < CELLS; ++c) e[c] = k7_old_at(k0 + c, nb, p.W, L0, off, start, m, stored);
+        for (int c = 0; c < CELLS; ++c) e[c] = k7_old_at(k0 + c, c, lane, nb, p.W, L0, off, start, m, stored);
     } else {
         k7_next_column<CELLS>(e, lane, p.W, nb, L0, off, hw, start, m, base, s, stored);
     }
@@ -256,7 +258,7 @@ struct K7Item {
     long long roff;  // first code of the read
     int32_t off_raw, m;
     int32_t filled;  // read bases [.., filled) are in the item's code ring
-    int32_t pad_;
+    int32_t side;
 };
 
 template <int CELLS>
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(K7_RUN_THREADS) k7_run(const ConsRunParams p) 
             K7Item m;
             m.roff = p.roffs[r]; m.off_raw = off_raw; m.m = static_cast<int>(p.roffs[r + 1] - p.roffs[r]);
             m.filled = max(0, ((side ? len1 : len0) + 1 - off) - p.W - 1);  // nothing below the first row the next column can touch is ever read
-            m.pad_ = 0;
+            m.side = side;
             s_item[slot] = m;
         }
         uint16_t *c16 = col + static_cast<size_t>(slot) * COLW;
@@ -321,25 +323,23 @@ __global__ void __launch_bounds__(K7_RUN_THREADS) k7_run(const ConsRunParams p) 
                 cost += min(c1, c2);
                 if (c1 <= c2 && !(vo[r] & VOTE_INACTIVE) && fu[r] >= ed[r]) {  // the read votes on side 0
                     const uint32_t v = vo[r] & 15u;
-                    const int w = v ? 12 / __popc(v) : 0;
+                    const int w = (0x346C0 >> (4 * __popc(v))) & 15;  // 12 / candidates: 12, 6, 4, 3 (0 for none)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) t0[k] += (v >> k & 1u) ? w : 0;
                 }
                 if (NS == 2 && c2 <= c1 && !(vo[R + r] & VOTE_INACTIVE) && fu[R + r] >= ed[R + r]) {  // ... on side 1
                     const uint32_t v = vo[R + r] & 15u;
-                    const int w = v ? 12 / __popc(v) : 0;
+                    const int w = (0x346C0 >> (4 * __popc(v))) & 15;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) t1[k] += (v >> k & 1u) ? w : 0;
                 }
             }
+            // sums over the warp with the hardware reduction (costs are below 2^31: <= 2,048 read-sides x 60,000 bases)
+            cost = __reduce_add_sync(0xffffffffu, static_cast<int>(cost));
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                cost += __shfl_xor_sync(0xffffffffu, cost, d);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    t0[k] += __shfl_xor_sync(0xffffffffu, t0[k], d);
-                    t1[k] += __shfl_xor_sync(0xffffffffu, t1[k], d);
-                }
+            for (int k = 0; k < 4; ++k) {
+                t0[k] = __reduce_add_sync(0xffffffffu, t0[k]);
+                if (NS == 2) t1[k] = __reduce_add_sync(0xffffffffu, t1[k]);
             }
             if (lane == 0) {
                 // one side's verdict: number of passing symbols (1 when only the best-voted one goes on, 0 = finished) and the symbol
@@ -376,12 +376,12 @@ __global__ void __launch_bounds__(K7_RUN_THREADS) k7_run(const ConsRunParams p) 
         if (!s_dec[2]) break;
         const int sym0 = s_dec[0], sym1 = s_dec[1];
         for (int j = 0; j < my_items; ++j) {
-            const int it = gwarp + j * total_warps, side = it / R, slot = warp * per_warp + j;
-            const int s = side ? sym1 : sym0;
+            const int it = gwarp + j * total_warps, slot = warp * per_warp + j;
+            const K7Item im = s_item[slot];
+            const int side = im.side, s = side ? sym1 : sym0;
             int o_ed = ed[it], o_full = fu[it];
             uint32_t o_votes = vo[it];
             if (s >= 0) {
-                const K7Item im = s_item[slot];
                 const int off = max(im.off_raw, 0), hw = im.off_raw < 0 ? 0 : p.half_window, start = max(0, off - hw);
                 const int L0 = side ? len1 : len0, L = L0 + 1, m = im.m;
                 if (L < start) {
@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(K7_RUN_THREADS) k7_run(const ConsRunParams p) 
                         __syncwarp();
                     }
                     uint16_t *c16 = col + static_cast<size_t>(slot) * COLW;
-                    auto stored = [&](int k) -> int {
-                        const int v = c16[(k % CELLS) * 32 + k / CELLS];
+                    auto stored = [&](int c, int ln) -> int {
+                        const int v = c16[c * 32 + ln];
                         return v == 0xFFFF ? CONS_INF : v;
                     };
                     auto base = [&](int x) -> uint32_t { return rg[x & (RING - 1)]; };
