@@ -314,7 +314,8 @@ sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int
  * (`band` rows either side of the read's diagonal, widened by offset_window / 2).  offsets[r] >= 0 is where read r is expected to
  * start inside the consensus (waffle_con's add_sequence_offset(.., Some(offset))): the read may start anywhere within
  * offset_window / 2 of it for free and is inactive before; offsets[r] < 0 (or offsets == NULL) anchors the read at the start of
- * the consensus (add_sequence / offset None). */
+ * the consensus (add_sequence / offset None).  Read bytes: A C G T (either case); '*' is a wildcard that matches every consensus
+ * symbol at no cost and votes for none (CdwfaConfig::wildcard as src/cyp2d6/caller.rs:148 sets it); any other byte matches nothing. */
 typedef struct sp_consensus sp_consensus;
 sp_status sp_consensus_create(sp_ctx *ctx, const sp_seqset *reads, const int32_t *offsets, int32_t offset_window, int32_t band,
                               int32_t max_tracks, sp_consensus **out);

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 INF = 0x3FFFFFFF
 VOTE_FINISHED, VOTE_INACTIVE = 1 << 5, 1 << 6
-_CODE = {65: 0, 67: 1, 71: 2, 84: 3, 97: 0, 99: 1, 103: 2, 116: 3}
+_CODE = {65: 0, 67: 1, 71: 2, 84: 3, 97: 0, 99: 1, 103: 2, 116: 3, 42: 5}  # '*' = wildcard: matches every symbol, votes for none
 VOTE_UNIT = 12  # one read's vote, split evenly over its 1..4 candidate symbols
 
 
@@ -55,7 +55,7 @@ def extend(reads: Sequence[bytes], offsets: Sequence[int], cfg: Config, src: Tra
     L0 = src.length
     L = L0 + (1 if ext else 0)
     out.length = L
-    s = _CODE.get(symbol, 4)
+    s = min(_CODE.get(symbol, 4), 4)
     eds, votes, fulls = [], [], []
     for r, read in enumerate(reads):
         off, m = max(offsets[r], 0), len(read)
@@ -85,7 +85,7 @@ def extend(reads: Sequence[bytes], offsets: Sequence[int], cfg: Config, src: Tra
                     v = max(0, L - (off + hw))
                 else:
                     d, h = old_at(i - 1), old_at(i)
-                    sub = 0 if (s < 4 and _CODE.get(read[i - 1], 4) == s) else 1
+                    sub = 0 if (s < 4 and _CODE.get(read[i - 1], 4) in (s, 5)) else 1
                     v = min(d + sub if d < INF else INF, h + 1 if h < INF else INF, prev + 1 if prev < INF else INF)
                 col[i] = v
                 prev = v
@@ -97,7 +97,7 @@ def extend(reads: Sequence[bytes], offsets: Sequence[int], cfg: Config, src: Tra
         if mn < INF:
             for i, v in col.items():
                 if v == mn:
-                    vt |= VOTE_FINISHED if i == m else (1 << _CODE.get(read[i], 4))
+                    vt |= VOTE_FINISHED if i == m else ((1 << _CODE.get(read[i], 4)) & 31)
         eds.append(mn); votes.append(vt); fulls.append(bf)
     return out, eds, votes, fulls
 
@@ -241,3 +241,45 @@ def dual_consensus(reads: Sequence[bytes], offsets: Optional[Sequence[int]] = No
             c2 = _side_cost(s2, reads)
             out.append(dict(consensus1=n.cons[0], consensus2=n.cons[1], is_consensus1=[a <= b for a, b in zip(c1, c2)], scores1=c1, scores2=c2))
     return out
+
+
+def priority_consensus(chains: Sequence[Sequence[bytes]], offsets: Sequence[Sequence[Optional[int]]], seeds: Sequence[Optional[int]],
+                       cfg: Optional[Config] = None):
+    """PriorityConsensusDWFA as the CYP2D6 caller drives it (src/cyp2d6/caller.rs:145-280), restated outline (parity unpinned; the
+    same policy as pb_starphase_b200/host/sp_host_consensus.cpp): inputs with different seeds never share a group; a group is
+    examined level by level with dual_consensus -- a dual answer splits it in two (both examined again at the same level), a
+    single answer moves it to the next level, after the last level it is final; groups ordered by their smallest input index.
+    Returns (consensuses[group][level] = (sequence, scores), sequence_indices)."""
+    cfg = cfg or Config()
+    levels = len(chains[0])
+    by_seed: Dict[tuple, List[int]] = {}
+    for i, sd in enumerate(seeds):
+        by_seed.setdefault((sd is not None, sd or 0), []).append(i)
+    work = [dict(members=by_seed[k], level=0, known=[None] * levels) for k in sorted(by_seed, reverse=True)]
+    done = []
+    while work:
+        g = work.pop()
+        if g["level"] == levels:
+            done.append(g)
+            continue
+        lv = g["level"]
+        d = dual_consensus([chains[i][lv] for i in g["members"]], [offsets[i][lv] for i in g["members"]], cfg)[0]
+        if d["consensus2"] is not None:
+            a = [i for i, first in zip(g["members"], d["is_consensus1"]) if first]
+            b = [i for i, first in zip(g["members"], d["is_consensus1"]) if not first]
+            work.append(dict(members=b, level=lv, known=[None] * levels))
+            work.append(dict(members=a, level=lv, known=[None] * levels))
+        else:
+            g["known"][lv] = (d["consensus1"], list(d["scores1"]))
+            g["level"] += 1
+            work.append(g)
+    done.sort(key=lambda g: g["members"][0])
+    cons, idx = [], [0] * len(chains)
+    for gi, g in enumerate(done):
+        for lv in range(levels):
+            if g["known"][lv] is None:
+                g["known"][lv] = consensus([chains[i][lv] for i in g["members"]], [offsets[i][lv] for i in g["members"]], cfg)[0]
+        cons.append([tuple(x) for x in g["known"]])
+        for i in g["members"]:
+            idx[i] = gi
+    return cons, idx

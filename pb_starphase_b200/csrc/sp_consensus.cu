@@ -31,6 +31,7 @@ static uint8_t code_of(uint8_t c) {
         case 'C': case 'c': return 1;
         case 'G': case 'g': return 2;
         case 'T': case 't': return 3;
+        case '*': return 5;  // wildcard (waffle_con's CdwfaConfig::wildcard as the CYP2D6 caller sets it, src/cyp2d6/caller.rs:148)
         default: return 4;
     }
 }
@@ -132,7 +133,7 @@ extern "C" sp_status sp_consensus_extend(sp_consensus *c, int32_t n_tasks, const
         if (src[q] < 0 || src[q] >= c->n_tracks || dst[q] < 0 || dst[q] >= c->n_tracks) return fail(ctx, SP_ERR_INVALID, "sp_consensus_extend: track out of range");
         if (is_dst[static_cast<size_t>(dst[q])]) return fail(ctx, SP_ERR_INVALID, "sp_consensus_extend: two tasks write the same track");
         is_dst[static_cast<size_t>(dst[q])] = 1;
-        if (symbols) sym[static_cast<size_t>(q)] = symbols[q] == 0 ? 255 : code_of(symbols[q]);  // symbol 0: report the track's state only
+        if (symbols) sym[static_cast<size_t>(q)] = symbols[q] == 0 ? 255 : std::min<uint8_t>(code_of(symbols[q]), 4);  // symbol 0: report the track's state only
     }
     for (int q = 0; q < n_tasks; ++q)
         if (src[q] != dst[q] && is_dst[static_cast<size_t>(src[q])])

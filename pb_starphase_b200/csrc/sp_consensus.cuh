@@ -29,9 +29,10 @@ namespace sp {
 constexpr int CONS_INF = 0x3FFFFFFF;
 constexpr uint8_t VOTE_FINISHED = 1u << 5;  // the read is consumed at a row reaching the minimum
 constexpr uint8_t VOTE_INACTIVE = 1u << 6;  // the consensus has not reached the read's window yet
+constexpr uint32_t CODE_WILDCARD = 5;       // read byte '*': matches every consensus symbol at no cost, votes for none
 
 struct ConsParams {
-    const uint8_t *codes;      // read bases as codes 0..3 (ACGT), 4 = other; concatenated
+    const uint8_t *codes;      // read bases as codes 0..3 (ACGT), 4 = other (matches nothing), 5 = wildcard '*'; concatenated
     const long long *roffs;    // [n_reads + 1]
     const int32_t *offset;     // [n_reads] nominal start of the read inside the consensus; < 0 = exactly at its start, no window
     int32_t *band;             // [n_tracks][n_reads][band_cells] last column, band coordinates
@@ -84,7 +85,8 @@ __device__ __forceinline__ void k7_next_column(int (&e)[CELLS], int lane, int W,
                 const int diag = k7_old_at(k, c, lane, nb, W, L0, off, start, m, stored);  // E[i-1] of column L0 has the same band index
                 const int horiz = c + 1 < CELLS ? k7_old_at(k + 1, c + 1, lane, nb, W, L0, off, start, m, stored)
                                                 : k7_old_at(k + 1, 0, lane + 1, nb, W, L0, off, start, m, stored);  // E[i] of column L0
-                const int sub = (s < 4u && base(i - 1) == s) ? 0 : 1;
+                const uint32_t rb = base(i - 1);
+                const int sub = (s < 4u && (rb == s || rb == CODE_WILDCARD)) ? 0 : 1;
                 v = min(diag < CONS_INF ? diag + sub : CONS_INF, horiz < CONS_INF ? horiz + 1 : CONS_INF);
             }
         }
@@ -136,7 +138,7 @@ __device__ __forceinline__ void k7_reduce_column(const int (&e)[CELLS], int lane
 #pragma unroll
     for (int c = 0; c < CELLS; ++c) {
         const int k = k0 + c, i = ibase + k;
-        if (k < nb && e[c] == mn && mn < CONS_INF && i >= 0 && i <= m) votes |= i == m ? VOTE_FINISHED : (1u << base(i));
+        if (k < nb && e[c] == mn && mn < CONS_INF && i >= 0 && i <= m) votes |= i == m ? VOTE_FINISHED : ((1u << base(i)) & 31u);  // a wildcard (code 5) names no symbol
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) votes |= __shfl_xor_sync(0xffffffffu, votes, d);

@@ -365,6 +365,73 @@ std::vector<DualConsensus> DualConsensusDWFA::consensus() {
 }
 
 // ------------------------------------------------------------------------------------------
+// PriorityConsensusDWFA (see starphase_host.hpp for the outline restated here)
+// ------------------------------------------------------------------------------------------
+void PriorityConsensusDWFA::add_seeded_sequence_chain(const std::vector<std::string> &sequence_chain,
+                                                      const std::vector<std::optional<size_t>> &offset_chain, std::optional<uint64_t> seed) {
+    if (sequence_chain.empty() || sequence_chain.size() != offset_chain.size()) throw HostError("priority consensus: one offset per chain level expected");
+    if (!chains_.empty() && chains_[0].size() != sequence_chain.size()) throw HostError("priority consensus: every chain needs the same number of levels");
+    chains_.push_back(sequence_chain); offsets_.push_back(offset_chain); seeds_.push_back(seed);
+}
+
+PriorityConsensus PriorityConsensusDWFA::consensus() {
+    if (chains_.empty()) throw HostError("priority consensus: no sequences were added");
+    const size_t levels = chains_[0].size();
+    struct Group {
+        std::vector<size_t> members;
+        size_t level = 0;
+        std::vector<std::optional<Consensus>> known;  // single consensus of exactly these members, per level, where a run gave it
+    };
+    // seeds first: unseeded inputs together, then one group per seed value (ascending)
+    std::map<std::pair<bool, uint64_t>, std::vector<size_t>> by_seed;
+    for (size_t i = 0; i < chains_.size(); ++i) by_seed[{seeds_[i].has_value(), seeds_[i].value_or(0)}].push_back(i);
+    std::vector<Group> work, done;
+    for (auto it = by_seed.rbegin(); it != by_seed.rend(); ++it) work.push_back({it->second, 0, std::vector<std::optional<Consensus>>(levels)});
+    while (!work.empty()) {
+        Group g = std::move(work.back());
+        work.pop_back();
+        if (g.level == levels) { done.push_back(std::move(g)); continue; }
+        DualConsensusDWFA dwfa(gpu_, config_);
+        for (size_t i : g.members) dwfa.add_sequence_offset(chains_[i][g.level], offsets_[i][g.level]);
+        const std::vector<DualConsensus> list = dwfa.consensus();
+        if (list.empty()) throw HostError("priority consensus: no consensus found");
+        const DualConsensus &d = list[0];
+        if (d.is_dual()) {  // two groups, each examined again at this level
+            Group a{{}, g.level, std::vector<std::optional<Consensus>>(levels)}, b = a;
+            for (size_t k = 0; k < g.members.size(); ++k) (d.is_consensus1[k] ? a : b).members.push_back(g.members[k]);
+            work.push_back(std::move(b)); work.push_back(std::move(a));
+        } else {
+            Consensus c;
+            c.sequence = d.consensus1;
+            for (const auto &x : d.scores1) c.scores.push_back(x.value_or(0));
+            g.known[g.level] = std::move(c);
+            ++g.level;
+            work.push_back(std::move(g));
+        }
+    }
+    std::sort(done.begin(), done.end(), [](const Group &a, const Group &b) { return a.members.front() < b.members.front(); });
+    PriorityConsensus out;
+    out.sequence_indices.assign(chains_.size(), 0);
+    for (size_t gi = 0; gi < done.size(); ++gi) {
+        Group &g = done[gi];
+        std::vector<Consensus> per_level;
+        for (size_t l = 0; l < levels; ++l) {
+            if (!g.known[l]) {  // the split happened at a later level: this level was only seen for the larger group
+                ConsensusDWFA single(gpu_, config_);
+                for (size_t i : g.members) single.add_sequence_offset(chains_[i][l], offsets_[i][l]);
+                const std::vector<Consensus> list = single.consensus();
+                if (list.empty()) throw HostError("priority consensus: no consensus found");
+                g.known[l] = list[0];
+            }
+            per_level.push_back(*g.known[l]);
+        }
+        out.consensuses.push_back(std::move(per_level));
+        for (size_t i : g.members) out.sequence_indices[i] = gi;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // the consensus step of the HLA caller
 // ------------------------------------------------------------------------------------------
 CdwfaConfig dwfa_config_from_cli(const DiplotypeSettings &cli, bool allow_early_termination) {  // src/hla/caller.rs:1097-1116

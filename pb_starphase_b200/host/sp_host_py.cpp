@@ -74,6 +74,22 @@ PYBIND11_MODULE(_starphase_host, m) {
         for (const Consensus &s : c.consensus()) out.append(py::make_tuple(py::bytes(s.sequence), s.scores));
         return py::make_tuple(out, c.n_extension_calls());
     });
+    // priority consensus: chains[i] = the representations of input i (e.g. HPC, raw), offsets[i] one per level (None = anchored),
+    // seeds[i] or None -> (consensuses[group][level] = (sequence, scores), group of every input)
+    m.def("priority_consensus", [cfg_from](GpuAligner &g, const std::vector<std::vector<std::string>> &chains,
+                                           const std::vector<std::vector<std::optional<size_t>>> &offsets,
+                                           const std::vector<std::optional<uint64_t>> &seeds, const py::dict &cfg) {
+        PriorityConsensusDWFA p(g, cfg_from(cfg));
+        for (size_t i = 0; i < chains.size(); ++i) p.add_seeded_sequence_chain(chains[i], offsets[i], seeds[i]);
+        const PriorityConsensus r = p.consensus();
+        py::list groups;
+        for (const auto &levels : r.consensuses) {
+            py::list one;
+            for (const Consensus &c : levels) one.append(py::make_tuple(py::bytes(c.sequence), c.scores));
+            groups.append(one);
+        }
+        return py::make_tuple(groups, r.sequence_indices);
+    });
     m.def("dual_consensus", [cfg_from](GpuAligner &g, const SeqList &reads, const std::vector<std::optional<size_t>> &offsets, const py::dict &cfg) {
         DualConsensusDWFA c(g, cfg_from(cfg));
         for (size_t r = 0; r < reads.size(); ++r) c.add_sequence_offset(reads[r], r < offsets.size() ? offsets[r] : std::nullopt);

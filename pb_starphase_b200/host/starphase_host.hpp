@@ -793,6 +793,32 @@ class DualConsensusDWFA {
     ConsensusDWFA inner_;
 };
 
+// waffle_con's PriorityConsensusDWFA as the CYP2D6 caller drives it (src/cyp2d6/caller.rs:145-280): every input is a chain of
+// representations of one read segment (there: homopolymer-compressed first, then the raw bases), an offset per level and an
+// optional seed; the result groups the inputs and gives every group one consensus per level.  Restated outline (parity unpinned,
+// DESIGN.md 4.7): inputs with different seeds never share a group; a group is examined level by level with DualConsensusDWFA -- a
+// dual answer splits it in two (both halves are examined again at the same level), a single answer moves it to the next level,
+// after the last level it is final; groups come out ordered by their smallest input index.
+struct PriorityConsensus {
+    std::vector<std::vector<Consensus>> consensuses;  // [group][level]; scores in the order of the group's members
+    std::vector<size_t> sequence_indices;             // group of every input, in insertion order
+};
+class PriorityConsensusDWFA {
+  public:
+    PriorityConsensusDWFA(GpuAligner &gpu, CdwfaConfig config) : gpu_(gpu), config_(config) {}
+    void add_seeded_sequence_chain(const std::vector<std::string> &sequence_chain, const std::vector<std::optional<size_t>> &offset_chain,
+                                   std::optional<uint64_t> seed);
+    size_t n_sequences() const { return chains_.size(); }
+    PriorityConsensus consensus();
+
+  private:
+    GpuAligner &gpu_;
+    CdwfaConfig config_;
+    std::vector<std::vector<std::string>> chains_;
+    std::vector<std::vector<std::optional<size_t>>> offsets_;
+    std::vector<std::optional<uint64_t>> seeds_;
+};
+
 // ---- the consensus step of the HLA caller (src/hla/caller.rs:1097-1247) ----
 // dwfa_config_from_cli (:1097-1116): min_count / min_af / dual_max_ed_delta from the CLI, queue 20, capacity 10, offset_window 400
 CdwfaConfig dwfa_config_from_cli(const DiplotypeSettings &cli_settings, bool allow_early_termination);

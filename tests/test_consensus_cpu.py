@@ -72,3 +72,22 @@ def test_offsets_assemble_partial_reads():
     offsets[3] = 115
     res = co.consensus(reads, offsets, co.Config(allow_early_termination=True, offset_window=40))
     assert res[0][0] == src and res[0][1] == [0] * 7
+
+
+def test_priority_consensus_groups_by_source():
+    """The priority chain (HPC first, then raw): sources that differ only in a homopolymer length are split at the second level,
+    a seeded input never joins the others, wildcards cost nothing."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import starphase_oracle as so
+    from test_consensus_gpu import priority_case
+
+    sources, chains, offsets, seeds, truth = priority_case(np.random.default_rng(21))
+    cons, idx = co.priority_consensus(chains, offsets, seeds)
+    assert len(cons) == 4 and [idx[k] for k in range(4)] == [0, 1, 2, 3]
+    for k, g in enumerate(idx):
+        assert g == idx[k % 4] and cons[g][1][0] == sources[truth[k]] and cons[g][0][0] == so.hpc(sources[truth[k]])
+        assert cons[g][1][1] == [0] * 5
+    # a read whose first 40 bases are wildcards votes with the rest and costs nothing
+    src = sources[0]
+    res = co.consensus([src, src, src, b"*" * 40 + src[40:]])
+    assert res[0][0] == src and res[0][1] == [0, 0, 0, 0]

@@ -24,8 +24,8 @@ def test_k7_extend_vs_oracle(ctx):
     rng = np.random.default_rng(5)
     src = rnd(rng, 180)
     reads, _ = synth.hifi_reads(rng, [src], 9, err=0.02, flank=0, lo=0, hi=1 << 20)
-    reads += [src[60:], src[75:160], b"", b"ACGTNACGT", src[:50]]
-    offsets = [-1] * 9 + [60, 80, -1, 10, 0]
+    reads += [src[60:], src[75:160], b"", b"ACGTNACGT", src[:50], b"*" * 30 + src[30:], src[:90] + b"**" + src[92:]]  # '*' = wildcard
+    offsets = [-1] * 9 + [60, 80, -1, 10, 0, -1, -1]
     for band, window in ((8, 0), (32, 0), (16, 30), (100, 64)):
         cfg = co.Config(band=band, offset_window=window)
         cons = sp.Consensus(ctx, reads, offsets, offset_window=window, band=band, max_tracks=6)
@@ -164,3 +164,43 @@ def test_hla_consensus_step_vs_oracle(hpc_only):
     assert got_pass == want_pass and tuple(got_groups) == want_groups
     assert want_pass and set(want_groups) == {a, b}
     assert want_d["is_consensus1"] in ([k % 2 == 0 for k in range(10)], [k % 2 == 1 for k in range(10)])  # the reads split by source allele
+
+
+def priority_case(rng):
+    """Four sources: A, B (two SNVs: differs at both levels), C (a homopolymer of A two bases longer: same HPC as A), D (unrelated,
+    seeded apart); five reads each, chain = (homopolymer-compressed, raw)."""
+    import starphase_oracle as so
+
+    a = rnd(rng, 300)
+    b = bytearray(a)
+    for q in (80, 190):
+        b[q] = b"ACGT"[(b"ACGT".index(bytes([a[q]])) + 2) % 4]
+    b = bytes(b)
+    c = a[:150] + a[150:151] * 2 + a[150:]
+    d = rnd(rng, 260)
+    sources = [a, b, c, d]
+    chains, offsets, seeds, truth = [], [], [], []
+    for k in range(20):
+        src = sources[k % 4]
+        chains.append([so.hpc(src), src])
+        offsets.append([None, None])
+        seeds.append(3 if k % 4 == 3 else None)
+        truth.append(k % 4)
+    return sources, chains, offsets, seeds, truth
+
+
+def test_priority_consensus_vs_oracle():
+    """PriorityConsensusDWFA (src/cyp2d6/caller.rs:145-280) through the C++ host against the oracle's restatement, and the property
+    that pins both: the reads come back grouped by source, every group with its (HPC, raw) consensus pair."""
+    import starphase_oracle as so
+    from pb_starphase_b200 import _starphase_host as host
+
+    sources, chains, offsets, seeds, truth = priority_case(np.random.default_rng(21))
+    want_cons, want_idx = co.priority_consensus(chains, offsets, seeds)
+    gpu = host.GpuAligner(0)
+    got_cons, got_idx = host.priority_consensus(gpu, [[x.decode() for x in ch] for ch in chains], offsets, seeds, {})
+    assert list(got_idx) == want_idx
+    assert [[(s, list(sc)) for s, sc in levels] for levels in got_cons] == [[(s, list(sc)) for s, sc in levels] for levels in want_cons]
+    assert len(want_cons) == 4
+    for k, g in enumerate(want_idx):
+        assert want_cons[g][1][0] == sources[truth[k]] and want_cons[g][0][0] == so.hpc(sources[truth[k]])
