@@ -128,6 +128,16 @@ sp_status sp_plan_lane_classes(const int64_t *lens, int64_t n, int max_classes, 
 
 /* Upload + pack a text set (reads / consensus sequences) into tile streams. */
 sp_status sp_targets_create(sp_ctx *ctx, const sp_seqset *targets, sp_targets **out);
+/* A text set built on the device from pieces of a resident one (row N4 of SURVEY.md 8f): output sequence q = the concatenation
+ * of the intervals [iv_begin[k], iv_end[k]), k in [iv_off[q], iv_off[q + 1]), of source sequence src_index[q], reverse-complemented
+ * as a whole when revcomp[q] != 0 (A<->T, C<->G in either case; N and any other byte stay; revcomp NULL = none).  This is
+ * splice_read's cDNA (src/hla/caller.rs:1518-1576: the exon intervals in read coordinates, which the host gets from the record's
+ * CIGAR) and the strand handling of :1337-1368 and src/hla/realigner.rs:511-515 without the bases crossing PCIe again: only the
+ * interval tables go up.  The result is an ordinary sp_targets (K1 texts, either side of K4 / K9). */
+sp_status sp_targets_derive(sp_ctx *ctx, const sp_targets *src, int64_t n_out, const int32_t *src_index, const int64_t *iv_off,
+                            const int32_t *iv_begin, const int32_t *iv_end, const uint8_t *revcomp, sp_targets **out);
+/* Copies a text set back: bases[sp_targets_total_len] and offsets[sp_targets_count + 1] (offsets[0] = 0). */
+sp_status sp_targets_read(const sp_targets *t, uint8_t *bases, int64_t *offsets);
 void sp_targets_destroy(sp_targets *t);
 int64_t sp_targets_count(const sp_targets *t);
 int64_t sp_targets_total_len(const sp_targets *t);

@@ -61,6 +61,8 @@ SIGNATURES = {
     "sp_patterns_padded_rows": (C.c_int64, [_P]),
     "sp_plan_lane_classes": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(C.c_int), _P, _P, _P, C.POINTER(C.c_int64)]),
     "sp_targets_create": (C.c_int, [_P, C.POINTER(SeqSet), C.POINTER(_P)]),
+    "sp_targets_derive": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "sp_targets_read": (C.c_int, [_P, _P, _P]),
     "sp_targets_destroy": (None, [_P]),
     "sp_targets_count": (C.c_int64, [_P]),
     "sp_targets_total_len": (C.c_int64, [_P]),
@@ -595,6 +597,31 @@ class TargetSet:
         self.n = int(ctx._lib.sp_targets_count(h))
         self.total_len = int(ctx._lib.sp_targets_total_len(h))
         return self
+
+    def derive(self, pieces, revcomp=None) -> "TargetSet":
+        """A new resident set built on the device: pieces[q] = (source index, [(begin, end), ...]) -- the concatenation of those
+        intervals of that sequence -- reverse-complemented as a whole where revcomp[q] is true (sp_targets_derive)."""
+        n = len(pieces)
+        src = np.ascontiguousarray([p[0] for p in pieces] or [0], dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.int64)
+        for q, p in enumerate(pieces):
+            off[q + 1] = off[q] + len(p[1])
+        iv = [iv for p in pieces for iv in p[1]] or [(0, 0)]
+        b = np.ascontiguousarray([x[0] for x in iv], dtype=np.int32)
+        e = np.ascontiguousarray([x[1] for x in iv], dtype=np.int32)
+        rc = np.ascontiguousarray(revcomp, dtype=np.uint8) if revcomp is not None else None
+        h = _P()
+        self.ctx._check(self.ctx._lib.sp_targets_derive(self.ctx._h, self._h, n, src.ctypes.data, off.ctypes.data, b.ctypes.data, e.ctypes.data,
+                                                        rc.ctypes.data if rc is not None else None, C.byref(h)))
+        return TargetSet._adopt(self.ctx, h)
+
+    def read(self):
+        """The sequences back as a list of bytes (sp_targets_read)."""
+        bases = np.zeros(max(self.total_len, 1), dtype=np.uint8)
+        offs = np.zeros(self.n + 1, dtype=np.int64)
+        self.ctx._check(self.ctx._lib.sp_targets_read(self._h, bases.ctypes.data, offs.ctypes.data))
+        raw = bases.tobytes()
+        return [raw[int(offs[i]):int(offs[i + 1])] for i in range(self.n)]
 
     def close(self):
         if getattr(self, "_h", None) and self.ctx._h:

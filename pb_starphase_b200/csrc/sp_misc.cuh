@@ -82,4 +82,50 @@ __global__ void __launch_bounds__(256) k6_variant_match(const uint32_t *__restri
     vi_match[t] = vi;
 }
 
+// ------------------------------------------------------------------------------------------
+// Derived text sets (row N4 of SURVEY.md 8f): spliced / reverse-complemented sequences built on the device from a resident set.
+// Output sequence q = the concatenation of its intervals of source sequence src_index[q], reverse-complemented as a whole when
+// revcomp[q] is set.  One thread per output base: two binary searches (sequence, interval) and one byte.
+// ------------------------------------------------------------------------------------------
+struct DeriveParams {
+    const uint8_t *src_bases;
+    const long long *src_offs;
+    const int32_t *src_index;   // [n_out]
+    const long long *iv_off;    // [n_out + 1] first interval of every output sequence
+    const int32_t *iv_begin;    // [n_iv]
+    const long long *iv_prefix; // [n_iv] output bases of the sequence before this interval (forward order)
+    const uint8_t *revcomp;     // [n_out]
+    const long long *out_offs;  // [n_out + 1]
+    uint8_t *out_bases;
+    long long n_out, total;
+};
+
+__device__ __forceinline__ uint8_t complement_base(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return c;  // N and anything else stays
+    }
+}
+
+__global__ void __launch_bounds__(256) derive_texts(const DeriveParams p) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    long long lo = 0, hi = p.n_out;  // the sequence that holds output base i: last q with out_offs[q] <= i
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (p.out_offs[mid] <= i) lo = mid; else hi = mid;
+    }
+    const long long q = lo, len = p.out_offs[q + 1] - p.out_offs[q];
+    const bool rc = p.revcomp[q] != 0;
+    const long long pos = rc ? len - 1 - (i - p.out_offs[q]) : i - p.out_offs[q];
+    long long a = p.iv_off[q], b = p.iv_off[q + 1];  // last interval whose prefix <= pos
+    while (b - a > 1) {
+        const long long mid = (a + b) >> 1;
+        if (p.iv_prefix[mid] <= pos) a = mid; else b = mid;
+    }
+    const uint8_t c = p.src_bases[p.src_offs[p.src_index[q]] + p.iv_begin[a] + (pos - p.iv_prefix[a])];
+    p.out_bases[i] = rc ? complement_base(c) : c;
+}
+
 }  // namespace sp

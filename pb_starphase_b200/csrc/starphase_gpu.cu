@@ -496,6 +496,93 @@ sp_status sp_internal_targets_adopt(sp_ctx *ctx, uint8_t *d_bases, long long *d_
     return SP_OK;
 }
 
+extern "C" sp_status sp_targets_derive(sp_ctx *ctx, const sp_targets *src, int64_t n_out, const int32_t *src_index, const int64_t *iv_off,
+                                       const int32_t *iv_begin, const int32_t *iv_end, const uint8_t *revcomp, sp_targets **out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!out) return fail(ctx, SP_ERR_INVALID, "sp_targets_derive: out is NULL");
+    *out = nullptr;
+    if (!src || n_out < 0 || (n_out > 0 && (!src_index || !iv_off))) return fail(ctx, SP_ERR_INVALID, "sp_targets_derive: bad argument");
+    const int64_t n_iv = n_out ? iv_off[n_out] : 0;
+    if (n_out > 0 && (iv_off[0] != 0 || n_iv < 0 || (n_iv > 0 && (!iv_begin || !iv_end)))) return fail(ctx, SP_ERR_INVALID, "sp_targets_derive: bad interval table");
+    std::vector<int64_t> out_offs(static_cast<size_t>(n_out) + 1, 0);
+    std::vector<long long> iv_prefix(static_cast<size_t>(std::max<int64_t>(n_iv, 1)), 0), iv_off_ll(static_cast<size_t>(n_out) + 1, 0);
+    for (int64_t q = 0; q < n_out; ++q) {
+        if (src_index[q] < 0 || src_index[q] >= src->n || iv_off[q + 1] < iv_off[q]) return fail(ctx, SP_ERR_INVALID, "sp_targets_derive: bad source index or interval range");
+        const int64_t slen = src->h_offs[static_cast<size_t>(src_index[q]) + 1] - src->h_offs[static_cast<size_t>(src_index[q])];
+        int64_t len = 0;
+        for (int64_t k = iv_off[q]; k < iv_off[q + 1]; ++k) {
+            if (iv_begin[k] < 0 || iv_end[k] < iv_begin[k] || iv_end[k] > slen) return fail(ctx, SP_ERR_INVALID, "sp_targets_derive: interval outside its source sequence");
+            iv_prefix[static_cast<size_t>(k)] = len;
+            len += iv_end[k] - iv_begin[k];
+        }
+        out_offs[static_cast<size_t>(q) + 1] = out_offs[static_cast<size_t>(q)] + len;
+        iv_off_ll[static_cast<size_t>(q) + 1] = iv_off[q + 1];
+    }
+    // empty intervals would break the "last interval whose prefix <= pos" search: they are dropped from the device tables
+    std::vector<int32_t> begin_c;
+    std::vector<long long> prefix_c, off_c(static_cast<size_t>(n_out) + 1, 0);
+    for (int64_t q = 0; q < n_out; ++q) {
+        for (int64_t k = iv_off[q]; k < iv_off[q + 1]; ++k)
+            if (iv_end[k] > iv_begin[k]) { begin_c.push_back(iv_begin[k]); prefix_c.push_back(iv_prefix[static_cast<size_t>(k)]); }
+        off_c[static_cast<size_t>(q) + 1] = static_cast<long long>(begin_c.size());
+    }
+    if (begin_c.empty()) { begin_c.push_back(0); prefix_c.push_back(0); }
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t total = out_offs[static_cast<size_t>(n_out)];
+    std::vector<long long> out_offs_ll(out_offs.begin(), out_offs.end());
+    std::vector<uint8_t> rc(static_cast<size_t>(std::max<int64_t>(n_out, 1)), 0);
+    for (int64_t q = 0; q < n_out; ++q) rc[static_cast<size_t>(q)] = revcomp ? revcomp[q] : 0;
+    uint8_t *d_bases = nullptr, *d_rc = nullptr;
+    long long *d_offs = nullptr, *d_ivoff = nullptr, *d_prefix = nullptr;
+    int32_t *d_src = nullptr, *d_begin = nullptr;
+    auto cleanup = [&]() { dev_free(ctx, d_rc); dev_free(ctx, d_ivoff); dev_free(ctx, d_prefix); dev_free(ctx, d_src); dev_free(ctx, d_begin); };
+    auto bail = [&](cudaError_t e) -> sp_status {
+        cleanup(); dev_free(ctx, d_bases); dev_free(ctx, d_offs);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SP_ERR_NOMEM : SP_ERR_CUDA, std::string("sp_targets_derive: ") + cudaGetErrorString(e));
+    };
+    cudaError_t e = dev_malloc(ctx, &d_bases, static_cast<size_t>(std::max<int64_t>(total, 16)));
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_offs, out_offs_ll.size() * sizeof(long long));
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_rc, rc.size());
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_ivoff, off_c.size() * sizeof(long long));
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_prefix, prefix_c.size() * sizeof(long long));
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_src, static_cast<size_t>(std::max<int64_t>(n_out, 1)) * 4);
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_begin, begin_c.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs, out_offs_ll.data(), out_offs_ll.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rc, rc.data(), rc.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ivoff, off_c.data(), off_c.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_prefix, prefix_c.data(), prefix_c.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_out) e = cudaMemcpyAsync(d_src, src_index, static_cast<size_t>(n_out) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_begin, begin_c.data(), begin_c.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return bail(e);
+    if (total > 0) {
+        DeriveParams prm;
+        prm.src_bases = src->d_bases; prm.src_offs = src->d_offs; prm.src_index = d_src; prm.iv_off = d_ivoff; prm.iv_begin = d_begin;
+        prm.iv_prefix = d_prefix; prm.revcomp = d_rc; prm.out_offs = d_offs; prm.out_bases = d_bases; prm.n_out = n_out; prm.total = total;
+        derive_texts<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(prm);
+        ++ctx->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the host tables above go out of scope
+    if (e != cudaSuccess) return bail(e);
+    cleanup();
+    const sp_status st = sp_internal_targets_adopt(ctx, d_bases, d_offs, out_offs.data(), n_out, out);
+    if (st != SP_OK) { dev_free(ctx, d_bases); dev_free(ctx, d_offs); }
+    return st;
+}
+
+extern "C" sp_status sp_targets_read(const sp_targets *t, uint8_t *bases, int64_t *offsets) {
+    if (!t) return SP_ERR_INVALID;
+    sp_ctx *ctx = t->ctx;
+    if (!offsets || (t->total_len > 0 && !bases)) return fail(ctx, SP_ERR_INVALID, "sp_targets_read: NULL argument");
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i <= t->n; ++i) offsets[i] = t->h_offs[static_cast<size_t>(i)];
+    if (t->total_len > 0) {
+        SP_CUDA(ctx, cudaMemcpyAsync(bases, t->d_bases, static_cast<size_t>(t->total_len), cudaMemcpyDeviceToHost, ctx->stream));
+        SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SP_OK;
+}
+
 extern "C" void sp_targets_destroy(sp_targets *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);

@@ -213,8 +213,9 @@ std::string reverse_complement(const std::string &s) {
     return out;
 }
 
-std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
-                                           const std::vector<std::pair<uint64_t, uint64_t>> &exons) {
+std::pair<std::vector<std::pair<size_t, size_t>>, size_t> splice_segments(size_t sequence_len, int64_t pos,
+                                                                          const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                                                          const std::vector<std::pair<uint64_t, uint64_t>> &exons) {
     // reference coordinate -> read coordinate for aligned (M / = / X) columns: rust-htslib's aligned_pairs()
     std::unordered_map<uint64_t, size_t> lookup;
     size_t q = 0;
@@ -232,7 +233,7 @@ std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t 
             default: throw HostError("Unexpected cigar type: " + std::to_string(op.second));
         }
     }
-    if (q > sequence.size()) throw HostError("splice_read: cigar is longer than the sequence");
+    if (q > sequence_len) throw HostError("splice_read: cigar is longer than the sequence");
     size_t offset = 0;
     std::vector<std::pair<size_t, size_t>> segments;
     for (const auto &ex : exons) {
@@ -243,12 +244,17 @@ std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t 
         if (segments.empty()) offset += static_cast<size_t>(first - ex.first);
         if (first <= last) segments.emplace_back(lookup.at(first), lookup.at(last) + 1);
     }
+    for (const auto &s : segments)
+        if (s.first > s.second || s.second > sequence_len) throw HostError("splice_read: slice index out of range");
+    return {segments, offset};
+}
+
+std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                           const std::vector<std::pair<uint64_t, uint64_t>> &exons) {
+    const auto seg = splice_segments(sequence.size(), pos, cigar, exons);
     std::string spliced;
-    for (const auto &s : segments) {
-        if (s.first > s.second || s.second > sequence.size()) throw HostError("splice_read: slice index out of range");
-        spliced.append(sequence, s.first, s.second - s.first);
-    }
-    return {spliced, offset};
+    for (const auto &s : seg.first) spliced.append(sequence, s.first, s.second - s.first);
+    return {spliced, seg.second};
 }
 
 ScoreReadTargets prepare_score_read_targets(const std::string &read_sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,

@@ -82,6 +82,36 @@ std::shared_ptr<ResidentSeqs> GpuAligner::upload(const SeqList &seqs) {
     return r;
 }
 
+std::shared_ptr<ResidentSeqs> GpuAligner::derive(const ResidentSeqs &src, const std::vector<std::pair<size_t, std::vector<std::pair<size_t, size_t>>>> &pieces,
+                                                 const std::vector<bool> &revcomp) {
+    if (!revcomp.empty() && revcomp.size() != pieces.size()) throw HostError("derive: one revcomp flag per output expected");
+    std::shared_ptr<ResidentSeqs> r(new ResidentSeqs());
+    std::vector<int32_t> src_index, iv_begin, iv_end;
+    std::vector<int64_t> iv_off(1, 0);
+    std::vector<uint8_t> rc;
+    for (size_t q = 0; q < pieces.size(); ++q) {
+        if (pieces[q].first >= src.seqs_.size()) throw HostError("derive: source index outside the set");
+        const std::string &s = src.seqs_[pieces[q].first];
+        std::string out;
+        for (const auto &iv : pieces[q].second) {
+            if (iv.first > iv.second || iv.second > s.size()) throw HostError("derive: interval outside its source sequence");
+            out.append(s, iv.first, iv.second - iv.first);
+            iv_begin.push_back(static_cast<int32_t>(iv.first)); iv_end.push_back(static_cast<int32_t>(iv.second));
+        }
+        const bool flip = !revcomp.empty() && revcomp[q];
+        r->seqs_.push_back(flip ? reverse_complement(out) : out);  // the host copy (lengths, CIGAR / MD strings)
+        src_index.push_back(static_cast<int32_t>(pieces[q].first));
+        iv_off.push_back(static_cast<int64_t>(iv_begin.size()));
+        rc.push_back(flip ? 1 : 0);
+    }
+    if (iv_begin.empty()) { iv_begin.push_back(0); iv_end.push_back(0); }
+    if (src_index.empty()) { src_index.push_back(0); rc.push_back(0); }
+    check(sp_targets_derive(ctx_, src.t_, static_cast<int64_t>(pieces.size()), src_index.data(), iv_off.data(), iv_begin.data(), iv_end.data(), rc.data(),
+                            &r->t_),
+          "sp_targets_derive");
+    return r;
+}
+
 ResidentSeqs::~ResidentSeqs() { sp_targets_destroy(t_); }
 
 // host sequence lists: uploaded for this call only

@@ -444,24 +444,64 @@ HlaGeneIndex::HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const s
     if (!settings.disable_cdna_scoring) cdna_ = gpu.prepare_patterns(cdna);
 }
 
+// the call from resident targets: Td = DNA targets (K1 now, K4 of the per-read assignment below), Tc = cDNA targets or null
+HlaGeneCall diplotype_from_targets(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<std::string> &qnames,
+                                          const std::shared_ptr<ResidentSeqs> &Td, const std::shared_ptr<ResidentSeqs> &Tc,
+                                          const DiplotypeSettings &settings);
+
 HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRead> &reads, const DiplotypeSettings &settings) {
+    if (reads.empty() || index.allowed_.empty()) return diplotype_from_targets(gpu, index, {}, nullptr, nullptr, settings);
+    SeqList dna_targets, cdna_targets;
+    std::vector<std::string> qnames;
+    for (const auto &r : reads) { dna_targets.push_back(r.dna_target); cdna_targets.push_back(r.cdna_target); qnames.push_back(r.qname); }
+    const bool dual = !(settings.disable_cdna_scoring || !index.cdna_);
+    return diplotype_from_targets(gpu, index, qnames, gpu.upload(dna_targets), dual ? gpu.upload(cdna_targets) : nullptr, settings);
+}
+
+HlaGeneCall diplotype_hla_gene_records(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRecord> &records,
+                                       const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand,
+                                       const DiplotypeSettings &settings) {
+    if (records.empty() || index.allowed_.empty()) return diplotype_from_targets(gpu, index, {}, nullptr, nullptr, settings);
+    // the reads go up once, with one extra sequence "N": the cDNA target of a read whose splice is empty (src/hla/caller.rs:1355-1366)
+    SeqList seqs;
+    std::vector<std::string> qnames;
+    for (const auto &r : records) { seqs.push_back(r.sequence); qnames.push_back(r.qname); }
+    seqs.push_back("N");
+    const std::shared_ptr<ResidentSeqs> reads = gpu.upload(seqs);
+    const bool dual = !(settings.disable_cdna_scoring || !index.cdna_);
+    std::vector<std::pair<size_t, std::vector<std::pair<size_t, size_t>>>> dna_pieces, cdna_pieces;
+    std::vector<bool> dna_rc, cdna_rc;
+    for (size_t q = 0; q < records.size(); ++q) {
+        dna_pieces.push_back({q, {{0, records[q].sequence.size()}}});
+        dna_rc.push_back(!is_forward_strand);
+        if (!dual) continue;
+        const auto seg = splice_segments(records[q].sequence.size(), records[q].pos, records[q].cigar, exons);
+        size_t total = 0;
+        for (const auto &sg : seg.first) total += sg.second - sg.first;
+        if (total == 0) { cdna_pieces.push_back({records.size(), {{0, 1}}}); cdna_rc.push_back(false); }
+        else { cdna_pieces.push_back({q, seg.first}); cdna_rc.push_back(!is_forward_strand); }
+    }
+    return diplotype_from_targets(gpu, index, qnames, gpu.derive(*reads, dna_pieces, dna_rc), dual ? gpu.derive(*reads, cdna_pieces, cdna_rc) : nullptr,
+                                  settings);
+}
+
+HlaGeneCall diplotype_from_targets(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<std::string> &qnames,
+                                          const std::shared_ptr<ResidentSeqs> &Td, const std::shared_ptr<ResidentSeqs> &Tc,
+                                          const DiplotypeSettings &settings) {
     const auto &allowed = index.allowed_;
     HlaGeneCall call;
-    if (reads.empty() || allowed.empty()) {  // sentinels of src/hla/caller.rs:32-37
+    if (qnames.empty() || allowed.empty()) {  // sentinels of src/hla/caller.rs:32-37
         call.hla_id1 = call.hla_id2 = "NO_READS";
         call.diplotype = {"NO_READS", "NO_READS"};
         return call;
     }
-    SeqList dna_targets, cdna_targets;
-    for (const auto &r : reads) { dna_targets.push_back(r.dna_target); cdna_targets.push_back(r.cdna_target); }
-    const int64_t R = static_cast<int64_t>(reads.size());
-    const std::shared_ptr<ResidentSeqs> Td = gpu.upload(dna_targets);  // K1 now, K4 of the per-read assignment below
+    const int64_t R = static_cast<int64_t>(qnames.size());
     const std::unique_ptr<DeviceMatrix> Dd = gpu.score_device(*Td, index.realigner_->index());
     std::vector<sp_pair_rec> top;
-    if (settings.disable_cdna_scoring || !index.cdna_) {
+    if (settings.disable_cdna_scoring || !index.cdna_ || !Tc) {
         top = gpu.pair_minsum_topk(*Dd, nullptr, 10);
     } else {
-        const std::unique_ptr<DeviceMatrix> Dc = gpu.score_device(cdna_targets, *index.cdna_);
+        const std::unique_ptr<DeviceMatrix> Dc = gpu.score_device(*Tc, *index.cdna_);
         top = gpu.pair_minsum_topk(*Dc, Dd.get(), 10);  // (cDNA, DNA) lexicographic: src/hla/mapping.rs:111-117
     }
     if (top.empty()) throw HostError("diplotype_hla_gene: pair ranking returned nothing");
@@ -486,7 +526,7 @@ HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::
     // per-read database assignment, as HlaRealigner::realign_record reports it (restricted to this gene): the DNA
     // distances are already on the device
     std::vector<std::pair<std::string, std::string>> qs;
-    for (const auto &r : reads) qs.emplace_back(r.qname, r.dna_target);
+    for (size_t r = 0; r < qnames.size(); ++r) qs.emplace_back(qnames[r], Td->sequences()[r]);
     call.mapping_details = index.realigner_->realign_records_scored(qs, *Dd, 5, Td.get());
     return call;
 }

@@ -363,6 +363,20 @@ PYBIND11_MODULE(_starphase_host, m) {
         return d;
     });
 
+    // records: (qname, read sequence, pos, cigar [(len, op)]); the DNA / cDNA targets are derived on the device (sp_targets_derive)
+    m.def("diplotype_hla_gene_records", [](GpuAligner &g, HlaGeneIndex &index,
+                                           const std::vector<std::tuple<std::string, std::string, int64_t, std::vector<std::pair<uint32_t, uint8_t>>>> &records,
+                                           const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand, const DiplotypeSettings &s) {
+        std::vector<HlaRecord> rs;
+        for (const auto &r : records) rs.push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r), std::get<3>(r)});
+        const HlaGeneCall c = diplotype_hla_gene_records(g, index, rs, exons, is_forward_strand, s);
+        py::dict d;
+        d["hla_id1"] = c.hla_id1; d["hla_id2"] = c.hla_id2; d["counts1"] = c.counts1; d["counts2"] = c.counts2;
+        d["pair_score_cdna"] = c.pair_score_cdna; d["pair_score_dna"] = c.pair_score_dna;
+        d["gene_details"] = c.gene_details();
+        return d;
+    });
+
     // ---- CYP2D6 ----
     using RegionRows = std::vector<std::tuple<std::string, std::optional<std::string>, std::optional<size_t>>>;
     m.def("label_ops", [](const std::string &type, const std::optional<std::string> &sub, const std::string &type2,

@@ -253,6 +253,11 @@ class GpuAligner {
                                               int k);
     // resident path: nothing of size reads x alleles crosses PCIe, no sequence is uploaded twice
     std::shared_ptr<ResidentSeqs> upload(const SeqList &seqs);
+    // a resident set built on the device from pieces of another (sp_targets_derive): output q = the concatenation of the
+    // intervals pieces[q].second of source sequence pieces[q].first, reverse-complemented as a whole where revcomp[q]; only the
+    // interval tables cross PCIe (the host copy of the result is cut from the host copy of the source)
+    std::shared_ptr<ResidentSeqs> derive(const ResidentSeqs &src, const std::vector<std::pair<size_t, std::vector<std::pair<size_t, size_t>>>> &pieces,
+                                         const std::vector<bool> &revcomp);
     std::shared_ptr<PatternSet> prepare_patterns(const SeqList &patterns);
     std::unique_ptr<DeviceMatrix> score_device(const SeqList &targets, const PatternSet &patterns);          // K1
     std::unique_ptr<DeviceMatrix> score_device(const ResidentSeqs &targets, const PatternSet &patterns, bool want_end_col = false);
@@ -392,6 +397,11 @@ struct ScoreReadResult {  // score_read's (HashMap<String, HlaMappingStats>, Rea
 // src/hla/caller.rs:1518-1576 on plain values: `sequence` aligned at reference position `pos` (0-based) with `cigar`
 // (BAM op codes: 0 M, 1 I, 2 D, 3 N, 4 S, 5 H, 7 =, 8 X); exons = half-open reference ranges in the gene
 // definition's order.  Returns (spliced bases, offset of the first covered exon base).
+// the read intervals splice_read concatenates (:1541-1562) and its offset into the first exon: what sp_targets_derive needs to
+// build the cDNA on the device
+std::pair<std::vector<std::pair<size_t, size_t>>, size_t> splice_segments(size_t sequence_len, int64_t pos,
+                                                                          const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
+                                                                          const std::vector<std::pair<uint64_t, uint64_t>> &exons);
 std::pair<std::string, size_t> splice_read(const std::string &sequence, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
                                            const std::vector<std::pair<uint64_t, uint64_t>> &exons);
 std::string reverse_complement(const std::string &s);  // src/util/sequence.rs; throws on a non-ACGTN byte like the reference
@@ -503,6 +513,7 @@ struct HlaGeneCall {
 };
 // One gene's resident database: the allowed alleles in BTreeMap order with their DNA / cDNA pattern sets on the device
 // and the realigner over the same DNA index.  Built once per database, reused for every sample of a cohort.
+struct HlaRecord;
 class HlaGeneIndex {
   public:
     HlaGeneIndex(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name, const DiplotypeSettings &settings);
@@ -514,6 +525,10 @@ class HlaGeneIndex {
   private:
     std::vector<std::string> skipped_;
     friend HlaGeneCall diplotype_hla_gene(GpuAligner &, HlaGeneIndex &, const std::vector<HlaRead> &, const DiplotypeSettings &);
+    friend HlaGeneCall diplotype_hla_gene_records(GpuAligner &, HlaGeneIndex &, const std::vector<HlaRecord> &,
+                                                  const std::vector<std::pair<uint64_t, uint64_t>> &, bool, const DiplotypeSettings &);
+    friend HlaGeneCall diplotype_from_targets(GpuAligner &, HlaGeneIndex &, const std::vector<std::string> &, const std::shared_ptr<ResidentSeqs> &,
+                                              const std::shared_ptr<ResidentSeqs> &, const DiplotypeSettings &);
     std::string gene_name_;
     HlaDatabase gene_db_;  // owns the allele definitions the realigner points to
     std::vector<const HlaAlleleDefinition *> allowed_;
@@ -523,6 +538,17 @@ class HlaGeneIndex {
 // north_star (2): exhaustive read x allele scoring, allele-pair min-sum ranking with the (cDNA, DNA) key, then the
 // reference's het/hom decision (src/hla/caller.rs:889-901) and diplotype strings (:1046-1065)
 HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRead> &reads, const DiplotypeSettings &settings);
+// the same call from aligned records (what the reference holds when it reaches score_read, src/hla/caller.rs:1337-1368): the
+// read sequences are uploaded once; the DNA targets (reverse-complemented for a reverse-strand gene) and the cDNA targets
+// (splice_read's exon intervals, "N" when nothing is left or cDNA scoring is off) are built on the device from them
+struct HlaRecord {
+    std::string qname, sequence;
+    int64_t pos = 0;
+    std::vector<std::pair<uint32_t, uint8_t>> cigar;
+};
+HlaGeneCall diplotype_hla_gene_records(GpuAligner &gpu, HlaGeneIndex &index, const std::vector<HlaRecord> &records,
+                                       const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool is_forward_strand,
+                                       const DiplotypeSettings &settings);
 // convenience: builds the index for this one call
 HlaGeneCall diplotype_hla_gene(GpuAligner &gpu, const HlaDatabase &database, const std::string &gene_name,
                                const std::vector<HlaRead> &reads, const DiplotypeSettings &settings);

@@ -89,6 +89,9 @@ extern "C" {
     pub fn sp_patterns_create(ctx: *mut sp_ctx, p: *const sp_seqset, mode: c_int, out: *mut *mut sp_patterns) -> c_int;
     pub fn sp_patterns_destroy(p: *mut sp_patterns);
     pub fn sp_targets_create(ctx: *mut sp_ctx, t: *const sp_seqset, out: *mut *mut sp_targets) -> c_int;
+    pub fn sp_targets_derive(ctx: *mut sp_ctx, src: *const sp_targets, n_out: i64, src_index: *const i32, iv_off: *const i64, iv_begin: *const i32,
+                             iv_end: *const i32, revcomp: *const u8, out: *mut *mut sp_targets) -> c_int;
+    pub fn sp_targets_read(t: *const sp_targets, bases: *mut u8, offsets: *mut i64) -> c_int;
     pub fn sp_targets_destroy(t: *mut sp_targets);
     pub fn sp_score_device(ctx: *mut sp_ctx, t: *const sp_targets, p: *const sp_patterns, elem_bits: c_int,
                            want_end_col: c_int, out: *mut *mut sp_dmatrix) -> c_int;

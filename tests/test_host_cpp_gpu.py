@@ -494,3 +494,33 @@ def test_find_base_type_in_sequences_vs_oracle(host, gpu, oracle):
     assert names[0] == ["REP6", "CYP2D6", "link_region", "REP7", "spacer", "CYP2D7"]
     assert names[1].count("CYP2D6") == 2 and names[1].count("link_region") == 2
     assert names[3] == ["CYP2D6*5"] and names[4] == [] and names[5] == [] and "CYP2D6::CYP2D7::exon2" in names[6]
+
+
+@pytest.mark.parametrize("is_forward_strand", [True, False])
+def test_diplotype_from_records_derives_targets_on_device(host, gpu, is_forward_strand):
+    """diplotype_hla_gene_records: the reads go up once, the DNA targets (reverse-complemented for a reverse-strand gene) and the
+    cDNA targets (splice_read's exon intervals; "N" when nothing is left) are cut on the device (sp_targets_derive).  Same call and
+    same gene-details JSON as the flow fed with host-prepared targets (prepare_score_read_targets, src/hla/caller.rs:1337-1368)."""
+    rows, reads = hla_db()
+    s = host.DiplotypeSettings()
+    index = host.HlaGeneIndex(gpu, rows, "HLA-A", s)
+    exons = [(5100, 5400), (5900, 6300), (7000, 7250), (9000, 9100)]
+    records, prepared = [], []
+    for k, (q, dna, _c) in enumerate(reads["HLA-A"]):
+        seq = dna.decode() if is_forward_strand else host.reverse_complement(dna.decode())  # as the aligned record holds it
+        n = len(seq)
+        if k == 0:
+            cigar, pos = [(n, 0)], 20000                                   # covers no exon: cDNA target "N"
+        elif k % 3 == 1:
+            cigar, pos = [(30, 4), (500, 7), (3, 1), (n - 533 - 12, 0), (12, 4)], 5000 + k   # clips, an insertion
+        else:
+            cigar, pos = [(900, 0), (7, 2), (n - 900, 8)], 5000 + k                            # a deletion inside exon 2
+        records.append((q, seq, pos, cigar))
+        d_t, c_t = host.prepare_score_read_targets(seq, pos, cigar, exons, is_forward_strand, s)
+        prepared.append((q, d_t, c_t))
+    assert prepared[0][2] == "N" and all(len(p[2]) > 300 for p in prepared[1:])
+    want = host.diplotype_hla_gene_indexed(gpu, index, prepared, s)
+    got = host.diplotype_hla_gene_records(gpu, index, records, exons, is_forward_strand, s)
+    assert {k: got[k] for k in got if k != "gene_details"} == {k: want[k] for k in want if k != "gene_details"}
+    assert got["gene_details"].pretty() == want["gene_details"].pretty()
+    assert host.diplotype_hla_gene_records(gpu, index, [], exons, True, s)["hla_id1"] == "NO_READS"

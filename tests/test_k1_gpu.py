@@ -204,3 +204,35 @@ def test_large_sampled_parity(ctx, oracle):
     Dref = oracle.score_batch([reads[r] for r in rows], alleles)
     assert (D[rows] == Dref).all()
     assert (D >= 0).all() and (D <= np.array([len(a) for a in alleles])[None, :]).all()
+
+
+def test_targets_derive_splice_and_revcomp(ctx, oracle):
+    """sp_targets_derive: spliced / reverse-complemented sequences built on the device from a resident set equal the host's
+    (splice_read's exon concatenation, reverse_complement: src/hla/caller.rs:1518-1576, :1337-1368), and score like them."""
+    import pb_starphase_b200 as sp
+
+    rng = np.random.default_rng(41)
+    srcs = [bytes(rng.choice(list(b"ACGTN"), n, p=[.24, .24, .24, .24, .04]).tolist()) for n in (700, 1, 0, 1300, 64)]
+    srcs.append(srcs[0][:200].lower())
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    pieces = [(0, [(10, 80), (200, 200), (300, 512), (690, 700)]), (3, [(0, 1300)]), (3, [(5, 6)]), (1, [(0, 1)]), (2, []), (4, [(0, 64), (0, 64)]),
+              (5, [(3, 190)]), (0, [])]
+    revcomp = [False, True, True, False, False, True, True, True]
+    want = []
+    for (s, ivs), rc in zip(pieces, revcomp):
+        x = b"".join(srcs[s][b:e] for b, e in ivs)
+        want.append(x[::-1].translate(comp) if rc else x)
+    T = ctx.targets(srcs)
+    D = T.derive(pieces, revcomp)
+    assert D.read() == want and D.n == len(want) and D.total_len == sum(map(len, want))
+    assert T.derive(pieces[:2]).read() == [b"".join(srcs[s][b:e] for b, e in ivs) for s, ivs in pieces[:2]]  # revcomp NULL
+    pats = [srcs[0][300:512], want[1][100:400], b"ACGTACGT"]
+    P = ctx.patterns(pats)
+    M = ctx.score_device(D, P, 32)
+    got = M.to_host()
+    assert (got == oracle.score_batch(want, pats)).all()
+    M.close(); P.close()
+    for bad in ([(9, [(0, 1)])], [(0, [(5, 3)])], [(0, [(0, 701)])]):
+        with pytest.raises(sp.SpError):
+            T.derive(bad)
+    D.close(); T.close()
