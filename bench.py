@@ -38,6 +38,7 @@ TOPK = 16
 
 PANEL_READS = 40960      # BASELINE configs[2]
 COHORT_PER_GPU = 125     # BASELINE configs[4]: 1,000 samples on 8 GPUs
+COHORT_WORKERS = 3        # host threads (one sp_ctx each) per GPU in the cohort leg
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first communicator
 # when NCCL_DEBUG=VERSION is set in the environment), so the process's fd 1 is pointed at stderr for its whole life and the
@@ -73,6 +74,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
     ap.add_argument("--cohort-samples", type=int, default=COHORT_PER_GPU,
                     help="samples per GPU for the cohort leg (BASELINE configs[4]: 125 x 8 GPUs = 1,000 samples); 0 disables it")
+    ap.add_argument("--cohort-workers", type=int, default=COHORT_WORKERS,
+                    help="host threads per GPU in the cohort leg, one sp_ctx each (sp_ctx_share_device); 1 = one sample at a time")
     ap.add_argument("--panel-reads", type=int, default=PANEL_READS,
                     help="reads of the strong-scaling panel leg (BASELINE configs[2]: 40,960); 0 disables it")
     ap.add_argument("--panel-steps", type=int, default=1, help="timed steps of the panel leg (one step is ~110 s on one GPU)")
@@ -216,17 +219,22 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # cohort leg (BASELINE configs[4]): independent samples through the C++ host, one at a time per GPU
 # ---------------------------------------------------------------------------------------------
-def run_cohort(w, n_samples, rank, world, local_rank):
+def run_cohort(w, n_samples, rank, world, local_rank, workers=1):
     """Per sample the complete calls a pb-StarPhase run makes on this path, through the C++ host above the C ABI
     (pb_starphase_b200/host): HLA-A and HLA-B diplotypes (64 reads per gene, DNA + cDNA, against that gene's resident allele
     set: K1 x2, K2 pair ranking, het/hom decision, per-read database assignment via K5 + K4), CYP2D6 (39-template search over
     96 reads with K4 tracebacks, weight_sequence spans, chains, find_best_chain_pair) -- ending in the result JSON text of
-    that sample.  Samples are independent: ranks work through disjoint samples with no exchange (replicas).
+    that sample.  Samples are independent: ranks work through disjoint samples with no exchange (replicas).  With
+    workers > 1 the rank runs that many host threads, each with its own GpuAligner (sp_ctx) in sp_ctx_share_device mode
+    and its own resident allele index, taking samples from one queue -- the way a cohort is run with the reference, many
+    single-sample runs side by side: the latency-bound CYP2D6 / read-assignment phases of one sample fill the GPU and
+    the host while another sample's K1 runs.
     Returns (seconds, samples, bytes of JSON, info)."""
+    import threading
+
     from pb_starphase_b200 import _starphase_host as host
     from pb_starphase_b200 import synth
 
-    gpu = host.GpuAligner(local_rank)
     settings = host.DiplotypeSettings()
     genes = list(w["gene_views"].items())
     rows = []
@@ -234,28 +242,34 @@ def run_cohort(w, n_samples, rank, world, local_rank):
         for a in range(na):
             rows.append((f"HLA:HLA{g * 100000 + a:06d}", gene, [f"{1 + a // 400:02d}", f"{1 + (a // 20) % 20:02d}", f"{1 + a % 20:02d}", "01"],
                          w["dna"][drow + a].decode(), w["cdna"][crow + a].decode()))
-    index = {gene: host.HlaGeneIndex(gpu, [r for r in rows if r[1] == gene], gene, settings) for gene, _ in genes}
     per_gene = 64
     meta = dict(pbstarphase_version="2.0.1", cpic_version="synthetic", hla_version="synthetic", pharmvar_version="synthetic", build_time="n/a")
     dbg = os.environ.get("SP_COHORT_DEBUG") == "1"
 
-    def one_sample(sid, cyp):
-        details, marks = {}, [("start", time.perf_counter())]
-        for gene, (_, _, _, col0, nr) in genes:
-            lo = col0 + (sid * per_gene) % max(nr - per_gene, 1)
-            reads = [(f"s{sid}/{gene}/{k}", w["reads"][lo + k].decode(), w["ctargets"][lo + k].decode()) for k in range(per_gene)]
-            details[gene] = host.diplotype_hla_gene_indexed(gpu, index[gene], reads, settings)["gene_details"]
-            marks.append((gene, time.perf_counter()))
-        hits = host.find_base_type_in_sequences(gpu, cyp["templates"], cyp["reads"], False, 0.5)
-        marks.append(("cyp_template_search", time.perf_counter()))
-        call = host.call_cyp2d6_chains(gpu, cyp["consensuses"], cyp["regions"], cyp["roi"], False, True)
-        marks.append(("cyp_chains", time.perf_counter()))
-        details["CYP2D6"] = call["gene_details"]
-        text = host.starphase_json("2.0.1", meta, details)
-        marks.append(("json", time.perf_counter()))
-        if dbg:
-            print("cohort rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
-        return text, sum(len(h) for h in hits)
+    class Worker:
+        def __init__(self):
+            self.gpu = host.GpuAligner(local_rank)
+            if workers > 1:
+                self.gpu.share_device(True)
+            self.index = {gene: host.HlaGeneIndex(self.gpu, [r for r in rows if r[1] == gene], gene, settings) for gene, _ in genes}
+
+        def one_sample(self, sid, cyp):
+            gpu, details, marks = self.gpu, {}, [("start", time.perf_counter())]
+            for gene, (_, _, _, col0, nr) in genes:
+                lo = col0 + (sid * per_gene) % max(nr - per_gene, 1)
+                reads = [(f"s{sid}/{gene}/{k}", w["reads"][lo + k].decode(), w["ctargets"][lo + k].decode()) for k in range(per_gene)]
+                details[gene] = host.diplotype_hla_gene_indexed(gpu, self.index[gene], reads, settings)["gene_details"]
+                marks.append((gene, time.perf_counter()))
+            hits = host.find_base_type_in_sequences(gpu, cyp["templates"], cyp["reads"], False, 0.5)
+            marks.append(("cyp_template_search", time.perf_counter()))
+            call = host.call_cyp2d6_chains(gpu, cyp["consensuses"], cyp["regions"], cyp["roi"], False, True)
+            marks.append(("cyp_chains", time.perf_counter()))
+            details["CYP2D6"] = call["gene_details"]
+            text = host.starphase_json("2.0.1", meta, details)
+            marks.append(("json", time.perf_counter()))
+            if dbg:
+                print("cohort rank", rank, "sample", sid, " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+            return text, sum(len(h) for h in hits)
 
     def cyp_inputs(sid):
         c = synth.cyp2d6_diploid_sample(2000 + sid)
@@ -265,17 +279,46 @@ def run_cohort(w, n_samples, rank, world, local_rank):
 
     sids = [rank + world * k for k in range(n_samples)]
     inputs = {sid: cyp_inputs(sid) for sid in sids}  # host-side inputs exist before the clock starts
-    for k in range(2):
-        one_sample(sids[k % len(sids)], inputs[sids[k % len(sids)]])
+    pool = [Worker() for _ in range(max(workers, 1))]
+    results, errors, lock, nxt = {}, [], threading.Lock(), [0]
+    start = threading.Barrier(len(pool) + 1)
+
+    def work(wk, k0):
+        try:
+            for k in range(2):  # untimed: pools, plans and page-locked buffers of this worker's context reach their sizes
+                sid = sids[(k0 + k) % len(sids)]
+                wk.one_sample(sid, inputs[sid])
+            start.wait()
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= len(sids):
+                    return
+                results[sids[k]] = wk.one_sample(sids[k], inputs[sids[k]])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            start.abort()
+
+    threads = [threading.Thread(target=work, args=(wk, 2 * i), daemon=True) for i, wk in enumerate(pool)]
+    for th in threads:
+        th.start()
+    try:
+        start.wait()
+    except threading.BrokenBarrierError:
+        pass
     t0 = time.perf_counter()
-    nbytes, text, n_hits = 0, "", 0
-    for sid in sids:
-        text, n_hits = one_sample(sid, inputs[sid])
-        nbytes += len(text)
+    for th in threads:
+        th.join()
     dt = time.perf_counter() - t0
+    if errors:
+        raise errors[0]
+    nbytes = sum(len(t) for t, _ in results.values())
+    text, n_hits = results[sids[-1]]
     doc = json.loads(text)
     calls = {g: d["diplotypes"][0]["diplotype"] for g, d in doc["gene_details"].items()}
-    return dt, n_samples, nbytes, dict(last_sample_calls=calls, cyp2d6_template_hits=n_hits, kernel_launches=int(gpu.launch_count()))
+    return dt, n_samples, nbytes, dict(last_sample_calls=calls, cyp2d6_template_hits=n_hits, workers_per_gpu=len(pool),
+                                       kernel_launches=int(sum(wk.gpu.launch_count() for wk in pool)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -472,7 +515,7 @@ def run_ours(args):
     if args.cohort_samples > 0:
         barrier()
         try:
-            host_s, host_n, host_bytes, host_info = run_cohort(w, args.cohort_samples, rank, world, local_rank)
+            host_s, host_n, host_bytes, host_info = run_cohort(w, args.cohort_samples, rank, world, local_rank, args.cohort_workers)
         except Exception as e:  # the contract line must not depend on this leg
             host_info = dict(error=f"{type(e).__name__}: {e}")
         barrier()
@@ -509,7 +552,8 @@ def run_ours(args):
         if host_n and host_s > 0:
             cohort = dict(samples_per_s=host_n / host_s, samples=host_n, ms_per_sample_per_gpu=host_s / (host_n / world) * 1e3,
                           json_bytes_per_sample=host_bytes // max(host_n // world, 1), **host_info,
-                          scaling="replicas: independent samples round-robin over ranks, no exchange (%d per GPU; 1,000 at 8 GPUs)" % (host_n // world),
+                          scaling="replicas: independent samples round-robin over ranks, no exchange (%d per GPU; 1,000 at 8 GPUs); per GPU %d host "
+                                  "threads with one sp_ctx each (sp_ctx_share_device) take samples from one queue" % (host_n // world, host_info.get("workers_per_gpu", 1)),
                           sample="per sample, through the C++ host above the C ABI: HLA-A + HLA-B diplotype calls (64 reads per gene, DNA + cDNA, "
                                  "against that gene's full allele set: K1 x2, K2, het/hom, K5 + K4 read assignment), CYP2D6 39-template search with "
                                  "K4 tracebacks + weight_sequence + chains + find_best_chain_pair on a diploid 96-read case, result JSON text out "

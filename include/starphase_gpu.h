@@ -102,6 +102,12 @@ float sp_last_kernel_ms(sp_ctx *ctx, int which);
 uint64_t sp_launch_count(const sp_ctx *ctx);
 /* Block until all work queued on the context stream has finished. */
 sp_status sp_ctx_synchronize(sp_ctx *ctx);
+/* Several contexts on one GPU, each driven by its own host thread (a cohort worker pool: the reference runs one sample per
+ * process, src/cli/diplotype.rs; a cohort is many such runs side by side).  With on != 0 the context launches K1 -- the one long
+ * kernel of the path -- one CTA per work item instead of as a persistent grid, and launches of several rounds go to a side stream
+ * of the lowest priority, so the short kernels of the other contexts (their streams have the highest priority) are dispatched
+ * as soon as any K1 CTA retires.  Results are bit-identical either way.  A context alone on its GPU should leave this off. */
+sp_status sp_ctx_share_device(sp_ctx *ctx, int on);
 /* Page-locked host memory for result buffers (CIGAR pools, matrices): every entry point accepts pageable memory, but device ->
  * host copies into page-locked memory run at PCIe speed and skip the first-touch page faults of a fresh allocation.  The caller
  * owns the block and releases it with sp_pinned_free (NULL is ignored). */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "sp_last_kernel_ms": (C.c_float, [_P, C.c_int]),
     "sp_launch_count": (C.c_uint64, [_P]),
     "sp_ctx_synchronize": (C.c_int, [_P]),
+    "sp_ctx_share_device": (C.c_int, [_P, C.c_int]),
     "sp_pinned_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "sp_pinned_free": (None, [_P, _P]),
     "sp_patterns_create": (C.c_int, [_P, C.POINTER(SeqSet), C.c_int, C.POINTER(_P)]),
@@ -443,6 +444,10 @@ class Context:
 
     def synchronize(self):
         self._check(self._lib.sp_ctx_synchronize(self._h))
+
+    def share_device(self, on: bool = True):
+        """Several contexts on one GPU, one host thread each: K1 runs one CTA per item at the lowest stream priority."""
+        self._check(self._lib.sp_ctx_share_device(self._h, 1 if on else 0))
 
     def int_peak(self, kind: int = 0) -> float:
         v = C.c_double(0)

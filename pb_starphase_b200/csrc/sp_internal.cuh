@@ -43,7 +43,22 @@ struct sp_ctx {
     // back into `stream` with events, created on first use
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
+    // sp_ctx_share_device: several contexts drive this GPU from concurrent host threads.  Long K1 launches then go to `bulk`, a
+    // stream of the lowest priority, one CTA per work item, forked from / joined into `stream` (created at the highest priority)
+    bool share_device = false;
+    cudaStream_t bulk = nullptr;
+    cudaEvent_t bulk_fork = nullptr, bulk_join = nullptr;
 };
+
+static inline cudaError_t ctx_bulk(sp_ctx *ctx) {
+    if (ctx->bulk) return cudaSuccess;
+    int lo = 0, hi = 0;  // numerically: lo = least priority, hi = greatest
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->bulk, cudaStreamNonBlocking, lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->bulk_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->bulk_join, cudaEventDisableTiming);
+    return e;
+}
 
 static inline cudaError_t ctx_aux(sp_ctx *ctx) {
     if (ctx->aux_fork) return cudaSuccess;

@@ -54,7 +54,8 @@ struct K1Params {
     int out16;
     int prefix_mode;                // SP_PREFIX: top row delta +1
     uint32_t one, m1, sixteen;      // +1, -1 (0xFFFFFFFF), 16: passed at run time so `x * one + y` stays an IMAD (FMA pipe)
-    int *next_item;                 // work counter (zeroed by the host before the launch): items are handed out dynamically
+    int *next_item;                 // work counter (zeroed by the host before the launch): items are handed out dynamically;
+                                    // nullptr: one CTA per item (grid = items)
     uint32_t seed_a, seed_b;        // 1, 0xFFFFFFFF again: `seed_a - seed_b` sets the borrow that seeds the Myers add chain.  Separate
                                     // parameters on purpose: inline-asm operands live in R registers, and sharing them with one / m1
                                     // turned every IMAD multiplier from a uniform register into a third R operand (K1 -10 %)
@@ -305,10 +306,14 @@ __global__ void __launch_bounds__(K1_THREADS, k1_min_blocks(U)) k1_infix(const K
     __shared__ int s_item;
     // items (pattern group x text tile) are handed out from an atomic counter: tiles hold whole texts and differ in length,
     // and with few reads per call (the cohort's 64 per gene) a static round-robin left the last round a fifth full
-    for (;;) {
-        if (threadIdx.x == 0) s_item = atomicAdd(p.next_item, 1);
-        __syncthreads();
-        const int item = s_item;
+    // Without a counter (a context that shares its GPU, sp_ctx_share_device) the launch brings one CTA per item: the hardware's CTA
+    // scheduler hands the items out, and every retiring CTA is a slot that a short kernel of another context can take
+    for (bool once = true;; once = false) {
+        if (p.next_item) {
+            if (threadIdx.x == 0) s_item = atomicAdd(p.next_item, 1);
+            __syncthreads();
+        }
+        const int item = p.next_item ? s_item : (once ? static_cast<int>(blockIdx.x) : n_items);
         if (item >= n_items) break;
         const int g = item / p.n_tiles;
         const int tile = item - g * p.n_tiles;

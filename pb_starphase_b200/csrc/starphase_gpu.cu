@@ -51,7 +51,11 @@ extern "C" sp_status sp_ctx_create(int device, void *stream, sp_ctx **out) {
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
     } else {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        // highest priority: when contexts share a GPU (sp_ctx_share_device) their long K1 launches run on a lowest-priority side
+        // stream and everything on this one is dispatched ahead of K1's waiting CTAs; alone on a GPU the priority changes nothing
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
             delete ctx;
             return fail(nullptr, SP_ERR_CUDA, "cudaStreamCreate failed");
         }
@@ -94,12 +98,23 @@ extern "C" void sp_ctx_destroy(sp_ctx *ctx) {
         if (ctx->aux_join[i]) cudaEventDestroy(ctx->aux_join[i]);
     }
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->bulk) { cudaStreamSynchronize(ctx->bulk); cudaStreamDestroy(ctx->bulk); }
+    if (ctx->bulk_fork) cudaEventDestroy(ctx->bulk_fork);
+    if (ctx->bulk_join) cudaEventDestroy(ctx->bulk_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (void *p : ctx->pool) cudaFree(p);
     cudaFree(ctx->d_counter);
     cudaFreeHost(ctx->h_stage);
     if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     delete ctx;
+}
+
+extern "C" sp_status sp_ctx_share_device(sp_ctx *ctx, int on) {
+    if (!ctx) return SP_ERR_INVALID;
+    SP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on) SP_CUDA(ctx, ctx_bulk(ctx));
+    ctx->share_device = on != 0;
+    return SP_OK;
 }
 
 extern "C" sp_status sp_pinned_alloc(sp_ctx *ctx, size_t bytes, void **out) {
@@ -668,11 +683,29 @@ static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_
     int occ = 0;
     SP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_infix<U, TE>, K1_THREADS, smem));
     if (occ < 1) return fail(ctx, SP_ERR_CUDA, "K1 does not fit on an SM with the requested shared memory");
-    // persistent CTAs: a multiple of the SM count, each looping over (pattern-group, text-tile) items
-    const int grid = std::min(n_items, ctx->num_sms * occ);
     if (first) ev_begin(ctx, 0);  // the K1 timer spans the launches of all lane-width classes of one call
-    SP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-    k1_infix<U, TE><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+    if (ctx->share_device) {
+        // One CTA per item, handed out by the hardware: every retiring CTA is a slot the short kernels of the other contexts
+        // on this GPU can take.  A launch of several rounds goes to the lowest-priority side stream, so that those kernels (and
+        // this context's own short K1 launches, which stay on the main stream) are dispatched ahead of its waiting CTAs
+        K1Params q = prm;
+        q.next_item = nullptr;
+        const bool bulk = n_items > 2 * ctx->num_sms * occ;
+        if (bulk) {
+            SP_CUDA(ctx, cudaEventRecord(ctx->bulk_fork, ctx->stream));
+            SP_CUDA(ctx, cudaStreamWaitEvent(ctx->bulk, ctx->bulk_fork, 0));
+        }
+        k1_infix<U, TE><<<n_items, K1_THREADS, smem, bulk ? ctx->bulk : ctx->stream>>>(q);
+        if (bulk) {
+            SP_CUDA(ctx, cudaEventRecord(ctx->bulk_join, ctx->bulk));
+            SP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->bulk_join, 0));
+        }
+    } else {
+        // persistent CTAs: a multiple of the SM count, each looping over (pattern-group, text-tile) items
+        const int grid = std::min(n_items, ctx->num_sms * occ);
+        SP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+        k1_infix<U, TE><<<grid, K1_THREADS, smem, ctx->stream>>>(prm);
+    }
     if (last) ev_end(ctx, 0);
     ++ctx->launches;
     SP_CUDA(ctx, cudaGetLastError());

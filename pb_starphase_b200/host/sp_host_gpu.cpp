@@ -38,6 +38,8 @@ GpuAligner::~GpuAligner() {
     sp_ctx_destroy(ctx_);
 }
 
+void GpuAligner::share_device(bool on) { check(sp_ctx_share_device(ctx_, on ? 1 : 0), "sp_ctx_share_device"); }
+
 uint32_t *GpuAligner::cigar_buffer(int slot, int64_t entries) {
     if (entries > cig_cap_[slot]) {
         sp_pinned_free(ctx_, cig_buf_[slot]);

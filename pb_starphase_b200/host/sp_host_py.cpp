@@ -237,6 +237,7 @@ PYBIND11_MODULE(_starphase_host, m) {
         .def(py::init<int>(), py::arg("device") = 0)
         .def("score_batch", [](GpuAligner &g, const SeqList &t, const SeqList &p) { return g.score_batch(t, p); })
         .def("launch_count", &GpuAligner::launch_count)
+        .def("share_device", &GpuAligner::share_device, py::arg("on") = true)
         .def("align_pairs", [](GpuAligner &g, const SeqList &t, const SeqList &p, const std::vector<std::pair<int32_t, int32_t>> &pairs, int match_score) {
             py::list out;
             for (const Alignment &a : g.align_pairs(t, p, pairs, nullptr, match_score)) {
@@ -355,7 +356,8 @@ PYBIND11_MODULE(_starphase_host, m) {
                                            const std::vector<std::tuple<std::string, std::string, std::string>> &reads, const DiplotypeSettings &s) {
         std::vector<HlaRead> rs;
         for (const auto &r : reads) rs.push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r)});
-        const HlaGeneCall c = diplotype_hla_gene(g, index, rs, s);
+        // the interpreter lock is dropped for the C++ call: a cohort driver runs one sample per thread (one GpuAligner each)
+        const HlaGeneCall c = [&] { py::gil_scoped_release nogil; return diplotype_hla_gene(g, index, rs, s); }();
         py::dict d;
         d["hla_id1"] = c.hla_id1; d["hla_id2"] = c.hla_id2; d["counts1"] = c.counts1; d["counts2"] = c.counts2;
         d["pair_score_cdna"] = c.pair_score_cdna; d["pair_score_dna"] = c.pair_score_dna;
@@ -397,9 +399,14 @@ PYBIND11_MODULE(_starphase_host, m) {
                                             const SeqList &seqs, bool penalize_unmapped, double max_missing_frac) {
         std::vector<std::pair<Cyp2d6RegionLabel, std::string>> ts;
         for (const auto &t : templates) ts.push_back({Cyp2d6RegionLabel{region_type_from_name(std::get<0>(t)), std::get<1>(t)}, std::get<2>(t)});
-        Cyp2d6Extractor ex(g, std::move(ts));
+        std::vector<std::vector<AlleleMapping>> all_hits;
+        {
+            py::gil_scoped_release nogil;
+            Cyp2d6Extractor ex(g, std::move(ts));
+            all_hits = ex.find_base_type_in_sequences(seqs, penalize_unmapped, max_missing_frac);
+        }
         py::list out;
-        for (const auto &hits : ex.find_base_type_in_sequences(seqs, penalize_unmapped, max_missing_frac)) {
+        for (const auto &hits : all_hits) {
             py::list one;
             for (const AlleleMapping &h : hits)
                 one.append(py::make_tuple(h.allele_label.full_allele(), h.region_start, h.region_end,
@@ -517,7 +524,10 @@ PYBIND11_MODULE(_starphase_host, m) {
         std::map<std::string, std::vector<Cyp2d6ReadRegion>> regions;
         for (const auto &kv : roi)
             for (const auto &r : kv.second) regions[kv.first].push_back({std::get<0>(r), std::get<1>(r), std::get<2>(r)});
-        const Cyp2d6Call c = call_cyp2d6_chains(g, Cyp2d6Config::default_config(), consensuses, make_regions(rows), regions, infer, normalize_all);
+        const Cyp2d6Call c = [&] {
+            py::gil_scoped_release nogil;
+            return call_cyp2d6_chains(g, Cyp2d6Config::default_config(), consensuses, make_regions(rows), regions, infer, normalize_all);
+        }();
         py::dict d;
         d["best_chains"] = c.chain_pair.best_chains; d["score"] = c.chain_pair.score; d["dangling"] = c.chain_pair.dangling_alleles;
         d["n_possible_chains"] = c.chain_pair.n_possible_chains; d["n_full_evaluations"] = c.chain_pair.n_full_evaluations;

@@ -283,6 +283,8 @@ class GpuAligner {
     void variant_match(const std::vector<std::vector<uint8_t>> &seq_alleles, const std::vector<std::vector<uint8_t>> &hap_alleles,
                        const std::vector<uint8_t> &is_vi, std::vector<uint32_t> &vi_match, std::vector<uint32_t> &all_match);
     uint64_t launch_count() const;
+    // several aligners on one GPU, one host thread each (a cohort worker pool): sp_ctx_share_device
+    void share_device(bool on);
     sp_ctx *raw() { return ctx_; }
 
   private:

@@ -63,6 +63,7 @@ extern "C" {
     pub fn sp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut sp_ctx) -> c_int;
     pub fn sp_ctx_destroy(ctx: *mut sp_ctx);
     pub fn sp_ctx_synchronize(ctx: *mut sp_ctx) -> c_int;
+    pub fn sp_ctx_share_device(ctx: *mut sp_ctx, on: c_int) -> c_int;
     pub fn sp_pinned_alloc(ctx: *mut sp_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn sp_pinned_free(ctx: *mut sp_ctx, p: *mut c_void);
     pub fn sp_version() -> *const c_char;

@@ -524,3 +524,47 @@ def test_diplotype_from_records_derives_targets_on_device(host, gpu, is_forward_
     assert {k: got[k] for k in got if k != "gene_details"} == {k: want[k] for k in want if k != "gene_details"}
     assert got["gene_details"].pretty() == want["gene_details"].pretty()
     assert host.diplotype_hla_gene_records(gpu, index, [], exons, True, s)["hla_id1"] == "NO_READS"
+
+
+# ---- a cohort worker pool: several GpuAligners on one GPU, one host thread each (sp_ctx_share_device) -----------------
+def test_concurrent_aligners_share_one_gpu(host, gpu, oracle):
+    """Three host threads, one GpuAligner each in share_device mode, run HLA calls, the template search and the chain call
+    side by side (the pybind layer drops the interpreter lock for the C++ calls); every result equals the one the
+    single aligner of this module gives on its own."""
+    import threading
+
+    rows, reads = hla_db(seed=21, n_alleles=40, n_reads=16)
+    cons, crow, roi = cyp_case(1)
+    cpp_roi = {q: [(a, b, s.decode()) for a, b, s in regs] for q, regs in roi.items()}
+    c = cyp_templates()
+    templates = [(t, s, (seq if seq is not None else c["spacer" if t == "spacer" else "link"]).decode()) for t, s, seq in c["templates"]]
+    rng = np.random.default_rng(9)
+    seqs = [(rnd(rng, 100) + noisy(rng, c["rep6"] + c["d6"] + c["link"] + c["rep7"] + c["spacer"] + c["d7"], 10).replace(b"N", b"A") + rnd(rng, 80)).decode()
+            for _ in range(6)]
+    settings = host.DiplotypeSettings()
+
+    def sample(g):
+        out = [host.diplotype_hla_gene(g, rows, gene, cpp_reads(reads[gene]), settings)["gene_details"].pretty() for gene in ("HLA-A", "HLA-B")]
+        out.append(host.find_base_type_in_sequences(g, templates, seqs, False, 0.5))
+        out.append(host.call_cyp2d6_chains(g, [x.decode() for x in cons], crow, cpp_roi, False, True)["gene_details"].pretty())
+        return out
+
+    want = sample(gpu)
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            g = host.GpuAligner(0)
+            g.share_device(True)
+            results[k] = [sample(g) for _ in range(3)]
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for k in range(3):
+        assert all(r == want for r in results[k])

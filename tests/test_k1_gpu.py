@@ -236,3 +236,36 @@ def test_targets_derive_splice_and_revcomp(ctx, oracle):
         with pytest.raises(sp.SpError):
             T.derive(bad)
     D.close(); T.close()
+
+
+def test_share_device_mode_is_bit_identical(oracle):
+    """sp_ctx_share_device: K1 as one CTA per item (short launches on the context stream, launches of several rounds on the
+    lowest-priority side stream) gives the matrix of the persistent grid, with two contexts scoring from two host threads."""
+    import threading
+
+    alleles, reads, _ = synth.hla_gene(1234, "HLA-A", n_alleles=1200, n_reads=40)  # ~38 pattern groups x ~40 text tiles: the bulk route
+    small_p, small_t = alleles[:9], reads[:5]                                     # a handful of items: stays on the main stream
+    with sp.Context(0) as plain:
+        want, want_e = plain.score_batch(reads, alleles, want_end_col=True)
+        want_small = plain.score_batch(small_t, small_p)
+    assert (want[:6, :40] == oracle.score_batch(reads[:6], alleles[:40])).all()
+    got = {}
+
+    def run(tag):
+        with sp.Context(0) as c:
+            c.share_device(True)
+            for _ in range(2):
+                got[tag] = (c.score_batch(reads, alleles, want_end_col=True), c.score_batch(small_t, small_p))
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for k in range(2):
+        (D, E), Ds = got[k]
+        assert (D == want).all() and (E == want_e).all() and (Ds == want_small).all()
+    with sp.Context(0) as c:  # switching the mode off again restores the persistent grid
+        c.share_device(True)
+        c.share_device(False)
+        assert (c.score_batch(small_t, small_p) == want_small).all()
