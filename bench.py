@@ -249,7 +249,7 @@ def run_cohort(w, n_samples, rank, world, local_rank, workers=1):
     class Worker:
         def __init__(self):
             self.gpu = host.GpuAligner(local_rank)
-            if workers > 1:
+            if workers > 1 and os.environ.get("SP_COHORT_NOSHARE") != "1":  # experiment hook: persistent K1 grids side by side
                 self.gpu.share_device(True)
             self.index = {gene: host.HlaGeneIndex(self.gpu, [r for r in rows if r[1] == gene], gene, settings) for gene, _ in genes}
 

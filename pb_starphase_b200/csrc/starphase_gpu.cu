@@ -690,7 +690,7 @@ static sp_status launch_k1(sp_ctx *ctx, const K1Params &prm, size_t smem, int n_
         // this context's own short K1 launches, which stay on the main stream) are dispatched ahead of its waiting CTAs
         K1Params q = prm;
         q.next_item = nullptr;
-        const bool bulk = n_items > 2 * ctx->num_sms * occ;
+        const bool bulk = n_items > 2 * ctx->num_sms * occ && !getenv("SP_SHARE_NOBULK");  // experiment hook: everything on the main stream
         if (bulk) {
             SP_CUDA(ctx, cudaEventRecord(ctx->bulk_fork, ctx->stream));
             SP_CUDA(ctx, cudaStreamWaitEvent(ctx->bulk, ctx->bulk_fork, 0));
