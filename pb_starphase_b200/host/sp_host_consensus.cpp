@@ -528,4 +528,144 @@ std::pair<std::string, std::optional<std::string>> consensus_per_group(GpuAligne
     return out;
 }
 
+// ------------------------------------------------------------------------------------------
+// the consensus stage of the CYP2D6 caller (src/cyp2d6/caller.rs:145-310, :750-893)
+// ------------------------------------------------------------------------------------------
+std::pair<std::string, size_t> hpc_with_guide(const std::string &sequence, const std::string &guide_sequence, size_t guide_offset) {
+    return {hpc(sequence), hpc_pos(guide_sequence, guide_offset)};  // src/util/homopolymers.rs:53-64
+}
+
+CdwfaConfig cyp2d6_consensus_config(const DiplotypeSettings &cli) {  // :145-162
+    CdwfaConfig c;
+    c.min_count = cli.min_consensus_count;
+    c.min_af = cli.min_consensus_fraction;
+    c.dual_max_ed_delta = cli.dual_max_ed_delta;
+    c.allow_early_termination = true;
+    c.max_queue_size = 20;
+    c.max_capacity_per_size = 10;
+    c.offset_window = 2 * 50;  // "+-50 bp, but the config only lets us look before" (:147-148)
+    return c;
+}
+
+Cyp2d6ConsensusInputs cyp2d6_consensus_inputs(const std::map<std::string, std::string> &read_sequences,
+                                              const std::map<std::string, std::vector<AlleleMapping>> &regions_of_interest,
+                                              const Cyp2d6Extractor &d6_typer, double max_missing_consensus_frac, size_t offset_window) {
+    Cyp2d6ConsensusInputs in;
+    auto get_allele = [&](const Cyp2d6RegionLabel &label) -> const std::string & {  // Cyp2d6Extractor::get_allele
+        for (const auto &t : d6_typer.hybrid_sequences())
+            if (t.first.region_type == label.region_type && t.first.subtype_label == label.subtype_label) return t.second;
+        throw HostError("cyp2d6_consensus_inputs: no template for " + label.full_allele());
+    };
+    for (const auto &kv : regions_of_interest) {  // BTreeMap order (:178)
+        const auto rs = read_sequences.find(kv.first);
+        if (rs == read_sequences.end()) throw HostError("cyp2d6_consensus_inputs: no sequence for read " + kv.first);
+        for (const AlleleMapping &region : kv.second) {
+            if (region.mapping_stats.custom_score(true) > max_missing_consensus_frac) continue;  // :181-184
+            if (region.region_end > rs->second.size() || region.region_start > region.region_end)
+                throw HostError("cyp2d6_consensus_inputs: region outside read " + kv.first);
+            const size_t prefix_len = region.mapping_stats.clipped_start.value_or(0);
+            const std::string seq = rs->second.substr(region.region_start, region.region_end - region.region_start);
+            const auto hp = hpc_with_guide(seq, get_allele(region.allele_label), prefix_len);  // :200-202
+            in.raw_sequences.push_back(seq);
+            in.base_offsets.push_back(prefix_len == 0 ? 0 : prefix_len + offset_window);      // :195-199
+            in.hpc_sequences.push_back(hp.first);
+            in.hpc_offsets.push_back(hp.second == 0 ? 0 : hp.second + offset_window);         // :204-208
+            in.sequence_ids.push_back(kv.first + "_" + std::to_string(region.region_start) + "_" + std::to_string(region.region_end) + "_" +
+                                      region.allele_label.full_allele());
+            in.flattened_regions_of_interest.emplace_back(kv.first, region);
+            std::optional<uint64_t> seed;  // :224-231
+            switch (region.allele_label.region_type) {
+                case Cyp2d6RegionType::Cyp2d6Deletion: seed = 0; break;
+                case Cyp2d6RegionType::Rep6: seed = 1; break;
+                case Cyp2d6RegionType::Rep7: seed = 2; break;
+                case Cyp2d6RegionType::Spacer: seed = 3; break;
+                case Cyp2d6RegionType::LinkRegion: seed = 4; break;
+                default: break;
+            }
+            in.seeds.push_back(seed);
+        }
+    }
+    return in;
+}
+
+PriorityConsensus cyp2d6_priority_consensus(GpuAligner &gpu, const Cyp2d6ConsensusInputs &in, const CdwfaConfig &config) {
+    PriorityConsensusDWFA dwfa(gpu, config);
+    auto opt = [](size_t v) { return v == 0 ? std::nullopt : std::optional<size_t>(v); };  // offset 0 = auto-start (:243-254)
+    for (size_t i = 0; i < in.raw_sequences.size(); ++i)
+        dwfa.add_seeded_sequence_chain({in.hpc_sequences[i], in.raw_sequences[i]}, {opt(in.hpc_offsets[i]), opt(in.base_offsets[i])}, in.seeds[i]);
+    return dwfa.consensus();
+}
+
+MultiConsensus merge_consensus_results(GpuAligner &gpu, const SeqList &sequences, const std::vector<size_t> &offsets,
+                                       const CdwfaConfig &cdwfa_config, const PriorityConsensus &raw, Cyp2d6Extractor &d6_typer,
+                                       const Cyp2d6TypingDb &db, const Cyp2d6Config &cyp2d6_config, double max_missing_consensus_frac) {
+    if (sequences.size() != offsets.size() || sequences.size() != raw.sequence_indices.size())
+        throw HostError("merge_consensus_results: one offset and one consensus index per sequence expected");
+    const std::string unknown = Cyp2d6RegionLabel{}.full_allele();
+    // every consensus is typed in one batch (:760-782); "no matches found" is the reference's error branch -> unknown
+    SeqList to_type;
+    for (const auto &levels : raw.consensuses) {
+        if (levels.size() < 2) throw HostError("merge_consensus_results: (HPC, full) consensus pairs expected");
+        const std::string &full = levels[1].sequence;
+        const size_t b = full.find_first_not_of('*'), e = full.find_last_not_of('*');
+        to_type.push_back(b == std::string::npos ? std::string() : full.substr(b, e - b + 1));  // trim_matches('*')
+    }
+    const bool force_assignment = false;
+    const std::vector<std::optional<Cyp2d6Region>> typed = d6_typer.find_full_type_in_sequences(to_type, max_missing_consensus_frac, force_assignment, db);
+    std::map<std::pair<std::string, std::string>, std::vector<size_t>> consensus_set;
+    std::map<std::string, std::vector<size_t>> unknown_set;
+    for (size_t i = 0; i < raw.consensuses.size(); ++i) {
+        const Cyp2d6RegionLabel label = typed[i] ? typed[i]->label : Cyp2d6RegionLabel{};
+        const std::string reduced = label.simplify_allele(true, cyp2d6_config.cyp_translate);  // keeps sub-alleles such as "*4.001"
+        if (!label.is_allowed_label()) unknown_set[raw.consensuses[i][0].sequence].push_back(i);
+        else consensus_set[{raw.consensuses[i][0].sequence, reduced}].push_back(i);
+    }
+    std::set<std::pair<std::string, std::string>> intentional_ignore;  // :797-835
+    for (auto &kv : unknown_set) {
+        std::vector<std::pair<std::string, std::string>> other_keys;
+        for (const auto &ck : consensus_set)
+            if (ck.first.first == kv.first) other_keys.push_back(ck.first);
+        if (other_keys.size() == 1) {
+            std::vector<size_t> &entry = consensus_set[other_keys[0]];
+            entry.insert(entry.end(), kv.second.begin(), kv.second.end());
+        } else {
+            const std::pair<std::string, std::string> key{kv.first, unknown};
+            if (other_keys.size() > 1) intentional_ignore.insert(key);
+            if (!consensus_set.emplace(key, kv.second).second) throw HostError("merge_consensus_results: duplicate unknown key");
+        }
+    }
+    MultiConsensus out;
+    out.sequence_indices.assign(raw.sequence_indices.size(), std::numeric_limits<size_t>::max());
+    for (const auto &kv : consensus_set) {
+        const std::vector<size_t> &con_indices = kv.second;
+        const size_t con_index = out.consensuses.size();
+        auto contains = [&](size_t v) { return std::find(con_indices.begin(), con_indices.end(), v) != con_indices.end(); };
+        Consensus consensus;
+        if (intentional_ignore.count(kv.first)) {  // a group with several possible parents: kept empty (:842-854)
+            size_t num_scored = 0;
+            for (size_t i = 0; i < raw.sequence_indices.size(); ++i)
+                if (contains(raw.sequence_indices[i])) { out.sequence_indices[i] = con_index; ++num_scored; }
+            consensus.scores.assign(num_scored, 0);
+        } else if (con_indices.size() == 1) {  // the full-length consensus as it is (:855-864)
+            for (size_t i = 0; i < raw.sequence_indices.size(); ++i)
+                if (raw.sequence_indices[i] == con_indices[0]) out.sequence_indices[i] = con_index;
+            consensus = raw.consensuses[con_indices[0]][1];
+        } else {  // a merge: one consensus of all their raw sequences (:865-886)
+            ConsensusDWFA combined(gpu, cdwfa_config);
+            for (size_t si = 0; si < sequences.size(); ++si)
+                if (contains(raw.sequence_indices[si])) {
+                    combined.add_sequence_offset(sequences[si], offsets[si] == 0 ? std::nullopt : std::optional<size_t>(offsets[si]));
+                    out.sequence_indices[si] = con_index;
+                }
+            const std::vector<Consensus> list = combined.consensus();
+            if (list.empty()) throw HostError("merge_consensus_results: no consensus for a merged group");
+            consensus = list[0];  // "Multiple consensuses found during collapse, picking first."
+        }
+        out.consensuses.push_back(std::move(consensus));
+    }
+    for (size_t v : out.sequence_indices)
+        if (v >= out.consensuses.size()) throw HostError("merge_consensus_results: a sequence lost its consensus");
+    return out;
+}
+
 }  // namespace starphase

@@ -448,6 +448,72 @@ PYBIND11_MODULE(_starphase_host, m) {
     }, py::arg("gpu"), py::arg("templates"), py::arg("sequences"), py::arg("max_missing_frac"), py::arg("force_assignment"), py::arg("backbone"),
        py::arg("backbone_start"), py::arg("variants"), py::arg("metadata"), py::arg("haplotype_lookup"), py::arg("mapped_hybrids"),
        py::arg("graph_band") = 128);
+    // ---- the consensus stage of the CYP2D6 caller (src/cyp2d6/caller.rs:145-310, :750-893) ----
+    m.def("hpc_with_guide", [](const std::string &seq, const std::string &guide, size_t off) {
+        const auto r = hpc_with_guide(seq, guide, off);
+        return py::make_tuple(py::bytes(r.first), r.second);
+    });
+    // roi: {read id: [(region type, subtype, start, end, (seq_len, nm, unmapped, clipped_start, clipped_end))]} as find_base_type_in_sequences returns them
+    m.def("cyp2d6_consensus_inputs", [](GpuAligner &g, const std::map<std::string, std::string> &read_sequences,
+                                        const std::map<std::string, std::vector<std::tuple<std::string, std::optional<std::string>, size_t, size_t,
+                                                                                             std::tuple<size_t, size_t, size_t, std::optional<size_t>, std::optional<size_t>>>>> &roi,
+                                        const std::vector<std::tuple<std::string, std::optional<std::string>, std::string>> &templates,
+                                        double max_missing_consensus_frac) {
+        std::vector<std::pair<Cyp2d6RegionLabel, std::string>> ts;
+        for (const auto &t : templates) ts.push_back({Cyp2d6RegionLabel{region_type_from_name(std::get<0>(t)), std::get<1>(t)}, std::get<2>(t)});
+        Cyp2d6Extractor ex(g, std::move(ts));
+        std::map<std::string, std::vector<AlleleMapping>> regions;
+        for (const auto &kv : roi)
+            for (const auto &r : kv.second) {
+                AlleleMapping a;
+                a.allele_label = Cyp2d6RegionLabel{region_type_from_name(std::get<0>(r)), std::get<1>(r)};
+                a.region_start = std::get<2>(r); a.region_end = std::get<3>(r);
+                const auto &st = std::get<4>(r);
+                a.mapping_stats = MappingStats(std::get<0>(st), std::get<1>(st), std::get<2>(st));
+                a.mapping_stats.clipped_start = std::get<3>(st); a.mapping_stats.clipped_end = std::get<4>(st);
+                regions[kv.first].push_back(a);
+            }
+        const Cyp2d6ConsensusInputs in = cyp2d6_consensus_inputs(read_sequences, regions, ex, max_missing_consensus_frac);
+        py::dict d;
+        py::list raw, hp;
+        for (const auto &x : in.raw_sequences) raw.append(py::bytes(x));
+        for (const auto &x : in.hpc_sequences) hp.append(py::bytes(x));
+        d["raw_sequences"] = raw; d["hpc_sequences"] = hp; d["base_offsets"] = in.base_offsets; d["hpc_offsets"] = in.hpc_offsets;
+        d["sequence_ids"] = in.sequence_ids; d["seeds"] = in.seeds;
+        return d;
+    });
+    // raw: (consensuses[group] = [(hpc sequence, scores), (full sequence, scores)], group of every sequence) as priority_consensus returns it
+    m.def("merge_consensus_results", [cfg_from](GpuAligner &g, const SeqList &sequences, const std::vector<size_t> &offsets, const py::dict &cfg,
+                                                const std::vector<std::vector<std::pair<std::string, std::vector<size_t>>>> &raw_consensuses,
+                                                const std::vector<size_t> &raw_indices,
+                                                const std::vector<std::tuple<std::string, std::optional<std::string>, std::string>> &templates,
+                                                const std::string &backbone, size_t backbone_start,
+                                                const std::vector<std::tuple<size_t, std::string, std::string>> &variants,
+                                                const std::vector<std::pair<std::string, bool>> &metadata,
+                                                const std::map<std::string, std::vector<uint8_t>> &lookup,
+                                                const std::vector<std::pair<std::string, std::optional<std::string>>> &mapped_hybrids,
+                                                double max_missing_consensus_frac) {
+        std::vector<std::pair<Cyp2d6RegionLabel, std::string>> ts;
+        for (const auto &t : templates) ts.push_back({Cyp2d6RegionLabel{region_type_from_name(std::get<0>(t)), std::get<1>(t)}, std::get<2>(t)});
+        Cyp2d6Extractor ex(g, std::move(ts));
+        Cyp2d6TypingDb db;
+        db.backbone = backbone; db.backbone_start = backbone_start; db.haplotype_lookup = lookup;
+        for (const auto &v : variants) db.variants.push_back({std::get<0>(v), std::get<1>(v), std::get<2>(v)});
+        for (const auto &v : metadata) db.metadata.push_back({v.first, v.second});
+        for (const auto &h : mapped_hybrids) db.mapped_hybrids.push_back(Cyp2d6RegionLabel{region_type_from_name(h.first), h.second});
+        PriorityConsensus raw;
+        raw.sequence_indices = raw_indices;
+        for (const auto &levels : raw_consensuses) {
+            std::vector<Consensus> one;
+            for (const auto &c : levels) one.push_back(Consensus{c.first, c.second});
+            raw.consensuses.push_back(std::move(one));
+        }
+        const MultiConsensus mc = merge_consensus_results(g, sequences, offsets, cfg_from(cfg), raw, ex, db, Cyp2d6Config::default_config(),
+                                                          max_missing_consensus_frac);
+        py::list cons;
+        for (const Consensus &c : mc.consensuses) cons.append(py::make_tuple(py::bytes(c.sequence), c.scores));
+        return py::make_tuple(cons, mc.sequence_indices);
+    });
     m.def("overlap_score", &overlap_score);
     m.def("region_variant_string", [](const std::string &label, bool is_vi, int state) {
         return RegionVariant{label, is_vi, static_cast<VariantAlleleRelationship>(state)}.to_string();

@@ -864,6 +864,37 @@ std::pair<std::string, std::optional<std::string>> consensus_per_group(GpuAligne
                                                                        const std::vector<bool> &is_consensus1, bool is_dual,
                                                                        const DiplotypeSettings &cli_settings);
 
+// ---- the consensus stage of the CYP2D6 caller (src/cyp2d6/caller.rs:145-310, :750-893) ----
+// hpc_with_guide (src/util/homopolymers.rs:53-64): (homopolymer-compressed sequence, position of guide_offset in the compressed guide)
+std::pair<std::string, size_t> hpc_with_guide(const std::string &sequence, const std::string &guide_sequence, size_t guide_offset);
+// the CdwfaConfig of :149-162 ('*' wildcard, early termination, queue 20, capacity 10, offset_window 2 x 50)
+CdwfaConfig cyp2d6_consensus_config(const DiplotypeSettings &cli_settings);
+// what the loop at :168-212 collects from the regions of interest, in BTreeMap order of the read ids
+struct Cyp2d6ConsensusInputs {
+    SeqList raw_sequences;            // the part of the read matching the region
+    SeqList hpc_sequences;            // its homopolymer-compressed form
+    std::vector<size_t> base_offsets, hpc_offsets;  // 0 = anchored at the start; else clipped template start (+ offset_window)
+    std::vector<std::string> sequence_ids;          // "{read_id}_{start}_{end}_{allele_label}"
+    std::vector<std::pair<std::string, AlleleMapping>> flattened_regions_of_interest;
+    std::vector<std::optional<uint64_t>> seeds;     // :224-231: *5, REP6, REP7, spacer and link regions never share a group
+};
+Cyp2d6ConsensusInputs cyp2d6_consensus_inputs(const std::map<std::string, std::string> &read_sequences,
+                                              const std::map<std::string, std::vector<AlleleMapping>> &regions_of_interest,
+                                              const Cyp2d6Extractor &d6_typer, double max_missing_consensus_frac, size_t offset_window = 50);
+// :163-262 + :283: the priority chain (HPC first, then the raw bases) over those inputs
+PriorityConsensus cyp2d6_priority_consensus(GpuAligner &gpu, const Cyp2d6ConsensusInputs &inputs, const CdwfaConfig &config);
+struct MultiConsensus {  // waffle_con::multi_consensus::MultiConsensus
+    std::vector<Consensus> consensuses;
+    std::vector<size_t> sequence_indices;
+};
+// merge_consensus_results (:750-893): consensuses with the same HPC form and the same (sub-allele) type become one -- typed with
+// find_full_type_in_sequences (K4 / K9 / K8 / K6), merged groups re-solved with ConsensusDWFA on the raw sequences (K7); groups
+// that cannot be typed join the single typed group with their HPC form, or stay an UNKNOWN pile (none), or are emptied (several)
+MultiConsensus merge_consensus_results(GpuAligner &gpu, const SeqList &sequences, const std::vector<size_t> &offsets,
+                                       const CdwfaConfig &cdwfa_config, const PriorityConsensus &raw_consensus_result,
+                                       Cyp2d6Extractor &d6_typer, const Cyp2d6TypingDb &db, const Cyp2d6Config &cyp2d6_config,
+                                       double max_missing_consensus_frac);
+
 // StarphaseJson, src/data_types/starphase_json.rs:13-21; metadata order of src/database/pgx_database.rs:359-371
 std::string starphase_json(const std::string &pbstarphase_version, const std::map<std::string, std::string> &database_metadata,
                            const std::map<std::string, Json> &gene_details);

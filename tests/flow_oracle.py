@@ -486,3 +486,91 @@ def find_base_type_in_sequences(orc, templates, seqs: Sequence[bytes], max_missi
         out.append([(labels[t].full_allele(), hs, he, (st.seq_len, st.nm, st.unmapped, st.clipped_start, st.clipped_end))
                     for hs, he, st, t in regions if not st.custom_score(True) > max_missing_frac])
     return out
+
+
+# ---- the consensus stage of the CYP2D6 caller (src/cyp2d6/caller.rs:145-310, :750-893) ------------------------------------
+def hpc_with_guide(sequence: bytes, guide_sequence: bytes, guide_offset: int):
+    """src/util/homopolymers.rs:53-64."""
+    return so.hpc(sequence), so.hpc_pos(guide_sequence, guide_offset)
+
+
+_SEEDS = {so.DELETION: 0, so.REP6: 1, so.REP7: 2, so.SPACER: 3, so.LINK: 4}  # src/cyp2d6/caller.rs:224-231
+
+
+def cyp2d6_consensus_inputs(read_sequences: Dict[str, bytes], roi: Dict[str, list], templates, max_missing_consensus_frac: float,
+                            offset_window: int = 50) -> dict:
+    """The loop at src/cyp2d6/caller.rs:168-212 (+ the seeds of :224-231).  roi: {read id: [(type, subtype, start, end, stats 5-tuple)]}."""
+    by_label = {(t[0], t[1]): t[2] for t in templates}
+    out = dict(raw_sequences=[], hpc_sequences=[], base_offsets=[], hpc_offsets=[], sequence_ids=[], seeds=[])
+    for read_id in sorted(roi):
+        for t, sub, start, end, st in roi[read_id]:
+            stats = so.MappingStats(*st)
+            if stats.custom_score(True) > max_missing_consensus_frac:
+                continue
+            prefix = st[3] or 0
+            seq = read_sequences[read_id][start:end]
+            hp, hp_off = hpc_with_guide(seq, by_label[(t, sub)], prefix)
+            out["raw_sequences"].append(seq)
+            out["base_offsets"].append(0 if prefix == 0 else prefix + offset_window)
+            out["hpc_sequences"].append(hp)
+            out["hpc_offsets"].append(0 if hp_off == 0 else hp_off + offset_window)
+            out["sequence_ids"].append(f"{read_id}_{start}_{end}_{so.RegionLabel(t, sub).full_allele()}")
+            out["seeds"].append(_SEEDS.get(t))
+    return out
+
+
+def merge_consensus_results(orc, sequences: Sequence[bytes], offsets: Sequence[int], cfg, raw_consensuses, raw_indices: Sequence[int],
+                            templates, db: dict, max_missing_consensus_frac: float):
+    """merge_consensus_results (src/cyp2d6/caller.rs:750-893) on oracle numbers: typing through find_full_type_in_sequences above,
+    merged groups through consensus_oracle.consensus.  raw_consensuses[group] = [(hpc sequence, scores), (full sequence, scores)].
+    Returns (consensuses [(sequence, scores)], sequence_indices)."""
+    import consensus_oracle as co
+
+    cyp = so.Cyp2d6Config.default()
+    to_type = [levels[1][0].strip(b"*") for levels in raw_consensuses]
+    typed = find_full_type_in_sequences(orc, templates, to_type, max_missing_consensus_frac, False, db)
+    consensus_set: Dict[Tuple[bytes, str], List[int]] = {}
+    unknown_set: Dict[bytes, List[int]] = {}
+    unknown = so.RegionLabel(so.UNKNOWN).full_allele()
+    for i, levels in enumerate(raw_consensuses):
+        label = so.RegionLabel(*typed[i][0]) if typed[i] is not None else so.RegionLabel(so.UNKNOWN)
+        if not label.is_allowed_label():
+            unknown_set.setdefault(levels[0][0], []).append(i)
+        else:
+            consensus_set.setdefault((levels[0][0], label.simplify_allele(True, cyp.cyp_translate)), []).append(i)
+    ignore = set()
+    for hp in sorted(unknown_set):
+        others = [k for k in sorted(consensus_set) if k[0] == hp]
+        if len(others) == 1:
+            consensus_set[others[0]].extend(unknown_set[hp])
+        else:
+            if len(others) > 1:
+                ignore.add((hp, unknown))
+            assert (hp, unknown) not in consensus_set
+            consensus_set[(hp, unknown)] = unknown_set[hp]
+    cons, idx = [], [None] * len(raw_indices)
+    for key in sorted(consensus_set, key=lambda k: (k[0], k[1].encode())):
+        members, ci = consensus_set[key], len(cons)
+        if key in ignore:
+            n = 0
+            for i, si in enumerate(raw_indices):
+                if si in members:
+                    idx[i] = ci
+                    n += 1
+            cons.append((b"", [0] * n))
+        elif len(members) == 1:
+            for i, si in enumerate(raw_indices):
+                if si == members[0]:
+                    idx[i] = ci
+            cons.append((raw_consensuses[members[0]][1][0], list(raw_consensuses[members[0]][1][1])))
+        else:
+            reads, offs = [], []
+            for si, (seq, off) in enumerate(zip(sequences, offsets)):
+                if raw_indices[si] in members:
+                    reads.append(seq)
+                    offs.append(None if off == 0 else off)
+                    idx[si] = ci
+            first = co.consensus(reads, offs, cfg)[0]
+            cons.append((first[0], list(first[1])))
+    assert all(v is not None for v in idx)
+    return cons, idx

@@ -164,3 +164,90 @@ def test_find_full_type_in_sequences_vs_oracle(oracle):
         assert (json.loads(g[2]) if g[2] is not None else None) == w[1]
     assert [w[0] for w in want[:len(truth)]] == truth
     assert want[len(truth)][0] == ("CYP2D7", None) and want[len(truth) + 1] is None
+
+
+def test_cyp2d6_consensus_stage_vs_oracle(oracle):
+    """The consensus stage of the CYP2D6 caller (src/cyp2d6/caller.rs:145-310, :750-893) through the C++ host against the same flow
+    on oracle numbers: the inputs the caller collects from the regions of interest (hpc_with_guide, offsets, seeds), the priority
+    chain over them, and merge_consensus_results with every branch -- two consensuses with one HPC form and one type are re-solved
+    as one (K7), a different type with the same HPC form stays apart, an untypable consensus joins its only typed HPC relative,
+    is emptied when it has two, and stays an UNKNOWN pile when it has none."""
+    import consensus_oracle as co
+    import flow_oracle as fo
+    from pb_starphase_b200 import _starphase_host as host
+    from pb_starphase_b200 import synth
+    from test_host_cpp_gpu import cyp_templates
+
+    c = cyp_templates(seed=5, scale=240)
+    templates = [(t, s, (seq if seq is not None else c["spacer" if t == "spacer" else "link"])) for t, s, seq in c["templates"]]
+    cpp_templates = [(t, s, q.decode()) for t, s, q in templates]
+    d6, d7 = c["d6"], c["d7"]
+    rng = np.random.default_rng(31)
+    gpu = host.GpuAligner(0)
+
+    # -- hpc_with_guide: the reference's vector (src/util/homopolymers.rs:93-101) --
+    assert host.hpc_with_guide("GAACCCGTTTT", "ATTGGGGGAACCCGTTTT", 6) == (b"GACGT", 2) == fo.hpc_with_guide(b"GAACCCGTTTT", b"ATTGGGGGAACCCGTTTT", 6)
+
+    # -- the inputs of the priority chain: a full D6, a D6 whose first 90 template bases are clipped, a REP6, a mostly missing D7 --
+    reads = {"m1/a": rnd(rng, 40) + c["rep6"] + d6 + rnd(rng, 30), "m1/b": d6[90:] + c["link"] + d7[:200]}
+    n6, nr = len(d6), len(c["rep6"])
+    roi = {"m1/a": [("REP6", None, 40, 40 + nr, (nr, 1, 0, 0, 0)), ("CYP2D6", None, 40 + nr, 40 + nr + n6, (n6, 2, 0, 0, 0))],
+           "m1/b": [("CYP2D6", None, 0, n6 - 90, (n6, 0, 90, 90, 0)), ("CYP2D7", None, n6 - 90 + len(c["link"]), len(reads["m1/b"]), (len(d7), 0, len(d7) - 200, 0, len(d7) - 200))]}
+    want_in = fo.cyp2d6_consensus_inputs(reads, roi, templates, 0.5)
+    got_in = host.cyp2d6_consensus_inputs(gpu, {k: v.decode() for k, v in reads.items()}, roi, cpp_templates, 0.5)
+    assert {k: list(got_in[k]) for k in want_in} == want_in
+    assert want_in["seeds"] == [1, None, None] and want_in["base_offsets"] == [0, 0, 140]  # the clipped D6 may start 90 +- 50 into the consensus
+    assert want_in["hpc_offsets"][2] == so.hpc_pos(d6, 90) + 50 and len(want_in["raw_sequences"]) == 3          # the D7 piece misses too much
+
+    # -- the priority chain over such inputs (HPC level first, then the raw bases): three D6 reads, one of them clipped, and a REP6 --
+    pr_reads = [d6, d6[90:], d6, c["rep6"]]
+    chains = [[so.hpc(r), r] for r in pr_reads]
+    offs = [[None, None], [so.hpc_pos(d6, 90) + 50, 140], [None, None], [None, None]]
+    cfg = dict(allow_early_termination=True, offset_window=100, min_count=1)
+    want_pc = co.priority_consensus(chains, offs, [None, None, None, 1], co.Config(**cfg))
+    got_pc = host.priority_consensus(gpu, [[x.decode() for x in ch] for ch in chains], offs, [None, None, None, 1], cfg)
+    assert list(got_pc[1]) == want_pc[1] == [0, 0, 0, 1]
+    assert [[(s, list(sc)) for s, sc in lv] for lv in got_pc[0]] == [[(s, list(sc)) for s, sc in lv] for lv in want_pc[0]]
+    assert want_pc[0][0][1][0] == d6 and want_pc[0][1][1][0] == c["rep6"]
+
+    # -- merge_consensus_results --
+    def dup(s, p):  # one more copy of base p: the homopolymer-compressed form stays the same
+        return s[:p] + s[p:p + 1] + s[p:]
+
+    def snv(s, p):
+        return s[:p] + bytes([b"ACGT"[(b"ACGT".index(s[p]) + 1) % 4]]) + s[p + 1:]
+
+    start, fl = 42_100_000, 100
+    backbone = rnd(rng, fl) + d6 + rnd(rng, fl)
+    p1, p2, p3, p4 = 120, 300, 470, 610  # V1, V2: homopolymer-length variants; V3: a substitution; p4: a length change the database does not know
+    while d6[p3 - 1] == d6[p3] or d6[p3 + 1] == d6[p3] or snv(d6, p3)[p3] in (d6[p3 - 1], d6[p3 + 1]):
+        p3 += 1
+    variants = [(start + fl + p1, d6[p1:p1 + 1], d6[p1:p1 + 1] * 2), (start + fl + p2, d6[p2:p2 + 1], d6[p2:p2 + 1] * 2),
+                (start + fl + p3, d6[p3:p3 + 1], snv(d6, p3)[p3:p3 + 1])]
+    haps = {"1.001": [0, 0, 0], "2.001": [1, 0, 0], "3.001": [0, 1, 0], "4.001": [0, 1, 0], "5.001": [0, 0, 1]}  # *3.001 == *4.001: ambiguous
+    meta = [("rs1", False), ("rs2", False), ("rs3", True)]
+    mapped = [("CYP2D6", None)]
+    db = dict(backbone=backbone, backbone_start=start, variants=variants, metadata=meta, haplotype_lookup=haps, mapped_hybrids=mapped)
+    A, B = dup(d6, p1), d6
+    fulls = [A, dup(A, p4), B, dup(d6, p2), rnd(rng, 500), d7, dup(snv(d6, p3), p2), snv(d6, p3)]
+    assert len({so.hpc(x) for x in fulls[:4]}) == 1 and so.hpc(fulls[6]) == so.hpc(fulls[7]) != so.hpc(d6)
+    sequences, offsets, raw_idx = [], [], []
+    for gi, full in enumerate(fulls):
+        noisy, _ = synth.hifi_reads(rng, [full], 3, err=0.003, flank=0, lo=0, hi=1 << 20)
+        for k, r in enumerate(noisy):
+            clipped = gi in (0, 7) and k == 2  # one read of two groups starts 60 bases into its region
+            sequences.append(r[60:] if clipped else r)
+            offsets.append(60 + 50 if clipped else 0)
+            raw_idx.append(gi)
+    raw = [[(so.hpc(full), [0, 0, 0]), (full, [1, 0, 2])] for full in fulls]
+    raw[2][1] = (b"**" + B + b"*", [1, 0, 2])  # wildcards around a consensus are trimmed before typing
+    want, want_idx = fo.merge_consensus_results(oracle, sequences, offsets, co.Config(**cfg), raw, raw_idx, templates, db, 0.1)
+    got, got_idx = host.merge_consensus_results(gpu, [s.decode() for s in sequences], offsets, cfg, raw, raw_idx, cpp_templates, backbone.decode(), start,
+                                                [(p, r.decode(), a.decode()) for p, r, a in variants], meta, haps, mapped, 0.1)
+    assert list(got_idx) == want_idx
+    assert [(s, list(sc)) for s, sc in got] == [(s, list(sc)) for s, sc in want]
+    # what the branches must have done: groups 0 + 1 one consensus (= A, the majority), 2 alone, 3 emptied, 4 an unknown pile, 5 alone, 6 + 7 one
+    assert want_idx[0] == want_idx[3] and want_idx[6] != want_idx[0] and want_idx[9] not in (want_idx[0], want_idx[6])
+    assert want[want_idx[9]] == (b"", [0, 0, 0]) and want_idx[18] == want_idx[21] and len(want) == 6
+    assert want[want_idx[6]][0] == b"**" + B + b"*" and want[want_idx[15]][0] == d7 and want[want_idx[12]][0] == fulls[4]
+    assert want[want_idx[0]][0] in (A, dup(A, p4)) and want[want_idx[18]][0] in (fulls[6], fulls[7])

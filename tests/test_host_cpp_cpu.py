@@ -427,6 +427,7 @@ def test_hpc_reference_vectors(host):  # src/util/homopolymers.rs:71-104, src/hl
     assert host.hpc_pos("ATTGGGGGAACCCGTTTT", 6) == 2 and host.hpc("GAACCCGTTTT") == "GACGT"   # test_hpc_guide
     assert host.hpc("AACCGGTTAACCGGTTAACCGGTT"[4:10]) == "GTA"                                    # test_realigned_record
     assert host.hpc_pos(seq, 100) == 4 == so.hpc_pos(seq.encode(), 100) and host.hpc("") == ""
+    assert host.hpc_with_guide("GAACCCGTTTT", "ATTGGGGGAACCCGTTTT", 6) == (b"GACGT", 2)            # test_hpc_guide, :93-101
 
 
 def test_overlap_score_and_region_variant_display(host):  # src/cyp2d6/haplotyper.rs:935-941, src/data_types/region_variants.rs:80-110
