@@ -108,8 +108,12 @@ def build_workload(n_gpus: int, scale: float, n_reads: int | None = None):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    # SM clock, its maximum and the four throttle reasons the contract names, once a second.  (Polling every 200 ms with power.draw
+    # in the query cost the timed steps 40-190 ms each in idle gaps between launches -- NVML queries contend with the CUDA calls
+    # of the step for the driver; the e2e loop, which runs without the sampler, never showed them.)
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 1000
 
     def __init__(self, device: int):
         self.rows, self.proc, self.device, self.first = [], None, device, 0
@@ -123,7 +127,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.PERIOD_MS), "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -140,12 +144,12 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         rows = self.rows[self.first:] or self.rows
-        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         reasons = set()
         for r in rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
@@ -433,7 +437,7 @@ def run_ours(args):
     gv = w["gene_views"]
     result = None
     sampler = ClockSampler(local_rank)
-    sampler.start()  # polls every 200 ms from here on; the samples of the timed region are the ones reported
+    sampler.start()  # polls once a second from here on; the samples of the timed region are the ones reported
     for _ in range(args.warmup):
         result = device_step(T_dna, T_cdna, gv)
     k1_ms.clear()
@@ -574,7 +578,8 @@ def run_ours(args):
             dtype="u32", data="synthetic",
             config=bench_config(world, args.scale),
             best_pairs={g: (r[0][:4] if r else None) for g, r in result.items()},
-            clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"]),
+            clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"], samples=clocks["samples"],
+                        period_ms=ClockSampler.PERIOD_MS),
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                      note="per step: read set from pinned host memory on rank 0 (sp_comm_bcast_targets x2), K1 x2 + all-gather, K2 per gene + "
                           "merge, u16 distance matrices [reads x alleles] (each rank its row block) + top-k records back to pinned host memory"),

@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(K7_RUN_THREADS) k7_run(const ConsRunParams p) 
         for (int j = 0; j < my_items; ++j) {
             const int it = gwarp + j * total_warps, slot = warp * per_warp + j;
             const K7Item im = s_item[slot];
+            __syncwarp();  // every lane has its copy before lane 0 updates `filled` below (racecheck: read here / write there)
             const int side = im.side, s = side ? sym1 : sym0;
             int o_ed = ed[it], o_full = fu[it];
             uint32_t o_votes = vo[it];
