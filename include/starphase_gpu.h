@@ -315,7 +315,10 @@ sp_status sp_pair_minsum_topk(sp_ctx *ctx, const sp_dmatrix *d, const sp_dmatrix
 /* Full upper-triangular matrix S[i * n + j] (j >= i; other entries 0) to host memory.  Used by the
  * CYP2D6 chain-pair path where float penalties are added on the host (chaining.rs:459-497). */
 sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint64_t *S);
-/* Host-buffer convenience: D (and D2, may be NULL) are [R][A] row-major int32 (R reads, A alleles / chains). */
+/* Host-buffer convenience: D (and D2, may be NULL) are [R][A] row-major int32 (R reads, A alleles / chains).
+ * Values must lie in [0, 2^27) (SP_ERR_RANGE otherwise): the kernel adds 32 reads in 32 bits before it widens to 64.  The same
+ * holds for 32-bit device matrices handed to the calls above; matrices written by sp_score_device hold distances <= the
+ * longest pattern and always qualify. */
 sp_status sp_pair_minsum_topk_host(sp_ctx *ctx, const int32_t *D, const int32_t *D2, int64_t R, int64_t A, int k,
                                    sp_pair_rec *out, int *n_out);
 sp_status sp_pair_minsum_full_host(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, uint64_t *S);

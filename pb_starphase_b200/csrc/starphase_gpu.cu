@@ -1361,6 +1361,11 @@ extern "C" sp_status sp_pair_minsum_full(sp_ctx *ctx, const sp_dmatrix *d, uint6
 static sp_status upload_rows(sp_ctx *ctx, const int32_t *D, int64_t R, int64_t A, sp_dmatrix **out) {
     if (!D || R < 0 || A < 0) return fail(ctx, SP_ERR_INVALID, "K2 host: bad argument");
     if (R > 0x7FFFFFF0ll || A > 0x7FFFFFF0ll) return fail(ctx, SP_ERR_RANGE, "K2 host: matrix too large");
+    // K2 adds the minima of 32 reads in a 32-bit partial sum before widening: 32 x 2^27 = 2^32.  Distances (at most the pattern
+    // length) and chain-window scores are far below that; anything else is a caller error, reported instead of wrapped around
+    for (int64_t i = 0; i < R * A; ++i)
+        if (static_cast<uint32_t>(D[i]) >= (1u << 27))
+            return fail(ctx, SP_ERR_RANGE, "K2 host: matrix values must lie in [0, 2^27)");
     SP_CUDA(ctx, cudaSetDevice(ctx->device));
     sp_dmatrix *d = new (std::nothrow) sp_dmatrix();
     if (!d) return fail(ctx, SP_ERR_NOMEM, "out of host memory");

@@ -59,3 +59,20 @@ def test_dual_device_matrices(ctx, oracle):
     dd, dc = ctx.score_device(T, P, elem_bits=16), ctx.score_device(Tc, Pc, elem_bits=16)
     got = ctx.pair_minsum_topk(dc, 12, d2=dd)
     assert got == oracle.pair_minsum_topk(dc.to_host(), 12, D2=dd.to_host())
+
+
+def test_host_matrix_value_range_is_checked(ctx):
+    """K2 adds 32 reads in 32 bits before widening: host matrices with values outside [0, 2^27) are refused, not wrapped around."""
+    import pb_starphase_b200 as sp
+
+    D = np.full((40, 6), 7, dtype=np.int32)
+    assert ctx.pair_minsum_topk(D, 3)[0][0] == 40 * 7
+    for bad in (1 << 27, -1):
+        E = D.copy()
+        E[17, 3] = bad
+        with pytest.raises(sp.SpError):
+            ctx.pair_minsum_topk(E, 3)
+        with pytest.raises(sp.SpError):
+            ctx.pair_minsum_full(E)
+    D[:, :] = (1 << 27) - 1  # the largest admissible value, 40 reads: beyond 32 bits in the total, exact
+    assert ctx.pair_minsum_topk(D, 1)[0][0] == 40 * ((1 << 27) - 1)
