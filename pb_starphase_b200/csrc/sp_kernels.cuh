@@ -135,16 +135,21 @@ __device__ __forceinline__ void load_row(const uint32_t *row, int lane, uint32_t
 // The ALU pipe (LOP3 / IADD3 / SHF: 64 lanes/clk/SM) bounds this kernel while the FMA pipe idles
 // (profiles/r01_k1_ncu_full.txt: alu 98 %, fma 2 %), and a full-rate IMAD issues for free beside a
 // saturated ALU pipe (profiles/r01_pipe_bench.txt: 8 LOP3 = 16.1 cycles, 8 LOP3 + 8 IMAD = 16.3).
-// Four of Myers' boolean operations are therefore computed as integer add/sub on the FMA pipe, using
-// disjointness / subset facts of the delta vectors (Hyyro's D0 form; npv = ~Pv is the stored state):
-//     nG  = ~(D0 | Pv)            LOP3        G' = D0 | Phs                 LOP3
-//     Ph  = Mv | nG   = Mv + nG   (Mv is a subset of D0)
-//     Mh  = Pv & D0   = D0 + Pv - (D0 | Pv) = D0 - npv + nG
-//     Mv' = Phs & D0  = D0 + Phs - G'
-//     ~Pv' = ~(Mhs | ~G') = G' - Mhs          (Mhs is a subset of D0: a -1 step to the left forces a zero diagonal)
-// leaving per 32-row word 5 LOP3 + 1 IADD3.X + 2 SHF on the ALU pipe (was 7 + 1 + 2) and 6 IMAD on the
-// FMA pipe.  The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
-// The Myers add (Eq & Pv) + Pv becomes t - npv - 1 (borrow chain seeded with 1, SubChain1).
+// Three of Myers' boolean operations are therefore computed as integer add/sub on the FMA pipe, using
+// disjointness / subset facts of the delta vectors (Hyyro's D0 form; npv = ~Pv is the stored state), and the
+// horizontal-minus vector is not computed at all:
+//     t   = Eq & Pv,  sum = t + Pv + [hin < 0]      LOP3, IADD3.X (borrow chain t - npv - 1 + carry, SubChainY)
+//     C   = sum ^ t ^ Pv                             LOP3   the carry-IN vector of that addition.  Its carry-OUT vector is
+//                                                           t | (C & Pv & ~Eq) = Pv & D0 = Mh, so C IS Mh shifted up one row
+//                                                           (with hin < 0 in bit 0): Mhs costs neither arithmetic nor a shift
+//     D0  = C | Eq | Mv                              LOP3
+//     nG  = ~(D0 | Pv)                               LOP3        G' = D0 | Phs                 LOP3
+//     Ph  = Mv | nG   = Mv + nG   (Mv is a subset of D0)                                      IMAD
+//     Mv' = Phs & D0  = D0 + Phs - G'                                                         2 IMAD
+//     ~Pv' = ~(Mhs | ~G') = G' - C            (C is a subset of D0)                           IMAD
+// leaving per 32-row word 5 LOP3 + 1 IADD3.X + 1 SHF (Phs) on the ALU pipe (the textbook form: 7 + 1 + 2) and 4 IMAD on
+// the FMA pipe; Mh itself is formed for the lane's last word only (2 IMAD), whose top bit is the delta that leaves the lane.
+// The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
 template <int U, bool TRACK_END, bool KEEP_D0 = false>
 __device__ __forceinline__ void column_step(const uint32_t *peq, int lane, uint32_t code, uint32_t one, uint32_t m1,
                                             uint32_t seed_a, uint32_t seed_b,
@@ -153,40 +158,39 @@ __device__ __forceinline__ void column_step(const uint32_t *peq, int lane, uint3
                                             int &best_col, uint32_t *d0_keep = nullptr) {
     uint32_t eq[U], t[U], sum[U];
     load_row<U>(peq + code * (32 * U), lane, eq);
-    // hin < 0 (Hyyro): the row above already paid for this column, i.e. Eq bit 0 is forced.  The bit is folded into the two
-    // 3-input LOP3s of word 0 that consume Eq instead of being OR-ed into eq[0] first (one ALU-pipe instruction per column)
-    const uint32_t ybit = Y >> 31;
-    t[0] = (eq[0] | ybit) & ~npv[0];
+    // hin < 0 (Hyyro: the row above already paid for this column) enters as the carry-in of the Myers add (SubChainY takes it from
+    // the top bit of Y) instead of being OR-ed into Eq bit 0: bit 0 of the carry-in vector is then that bit, the diagonal-zero
+    // vector gets it through c[0], and words 1 .. U-1 receive the carry of the word below -- exactly the bit a shift of Mh would
+    // have moved there
 #pragma unroll
-    for (int u = 1; u < U; ++u) t[u] = eq[u] & ~npv[u];
-    SubChain1<U>::run(sum, t, npv, seed_a, seed_b);
-    uint32_t ph[U], mh[U], d0[U];
+    for (int u = 0; u < U; ++u) t[u] = eq[u] & ~npv[u];
+    SubChainY<U>::run(sum, t, npv, Y);
+    uint32_t ph[U], c[U], d0[U];
+    uint32_t mh_last = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const uint32_t xh = ~(sum[u] ^ npv[u]) | eq[u];
-        d0[u] = u == 0 ? (xh | mv[u] | ybit) : (xh | mv[u]);
-        const uint32_t a1 = npv[u] * m1 + d0[u];   // D0 - npv          (IMAD)
-        const uint32_t ng = ~d0[u] & npv[u];       // ~(D0 | Pv)        (LOP3)
-        mh[u] = ng * one + a1;                     //                   (IMAD)
-        ph[u] = ng * one + mv[u];                  //                   (IMAD)
+        c[u] = ~(sum[u] ^ t[u] ^ npv[u]);          // carry-in vector = Mh shifted up one row  (LOP3)
+        d0[u] = c[u] | eq[u] | mv[u];              //                                          (LOP3)
+        const uint32_t ng = ~d0[u] & npv[u];       // ~(D0 | Pv)                               (LOP3)
+        ph[u] = ng * one + mv[u];                  //                                          (IMAD)
+        if (u == U - 1) mh_last = ng * one + (npv[u] * m1 + d0[u]);  // Mh of the lane's last word only: its top bit leaves the lane (2 IMAD)
         if (KEEP_D0) d0_keep[u] = d0[u];           // K4 keeps the diagonal-zero vector for the traceback
     }
     // horizontal delta of the lane's last row: carry for the next lane, score for a last lane
     cph = __funnelshift_l(ph[U - 1], cph, 1);
-    cmh = __funnelshift_l(mh[U - 1], cmh, 1);
+    cmh = __funnelshift_l(mh_last, cmh, 1);
     if (TRACK_END) {  // per-column score and arg-min; without end columns the caller does it per chunk from cph/cmh
-        score += static_cast<int>(ph[U - 1] >> 31) - static_cast<int>(mh[U - 1] >> 31);
+        score += static_cast<int>(ph[U - 1] >> 31) - static_cast<int>(mh_last >> 31);
         ++col;
         if (score < best) { best = score; best_col = col; }
     }
 #pragma unroll
     for (int u = U - 1; u >= 0; --u) {
         const uint32_t phs = __funnelshift_l(u ? ph[u - 1] : X, ph[u], 1);
-        const uint32_t mhs = __funnelshift_l(u ? mh[u - 1] : Y, mh[u], 1);
         const uint32_t b1 = phs * one + d0[u];     // D0 + Phs          (IMAD)
         const uint32_t g = d0[u] | phs;            //                   (LOP3)
         mv[u] = g * m1 + b1;                       // Phs & D0          (IMAD)
-        npv[u] = mhs * m1 + g;                     // ~Pv'              (IMAD)
+        npv[u] = c[u] * m1 + g;                    // ~Pv' = G - Mhs    (IMAD)
     }
     X <<= 1;
     Y <<= 1;
