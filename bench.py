@@ -600,8 +600,9 @@ def run_ours(args):
                                       "MEASURED_PEAKS.json holds no integer peak",
                           peak_alu_pipe_only=int_peak / 1e12, frac_alu_pipe_only=achieved / int_peak,
                           peak_theoretical=148 * 128 * 1.965e9 / 1e12,
-                          note="K1 issues 8 of its ~14 instructions per 32 cells on the ALU pipe (the binding one) and 6 "
-                               "as IMAD on the FMA pipe, so the algorithmic count can exceed the ALU-pipe-only peak (DESIGN.md 4.1)",
+                          note="K1 issues 7 of its ~11 instructions per 32 cells on the ALU pipe (the binding one) and 4 "
+                               "as IMAD on the FMA pipe (the algorithmic count of SURVEY 8d is 11.5), so the algorithmic count "
+                               "exceeds the ALU-pipe-only peak (DESIGN.md 4.1)",
                           k1_ms=k1_avg_ms, k1_tcups=cells_dna_local / (k1_avg_ms * 1e-3) / 1e12,
                           traffic=(traffic.get("bytes_per_step") if world == 1 and args.scale == 1.0 else None),
                           traffic_source=traffic.get("source") if traffic else None,

@@ -282,7 +282,7 @@ extern "C" sp_status sp_align_resident(sp_ctx *ctx, const sp_targets *texts, con
         prm.blobs = d_blobs; prm.tbases = texts->d_bases; prm.lane_pair = d_lane_pair; prm.lane_first = d_lane_first; prm.pairs = d_pairs;
         prm.cigar = d_cigar; prm.dense = d_dense; prm.dense_used = d_used; prm.dense_cap = static_cast<unsigned long long>(cigar_cap);
         prm.scratch = d_scratch; prm.slot_words = c.slot_words; prm.recs = d_recs; prm.n_bins = c.n_bins; prm.two_pass = c.two_pass ? 1 : 0;
-        prm.next_bin = ctx->d_counter; prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
+        prm.next_bin = ctx->d_counter; prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
         switch (c.U) {
             case 4: SP_TRY(launch_class<4>(ctx, prm, grid)); break;
             case 8: SP_TRY(launch_class<8>(ctx, prm, grid)); break;

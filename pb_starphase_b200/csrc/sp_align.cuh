@@ -63,7 +63,7 @@ struct AlignParams {
     int n_bins;
     int two_pass;                // every pair of this launch has n > 2m
     int *next_bin;               // work counter
-    uint32_t one, m1, seed_a, seed_b;
+    uint32_t one, m1;
 };
 
 // 32-byte store (STG.256): one full L2 sector per lane and word group, so no sector is ever written in halves
@@ -123,7 +123,7 @@ __device__ __forceinline__ void k4_forward(const uint32_t *blob, const uint8_t *
 #pragma unroll
             for (int c = 0; c < K1_CHUNK; ++c) {
                 const int j = j0 + c;
-                column_step<U, true, STORE>(blob, lane, lut[cur[c]], p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, cph, cmh, score, best, col,
+                column_step<U, true, STORE>(blob, lane, lut[cur[c]], p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col,
                                             best_col, d0);
                 if (STORE && j < ncols && row_hi >= j + 1 + band_lo && row_lo <= j + 1 + band_hi) {
                     uint32_t *dst = scr + static_cast<size_t>(j) * 2 * Wp + 2 * (rel * U - wf4);

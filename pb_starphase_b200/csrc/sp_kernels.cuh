@@ -56,9 +56,6 @@ struct K1Params {
     uint32_t one, m1, sixteen;      // +1, -1 (0xFFFFFFFF), 16: passed at run time so `x * one + y` stays an IMAD (FMA pipe)
     int *next_item;                 // work counter (zeroed by the host before the launch): items are handed out dynamically;
                                     // nullptr: one CTA per item (grid = items)
-    uint32_t seed_a, seed_b;        // 1, 0xFFFFFFFF again: `seed_a - seed_b` sets the borrow that seeds the Myers add chain.  Separate
-                                    // parameters on purpose: inline-asm operands live in R registers, and sharing them with one / m1
-                                    // turned every IMAD multiplier from a uniform register into a third R operand (K1 -10 %)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -152,7 +149,6 @@ __device__ __forceinline__ void load_row(const uint32_t *row, int lane, uint32_t
 // The multipliers +1 / -1 are kernel parameters so ptxas cannot turn the IMADs back into IADD3.
 template <int U, bool TRACK_END, bool KEEP_D0 = false>
 __device__ __forceinline__ void column_step(const uint32_t *peq, int lane, uint32_t code, uint32_t one, uint32_t m1,
-                                            uint32_t seed_a, uint32_t seed_b,
                                             uint32_t (&npv)[U], uint32_t (&mv)[U], uint32_t &X, uint32_t &Y,
                                             uint32_t &cph, uint32_t &cmh, int &score, int &best, int &col,
                                             int &best_col, uint32_t *d0_keep = nullptr) {
@@ -258,7 +254,7 @@ __device__ __forceinline__ void k1_warp_run(const uint32_t *blob, const uint2 *s
             uint32_t cphA = 0, cmhA = 0, cphB = 0, cmhB = 0;  // columns 0-3 and 4-7
 #pragma unroll
             for (int c = 0; c < K1_CHUNK; ++c)
-                column_step<U, TRACK_END>(blob, lane, codes[c], p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, c < 4 ? cphA : cphB,
+                column_step<U, TRACK_END>(blob, lane, codes[c], p.one, p.m1, npv, mv, X, Y, c < 4 ? cphA : cphB,
                                           c < 4 ? cmhA : cmhB, score, best, col, best_col);
             const uint32_t iA = cmhA * p.sixteen + cphA, iB = cmhB * p.sixteen + cphB;  // IMAD: table indices
             carry_out = (cphA * p.sixteen + cphB) | ((iA & 0xF0u) << 8) | ((iB & 0xF0u) << 4);
@@ -358,7 +354,7 @@ struct SpanParams {
     int32_t *S;              // out: start columns  [p * ld + t]
     long long ld;
     int nt, np;
-    uint32_t one, m1, seed_a, seed_b;
+    uint32_t one, m1;
     int max_dist_permille;   // pairs with D * 1000 > |P| * this get S = -1 and no reverse pass; < 0: every pair
     const int32_t *plen;     // [np] pattern lengths
     unsigned long long *next_pair;  // work counter (zeroed by the host): pairs are handed out one at a time
@@ -422,7 +418,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k3_span_starts(const SpanParams
                 for (int c = 0; c < K1_CHUNK; ++c) {
                     const int j = idx * K1_CHUNK + c;
                     const uint32_t code = j < wlen ? base_code(T[e - 1 - j]) : 4u;
-                    column_step<U, true>(blob, lane, code, p.one, p.m1, p.seed_a, p.seed_b, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
+                    column_step<U, true>(blob, lane, code, p.one, p.m1, npv, mv, X, Y, cph, cmh, score, best, col, best_col);
                 }
                 carry_out = cph | (cmh << 8);
             }

@@ -769,7 +769,7 @@ static sp_status run_k1(sp_ctx *ctx, sp_targets *t, const sp_patterns *p, void *
         prm.ld = ld;
         prm.n_groups = pc.n_groups; prm.n_tiles = pk->n_tiles; prm.out16 = elem_bits == 16;
         prm.prefix_mode = p->mode == SP_PREFIX;
-        prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu; prm.sixteen = 16u;
+        prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.sixteen = 16u;
         prm.next_item = ctx->d_counter;
         const int64_t n_items64 = static_cast<int64_t>(prm.n_groups) * prm.n_tiles;
         if (n_items64 > 0x7FFFFFFFll) return fail(ctx, SP_ERR_RANGE, "work list too large");
@@ -1020,7 +1020,7 @@ extern "C" sp_status sp_score_spans_filtered(sp_ctx *ctx, const sp_seqset *targe
         SpanParams prm;
         prm.blobs = d_blobs; prm.tbases = t->d_bases; prm.toffs = t->d_offs;
         prm.D = static_cast<const int32_t *>(d->d); prm.E = d->d_end; prm.S = d_S; prm.ld = d->ld;
-        prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu; prm.seed_a = 1u; prm.seed_b = 0xFFFFFFFFu;
+        prm.nt = static_cast<int>(nt); prm.np = static_cast<int>(np); prm.one = 1u; prm.m1 = 0xFFFFFFFFu;
         prm.max_dist_permille = max_dist_permille; prm.plen = d_plen; prm.next_pair = d_next;
         const size_t smem = static_cast<size_t>(K1_WARPS) * blob_words(span_u) * 4;
         const long long total = nt * np;
