@@ -7,6 +7,7 @@ CPU: a missing library or a missing GPU raises SpError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional, Sequence, Tuple
 
@@ -38,7 +39,9 @@ class AlignRec(C.Structure):
 
 
 def lib_path() -> Path:
-    return Path(__file__).resolve().parent / "libstarphase_gpu.so"
+    # $SP_GPU_LIB: another build of the same library (A/B runs of a kernel variant on the GPU box)
+    over = os.environ.get("SP_GPU_LIB")
+    return Path(over) if over else Path(__file__).resolve().parent / "libstarphase_gpu.so"
 
 
 _lib = None
