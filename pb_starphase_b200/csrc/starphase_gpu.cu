@@ -196,7 +196,9 @@ sp_status upload_seqset(sp_ctx *ctx, const sp_seqset *s, uint8_t **d_bases, long
 // lane widths compiled into the library
 static const int kUmin = 4, kUmax = 16;
 static const int kULong[2] = {20, 24};  // only for pattern sets holding a pattern of more than 16,384 rows
-// modelled ALU-pipe instructions per text column of one warp (8 per word + per-column bookkeeping)
+// modelled ALU-pipe instructions per text column of one warp.  The constants are round 1's count (8 per word + 17 of
+// per-column bookkeeping); the kernel is at 7 per word + ~4 now, and the classes chosen for the IMGT-shaped sets are the same for any
+// bookkeeping constant between 1 and 17 (lane granularity decides, not the model), so the constants were left alone
 static double warp_cost(int U) {
     static const double book = getenv("SP_PLAN_BOOK") ? atof(getenv("SP_PLAN_BOOK")) : 17.0;  // experiment hook
     return 8.0 * U + book;
