@@ -245,3 +245,24 @@ def test_result_json_layout():
     back = json.loads(text)
     assert list(back) == ["pbstarphase_version", "database_metadata", "gene_details"]
     assert back["gene_details"]["HLA-A"]["mapping_details"][0]["best_mapping_stats"]["dna_stats"]["nm"] == 2
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_rows():
+    """bench.py's `clocks` key: median SM clock, its maximum and the active throttle reasons of the samples taken after mark()."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("bench_for_test", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.rows = [["1200", "1965", "Not Active", "Not Active", "Not Active", "Active"],      # warm-up: before mark()
+              ["1965", "1965", "Not Active", "Not Active", "Not Active", "Not Active"]]
+    s.mark()
+    s.rows += [["1965", "1965", "Not Active", "Not Active", "Not Active", "Not Active"],
+               ["1950", "1965", "Not Active", "Not Active", "Not Active", "Active"],
+               ["1965", "1965", "Not Active", "Not Active", "Not Active", "Not Active"],
+               ["[N/A]", "1965", "x"]]                                                        # a malformed row is skipped
+    got = s.stop()
+    assert got == dict(sm_mhz=1965.0, sm_max_mhz=1965.0, reasons=["sw_power_cap"], samples=3)
+    assert bench.ClockSampler.Q.count(",") == 5 and "power.draw" not in bench.ClockSampler.Q
