@@ -32,7 +32,7 @@ static std::optional<Mapping> mapping_from_alignment(const Alignment &a, size_t 
     return m;
 }
 
-static bool is_allowed_allele_def(const HlaAlleleDefinition &def, const std::string &gene_name, const DiplotypeSettings &s) {
+bool is_allowed_allele_def(const HlaAlleleDefinition &def, const std::string &gene_name, const DiplotypeSettings &s) {
     return def.gene_name == gene_name && (def.dna_sequence.has_value() || !s.hla_require_dna);  // src/hla/caller.rs:1090-1095
 }
 

@@ -169,6 +169,14 @@ PYBIND11_MODULE(_starphase_host, m) {
     m.def("cigar_string", &cigar_string);
     m.def("md_string", &md_string, py::arg("cigar"), py::arg("target"), py::arg("target_start"), py::arg("query"), py::arg("query_start"));
     m.def("reverse_complement", &reverse_complement);
+    m.def("is_allowed_allele_def", [](const std::string &def_gene, bool has_dna, const std::string &gene_name, bool hla_require_dna) {
+        HlaAlleleDefinition d;
+        d.hla_id = "HLA1"; d.gene_name = def_gene; d.cdna_sequence = "AG";
+        if (has_dna) d.dna_sequence = "ACGT";
+        DiplotypeSettings s;
+        s.hla_require_dna = hla_require_dna;
+        return is_allowed_allele_def(d, gene_name, s);
+    });
     m.def("splice_read", &splice_read, py::arg("sequence"), py::arg("pos"), py::arg("cigar"), py::arg("exons"));
     m.def("prepare_score_read_targets", [](const std::string &seq, int64_t pos, const std::vector<std::pair<uint32_t, uint8_t>> &cigar,
                                            const std::vector<std::pair<uint64_t, uint64_t>> &exons, bool fwd, const DiplotypeSettings &s) {

@@ -331,6 +331,10 @@ struct HlaAlleleDefinition {  // the members of src/hla/alleles.rs the path read
 };
 using HlaDatabase = std::map<std::string, HlaAlleleDefinition>;  // BTreeMap<hla_id, def>: iteration order is semantics
 
+struct DiplotypeSettings;
+// src/hla/caller.rs:1090-1095: the allele belongs to the gene and has a DNA sequence (unless hla_require_dna is off)
+bool is_allowed_allele_def(const HlaAlleleDefinition &def, const std::string &gene_name, const DiplotypeSettings &cli_settings);
+
 struct DiplotypeSettings {  // the members of src/cli/diplotype.rs the path reads
     bool disable_cdna_scoring = false;
     bool hla_require_dna = true;

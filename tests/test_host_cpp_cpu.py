@@ -479,3 +479,23 @@ def test_harmonic_mean_reference_vector(host):  # src/data_types/mapping.rs:230-
     assert host.harmonic_mean([]) == 0.0
     with pytest.raises(host.HostError, match="dna_score must be > 0.0"):
         host.harmonic_mean([0.1, 0.0])
+
+
+def test_is_allowed_allele_def(host):  # src/hla/caller.rs:1673-1701
+    assert host.is_allowed_allele_def("HLA-A", True, "HLA-A", True)        # base case
+    assert not host.is_allowed_allele_def("HLA-B", True, "HLA-A", True)    # wrong gene
+    assert not host.is_allowed_allele_def("HLA-A", False, "HLA-A", True)   # no DNA while DNA is required
+    assert host.is_allowed_allele_def("HLA-A", False, "HLA-A", False)      # requirement lifted
+
+
+def test_score_min(host):  # src/data_types/mapping.rs:220-228, src/hla/mapping.rs:221-229
+    def hla(cdna, dna):
+        h = host.HlaMappingStats()
+        h.cdna_stats, h.dna_stats = cdna, dna
+        return h.mapping_score()
+
+    st = lambda nm: host.MappingStats(10, nm, 0)  # noqa: E731
+    assert [st(n).mapping_score() for n in (10, 9, 2)] == [1.0, 0.9, 0.2]
+    s1, s2, s3 = hla(None, st(5)), hla(st(9), None), hla(None, st(2))   # (1.0, 0.5), (0.9, 1.0), (1.0, 0.2): a missing side scores 1.0
+    assert (s1, s2, s3) == ((1.0, 0.5), (0.9, 1.0), (1.0, 0.2))
+    assert min(s1, s2) == s2 and min(s1, s3) == s3 and min(s2, s3) == s2  # cDNA first, then DNA
